@@ -1,0 +1,980 @@
+"""CPU oracle (TEST INFRASTRUCTURE ONLY) -- a big-int restatement of hashcloak/bbs_sign (`bbs_plus`).
+
+This file is the *checker*, never the product: only `tests/`, `__graft_entry__.smoke()` and the
+`cpu_baseline` / `--impl reference` legs of `bench.py` may import it.  The shipped path is the CUDA
+library behind `include/bbs_b200.h`; it never calls into `oracle/`.
+
+Parity status: PINNED for BLS12-381 by every known-answer test the reference holds
+(`/root/reference/src/tests/test_vector.rs`; see `tests/test_oracle_kat.py`).  BN254 is "parity
+unpinned" at the arkworks encoding boundary: the reference has no BN254 KAT except the P1 constant
+(`src/constants.rs:40-49`), which this oracle reproduces through its SvdW hash-to-curve.
+
+The arithmetic the reference delegates to third-party crates that are NOT under /root/reference
+(ark-ff/ark-ec/ark-serialize 0.4.2, ark-bls12-381/ark-bn254 0.4.0, zkcrypto bls12_381 0.8.0 @9ea427c,
+bn254_hash2curve 0.1.2, sha2 0.10.6) is restated from the published algorithms (RFC 9380, IRTF
+draft-irtf-cfrg-bbs-signatures, zcash/ark encodings) and anchored on the reference's call sites.
+
+Every function cites the reference file:line it follows.
+"""
+from __future__ import annotations
+
+import hashlib
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+# --------------------------------------------------------------------------------------------
+# hashing: src/utils/utilities_helper.rs:42-97 (expand_message), :15-40 (from_okm)
+# --------------------------------------------------------------------------------------------
+
+
+def expand_message(msg: bytes, dst: bytes, len_in_bytes: int) -> bytes:
+    """RFC 9380 expand_message_xmd with SHA-256.  Follows utilities_helper.rs:42-97."""
+    ell = (len_in_bytes + 31) // 32
+    if ell > 255:
+        raise ValueError("ell was too big in expand_message_xmd")  # utilities_helper.rs:46-48 (panic)
+    if len(dst) > 255:
+        raise ValueError("dst size is invalid")  # utilities_helper.rs:50-52 (panic)
+    dst_prime = dst + bytes([len(dst)])
+    b0 = hashlib.sha256(b"\0" * 64 + msg + bytes([(len_in_bytes >> 8) & 0xFF, len_in_bytes & 0xFF, 0]) + dst_prime).digest()
+    b = hashlib.sha256(b0 + b"\x01" + dst_prime).digest()
+    out = b
+    for i in range(2, ell + 1):
+        b = hashlib.sha256(bytes(x ^ y for x, y in zip(b0, b)) + bytes([i]) + dst_prime).digest()
+        out += b
+    return out[:len_in_bytes]
+
+
+# --------------------------------------------------------------------------------------------
+# tiny field helpers
+# --------------------------------------------------------------------------------------------
+
+
+def _inv(a: int, p: int) -> int:
+    return pow(a, -1, p)
+
+
+class Fp2Ops:
+    """Fp2 = Fp[u]/(u^2+1), elements are (c0, c1)."""
+
+    def __init__(self, p: int):
+        self.p = p
+        self.zero = (0, 0)
+        self.one = (1, 0)
+
+    def add(self, a, b):
+        return ((a[0] + b[0]) % self.p, (a[1] + b[1]) % self.p)
+
+    def sub(self, a, b):
+        return ((a[0] - b[0]) % self.p, (a[1] - b[1]) % self.p)
+
+    def neg(self, a):
+        return ((-a[0]) % self.p, (-a[1]) % self.p)
+
+    def mul(self, a, b):
+        p = self.p
+        return ((a[0] * b[0] - a[1] * b[1]) % p, (a[0] * b[1] + a[1] * b[0]) % p)
+
+    def inv(self, a):
+        p = self.p
+        d = _inv((a[0] * a[0] + a[1] * a[1]) % p, p)
+        return (a[0] * d % p, (-a[1] * d) % p)
+
+    def pow(self, a, e):
+        r = self.one
+        while e:
+            if e & 1:
+                r = self.mul(r, a)
+            a = self.mul(a, a)
+            e >>= 1
+        return r
+
+    def sqrt(self, a):
+        """Square root in Fp2 for p = 3 mod 4 (both curves); returns None if a is not a square."""
+        p = self.p
+        if a == self.zero:
+            return self.zero
+        a1 = self.pow(a, (p - 3) // 4)
+        alpha = self.mul(self.mul(a1, a1), a)
+        x0 = self.mul(a1, a)
+        if alpha == (p - 1, 0):
+            cand = self.mul((0, 1), x0)
+        else:
+            b = self.pow(self.add(self.one, alpha), (p - 1) // 2)
+            cand = self.mul(b, x0)
+        return cand if self.mul(cand, cand) == (a[0] % p, a[1] % p) else None
+
+    def gt(self, a, b):
+        """arkworks QuadExt ordering: c1 compared first, then c0."""
+        return (a[1], a[0]) > (b[1], b[0])
+
+
+class FpOps:
+    def __init__(self, p: int):
+        self.p = p
+        self.zero = 0
+        self.one = 1
+
+    def add(self, a, b):
+        return (a + b) % self.p
+
+    def sub(self, a, b):
+        return (a - b) % self.p
+
+    def neg(self, a):
+        return (-a) % self.p
+
+    def mul(self, a, b):
+        return a * b % self.p
+
+    def inv(self, a):
+        return _inv(a, self.p)
+
+
+def ec_add(F, P, Q):
+    """Affine short-Weierstrass (a=0) addition; None is the identity."""
+    if P is None:
+        return Q
+    if Q is None:
+        return P
+    if P[0] == Q[0]:
+        if P[1] != Q[1] or P[1] == F.zero:
+            return None
+        x2 = F.mul(P[0], P[0])
+        lam = F.mul(F.add(F.add(x2, x2), x2), F.inv(F.add(P[1], P[1])))
+    else:
+        lam = F.mul(F.sub(Q[1], P[1]), F.inv(F.sub(Q[0], P[0])))
+    x3 = F.sub(F.sub(F.mul(lam, lam), P[0]), Q[0])
+    return (x3, F.sub(F.mul(lam, F.sub(P[0], x3)), P[1]))
+
+
+def ec_neg(F, P):
+    return None if P is None else (P[0], F.neg(P[1]))
+
+
+def ec_mul(F, P, k: int):
+    """ark-ec `Projective * Fr` semantics (group scalar multiplication); k is taken as given (>= 0)."""
+    R = None
+    while k:
+        if k & 1:
+            R = ec_add(F, R, P)
+        P = ec_add(F, P, P)
+        k >>= 1
+    return R
+
+
+# --------------------------------------------------------------------------------------------
+# ciphersuites: src/constants.rs:27-89
+# --------------------------------------------------------------------------------------------
+
+
+@dataclass
+class Suite:
+    name: str
+    p: int
+    r: int
+    b: int                      # G1: y^2 = x^3 + b
+    b2: Tuple[int, int]         # twist: y^2 = x^3 + b2
+    twist: str                  # "M" or "D"
+    xi_c: int                   # xi = xi_c + u
+    ate_loop: int               # trace - 1 (plain ate pairing; verdict-equivalent to the optimal ate)
+    BP1: Tuple[int, int]
+    BP2: Tuple[Tuple[int, int], Tuple[int, int]]
+    P1: Tuple[int, int]
+    ciphersuite_id: bytes
+    fp_bytes: int
+    F1: FpOps = field(init=False)
+    F2: Fp2Ops = field(init=False)
+
+    def __post_init__(self):
+        self.F1 = FpOps(self.p)
+        self.F2 = Fp2Ops(self.p)
+
+    @property
+    def api_id(self) -> bytes:
+        # verify.rs:31, sign.rs:44, proof_gen.rs:95, proof_verify.rs:35
+        return self.ciphersuite_id + b"H2G_HM2S_"
+
+    # ---- FromOkm: utilities_helper.rs:15-40 -------------------------------------------------
+    def from_okm(self, data: bytes) -> int:
+        assert len(data) == 48
+        return int.from_bytes(data, "big") % self.r
+
+    # ---- encodings ---------------------------------------------
+    def scalar_le(self, s: int) -> bytes:
+        """ark `Fr::serialize_compressed`: 32 bytes little-endian."""
+        return (s % self.r).to_bytes(32, "little")
+
+    def scalar_be(self, s: int) -> bytes:
+        """serialize_compressed + `.reverse()` as the reference does wherever a scalar is hashed."""
+        return (s % self.r).to_bytes(32, "big")
+
+    def g1_compress(self, P) -> bytes:
+        raise NotImplementedError
+
+    def g1_decompress(self, b: bytes):
+        raise NotImplementedError
+
+    def g2_compress(self, Q) -> bytes:
+        raise NotImplementedError
+
+    def g2_decompress(self, b: bytes):
+        raise NotImplementedError
+
+    def hash_to_g1(self, msg: bytes, dst: bytes):
+        raise NotImplementedError
+
+    def g1_on_curve(self, P) -> bool:
+        return P is None or (P[1] * P[1] - P[0] ** 3 - self.b) % self.p == 0
+
+    def g2_on_curve(self, Q) -> bool:
+        if Q is None:
+            return True
+        F = self.F2
+        return F.mul(Q[1], Q[1]) == F.add(F.mul(F.mul(Q[0], Q[0]), Q[0]), self.b2)
+
+
+class BlsSuite(Suite):
+    """BLS12-381: zcash/IETF point encoding (ark-bls12-381 0.4.0 overrides the SW serializer)."""
+
+    def g1_compress(self, P) -> bytes:
+        if P is None:
+            return bytes([0xC0]) + bytes(47)
+        b = bytearray(P[0].to_bytes(48, "big"))
+        b[0] |= 0x80
+        if P[1] > (self.p - 1) // 2:
+            b[0] |= 0x20
+        return bytes(b)
+
+    def g1_decompress(self, b: bytes):
+        assert len(b) == 48
+        if not b[0] & 0x80:
+            raise ValueError("uncompressed flag")
+        if b[0] & 0x40:
+            if any(b[1:]) or b[0] & 0x3F:
+                raise ValueError("bad infinity encoding")
+            return None
+        s = (b[0] >> 5) & 1
+        x = int.from_bytes(bytes([b[0] & 0x1F]) + b[1:], "big")
+        if x >= self.p:
+            raise ValueError("x not canonical")
+        rhs = (x ** 3 + self.b) % self.p
+        y = pow(rhs, (self.p + 1) // 4, self.p)
+        if y * y % self.p != rhs:
+            raise ValueError("not on curve")
+        if (y > (self.p - 1) // 2) != bool(s):
+            y = self.p - y
+        return (x, y)
+
+    def g2_compress(self, Q) -> bytes:
+        if Q is None:
+            return bytes([0xC0]) + bytes(95)
+        b = bytearray(Q[0][1].to_bytes(48, "big") + Q[0][0].to_bytes(48, "big"))
+        b[0] |= 0x80
+        if self.F2.gt(Q[1], self.F2.neg(Q[1])):
+            b[0] |= 0x20
+        return bytes(b)
+
+    def g2_decompress(self, b: bytes):
+        assert len(b) == 96
+        if not b[0] & 0x80:
+            raise ValueError("uncompressed flag")
+        if b[0] & 0x40:
+            return None
+        s = (b[0] >> 5) & 1
+        c1 = int.from_bytes(bytes([b[0] & 0x1F]) + b[1:48], "big")
+        c0 = int.from_bytes(b[48:], "big")
+        F = self.F2
+        X = (c0, c1)
+        rhs = F.add(F.mul(F.mul(X, X), X), self.b2)
+        y = F.sqrt(rhs)
+        if y is None:
+            raise ValueError("not on curve")
+        if F.gt(y, F.neg(y)) != bool(s):
+            y = F.neg(y)
+        return (X, y)
+
+    # ---- RFC 9380 BLS12381G1_XMD:SHA-256_SSWU_RO_ (zkcrypto bls12_381, interface_utilities.rs:30-44)
+    _ISO_A = 0x144698A3B8E9433D693A02C96D4982B0EA985383EE66A8D8E8981AEFD881AC98936F8DA0E0F97F5CF428082D584C1D
+    _ISO_B = 0x12E2908D11688030018B12E8753EEE3B2016C1F0F24F4070A0B9C14FCEF35EF55A23215A316CEAA5D1CC48E98E172BE0
+    _ISO_Z = 11
+    # x-coordinates of the rational order-11 kernel {+-K .. +-5K} of the 11-isogeny E' -> E
+    _KER_X = (
+        0x010EF325DD1E98BDF0D97A4C6B7F968ED7F31F2FBFF088ACB39D5319CFC261EA18773405F325612742F0C5D90634BCF4,
+        0x0D7F2D0D03AE035321EED4C1479D13251ABF0E9A96479623EB5380B575E319851FB5E5A8B43B9C1A46880F54BF2B2F7C,
+        0x105249B4CAC630CE5AA18E6C1189A18C82019B4E12E491FBAC012C259CA3A67F638560B8BB416AF02A4724385ED0FC8E,
+        0x140D41735B10CE710727CD9356905701A2B866B803BAA468948B7F423DDCC560C9A8F1CD5F8ED4297C37464FB8BFE4A7,
+        0x1665A9C648E78314490A94F654D9B1039AB85847223BFAED9AA54F0F07736D122D1CECA1AC0E9123E753FDE16E97C3D7,
+    )
+    _H_EFF = 0xD201000000010001
+    _velu_tab = None
+
+    def _velu_setup(self):
+        p, A, B = self.p, self._ISO_A, self._ISO_B
+        tab = []
+        for xq in self._KER_X:
+            rhs = (xq ** 3 + A * xq + B) % p
+            yq = pow(rhs, (p + 1) // 4, p)
+            assert yq * yq % p == rhs
+            gx = (3 * xq * xq + A) % p
+            gy = (-2 * yq) % p
+            tab.append((xq, yq, gx, gy, 2 * gx % p, gy * gy % p))
+        self._velu_tab = tab
+
+    def _sswu(self, u: int):
+        p, A, B, Z = self.p, self._ISO_A, self._ISO_B, self._ISO_Z
+        tv = (Z * Z * pow(u, 4, p) + Z * u * u) % p
+        tv1 = pow(tv, p - 2, p)  # inv0
+        if tv1 == 0:
+            x1 = B * _inv(Z * A % p, p) % p
+        else:
+            x1 = (-B * _inv(A, p)) % p * (1 + tv1) % p
+        g1 = (x1 ** 3 + A * x1 + B) % p
+        if g1 == 0 or pow(g1, (p - 1) // 2, p) == 1:
+            X, Y = x1, pow(g1, (p + 1) // 4, p)
+        else:
+            X = Z * u * u % p * x1 % p
+            g2 = (X ** 3 + A * X + B) % p
+            Y = pow(g2, (p + 1) // 4, p)
+            assert Y * Y % p == g2
+        if (u & 1) != (Y & 1):
+            Y = p - Y
+        return (X, Y)
+
+    def _iso11(self, Pt):
+        if self._velu_tab is None:
+            self._velu_setup()
+        p = self.p
+        X, Y = Pt
+        xo, yo = X, Y
+        for (xq, yq, gx, gy, vq, uq) in self._velu_tab:
+            d = _inv((X - xq) % p, p)
+            d2 = d * d % p
+            d3 = d2 * d % p
+            xo = (xo + vq * d + uq * d2) % p
+            yo = (yo - (uq * 2 * Y * d3 + vq * (Y - yq) * d2 - gx * gy * d2)) % p
+        i11 = _inv(11, p)
+        return (xo * i11 * i11 % p, yo * pow(i11, 3, p) % p)
+
+    def hash_to_g1(self, msg: bytes, dst: bytes):
+        p = self.p
+        ub = expand_message(msg, dst, 128)
+        u0 = int.from_bytes(ub[:64], "big") % p
+        u1 = int.from_bytes(ub[64:], "big") % p
+        R = ec_add(self.F1, self._iso11(self._sswu(u0)), self._iso11(self._sswu(u1)))
+        return ec_mul(self.F1, R, self._H_EFF)
+
+
+class BnSuite(Suite):
+    """BN254: arkworks 0.4.2 default SW encoding (little-endian x, flags in the last byte).  UNPINNED."""
+
+    def g1_compress(self, P) -> bytes:
+        if P is None:
+            b = bytearray(32)
+            b[31] |= 0x40
+            return bytes(b)
+        b = bytearray(P[0].to_bytes(32, "little"))
+        if P[1] > (self.p - P[1]) % self.p:  # SWFlags::from_y_coordinate: y <= -y -> positive
+            b[31] |= 0x80
+        return bytes(b)
+
+    def g1_decompress(self, b: bytes):
+        assert len(b) == 32
+        flags = b[31] & 0xC0
+        if flags == 0xC0:
+            raise ValueError("invalid flags")
+        if flags & 0x40:
+            return None
+        x = int.from_bytes(b[:31] + bytes([b[31] & 0x3F]), "little")
+        if x >= self.p:
+            raise ValueError("x not canonical")
+        rhs = (x ** 3 + self.b) % self.p
+        y = pow(rhs, (self.p + 1) // 4, self.p)
+        if y * y % self.p != rhs:
+            raise ValueError("not on curve")
+        neg = bool(flags & 0x80)
+        if (y > (self.p - y) % self.p) != neg:
+            y = (self.p - y) % self.p
+        return (x, y)
+
+    def g2_compress(self, Q) -> bytes:
+        if Q is None:
+            b = bytearray(64)
+            b[63] |= 0x40
+            return bytes(b)
+        b = bytearray(Q[0][0].to_bytes(32, "little") + Q[0][1].to_bytes(32, "little"))
+        if self.F2.gt(Q[1], self.F2.neg(Q[1])):
+            b[63] |= 0x80
+        return bytes(b)
+
+    def g2_decompress(self, b: bytes):
+        assert len(b) == 64
+        flags = b[63] & 0xC0
+        if flags == 0xC0:
+            raise ValueError("invalid flags")
+        if flags & 0x40:
+            return None
+        c0 = int.from_bytes(b[:32], "little")
+        c1 = int.from_bytes(b[32:63] + bytes([b[63] & 0x3F]), "little")
+        F = self.F2
+        X = (c0, c1)
+        rhs = F.add(F.mul(F.mul(X, X), X), self.b2)
+        y = F.sqrt(rhs)
+        if y is None:
+            raise ValueError("not on curve")
+        if F.gt(y, F.neg(y)) != bool(flags & 0x80):
+            y = F.neg(y)
+        return (X, y)
+
+    # ---- bn254_hash2curve 0.1.2: RFC 9380 6.6.1 SvdW, Z=1 (interface_utilities.rs:24-28)
+    def _svdw(self, u: int):
+        p = self.p
+        Z = 1
+        g = lambda x: (x ** 3 + 3) % p
+        is_sq = lambda a: a == 0 or pow(a, (p - 1) // 2, p) == 1
+        c1 = g(Z)
+        c2 = (-Z * _inv(2, p)) % p
+        c3 = pow((-g(Z) * 3 * Z * Z) % p, (p + 1) // 4, p)
+        if c3 & 1:
+            c3 = p - c3
+        c4 = (-4 * g(Z) * _inv(3 * Z * Z, p)) % p
+        tv1 = u * u % p * c1 % p
+        tv2 = (1 + tv1) % p
+        tv1 = (1 - tv1) % p
+        tv3 = pow(tv1 * tv2 % p, p - 2, p)
+        tv4 = u * tv1 % p * tv3 % p * c3 % p
+        x1 = (c2 - tv4) % p
+        e1 = is_sq(g(x1))
+        x2 = (c2 + tv4) % p
+        e2 = is_sq(g(x2)) and not e1
+        x3 = tv2 * tv2 % p * tv3 % p
+        x3 = (x3 * x3 % p * c4 + Z) % p
+        x = x1 if e1 else x3
+        if e2:
+            x = x2
+        y = pow(g(x), (p + 1) // 4, p)
+        assert y * y % p == g(x)
+        if (u & 1) != (y & 1):
+            y = p - y
+        return (x, y)
+
+    def hash_to_g1(self, msg: bytes, dst: bytes):
+        p = self.p
+        ub = expand_message(msg, dst, 96)
+        u0 = int.from_bytes(ub[:48], "big") % p
+        u1 = int.from_bytes(ub[48:], "big") % p
+        return ec_add(self.F1, self._svdw(u0), self._svdw(u1))
+
+
+def _make_bls() -> BlsSuite:
+    x = -0xD201000000010000
+    r = x ** 4 - x ** 2 + 1
+    p = (x - 1) ** 2 * r // 3 + x
+    assert r == 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001  # utilities_helper.rs:33
+    s = BlsSuite(
+        name="BLS12_381", p=p, r=r, b=4, b2=(4, 4), twist="M", xi_c=1, ate_loop=abs(x),
+        BP1=(0, 0), BP2=((0, 0), (0, 0)),
+        # constants.rs:75-78
+        P1=(1355253221325668152696183518801331769866100080859571110928822005264442742039790254588065001486134245057142899747017,
+            2563071790429735027383427649950865259619709115697058137448106859255609577834149037543606665262210555960464099235249),
+        ciphersuite_id=b"BBS_BLS12381G1_XMD:SHA-256_SSWU_RO_",  # constants.rs:82
+        fp_bytes=48,
+    )
+    # generators pinned by test_vector.rs:60,64 (BP1, BP2 compressed encodings)
+    s.BP1 = s.g1_decompress(bytes.fromhex(
+        "97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"))
+    s.BP2 = s.g2_decompress(bytes.fromhex(
+        "93e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e"
+        "024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8"))
+    return s
+
+
+def _make_bn() -> BnSuite:
+    t = 4965661367192848881
+    p = 36 * t ** 4 + 36 * t ** 3 + 24 * t ** 2 + 6 * t + 1
+    r = 36 * t ** 4 + 36 * t ** 3 + 18 * t ** 2 + 6 * t + 1
+    assert r == 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001  # utilities_helper.rs:18
+    F2 = Fp2Ops(p)
+    b2 = F2.mul((3, 0), F2.inv((9, 1)))
+    return BnSuite(
+        name="BN254", p=p, r=r, b=3, b2=b2, twist="D", xi_c=9, ate_loop=6 * t * t,
+        BP1=(1, 2),
+        # ark-bn254 G2 generator (EIP-197), SURVEY B.2
+        BP2=((10857046999023057135944570762232829481370756359578518086990519993285655852781,
+              11559732032986387107991004021392285783925812861821192530917403151452391805634),
+             (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+              4082367875863433681332203403145435568316851327593401208105741076214120093531)),
+        # constants.rs:40-49
+        P1=(7738860219269362160002109478394842060990190871738832255540382874922375322334,
+            8255268479661695615178834896135584953541182794935974658059743263102507888551),
+        ciphersuite_id=b"BBS_QUUX-V01-CS02-with-BN254G1_XMD:SHA-256_SVDW_RO_",  # constants.rs:54
+        fp_bytes=32,
+    )
+
+
+BLS12_381 = _make_bls()
+BN254 = _make_bn()
+SUITES = {"BLS12_381": BLS12_381, "BN254": BN254}
+
+
+# --------------------------------------------------------------------------------------------
+# pairing oracle: flat Fp12 = Fp[w]/(w^12 - 2c w^6 + c^2+1), u = w^6 - c, xi = c + u = w^6
+# Plain ate pairing with loop count (trace-1); exponent (p^12-1)/r by square-and-multiply.
+# Only the ==1 verdict is observable in the reference (verify.rs:88-92, proof_verify.rs:112-115), and
+# that verdict is the same for every non-degenerate bilinear pairing on G1 x G2.
+# --------------------------------------------------------------------------------------------
+
+
+class Fp12Flat:
+    def __init__(self, cs: Suite):
+        self.p = cs.p
+        self.c = cs.xi_c
+        self.k6 = 2 * cs.xi_c
+        self.k0 = cs.xi_c * cs.xi_c + 1
+        self.one = [1] + [0] * 11
+
+    def mul(self, a, b):
+        p = self.p
+        t = [0] * 23
+        for i, ai in enumerate(a):
+            if ai:
+                for j, bj in enumerate(b):
+                    t[i + j] += ai * bj
+        for k in range(22, 11, -1):
+            cc = t[k]
+            t[k] = 0
+            t[k - 6] += self.k6 * cc
+            t[k - 12] -= self.k0 * cc
+        return [v % p for v in t[:12]]
+
+    def pow(self, a, e):
+        r = self.one
+        while e:
+            if e & 1:
+                r = self.mul(r, a)
+            a = self.mul(a, a)
+            e >>= 1
+        return r
+
+    def emb2(self, c):
+        v = [0] * 12
+        v[0] = (c[0] - self.c * c[1]) % self.p
+        v[6] = c[1] % self.p
+        return v
+
+    def wpow(self, k):
+        v = [0] * 12
+        v[k] = 1
+        return v
+
+
+def miller_loop(cs: Suite, P, Q):
+    """f_{T,Q}(P), T = trace-1, Q on the twist (affine over Fp2), P in G1.  Pairs with an identity
+    argument contribute 1 (ark-ec multi_miller_loop filters them)."""
+    F12 = Fp12Flat(cs)
+    if P is None or Q is None:
+        return F12.one
+    F2 = cs.F2
+    p = cs.p
+    xP, yP = P
+    # w^-1 from the modulus polynomial: w*(w^11 - k6 w^5) = -k0
+    winv = [0] * 12
+    ik0 = _inv(F12.k0, p)
+    winv[11] = (-ik0) % p
+    winv[5] = F12.k6 * ik0 % p
+    assert F12.mul(winv, F12.wpow(1)) == F12.one
+    wi3 = F12.mul(F12.mul(winv, winv), winv)
+
+    def line(T, lam):
+        a = [yP % p] + [0] * 11
+        lx = F12.emb2(F2.mul(lam, (xP, 0)))
+        c = F12.emb2(F2.sub(F2.mul(lam, T[0]), T[1]))
+        if cs.twist == "M":   # untwist (x,y) -> (x/w^2, y/w^3):  l = yP - lam xP w^-1 + (lam xT - yT) w^-3
+            b = F12.mul(lx, winv)
+            c = F12.mul(c, wi3)
+        else:                 # untwist (x,y) -> (x w^2, y w^3):  l = yP - lam xP w + (lam xT - yT) w^3
+            b = F12.mul(lx, F12.wpow(1))
+            c = F12.mul(c, F12.wpow(3))
+        return [(a[i] - b[i] + c[i]) % p for i in range(12)]
+
+    T = Q
+    f = F12.one
+    for bit in bin(cs.ate_loop)[3:]:
+        x2 = F2.mul(T[0], T[0])
+        lam = F2.mul(F2.add(F2.add(x2, x2), x2), F2.inv(F2.add(T[1], T[1])))
+        f = F12.mul(F12.mul(f, f), line(T, lam))
+        T = ec_add(F2, T, T)
+        if bit == "1":
+            lam = F2.mul(F2.sub(Q[1], T[1]), F2.inv(F2.sub(Q[0], T[0])))
+            f = F12.mul(f, line(T, lam))
+            T = ec_add(F2, T, Q)
+    return f
+
+
+def pairing_product_is_one(cs: Suite, pairs) -> bool:
+    """prod e(P_i, Q_i) == 1, one shared final exponentiation (a homomorphism, so verdict-equal to
+    the reference's two `E::pairing` calls multiplied: verify.rs:88-92)."""
+    F12 = Fp12Flat(cs)
+    f = F12.one
+    for (P, Q) in pairs:
+        f = F12.mul(f, miller_loop(cs, P, Q))
+    return F12.pow(f, (cs.p ** 12 - 1) // cs.r) == F12.one
+
+
+# --------------------------------------------------------------------------------------------
+# core utilities: src/utils/core_utilities.rs
+# --------------------------------------------------------------------------------------------
+
+
+def hash_to_scalar(cs: Suite, msg: bytes, dst: bytes) -> int:
+    """core_utilities.rs:11-21."""
+    return cs.from_okm(expand_message(msg, dst, 48))
+
+
+def calculate_domain(cs: Suite, pk, q_1, h_points, header: bytes, api_id: bytes) -> int:
+    """core_utilities.rs:24-63:  H2S(comp(PK) || L || comp(Q1) || comp(H_i)* || api_id || len(header) || header)."""
+    dom_octs = len(h_points).to_bytes(8, "big") + cs.g1_compress(q_1)
+    for h in h_points:
+        dom_octs += cs.g1_compress(h)
+    dom_octs += api_id
+    dom_input = cs.g2_compress(pk) + dom_octs + len(header).to_bytes(8, "big") + header
+    return hash_to_scalar(cs, dom_input, api_id + b"H2S_")
+
+
+def seeded_random_scalars(cs: Suite, seed: bytes, dst: bytes, count: int) -> List[int]:
+    """core_utilities.rs:84-100."""
+    v = expand_message(seed, dst, 48 * count)
+    return [cs.from_okm(v[48 * i:48 * i + 48]) for i in range(count)]
+
+
+MOCK_SEED = bytes.fromhex("332e313431353932363533353839373933323338343632363433333833323739")
+MOCK_DST = b"BBS_BLS12381G1_XMD:SHA-256_SSWU_RO_H2G_HM2S_MOCK_RANDOM_SCALARS_DST_"
+
+
+def mocked_calculate_random_scalars(cs: Suite, count: int) -> List[int]:
+    """core_utilities.rs:103-113 (the BLS DST is hard-coded even for BN254)."""
+    return seeded_random_scalars(cs, MOCK_SEED, MOCK_DST, count)
+
+
+# --------------------------------------------------------------------------------------------
+# interface utilities: src/utils/interface_utilities.rs
+# --------------------------------------------------------------------------------------------
+
+
+def create_generators(cs: Suite, count: int, api_id: bytes, seed_name: bytes = b"MESSAGE_GENERATOR_SEED"):
+    """interface_utilities.rs:47-73.  `seed_name=b"BP_MESSAGE_GENERATOR_SEED"` reproduces P1
+    (comments test_vector.rs:15-25)."""
+    seed_dst = api_id + b"SIG_GENERATOR_SEED_"
+    generator_dst = api_id + b"SIG_GENERATOR_DST_"
+    generator_seed = api_id + seed_name
+    v = expand_message(generator_seed, seed_dst, 48)
+    out = []
+    for i in range(count):
+        v = expand_message(v + (i + 1).to_bytes(8, "big"), seed_dst, 48)
+        out.append(cs.hash_to_g1(v, generator_dst))
+    return out
+
+
+def msg_to_scalars(cs: Suite, messages: Sequence[bytes], api_id: bytes) -> List[int]:
+    """interface_utilities.rs:76-88."""
+    map_dst = api_id + b"MAP_MSG_TO_SCALAR_AS_HASH_"
+    return [hash_to_scalar(cs, m, map_dst) for m in messages]
+
+
+# --------------------------------------------------------------------------------------------
+# key generation: src/key_gen.rs
+# --------------------------------------------------------------------------------------------
+
+
+class KeyGenError(Exception):
+    pass
+
+
+def key_gen(cs: Suite, key_material: bytes, key_info: bytes, key_dst: bytes) -> int:
+    """key_gen.rs:46-80."""
+    if len(key_material) < 32:
+        raise KeyGenError("InvalidKeyMaterialLength")
+    if len(key_info) > 65535:
+        raise KeyGenError("InvalidKeyInfoLength")
+    sk = hash_to_scalar(cs, key_material + len(key_info).to_bytes(2, "big") + key_info, key_dst)
+    if sk == 0:
+        raise KeyGenError("InvalidSecretKey")
+    return sk
+
+
+def sk_to_pk(cs: Suite, sk: int):
+    """key_gen.rs:82-89."""
+    return ec_mul(cs.F2, cs.BP2, sk % cs.r)
+
+
+# --------------------------------------------------------------------------------------------
+# sign: src/sign.rs
+# --------------------------------------------------------------------------------------------
+
+
+class SignatureError(Exception):
+    pass
+
+
+class ProofGenError(Exception):
+    pass
+
+
+def compute_B(cs: Suite, generators, domain: int, msg_scalars: Sequence[int]):
+    """B = P1 + Q1*domain + sum H_i*m_i: sign.rs:120-126 == verify.rs:81-86 == proof_gen.rs:249-253."""
+    F = cs.F1
+    b = ec_add(F, cs.P1, ec_mul(F, generators[0], domain))
+    for i in range(1, len(msg_scalars) + 1):
+        b = ec_add(F, b, ec_mul(F, generators[i], msg_scalars[i - 1] % cs.r))
+    return b
+
+
+def core_sign(cs: Suite, sk: int, generators, header: bytes, messages: Sequence[int], api_id: bytes):
+    """sign.rs:63-133.  Returns (A, e)."""
+    if len(messages) + 1 != len(generators):
+        raise SignatureError("InvalidMessageAndGeneratorsLength")
+    pk = sk_to_pk(cs, sk)
+    L = len(messages)
+    domain = calculate_domain(cs, pk, generators[0], generators[1:L + 1], header, api_id)
+    ser = cs.scalar_be(sk)
+    for m in messages:
+        ser += cs.scalar_be(m)
+    ser += cs.scalar_be(domain)
+    e = hash_to_scalar(cs, ser, api_id + b"H2S_")
+    b = compute_B(cs, generators, domain, messages)
+    sk_plus_e = (sk + e) % cs.r
+    if sk_plus_e == 0:
+        raise ZeroDivisionError("sk+e == 0 (reference panics: sign.rs:129)")
+    a = ec_mul(cs.F1, b, _inv(sk_plus_e, cs.r))
+    return (a, e)
+
+
+def sign(cs: Suite, sk: int, messages: Sequence[bytes], header: bytes):
+    """sign.rs:32-60."""
+    api_id = cs.api_id
+    ms = msg_to_scalars(cs, messages, api_id)
+    gens = create_generators_cached(cs, len(messages) + 1, api_id)
+    return core_sign(cs, sk, gens, header, ms, api_id)
+
+
+# --------------------------------------------------------------------------------------------
+# verify: src/verify.rs
+# --------------------------------------------------------------------------------------------
+
+
+def core_verify(cs: Suite, pk, signature, generators, header: bytes, messages: Sequence[int], api_id: bytes,
+                trapdoor_sk: Optional[int] = None) -> bool:
+    """verify.rs:53-93.  With `trapdoor_sk` (the issuer secret, known for synthetic data) the pairing
+    equation is replaced by the equivalent G1 identity (sk+e)*A == B; only valid when
+    pk == sk*BP2."""
+    if len(messages) + 1 != len(generators):
+        raise SignatureError("InvalidMessageAndGeneratorsLength")
+    a, e = signature
+    L = len(messages)
+    domain = calculate_domain(cs, pk, generators[0], generators[1:L + 1], header, api_id)
+    b = compute_B(cs, generators, domain, messages)
+    if trapdoor_sk is not None:
+        # e(A, (sk+e) BP2) e(B, -BP2) == 1  <=>  (sk+e) A - B == O
+        return ec_add(cs.F1, ec_mul(cs.F1, a, (trapdoor_sk + e) % cs.r), ec_neg(cs.F1, b)) is None
+    w = ec_add(cs.F2, pk, ec_mul(cs.F2, cs.BP2, e % cs.r))
+    return pairing_product_is_one(cs, [(a, w), (b, ec_neg(cs.F2, cs.BP2))])
+
+
+def verify(cs: Suite, pk, signature, header: bytes, messages: Sequence[bytes], trapdoor_sk=None) -> bool:
+    """verify.rs:18-50."""
+    api_id = cs.api_id
+    ms = msg_to_scalars(cs, messages, api_id)
+    gens = create_generators_cached(cs, len(messages) + 1, api_id)
+    return core_verify(cs, pk, signature, gens, header, ms, api_id, trapdoor_sk)
+
+
+# --------------------------------------------------------------------------------------------
+# proof generation: src/proof_gen.rs
+# --------------------------------------------------------------------------------------------
+
+
+@dataclass
+class Proof:
+    """proof_gen.rs:29-39."""
+    a_bar: object
+    b_bar: object
+    d: object
+    e_cap: int
+    r1_cap: int
+    r3_cap: int
+    commitments: List[int]
+    challenge: int
+
+
+def proof_challenge_calculate(cs: Suite, points, domain: int, disclosed_messages, disclosed_indexes, ph: bytes,
+                              api_id: bytes) -> int:
+    """proof_gen.rs:272-328."""
+    if len(disclosed_messages) != len(disclosed_indexes):
+        raise ProofGenError("InvalidIndicesAndMessagesLength")
+    ser = len(disclosed_indexes).to_bytes(8, "big")
+    for idx, m in zip(disclosed_indexes, disclosed_messages):
+        ser += idx.to_bytes(8, "big") + cs.scalar_be(m)
+    for P in points:
+        ser += cs.g1_compress(P)
+    ser += cs.scalar_be(domain)
+    ser += len(ph).to_bytes(8, "big") + ph
+    return hash_to_scalar(cs, ser, api_id + b"H2S_")
+
+
+def core_proof_gen(cs: Suite, pk, signature, header: bytes, generators, ph: bytes, messages: Sequence[int],
+                   disclosed_indexes: Sequence[int], api_id: bytes, random_scalars: Optional[List[int]] = None) -> Proof:
+    """proof_gen.rs:116-208 with proof_init :211-269 and proof_finalize :331-365 inlined.
+    `random_scalars=None` uses the mocked scalars (feature testvector_bls12_381, proof_gen.rs:145-149)."""
+    F, r = cs.F1, cs.r
+    L, R = len(messages), len(disclosed_indexes)
+    if R > L:
+        raise ProofGenError("InvalidDisclosedIndicesLength")
+    for i in disclosed_indexes:
+        if i >= L:
+            raise ProofGenError("InvalidDisclosedIndex")
+    dis = sorted(set(disclosed_indexes))
+    undis = [i for i in range(L) if i not in set(dis)]
+    if random_scalars is None:
+        random_scalars = mocked_calculate_random_scalars(cs, 5 + L - R)
+    rs = random_scalars
+    # proof_init
+    if L + 1 != len(generators):
+        raise ProofGenError("InvalidMessageAndGeneratorsLength")
+    if len(rs) != len(undis) + 5:
+        raise ProofGenError("InvalidRandomScalarsAndUndisclosedIndicesLength")
+    a, e = signature
+    domain = calculate_domain(cs, pk, generators[0], generators[1:L + 1], header, api_id)
+    b = compute_B(cs, generators, domain, messages)
+    d = ec_mul(F, b, rs[1])
+    a_bar = ec_mul(F, a, rs[0] * rs[1] % r)
+    b_bar = ec_add(F, ec_mul(F, d, rs[0]), ec_neg(F, ec_mul(F, a_bar, e % r)))
+    t1 = ec_add(F, ec_mul(F, a_bar, rs[2]), ec_mul(F, d, rs[3]))
+    t2 = ec_mul(F, d, rs[4])
+    for k, j in enumerate(undis):
+        t2 = ec_add(F, t2, ec_mul(F, generators[1 + j], rs[5 + k]))
+    dis_msgs = [messages[i] for i in dis]
+    undis_msgs = [messages[i] for i in undis]
+    c = proof_challenge_calculate(cs, [a_bar, b_bar, d, t1, t2], domain, dis_msgs, dis, ph, api_id)
+    # proof_finalize
+    r3 = _inv(rs[1], r)
+    e_cap = (rs[2] + e * c) % r
+    r1_cap = (rs[3] - rs[0] * c) % r
+    r3_cap = (rs[4] - r3 * c) % r
+    commitments = [(rs[5 + k] + undis_msgs[k] * c) % r for k in range(len(undis))]
+    return Proof(a_bar, b_bar, d, e_cap, r1_cap, r3_cap, commitments, c)
+
+
+def proof_gen(cs: Suite, pk, signature, header: bytes, ph: bytes, messages: Sequence[bytes],
+              disclosed_indexes: Sequence[int], random_scalars=None) -> Proof:
+    """proof_gen.rs:78-113."""
+    api_id = cs.api_id
+    ms = msg_to_scalars(cs, messages, api_id)
+    gens = create_generators_cached(cs, len(messages) + 1, api_id)
+    return core_proof_gen(cs, pk, signature, header, gens, ph, ms, disclosed_indexes, api_id, random_scalars)
+
+
+# --------------------------------------------------------------------------------------------
+# proof verification: src/proof_verify.rs
+# --------------------------------------------------------------------------------------------
+
+
+def proof_verify_init(cs: Suite, pk, proof: Proof, generators, header: bytes, disclosed_messages: Sequence[int],
+                      disclosed_indexes: Sequence[int], api_id: bytes):
+    """proof_verify.rs:119-188.  Returns ([Abar,Bbar,D,T1,T2], domain)."""
+    F, r = cs.F1, cs.r
+    U, R = len(proof.commitments), len(disclosed_indexes)
+    L = R + U
+    for i in disclosed_indexes:
+        if i >= L:
+            raise ProofGenError("InvalidDisclosedIndex")
+    if len(disclosed_messages) != R:
+        raise ProofGenError("InvalidIndicesAndMessagesLength")
+    if len(generators) != L + 1:
+        raise ProofGenError("InvalidMessageAndGeneratorsLength")
+    dset = set(disclosed_indexes)
+    undis = [i for i in range(L) if i not in dset]
+    if len(undis) > U:
+        # the reference indexes commitments[i] out of bounds and panics (proof_verify.rs:179)
+        raise IndexError("duplicate disclosed index (reference panics)")
+    domain = calculate_domain(cs, pk, generators[0], generators[1:L + 1], header, api_id)
+    c = proof.challenge % r
+    t1 = ec_add(F, ec_add(F, ec_mul(F, proof.b_bar, c), ec_mul(F, proof.a_bar, proof.e_cap % r)),
+                ec_mul(F, proof.d, proof.r1_cap % r))
+    bv = ec_add(F, cs.P1, ec_mul(F, generators[0], domain))
+    msg_generators = generators[1:L + 1]
+    for k, idx in enumerate(disclosed_indexes):
+        bv = ec_add(F, bv, ec_mul(F, msg_generators[idx], disclosed_messages[k] % r))
+    t2 = ec_add(F, ec_mul(F, bv, c), ec_mul(F, proof.d, proof.r3_cap % r))
+    for k, idx in enumerate(undis):
+        t2 = ec_add(F, t2, ec_mul(F, msg_generators[idx], proof.commitments[k] % r))
+    return [proof.a_bar, proof.b_bar, proof.d, t1, t2], domain
+
+
+def core_proof_verify(cs: Suite, pk, proof: Proof, generators, header: bytes, ph: bytes,
+                      disclosed_messages: Sequence[int], disclosed_indexes: Sequence[int], api_id: bytes,
+                      trapdoor_sk: Optional[int] = None) -> bool:
+    """proof_verify.rs:64-116.  `trapdoor_sk`: pairing check replaced by Bbar == sk*Abar."""
+    points, domain = proof_verify_init(cs, pk, proof, generators, header, disclosed_messages, disclosed_indexes, api_id)
+    c = proof_challenge_calculate(cs, points, domain, disclosed_messages, disclosed_indexes, ph, api_id)
+    if c != proof.challenge % cs.r:
+        return False
+    if trapdoor_sk is not None:
+        return ec_mul(cs.F1, proof.a_bar, trapdoor_sk % cs.r) == proof.b_bar
+    return pairing_product_is_one(cs, [(proof.a_bar, pk), (proof.b_bar, ec_neg(cs.F2, cs.BP2))])
+
+
+def proof_verify(cs: Suite, pk, proof: Proof, header: bytes, ph: bytes, disclosed_messages: Sequence[bytes],
+                 disclosed_indexes: Sequence[int], trapdoor_sk=None) -> bool:
+    """proof_verify.rs:19-61."""
+    api_id = cs.api_id
+    ms = msg_to_scalars(cs, disclosed_messages, api_id)
+    gens = create_generators_cached(cs, len(proof.commitments) + len(disclosed_indexes) + 1, api_id)
+    return core_proof_verify(cs, pk, proof, gens, header, ph, ms, disclosed_indexes, api_id, trapdoor_sk)
+
+
+# --------------------------------------------------------------------------------------------
+# wire formats and a prefix-stable generator cache
+# --------------------------------------------------------------------------------------------
+
+_GEN_CACHE = {}
+
+
+def create_generators_cached(cs: Suite, count: int, api_id: bytes):
+    """create_generators is prefix-stable (each generator depends only on its index), so a longer cached
+    list serves every shorter request.  The reference recomputes it on every call."""
+    key = (cs.name, api_id)
+    have = _GEN_CACHE.get(key, [])
+    if len(have) < count:
+        have = create_generators(cs, count, api_id)
+        _GEN_CACHE[key] = have
+    return have[:count]
+
+
+def signature_to_bytes(cs: Suite, sig) -> bytes:
+    """ark CanonicalSerialize of Signature{a,e}: comp(a) || LE32(e)  (sign.rs:18-22)."""
+    return cs.g1_compress(sig[0]) + cs.scalar_le(sig[1])
+
+
+def signature_to_octets(cs: Suite, sig) -> bytes:
+    """IRTF octet form used by test_vector.rs:187-191: comp(A) || BE32(e)."""
+    return cs.g1_compress(sig[0]) + cs.scalar_be(sig[1])
+
+
+def proof_to_octets(cs: Suite, pr: Proof) -> bytes:
+    """IRTF octet form of test_vector.rs:242-259 extended with commitments (draft order):
+    Abar||Bbar||D||e^||r1^||r3^||m^_1..m^_U||c, scalars big-endian."""
+    out = cs.g1_compress(pr.a_bar) + cs.g1_compress(pr.b_bar) + cs.g1_compress(pr.d)
+    out += cs.scalar_be(pr.e_cap) + cs.scalar_be(pr.r1_cap) + cs.scalar_be(pr.r3_cap)
+    for m in pr.commitments:
+        out += cs.scalar_be(m)
+    return out + cs.scalar_be(pr.challenge)
+
+
+def proof_to_bytes(cs: Suite, pr: Proof) -> bytes:
+    """ark CanonicalSerialize of Proof (proof_gen.rs:29-39): 3 points, 3 LE scalars, u64LE len,
+    commitments LE, challenge LE."""
+    out = cs.g1_compress(pr.a_bar) + cs.g1_compress(pr.b_bar) + cs.g1_compress(pr.d)
+    out += cs.scalar_le(pr.e_cap) + cs.scalar_le(pr.r1_cap) + cs.scalar_le(pr.r3_cap)
+    out += len(pr.commitments).to_bytes(8, "little")
+    for m in pr.commitments:
+        out += cs.scalar_le(m)
+    return out + cs.scalar_le(pr.challenge)

@@ -1,0 +1,113 @@
+"""Pins oracle/bbs_oracle.py against every known-answer test the reference holds for the path
+(/root/reference/src/tests/test_vector.rs, all BLS12-381-SHA-256 IRTF fixtures) plus the BN254 P1
+constant (/root/reference/src/constants.rs:40-49)."""
+import pytest
+
+from oracle import bbs_oracle as O
+
+BLS, BN = O.BLS12_381, O.BN254
+MSG = bytes.fromhex("9872ad089e452c7b6e283dfac2a80d58e8d0ff71cc4d5e310a1debdda4a45f02")
+HEADER = bytes.fromhex("11223344556677889900aabbccddeeff")
+PH = bytes.fromhex("bed231d880675ed101ead304512e043ade9958dd0241ea70b4b3957fba941501")
+KEY_MATERIAL = bytes.fromhex("746869732d49532d6a7573742d616e2d546573742d494b4d2d746f2d67656e65726174652d246528724074232d6b6579")
+KEY_INFO = bytes.fromhex("746869732d49532d736f6d652d6b65792d6d657461646174612d746f2d62652d757365642d696e2d746573742d6b65792d67656e")
+KEY_DST = bytes.fromhex("4242535f424c53313233383147315f584d443a5348412d3235365f535357555f524f5f4832475f484d32535f4b455947454e5f4453545f")
+SIG_HEX = ("84773160b824e194073a57493dac1a20b667af70cd2352d8af241c77658da5253aa8458317cca0eae615690d55b1f271"
+           "64657dcafee1d5c1973947aa70e2cfbb4c892340be5969920d0916067b4565a0")
+PROOF_HEX = ("94916292a7a6bade28456c601d3af33fcf39278d6594b467e128a3f83686a104ef2b2fcf72df0215eeaf69262ffe8194"
+             "a19fab31a82ddbe06908985abc4c9825788b8a1610942d12b7f5debbea8985296361206dbace7af0cc834c80f33e0aad"
+             "aeea5597befbb651827b5eed5a66f1a959bb46cfd5ca1a817a14475960f69b32c54db7587b5ee3ab665fbd37b506830a"
+             "49f21d592f5e634f47cee05a025a2f8f94e73a6c15f02301d1178a92873b6e86"
+             "34bafe4983c3e15a663d64080678dbf29417519b78af042be2b3e1c4d08b8d52"
+             "0ffab008cbaaca5671a15b22c239b38e940cfeaa5e72104576a9ec4a6fad78c5"
+             "32381aeaa6fb56409cef56ee5c140d455feeb04426193c57086c9b6d397d9418")
+
+
+def test_constants_bls():  # test_vector.rs:57-69
+    assert BLS.g1_compress(BLS.BP1).hex() == "97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"
+    assert BLS.g2_compress(BLS.BP2).hex() == ("93e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e"
+                                               "024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8")
+    assert BLS.g1_compress(BLS.P1).hex() == "a8ce256102840821a3e94ea9025e4662b205762f9776b3a766c872b948f1fd225e7c59698588e70d11406d161b4e28c9"
+    assert BLS.g1_on_curve(BLS.P1) and BLS.g2_on_curve(BLS.BP2)
+
+
+def test_hash_to_scalar():  # test_vector.rs:73-83
+    dst = bytes.fromhex("4242535f424c53313233383147315f584d443a5348412d3235365f535357555f524f5f4832475f484d32535f4832535f")
+    assert dst == BLS.api_id + b"H2S_"
+    assert O.hash_to_scalar(BLS, MSG, dst) == 0x0f90cbee27beb214e6545becb8404640d3612da5d6758dffeccd77ed7169807c
+
+
+def test_mocked_random_scalars():  # test_vector.rs:87-97
+    s = O.mocked_calculate_random_scalars(BLS, 10)
+    assert s[0] == 0x04f8e2518993c4383957ad14eb13a023c4ad0c67d01ec86eeb902e732ed6df3f
+    assert s[9] == 0x485e2adab17b76f5334c95bf36c03ccf91cef77dcfcdc6b8a69e2090b3156663
+
+
+def test_msg_to_scalars():  # test_vector.rs:101-120
+    s = O.msg_to_scalars(BLS, [MSG, b""], BLS.api_id)
+    assert s[0] == 0x1cb5bb86114b34dc438a911617655a1db595abafac92f47c5001799cf624b430
+    assert s[1] == 0x08e3afeb2b4f2b5f907924ef42856616e6f2d5f1fb373736db1cca32707a7d16
+
+
+def test_create_generators():  # test_vector.rs:124-136
+    g = O.create_generators(BLS, 11, BLS.api_id)
+    want = {0: "a9ec65b70a7fbe40c874c9eb041c2cb0a7af36ccec1bea48fa2ba4c2eb67ef7f9ecb17ed27d38d27cdeddff44c8137be",
+            1: "98cd5313283aaf5db1b3ba8611fe6070d19e605de4078c38df36019fbaad0bd28dd090fd24ed27f7f4d22d5ff5dea7d4",
+            2: "a31fbe20c5c135bcaa8d9fc4e4ac665cc6db0226f35e737507e803044093f37697a9d452490a970eea6f9ad6c3dcaa3a",
+            10: "a1f229540474f4d6f1134761b92b788128c7ac8dc9b0c52d59493132679673032ac7db3fb3d79b46b13c1c41ee495bca"}
+    for i, h in want.items():
+        assert BLS.g1_compress(g[i]).hex() == h
+    # P1 = first generator under the BP_ seed (comments test_vector.rs:15-25), both curves
+    assert O.create_generators(BLS, 1, BLS.api_id, b"BP_MESSAGE_GENERATOR_SEED")[0] == BLS.P1
+    assert O.create_generators(BN, 1, BN.api_id, b"BP_MESSAGE_GENERATOR_SEED")[0] == BN.P1  # constants.rs:40-49
+
+
+def test_keygen():  # test_vector.rs:140-160
+    sk = O.key_gen(BLS, KEY_MATERIAL, KEY_INFO, KEY_DST)
+    assert sk == 0x60e55110f76883a13d030b2f6bd11883422d5abde717569fc0731f51237169fc
+    assert BLS.g2_compress(O.sk_to_pk(BLS, sk)).hex() == (
+        "a820f230f6ae38503b86c70dc50b61c58a77e45c39ab25c0652bbaa8fa136f2851bd4781c9dcde39fc9d1d52c9e60268"
+        "061e7d7632171d91aa8d460acee0e96f1e7c4cfb12d3ff9ab5d5dc91c277db75c845d649ef3c4f63aebc364cd55ded0c")
+    with pytest.raises(O.KeyGenError):
+        O.key_gen(BLS, b"short", b"", KEY_DST)
+
+
+def test_sign_and_proof_kat():  # test_vector.rs:164-192 and :199-260
+    sk = O.key_gen(BLS, KEY_MATERIAL, KEY_INFO, KEY_DST)
+    pk = O.sk_to_pk(BLS, sk)
+    sig = O.sign(BLS, sk, [MSG], HEADER)
+    assert O.signature_to_octets(BLS, sig).hex() == SIG_HEX
+    proof = O.proof_gen(BLS, pk, sig, HEADER, PH, [MSG], [0])  # mocked scalars
+    assert O.proof_to_octets(BLS, proof).hex() == PROOF_HEX
+    # verifier side recomputes T1/T2/challenge (pins proof_verify_init); trapdoor replaces the pairing
+    assert O.proof_verify(BLS, pk, proof, HEADER, PH, [MSG], [0], trapdoor_sk=sk)
+    assert O.verify(BLS, pk, sig, HEADER, [MSG], trapdoor_sk=sk)
+    assert not O.verify(BLS, pk, (sig[0], sig[1] + 1), HEADER, [MSG], trapdoor_sk=sk)
+
+
+def test_pairing_accepts_irtf_signature_and_rejects_mutations():
+    sk = O.key_gen(BLS, KEY_MATERIAL, KEY_INFO, KEY_DST)
+    pk = O.sk_to_pk(BLS, sk)
+    sig = O.sign(BLS, sk, [MSG], HEADER)
+    assert O.verify(BLS, pk, sig, HEADER, [MSG])
+    assert not O.verify(BLS, pk, (sig[0], sig[1] + 1), HEADER, [MSG])
+    assert not O.verify(BLS, pk, (None, sig[1]), HEADER, [MSG])      # A = identity -> Ok(false)
+    assert not O.verify(BLS, None, sig, HEADER, [MSG])               # default pk -> Ok(false)
+
+
+def test_bn254_roundtrip_readme_example():  # README.md:64-92 (BASELINE config 1)
+    km = bytes([5] * 32)
+    sk = O.key_gen(BN, km, b"", b"BBS-SIG-KEYGEN-SALT-")
+    pk = O.sk_to_pk(BN, sk)
+    assert BN.g2_on_curve(BN.BP2) and O.ec_mul(BN.F2, BN.BP2, BN.r) is None
+    msgs = [b"message1", b"message2", b"msg3", b"msg4"]
+    sig = O.sign(BN, sk, msgs, b"")
+    assert O.verify(BN, pk, sig, b"", msgs)
+    assert O.verify(BN, pk, sig, b"", msgs, trapdoor_sk=sk)
+    rs = O.seeded_random_scalars(BN, b"seed", b"dst", 5 + 2)
+    proof = O.proof_gen(BN, pk, sig, b"", b"", msgs, [0, 2], random_scalars=rs)
+    assert O.proof_verify(BN, pk, proof, b"", b"", [msgs[0], msgs[2]], [0, 2])
+    assert not O.proof_verify(BN, pk, proof, b"", b"", [msgs[0], msgs[3]], [0, 2])
+    # encodings round-trip
+    assert BN.g1_decompress(BN.g1_compress(sig[0])) == sig[0]
+    assert BN.g2_decompress(BN.g2_compress(pk)) == pk
