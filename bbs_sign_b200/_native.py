@@ -1,0 +1,78 @@
+"""ctypes binding of the C ABI declared in include/bbs_b200.h.
+
+`load()` opens the CUDA library built in-tree (`bbs_sign_b200/libbbs_b200.so`) and fails loudly when
+it is missing: there is no CPU fallback on the product path.  (`load(path)` with an explicit path is
+used by the GPU-less logic tests to bind the host-simulation build of the same sources.)"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbbs_b200.so")
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+
+# every symbol include/bbs_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "bbs_g1_bytes": (C.c_size_t, [C.c_int]),
+    "bbs_g2_bytes": (C.c_size_t, [C.c_int]),
+    "bbs_signature_bytes": (C.c_size_t, [C.c_int]),
+    "bbs_proof_fixed_bytes": (C.c_size_t, [C.c_int]),
+    "bbs_last_error": (C.c_char_p, []),
+    "bbs_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t,
+                                 C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "bbs_ctx_destroy": (None, [C.c_void_p]),
+    "bbs_ctx_domain": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bbs_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
+    "bbs_msg_to_scalars": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bbs_core_verify_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "bbs_verify_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "bbs_core_sign_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "bbs_sign_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
+    "bbs_core_proof_verify_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "bbs_proof_verify_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "bbs_msg_to_scalars_dev": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bbs_core_verify_batch_dev": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                            C.c_void_p]),
+    "bbs_verify_batch_dev": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                       C.c_void_p, C.c_void_p]),
+    "bbs_core_sign_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bbs_core_proof_verify_batch_dev": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                                  C.c_void_p, C.c_void_p]),
+    "bbs_selftest_field": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bbs_selftest_g1_mul": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bbs_selftest_pairing": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+_CACHE = {}
+
+
+def load(path: str | None = None) -> C.CDLL:
+    path = path or LIB_PATH
+    if path in _CACHE:
+        return _CACHE[path]
+    if not os.path.exists(path):
+        raise NativeLibraryMissing(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  bbs_sign_b200 has no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _CACHE[path] = lib
+    return lib

@@ -1,0 +1,340 @@
+"""Host-side mirror of the reference's interface for the hot path, as batch calls over the C ABI.
+
+Reference (Rust, /root/reference/src)                     here
+---------------------------------------------------------------------------------------------
+PublicKey::verify        (verify.rs:18-50)                PublicKey.verify_batch
+PublicKey::core_verify   (verify.rs:53-93)                PublicKey.core_verify_batch
+proof_verify             (proof_verify.rs:19-61)          proof_verify_batch
+core_proof_verify        (proof_verify.rs:64-116)         core_proof_verify_batch
+SecretKey::sign          (sign.rs:32-60)                  SecretKey.sign_batch
+SecretKey::core_sign     (sign.rs:63-133)                 SecretKey.core_sign_batch
+msg_to_scalars           (interface_utilities.rs:76-88)   BatchContext.msg_to_scalars
+Bls12381Const / Bn254Const (constants.rs)                 BLS12_381 / BN254
+
+Results follow the reference's `Result<bool, Error>`: every batch call returns a `numpy.uint8` status
+vector with 1 = Ok(true), 0 = Ok(false), 2.. = the Err variants (see include/bbs_b200.h).
+
+All arithmetic happens in the CUDA library; this module only packs bytes.  There is no CPU fallback:
+importing works anywhere, creating a context needs the built library and a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _native
+
+ST_REJECT, ST_ACCEPT, ST_ERR_MSG_GEN_LEN, ST_ERR_DISCLOSED_INDEX, ST_ERR_IDX_MSG_LEN, ST_ERR_MALFORMED = range(6)
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+
+class BbsError(RuntimeError):
+    pass
+
+
+@dataclass(frozen=True)
+class Ciphersuite:
+    """The reference's `Constants` impls (constants.rs:27-89)."""
+    name: str
+    curve_id: int
+    g1_bytes: int
+    g2_bytes: int
+    ciphersuite_id: bytes
+
+    @property
+    def api_id(self) -> bytes:  # verify.rs:31
+        return self.ciphersuite_id + b"H2G_HM2S_"
+
+    @property
+    def signature_bytes(self) -> int:
+        return self.g1_bytes + 32
+
+    @property
+    def proof_fixed_bytes(self) -> int:
+        return 3 * self.g1_bytes + 128
+
+    def create_generators(self, count: int) -> bytes:
+        """`create_generators(count, api_id)` (interface_utilities.rs:47-73) for this suite's api_id, as
+        `count` compressed G1 points.  Generators are constants of the ciphersuite (prefix-stable); the
+        first 129 are shipped as a table (tools/gen_generators.py).  Deriving them on the device is the
+        'next' row SURVEY 8f-4."""
+        path = os.path.join(_DATA, f"generators_{self.name.lower()}.bin")
+        with open(path, "rb") as f:
+            blob = f.read()
+        have = len(blob) // self.g1_bytes
+        if count > have:
+            raise BbsError(f"only {have} precomputed generators are shipped for {self.name}; "
+                           "pass caller-supplied generators to BatchContext for more")
+        return blob[: count * self.g1_bytes]
+
+
+BLS12_381 = Ciphersuite("BLS12_381", 1, 48, 96, b"BBS_BLS12381G1_XMD:SHA-256_SSWU_RO_")
+BN254 = Ciphersuite("BN254", 2, 32, 64, b"BBS_QUUX-V01-CS02-with-BN254G1_XMD:SHA-256_SVDW_RO_")
+
+
+def _buf(b) -> np.ndarray:
+    a = np.frombuffer(b, dtype=np.uint8) if not isinstance(b, np.ndarray) else np.ascontiguousarray(b).view(np.uint8).reshape(-1)
+    return a
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _pack_ragged(items: Sequence[bytes]):
+    offs = np.zeros(len(items) + 1, dtype=np.uint64)
+    if len(items):
+        offs[1:] = np.cumsum([len(m) for m in items], dtype=np.uint64)
+    flat = np.frombuffer(b"".join(items), dtype=np.uint8) if len(items) else np.zeros(0, dtype=np.uint8)
+    if flat.size == 0:
+        flat = np.zeros(1, dtype=np.uint8)
+    return flat, offs
+
+
+class BatchContext:
+    """Per (GPU, issuer key, header, generators) state: `bbs_ctx_create` of include/bbs_b200.h."""
+
+    def __init__(self, suite: Ciphersuite, pk: bytes, header: bytes = b"", n_messages: Optional[int] = None,
+                 generators: Optional[bytes] = None, api_id: Optional[bytes] = None, device: int = 0,
+                 lib_path: Optional[str] = None):
+        self.suite = suite
+        self.lib = _native.load(lib_path)
+        if generators is None:
+            if n_messages is None:
+                raise BbsError("n_messages or generators required")
+            generators = suite.create_generators(n_messages + 1)
+        if len(generators) % suite.g1_bytes:
+            raise BbsError("generators must be a whole number of compressed G1 points")
+        self.n_generators = len(generators) // suite.g1_bytes
+        self.L = self.n_generators - 1
+        self.api_id = suite.api_id if api_id is None else api_id
+        self.header = header
+        self.pk = bytes(pk)
+        if len(self.pk) != suite.g2_bytes:
+            raise BbsError("public key has the wrong length")
+        h = C.c_void_p()
+        hdr = _buf(header) if header else None
+        aid = _buf(self.api_id) if self.api_id else None
+        rc = self.lib.bbs_ctx_create(suite.curve_id, device, _ptr(_buf(self.pk)), _ptr(_buf(generators)),
+                                     self.n_generators, _ptr(hdr), len(header), _ptr(aid), len(self.api_id), C.byref(h))
+        if rc != 0:
+            raise BbsError(f"bbs_ctx_create failed ({rc}): {self.lib.bbs_last_error().decode()}")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.bbs_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise BbsError(f"{what} failed ({rc}): {self.lib.bbs_last_error().decode()}")
+
+    def domain(self) -> bytes:
+        out = np.zeros(32, dtype=np.uint8)
+        self._check(self.lib.bbs_ctx_domain(self._h, _ptr(out)), "bbs_ctx_domain")
+        return out.tobytes()
+
+    def launch_count(self) -> int:
+        return int(self.lib.bbs_ctx_launch_count(self._h))
+
+    # ---- interface_utilities.rs:76-88 ----
+    def msg_to_scalars(self, messages: Sequence[bytes]) -> np.ndarray:
+        flat, offs = _pack_ragged(messages)
+        out = np.zeros((len(messages), 32), dtype=np.uint8)
+        self._check(self.lib.bbs_msg_to_scalars(self._h, len(messages), _ptr(flat), _ptr(offs), _ptr(out)), "bbs_msg_to_scalars")
+        return out
+
+    # ---- verify.rs ----
+    def core_verify_batch(self, signatures, msg_scalars, n_msgs: int) -> np.ndarray:
+        sigs = _buf(signatures)
+        n = sigs.size // self.suite.signature_bytes
+        sc = _buf(msg_scalars)
+        if sc.size != n * n_msgs * 32:
+            raise BbsError("msg_scalars has the wrong size")
+        if sc.size == 0:
+            sc = np.zeros(1, dtype=np.uint8)
+        st = np.full(n, 255, dtype=np.uint8)
+        self._check(self.lib.bbs_core_verify_batch(self._h, n, _ptr(sigs), _ptr(sc), n_msgs, _ptr(st)), "bbs_core_verify_batch")
+        return st
+
+    def verify_batch(self, signatures, messages: Sequence[Sequence[bytes]]) -> np.ndarray:
+        sigs = _buf(signatures)
+        n = sigs.size // self.suite.signature_bytes
+        if len(messages) != n:
+            raise BbsError("one message list per signature required")
+        n_msgs = len(messages[0]) if n else 0
+        if any(len(m) != n_msgs for m in messages):
+            raise BbsError("all items of a batch must carry the same number of messages")
+        flat, offs = _pack_ragged([m for item in messages for m in item])
+        st = np.full(n, 255, dtype=np.uint8)
+        self._check(self.lib.bbs_verify_batch(self._h, n, _ptr(sigs), _ptr(flat), _ptr(offs), n_msgs, _ptr(st)), "bbs_verify_batch")
+        return st
+
+    # ---- sign.rs ----
+    def core_sign_batch(self, sk_le32: bytes, msg_scalars, n: int, n_msgs: int, want_b: bool = False):
+        sc = _buf(msg_scalars)
+        if sc.size != n * n_msgs * 32:
+            raise BbsError("msg_scalars has the wrong size")
+        if sc.size == 0:
+            sc = np.zeros(1, dtype=np.uint8)
+        sigs = np.zeros((n, self.suite.signature_bytes), dtype=np.uint8)
+        b = np.zeros((n, self.suite.g1_bytes), dtype=np.uint8) if want_b else None
+        st = np.full(n, 255, dtype=np.uint8)
+        self._check(self.lib.bbs_core_sign_batch(self._h, _ptr(_buf(sk_le32)), n, _ptr(sc), n_msgs, _ptr(sigs), _ptr(b), _ptr(st)),
+                    "bbs_core_sign_batch")
+        return sigs, b, st
+
+    def sign_batch(self, sk_le32: bytes, messages: Sequence[Sequence[bytes]], want_b: bool = False):
+        n = len(messages)
+        n_msgs = len(messages[0]) if n else 0
+        if any(len(m) != n_msgs for m in messages):
+            raise BbsError("all items of a batch must carry the same number of messages")
+        flat, offs = _pack_ragged([m for item in messages for m in item])
+        sigs = np.zeros((n, self.suite.signature_bytes), dtype=np.uint8)
+        b = np.zeros((n, self.suite.g1_bytes), dtype=np.uint8) if want_b else None
+        st = np.full(n, 255, dtype=np.uint8)
+        self._check(self.lib.bbs_sign_batch(self._h, _ptr(_buf(sk_le32)), n, _ptr(flat), _ptr(offs), n_msgs, _ptr(sigs), _ptr(b), _ptr(st)),
+                    "bbs_sign_batch")
+        return sigs, b, st
+
+    # ---- proof_verify.rs ----
+    def _pack_proofs(self, proofs: Sequence["ProofBytes"], disclosed_indexes: Sequence[Sequence[int]]):
+        n = len(proofs)
+        fixed = np.frombuffer(b"".join(p.fixed for p in proofs), dtype=np.uint8) if n else np.zeros(1, np.uint8)
+        commit_off = np.zeros(n + 1, dtype=np.uint64)
+        dis_off = np.zeros(n + 1, dtype=np.uint64)
+        if n:
+            commit_off[1:] = np.cumsum([len(p.commitments) // 32 for p in proofs], dtype=np.uint64)
+            dis_off[1:] = np.cumsum([len(d) for d in disclosed_indexes], dtype=np.uint64)
+        commit = np.frombuffer(b"".join(p.commitments for p in proofs), dtype=np.uint8)
+        if commit.size == 0:
+            commit = np.zeros(1, np.uint8)
+        idx = np.array([i for d in disclosed_indexes for i in d], dtype=np.uint32)
+        if idx.size == 0:
+            idx = np.zeros(1, np.uint32)
+        return fixed, commit, commit_off, idx, dis_off
+
+    def core_proof_verify_batch(self, proofs, ph: bytes, disclosed_scalars: Sequence[Sequence[bytes]],
+                                disclosed_indexes: Sequence[Sequence[int]]) -> np.ndarray:
+        n = len(proofs)
+        st = np.full(n, 255, dtype=np.uint8)
+        # InvalidIndicesAndMessagesLength (proof_verify.rs:144-146) is a property of the host-side lists
+        bad = [len(disclosed_scalars[i]) != len(disclosed_indexes[i]) for i in range(n)]
+        keep = [i for i in range(n) if not bad[i]]
+        if keep:
+            fixed, commit, commit_off, idx, dis_off = self._pack_proofs([proofs[i] for i in keep], [disclosed_indexes[i] for i in keep])
+            sc = np.frombuffer(b"".join(s for i in keep for s in disclosed_scalars[i]), dtype=np.uint8)
+            if sc.size == 0:
+                sc = np.zeros(1, np.uint8)
+            phb = _buf(ph) if ph else None
+            out = np.full(len(keep), 255, dtype=np.uint8)
+            self._check(self.lib.bbs_core_proof_verify_batch(self._h, len(keep), _ptr(fixed), _ptr(commit), _ptr(commit_off),
+                                                             _ptr(idx), _ptr(sc), _ptr(dis_off), _ptr(phb), len(ph), _ptr(out)),
+                        "bbs_core_proof_verify_batch")
+            st[keep] = out
+        for i in range(n):
+            if bad[i]:
+                st[i] = self._length_error_status(proofs[i], disclosed_indexes[i])
+        return st
+
+    def _length_error_status(self, proof, idxs):
+        # reference order (proof_verify.rs:139-146): index range check first, then the length check
+        L = len(proof.commitments) // 32 + len(idxs)
+        return ST_ERR_DISCLOSED_INDEX if any(i >= L for i in idxs) else ST_ERR_IDX_MSG_LEN
+
+    def proof_verify_batch(self, proofs, ph: bytes, disclosed_messages: Sequence[Sequence[bytes]],
+                           disclosed_indexes: Sequence[Sequence[int]]) -> np.ndarray:
+        n = len(proofs)
+        st = np.full(n, 255, dtype=np.uint8)
+        bad = [len(disclosed_messages[i]) != len(disclosed_indexes[i]) for i in range(n)]
+        keep = [i for i in range(n) if not bad[i]]
+        if keep:
+            fixed, commit, commit_off, idx, dis_off = self._pack_proofs([proofs[i] for i in keep], [disclosed_indexes[i] for i in keep])
+            flat, moffs = _pack_ragged([m for i in keep for m in disclosed_messages[i]])
+            phb = _buf(ph) if ph else None
+            out = np.full(len(keep), 255, dtype=np.uint8)
+            self._check(self.lib.bbs_proof_verify_batch(self._h, len(keep), _ptr(fixed), _ptr(commit), _ptr(commit_off), _ptr(idx),
+                                                        _ptr(flat), _ptr(moffs), _ptr(dis_off), _ptr(phb), len(ph), _ptr(out)),
+                        "bbs_proof_verify_batch")
+            st[keep] = out
+        for i in range(n):
+            if bad[i]:
+                st[i] = self._length_error_status(proofs[i], disclosed_indexes[i])
+        return st
+
+
+@dataclass
+class ProofBytes:
+    """`Proof<E,F>` (proof_gen.rs:29-39) split as the ABI wants it: the fixed-size fields
+    comp(Abar)||comp(Bbar)||comp(D)||LE32(e^)||LE32(r1^)||LE32(r3^)||LE32(c), and the LE32 commitments."""
+    fixed: bytes
+    commitments: bytes
+
+    @staticmethod
+    def from_canonical(suite: Ciphersuite, blob: bytes) -> "ProofBytes":
+        """Parse ark `CanonicalSerialize` of Proof: 3 points, 3 scalars, u64 LE length, commitments, challenge."""
+        g = suite.g1_bytes
+        head = blob[: 3 * g + 96]
+        u = int.from_bytes(blob[3 * g + 96: 3 * g + 104], "little")
+        commitments = blob[3 * g + 104: 3 * g + 104 + 32 * u]
+        challenge = blob[3 * g + 104 + 32 * u: 3 * g + 136 + 32 * u]
+        if len(challenge) != 32:
+            raise BbsError("truncated proof")
+        return ProofBytes(head + challenge, commitments)
+
+
+class PublicKey:
+    """`PublicKey<E>` (key_gen.rs:12-15) with the batch entry points the north star adds."""
+
+    def __init__(self, suite: Ciphersuite, pk: bytes):
+        self.suite, self.pk = suite, bytes(pk)
+        self._ctx = {}
+
+    def context(self, header: bytes, n_messages: int, device: int = 0) -> BatchContext:
+        key = (header, n_messages, device)
+        if key not in self._ctx:
+            self._ctx[key] = BatchContext(self.suite, self.pk, header, n_messages, device=device)
+        return self._ctx[key]
+
+    def verify_batch(self, signatures, header: bytes, messages: Sequence[Sequence[bytes]], device: int = 0) -> np.ndarray:
+        """verify.rs:18-50 for a batch sharing `header`; messages[i] is the message list of signature i."""
+        n_msgs = len(messages[0]) if len(messages) else 0
+        return self.context(header, n_msgs, device).verify_batch(signatures, messages)
+
+    def proof_verify_batch(self, proofs: Sequence[ProofBytes], header: bytes, ph: bytes,
+                           disclosed_messages: Sequence[Sequence[bytes]], disclosed_indexes: Sequence[Sequence[int]],
+                           device: int = 0) -> np.ndarray:
+        """proof_verify.rs:19-61 for a batch sharing header / ph and the same total message count."""
+        if not proofs:
+            return np.zeros(0, dtype=np.uint8)
+        L = len(proofs[0].commitments) // 32 + len(disclosed_indexes[0])
+        return self.context(header, L, device).proof_verify_batch(proofs, ph, disclosed_messages, disclosed_indexes)
+
+
+class SecretKey:
+    """`SecretKey<F>` (key_gen.rs:29-32); `sk` is the 32-byte little-endian scalar, `pk` its public key
+    (the reference derives it with sk_to_pk on every sign call, sign.rs:81)."""
+
+    def __init__(self, suite: Ciphersuite, sk_le32: bytes, pk: bytes):
+        self.suite, self.sk, self.pk = suite, bytes(sk_le32), PublicKey(suite, pk)
+
+    def sign_batch(self, messages: Sequence[Sequence[bytes]], header: bytes, want_b: bool = False, device: int = 0):
+        """sign.rs:32-60 for a batch sharing `header`."""
+        n_msgs = len(messages[0]) if len(messages) else 0
+        return self.pk.context(header, n_msgs, device).sign_batch(self.sk, messages, want_b)

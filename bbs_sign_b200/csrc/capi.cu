@@ -1,0 +1,446 @@
+// C ABI (include/bbs_b200.h) of the B200 batch engine.  Host code here only moves bytes and enqueues
+// kernels; every field / curve / pairing / hash operation of the path runs on the GPU (kernels.cuh).
+#include "../../include/bbs_b200.h"
+#include "kernels.cuh"
+#include "launch.cuh"
+
+#include <new>
+#include <vector>
+
+using namespace bbs;
+
+namespace {
+
+constexpr int TPB_HEAVY = 128;   // G1 / pairing kernels
+constexpr int TPB_LIGHT = 128;   // hashing
+
+struct Ctx {
+    int curve = 0, device = 0;
+    uint32_t L = 0;
+    rt_stream_t stream = nullptr;
+    uint64_t launches = 0;
+    DevBuf pk_comp, gens_comp, api_id, header, dst_h2s, dst_map;
+    DevBuf gens, W, K, domain, tab, lines, misc;
+    CtxView view{};
+    // grow-only scratch for the batch calls
+    DevBuf s_sigs, s_scalars, s_msgs, s_offsets, s_pair, s_flags, s_status, s_out, s_out2;
+    DevBuf s_commit, s_commit_off, s_dis_idx, s_dis_scalars, s_dis_off, s_ph, s_dis_msgs, s_dis_msg_off;
+    void release_all() {
+        DevBuf* all[] = {&pk_comp, &gens_comp, &api_id, &header, &dst_h2s, &dst_map, &gens, &W, &K, &domain, &tab,
+                         &lines, &misc, &s_sigs, &s_scalars, &s_msgs, &s_offsets, &s_pair, &s_flags, &s_status, &s_out,
+                         &s_out2, &s_commit, &s_commit_off, &s_dis_idx, &s_dis_scalars, &s_dis_off, &s_ph, &s_dis_msgs,
+                         &s_dis_msg_off};
+        for (DevBuf* b : all) b->release();
+    }
+};
+
+#define TRY(expr) do { int rc_ = (expr); if (rc_) return rc_; } while (0)
+
+int arg_error(const char* what) { rt_set_error("bad argument", what); return BBS_E_ARG; }
+
+template <class C>
+struct Impl {
+    static constexpr size_t SIG = C::G1_BYTES + 32;
+    static constexpr size_t PROOF = 3 * C::G1_BYTES + 128;
+
+    static int create(Ctx* c, const uint8_t* pk, const uint8_t* gens, uint32_t n_gens, const uint8_t* header,
+                      size_t header_len, const uint8_t* api_id, size_t api_id_len) {
+        const uint32_t L = n_gens - 1;
+        c->L = L;
+        rt_stream_t s = c->stream;
+        std::vector<uint8_t> dsth(api_id, api_id + api_id_len), dstm(api_id, api_id + api_id_len);
+        const char* h2s = "H2S_";                            // verify.rs / core_utilities.rs:60
+        const char* map = "MAP_MSG_TO_SCALAR_AS_HASH_";      // interface_utilities.rs:82
+        dsth.insert(dsth.end(), h2s, h2s + 4);
+        dstm.insert(dstm.end(), map, map + 26);
+        if (dstm.size() > 255) return arg_error("dst size is invalid (api_id too long; utilities_helper.rs:50-52)");
+        TRY(c->pk_comp.reserve(C::G2_BYTES));
+        TRY(c->gens_comp.reserve((size_t)n_gens * C::G1_BYTES));
+        TRY(c->api_id.reserve(api_id_len));
+        TRY(c->header.reserve(header_len));
+        TRY(c->dst_h2s.reserve(dsth.size()));
+        TRY(c->dst_map.reserve(dstm.size()));
+        TRY(c->gens.reserve((size_t)n_gens * 2 * C::Fp::N * 4));
+        TRY(c->W.reserve(4 * C::Fp::N * 4));
+        TRY(c->K.reserve(2 * C::Fp::N * 4));
+        TRY(c->domain.reserve(32));
+        TRY(c->misc.reserve((n_gens + 2) * 4));
+        const size_t tab_entries = (size_t)(L + 1) * TAB_WINDOWS * TAB_ENTRIES;
+        TRY(c->tab.reserve(tab_entries * 2 * C::Fp::N * 4));
+        const int n_lines = ate_line_count<C>();
+        TRY(c->lines.reserve((size_t)n_lines * 2 * 4 * C::Fp::N * 4));
+        TRY(rt_h2d(c->pk_comp.p, pk, C::G2_BYTES, s));
+        TRY(rt_h2d(c->gens_comp.p, gens, (size_t)n_gens * C::G1_BYTES, s));
+        TRY(rt_h2d(c->api_id.p, api_id, api_id_len, s));
+        TRY(rt_h2d(c->header.p, header, header_len, s));
+        TRY(rt_h2d(c->dst_h2s.p, dsth.data(), dsth.size(), s));
+        TRY(rt_h2d(c->dst_map.p, dstm.data(), dstm.size(), s));
+        TRY(rt_memset(c->lines.p, 0, (size_t)n_lines * 2 * 4 * C::Fp::N * 4, s));
+        uint32_t* d_status = (uint32_t*)c->misc.p;
+        // 1. decode generators and public key
+        CtxDecodeArgs da{(const uint8_t*)c->gens_comp.p, (const uint8_t*)c->pk_comp.p, n_gens, (uint32_t*)c->gens.p,
+                         (uint32_t*)c->W.p, d_status};
+        TRY((rt_launch<CtxDecodeArgs, &ctx_decode_item<C>, 32>(da, n_gens + 1, s)));
+        std::vector<uint32_t> st(n_gens + 2);
+        TRY(rt_d2h(st.data(), d_status, (n_gens + 1) * 4, s));
+        TRY(rt_sync(s));
+        for (uint32_t j = 0; j < n_gens; j++)
+            if (st[j] != PT_OK) return arg_error("generator is not a valid non-identity G1 encoding");
+        if (st[n_gens] == PT_BAD) return arg_error("public key is not a valid G2 encoding");
+        const uint32_t w_inf = st[n_gens] == PT_INF;
+        // 2. domain and K
+        uint32_t* d_kinf = d_status + n_gens + 1;
+        CtxDomainArgs dom{(const uint8_t*)c->pk_comp.p, (const uint8_t*)c->gens_comp.p, L,
+                          (const uint8_t*)c->api_id.p, (uint32_t)api_id_len, (const uint8_t*)c->header.p,
+                          (uint32_t)header_len, (const uint8_t*)c->dst_h2s.p, (uint32_t)dsth.size(),
+                          (const uint32_t*)c->gens.p, (uint32_t*)c->domain.p, (uint32_t*)c->K.p, d_kinf};
+        TRY((rt_launch<CtxDomainArgs, &ctx_domain_item<C>, 32>(dom, 1, s)));
+        uint32_t k_inf = 0;
+        TRY(rt_d2h(&k_inf, d_kinf, 4, s));
+        TRY(rt_sync(s));
+        // 3. window tables, 4. line tables
+        CtxTableArgs ta{(const uint32_t*)c->K.p, (const uint32_t*)c->gens.p, (uint32_t*)c->tab.p};
+        TRY((rt_launch<CtxTableArgs, &ctx_table_item<C>, TPB_HEAVY>(ta, (uint32_t)tab_entries, s)));
+        CtxLinesArgs la{(const uint32_t*)c->W.p, w_inf, (uint32_t*)c->lines.p};
+        TRY((rt_launch<CtxLinesArgs, &ctx_lines_item<C>, 32>(la, 2, s)));
+        TRY(rt_sync(s));
+        c->launches += 4;
+        CtxView& v = c->view;
+        v.L = L; v.w_inf = w_inf; v.k_inf = k_inf;
+        v.dst_h2s = (const uint8_t*)c->dst_h2s.p; v.dst_h2s_len = (uint32_t)dsth.size();
+        v.dst_map = (const uint8_t*)c->dst_map.p; v.dst_map_len = (uint32_t)dstm.size();
+        v.gens = (const uint32_t*)c->gens.p; v.W = (const uint32_t*)c->W.p; v.K = (const uint32_t*)c->K.p;
+        v.domain = (const uint32_t*)c->domain.p; v.tab = (const uint32_t*)c->tab.p;
+        v.lines = (const uint32_t*)c->lines.p;
+        return BBS_OK;
+    }
+
+    static int h2s_dev(Ctx* c, size_t count, const uint8_t* d_msgs, const uint64_t* d_off, uint8_t* d_out, rt_stream_t s) {
+        H2sArgs a{d_msgs, d_off, c->view.dst_map, c->view.dst_map_len, d_out};
+        TRY((rt_launch<H2sArgs, &h2s_item<C>, TPB_LIGHT>(a, (uint32_t)count, s)));
+        c->launches += count ? 1 : 0;
+        return BBS_OK;
+    }
+
+    static int pairing_dev(Ctx* c, size_t n, uint8_t* d_status, rt_stream_t s) {
+        PairingArgs pa{c->view.lines, (const uint32_t*)c->s_pair.p, (const uint32_t*)c->s_flags.p, d_status};
+        TRY((rt_launch<PairingArgs, &pairing_item<C>, TPB_HEAVY>(pa, (uint32_t)n, s)));
+        c->launches += n ? 1 : 0;
+        return BBS_OK;
+    }
+
+    static int core_verify_dev(Ctx* c, size_t n, const uint8_t* d_sigs, const uint8_t* d_scalars, uint32_t n_msgs,
+                               uint8_t* d_status, rt_stream_t s) {
+        TRY(c->s_pair.reserve(n * 6 * C::Fp::N * 4));
+        TRY(c->s_flags.reserve(n * 4));
+        VerifyG1Args a{c->view, d_sigs, d_scalars, n_msgs, (uint32_t*)c->s_pair.p, (uint32_t*)c->s_flags.p, d_status};
+        TRY((rt_launch<VerifyG1Args, &verify_g1_item<C>, TPB_HEAVY>(a, (uint32_t)n, s)));
+        c->launches += n ? 1 : 0;
+        return pairing_dev(c, n, d_status, s);
+    }
+
+    static int verify_dev(Ctx* c, size_t n, const uint8_t* d_sigs, const uint8_t* d_msgs, const uint64_t* d_off,
+                          uint32_t n_msgs, uint8_t* d_status, rt_stream_t s) {
+        TRY(c->s_scalars.reserve(n * n_msgs * 32));
+        TRY(h2s_dev(c, n * n_msgs, d_msgs, d_off, (uint8_t*)c->s_scalars.p, s));
+        return core_verify_dev(c, n, d_sigs, (const uint8_t*)c->s_scalars.p, n_msgs, d_status, s);
+    }
+
+    static int core_sign_dev(Ctx* c, const uint8_t* sk, size_t n, const uint8_t* d_scalars, uint32_t n_msgs,
+                             uint8_t* d_sigs, uint8_t* d_b, uint8_t* d_status, rt_stream_t s) {
+        SignArgs a{};
+        a.ctx = c->view;
+        limbs_from_le<8>(a.sk, sk);
+        if (!fe_is_canonical<typename C::Fr>(a.sk)) return arg_error("secret key scalar is not canonical");
+        a.scalars = d_scalars; a.n_msgs = n_msgs; a.sigs_out = d_sigs; a.b_out = d_b; a.status = d_status;
+        TRY((rt_launch<SignArgs, &sign_item<C>, TPB_HEAVY>(a, (uint32_t)n, s)));
+        c->launches += n ? 1 : 0;
+        return BBS_OK;
+    }
+
+    static int core_proof_verify_dev(Ctx* c, size_t n, const uint8_t* d_proofs, const uint8_t* d_commit,
+                                     const uint64_t* d_commit_off, const uint32_t* d_idx, const uint8_t* d_dis_scalars,
+                                     const uint64_t* d_dis_off, const uint8_t* d_ph, size_t ph_len, uint8_t* d_status,
+                                     rt_stream_t s) {
+        TRY(c->s_pair.reserve(n * 6 * C::Fp::N * 4));
+        TRY(c->s_flags.reserve(n * 4));
+        ProofG1Args a{c->view, d_proofs, d_commit, d_commit_off, d_idx, d_dis_scalars, d_dis_off, d_ph,
+                      (uint32_t)ph_len, (uint32_t*)c->s_pair.p, (uint32_t*)c->s_flags.p, d_status};
+        TRY((rt_launch<ProofG1Args, &proof_g1_item<C>, TPB_HEAVY>(a, (uint32_t)n, s)));
+        c->launches += n ? 1 : 0;
+        return pairing_dev(c, n, d_status, s);
+    }
+
+    // ---- host-buffer wrappers ---------------------------------------------------------------------
+    static int stage(DevBuf& b, const void* h, size_t bytes, rt_stream_t s) {
+        TRY(b.reserve(bytes));
+        return rt_h2d(b.p, h, bytes, s);
+    }
+    static int finish_status(Ctx* c, size_t n, uint8_t* status) {
+        TRY(rt_d2h(status, c->s_status.p, n, c->stream));
+        return rt_sync(c->stream);
+    }
+
+    static int msg_to_scalars(Ctx* c, size_t count, const uint8_t* msgs, const uint64_t* off, uint8_t* out) {
+        rt_stream_t s = c->stream;
+        TRY(stage(c->s_msgs, msgs, off[count], s));
+        TRY(stage(c->s_offsets, off, (count + 1) * 8, s));
+        TRY(c->s_scalars.reserve(count * 32));
+        TRY(h2s_dev(c, count, (const uint8_t*)c->s_msgs.p, (const uint64_t*)c->s_offsets.p, (uint8_t*)c->s_scalars.p, s));
+        TRY(rt_d2h(out, c->s_scalars.p, count * 32, s));
+        return rt_sync(s);
+    }
+    static int core_verify(Ctx* c, size_t n, const uint8_t* sigs, const uint8_t* scalars, uint32_t n_msgs, uint8_t* status) {
+        rt_stream_t s = c->stream;
+        TRY(stage(c->s_sigs, sigs, n * SIG, s));
+        TRY(stage(c->s_scalars, scalars, n * n_msgs * 32, s));
+        TRY(c->s_status.reserve(n));
+        TRY(core_verify_dev(c, n, (const uint8_t*)c->s_sigs.p, (const uint8_t*)c->s_scalars.p, n_msgs,
+                            (uint8_t*)c->s_status.p, s));
+        return finish_status(c, n, status);
+    }
+    static int verify(Ctx* c, size_t n, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off, uint32_t n_msgs,
+                      uint8_t* status) {
+        rt_stream_t s = c->stream;
+        const size_t count = n * n_msgs;
+        TRY(stage(c->s_sigs, sigs, n * SIG, s));
+        TRY(stage(c->s_msgs, msgs, off[count], s));
+        TRY(stage(c->s_offsets, off, (count + 1) * 8, s));
+        TRY(c->s_status.reserve(n));
+        TRY(verify_dev(c, n, (const uint8_t*)c->s_sigs.p, (const uint8_t*)c->s_msgs.p, (const uint64_t*)c->s_offsets.p,
+                       n_msgs, (uint8_t*)c->s_status.p, s));
+        return finish_status(c, n, status);
+    }
+    static int sign_common(Ctx* c, const uint8_t* sk, size_t n, uint32_t n_msgs, uint8_t* sigs_out, uint8_t* b_out,
+                           uint8_t* status) {
+        rt_stream_t s = c->stream;
+        TRY(c->s_out.reserve(n * SIG));
+        TRY(c->s_out2.reserve(n * C::G1_BYTES));
+        TRY(c->s_status.reserve(n));
+        TRY(rt_memset(c->s_out.p, 0, n * SIG, s));
+        TRY(core_sign_dev(c, sk, n, (const uint8_t*)c->s_scalars.p, n_msgs, (uint8_t*)c->s_out.p,
+                          b_out ? (uint8_t*)c->s_out2.p : nullptr, (uint8_t*)c->s_status.p, s));
+        TRY(rt_d2h(sigs_out, c->s_out.p, n * SIG, s));
+        if (b_out) TRY(rt_d2h(b_out, c->s_out2.p, n * C::G1_BYTES, s));
+        return finish_status(c, n, status);
+    }
+    static int core_sign(Ctx* c, const uint8_t* sk, size_t n, const uint8_t* scalars, uint32_t n_msgs, uint8_t* sigs_out,
+                         uint8_t* b_out, uint8_t* status) {
+        TRY(stage(c->s_scalars, scalars, n * n_msgs * 32, c->stream));
+        return sign_common(c, sk, n, n_msgs, sigs_out, b_out, status);
+    }
+    static int sign(Ctx* c, const uint8_t* sk, size_t n, const uint8_t* msgs, const uint64_t* off, uint32_t n_msgs,
+                    uint8_t* sigs_out, uint8_t* b_out, uint8_t* status) {
+        rt_stream_t s = c->stream;
+        const size_t count = n * n_msgs;
+        TRY(stage(c->s_msgs, msgs, off[count], s));
+        TRY(stage(c->s_offsets, off, (count + 1) * 8, s));
+        TRY(c->s_scalars.reserve(count * 32));
+        TRY(h2s_dev(c, count, (const uint8_t*)c->s_msgs.p, (const uint64_t*)c->s_offsets.p, (uint8_t*)c->s_scalars.p, s));
+        return sign_common(c, sk, n, n_msgs, sigs_out, b_out, status);
+    }
+    static int proof_common(Ctx* c, size_t n, const uint8_t* proofs, const uint8_t* commit, const uint64_t* commit_off,
+                            const uint32_t* idx, const uint64_t* dis_off, const uint8_t* ph, size_t ph_len,
+                            uint8_t* status) {
+        rt_stream_t s = c->stream;
+        TRY(stage(c->s_sigs, proofs, n * PROOF, s));
+        TRY(stage(c->s_commit, commit, commit_off[n] * 32, s));
+        TRY(stage(c->s_commit_off, commit_off, (n + 1) * 8, s));
+        TRY(stage(c->s_dis_idx, idx, dis_off[n] * 4, s));
+        TRY(stage(c->s_dis_off, dis_off, (n + 1) * 8, s));
+        TRY(stage(c->s_ph, ph, ph_len, s));
+        TRY(c->s_status.reserve(n));
+        TRY(core_proof_verify_dev(c, n, (const uint8_t*)c->s_sigs.p, (const uint8_t*)c->s_commit.p,
+                                  (const uint64_t*)c->s_commit_off.p, (const uint32_t*)c->s_dis_idx.p,
+                                  (const uint8_t*)c->s_dis_scalars.p, (const uint64_t*)c->s_dis_off.p,
+                                  (const uint8_t*)c->s_ph.p, ph_len, (uint8_t*)c->s_status.p, s));
+        return finish_status(c, n, status);
+    }
+    static int core_proof_verify(Ctx* c, size_t n, const uint8_t* proofs, const uint8_t* commit, const uint64_t* commit_off,
+                                 const uint32_t* idx, const uint8_t* dis_scalars, const uint64_t* dis_off,
+                                 const uint8_t* ph, size_t ph_len, uint8_t* status) {
+        TRY(stage(c->s_dis_scalars, dis_scalars, dis_off[n] * 32, c->stream));
+        return proof_common(c, n, proofs, commit, commit_off, idx, dis_off, ph, ph_len, status);
+    }
+    static int proof_verify(Ctx* c, size_t n, const uint8_t* proofs, const uint8_t* commit, const uint64_t* commit_off,
+                            const uint32_t* idx, const uint8_t* dis_msgs, const uint64_t* dis_msg_off,
+                            const uint64_t* dis_off, const uint8_t* ph, size_t ph_len, uint8_t* status) {
+        rt_stream_t s = c->stream;
+        const size_t count = dis_off[n];
+        TRY(stage(c->s_dis_msgs, dis_msgs, dis_msg_off[count], s));
+        TRY(stage(c->s_dis_msg_off, dis_msg_off, (count + 1) * 8, s));
+        TRY(c->s_dis_scalars.reserve(count * 32));
+        TRY(h2s_dev(c, count, (const uint8_t*)c->s_dis_msgs.p, (const uint64_t*)c->s_dis_msg_off.p,
+                    (uint8_t*)c->s_dis_scalars.p, s));
+        return proof_common(c, n, proofs, commit, commit_off, idx, dis_off, ph, ph_len, status);
+    }
+};
+
+#include "selftest.cuh"
+
+Ctx* as_ctx(bbs_ctx* p) { return reinterpret_cast<Ctx*>(p); }
+
+#define DISPATCH(c, call)                                              \
+    do {                                                               \
+        if (!(c)) return arg_error("null context");                    \
+        if (rt_set_device((c)->device)) return BBS_E_CUDA;             \
+        if ((c)->curve == BBS_CURVE_BLS12_381) return Impl<Bls>::call; \
+        return Impl<Bn>::call;                                         \
+    } while (0)
+
+}  // namespace
+
+extern "C" {
+
+size_t bbs_g1_bytes(int curve) { return curve == BBS_CURVE_BLS12_381 ? 48 : (curve == BBS_CURVE_BN254 ? 32 : 0); }
+size_t bbs_g2_bytes(int curve) { return 2 * bbs_g1_bytes(curve); }
+size_t bbs_signature_bytes(int curve) { return bbs_g1_bytes(curve) ? bbs_g1_bytes(curve) + 32 : 0; }
+size_t bbs_proof_fixed_bytes(int curve) { return bbs_g1_bytes(curve) ? 3 * bbs_g1_bytes(curve) + 128 : 0; }
+const char* bbs_last_error(void) { return rt_errbuf(); }
+
+int bbs_ctx_create(int curve, int device, const uint8_t* pk, const uint8_t* generators, uint32_t n_generators,
+                   const uint8_t* header, size_t header_len, const uint8_t* api_id, size_t api_id_len, bbs_ctx** out) {
+    if (!out) return arg_error("out is null");
+    *out = nullptr;
+    if (curve != BBS_CURVE_BLS12_381 && curve != BBS_CURVE_BN254) return arg_error("unknown curve id");
+    if (!pk || !generators || n_generators < 1) return arg_error("pk / generators missing");
+    if (n_generators - 1 > BBS_MAX_MESSAGES) return arg_error("too many generators");
+    if ((header_len && !header) || (api_id_len && !api_id)) return arg_error("null header / api_id");
+    if (rt_set_device(device)) return BBS_E_CUDA;
+    if (rt_set_stack(48 * 1024)) return BBS_E_CUDA;
+    Ctx* c = new (std::nothrow) Ctx();
+    if (!c) return arg_error("out of host memory");
+    c->curve = curve; c->device = device;
+    int rc = rt_stream_create(&c->stream);
+    if (!rc) {
+        rc = curve == BBS_CURVE_BLS12_381
+                 ? Impl<Bls>::create(c, pk, generators, n_generators, header, header_len, api_id, api_id_len)
+                 : Impl<Bn>::create(c, pk, generators, n_generators, header, header_len, api_id, api_id_len);
+    }
+    if (rc) { c->release_all(); rt_stream_destroy(c->stream); delete c; return rc; }
+    *out = reinterpret_cast<bbs_ctx*>(c);
+    return BBS_OK;
+}
+
+void bbs_ctx_destroy(bbs_ctx* p) {
+    Ctx* c = as_ctx(p);
+    if (!c) return;
+    rt_set_device(c->device);
+    rt_sync(c->stream);
+    c->release_all();
+    rt_stream_destroy(c->stream);
+    delete c;
+}
+
+int bbs_ctx_domain(bbs_ctx* p, uint8_t out[32]) {
+    Ctx* c = as_ctx(p);
+    if (!c || !out) return arg_error("null");
+    if (rt_set_device(c->device)) return BBS_E_CUDA;
+    TRY(rt_d2h(out, c->domain.p, 32, c->stream));
+    return rt_sync(c->stream);
+}
+
+uint64_t bbs_ctx_launch_count(bbs_ctx* p) { return p ? as_ctx(p)->launches : 0; }
+
+int bbs_msg_to_scalars(bbs_ctx* p, size_t count, const uint8_t* msgs, const uint64_t* off, uint8_t* out) {
+    Ctx* c = as_ctx(p);
+    if (count && (!off || !out)) return arg_error("null");
+    if (!count) return BBS_OK;
+    DISPATCH(c, msg_to_scalars(c, count, msgs, off, out));
+}
+int bbs_core_verify_batch(bbs_ctx* p, size_t n, const uint8_t* sigs, const uint8_t* scalars, uint32_t n_msgs, uint8_t* status) {
+    Ctx* c = as_ctx(p);
+    if (!n) return BBS_OK;
+    if (!sigs || !status || (n_msgs && !scalars)) return arg_error("null");
+    DISPATCH(c, core_verify(c, n, sigs, scalars, n_msgs, status));
+}
+int bbs_verify_batch(bbs_ctx* p, size_t n, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off, uint32_t n_msgs,
+                     uint8_t* status) {
+    Ctx* c = as_ctx(p);
+    if (!n) return BBS_OK;
+    if (!sigs || !status || !off) return arg_error("null");
+    DISPATCH(c, verify(c, n, sigs, msgs, off, n_msgs, status));
+}
+int bbs_core_sign_batch(bbs_ctx* p, const uint8_t sk[32], size_t n, const uint8_t* scalars, uint32_t n_msgs,
+                        uint8_t* sigs_out, uint8_t* b_out, uint8_t* status) {
+    Ctx* c = as_ctx(p);
+    if (!n) return BBS_OK;
+    if (!sk || !sigs_out || !status || (n_msgs && !scalars)) return arg_error("null");
+    DISPATCH(c, core_sign(c, sk, n, scalars, n_msgs, sigs_out, b_out, status));
+}
+int bbs_sign_batch(bbs_ctx* p, const uint8_t sk[32], size_t n, const uint8_t* msgs, const uint64_t* off, uint32_t n_msgs,
+                   uint8_t* sigs_out, uint8_t* b_out, uint8_t* status) {
+    Ctx* c = as_ctx(p);
+    if (!n) return BBS_OK;
+    if (!sk || !sigs_out || !status || !off) return arg_error("null");
+    DISPATCH(c, sign(c, sk, n, msgs, off, n_msgs, sigs_out, b_out, status));
+}
+int bbs_core_proof_verify_batch(bbs_ctx* p, size_t n, const uint8_t* proofs, const uint8_t* commit,
+                                const uint64_t* commit_off, const uint32_t* idx, const uint8_t* dis_scalars,
+                                const uint64_t* dis_off, const uint8_t* ph, size_t ph_len, uint8_t* status) {
+    Ctx* c = as_ctx(p);
+    if (!n) return BBS_OK;
+    if (!proofs || !commit_off || !dis_off || !status) return arg_error("null");
+    DISPATCH(c, core_proof_verify(c, n, proofs, commit, commit_off, idx, dis_scalars, dis_off, ph, ph_len, status));
+}
+int bbs_proof_verify_batch(bbs_ctx* p, size_t n, const uint8_t* proofs, const uint8_t* commit, const uint64_t* commit_off,
+                           const uint32_t* idx, const uint8_t* dis_msgs, const uint64_t* dis_msg_off,
+                           const uint64_t* dis_off, const uint8_t* ph, size_t ph_len, uint8_t* status) {
+    Ctx* c = as_ctx(p);
+    if (!n) return BBS_OK;
+    if (!proofs || !commit_off || !dis_off || !dis_msg_off || !status) return arg_error("null");
+    DISPATCH(c, proof_verify(c, n, proofs, commit, commit_off, idx, dis_msgs, dis_msg_off, dis_off, ph, ph_len, status));
+}
+
+int bbs_msg_to_scalars_dev(bbs_ctx* p, size_t count, const uint8_t* d_msgs, const uint64_t* d_off, uint8_t* d_out, void* stream) {
+    Ctx* c = as_ctx(p);
+    DISPATCH(c, h2s_dev(c, count, d_msgs, d_off, d_out, (rt_stream_t)stream));
+}
+int bbs_core_verify_batch_dev(bbs_ctx* p, size_t n, const uint8_t* d_sigs, const uint8_t* d_scalars, uint32_t n_msgs,
+                              uint8_t* d_status, void* stream) {
+    Ctx* c = as_ctx(p);
+    DISPATCH(c, core_verify_dev(c, n, d_sigs, d_scalars, n_msgs, d_status, (rt_stream_t)stream));
+}
+int bbs_verify_batch_dev(bbs_ctx* p, size_t n, const uint8_t* d_sigs, const uint8_t* d_msgs, const uint64_t* d_off,
+                         uint32_t n_msgs, uint8_t* d_status, void* stream) {
+    Ctx* c = as_ctx(p);
+    DISPATCH(c, verify_dev(c, n, d_sigs, d_msgs, d_off, n_msgs, d_status, (rt_stream_t)stream));
+}
+int bbs_core_sign_batch_dev(bbs_ctx* p, const uint8_t sk[32], size_t n, const uint8_t* d_scalars, uint32_t n_msgs,
+                            uint8_t* d_sigs, uint8_t* d_b, uint8_t* d_status, void* stream) {
+    Ctx* c = as_ctx(p);
+    if (!sk) return arg_error("null");
+    DISPATCH(c, core_sign_dev(c, sk, n, d_scalars, n_msgs, d_sigs, d_b, d_status, (rt_stream_t)stream));
+}
+int bbs_core_proof_verify_batch_dev(bbs_ctx* p, size_t n, const uint8_t* d_proofs, const uint8_t* d_commit,
+                                    const uint64_t* d_commit_off, const uint32_t* d_idx, const uint8_t* d_dis_scalars,
+                                    const uint64_t* d_dis_off, const uint8_t* d_ph, size_t ph_len, uint8_t* d_status,
+                                    void* stream) {
+    Ctx* c = as_ctx(p);
+    DISPATCH(c, core_proof_verify_dev(c, n, d_proofs, d_commit, d_commit_off, d_idx, d_dis_scalars, d_dis_off, d_ph,
+                                      ph_len, d_status, (rt_stream_t)stream));
+}
+
+int bbs_selftest_field(int curve, int device, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    if (rt_set_device(device)) return BBS_E_CUDA;
+    if (curve == BBS_CURVE_BLS12_381) return selftest_field<Bls>(op, n, a, b, out);
+    if (curve == BBS_CURVE_BN254) return selftest_field<Bn>(op, n, a, b, out);
+    return arg_error("unknown curve id");
+}
+int bbs_selftest_g1_mul(int curve, int device, size_t n, const uint8_t* pts, const uint8_t* sc, uint8_t* out) {
+    if (rt_set_device(device)) return BBS_E_CUDA;
+    if (rt_set_stack(48 * 1024)) return BBS_E_CUDA;
+    if (curve == BBS_CURVE_BLS12_381) return selftest_g1_mul<Bls>(n, pts, sc, out);
+    if (curve == BBS_CURVE_BN254) return selftest_g1_mul<Bn>(n, pts, sc, out);
+    return arg_error("unknown curve id");
+}
+int bbs_selftest_pairing(int curve, int device, size_t n, const uint8_t* p_points, const uint8_t* r_points,
+                         const uint8_t* q_point, uint8_t* status) {
+    if (rt_set_device(device)) return BBS_E_CUDA;
+    if (rt_set_stack(48 * 1024)) return BBS_E_CUDA;
+    if (curve == BBS_CURVE_BLS12_381) return selftest_pairing<Bls>(n, p_points, r_points, q_point, status);
+    if (curve == BBS_CURVE_BN254) return selftest_pairing<Bn>(n, p_points, r_points, q_point, status);
+    return arg_error("unknown curve id");
+}
+
+}  // extern "C"

@@ -1,0 +1,377 @@
+// Fixed-width Montgomery arithmetic on 32-bit limbs for the four prime fields of the path:
+// BLS12-381 Fp (12 limbs) / Fr (8), BN254 Fp (8) / Fr (8).  Replaces ark-ff `Fp<MontBackend>` under
+// every hot-path row of SURVEY 8a (a10).  R = 2^(32N), the same Montgomery radix arkworks uses for
+// its 64-bit limbs, so values are interchangeable limb-for-limb.
+//
+// Device code: each row of the operand-scanning product is a pure mad.lo.cc / madc.hi.cc chain
+// (gen_mont_asm.cuh), i.e. carries ride on the IMAD pipe; no separate carry instructions.
+// Host code (`BBS_HOSTSIM`, tests only): portable 64-bit fallback of the same functions so the whole
+// pipeline can be debugged in a container without a GPU.  The shipped library is CUDA-only.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(__CUDACC__)
+#define BBS_HD __host__ __device__ __forceinline__
+#define BBS_HDN __host__ __device__ __noinline__
+#else
+#define BBS_HD inline
+#define BBS_HDN
+#ifndef __constant__
+#define __constant__
+#endif
+#endif
+
+#if defined(__CUDACC__)
+#define BBS_CONST_ARRAY(name, n, ...)                                   \
+    static __constant__ uint32_t name##_dev[n] = {__VA_ARGS__};          \
+    static const uint32_t name##_host[n] = {__VA_ARGS__};                \
+    BBS_HD const uint32_t* name() {                                      \
+        return BBS_SELECT_DEV(name##_dev, name##_host);                  \
+    }
+#ifdef __CUDA_ARCH__
+#define BBS_SELECT_DEV(d, h) (d)
+#else
+#define BBS_SELECT_DEV(d, h) (h)
+#endif
+#else
+#define BBS_CONST_ARRAY(name, n, ...)                                   \
+    static const uint32_t name##_host[n] = {__VA_ARGS__};                \
+    inline const uint32_t* name() { return name##_host; }
+#endif
+
+#include "gen_constants.cuh"
+#include "gen_mont_asm.cuh"
+
+namespace bbs {
+
+// ---- field parameter packs ---------------------------------------------------------------------
+struct BlsFp {
+    static constexpr int N = 12;
+    static constexpr int BITS = BLS_FP_BITS;
+    static constexpr uint32_t INV = BLS_FP_INV;
+    static BBS_HD const uint32_t* P() { return BLS_FP_P(); }
+    static BBS_HD const uint32_t* ONE() { return BLS_FP_ONE(); }
+    static BBS_HD const uint32_t* R2() { return BLS_FP_R2(); }
+    static BBS_HD const uint32_t* EXP_INV() { return BLS_FP_EXP_INV(); }
+    static BBS_HD const uint32_t* EXP_SQRT() { return BLS_FP_EXP_SQRT(); }
+    static BBS_HD const uint32_t* HALF() { return BLS_FP_HALF(); }
+    static BBS_HD const uint32_t* EXP_PM3D4() { return BLS_FP_EXP_PM3D4(); }
+};
+struct BlsFr {
+    static constexpr int N = 8;
+    static constexpr int BITS = BLS_FR_BITS;
+    static constexpr uint32_t INV = BLS_FR_INV;
+    static BBS_HD const uint32_t* P() { return BLS_FR_P(); }
+    static BBS_HD const uint32_t* ONE() { return BLS_FR_ONE(); }
+    static BBS_HD const uint32_t* R2() { return BLS_FR_R2(); }
+    static BBS_HD const uint32_t* EXP_INV() { return BLS_FR_EXP_INV(); }
+};
+struct BnFp {
+    static constexpr int N = 8;
+    static constexpr int BITS = BN_FP_BITS;
+    static constexpr uint32_t INV = BN_FP_INV;
+    static BBS_HD const uint32_t* P() { return BN_FP_P(); }
+    static BBS_HD const uint32_t* ONE() { return BN_FP_ONE(); }
+    static BBS_HD const uint32_t* R2() { return BN_FP_R2(); }
+    static BBS_HD const uint32_t* EXP_INV() { return BN_FP_EXP_INV(); }
+    static BBS_HD const uint32_t* EXP_SQRT() { return BN_FP_EXP_SQRT(); }
+    static BBS_HD const uint32_t* HALF() { return BN_FP_HALF(); }
+    static BBS_HD const uint32_t* EXP_PM3D4() { return BN_FP_EXP_PM3D4(); }
+};
+struct BnFr {
+    static constexpr int N = 8;
+    static constexpr int BITS = BN_FR_BITS;
+    static constexpr uint32_t INV = BN_FR_INV;
+    static BBS_HD const uint32_t* P() { return BN_FR_P(); }
+    static BBS_HD const uint32_t* ONE() { return BN_FR_ONE(); }
+    static BBS_HD const uint32_t* R2() { return BN_FR_R2(); }
+    static BBS_HD const uint32_t* EXP_INV() { return BN_FR_EXP_INV(); }
+};
+
+// ---- raw multi-limb helpers ----------------------------------------------------------------------
+template <int N>
+BBS_HD uint32_t bn_add(uint32_t* r, const uint32_t* a, const uint32_t* b) {  // returns carry
+#ifdef __CUDA_ARCH__
+    uint32_t x[N], y[N], z[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) { x[i] = a[i]; y[i] = b[i]; }
+    uint32_t c = bbs_addn<N>(z, x, y);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = z[i];
+    return c;
+#else
+    uint64_t c = 0;
+    for (int i = 0; i < N; i++) {
+        c += (uint64_t)a[i] + b[i];
+        r[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    return (uint32_t)c;
+#endif
+}
+
+template <int N>
+BBS_HD uint32_t bn_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {  // returns borrow mask
+#ifdef __CUDA_ARCH__
+    uint32_t x[N], y[N], z[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) { x[i] = a[i]; y[i] = b[i]; }
+    uint32_t c = bbs_subn<N>(z, x, y);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = z[i];
+    return c;
+#else
+    int64_t c = 0;
+    for (int i = 0; i < N; i++) {
+        c += (int64_t)a[i] - (int64_t)b[i];
+        r[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    return c ? 0xffffffffu : 0u;
+#endif
+}
+
+template <int N>
+BBS_HD bool bn_is_zero(const uint32_t* a) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) o |= a[i];
+    return o == 0;
+}
+
+template <int N>
+BBS_HD bool bn_eq(const uint32_t* a, const uint32_t* b) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) o |= a[i] ^ b[i];
+    return o == 0;
+}
+
+template <int N>
+BBS_HD void bn_copy(uint32_t* r, const uint32_t* a) {
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = a[i];
+}
+
+template <int N>
+BBS_HD void bn_zero(uint32_t* r) {
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = 0;
+}
+
+// a > b as little-endian integers
+template <int N>
+BBS_HD bool bn_gt(const uint32_t* a, const uint32_t* b) {
+    uint32_t t[N];
+    return bn_sub<N>(t, b, a) != 0;  // b - a borrows  <=>  a > b
+}
+
+// ---- modular add / sub / neg (canonical representatives in [0, p)) ------------------------------
+template <class F>
+BBS_HD void fe_add(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    constexpr int N = F::N;
+    uint32_t s[N], d[N];
+    bn_add<N>(s, a, b);  // 2p < 2^(32N) for every modulus here: no carry out
+    uint32_t borrow = bn_sub<N>(d, s, F::P());
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = borrow ? s[i] : d[i];
+}
+
+template <class F>
+BBS_HD void fe_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    constexpr int N = F::N;
+    uint32_t d[N], s[N];
+    uint32_t borrow = bn_sub<N>(d, a, b);
+    bn_add<N>(s, d, F::P());
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = borrow ? s[i] : d[i];
+}
+
+template <class F>
+BBS_HD void fe_neg(uint32_t* r, const uint32_t* a) {
+    constexpr int N = F::N;
+    uint32_t d[N];
+    bool z = bn_is_zero<N>(a);
+    bn_sub<N>(d, F::P(), a);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = z ? 0u : d[i];
+}
+
+template <class F>
+BBS_HD void fe_dbl(uint32_t* r, const uint32_t* a) { fe_add<F>(r, a, a); }
+
+// ---- Montgomery product ---------------------------------------------------------------------------
+// CIOS, one limb of b per row.  Bound: with a, b < p and 2p < R the running value stays < 2p, so the
+// accumulator needs N+1 words and the result needs one conditional subtraction.
+template <class F>
+BBS_HD void fe_mul_inl(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    constexpr int N = F::N;
+#ifdef __CUDA_ARCH__
+    uint32_t A[N], B[N], M[N], t[N + 1];
+    const uint32_t* pm = F::P();
+#pragma unroll
+    for (int i = 0; i < N; i++) { A[i] = a[i]; B[i] = b[i]; M[i] = pm[i]; }
+#pragma unroll
+    for (int i = 0; i <= N; i++) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        bbs_mad_even<N>(t, A, B[i]);
+        bbs_mad_odd<N>(t, A, B[i]);
+        uint32_t m = t[0] * F::INV;
+        bbs_mad_even<N>(t, M, m);
+        bbs_mad_odd<N>(t, M, m);
+#pragma unroll
+        for (int j = 0; j < N; j++) t[j] = t[j + 1];
+        t[N] = 0;
+    }
+    uint32_t d[N];
+    uint32_t borrow = bbs_subn<N>(d, t, M);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = borrow ? t[i] : d[i];
+#else
+    uint32_t t[N + 2];
+    const uint32_t* pm = F::P();
+    for (int i = 0; i < N + 2; i++) t[i] = 0;
+    for (int i = 0; i < N; i++) {
+        uint64_t c = 0;
+        for (int j = 0; j < N; j++) {
+            c += (uint64_t)a[j] * b[i] + t[j];
+            t[j] = (uint32_t)c;
+            c >>= 32;
+        }
+        c += t[N];
+        t[N] = (uint32_t)c;
+        t[N + 1] = (uint32_t)(c >> 32);
+        uint32_t m = t[0] * F::INV;
+        c = ((uint64_t)m * pm[0] + t[0]) >> 32;
+        for (int j = 1; j < N; j++) {
+            c += (uint64_t)m * pm[j] + t[j];
+            t[j - 1] = (uint32_t)c;
+            c >>= 32;
+        }
+        c += t[N];
+        t[N - 1] = (uint32_t)c;
+        t[N] = t[N + 1] + (uint32_t)(c >> 32);
+    }
+    uint32_t d[N];
+    uint32_t borrow = bn_sub<N>(d, t, pm);
+    bool ge = (t[N] != 0) || !borrow;
+    for (int i = 0; i < N; i++) r[i] = ge ? d[i] : t[i];
+#endif
+}
+
+// Out-of-line instance: the 1-thread-per-item kernels call this so code size stays bounded
+// (one ~0.7k-instruction body per field instead of one per call site).
+template <class F>
+BBS_HDN void fe_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    fe_mul_inl<F>(r, a, b);
+}
+
+template <class F>
+BBS_HD void fe_sqr(uint32_t* r, const uint32_t* a) { fe_mul<F>(r, a, a); }
+
+template <class F>
+BBS_HD void fe_to_mont(uint32_t* r, const uint32_t* a) { fe_mul<F>(r, a, F::R2()); }
+
+template <class F>
+BBS_HD void fe_from_mont(uint32_t* r, const uint32_t* a) {
+    uint32_t one[F::N];
+    bn_zero<F::N>(one);
+    one[0] = 1;
+    fe_mul<F>(r, a, one);
+}
+
+template <class F>
+BBS_HD void fe_set_one(uint32_t* r) { bn_copy<F::N>(r, F::ONE()); }
+
+// r = a^e, e given as little-endian 32-bit limbs (a public constant: uniform control flow across the
+// warp); fixed 4-bit windows, MSB first.
+template <class F>
+BBS_HD void fe_pow(uint32_t* r, const uint32_t* a, const uint32_t* e, int ebits) {
+    constexpr int N = F::N;
+    uint32_t tab[16][N];
+    fe_set_one<F>(tab[0]);
+    bn_copy<N>(tab[1], a);
+    for (int i = 2; i < 16; i++) fe_mul<F>(tab[i], tab[i - 1], a);
+    uint32_t acc[N];
+    int top = (ebits + 3) / 4 - 1;
+    {
+        uint32_t d = (e[(top * 4) >> 5] >> ((top * 4) & 31)) & 15;
+        bn_copy<N>(acc, tab[d]);
+    }
+    for (int w = top - 1; w >= 0; w--) {
+        fe_sqr<F>(acc, acc);
+        fe_sqr<F>(acc, acc);
+        fe_sqr<F>(acc, acc);
+        fe_sqr<F>(acc, acc);
+        uint32_t d = (e[(w * 4) >> 5] >> ((w * 4) & 31)) & 15;
+        if (d) fe_mul<F>(acc, acc, tab[d]);
+    }
+    bn_copy<N>(r, acc);
+}
+
+// Fermat inversion; inv(0) = 0 (matches the `inv0` convention; callers test for zero where it matters)
+template <class F>
+BBS_HD void fe_inv(uint32_t* r, const uint32_t* a) { fe_pow<F>(r, a, F::EXP_INV(), F::BITS); }
+
+// square root for p = 3 mod 4; returns false when a is a non-residue
+template <class F>
+BBS_HD bool fe_sqrt(uint32_t* r, const uint32_t* a) {
+    uint32_t s[F::N], q[F::N];
+    fe_pow<F>(s, a, F::EXP_SQRT(), F::BITS - 1);
+    fe_sqr<F>(q, s);
+    bool ok = bn_eq<F::N>(q, a);
+    bn_copy<F::N>(r, s);
+    return ok;
+}
+
+// canonical(a) > (p-1)/2   (the "y is lexicographically largest / negative" flag of both encodings)
+template <class F>
+BBS_HD bool fe_is_high(const uint32_t* a_mont) {
+    uint32_t c[F::N];
+    fe_from_mont<F>(c, a_mont);
+    return bn_gt<F::N>(c, F::HALF());
+}
+
+// ---- byte <-> limb conversion (canonical, non-Montgomery) -----------------------------------------
+template <int N>
+BBS_HD void limbs_from_be(uint32_t* r, const uint8_t* b) {  // 4N big-endian bytes
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const uint8_t* q = b + 4 * (N - 1 - i);
+        r[i] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+    }
+}
+template <int N>
+BBS_HD void limbs_to_be(uint8_t* b, const uint32_t* a) {
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        uint8_t* q = b + 4 * (N - 1 - i);
+        q[0] = (uint8_t)(a[i] >> 24); q[1] = (uint8_t)(a[i] >> 16); q[2] = (uint8_t)(a[i] >> 8); q[3] = (uint8_t)a[i];
+    }
+}
+template <int N>
+BBS_HD void limbs_from_le(uint32_t* r, const uint8_t* b) {
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const uint8_t* q = b + 4 * i;
+        r[i] = ((uint32_t)q[3] << 24) | ((uint32_t)q[2] << 16) | ((uint32_t)q[1] << 8) | q[0];
+    }
+}
+template <int N>
+BBS_HD void limbs_to_le(uint8_t* b, const uint32_t* a) {
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        uint8_t* q = b + 4 * i;
+        q[0] = (uint8_t)a[i]; q[1] = (uint8_t)(a[i] >> 8); q[2] = (uint8_t)(a[i] >> 16); q[3] = (uint8_t)(a[i] >> 24);
+    }
+}
+
+// canonical limbs < p ?
+template <class F>
+BBS_HD bool fe_is_canonical(const uint32_t* a) {
+    return bn_gt<F::N>(F::P(), a);
+}
+
+}  // namespace bbs

@@ -1,0 +1,351 @@
+// Per-item bodies of every kernel on the path, written as plain functions of (args, item index) so the
+// same source runs as a CUDA kernel (one thread per item; `launch.cuh`) and, in tests only, as a host
+// loop (BBS_HOSTSIM) for GPU-less debugging.
+//
+//   ctx creation : ctx_decode_item, ctx_domain_item, ctx_table_item, ctx_lines_item
+//   hashing      : h2s_item                      (msg_to_scalars, interface_utilities.rs:76-88)
+//   verify       : verify_g1_item -> pairing_item (core_verify, verify.rs:53-93)
+//   sign         : sign_item                      (core_sign, sign.rs:63-133)
+//   proof verify : proof_g1_item -> pairing_item  (core_proof_verify, proof_verify.rs:64-188)
+#pragma once
+#include "g2.cuh"
+#include "sha256.cuh"
+
+namespace bbs {
+
+// per-item status bytes (include/bbs_b200.h)
+enum : uint8_t {
+    ST_REJECT = 0,            // Ok(false)
+    ST_ACCEPT = 1,            // Ok(true)
+    ST_ERR_MSG_GEN_LEN = 2,   // InvalidMessageAndGeneratorsLength (sign.rs:26, proof_gen.rs:66)
+    ST_ERR_DISCLOSED_INDEX = 3,  // InvalidDisclosedIndex (proof_gen.rs:62-65)
+    ST_ERR_IDX_MSG_LEN = 4,   // InvalidIndicesAndMessagesLength (proof_gen.rs:72-74)
+    ST_ERR_MALFORMED = 5,     // undecodable point / non-canonical scalar / the reference's panic cases
+};
+
+constexpr int TAB_WINDOWS = 32;   // 8-bit windows over a 256-bit scalar
+constexpr int TAB_ENTRIES = 255;  // digits 1..255
+constexpr int MAX_L = 256;
+
+// Read-only per-issuer state living in device memory (built once by bbs_ctx_create)
+struct CtxView {
+    uint32_t L;               // message generators H_1..H_L
+    uint32_t w_inf;           // public key is the identity
+    uint32_t k_inf;           // K = P1 + Q1*domain is the identity
+    uint32_t dst_h2s_len, dst_map_len;
+    const uint8_t* dst_h2s;   // api_id || "H2S_"
+    const uint8_t* dst_map;   // api_id || "MAP_MSG_TO_SCALAR_AS_HASH_"
+    const uint32_t* gens;     // (L+1) affine points: Q1, H_1..H_L
+    const uint32_t* W;        // affine G2 public key
+    const uint32_t* K;        // affine K
+    const uint32_t* domain;   // canonical limbs (8)
+    const uint32_t* tab;      // fixed-base tables: generator index g in [0, L] (0 = K, j = H_j)
+    const uint32_t* lines;    // line table for (W, BP2)
+};
+
+// ---- ctx creation ----------------------------------------------------------------------------------
+struct CtxDecodeArgs {
+    const uint8_t* gens_comp; const uint8_t* pk_comp; uint32_t n_gens;
+    uint32_t* gens; uint32_t* W; uint32_t* status;   // status[j]: PT_* per generator, status[n_gens]: pk
+};
+template <class C> BBS_HD void ctx_decode_item(const CtxDecodeArgs& a, uint32_t i) {
+    if (i < a.n_gens) a.status[i] = g1_decompress<C>(a.gens + i * G1A, a.gens_comp + i * C::G1_BYTES);
+    else a.status[i] = g2_decompress<C>(a.W, a.pk_comp);
+}
+
+struct CtxDomainArgs {
+    const uint8_t* pk_comp; const uint8_t* gens_comp; uint32_t L;
+    const uint8_t* api_id; uint32_t api_id_len; const uint8_t* header; uint32_t header_len;
+    const uint8_t* dst_h2s; uint32_t dst_h2s_len;
+    const uint32_t* gens; uint32_t* domain; uint32_t* K; uint32_t* k_inf;
+};
+// calculate_domain (core_utilities.rs:24-63) + K = P1 + Q1*domain (verify.rs:81-82)
+template <class C> BBS_HD void ctx_domain_item(const CtxDomainArgs& a, uint32_t) {
+    Xmd48 x;
+    x.begin();
+    x.s.update(a.pk_comp, C::G2_BYTES);
+    x.s.put_be64(a.L);
+    x.s.update(a.gens_comp, (a.L + 1) * C::G1_BYTES);
+    x.s.update(a.api_id, a.api_id_len);
+    x.s.put_be64(a.header_len);
+    x.s.update(a.header, a.header_len);
+    uint32_t okm[12], dom[8];
+    x.finish(a.dst_h2s, a.dst_h2s_len, okm);
+    okm48_to_scalar<typename C::Fr>(dom, okm);
+    bn_copy<8>(a.domain, dom);
+    uint32_t acc[G1J], p1[G1J];
+    g1_mul_affine<C>(acc, a.gens, dom, 256);
+    g1_from_affine<C>(p1, C::P1());
+    g1_add<C>(acc, acc, p1);
+    *a.k_inf = g1_to_affine<C>(a.K, acc) ? 0u : 1u;
+}
+
+struct CtxTableArgs { const uint32_t* K; const uint32_t* gens; uint32_t* tab; };
+// entry (g, w, d) = (d * 2^(8w)) * base_g in affine form
+template <class C> BBS_HD void ctx_table_item(const CtxTableArgs& a, uint32_t i) {
+    uint32_t d = i % TAB_ENTRIES + 1, w = (i / TAB_ENTRIES) % TAB_WINDOWS, g = i / (TAB_ENTRIES * TAB_WINDOWS);
+    const uint32_t* base = g == 0 ? a.K : a.gens + g * G1A;
+    uint32_t k[9];
+    for (int j = 0; j < 9; j++) k[j] = 0;
+    k[w >> 2] = d << (8 * (w & 3));
+    uint32_t acc[G1J];
+    g1_mul_affine<C>(acc, base, k, 8 * (int)w + 8);
+    g1_to_affine<C>(a.tab + (size_t)i * G1A, acc);
+}
+
+struct CtxLinesArgs { const uint32_t* W; uint32_t w_inf; uint32_t* lines; };
+template <class C> BBS_HD void ctx_lines_item(const CtxLinesArgs& a, uint32_t i) {
+    if (i == 0) { if (!a.w_inf) g2_precompute_lines<C>(a.lines, a.W, 0); }
+    else g2_precompute_lines<C>(a.lines, C::G2(), 1);
+}
+
+// ---- msg_to_scalars ----------------------------------------------------------------------------------
+struct H2sArgs {
+    const uint8_t* msgs; const uint64_t* offsets;   // message t = msgs[offsets[t] .. offsets[t+1])
+    const uint8_t* dst; uint32_t dst_len;
+    uint8_t* out;                                   // 32-byte little-endian scalars
+};
+template <class C> BBS_HD void h2s_item(const H2sArgs& a, uint32_t t) {
+    uint32_t s[8];
+    uint64_t b = a.offsets[t], e = a.offsets[t + 1];
+    hash_to_scalar<typename C::Fr>(s, a.msgs + b, (uint32_t)(e - b), a.dst, a.dst_len);
+    limbs_to_le<8>(a.out + (size_t)t * 32, s);
+}
+
+// ---- fixed-base MSM over the window tables -------------------------------------------------------------
+// acc += s * base_g, s canonical limbs (8)
+template <class C> BBS_HD void tab_accumulate(uint32_t* acc, const uint32_t* tab, uint32_t g, const uint32_t* s) {
+    const uint32_t* tg = tab + (size_t)g * TAB_WINDOWS * TAB_ENTRIES * G1A;
+    for (int w = 0; w < TAB_WINDOWS; w++) {
+        uint32_t d = (s[w >> 2] >> (8 * (w & 3))) & 0xff;
+        if (d) {
+            uint32_t e[G1A];
+            const uint32_t* src = tg + ((size_t)w * TAB_ENTRIES + (d - 1)) * G1A;
+            for (int j = 0; j < G1A; j++) e[j] = src[j];
+            g1_add_mixed<C>(acc, acc, e);
+        }
+    }
+}
+
+// pair-argument record handed from the G1 kernels to the pairing kernel
+#define PAIR_WORDS (6 * C::Fp::N)
+enum : uint32_t { FL_SKIP0 = 1, FL_SKIP1 = 2, FL_DONE = 4 };   // FL_DONE: status already final, no pairing
+
+// ---- core_verify, G1 half ------------------------------------------------------------------------------
+struct VerifyG1Args {
+    CtxView ctx;
+    const uint8_t* sigs;       // n x (G1 compressed || LE32 e)   (ark CanonicalSerialize of Signature, sign.rs:18-22)
+    const uint8_t* scalars;    // n x n_msgs x LE32
+    uint32_t n_msgs;
+    uint32_t* pair; uint32_t* flags; uint8_t* status;
+};
+template <class C> BBS_HD void verify_g1_item(const VerifyG1Args& a, uint32_t i) {
+    const CtxView& cx = a.ctx;
+    if (a.n_msgs != cx.L) { a.status[i] = ST_ERR_MSG_GEN_LEN; a.flags[i] = FL_DONE; return; }   // verify.rs:68-71
+    const uint8_t* sig = a.sigs + (size_t)i * (C::G1_BYTES + 32);
+    uint32_t A[G1A], e[8];
+    int pa = g1_decompress<C>(A, sig);
+    bool ok = pa != PT_BAD && fr_from_le32<C>(e, sig + C::G1_BYTES);
+    // B = P1 + Q1*domain + sum H_j m_j  (verify.rs:81-86), K = P1 + Q1*domain hoisted into the context
+    uint32_t B[G1J];
+    if (cx.k_inf) g1_set_inf<C>(B); else g1_from_affine<C>(B, cx.K);
+    const uint8_t* sc = a.scalars + (size_t)i * a.n_msgs * 32;
+    for (uint32_t j = 0; j < a.n_msgs && ok; j++) {
+        uint32_t m[8];
+        ok = fr_from_le32<C>(m, sc + j * 32);
+        if (ok) tab_accumulate<C>(B, cx.tab, j + 1, m);
+    }
+    if (!ok) { a.status[i] = ST_ERR_MALFORMED; a.flags[i] = FL_DONE; return; }
+    // e(A, W + e BP2) e(B, -BP2) == 1  <=>  e(A, W) e(eA - B, BP2) == 1   (SURVEY 8a note (i))
+    uint32_t Cc[G1J];
+    g1_neg<C>(Cc, B);
+    if (pa == PT_OK) {
+        uint32_t eA[G1J];
+        g1_mul_affine<C>(eA, A, e, C::Fr::BITS);
+        g1_add<C>(Cc, Cc, eA);
+    }
+    uint32_t* pr = a.pair + (size_t)i * PAIR_WORDS;
+    bn_copy<2 * C::Fp::N>(pr, A); fe_set_one<typename C::Fp>(pr + 2 * FPN);
+    g1_to_line_arg<C>(pr + 3 * FPN, Cc);
+    uint32_t fl = 0;
+    if (pa == PT_INF || cx.w_inf) fl |= FL_SKIP0;
+    if (g1_is_inf<C>(Cc)) fl |= FL_SKIP1;
+    a.flags[i] = fl;
+}
+
+// ---- pairing half (shared by verify and proof verify) ----------------------------------------------------
+struct PairingArgs { const uint32_t* lines; const uint32_t* pair; const uint32_t* flags; uint8_t* status; };
+template <class C> BBS_HD void pairing_item(const PairingArgs& a, uint32_t i) {
+    uint32_t fl = a.flags[i];
+    if (fl & FL_DONE) return;
+    uint32_t P[PAIR_WORDS], f[F12N];
+    const uint32_t* src = a.pair + (size_t)i * PAIR_WORDS;
+    for (int j = 0; j < PAIR_WORDS; j++) P[j] = src[j];
+    miller2<C>(f, a.lines, P, (fl & FL_SKIP0) != 0, P + 3 * FPN, (fl & FL_SKIP1) != 0);
+    a.status[i] = final_exp_is_one<C>(f) ? ST_ACCEPT : ST_REJECT;
+}
+
+// ---- core_sign -----------------------------------------------------------------------------------------
+struct SignArgs {
+    CtxView ctx;
+    uint32_t sk[8];            // canonical limbs
+    const uint8_t* scalars; uint32_t n_msgs;
+    uint8_t* sigs_out;         // n x (G1 compressed || LE32 e)
+    uint8_t* b_out;            // optional: n x G1 compressed B (row a7)
+    uint8_t* status;
+};
+template <class C> BBS_HD void sign_item(const SignArgs& a, uint32_t i) {
+    using Fr = typename C::Fr;
+    const CtxView& cx = a.ctx;
+    uint8_t* out = a.sigs_out + (size_t)i * (C::G1_BYTES + 32);
+    if (a.n_msgs != cx.L) { a.status[i] = ST_ERR_MSG_GEN_LEN; return; }            // sign.rs:76-79
+    const uint8_t* sc = a.scalars + (size_t)i * a.n_msgs * 32;
+    // e = H2S(BE(sk) || BE(m_1..m_L) || BE(domain), api_id || "H2S_")   (sign.rs:90-118)
+    Xmd48 x;
+    x.begin();
+    for (int k = 7; k >= 0; k--) x.s.update_words(&a.sk[k], 1);
+    uint32_t B[G1J];
+    if (cx.k_inf) g1_set_inf<C>(B); else g1_from_affine<C>(B, cx.K);
+    bool ok = true;
+    for (uint32_t j = 0; j < a.n_msgs && ok; j++) {
+        uint32_t m[8];
+        ok = fr_from_le32<C>(m, sc + j * 32);
+        if (!ok) break;
+        for (int k = 7; k >= 0; k--) x.s.update_words(&m[k], 1);
+        tab_accumulate<C>(B, cx.tab, j + 1, m);                                      // sign.rs:120-126
+    }
+    if (!ok) { a.status[i] = ST_ERR_MALFORMED; return; }
+    for (int k = 7; k >= 0; k--) x.s.update_words(&cx.domain[k], 1);
+    uint32_t okm[12], e[8], s[8], sm[8];
+    x.finish(cx.dst_h2s, cx.dst_h2s_len, okm);
+    okm48_to_scalar<Fr>(e, okm);
+    fe_add<Fr>(s, a.sk, e);
+    if (bn_is_zero<8>(s)) { a.status[i] = ST_ERR_MALFORMED; return; }               // sign.rs:129 panics
+    fe_to_mont<Fr>(sm, s); fe_inv<Fr>(sm, sm); fe_from_mont<Fr>(s, sm);              // (sk+e)^-1
+    uint32_t Aj[G1J];
+    g1_mul<C>(Aj, B, s, Fr::BITS);                                                   // sign.rs:130
+    g1_compress<C>(out, Aj);
+    limbs_to_le<8>(out + C::G1_BYTES, e);
+    if (a.b_out) g1_compress<C>(a.b_out + (size_t)i * C::G1_BYTES, B);
+    a.status[i] = ST_ACCEPT;
+}
+
+// ---- core_proof_verify, G1 half ---------------------------------------------------------------------------
+struct ProofG1Args {
+    CtxView ctx;
+    const uint8_t* proofs;         // n x (3 G1 compressed || LE32 e^, r1^, r3^, c)
+    const uint8_t* commitments;    // flat LE32 scalars m^_j
+    const uint64_t* commit_off;    // n+1, in scalars
+    const uint32_t* dis_idx;       // flat disclosed indexes
+    const uint8_t* dis_scalars;    // flat LE32 disclosed message scalars (same indexing as dis_idx)
+    const uint64_t* dis_off;       // n+1
+    const uint8_t* ph; uint32_t ph_len;
+    uint32_t* pair; uint32_t* flags; uint8_t* status;
+};
+template <class C> BBS_HD void proof_g1_item(const ProofG1Args& a, uint32_t i) {
+    using F = typename C::Fp;
+    using Fr = typename C::Fr;
+    const CtxView& cx = a.ctx;
+    constexpr int GB = C::G1_BYTES;
+    const uint8_t* pf = a.proofs + (size_t)i * (3 * GB + 128);
+    uint64_t cb = a.commit_off[i], U = a.commit_off[i + 1] - cb;
+    uint64_t db = a.dis_off[i], R = a.dis_off[i + 1] - db;
+    uint64_t L = R + U;
+#define PROOF_FAIL(code) { a.status[i] = (code); a.flags[i] = FL_DONE; return; }
+    // proof_verify.rs:139-150, in the reference's order
+    uint32_t mask[MAX_L / 32];
+    for (int k = 0; k < MAX_L / 32; k++) mask[k] = 0;
+    bool dup = false;
+    for (uint64_t k = 0; k < R; k++) {
+        uint32_t idx = a.dis_idx[db + k];
+        if (idx >= L) PROOF_FAIL(ST_ERR_DISCLOSED_INDEX)
+        if (idx < MAX_L) { dup |= (mask[idx >> 5] >> (idx & 31)) & 1; mask[idx >> 5] |= 1u << (idx & 31); }
+    }
+    if (L != cx.L) PROOF_FAIL(ST_ERR_MSG_GEN_LEN)
+    if (dup) PROOF_FAIL(ST_ERR_MALFORMED)     // the reference indexes out of bounds and panics (proof_verify.rs:179)
+    uint32_t Ab[G1A], Bb[G1A], D[G1A], ecap[8], r1cap[8], r3cap[8], c[8];
+    int pA = g1_decompress<C>(Ab, pf), pB = g1_decompress<C>(Bb, pf + GB), pD = g1_decompress<C>(D, pf + 2 * GB);
+    bool ok = pA != PT_BAD && pB != PT_BAD && pD != PT_BAD;
+    ok = ok && fr_from_le32<C>(ecap, pf + 3 * GB) && fr_from_le32<C>(r1cap, pf + 3 * GB + 32) &&
+         fr_from_le32<C>(r3cap, pf + 3 * GB + 64) && fr_from_le32<C>(c, pf + 3 * GB + 96);
+    if (!ok) PROOF_FAIL(ST_ERR_MALFORMED)
+    // T1 = Bbar*c + Abar*e^ + D*r1^   (proof_verify.rs:163-164), shared doublings
+    uint32_t T1[G1J], T2[G1J];
+    g1_set_inf<C>(T1);
+    for (int b = Fr::BITS - 1; b >= 0; b--) {
+        g1_dbl<C>(T1, T1);
+        if (pB == PT_OK && ((c[b >> 5] >> (b & 31)) & 1)) g1_add_mixed<C>(T1, T1, Bb);
+        if (pA == PT_OK && ((ecap[b >> 5] >> (b & 31)) & 1)) g1_add_mixed<C>(T1, T1, Ab);
+        if (pD == PT_OK && ((r1cap[b >> 5] >> (b & 31)) & 1)) g1_add_mixed<C>(T1, T1, D);
+    }
+    // T2 = Bv*c + D*r3^ + sum H_undisclosed m^   with Bv*c = K*c + sum H_disclosed (c m)   (:165-182)
+    uint32_t cm[8];
+    fe_to_mont<Fr>(cm, c);
+    g1_set_inf<C>(T2);
+    if (!cx.k_inf) tab_accumulate<C>(T2, cx.tab, 0, c);
+    for (uint64_t k = 0; k < R; k++) {
+        uint32_t m[8];
+        if (!fr_from_le32<C>(m, a.dis_scalars + (db + k) * 32)) PROOF_FAIL(ST_ERR_MALFORMED)
+        fe_mul<Fr>(m, m, cm);                                   // c * m_k, canonical
+        tab_accumulate<C>(T2, cx.tab, a.dis_idx[db + k] + 1, m);
+    }
+    {
+        uint64_t k = 0;
+        for (uint32_t j = 0; j < (uint32_t)L; j++) {
+            if ((mask[j >> 5] >> (j & 31)) & 1) continue;
+            uint32_t m[8];
+            if (!fr_from_le32<C>(m, a.commitments + (cb + k) * 32)) PROOF_FAIL(ST_ERR_MALFORMED)
+            tab_accumulate<C>(T2, cx.tab, j + 1, m);
+            k++;
+        }
+    }
+    if (pD == PT_OK) {
+        uint32_t t[G1J];
+        g1_mul_affine<C>(t, D, r3cap, Fr::BITS);
+        g1_add<C>(T2, T2, t);
+    }
+    // challenge (proof_gen.rs:272-328)
+    Xmd48 x;
+    x.begin();
+    x.s.put_be64(R);
+    for (uint64_t k = 0; k < R; k++) {
+        uint32_t m[8];
+        x.s.put_be64(a.dis_idx[db + k]);
+        limbs_from_le<8>(m, a.dis_scalars + (db + k) * 32);
+        for (int q = 7; q >= 0; q--) x.s.update_words(&m[q], 1);
+    }
+    x.s.update(pf, 3 * GB);                                     // canonical encodings of Abar, Bbar, D
+    {
+        // one shared inversion for T1, T2 (Montgomery's trick)
+        bool i1 = g1_is_inf<C>(T1), i2 = g1_is_inf<C>(T2);
+        uint32_t z1[FPN], z2[FPN], zz[FPN], t[FPN], aff[G1A];
+        uint8_t enc[GB];
+        if (i1) fe_set_one<F>(z1); else bn_copy<C::Fp::N>(z1, T1 + 2 * FPN);
+        if (i2) fe_set_one<F>(z2); else bn_copy<C::Fp::N>(z2, T2 + 2 * FPN);
+        fe_mul<F>(zz, z1, z2); fe_inv<F>(zz, zz);
+        fe_mul<F>(t, zz, z2);                                   // 1/z1
+        fe_mul<F>(zz, zz, z1);                                  // 1/z2
+        fe_sqr<F>(z1, t); fe_mul<F>(aff, T1, z1); fe_mul<F>(z1, z1, t); fe_mul<F>(aff + FPN, T1 + FPN, z1);
+        g1_compress_affine<C>(enc, aff, i1); x.s.update(enc, GB);
+        fe_sqr<F>(z2, zz); fe_mul<F>(aff, T2, z2); fe_mul<F>(z2, z2, zz); fe_mul<F>(aff + FPN, T2 + FPN, z2);
+        g1_compress_affine<C>(enc, aff, i2); x.s.update(enc, GB);
+    }
+    for (int q = 7; q >= 0; q--) x.s.update_words(&cx.domain[q], 1);
+    x.s.put_be64(a.ph_len);
+    x.s.update(a.ph, a.ph_len);
+    uint32_t okm[12], c2[8];
+    x.finish(cx.dst_h2s, cx.dst_h2s_len, okm);
+    okm48_to_scalar<Fr>(c2, okm);
+    if (!bn_eq<8>(c2, c)) PROOF_FAIL(ST_REJECT)                 // proof_verify.rs:108-110: no pairing
+    // e(Abar, W) e(Bbar, -BP2) = e(Abar, W) e(-Bbar, BP2)      (proof_verify.rs:112-115)
+    uint32_t* pr = a.pair + (size_t)i * PAIR_WORDS;
+    bn_copy<2 * C::Fp::N>(pr, Ab); fe_set_one<F>(pr + 2 * FPN);
+    bn_copy<C::Fp::N>(pr + 3 * FPN, Bb); fe_neg<F>(pr + 4 * FPN, Bb + FPN); fe_set_one<F>(pr + 5 * FPN);
+    uint32_t fl = 0;
+    if (pA == PT_INF || cx.w_inf) fl |= FL_SKIP0;
+    if (pB == PT_INF) fl |= FL_SKIP1;
+    a.flags[i] = fl;
+#undef PROOF_FAIL
+}
+
+}  // namespace bbs

@@ -1,0 +1,158 @@
+/* bbs_b200.h -- C ABI of the B200-native batch engine for the BBS verification hot path of
+ * hashcloak/bbs_sign (`bbs_plus` crate).  Plain pointers and sizes only; every entry point names the
+ * reference interface (file:line under /root/reference) it replaces for a whole batch.
+ *
+ * The reference has no FFI of its own (pure generic Rust); this header is the boundary the north star
+ * asks for: the Rust side (`verify_batch`, `proof_verify_batch`, `sign_batch`) binds
+ * exactly these symbols.  All arithmetic runs on the GPU (sm_100a); there is no CPU fallback: without a
+ * CUDA device every call returns BBS_E_CUDA.
+ *
+ * Wire formats are the reference's own `CanonicalSerialize` encodings:
+ *   scalar      : 32 bytes little-endian, canonical (< r)
+ *   G1 / G2     : ark `serialize_compressed` -- BLS12-381: 48 / 96 bytes zcash format;
+ *                 BN254: 32 / 64 bytes arkworks SW format
+ *   Signature   : comp(A) || LE32(e)                                   (src/sign.rs:18-22)
+ *   Proof fixed : comp(Abar) || comp(Bbar) || comp(D) || LE32(e^) || LE32(r1^) || LE32(r3^) || LE32(c)
+ *                 (the fixed-size fields of src/proof_gen.rs:29-39; commitments travel separately)
+ *
+ * Threading: one context per (GPU, issuer key, header, L).  Calls on one context are serialized by the
+ * caller; different contexts are independent (one host thread per GPU for multi-GPU sharding).
+ */
+#ifndef BBS_B200_H
+#define BBS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bbs_ctx bbs_ctx;
+
+/* curve_id: the reference's type parameter E (with its C / H / F companions) */
+#define BBS_CURVE_BLS12_381 1 /* Bls12_381 + Bls12381Const + HashToG1Bls12381  (src/constants.rs:63-89) */
+#define BBS_CURVE_BN254 2     /* Bn254 + Bn254Const + HashToG1Bn254            (src/constants.rs:27-61) */
+
+/* return codes */
+#define BBS_OK 0
+#define BBS_E_ARG (-1)       /* null pointer, bad curve id, L too large, undecodable key or generator */
+#define BBS_E_CUDA (-2)      /* CUDA runtime error (no device, out of memory, launch failure) */
+
+/* per-item status bytes */
+#define BBS_ST_REJECT 0              /* Ok(false) */
+#define BBS_ST_ACCEPT 1              /* Ok(true)  */
+#define BBS_ST_ERR_MSG_GEN_LEN 2     /* Err(InvalidMessageAndGeneratorsLength)  src/sign.rs:24-28, src/proof_gen.rs:66 */
+#define BBS_ST_ERR_DISCLOSED_INDEX 3 /* Err(InvalidDisclosedIndex)              src/proof_gen.rs:62-65 */
+#define BBS_ST_ERR_IDX_MSG_LEN 4     /* Err(InvalidIndicesAndMessagesLength)    src/proof_gen.rs:72-74 */
+#define BBS_ST_ERR_MALFORMED 5       /* undecodable point, scalar >= r, or an input on which the reference
+                                        panics (duplicate disclosed index src/proof_verify.rs:179; sk+e == 0
+                                        src/sign.rs:129) */
+
+#define BBS_MAX_MESSAGES 256
+
+/* Sizes of the encodings for a curve (bytes). */
+size_t bbs_g1_bytes(int curve_id);
+size_t bbs_g2_bytes(int curve_id);
+size_t bbs_signature_bytes(int curve_id);   /* g1 + 32 */
+size_t bbs_proof_fixed_bytes(int curve_id); /* 3*g1 + 4*32 */
+
+/* Last error text of the calling thread ("" if none). */
+const char* bbs_last_error(void);
+
+/* Builds the per-issuer state on `device`:
+ *   decodes `pk` (G2) and the `n_generators` = L+1 generators Q1, H_1..H_L (G1) -- the `generators: &[E::G1]`
+ *   argument of core_verify / core_sign / core_proof_verify (src/verify.rs:53-60, src/sign.rs:63-69,
+ *   src/proof_verify.rs:64-73); computes `calculate_domain` (src/utils/core_utilities.rs:24-63) for
+ *   (pk, generators, header, api_id) once; K = P1 + Q1*domain; 8-bit fixed-base window tables for K and
+ *   every H_j; and the Miller-loop line tables of pk and BP2.
+ * `api_id` is the reference's `api_id` (CIPHERSUITE_ID || "H2G_HM2S_" in the interface functions,
+ * arbitrary in the core tests).  Identity pk is allowed (the reference returns Ok(false) for it).
+ * Generators must be non-identity points of G1. */
+int bbs_ctx_create(int curve_id, int device, const uint8_t* pk, const uint8_t* generators, uint32_t n_generators,
+                   const uint8_t* header, size_t header_len, const uint8_t* api_id, size_t api_id_len,
+                   bbs_ctx** out);
+void bbs_ctx_destroy(bbs_ctx* ctx);
+
+/* 32-byte little-endian domain scalar of the context (src/utils/core_utilities.rs:24-63). */
+int bbs_ctx_domain(bbs_ctx* ctx, uint8_t out_le32[32]);
+
+/* ---- host-buffer entry points (copies inside) ---------------------------------------------------- */
+
+/* msg_to_scalars (src/utils/interface_utilities.rs:76-88) for `count` messages:
+ * message t = msgs[offsets[t] .. offsets[t+1]); out = count x LE32. */
+int bbs_msg_to_scalars(bbs_ctx* ctx, size_t count, const uint8_t* msgs, const uint64_t* offsets, uint8_t* out);
+
+/* PublicKey::core_verify (src/verify.rs:53-93) for n signatures, each over `n_msgs` scalar messages.
+ * status[i] in {ACCEPT, REJECT, ERR_MSG_GEN_LEN (n_msgs != L), ERR_MALFORMED}. */
+int bbs_core_verify_batch(bbs_ctx* ctx, size_t n, const uint8_t* sigs, const uint8_t* msg_scalars, uint32_t n_msgs,
+                          uint8_t* status);
+
+/* PublicKey::verify (src/verify.rs:18-50): byte messages; item i owns messages i*n_msgs .. (i+1)*n_msgs-1,
+ * message t = msgs[offsets[t] .. offsets[t+1]), offsets has n*n_msgs + 1 entries. */
+int bbs_verify_batch(bbs_ctx* ctx, size_t n, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* offsets,
+                     uint32_t n_msgs, uint8_t* status);
+
+/* SecretKey::core_sign (src/sign.rs:63-133): sigs_out = n x Signature; b_out (may be NULL) = n x comp(B),
+ * the B point of src/sign.rs:120-126.  The context's pk must be sk*BP2 (the reference derives pk from sk,
+ * src/sign.rs:81).  status[i] = ACCEPT on success. */
+int bbs_core_sign_batch(bbs_ctx* ctx, const uint8_t sk_le32[32], size_t n, const uint8_t* msg_scalars,
+                        uint32_t n_msgs, uint8_t* sigs_out, uint8_t* b_out, uint8_t* status);
+
+/* SecretKey::sign (src/sign.rs:32-60): byte messages, layout as bbs_verify_batch. */
+int bbs_sign_batch(bbs_ctx* ctx, const uint8_t sk_le32[32], size_t n, const uint8_t* msgs, const uint64_t* offsets,
+                   uint32_t n_msgs, uint8_t* sigs_out, uint8_t* b_out, uint8_t* status);
+
+/* core_proof_verify (src/proof_verify.rs:64-116) for n proofs.
+ *   proofs_fixed     : n x Proof-fixed encoding (above)
+ *   commitments      : flat LE32 scalars; proof i owns commitments[commit_off[i] .. commit_off[i+1])
+ *   disclosed_idx    : flat indexes; proof i discloses disclosed_idx[dis_off[i] .. dis_off[i+1])
+ *   disclosed_scalars: flat LE32 message scalars, same indexing as disclosed_idx
+ *   ph               : presentation header shared by the batch
+ * status[i] in {ACCEPT, REJECT, ERR_DISCLOSED_INDEX, ERR_MSG_GEN_LEN, ERR_MALFORMED}. */
+int bbs_core_proof_verify_batch(bbs_ctx* ctx, size_t n, const uint8_t* proofs_fixed, const uint8_t* commitments,
+                                const uint64_t* commit_off, const uint32_t* disclosed_idx,
+                                const uint8_t* disclosed_scalars, const uint64_t* dis_off, const uint8_t* ph,
+                                size_t ph_len, uint8_t* status);
+
+/* proof_verify (src/proof_verify.rs:19-61): disclosed messages as bytes;
+ * disclosed message k (flat numbering, same as disclosed_idx) = dis_msgs[dis_msg_off[k] .. dis_msg_off[k+1]). */
+int bbs_proof_verify_batch(bbs_ctx* ctx, size_t n, const uint8_t* proofs_fixed, const uint8_t* commitments,
+                           const uint64_t* commit_off, const uint32_t* disclosed_idx, const uint8_t* dis_msgs,
+                           const uint64_t* dis_msg_off, const uint64_t* dis_off, const uint8_t* ph, size_t ph_len,
+                           uint8_t* status);
+
+/* ---- device-buffer entry points (no copies; all pointers are device pointers on the context's GPU;
+ *      work is enqueued on `stream` (a cudaStream_t, NULL = default stream) and NOT synchronized) ------ */
+int bbs_msg_to_scalars_dev(bbs_ctx* ctx, size_t count, const uint8_t* d_msgs, const uint64_t* d_offsets,
+                           uint8_t* d_out, void* stream);
+int bbs_core_verify_batch_dev(bbs_ctx* ctx, size_t n, const uint8_t* d_sigs, const uint8_t* d_msg_scalars,
+                              uint32_t n_msgs, uint8_t* d_status, void* stream);
+int bbs_verify_batch_dev(bbs_ctx* ctx, size_t n, const uint8_t* d_sigs, const uint8_t* d_msgs,
+                         const uint64_t* d_offsets, uint32_t n_msgs, uint8_t* d_status, void* stream);
+int bbs_core_sign_batch_dev(bbs_ctx* ctx, const uint8_t sk_le32[32], size_t n, const uint8_t* d_msg_scalars,
+                            uint32_t n_msgs, uint8_t* d_sigs_out, uint8_t* d_b_out, uint8_t* d_status, void* stream);
+int bbs_core_proof_verify_batch_dev(bbs_ctx* ctx, size_t n, const uint8_t* d_proofs_fixed,
+                                    const uint8_t* d_commitments, const uint64_t* d_commit_off,
+                                    const uint32_t* d_disclosed_idx, const uint8_t* d_disclosed_scalars,
+                                    const uint64_t* d_dis_off, const uint8_t* d_ph, size_t ph_len,
+                                    uint8_t* d_status, void* stream);
+
+/* Number of kernels the library has launched on this context since creation (for bench accounting). */
+uint64_t bbs_ctx_launch_count(bbs_ctx* ctx);
+
+/* ---- arithmetic self-test hooks (parity tests of the field / curve layers against the oracle) ------
+ * op: 0 = Fp mul, 1 = Fp add, 2 = Fp sub, 3 = Fp inv, 4 = Fp sqrt (0 if none), 5 = Fr mul, 6 = Fr inv.
+ * a, b, out: n x field-size canonical little-endian values (48 / 32 bytes for Fp, 32 for Fr). */
+int bbs_selftest_field(int curve_id, int device, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out);
+/* out[i] = comp(k_i * P_i) for compressed G1 points and LE32 scalars. */
+int bbs_selftest_g1_mul(int curve_id, int device, size_t n, const uint8_t* points, const uint8_t* scalars,
+                        uint8_t* out);
+/* status[i] = (e(P_i, Q) * e(R_i, BP2) == 1) for compressed G1 points P_i, R_i and one compressed G2 point Q. */
+int bbs_selftest_pairing(int curve_id, int device, size_t n, const uint8_t* p_points, const uint8_t* r_points,
+                         const uint8_t* q_point, uint8_t* status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBS_B200_H */

@@ -1,0 +1,339 @@
+"""Parity cases shared by the GPU tests (`-m gpu`, CUDA library through the C ABI) and the GPU-less
+logic tests (host simulation of the same sources).  Every case compares the library with the oracle
+(oracle/bbs_oracle.py) on the same seeded inputs; the bar is bit-exact bytes / identical status vectors.
+
+The cases mirror the reference's own tests: test_vector.rs (KATs), core_sign_tests.rs, sign_verify_tests.rs,
+proof_verify_tests.rs, bbs_over_bls_tests.rs (round trips and the rejection classes)."""
+import ctypes as C
+import hashlib
+import random
+
+import numpy as np
+
+from bbs_sign_b200 import api as A
+from oracle import bbs_oracle as O
+
+SUITES = {"BLS12_381": (A.BLS12_381, O.BLS12_381), "BN254": (A.BN254, O.BN254)}
+
+MSG = bytes.fromhex("9872ad089e452c7b6e283dfac2a80d58e8d0ff71cc4d5e310a1debdda4a45f02")
+HEADER = bytes.fromhex("11223344556677889900aabbccddeeff")
+PH = bytes.fromhex("bed231d880675ed101ead304512e043ade9958dd0241ea70b4b3957fba941501")
+IRTF_SK = 0x60e55110f76883a13d030b2f6bd11883422d5abde717569fc0731f51237169fc
+IRTF_SIG = bytes.fromhex("84773160b824e194073a57493dac1a20b667af70cd2352d8af241c77658da5253aa8458317cca0eae615690d55b1f271"
+                         "64657dcafee1d5c1973947aa70e2cfbb4c892340be5969920d0916067b4565a0")
+IRTF_B = bytes.fromhex("92d264aed02bf23de022ebe778c4f929fddf829f504e451d011ed89a313b8167ac947332e1648157ceffc6e6e41ab255")
+IRTF_DOMAIN = 0x25d57fab92a8274c68fde5c3f16d4b275e4a156f211ae34b3ab32fbaf506ed5c
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def rng_bytes(seed: str, n: int) -> bytes:
+    out = b""
+    i = 0
+    while len(out) < n:
+        out += hashlib.sha256(f"{seed}/{i}".encode()).digest()
+        i += 1
+    return out[:n]
+
+
+def keypair(ocs, seed=1):
+    km = hashlib.sha256(b"bbs-b200-key" + seed.to_bytes(4, "big")).digest()
+    sk = O.key_gen(ocs, km, b"", b"BBS-SIG-KEYGEN-SALT-")
+    return sk, O.sk_to_pk(ocs, sk)
+
+
+def gens_bytes(ocs, gens):
+    return b"".join(ocs.g1_compress(g) for g in gens)
+
+
+def make_ctx(lib_path, suite, ocs, pk, header, L, api_id=None, gens=None):
+    api_id = ocs.api_id if api_id is None else api_id
+    if gens is None:
+        gens = O.create_generators_cached(ocs, L + 1, api_id)
+    return A.BatchContext(suite, ocs.g2_compress(pk), header, generators=gens_bytes(ocs, gens), api_id=api_id,
+                          lib_path=lib_path), gens
+
+
+# ---------------------------------------------------------------------------------------------------
+def case_field(lib, curve_name, n=64):
+    suite, ocs = SUITES[curve_name]
+    rnd = random.Random(7)
+    for op, mod, width in [(0, ocs.p, ocs.fp_bytes), (1, ocs.p, ocs.fp_bytes), (2, ocs.p, ocs.fp_bytes),
+                           (3, ocs.p, ocs.fp_bytes), (4, ocs.p, ocs.fp_bytes), (5, ocs.r, 32), (6, ocs.r, 32)]:
+        edge = [0, 1, 2, mod - 1, mod - 2, (1 << (8 * width)) % mod, (mod - 1) // 2, (mod + 1) // 2]
+        xs = edge + [rnd.randrange(mod) for _ in range(n - len(edge))]
+        ys = list(reversed(edge)) + [rnd.randrange(mod) for _ in range(n - len(edge))]
+        if op == 4:
+            xs = [x * x % mod for x in xs[: n // 2]] + xs[n // 2:]
+        a = np.frombuffer(b"".join(x.to_bytes(width, "little") for x in xs), dtype=np.uint8)
+        b = np.frombuffer(b"".join(y.to_bytes(width, "little") for y in ys), dtype=np.uint8)
+        out = np.zeros(n * width, dtype=np.uint8)
+        rc = lib.bbs_selftest_field(suite.curve_id, 0, op, n, ptr(a), ptr(b), ptr(out))
+        assert rc == 0, lib.bbs_last_error()
+        got = [int.from_bytes(out[i * width:(i + 1) * width].tobytes(), "little") for i in range(n)]
+        for i, (x, y, g) in enumerate(zip(xs, ys, got)):
+            if op in (0, 5):
+                want = x * y % mod
+            elif op == 1:
+                want = (x + y) % mod
+            elif op == 2:
+                want = (x - y) % mod
+            elif op in (3, 6):
+                want = pow(x, mod - 2, mod)
+            else:
+                s = pow(x, (mod + 1) // 4, mod)
+                want = s if s * s % mod == x else 0
+                if want and g != want:
+                    want = mod - want  # either root is a square root; the kernel returns a^((p+1)/4)
+            assert g == want, (curve_name, op, i, hex(x), hex(y), hex(g), hex(want))
+
+
+def case_g1_mul(lib, curve_name, n=12):
+    suite, ocs = SUITES[curve_name]
+    rnd = random.Random(11)
+    pts, ks = [], []
+    for i in range(n):
+        P = O.ec_mul(ocs.F1, ocs.BP1, rnd.randrange(1, ocs.r))
+        k = [0, 1, 2, ocs.r - 1, ocs.r, (1 << 256) - 1][i] if i < 6 else rnd.randrange(ocs.r)
+        if i == 7:
+            P = None
+        pts.append(P)
+        ks.append(k)
+    a = np.frombuffer(b"".join(ocs.g1_compress(P) for P in pts), dtype=np.uint8)
+    b = np.frombuffer(b"".join(k.to_bytes(32, "little") for k in ks), dtype=np.uint8)
+    out = np.zeros(n * suite.g1_bytes, dtype=np.uint8)
+    rc = lib.bbs_selftest_g1_mul(suite.curve_id, 0, n, ptr(a), ptr(b), ptr(out))
+    assert rc == 0, lib.bbs_last_error()
+    for i in range(n):
+        want = ocs.g1_compress(O.ec_mul(ocs.F1, pts[i], ks[i]))
+        got = out[i * suite.g1_bytes:(i + 1) * suite.g1_bytes].tobytes()
+        assert got == want, (curve_name, i, got.hex(), want.hex())
+
+
+def case_pairing(lib, curve_name):
+    suite, ocs = SUITES[curve_name]
+    rnd = random.Random(5)
+    a_, b_ = rnd.randrange(1, ocs.r), rnd.randrange(1, ocs.r)
+    Q = O.ec_mul(ocs.F2, ocs.BP2, b_)
+    P = O.ec_mul(ocs.F1, ocs.BP1, a_)
+    R_good = O.ec_neg(ocs.F1, O.ec_mul(ocs.F1, ocs.BP1, a_ * b_ % ocs.r))      # e(P,Q) e(R,BP2) = 1
+    R_bad = O.ec_mul(ocs.F1, ocs.BP1, (a_ * b_ + 1) % ocs.r)
+    cases = [(P, R_good, 1), (P, R_bad, 0), (None, R_good, 0), (P, None, 0), (None, None, 1)]
+    p = np.frombuffer(b"".join(ocs.g1_compress(c[0]) for c in cases), dtype=np.uint8)
+    r = np.frombuffer(b"".join(ocs.g1_compress(c[1]) for c in cases), dtype=np.uint8)
+    q = np.frombuffer(ocs.g2_compress(Q), dtype=np.uint8)
+    st = np.full(len(cases), 255, dtype=np.uint8)
+    rc = lib.bbs_selftest_pairing(suite.curve_id, 0, len(cases), ptr(p), ptr(r), ptr(q), ptr(st))
+    assert rc == 0, lib.bbs_last_error()
+    assert st.tolist() == [c[2] for c in cases], st.tolist()
+    # identity Q: first pair contributes 1
+    q = np.frombuffer(ocs.g2_compress(None), dtype=np.uint8)
+    rc = lib.bbs_selftest_pairing(suite.curve_id, 0, len(cases), ptr(p), ptr(r), ptr(q), ptr(st))
+    assert rc == 0
+    assert st.tolist() == [0, 0, 0, 1, 1], st.tolist()
+
+
+def case_irtf_kat(lib_path):
+    """test_vector.rs: msg->scalar, domain, B, signature and proof fixtures through the ABI (BLS12-381)."""
+    suite, ocs = SUITES["BLS12_381"]
+    pk = O.sk_to_pk(ocs, IRTF_SK)
+    ctx, gens = make_ctx(lib_path, suite, ocs, pk, HEADER, 1)
+    sc = ctx.msg_to_scalars([MSG, b""])
+    assert sc[0].tobytes()[::-1].hex() == "1cb5bb86114b34dc438a911617655a1db595abafac92f47c5001799cf624b430"
+    assert sc[1].tobytes()[::-1].hex() == "08e3afeb2b4f2b5f907924ef42856616e6f2d5f1fb373736db1cca32707a7d16"
+    assert int.from_bytes(ctx.domain(), "little") == IRTF_DOMAIN
+    sigs, b, st = ctx.sign_batch(IRTF_SK.to_bytes(32, "little"), [[MSG]], want_b=True)
+    assert st.tolist() == [1]
+    got = sigs[0].tobytes()
+    assert got[:48] + got[48:][::-1] == IRTF_SIG            # test_vector.rs:187-191 (e is big-endian there)
+    assert b[0].tobytes() == IRTF_B
+    assert ctx.verify_batch(sigs, [[MSG]]).tolist() == [1]
+    # proof fixture (test_vector.rs:199-260): produced by the oracle (pinned to the KAT), verified by the library
+    sig = (ocs.g1_decompress(IRTF_SIG[:48]), int.from_bytes(IRTF_SIG[48:], "big"))
+    proof = O.proof_gen(ocs, pk, sig, HEADER, PH, [MSG], [0])
+    pb = A.ProofBytes.from_canonical(suite, O.proof_to_bytes(ocs, proof))
+    assert ctx.proof_verify_batch([pb], PH, [[MSG]], [[0]]).tolist() == [1]
+    assert ctx.proof_verify_batch([pb], b"", [[MSG]], [[0]]).tolist() == [0]
+    ctx.close()
+
+
+def _corrupt_sig(ocs, sig, kind, other_sig):
+    a, e = sig
+    if kind == "e+1":
+        return (a, (e + 1) % ocs.r)
+    if kind == "A=identity":
+        return (None, e)
+    if kind == "wrong-issuer":
+        return other_sig
+    return sig
+
+
+def case_verify(lib_path, curve_name, L, n=10, header=b"hdr", use_pairing_oracle_on=2):
+    """sign -> verify round trips and the rejection classes of sign_verify_tests.rs / core_sign_tests.rs."""
+    suite, ocs = SUITES[curve_name]
+    sk, pk = keypair(ocs, 1)
+    sk2, pk2 = keypair(ocs, 2)
+    ctx, gens = make_ctx(lib_path, suite, ocs, pk, header, L)
+    msgs = [[rng_bytes(f"m{i}.{j}", 32 if j % 3 else 5) for j in range(L)] for i in range(n)]
+    if L:
+        msgs[0][0] = b""   # empty message (test_vector.rs:115-119)
+    # library signs; oracle signs; bytes must agree
+    sigs, b_pts, st = ctx.sign_batch(sk.to_bytes(32, "little"), msgs, want_b=True)
+    assert st.tolist() == [1] * n
+    osigs = [O.sign(ocs, sk, m, header) for m in msgs]
+    for i in range(n):
+        assert sigs[i].tobytes() == O.signature_to_bytes(ocs, osigs[i]), (curve_name, L, i)
+        ms = O.msg_to_scalars(ocs, msgs[i], ocs.api_id)
+        dom = O.calculate_domain(ocs, pk, gens[0], gens[1:], header, ocs.api_id)
+        assert b_pts[i].tobytes() == ocs.g1_compress(O.compute_B(ocs, gens, dom, ms))
+    # verify: valid + corrupted, expectations from the oracle
+    kinds = ["ok", "e+1", "A=identity", "wrong-issuer", "msg-flip", "ok"]
+    items, exp = [], []
+    for i in range(n):
+        kind = kinds[i % len(kinds)]
+        m = list(msgs[i])
+        s = osigs[i]
+        if kind == "msg-flip" and L:
+            m[L - 1] = m[L - 1] + b"x"
+        else:
+            s = _corrupt_sig(ocs, s, kind, O.sign(ocs, sk2, msgs[i], header))
+        items.append((s, m))
+        if i < use_pairing_oracle_on:
+            exp.append(int(O.verify(ocs, pk, s, header, m)))
+        else:
+            exp.append(int(O.verify(ocs, pk, s, header, m, trapdoor_sk=sk)))
+    blob = b"".join(O.signature_to_bytes(ocs, s) for s, _ in items)
+    got = ctx.verify_batch(np.frombuffer(blob, dtype=np.uint8), [m for _, m in items])
+    assert got.tolist() == exp, (curve_name, L, got.tolist(), exp)
+    # core_verify with scalar messages gives the same verdicts
+    sc = b"".join(ocs.scalar_le(x) for _, m in items for x in O.msg_to_scalars(ocs, m, ocs.api_id))
+    got2 = ctx.core_verify_batch(np.frombuffer(blob, dtype=np.uint8), np.frombuffer(sc, dtype=np.uint8) if sc else np.zeros(0, np.uint8), L)
+    assert got2.tolist() == exp
+    # generator / message count mismatch -> Err(InvalidMessageAndGeneratorsLength) (verify.rs:68-71)
+    sc1 = b"".join(ocs.scalar_le(7) for _ in range(n * (L + 1)))
+    got3 = ctx.core_verify_batch(np.frombuffer(blob, dtype=np.uint8), np.frombuffer(sc1, dtype=np.uint8), L + 1)
+    assert got3.tolist() == [A.ST_ERR_MSG_GEN_LEN] * n
+    ctx.close()
+    # default (identity) public key -> Ok(false) (sign_verify_tests.rs:84-93)
+    ctx0, _ = make_ctx(lib_path, suite, ocs, None, header, L)
+    got4 = ctx0.verify_batch(np.frombuffer(blob, dtype=np.uint8), [m for _, m in items])
+    exp4 = [int(O.verify(ocs, None, s, header, m)) if i < 1 else 0 for i, (s, m) in enumerate(items)]
+    assert got4.tolist() == exp4
+    ctx0.close()
+
+
+def case_verify_malformed(lib_path, curve_name):
+    suite, ocs = SUITES[curve_name]
+    sk, pk = keypair(ocs, 1)
+    L = 2
+    ctx, gens = make_ctx(lib_path, suite, ocs, pk, b"", L)
+    msgs = [[b"a", b"b"]] * 4
+    sig = O.sign(ocs, sk, msgs[0], b"")
+    good = O.signature_to_bytes(ocs, sig)
+    g = suite.g1_bytes
+    # x not on the curve: search a small x with no square root
+    bad_pt = None
+    x = 1
+    while bad_pt is None:
+        rhs = (x ** 3 + ocs.b) % ocs.p
+        if pow(rhs, (ocs.p - 1) // 2, ocs.p) != 1:
+            enc = bytearray(x.to_bytes(g, "big" if curve_name == "BLS12_381" else "little"))
+            if curve_name == "BLS12_381":
+                enc[0] |= 0x80
+            bad_pt = bytes(enc)
+        x += 1
+    non_canon_e = good[:g] + (ocs.r + 5).to_bytes(32, "little")
+    x_ge_p = bytearray(good)
+    if curve_name == "BLS12_381":
+        x_ge_p[:g] = bytes([0x9f]) + bytes([0xff]) * (g - 1)
+    else:
+        x_ge_p[:g] = bytes([0xff]) * (g - 1) + bytes([0x3f])
+    blob = good + bad_pt + good[g:] + non_canon_e + bytes(x_ge_p)
+    st = ctx.verify_batch(np.frombuffer(blob, dtype=np.uint8), msgs)
+    assert st.tolist() == [1, A.ST_ERR_MALFORMED, A.ST_ERR_MALFORMED, A.ST_ERR_MALFORMED], st.tolist()
+    ctx.close()
+
+
+def make_proofs(ocs, sk, pk, header, ph, L, disclosed, n, seed="p"):
+    out = []
+    for i in range(n):
+        msgs = [rng_bytes(f"{seed}{i}.{j}", 32) for j in range(L)]
+        sig = O.sign(ocs, sk, msgs, header)
+        rs = O.seeded_random_scalars(ocs, f"{seed}{i}".encode(), b"rs-dst", 5 + L - len(set(disclosed)))
+        pr = O.proof_gen(ocs, pk, sig, header, ph, msgs, disclosed, random_scalars=rs)
+        out.append((pr, msgs))
+    return out
+
+
+def case_proof_verify(lib_path, curve_name, L, disclosed, n=8, header=b"h", ph=b"ph", pairing_on=1):
+    """proof_verify_tests.rs / bbs_over_bls_tests.rs: happy paths and forged inputs."""
+    suite, ocs = SUITES[curve_name]
+    sk, pk = keypair(ocs, 1)
+    ctx, gens = make_ctx(lib_path, suite, ocs, pk, header, L)
+    base = make_proofs(ocs, sk, pk, header, ph, L, disclosed, n)
+    dis = sorted(set(disclosed))
+    kinds = ["ok", "Abar=identity", "challenge+1", "swap-commit", "wrong-msg", "ok", "Bbar-mutated", "e_cap+1"]
+    proofs, dmsgs, didx, exp = [], [], [], []
+    for i, (pr, msgs) in enumerate(base):
+        kind = kinds[i % len(kinds)]
+        p = O.Proof(pr.a_bar, pr.b_bar, pr.d, pr.e_cap, pr.r1_cap, pr.r3_cap, list(pr.commitments), pr.challenge)
+        dm = [msgs[j] for j in dis]
+        if kind == "Abar=identity":
+            p.a_bar = None
+        elif kind == "challenge+1":
+            p.challenge = (p.challenge + 1) % ocs.r
+        elif kind == "swap-commit" and len(p.commitments) >= 2:
+            p.commitments[0], p.commitments[1] = p.commitments[1], p.commitments[0]
+        elif kind == "wrong-msg" and dm:
+            dm[0] = dm[0] + b"!"
+        elif kind == "Bbar-mutated":
+            p.b_bar = O.ec_add(ocs.F1, p.b_bar, ocs.BP1)
+        elif kind == "e_cap+1":
+            p.e_cap = (p.e_cap + 1) % ocs.r
+        proofs.append(A.ProofBytes.from_canonical(suite, O.proof_to_bytes(ocs, p)))
+        dmsgs.append(dm)
+        didx.append(dis)
+        td = None if i < pairing_on else sk
+        exp.append(int(O.proof_verify(ocs, pk, p, header, ph, dm, dis, trapdoor_sk=td)))
+    got = ctx.proof_verify_batch(proofs, ph, dmsgs, didx)
+    assert got.tolist() == exp, (curve_name, L, disclosed, got.tolist(), exp)
+    # scalar-level entry point agrees
+    dsc = [[ocs.scalar_le(x) for x in O.msg_to_scalars(ocs, dm, ocs.api_id)] for dm in dmsgs]
+    got2 = ctx.core_proof_verify_batch(proofs, ph, dsc, didx)
+    assert got2.tolist() == exp
+    ctx.close()
+
+
+def case_proof_errors(lib_path, curve_name):
+    """Err(...) paths of proof_verify_init (proof_verify.rs:139-150) and the documented panic mapping."""
+    suite, ocs = SUITES[curve_name]
+    sk, pk = keypair(ocs, 1)
+    L, dis = 4, [0, 2]
+    ctx, gens = make_ctx(lib_path, suite, ocs, pk, b"", L)
+    (pr, msgs), = make_proofs(ocs, sk, pk, b"", b"", L, dis, 1)
+    pb = A.ProofBytes.from_canonical(suite, O.proof_to_bytes(ocs, pr))
+    dm = [msgs[0], msgs[2]]
+    zero = A.ProofBytes(bytes(suite.g1_bytes * 3 + 128), b"")          # all-zero bytes: undecodable points
+    if curve_name == "BN254":
+        # ark's default encoding of the identity is all-zero x with the infinity flag; all-zero bytes decode to x=0
+        pass
+    cases = [
+        ([pb], [dm], [[0, 2]], [1]),
+        ([pb], [dm], [[0, 9]], [A.ST_ERR_DISCLOSED_INDEX]),            # index >= L
+        ([pb], [[msgs[0]]], [[0, 2]], [A.ST_ERR_IDX_MSG_LEN]),         # fewer messages than indexes
+        ([pb], [dm + [b"x"]], [[0, 2, 3]], [A.ST_ERR_MSG_GEN_LEN]),    # R + U != L
+        ([pb], [[msgs[0], msgs[0]]], [[0, 0]], [A.ST_ERR_MALFORMED]),  # duplicate index: the reference panics
+    ]
+    for proofs, m, idx, want in cases:
+        got = ctx.proof_verify_batch(proofs, b"", m, idx)
+        assert got.tolist() == want, (idx, got.tolist(), want)
+    # Proof::default()-style forged input: identity points, zero scalars, 2 commitments (proof_verify_tests.rs:160-184)
+    ident = ocs.g1_compress(None)
+    forged = A.ProofBytes(ident * 3 + bytes(128), bytes(64))
+    got = ctx.proof_verify_batch([forged], b"", [dm], [[0, 2]])
+    p0 = O.Proof(None, None, None, 0, 0, 0, [0, 0], 0)
+    want = int(O.proof_verify(ocs, pk, p0, b"", b"", dm, [0, 2]))
+    assert got.tolist() == [want]
+    ctx.close()

@@ -1,0 +1,58 @@
+"""GPU-less logic tests: the CUDA sources compiled for x86 (tests/hostsim.py) driven through the same C
+ABI and the same parity cases the GPU tests use.  They check the pipeline logic, byte plumbing and
+the oracle agreement of everything except the PTX arithmetic itself (which only a GPU can run)."""
+import pytest
+
+import hostsim
+import parity_cases as P
+from bbs_sign_b200 import _native
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    return hostsim.build()
+
+
+@pytest.fixture(scope="module")
+def lib(lib_path):
+    return _native.load(lib_path)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_field(lib, curve):
+    P.case_field(lib, curve)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_g1_mul(lib, curve):
+    P.case_g1_mul(lib, curve)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_pairing(lib, curve):
+    P.case_pairing(lib, curve)
+
+
+def test_irtf_kat(lib_path):
+    P.case_irtf_kat(lib_path)
+
+
+@pytest.mark.parametrize("curve,L", [("BLS12_381", 3), ("BN254", 2), ("BLS12_381", 0)])
+def test_verify(lib_path, curve, L):
+    P.case_verify(lib_path, curve, L, n=6, use_pairing_oracle_on=1)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_verify_malformed(lib_path, curve):
+    P.case_verify_malformed(lib_path, curve)
+
+
+@pytest.mark.parametrize("curve,L,dis", [("BLS12_381", 4, [0, 2]), ("BN254", 3, [1]), ("BLS12_381", 2, [0, 1]),
+                                         ("BN254", 2, [])])
+def test_proof_verify(lib_path, curve, L, dis):
+    P.case_proof_verify(lib_path, curve, L, dis, n=8, pairing_on=1)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_proof_errors(lib_path, curve):
+    P.case_proof_errors(lib_path, curve)
