@@ -1,8 +1,7 @@
 // C ABI (include/bbs_b200.h) of the B200 batch engine.  Host code here only moves bytes and enqueues
 // kernels; every field / curve / pairing / hash operation of the path runs on the GPU (kernels.cuh).
 #include "../../include/bbs_b200.h"
-#include "kernels.cuh"
-#include "launch.cuh"
+#include "launchers.cuh"
 
 #include <new>
 #include <vector>
@@ -80,7 +79,7 @@ struct Impl {
         // 1. decode generators and public key
         CtxDecodeArgs da{(const uint8_t*)c->gens_comp.p, (const uint8_t*)c->pk_comp.p, n_gens, (uint32_t*)c->gens.p,
                          (uint32_t*)c->W.p, d_status};
-        TRY((rt_launch<CtxDecodeArgs, &ctx_decode_item<C>, 32>(da, n_gens + 1, s)));
+        TRY((launch_ctx_decode<C>(da, n_gens + 1, s)));
         std::vector<uint32_t> st(n_gens + 2);
         TRY(rt_d2h(st.data(), d_status, (n_gens + 1) * 4, s));
         TRY(rt_sync(s));
@@ -94,15 +93,15 @@ struct Impl {
                           (const uint8_t*)c->api_id.p, (uint32_t)api_id_len, (const uint8_t*)c->header.p,
                           (uint32_t)header_len, (const uint8_t*)c->dst_h2s.p, (uint32_t)dsth.size(),
                           (const uint32_t*)c->gens.p, (uint32_t*)c->domain.p, (uint32_t*)c->K.p, d_kinf};
-        TRY((rt_launch<CtxDomainArgs, &ctx_domain_item<C>, 32>(dom, 1, s)));
+        TRY((launch_ctx_domain<C>(dom, 1, s)));
         uint32_t k_inf = 0;
         TRY(rt_d2h(&k_inf, d_kinf, 4, s));
         TRY(rt_sync(s));
         // 3. window tables, 4. line tables
         CtxTableArgs ta{(const uint32_t*)c->K.p, (const uint32_t*)c->gens.p, (uint32_t*)c->tab.p};
-        TRY((rt_launch<CtxTableArgs, &ctx_table_item<C>, TPB_HEAVY>(ta, (uint32_t)tab_entries, s)));
+        TRY((launch_ctx_table<C>(ta, (uint32_t)tab_entries, s)));
         CtxLinesArgs la{(const uint32_t*)c->W.p, w_inf, (uint32_t*)c->lines.p};
-        TRY((rt_launch<CtxLinesArgs, &ctx_lines_item<C>, 32>(la, 2, s)));
+        TRY((launch_ctx_lines<C>(la, 2, s)));
         TRY(rt_sync(s));
         c->launches += 4;
         CtxView& v = c->view;
@@ -117,14 +116,14 @@ struct Impl {
 
     static int h2s_dev(Ctx* c, size_t count, const uint8_t* d_msgs, const uint64_t* d_off, uint8_t* d_out, rt_stream_t s) {
         H2sArgs a{d_msgs, d_off, c->view.dst_map, c->view.dst_map_len, d_out};
-        TRY((rt_launch<H2sArgs, &h2s_item<C>, TPB_LIGHT>(a, (uint32_t)count, s)));
+        TRY((launch_h2s<C>(a, (uint32_t)count, s)));
         c->launches += count ? 1 : 0;
         return BBS_OK;
     }
 
     static int pairing_dev(Ctx* c, size_t n, uint8_t* d_status, rt_stream_t s) {
         PairingArgs pa{c->view.lines, (const uint32_t*)c->s_pair.p, (const uint32_t*)c->s_flags.p, d_status};
-        TRY((rt_launch<PairingArgs, &pairing_item<C>, TPB_HEAVY>(pa, (uint32_t)n, s)));
+        TRY((launch_pairing<C>(pa, (uint32_t)n, s)));
         c->launches += n ? 1 : 0;
         return BBS_OK;
     }
@@ -134,7 +133,7 @@ struct Impl {
         TRY(c->s_pair.reserve(n * 6 * C::Fp::N * 4));
         TRY(c->s_flags.reserve(n * 4));
         VerifyG1Args a{c->view, d_sigs, d_scalars, n_msgs, (uint32_t*)c->s_pair.p, (uint32_t*)c->s_flags.p, d_status};
-        TRY((rt_launch<VerifyG1Args, &verify_g1_item<C>, TPB_HEAVY>(a, (uint32_t)n, s)));
+        TRY((launch_verify_g1<C>(a, (uint32_t)n, s)));
         c->launches += n ? 1 : 0;
         return pairing_dev(c, n, d_status, s);
     }
@@ -153,7 +152,7 @@ struct Impl {
         limbs_from_le<8>(a.sk, sk);
         if (!fe_is_canonical<typename C::Fr>(a.sk)) return arg_error("secret key scalar is not canonical");
         a.scalars = d_scalars; a.n_msgs = n_msgs; a.sigs_out = d_sigs; a.b_out = d_b; a.status = d_status;
-        TRY((rt_launch<SignArgs, &sign_item<C>, TPB_HEAVY>(a, (uint32_t)n, s)));
+        TRY((launch_sign<C>(a, (uint32_t)n, s)));
         c->launches += n ? 1 : 0;
         return BBS_OK;
     }
@@ -166,7 +165,7 @@ struct Impl {
         TRY(c->s_flags.reserve(n * 4));
         ProofG1Args a{c->view, d_proofs, d_commit, d_commit_off, d_idx, d_dis_scalars, d_dis_off, d_ph,
                       (uint32_t)ph_len, (uint32_t*)c->s_pair.p, (uint32_t*)c->s_flags.p, d_status};
-        TRY((rt_launch<ProofG1Args, &proof_g1_item<C>, TPB_HEAVY>(a, (uint32_t)n, s)));
+        TRY((launch_proof_g1<C>(a, (uint32_t)n, s)));
         c->launches += n ? 1 : 0;
         return pairing_dev(c, n, d_status, s);
     }
@@ -276,7 +275,7 @@ struct Impl {
     }
 };
 
-#include "selftest.cuh"
+#include "selftest_host.inc"
 
 Ctx* as_ctx(bbs_ctx* p) { return reinterpret_cast<Ctx*>(p); }
 

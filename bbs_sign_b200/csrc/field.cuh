@@ -13,10 +13,10 @@
 
 #if defined(__CUDACC__)
 #define BBS_HD __host__ __device__ __forceinline__
-#define BBS_HDN __host__ __device__ __noinline__
+#define BBS_HDN inline __host__ __device__ __noinline__
 #else
 #define BBS_HD inline
-#define BBS_HDN
+#define BBS_HDN inline __attribute__((noinline))
 #ifndef __constant__
 #define __constant__
 #endif
@@ -38,6 +38,16 @@
 #define BBS_CONST_ARRAY(name, n, ...)                                   \
     static const uint32_t name##_host[n] = {__VA_ARGS__};                \
     inline const uint32_t* name() { return name##_host; }
+#endif
+
+// Every out-of-line device function starts and ends with a compiler-level memory barrier.  Without it
+// cicc 12.9's inter-procedural attribute inference was observed to constant-fold a comparison of two
+// buffers written by such calls (fe_sqrt's y^2 == x check became `false`); the barrier makes the callee
+// opaque ("may read / write anything") at zero run-time cost.  Repro notes: tools/dbg/.
+#ifdef __CUDA_ARCH__
+#define BBS_OPAQUE_CALL_BARRIER() asm volatile("" ::: "memory")
+#else
+#define BBS_OPAQUE_CALL_BARRIER() ((void)0)
 #endif
 
 #include "gen_constants.cuh"
@@ -148,10 +158,19 @@ BBS_HD bool bn_eq(const uint32_t* a, const uint32_t* b) {
     return o == 0;
 }
 
+// Element copies go through an opaque register move on the device so NVVM cannot turn them into a
+// memcpy: cicc 12.9 mis-optimises memcpy chains between the stack arrays of inlined callees (observed:
+// fe_sqrt's final comparison constant-folded to false; tools/dbg/).
 template <int N>
 BBS_HD void bn_copy(uint32_t* r, const uint32_t* a) {
 #pragma unroll
-    for (int i = 0; i < N; i++) r[i] = a[i];
+    for (int i = 0; i < N; i++) {
+        uint32_t x = a[i];
+#ifdef __CUDA_ARCH__
+        asm volatile("" : "+r"(x));
+#endif
+        r[i] = x;
+    }
 }
 
 template <int N>
@@ -265,7 +284,9 @@ BBS_HD void fe_mul_inl(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 // (one ~0.7k-instruction body per field instead of one per call site).
 template <class F>
 BBS_HDN void fe_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    BBS_OPAQUE_CALL_BARRIER();
     fe_mul_inl<F>(r, a, b);
+    BBS_OPAQUE_CALL_BARRIER();
 }
 
 template <class F>
@@ -288,7 +309,7 @@ BBS_HD void fe_set_one(uint32_t* r) { bn_copy<F::N>(r, F::ONE()); }
 // r = a^e, e given as little-endian 32-bit limbs (a public constant: uniform control flow across the
 // warp); fixed 4-bit windows, MSB first.
 template <class F>
-BBS_HD void fe_pow(uint32_t* r, const uint32_t* a, const uint32_t* e, int ebits) {
+BBS_HDN void fe_pow(uint32_t* r, const uint32_t* a, const uint32_t* e, int ebits) {
     constexpr int N = F::N;
     uint32_t tab[16][N];
     fe_set_one<F>(tab[0]);
@@ -313,11 +334,11 @@ BBS_HD void fe_pow(uint32_t* r, const uint32_t* a, const uint32_t* e, int ebits)
 
 // Fermat inversion; inv(0) = 0 (matches the `inv0` convention; callers test for zero where it matters)
 template <class F>
-BBS_HD void fe_inv(uint32_t* r, const uint32_t* a) { fe_pow<F>(r, a, F::EXP_INV(), F::BITS); }
+BBS_HDN void fe_inv(uint32_t* r, const uint32_t* a) { fe_pow<F>(r, a, F::EXP_INV(), F::BITS); }
 
 // square root for p = 3 mod 4; returns false when a is a non-residue
 template <class F>
-BBS_HD bool fe_sqrt(uint32_t* r, const uint32_t* a) {
+BBS_HDN bool fe_sqrt(uint32_t* r, const uint32_t* a) {
     uint32_t s[F::N], q[F::N];
     fe_pow<F>(s, a, F::EXP_SQRT(), F::BITS - 1);
     fe_sqr<F>(q, s);
@@ -328,7 +349,7 @@ BBS_HD bool fe_sqrt(uint32_t* r, const uint32_t* a) {
 
 // canonical(a) > (p-1)/2   (the "y is lexicographically largest / negative" flag of both encodings)
 template <class F>
-BBS_HD bool fe_is_high(const uint32_t* a_mont) {
+BBS_HDN bool fe_is_high(const uint32_t* a_mont) {
     uint32_t c[F::N];
     fe_from_mont<F>(c, a_mont);
     return bn_gt<F::N>(c, F::HALF());

@@ -100,7 +100,7 @@ template <class C> BBS_HDN void g1_add(uint32_t* r, const uint32_t* p, const uin
 }
 
 // Jacobian -> affine (x, y); returns false for the identity (then r is zeroed)
-template <class C> BBS_HD bool g1_to_affine(uint32_t* r, const uint32_t* p) {
+template <class C> BBS_HDN bool g1_to_affine(uint32_t* r, const uint32_t* p) {
     using F = typename C::Fp;
     if (g1_is_inf<C>(p)) { bn_zero<2 * C::Fp::N>(r); return false; }
     uint32_t zi[FPN], zi2[FPN];
@@ -113,7 +113,7 @@ template <class C> BBS_HD bool g1_to_affine(uint32_t* r, const uint32_t* p) {
 }
 
 // y^2 == x^3 + b  (affine, Montgomery)
-template <class C> BBS_HD bool g1_on_curve(const uint32_t* a) {
+template <class C> BBS_HDN bool g1_on_curve(const uint32_t* a) {
     using F = typename C::Fp;
     uint32_t l[FPN], rr[FPN];
     fe_sqr<F>(l, a + FPN);
@@ -123,7 +123,7 @@ template <class C> BBS_HD bool g1_on_curve(const uint32_t* a) {
 
 // r = k * P  (P Jacobian), k = canonical little-endian limbs, `bits` significant bits; MSB-first
 // double-and-add (what ark-ec's `Projective * Fr` does; variable time like the reference).
-template <class C> BBS_HD void g1_mul(uint32_t* r, const uint32_t* p, const uint32_t* k, int bits) {
+template <class C> BBS_HDN void g1_mul(uint32_t* r, const uint32_t* p, const uint32_t* k, int bits) {
     uint32_t acc[G1J], base[G1J];
     g1_copy<C>(base, p);
     g1_set_inf<C>(acc);
@@ -134,7 +134,7 @@ template <class C> BBS_HD void g1_mul(uint32_t* r, const uint32_t* p, const uint
     g1_copy<C>(r, acc);
 }
 // same with an affine base (mixed additions)
-template <class C> BBS_HD void g1_mul_affine(uint32_t* r, const uint32_t* a, const uint32_t* k, int bits) {
+template <class C> BBS_HDN void g1_mul_affine(uint32_t* r, const uint32_t* a, const uint32_t* k, int bits) {
     uint32_t acc[G1J];
     g1_set_inf<C>(acc);
     for (int i = bits - 1; i >= 0; i--) {
@@ -150,10 +150,10 @@ enum : int { PT_OK = 0, PT_INF = 1, PT_BAD = 2 };
 // compressed bytes -> affine Montgomery point.  PT_INF for the identity encoding, PT_BAD for anything
 // ark's deserializer would refuse (bad flags, x >= p, x not on the curve).  No subgroup check: the
 // reference's verify functions take already-typed points and perform none.
-template <class C> BBS_HD int g1_decompress(uint32_t* r /*affine*/, const uint8_t* in);
-template <class C> BBS_HD void g1_compress_affine(uint8_t* out, const uint32_t* a /*affine*/, bool inf);
+template <class C> BBS_HDN int g1_decompress(uint32_t* r /*affine*/, const uint8_t* in);
+template <class C> BBS_HDN void g1_compress_affine(uint8_t* out, const uint32_t* a /*affine*/, bool inf);
 
-template <class C> BBS_HD int g1_finish_decompress(uint32_t* r, uint32_t* x_canon, bool want_high) {
+template <class C> BBS_HDN int g1_finish_decompress(uint32_t* r, uint32_t* x_canon, bool want_high) {
     using F = typename C::Fp;
     if (!fe_is_canonical<F>(x_canon)) return PT_BAD;
     uint32_t x[FPN], rhs[FPN], y[FPN];
@@ -166,7 +166,7 @@ template <class C> BBS_HD int g1_finish_decompress(uint32_t* r, uint32_t* x_cano
 }
 
 // BLS12-381: zcash / IETF format, 48 bytes big-endian x, flags in the top 3 bits of byte 0
-template <> BBS_HD int g1_decompress<Bls>(uint32_t* r, const uint8_t* in) {
+template <> BBS_HDN int g1_decompress<Bls>(uint32_t* r, const uint8_t* in) {
     uint8_t b0 = in[0];
     if (!(b0 & 0x80)) return PT_BAD;
     if (b0 & 0x40) {
@@ -182,7 +182,7 @@ template <> BBS_HD int g1_decompress<Bls>(uint32_t* r, const uint8_t* in) {
     limbs_from_be<12>(x, tmp);
     return g1_finish_decompress<Bls>(r, x, (b0 & 0x20) != 0);
 }
-template <> BBS_HD void g1_compress_affine<Bls>(uint8_t* out, const uint32_t* a, bool inf) {
+template <> BBS_HDN void g1_compress_affine<Bls>(uint8_t* out, const uint32_t* a, bool inf) {
     if (inf) { out[0] = 0xc0; for (int i = 1; i < 48; i++) out[i] = 0; return; }
     uint32_t x[12];
     fe_from_mont<BlsFp>(x, a);
@@ -191,7 +191,7 @@ template <> BBS_HD void g1_compress_affine<Bls>(uint8_t* out, const uint32_t* a,
     if (fe_is_high<BlsFp>(a + 12)) out[0] |= 0x20;
 }
 // BN254: arkworks default SW format, 32 bytes little-endian x, flags in the top 2 bits of byte 31
-template <> BBS_HD int g1_decompress<Bn>(uint32_t* r, const uint8_t* in) {
+template <> BBS_HDN int g1_decompress<Bn>(uint32_t* r, const uint8_t* in) {
     uint8_t fl = in[31] & 0xc0;
     if (fl == 0xc0) return PT_BAD;
     if (fl & 0x40) { bn_zero<16>(r); return PT_INF; }
@@ -202,7 +202,7 @@ template <> BBS_HD int g1_decompress<Bn>(uint32_t* r, const uint8_t* in) {
     limbs_from_le<8>(x, tmp);
     return g1_finish_decompress<Bn>(r, x, (fl & 0x80) != 0);
 }
-template <> BBS_HD void g1_compress_affine<Bn>(uint8_t* out, const uint32_t* a, bool inf) {
+template <> BBS_HDN void g1_compress_affine<Bn>(uint8_t* out, const uint32_t* a, bool inf) {
     if (inf) { for (int i = 0; i < 32; i++) out[i] = 0; out[31] = 0x40; return; }
     uint32_t x[8];
     fe_from_mont<BnFp>(x, a);
@@ -211,7 +211,7 @@ template <> BBS_HD void g1_compress_affine<Bn>(uint8_t* out, const uint32_t* a, 
 }
 
 // Jacobian -> compressed bytes (one inversion)
-template <class C> BBS_HD void g1_compress(uint8_t* out, const uint32_t* p) {
+template <class C> BBS_HDN void g1_compress(uint8_t* out, const uint32_t* p) {
     uint32_t a[G1A];
     bool ok = g1_to_affine<C>(a, p);
     g1_compress_affine<C>(out, a, !ok);

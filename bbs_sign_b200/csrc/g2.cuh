@@ -5,7 +5,7 @@
 
 namespace bbs {
 
-template <class C> BBS_HD void f2_pow(uint32_t* r, const uint32_t* a, const uint32_t* e, int ebits) {
+template <class C> BBS_HDN void f2_pow(uint32_t* r, const uint32_t* a, const uint32_t* e, int ebits) {
     uint32_t acc[F2N];
     f2_one<C>(acc);
     for (int i = ebits - 1; i >= 0; i--) {
@@ -16,7 +16,7 @@ template <class C> BBS_HD void f2_pow(uint32_t* r, const uint32_t* a, const uint
 }
 
 // sqrt in Fp2 for p = 3 mod 4 (Adj-Rodriguez-Henriquez, the algorithm ark-ff uses for this case)
-template <class C> BBS_HD bool f2_sqrt(uint32_t* r, const uint32_t* a) {
+template <class C> BBS_HDN bool f2_sqrt(uint32_t* r, const uint32_t* a) {
     using F = typename C::Fp;
     if (f2_is_zero<C>(a)) { f2_zero<C>(r); return true; }
     uint32_t a1[F2N], alpha[F2N], x0[F2N], m1[F2N], cand[F2N], chk[F2N];
@@ -46,13 +46,13 @@ template <class C> BBS_HD bool f2_is_high(const uint32_t* y) {
     return fe_is_high<F>(y);
 }
 
-template <class C> BBS_HD void g2_twist_b(uint32_t* b2);
-template <> BBS_HD void g2_twist_b<Bls>(uint32_t* b2) {   // 4 (1+u)
+template <class C> BBS_HDN void g2_twist_b(uint32_t* b2);
+template <> BBS_HDN void g2_twist_b<Bls>(uint32_t* b2) {   // 4 (1+u)
     uint32_t four[12];
     fe_set_one<BlsFp>(four); fe_dbl<BlsFp>(four, four); fe_dbl<BlsFp>(four, four);
     bn_copy<12>(b2, four); bn_copy<12>(b2 + 12, four);
 }
-template <> BBS_HD void g2_twist_b<Bn>(uint32_t* b2) {    // 3 / (9+u)
+template <> BBS_HDN void g2_twist_b<Bn>(uint32_t* b2) {    // 3 / (9+u)
     uint32_t xi[16], three[16];
     bn_copy<16>(xi, BN_XI());
     f2_inv<Bn>(xi, xi);
@@ -60,7 +60,7 @@ template <> BBS_HD void g2_twist_b<Bn>(uint32_t* b2) {    // 3 / (9+u)
     f2_mul<Bn>(b2, three, xi);
 }
 
-template <class C> BBS_HD int g2_finish_decompress(uint32_t* r, uint32_t* xc0, uint32_t* xc1, bool want_high) {
+template <class C> BBS_HDN int g2_finish_decompress(uint32_t* r, uint32_t* xc0, uint32_t* xc1, bool want_high) {
     using F = typename C::Fp;
     if (!fe_is_canonical<F>(xc0) || !fe_is_canonical<F>(xc1)) return PT_BAD;
     uint32_t x[F2N], rhs[F2N], y[F2N], b2[F2N];
@@ -73,9 +73,9 @@ template <class C> BBS_HD int g2_finish_decompress(uint32_t* r, uint32_t* xc0, u
     return PT_OK;
 }
 
-template <class C> BBS_HD int g2_decompress(uint32_t* r /*affine [x|y] Fp2*/, const uint8_t* in);
+template <class C> BBS_HDN int g2_decompress(uint32_t* r /*affine [x|y] Fp2*/, const uint8_t* in);
 // BLS12-381 (zcash): 96 bytes = BE(x.c1) || BE(x.c0), flags in byte 0
-template <> BBS_HD int g2_decompress<Bls>(uint32_t* r, const uint8_t* in) {
+template <> BBS_HDN int g2_decompress<Bls>(uint32_t* r, const uint8_t* in) {
     uint8_t b0 = in[0];
     if (!(b0 & 0x80)) return PT_BAD;
     if (b0 & 0x40) {
@@ -93,7 +93,7 @@ template <> BBS_HD int g2_decompress<Bls>(uint32_t* r, const uint8_t* in) {
     return g2_finish_decompress<Bls>(r, c0, c1, (b0 & 0x20) != 0);
 }
 // BN254 (ark default): 64 bytes = LE(x.c0) || LE(x.c1), flags in byte 63
-template <> BBS_HD int g2_decompress<Bn>(uint32_t* r, const uint8_t* in) {
+template <> BBS_HDN int g2_decompress<Bn>(uint32_t* r, const uint8_t* in) {
     uint8_t fl = in[63] & 0xc0;
     if (fl == 0xc0) return PT_BAD;
     if (fl & 0x40) { bn_zero<32>(r); return PT_INF; }

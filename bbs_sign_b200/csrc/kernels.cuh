@@ -114,7 +114,7 @@ template <class C> BBS_HD void h2s_item(const H2sArgs& a, uint32_t t) {
 
 // ---- fixed-base MSM over the window tables -------------------------------------------------------------
 // acc += s * base_g, s canonical limbs (8)
-template <class C> BBS_HD void tab_accumulate(uint32_t* acc, const uint32_t* tab, uint32_t g, const uint32_t* s) {
+template <class C> BBS_HDN void tab_accumulate(uint32_t* acc, const uint32_t* tab, uint32_t g, const uint32_t* s) {
     const uint32_t* tg = tab + (size_t)g * TAB_WINDOWS * TAB_ENTRIES * G1A;
     for (int w = 0; w < TAB_WINDOWS; w++) {
         uint32_t d = (s[w >> 2] >> (8 * (w & 3))) & 0xff;

@@ -1,0 +1,24 @@
+// One launcher per kernel and curve.  Each is explicitly instantiated in its own translation unit
+// (tu_*.cu, compiled once per curve) so the library builds in parallel; capi.cu only sees declarations.
+#pragma once
+#include "kernels.cuh"
+#include "selftest.cuh"
+#include "launch.cuh"
+
+namespace bbs {
+
+template <class C> int launch_ctx_decode(const CtxDecodeArgs& a, uint32_t n, rt_stream_t s);
+template <class C> int launch_ctx_domain(const CtxDomainArgs& a, uint32_t n, rt_stream_t s);
+template <class C> int launch_ctx_table(const CtxTableArgs& a, uint32_t n, rt_stream_t s);
+template <class C> int launch_ctx_lines(const CtxLinesArgs& a, uint32_t n, rt_stream_t s);
+template <class C> int launch_h2s(const H2sArgs& a, uint32_t n, rt_stream_t s);
+template <class C> int launch_verify_g1(const VerifyG1Args& a, uint32_t n, rt_stream_t s);
+template <class C> int launch_pairing(const PairingArgs& a, uint32_t n, rt_stream_t s);
+template <class C> int launch_sign(const SignArgs& a, uint32_t n, rt_stream_t s);
+template <class C> int launch_proof_g1(const ProofG1Args& a, uint32_t n, rt_stream_t s);
+template <class C> int launch_field_test(const FieldTestArgs& a, uint32_t n, rt_stream_t s);
+template <class C> int launch_g1_mul_test(const G1MulTestArgs& a, uint32_t n, rt_stream_t s);
+template <class C> int launch_pair_test_prep(const PairTestPrepArgs& a, uint32_t n, rt_stream_t s);
+template <class C> int launch_pair_test(const PairTestArgs& a, uint32_t n, rt_stream_t s);
+
+}  // namespace bbs

@@ -37,7 +37,7 @@ template <class C> BBS_HD int ate_line_count() {
 
 // ---- G2 affine steps on the twist, emitting line coefficients ------------------------------------
 // T <- 2T ; line: lambda = 3 xT^2 / (2 yT)
-template <class C> BBS_HD void g2_dbl_step(uint32_t* line, uint32_t* T) {
+template <class C> BBS_HDN void g2_dbl_step(uint32_t* line, uint32_t* T) {
     uint32_t lam[F2N], t[F2N], x3[F2N], y3[F2N];
     f2_sqr<C>(lam, T); f2_dbl<C>(t, lam); f2_add<C>(lam, lam, t);
     f2_dbl<C>(t, T + F2N); f2_inv<C>(t, t);
@@ -49,7 +49,7 @@ template <class C> BBS_HD void g2_dbl_step(uint32_t* line, uint32_t* T) {
     f2_copy<C>(T, x3); f2_copy<C>(T + F2N, y3);
 }
 // T <- T + Q ; line through T and Q
-template <class C> BBS_HD void g2_add_step(uint32_t* line, uint32_t* T, const uint32_t* Q) {
+template <class C> BBS_HDN void g2_add_step(uint32_t* line, uint32_t* T, const uint32_t* Q) {
     uint32_t lam[F2N], t[F2N], x3[F2N], y3[F2N];
     f2_sub<C>(lam, Q + F2N, T + F2N);
     f2_sub<C>(t, Q, T); f2_inv<C>(t, t);
@@ -63,7 +63,7 @@ template <class C> BBS_HD void g2_add_step(uint32_t* line, uint32_t* T, const ui
 
 // Q: affine twist point [x(Fp2)|y(Fp2)], must not be the identity and must have order r.
 // out: line k of pair `pair` lives at out + (2k + pair) * LINE_WORDS.
-template <class C> BBS_HD void g2_precompute_lines(uint32_t* out, const uint32_t* Q, int pair) {
+template <class C> BBS_HDN void g2_precompute_lines(uint32_t* out, const uint32_t* Q, int pair) {
     uint32_t T[2 * F2N], nQ[2 * F2N];
     bn_copy<4 * C::Fp::N>(T, Q);
     f2_copy<C>(nQ, Q); f2_neg<C>(nQ + F2N, Q + F2N);
@@ -89,7 +89,7 @@ template <class C> BBS_HD void g2_precompute_lines(uint32_t* out, const uint32_t
 // ---- line evaluation --------------------------------------------------------------------------------
 // P is given as (px, py, pz) = (X*Z, Y, Z^3) of a Jacobian point (affine: (x, y, 1)); the evaluated line is
 // scaled by Z^3 in Fp, which the final exponentiation kills.
-template <class C> BBS_HD void f12_mul_line(uint32_t* f, const uint32_t* line, const uint32_t* P) {
+template <class C> BBS_HDN void f12_mul_line(uint32_t* f, const uint32_t* line, const uint32_t* P) {
     uint32_t a[F2N], b[F2N], y[F2N];
     f2_mul_fp<C>(a, line, P + 2 * FPN);          // A * pz
     f2_mul_fp<C>(b, line + F2N, P);              // Bc * px
@@ -99,7 +99,7 @@ template <class C> BBS_HD void f12_mul_line(uint32_t* f, const uint32_t* line, c
 }
 
 // Jacobian point -> (X*Z, Y, Z^3)
-template <class C> BBS_HD void g1_to_line_arg(uint32_t* out, const uint32_t* p) {
+template <class C> BBS_HDN void g1_to_line_arg(uint32_t* out, const uint32_t* p) {
     using F = typename C::Fp;
     uint32_t z2[FPN];
     fe_mul<F>(out, p, p + 2 * FPN);
@@ -110,7 +110,7 @@ template <class C> BBS_HD void g1_to_line_arg(uint32_t* out, const uint32_t* p) 
 
 // f = f_{Q0}(P0) * f_{Q1}(P1) over the shared loop; a skipped pair contributes 1 (ark-ec filters pairs
 // with an identity argument: SURVEY 4 / Appendix C).
-template <class C> BBS_HD void miller2(uint32_t* f, const uint32_t* lines, const uint32_t* P0, bool skip0,
+template <class C> BBS_HDN void miller2(uint32_t* f, const uint32_t* lines, const uint32_t* P0, bool skip0,
                                        const uint32_t* P1, bool skip1) {
     f12_one<C>(f);
     int k = 0;
@@ -136,7 +136,7 @@ template <class C> BBS_HD void miller2(uint32_t* f, const uint32_t* lines, const
 
 // ---- final exponentiation ---------------------------------------------------------------------------
 // r = a^e for a in the cyclotomic subgroup, e > 0 (a public constant)
-template <class C> BBS_HD void f12_cyc_pow(uint32_t* r, const uint32_t* a, uint64_t e) {
+template <class C> BBS_HDN void f12_cyc_pow(uint32_t* r, const uint32_t* a, uint64_t e) {
     uint32_t acc[F12N];
     f12_copy<C>(acc, a);
     int top = 63;
@@ -148,11 +148,11 @@ template <class C> BBS_HD void f12_cyc_pow(uint32_t* r, const uint32_t* a, uint6
     f12_copy<C>(r, acc);
 }
 
-template <class C> BBS_HD void final_exp_hard(uint32_t* r, const uint32_t* f);
+template <class C> BBS_HDN void final_exp_hard(uint32_t* r, const uint32_t* f);
 
 // BLS12 (x < 0): 3 (p^4-p^2+1)/r = (x-1)^2 (x+p) (x^2+p^2-1) + 3   [Hayashida-Hayasaka-Teruya, eprint 2020/875]
 // f^x = conj(f^|x|) in the cyclotomic subgroup.
-template <> BBS_HD void final_exp_hard<Bls>(uint32_t* r, const uint32_t* f) {
+template <> BBS_HDN void final_exp_hard<Bls>(uint32_t* r, const uint32_t* f) {
     using C = Bls;
     uint32_t a[F12N], b[F12N], c[F12N];
     f12_cyc_pow<C>(a, f, BLS_X_ABS); f12_conj<C>(a, a); f12_conj<C>(b, f); f12_mul<C>(a, a, b);      // f^(x-1)
@@ -166,7 +166,7 @@ template <> BBS_HD void final_exp_hard<Bls>(uint32_t* r, const uint32_t* f) {
 }
 
 // BN (x = t > 0): Fuentes-Castaneda et al. addition chain (the one ark-ec's bn model uses)
-template <> BBS_HD void final_exp_hard<Bn>(uint32_t* r, const uint32_t* f) {
+template <> BBS_HDN void final_exp_hard<Bn>(uint32_t* r, const uint32_t* f) {
     using C = Bn;
     uint32_t y0[F12N], y1[F12N], y3[F12N], y4[F12N], y6[F12N], y8[F12N], y9[F12N], t[F12N], u[F12N];
     f12_cyc_pow<C>(y0, f, BN_T); f12_conj<C>(y0, y0);        // f^-x
@@ -191,7 +191,7 @@ template <> BBS_HD void final_exp_hard<Bn>(uint32_t* r, const uint32_t* f) {
 }
 
 // f^((p^12-1)/r * c) == 1 ?   (c = 3 for BLS12, 1 for BN; gcd(c, r) = 1 so the verdict is unchanged)
-template <class C> BBS_HD bool final_exp_is_one(const uint32_t* f) {
+template <class C> BBS_HDN bool final_exp_is_one(const uint32_t* f) {
     uint32_t a[F12N], b[F12N];
     f12_inv<C>(a, f);
     f12_conj<C>(b, f);

@@ -30,7 +30,7 @@ struct Sha256 {
         for (int i = 0; i < 16; i++) w[i] = 0;
         fill = 0; total = 0;
     }
-    BBS_HD void compress() {
+    BBS_HDN void compress() {
         const uint32_t* K = SHA256_K();
         uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
         uint32_t m[16];
@@ -66,7 +66,7 @@ struct Sha256 {
         fill++; total++;
         if (fill == 64) compress();
     }
-    BBS_HD void update(const uint8_t* p, uint32_t n) {
+    BBS_HDN void update(const uint8_t* p, uint32_t n) {
         for (uint32_t i = 0; i < n; i++) put(p[i]);
     }
     // 32 bytes given as 8 big-endian words
@@ -78,7 +78,7 @@ struct Sha256 {
     BBS_HD void put_be64(uint64_t v) {
         for (int i = 7; i >= 0; i--) put((uint8_t)(v >> (8 * i)));
     }
-    BBS_HD void finish(uint32_t* out8) {
+    BBS_HDN void finish(uint32_t* out8) {
         uint32_t bits_lo = total << 3, bits_hi = total >> 29;
         uint32_t t = total;
         put(0x80);
@@ -98,7 +98,7 @@ struct Xmd48 {
         s.init();
         for (int i = 0; i < 64; i++) s.put(0);   // Z_pad (utilities_helper.rs:55)
     }
-    BBS_HD void finish(const uint8_t* dst, uint32_t dst_len, uint32_t* out12) {
+    BBS_HDN void finish(const uint8_t* dst, uint32_t dst_len, uint32_t* out12) {
         s.put(0); s.put(48); s.put(0);           // I2OSP(48, 2) || 0x00 (utilities_helper.rs:57)
         s.update(dst, dst_len); s.put((uint8_t)dst_len);
         uint32_t b0[8], b1[8], b2[8];
@@ -118,7 +118,7 @@ struct Xmd48 {
 // x = hi * 2^256 + lo with hi < 2^128: lo mod r by conditional subtractions (2^256 < 3r for BLS12-381,
 // < 6r for BN254), hi * 2^256 mod r = mont_mul(hi, R^2) since R = 2^256.
 template <class Fr>
-BBS_HD void okm48_to_scalar(uint32_t* r, const uint32_t* be12) {
+BBS_HDN void okm48_to_scalar(uint32_t* r, const uint32_t* be12) {
     uint32_t lo[8], hi[8], t[8];
     for (int i = 0; i < 8; i++) lo[i] = be12[11 - i];
     for (int i = 0; i < 4; i++) hi[i] = be12[3 - i];
@@ -133,7 +133,7 @@ BBS_HD void okm48_to_scalar(uint32_t* r, const uint32_t* be12) {
 
 // hash_to_scalar(msg, dst) for a byte-string message
 template <class Fr>
-BBS_HD void hash_to_scalar(uint32_t* r, const uint8_t* msg, uint32_t len, const uint8_t* dst, uint32_t dst_len) {
+BBS_HDN void hash_to_scalar(uint32_t* r, const uint8_t* msg, uint32_t len, const uint8_t* dst, uint32_t dst_len) {
     Xmd48 x;
     x.begin();
     x.s.update(msg, len);

@@ -105,7 +105,7 @@ template <class C> BBS_HDN void f2_sqr(uint32_t* r, const uint32_t* a) {
 template <class C> BBS_HD void f2_mul_fp(uint32_t* r, const uint32_t* a, const uint32_t* k) {
     fe_mul<typename C::Fp>(r, a, k); fe_mul<typename C::Fp>(r + FPN, a + FPN, k);
 }
-template <class C> BBS_HD void f2_inv(uint32_t* r, const uint32_t* a) {
+template <class C> BBS_HDN void f2_inv(uint32_t* r, const uint32_t* a) {
     using F = typename C::Fp;
     uint32_t n[FPN], t[FPN];
     fe_sqr<F>(n, a);
@@ -175,7 +175,7 @@ template <class C> BBS_HD void f6_mul_by_1(uint32_t* r, const uint32_t* a, const
     f2_mul<C>(c2, a + F2N, b1);
     f2_copy<C>(r, c0); f2_copy<C>(r + F2N, c1); f2_copy<C>(r + 2 * F2N, c2);
 }
-template <class C> BBS_HD void f6_inv(uint32_t* r, const uint32_t* a) {
+template <class C> BBS_HDN void f6_inv(uint32_t* r, const uint32_t* a) {
     const uint32_t *a0 = a, *a1 = a + F2N, *a2 = a + 2 * F2N;
     uint32_t c0[F2N], c1[F2N], c2[F2N], t[F2N], d[F2N];
     // c0 = a0^2 - xi a1 a2 ; c1 = xi a2^2 - a0 a1 ; c2 = a1^2 - a0 a2
@@ -228,7 +228,7 @@ template <class C> BBS_HDN void f12_sqr(uint32_t* r, const uint32_t* a) {
     f6_sub<C>(r, s, t);
     f6_add<C>(r + F6N, ab, ab);
 }
-template <class C> BBS_HD void f12_inv(uint32_t* r, const uint32_t* a) {
+template <class C> BBS_HDN void f12_inv(uint32_t* r, const uint32_t* a) {
     uint32_t t0[F6N], t1[F6N];
     f6_mul<C>(t0, a, a);
     f6_mul<C>(t1, a + F6N, a + F6N);
@@ -240,7 +240,7 @@ template <class C> BBS_HD void f12_inv(uint32_t* r, const uint32_t* a) {
     f6_neg<C>(r + F6N, t1);
 }
 // slot s of the tower layout [c0.c0 c0.c1 c0.c2 c1.c0 c1.c1 c1.c2] carries w-power {0,2,4,1,3,5}[s]
-template <class C> BBS_HD void f12_frob(uint32_t* r, const uint32_t* a, int j) {
+template <class C> BBS_HDN void f12_frob(uint32_t* r, const uint32_t* a, int j) {
     const uint32_t* g = C::FROB(j);
     const int wpow[6] = {0, 2, 4, 1, 3, 5};
     for (int s = 0; s < 6; s++) {

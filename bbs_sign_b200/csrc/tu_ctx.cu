@@ -1,0 +1,33 @@
+// Translation unit for the `ctx` kernels (see launchers.cuh).  Built once per curve: -DBBS_TU_BLS / -DBBS_TU_BN;
+// with neither macro both curves are instantiated (host-simulation build).
+#include "launchers.cuh"
+
+namespace bbs {
+
+template <class C> int launch_ctx_decode(const CtxDecodeArgs& a, uint32_t n, rt_stream_t s) {
+    return rt_launch<CtxDecodeArgs, &ctx_decode_item<C>, 32>(a, n, s);
+}
+template <class C> int launch_ctx_domain(const CtxDomainArgs& a, uint32_t n, rt_stream_t s) {
+    return rt_launch<CtxDomainArgs, &ctx_domain_item<C>, 32>(a, n, s);
+}
+template <class C> int launch_ctx_table(const CtxTableArgs& a, uint32_t n, rt_stream_t s) {
+    return rt_launch<CtxTableArgs, &ctx_table_item<C>, 128>(a, n, s);
+}
+template <class C> int launch_ctx_lines(const CtxLinesArgs& a, uint32_t n, rt_stream_t s) {
+    return rt_launch<CtxLinesArgs, &ctx_lines_item<C>, 32>(a, n, s);
+}
+
+#if defined(BBS_TU_BLS) || !defined(BBS_TU_BN)
+template int launch_ctx_decode<Bls>(const CtxDecodeArgs&, uint32_t, rt_stream_t);
+template int launch_ctx_domain<Bls>(const CtxDomainArgs&, uint32_t, rt_stream_t);
+template int launch_ctx_table<Bls>(const CtxTableArgs&, uint32_t, rt_stream_t);
+template int launch_ctx_lines<Bls>(const CtxLinesArgs&, uint32_t, rt_stream_t);
+#endif
+#if defined(BBS_TU_BN) || !defined(BBS_TU_BLS)
+template int launch_ctx_decode<Bn>(const CtxDecodeArgs&, uint32_t, rt_stream_t);
+template int launch_ctx_domain<Bn>(const CtxDomainArgs&, uint32_t, rt_stream_t);
+template int launch_ctx_table<Bn>(const CtxTableArgs&, uint32_t, rt_stream_t);
+template int launch_ctx_lines<Bn>(const CtxLinesArgs&, uint32_t, rt_stream_t);
+#endif
+
+}  // namespace bbs

@@ -1,0 +1,18 @@
+// Translation unit for the `sign` kernels (see launchers.cuh).  Built once per curve: -DBBS_TU_BLS / -DBBS_TU_BN;
+// with neither macro both curves are instantiated (host-simulation build).
+#include "launchers.cuh"
+
+namespace bbs {
+
+template <class C> int launch_sign(const SignArgs& a, uint32_t n, rt_stream_t s) {
+    return rt_launch<SignArgs, &sign_item<C>, 128>(a, n, s);
+}
+
+#if defined(BBS_TU_BLS) || !defined(BBS_TU_BN)
+template int launch_sign<Bls>(const SignArgs&, uint32_t, rt_stream_t);
+#endif
+#if defined(BBS_TU_BN) || !defined(BBS_TU_BLS)
+template int launch_sign<Bn>(const SignArgs&, uint32_t, rt_stream_t);
+#endif
+
+}  // namespace bbs

@@ -16,7 +16,7 @@ def build() -> str:
     srcs = [os.path.join(SRC, f) for f in os.listdir(SRC)] + [os.path.join(ROOT, "include", "bbs_b200.h")]
     if os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(s) for s in srcs):
         return OUT
-    cmd = ["g++", "-O2", "-std=c++17", "-fopenmp", "-DBBS_HOSTSIM", "-x", "c++", "-fPIC", "-shared", "-o", OUT,
-           os.path.join(SRC, "capi.cu")]
+    cmd = ["g++", "-O2", "-std=c++17", "-fopenmp", "-w", "-DBBS_HOSTSIM", "-x", "c++", "-fPIC", "-shared", "-o", OUT,
+           os.path.join(SRC, "capi.cu")] + sorted(os.path.join(SRC, f) for f in os.listdir(SRC) if f.startswith("tu_"))
     subprocess.run(cmd, check=True)
     return OUT
