@@ -13,11 +13,42 @@ namespace {
 constexpr int TPB_HEAVY = 128;   // G1 / pairing kernels
 constexpr int TPB_LIGHT = 128;   // hashing
 
+// CUDA events on the launching stream: mark k sits before kernel k of a batch call (last mark = end)
+struct ProfEvents {
+    static constexpr int MAX = 8;
+#ifndef BBS_HOSTSIM
+    cudaEvent_t ev[MAX] = {};
+    int used = 0;
+    int mark(int slot, rt_stream_t s) {
+        if (slot >= MAX) return 0;
+        if (!ev[slot]) RT_CHECK(cudaEventCreate(&ev[slot]));
+        RT_CHECK(cudaEventRecord(ev[slot], s));
+        used = slot + 1;
+        return 0;
+    }
+    int read(float* ms, int n) {
+        for (int i = 0; i < n; i++) ms[i] = 0.f;
+        for (int i = 0; i + 1 < used && i < n; i++) {
+            RT_CHECK(cudaEventSynchronize(ev[i + 1]));
+            RT_CHECK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+        }
+        return 0;
+    }
+    void release() { for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; } }
+#else
+    int mark(int, rt_stream_t) { return 0; }
+    int read(float* ms, int n) { for (int i = 0; i < n; i++) ms[i] = 0.f; return 0; }
+    void release() {}
+#endif
+};
+
 struct Ctx {
     int curve = 0, device = 0;
     uint32_t L = 0;
     rt_stream_t stream = nullptr;
     uint64_t launches = 0;
+    bool profile = false;            // bbs_ctx_set_profiling: CUDA events around each kernel of a batch call
+    ProfEvents prof;
     DevBuf pk_comp, gens_comp, api_id, header, dst_h2s, dst_map;
     DevBuf gens, W, K, domain, tab, lines, misc;
     CtxView view{};
@@ -34,6 +65,7 @@ struct Ctx {
 };
 
 #define TRY(expr) do { int rc_ = (expr); if (rc_) return rc_; } while (0)
+#define PROF(c, slot, s) do { if ((c)->profile) TRY((c)->prof.mark(slot, s)); } while (0)
 
 int arg_error(const char* what) { rt_set_error("bad argument", what); return BBS_E_ARG; }
 
@@ -133,14 +165,19 @@ struct Impl {
         TRY(c->s_pair.reserve(n * 6 * C::Fp::N * 4));
         TRY(c->s_flags.reserve(n * 4));
         VerifyG1Args a{c->view, d_sigs, d_scalars, n_msgs, (uint32_t*)c->s_pair.p, (uint32_t*)c->s_flags.p, d_status};
+        PROF(c, 1, s);
         TRY((launch_verify_g1<C>(a, (uint32_t)n, s)));
         c->launches += n ? 1 : 0;
-        return pairing_dev(c, n, d_status, s);
+        PROF(c, 2, s);
+        TRY(pairing_dev(c, n, d_status, s));
+        PROF(c, 3, s);
+        return BBS_OK;
     }
 
     static int verify_dev(Ctx* c, size_t n, const uint8_t* d_sigs, const uint8_t* d_msgs, const uint64_t* d_off,
                           uint32_t n_msgs, uint8_t* d_status, rt_stream_t s) {
         TRY(c->s_scalars.reserve(n * n_msgs * 32));
+        PROF(c, 0, s);
         TRY(h2s_dev(c, n * n_msgs, d_msgs, d_off, (uint8_t*)c->s_scalars.p, s));
         return core_verify_dev(c, n, d_sigs, (const uint8_t*)c->s_scalars.p, n_msgs, d_status, s);
     }
@@ -152,8 +189,10 @@ struct Impl {
         limbs_from_le<8>(a.sk, sk);
         if (!fe_is_canonical<typename C::Fr>(a.sk)) return arg_error("secret key scalar is not canonical");
         a.scalars = d_scalars; a.n_msgs = n_msgs; a.sigs_out = d_sigs; a.b_out = d_b; a.status = d_status;
+        PROF(c, 1, s);
         TRY((launch_sign<C>(a, (uint32_t)n, s)));
         c->launches += n ? 1 : 0;
+        PROF(c, 2, s);
         return BBS_OK;
     }
 
@@ -165,9 +204,13 @@ struct Impl {
         TRY(c->s_flags.reserve(n * 4));
         ProofG1Args a{c->view, d_proofs, d_commit, d_commit_off, d_idx, d_dis_scalars, d_dis_off, d_ph,
                       (uint32_t)ph_len, (uint32_t*)c->s_pair.p, (uint32_t*)c->s_flags.p, d_status};
+        PROF(c, 1, s);
         TRY((launch_proof_g1<C>(a, (uint32_t)n, s)));
         c->launches += n ? 1 : 0;
-        return pairing_dev(c, n, d_status, s);
+        PROF(c, 2, s);
+        TRY(pairing_dev(c, n, d_status, s));
+        PROF(c, 3, s);
+        return BBS_OK;
     }
 
     // ---- host-buffer wrappers ---------------------------------------------------------------------
@@ -276,6 +319,7 @@ struct Impl {
 };
 
 #include "selftest_host.inc"
+#include "imad_peak.inc"
 
 Ctx* as_ctx(bbs_ctx* p) { return reinterpret_cast<Ctx*>(p); }
 
@@ -327,6 +371,7 @@ void bbs_ctx_destroy(bbs_ctx* p) {
     rt_set_device(c->device);
     rt_sync(c->stream);
     c->release_all();
+    c->prof.release();
     rt_stream_destroy(c->stream);
     delete c;
 }
@@ -340,6 +385,22 @@ int bbs_ctx_domain(bbs_ctx* p, uint8_t out[32]) {
 }
 
 uint64_t bbs_ctx_launch_count(bbs_ctx* p) { return p ? as_ctx(p)->launches : 0; }
+
+int bbs_ctx_set_profiling(bbs_ctx* p, int on) {
+    if (!p) return arg_error("null context");
+    as_ctx(p)->profile = on != 0;
+    return BBS_OK;
+}
+int bbs_ctx_kernel_times(bbs_ctx* p, float* ms, int n) {
+    Ctx* c = as_ctx(p);
+    if (!c || !ms) return arg_error("null");
+    if (rt_set_device(c->device)) return BBS_E_CUDA;
+    return c->prof.read(ms, n);
+}
+int bbs_imad_peak(int device, int iters, double* gprod_per_s, float* ms_out) {
+    if (rt_set_device(device)) return BBS_E_CUDA;
+    return imad_peak(iters, gprod_per_s, ms_out);
+}
 
 int bbs_msg_to_scalars(bbs_ctx* p, size_t count, const uint8_t* msgs, const uint64_t* off, uint8_t* out) {
     Ctx* c = as_ctx(p);

@@ -1,0 +1,312 @@
+#!/usr/bin/env python3
+"""bench.py -- BLS12-381 BBS batch verify throughput on B200 (BASELINE.json metric, config 2).
+
+A step = one pass of the hot path (msg_to_scalars -> core_verify G1 half -> two-pair pairing) over one
+batch of 65,536 synthetic signatures x L=10 messages of 32 bytes under one issuer key, 1/16 of them
+corrupted.  Signatures are produced by the library's own `bbs_sign_batch` on the GPU (no oracle on the
+product path); the status vector of every run is checked against the construction (valid -> 1,
+corrupted -> 0).
+
+  python bench.py --gpus N --steps K --warmup W           our arm (torchrun for N > 1, one rank per GPU)
+  python bench.py --impl reference ...                    CPU arm: the oracle port of the reference's path
+
+Prints ONE JSON line (rank 0)."""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "bls12_381_bbs_verifies_per_sec_L10"
+UNIT = "verifies/s"
+N_DEFAULT = 65536
+L_DEFAULT = 10
+# IRTF draft key pair (test_vector.rs:140-160): sk little-endian, pk compressed
+IRTF_SK = 0x60e55110f76883a13d030b2f6bd11883422d5abde717569fc0731f51237169fc
+IRTF_PK = bytes.fromhex("a820f230f6ae38503b86c70dc50b61c58a77e45c39ab25c0652bbaa8fa136f2851bd4781c9dcde39fc9d1d52c9e60268"
+                        "061e7d7632171d91aa8d460acee0e96f1e7c4cfb12d3ff9ab5d5dc91c277db75c845d649ef3c4f63aebc364cd55ded0c")
+# counting model of SURVEY 8(d) / Appendix D: 32x32->64 products per BLS12-381 verify at L=10
+PRODUCTS_PER_VERIFY = 19509 * 300 + 3285 * 234              # 6.62e6
+PRODUCTS_PAIRING = (8116 + 7777) * 300 + (76 * 300 + 380 * 234)  # Miller + final exp + its one inversion
+PRODUCTS_G1 = PRODUCTS_PER_VERIFY - PRODUCTS_PAIRING
+SIG_BYTES = 80
+MSG_BYTES = 32
+
+
+def ptr(a):
+    return C.c_void_p(a.ctypes.data) if isinstance(a, np.ndarray) else C.c_void_p(a.data_ptr())
+
+
+def make_workload(ctx, lib, n, L, seed):
+    """Synthetic batch: random 32-byte messages, signed on the GPU, 1/16 corrupted."""
+    rng = np.random.default_rng(seed)
+    msgs = rng.integers(0, 256, size=n * L * MSG_BYTES, dtype=np.uint8)
+    offs = (np.arange(n * L + 1, dtype=np.uint64) * MSG_BYTES)
+    sigs = np.zeros(n * SIG_BYTES, dtype=np.uint8)
+    st = np.zeros(n, dtype=np.uint8)
+    sk = np.frombuffer(IRTF_SK.to_bytes(32, "little"), dtype=np.uint8).copy()
+    rc = lib.bbs_sign_batch(ctx.handle, ptr(sk), n, ptr(msgs), ptr(offs), L, ptr(sigs), None, ptr(st))
+    if rc != 0 or not (st == 1).all():
+        raise RuntimeError(f"bbs_sign_batch failed rc={rc}: {lib.bbs_last_error().decode()}")
+    sigs = sigs.reshape(n, SIG_BYTES)
+    expect = np.ones(n, dtype=np.uint8)
+    bad = np.arange(3, n, 16)
+    for k, i in enumerate(bad):
+        kind = k % 4
+        if kind == 0:      # flipped message byte
+            msgs[(i * L + (k % L)) * MSG_BYTES + 7] ^= 0x40
+        elif kind == 1:    # e ^ 1
+            sigs[i, 48] ^= 1
+        elif kind == 2:    # A = identity
+            sigs[i, :48] = 0
+            sigs[i, 0] = 0xC0
+        else:              # A of the neighbouring signature
+            sigs[i, :48] = sigs[i - 1, :48]
+        expect[i] = 0
+    return msgs, offs, np.ascontiguousarray(sigs.reshape(-1)), expect
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.dev, self.rows, self.proc = dev, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.dev)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 8 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 8 and r[2].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        # under load = upper half of the samples
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from bbs_sign_b200 import api, _native
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    lib = _native.load()
+    n, L = args.n, args.L
+    ctx = api.BatchContext(api.BLS12_381, IRTF_PK, header=b"", n_messages=L, device=local)
+    msgs, offs, sigs, expect = make_workload(ctx, lib, n, L, seed=1234 + rank)
+
+    # ---- device-resident arm: inputs already in HBM ------------------------------------------------
+    dev = torch.device("cuda", local)
+    d_msgs = torch.from_numpy(msgs).to(dev)
+    d_offs = torch.from_numpy(offs.view(np.int64)).to(dev)
+    d_sigs = torch.from_numpy(sigs).to(dev)
+    d_status = torch.zeros(n, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    stream = torch.cuda.current_stream()
+    lib.bbs_ctx_set_profiling(ctx.handle, 1)
+
+    def step():
+        rc = lib.bbs_verify_batch_dev(ctx.handle, n, ptr(d_sigs), ptr(d_msgs), ptr(d_offs), L, ptr(d_status),
+                                      C.c_void_p(stream.cuda_stream))
+        if rc != 0:
+            raise RuntimeError(lib.bbs_last_error().decode())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    got = d_status.cpu().numpy()
+    if not np.array_equal(got, expect):
+        raise RuntimeError(f"status vector mismatch: {int((got != expect).sum())} of {n} items")
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ktimes = np.zeros((args.steps, 3), dtype=np.float32)
+    barrier()
+    for k in range(args.steps):
+        flush.fill_(k)                      # L2 flush between timed iterations (outside the timed events)
+        ev[k][0].record(stream)
+        step()
+        ev[k][1].record(stream)
+        ev[k][1].synchronize()
+        kt = (C.c_float * 3)()
+        lib.bbs_ctx_kernel_times(ctx.handle, kt, 3)
+        ktimes[k] = list(kt)
+    barrier()
+    clocks = sampler.stop()
+    launches = (ctx.launch_count() - launches0) // max(args.steps, 1)
+    ms = np.array([a.elapsed_time(b) for a, b in ev])
+    t_local = float(ms.sum()) * 1e-3
+    t = torch.tensor([t_local], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_max = float(t.item())
+    if not np.array_equal(d_status.cpu().numpy(), expect):
+        raise RuntimeError("status vector mismatch after the timed region")
+    value = world * n * args.steps / t_max
+
+    # ---- end-to-end arm: host (pinned) buffers through the reference-facing call, copies included ----
+    lib.bbs_ctx_set_profiling(ctx.handle, 0)
+    p_msgs = torch.from_numpy(msgs).pin_memory()
+    p_offs = torch.from_numpy(offs.view(np.int64)).pin_memory()
+    p_sigs = torch.from_numpy(sigs).pin_memory()
+    p_status = torch.zeros(n, dtype=torch.uint8).pin_memory()
+
+    def e2e_step():
+        rc = lib.bbs_verify_batch(ctx.handle, n, ptr(p_sigs), ptr(p_msgs), ptr(p_offs), L, ptr(p_status))
+        if rc != 0:
+            raise RuntimeError(lib.bbs_last_error().decode())
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    if not np.array_equal(p_status.numpy(), expect):
+        raise RuntimeError("e2e status vector mismatch")
+    e2e_value = world * n * args.steps / float(te.item())
+
+    out = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel (pairing), integer-multiply bound ------------------------
+        gprod = C.c_double()
+        pk_ms = C.c_float()
+        lib.bbs_imad_peak(local, 2000, C.byref(gprod), C.byref(pk_ms))
+        peak = gprod.value * 1e9
+        kmean = ktimes.mean(axis=0)
+        pairing_s = float(kmean[2]) * 1e-3
+        achieved = n * PRODUCTS_PAIRING / pairing_s
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        alg_bytes = n * (6 * 12 * 4 + 4 + 1)        # pair record + flags in, status out
+        cpu = cpu_baseline(args, sample=args.cpu_sample) if world == 1 and not args.no_cpu else None
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"BLS12-381-SHA-256 batch verify: {n} signatures x L={L} messages of 32 B, one issuer key, "
+                                   "1/16 corrupted (BASELINE configs[1])", "n_per_gpu": n, "L": L,
+                       "l2": "256 MB flush write between timed iterations", "sharding": "by signature index, no collective"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(msgs.nbytes + offs.nbytes + sigs.nbytes),
+                    "d2h_bytes_per_step": int(n)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "kernels_ms": {"msg_to_scalars": float(kmean[0]), "verify_g1": float(kmean[1]), "pairing": float(kmean[2])},
+            "roofline": {"kernel": "pairing_item<Bls> (2-pair Miller loop + final exponentiation)", "bound": "imad",
+                         "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T(32x32->64 products)/s",
+                         "frac": achieved / peak, "peak_source": "measured in this run (bbs_imad_peak); nominal 148 SM x 32/clk",
+                         "algorithmic_products_per_item": PRODUCTS_PAIRING,
+                         "whole_step_frac": value / world * PRODUCTS_PER_VERIFY / peak,
+                         "traffic": None,
+                         "hbm": {"achieved_gbs": alg_bytes / pairing_s / 1e9, "peak_gbs": hbm_peak,
+                                 "frac": alg_bytes / pairing_s / 1e9 / hbm_peak,
+                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+        }
+        if cpu:
+            out["cpu_baseline"] = cpu
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return out
+
+
+def cpu_baseline(args, sample):
+    """The oracle port of the reference's per-item path (msg_to_scalars + core_verify with two pairings) on
+    the host.  Uses oracle/_ref/ (compiled C restatement, all cores) when present, else the big-int Python
+    oracle on one core."""
+    from oracle import cpu_ref
+    return cpu_ref.time_verify(L=args.L, sample=sample)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    from oracle import cpu_ref
+    vals = []
+    for _ in range(args.warmup):
+        cpu_ref.time_verify(L=args.L, sample=max(args.cpu_sample // 4, 1))
+    last = None
+    t_total = 0.0
+    for _ in range(args.steps):
+        last = cpu_ref.time_verify(L=args.L, sample=args.cpu_sample)
+        vals.append(last["value"])
+        t_total += last["seconds"]
+    v = float(np.mean(vals))
+    return {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"BLS12-381-SHA-256 batch verify, L={args.L} messages of 32 B, one issuer key "
+                               f"(bounded sample of {args.cpu_sample} signatures per step of BASELINE configs[1])"},
+        "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=N_DEFAULT)
+    ap.add_argument("--L", type=int, default=L_DEFAULT)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="signatures per CPU-baseline step (0 = auto)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

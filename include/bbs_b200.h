@@ -141,6 +141,16 @@ int bbs_core_proof_verify_batch_dev(bbs_ctx* ctx, size_t n, const uint8_t* d_pro
 /* Number of kernels the library has launched on this context since creation (for bench accounting). */
 uint64_t bbs_ctx_launch_count(bbs_ctx* ctx);
 
+/* ---- measurement hooks ------------------------------------------------------------------------------
+ * With profiling on, every *_dev batch call records CUDA events on its launching stream around each of its
+ * kernels; bbs_ctx_kernel_times returns the durations (ms) of the last call in launch order:
+ *   verify / proof verify: [msg_to_scalars (0 if absent), G1 kernel, pairing kernel];  sign: [h2s, sign]. */
+int bbs_ctx_set_profiling(bbs_ctx* ctx, int on);
+int bbs_ctx_kernel_times(bbs_ctx* ctx, float* ms, int n);
+/* Integer-multiply roofline probe: independent mad.lo/mad.hi chains on every SM.  Returns the measured rate
+ * of full 32x32->64 products (one mad.lo + one mad.hi) in 1e9 products/s and the kernel time. */
+int bbs_imad_peak(int device, int iters, double* gprod_per_s, float* ms);
+
 /* ---- arithmetic self-test hooks (parity tests of the field / curve layers against the oracle) ------
  * op: 0 = Fp mul, 1 = Fp add, 2 = Fp sub, 3 = Fp inv, 4 = Fp sqrt (0 if none), 5 = Fr mul, 6 = Fr inv.
  * a, b, out: n x field-size canonical little-endian values (48 / 32 bytes for Fp, 32 for Fr). */
