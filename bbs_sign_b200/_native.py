@@ -50,7 +50,7 @@ SYMBOLS = {
                                                   C.c_void_p, C.c_void_p]),
     "bbs_ctx_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "bbs_ctx_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
-    "bbs_imad_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
+    "bbs_imad_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
     "bbs_selftest_field": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bbs_selftest_g1_mul": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bbs_selftest_pairing": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -65,7 +65,7 @@ _CACHE = {}
 
 
 def load(path: str | None = None) -> C.CDLL:
-    path = path or LIB_PATH
+    path = path or os.environ.get("BBS_B200_LIB") or LIB_PATH   # BBS_B200_LIB: alternative CUDA builds (tuning experiments)
     if path in _CACHE:
         return _CACHE[path]
     if not os.path.exists(path):

@@ -397,9 +397,9 @@ int bbs_ctx_kernel_times(bbs_ctx* p, float* ms, int n) {
     if (rt_set_device(c->device)) return BBS_E_CUDA;
     return c->prof.read(ms, n);
 }
-int bbs_imad_peak(int device, int iters, double* gprod_per_s, float* ms_out) {
+int bbs_imad_peak(int device, int iters, int mode, double* gprod_per_s, float* ms_out) {
     if (rt_set_device(device)) return BBS_E_CUDA;
-    return imad_peak(iters, gprod_per_s, ms_out);
+    return imad_peak(iters, mode, gprod_per_s, ms_out);
 }
 
 int bbs_msg_to_scalars(bbs_ctx* p, size_t count, const uint8_t* msgs, const uint64_t* off, uint8_t* out) {

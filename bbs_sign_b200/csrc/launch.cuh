@@ -27,7 +27,7 @@ inline int rt_stream_create(rt_stream_t* s) { *s = nullptr; return 0; }
 inline void rt_stream_destroy(rt_stream_t) {}
 inline int rt_set_stack(size_t) { return 0; }
 
-template <class Args, void (*Body)(const Args&, uint32_t), int TPB>
+template <class Args, void (*Body)(const Args&, uint32_t), int TPB, int MINB = 1>
 inline int rt_launch(const Args& a, uint32_t n, rt_stream_t) {
 #pragma omp parallel for schedule(dynamic, 16)
     for (int64_t i = 0; i < (int64_t)n; i++) Body(a, (uint32_t)i);
@@ -65,16 +65,16 @@ inline int rt_set_stack(size_t bytes) {
     return 0;
 }
 
-template <class Args, void (*Body)(const Args&, uint32_t), int TPB>
-__global__ void __launch_bounds__(TPB) k_items(const Args a, uint32_t n) {
+template <class Args, void (*Body)(const Args&, uint32_t), int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) k_items(const Args a, uint32_t n) {
     uint32_t i = blockIdx.x * TPB + threadIdx.x;
     if (i < n) Body(a, i);
 }
 
-template <class Args, void (*Body)(const Args&, uint32_t), int TPB>
+template <class Args, void (*Body)(const Args&, uint32_t), int TPB, int MINB = 1>
 inline int rt_launch(const Args& a, uint32_t n, rt_stream_t s) {
     if (n == 0) return 0;
-    k_items<Args, Body, TPB><<<(n + TPB - 1) / TPB, TPB, 0, s>>>(a, n);
+    k_items<Args, Body, TPB, MINB><<<(n + TPB - 1) / TPB, TPB, 0, s>>>(a, n);
     RT_CHECK(cudaGetLastError());
     return 0;
 }

@@ -2,10 +2,18 @@
 // with neither macro both curves are instantiated (host-simulation build).
 #include "launchers.cuh"
 
+// occupancy knobs (threads per block, min resident blocks per SM -> register cap); -D overridable
+#ifndef BBS_PAIRING_TPB
+#define BBS_PAIRING_TPB 128
+#endif
+#ifndef BBS_PAIRING_MINB
+#define BBS_PAIRING_MINB 4
+#endif
+
 namespace bbs {
 
 template <class C> int launch_pairing(const PairingArgs& a, uint32_t n, rt_stream_t s) {
-    return rt_launch<PairingArgs, &pairing_item<C>, 128>(a, n, s);
+    return rt_launch<PairingArgs, &pairing_item<C>, BBS_PAIRING_TPB, BBS_PAIRING_MINB>(a, n, s);
 }
 
 #if defined(BBS_TU_BLS) || !defined(BBS_TU_BN)

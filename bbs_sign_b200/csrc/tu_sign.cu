@@ -2,10 +2,18 @@
 // with neither macro both curves are instantiated (host-simulation build).
 #include "launchers.cuh"
 
+// occupancy knobs (threads per block, min resident blocks per SM -> register cap); -D overridable
+#ifndef BBS_SIGN_TPB
+#define BBS_SIGN_TPB 128
+#endif
+#ifndef BBS_SIGN_MINB
+#define BBS_SIGN_MINB 4
+#endif
+
 namespace bbs {
 
 template <class C> int launch_sign(const SignArgs& a, uint32_t n, rt_stream_t s) {
-    return rt_launch<SignArgs, &sign_item<C>, 128>(a, n, s);
+    return rt_launch<SignArgs, &sign_item<C>, BBS_SIGN_TPB, BBS_SIGN_MINB>(a, n, s);
 }
 
 #if defined(BBS_TU_BLS) || !defined(BBS_TU_BN)

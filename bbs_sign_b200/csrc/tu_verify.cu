@@ -2,10 +2,18 @@
 // with neither macro both curves are instantiated (host-simulation build).
 #include "launchers.cuh"
 
+// occupancy knobs (threads per block, min resident blocks per SM -> register cap); -D overridable
+#ifndef BBS_VERIFY_G1_TPB
+#define BBS_VERIFY_G1_TPB 128
+#endif
+#ifndef BBS_VERIFY_G1_MINB
+#define BBS_VERIFY_G1_MINB 4
+#endif
+
 namespace bbs {
 
 template <class C> int launch_verify_g1(const VerifyG1Args& a, uint32_t n, rt_stream_t s) {
-    return rt_launch<VerifyG1Args, &verify_g1_item<C>, 128>(a, n, s);
+    return rt_launch<VerifyG1Args, &verify_g1_item<C>, BBS_VERIFY_G1_TPB, BBS_VERIFY_G1_MINB>(a, n, s);
 }
 
 #if defined(BBS_TU_BLS) || !defined(BBS_TU_BN)

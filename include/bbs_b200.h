@@ -147,9 +147,10 @@ uint64_t bbs_ctx_launch_count(bbs_ctx* ctx);
  *   verify / proof verify: [msg_to_scalars (0 if absent), G1 kernel, pairing kernel];  sign: [h2s, sign]. */
 int bbs_ctx_set_profiling(bbs_ctx* ctx, int on);
 int bbs_ctx_kernel_times(bbs_ctx* ctx, float* ms, int n);
-/* Integer-multiply roofline probe: independent mad.lo/mad.hi chains on every SM.  Returns the measured rate
- * of full 32x32->64 products (one mad.lo + one mad.hi) in 1e9 products/s and the kernel time. */
-int bbs_imad_peak(int device, int iters, double* gprod_per_s, float* ms);
+/* Integer-multiply roofline probe: 8 independent multiply-accumulate chains per thread on every SM.
+ * mode 0: one mad.lo.u32 + one mad.hi.u32 per product; mode 1: one mad.wide.u32 (IMAD.WIDE) per product.
+ * Returns the measured rate of full 32x32->64 products in 1e9 products/s and the kernel time. */
+int bbs_imad_peak(int device, int iters, int mode, double* gprod_per_s, float* ms);
 
 /* ---- arithmetic self-test hooks (parity tests of the field / curve layers against the oracle) ------
  * op: 0 = Fp mul, 1 = Fp add, 2 = Fp sub, 3 = Fp inv, 4 = Fp sqrt (0 if none), 5 = Fr mul, 6 = Fr inv.

@@ -1,0 +1,61 @@
+"""Pins the oracle's C restatement (oracle/cref/bbs_cref.c) against the IRTF signature fixture
+(test_vector.rs:164-192) and against the big-int Python oracle on seeded random cases."""
+import hashlib
+import os
+import subprocess
+
+import pytest
+
+from oracle import bbs_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def CB():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle", "cref")], check=True, capture_output=True)
+    from oracle import cref_binding
+    return cref_binding
+
+
+def test_irtf_signature_fixture(CB):
+    cs = O.BLS12_381
+    sk = 0x60e55110f76883a13d030b2f6bd11883422d5abde717569fc0731f51237169fc
+    msg = bytes.fromhex("9872ad089e452c7b6e283dfac2a80d58e8d0ff71cc4d5e310a1debdda4a45f02")
+    header = bytes.fromhex("11223344556677889900aabbccddeeff")
+    ctx = CB.CrefContext(cs, O.sk_to_pk(cs, sk), O.create_generators_cached(cs, 2, cs.api_id))
+    sig, b = ctx.sign(sk, [msg], header)
+    assert (sig[:48] + sig[48:][::-1]).hex() == (
+        "84773160b824e194073a57493dac1a20b667af70cd2352d8af241c77658da5253aa8458317cca0eae615690d55b1f271"
+        "64657dcafee1d5c1973947aa70e2cfbb4c892340be5969920d0916067b4565a0")
+    assert b.hex() == "92d264aed02bf23de022ebe778c4f929fddf829f504e451d011ed89a313b8167ac947332e1648157ceffc6e6e41ab255"
+    assert ctx.verify_batch(sig, [[msg]], header).tolist() == [1]
+
+
+@pytest.mark.parametrize("L", [0, 1, 5])
+def test_against_python_oracle(CB, L):
+    cs = O.BLS12_381
+    sk = O.key_gen(cs, hashlib.sha256(b"k1").digest(), b"", b"BBS-SIG-KEYGEN-SALT-")
+    sk2 = O.key_gen(cs, hashlib.sha256(b"k2").digest(), b"", b"BBS-SIG-KEYGEN-SALT-")
+    pk = O.sk_to_pk(cs, sk)
+    gens = O.create_generators_cached(cs, L + 1, cs.api_id)
+    ctx = CB.CrefContext(cs, pk, gens)
+    items, exp = [], []
+    for i in range(8):
+        msgs = [hashlib.sha256(f"{L}/{i}/{j}".encode()).digest()[: (5 if j % 2 else 32)] for j in range(L)]
+        sig = O.sign(cs, sk, msgs, b"hd")
+        csig, _ = ctx.sign(sk, msgs, b"hd")
+        assert csig == O.signature_to_bytes(cs, sig)           # C sign == Python sign, byte for byte
+        kind = i % 4
+        if kind == 1:
+            sig = (sig[0], (sig[1] + 1) % cs.r)
+        elif kind == 2:
+            sig = (None, sig[1])
+        elif kind == 3:
+            sig = O.sign(cs, sk2, msgs, b"hd")
+        items.append((sig, msgs))
+        exp.append(int(O.verify(cs, pk, sig, b"hd", msgs, trapdoor_sk=sk)))
+    st = ctx.verify_batch(b"".join(O.signature_to_bytes(cs, s) for s, _ in items), [m for _, m in items], b"hd")
+    assert st.tolist() == exp
+    # the pairing itself (no trapdoor) on one valid and one forged item
+    assert O.verify(cs, pk, items[0][0], b"hd", items[0][1]) == bool(st[0])
