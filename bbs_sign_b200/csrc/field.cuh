@@ -52,6 +52,7 @@
 
 #include "gen_constants.cuh"
 #include "gen_mont_asm.cuh"
+#include "gen_mont_mul.cuh"
 
 namespace bbs {
 
@@ -227,23 +228,11 @@ template <class F>
 BBS_HD void fe_mul_inl(uint32_t* r, const uint32_t* a, const uint32_t* b) {
     constexpr int N = F::N;
 #ifdef __CUDA_ARCH__
-    uint32_t A[N], B[N], M[N], t[N + 1];
+    uint32_t A[N], B[N], M[N], t[N];
     const uint32_t* pm = F::P();
 #pragma unroll
     for (int i = 0; i < N; i++) { A[i] = a[i]; B[i] = b[i]; M[i] = pm[i]; }
-#pragma unroll
-    for (int i = 0; i <= N; i++) t[i] = 0;
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-        bbs_mad_even<N>(t, A, B[i]);
-        bbs_mad_odd<N>(t, A, B[i]);
-        uint32_t m = t[0] * F::INV;
-        bbs_mad_even<N>(t, M, m);
-        bbs_mad_odd<N>(t, M, m);
-#pragma unroll
-        for (int j = 0; j < N; j++) t[j] = t[j + 1];
-        t[N] = 0;
-    }
+    bbs_mont_mul<N>(t, A, B, M, F::INV);      // two-accumulator CIOS, result < 2p (gen_mont_mul.cuh)
     uint32_t d[N];
     uint32_t borrow = bbs_subn<N>(d, t, M);
 #pragma unroll

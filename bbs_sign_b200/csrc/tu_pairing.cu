@@ -7,7 +7,7 @@
 #define BBS_PAIRING_TPB 128
 #endif
 #ifndef BBS_PAIRING_MINB
-#define BBS_PAIRING_MINB 4
+#define BBS_PAIRING_MINB 2
 #endif
 
 namespace bbs {
