@@ -50,14 +50,16 @@ struct Ctx {
     bool profile = false;            // bbs_ctx_set_profiling: CUDA events around each kernel of a batch call
     ProfEvents prof;
     DevBuf pk_comp, gens_comp, api_id, header, dst_h2s, dst_map;
-    DevBuf gens, W, K, domain, tab, lines, misc;
+    DevBuf gens, W, K, domain, tab, lines, lines_coop, misc;
+    bool coop = false;               // cooperative pairing kernel usable (BLS12-381, no degenerate line)
     CtxView view{};
     // grow-only scratch for the batch calls
+    DevBuf s_gscr;
     DevBuf s_sigs, s_scalars, s_msgs, s_offsets, s_pair, s_flags, s_status, s_out, s_out2;
     DevBuf s_commit, s_commit_off, s_dis_idx, s_dis_scalars, s_dis_off, s_ph, s_dis_msgs, s_dis_msg_off;
     void release_all() {
         DevBuf* all[] = {&pk_comp, &gens_comp, &api_id, &header, &dst_h2s, &dst_map, &gens, &W, &K, &domain, &tab,
-                         &lines, &misc, &s_sigs, &s_scalars, &s_msgs, &s_offsets, &s_pair, &s_flags, &s_status, &s_out,
+                         &lines, &lines_coop, &s_gscr, &misc, &s_sigs, &s_scalars, &s_msgs, &s_offsets, &s_pair, &s_flags, &s_status, &s_out,
                          &s_out2, &s_commit, &s_commit_off, &s_dis_idx, &s_dis_scalars, &s_dis_off, &s_ph, &s_dis_msgs,
                          &s_dis_msg_off};
         for (DevBuf* b : all) b->release();
@@ -136,6 +138,22 @@ struct Impl {
         TRY((launch_ctx_lines<C>(la, 2, s)));
         TRY(rt_sync(s));
         c->launches += 4;
+        // 5. normalised line table of the cooperative pairing kernel
+        c->coop = false;
+#ifndef BBS_HOSTSIM
+        if (C::ID == Bls::ID) {
+            TRY(c->lines_coop.reserve((size_t)n_lines * 2 * 4 * C::Fp::N * 4));
+            uint32_t* d_deg = d_status;
+            TRY(rt_memset(d_deg, 0, 4, s));
+            CtxLinesCoopArgs lc{(const uint32_t*)c->lines.p, (uint32_t*)c->lines_coop.p, d_deg, w_inf};
+            TRY((launch_ctx_lines_coop<C>(lc, (uint32_t)(2 * n_lines), s)));
+            uint32_t deg = 0;
+            TRY(rt_d2h(&deg, d_deg, 4, s));
+            TRY(rt_sync(s));
+            c->launches += 1;
+            c->coop = deg == 0 && !getenv("BBS_NO_COOP");
+        }
+#endif
         CtxView& v = c->view;
         v.L = L; v.w_inf = w_inf; v.k_inf = k_inf;
         v.dst_h2s = (const uint8_t*)c->dst_h2s.p; v.dst_h2s_len = (uint32_t)dsth.size();
@@ -154,6 +172,16 @@ struct Impl {
     }
 
     static int pairing_dev(Ctx* c, size_t n, uint8_t* d_status, rt_stream_t s) {
+#ifndef BBS_HOSTSIM
+        if (c->coop) {
+            TRY(c->s_gscr.reserve(coop_gscratch_bytes_bls(n)));
+            CoopArgs ca{(const uint32_t*)c->lines_coop.p, (const uint32_t*)c->s_pair.p, (const uint32_t*)c->s_flags.p,
+                        d_status, (uint32_t*)c->s_gscr.p, (uint32_t)n};
+            TRY(launch_pairing_coop_bls(ca, s));
+            c->launches += n ? 1 : 0;
+            return BBS_OK;
+        }
+#endif
         PairingArgs pa{c->view.lines, (const uint32_t*)c->s_pair.p, (const uint32_t*)c->s_flags.p, d_status};
         TRY((launch_pairing<C>(pa, (uint32_t)n, s)));
         c->launches += n ? 1 : 0;

@@ -99,6 +99,22 @@ template <class C> BBS_HD void ctx_lines_item(const CtxLinesArgs& a, uint32_t i)
     else g2_precompute_lines<C>(a.lines, C::G2(), 1);
 }
 
+// Line table of the cooperative pairing kernel: entry (line, pair) = (Bc / A, 1 / A), i.e. the line scaled to
+// constant term 1 (any Fp2 factor dies in the final exponentiation).  A == 0 (a tangent / chord through the origin,
+// impossible for an honest key) is reported so that the context falls back to the per-thread kernel.
+struct CtxLinesCoopArgs { const uint32_t* lines; uint32_t* lines2; uint32_t* degenerate; uint32_t w_inf; };
+template <class C> BBS_HD void ctx_lines_coop_item(const CtxLinesCoopArgs& a, uint32_t i) {
+    const uint32_t* src = a.lines + (size_t)i * LINE_WORDS;
+    uint32_t* dst = a.lines2 + ((size_t)(i >> 1) * 4 + (i & 1) * 2) * F2N;
+    if ((i & 1) == 0 && a.w_inf) { bn_zero<4 * C::Fp::N>(dst); return; }
+    if (f2_is_zero<C>(src)) { *a.degenerate = 1; bn_zero<4 * C::Fp::N>(dst); return; }
+    uint32_t ai[F2N], bp[F2N];
+    f2_inv<C>(ai, src);
+    f2_mul<C>(bp, src + F2N, ai);
+    f2_copy<C>(dst, bp);
+    f2_copy<C>(dst + F2N, ai);
+}
+
 // ---- msg_to_scalars ----------------------------------------------------------------------------------
 struct H2sArgs {
     const uint8_t* msgs; const uint64_t* offsets;   // message t = msgs[offsets[t] .. offsets[t+1])
@@ -164,12 +180,16 @@ template <class C> BBS_HD void verify_g1_item(const VerifyG1Args& a, uint32_t i)
         g1_mul_affine<C>(eA, A, e, C::Fr::BITS);
         g1_add<C>(Cc, Cc, eA);
     }
+    // both pairing arguments leave this kernel affine: (x, y, 1).  The cooperative pairing kernel normalises its
+    // lines to constant term 1, which needs Z = 1 (pairing_coop.cuh); the per-thread kernel accepts it as (XZ, Y, Z^3).
     uint32_t* pr = a.pair + (size_t)i * PAIR_WORDS;
     bn_copy<2 * C::Fp::N>(pr, A); fe_set_one<typename C::Fp>(pr + 2 * FPN);
-    g1_to_line_arg<C>(pr + 3 * FPN, Cc);
+    uint32_t caff[G1A];
+    bool cfin = g1_to_affine<C>(caff, Cc);
+    bn_copy<2 * C::Fp::N>(pr + 3 * FPN, caff); fe_set_one<typename C::Fp>(pr + 5 * FPN);
     uint32_t fl = 0;
     if (pa == PT_INF || cx.w_inf) fl |= FL_SKIP0;
-    if (g1_is_inf<C>(Cc)) fl |= FL_SKIP1;
+    if (!cfin) fl |= FL_SKIP1;
     a.flags[i] = fl;
 }
 

@@ -2,6 +2,7 @@
 // (tu_*.cu, compiled once per curve) so the library builds in parallel; capi.cu only sees declarations.
 #pragma once
 #include "kernels.cuh"
+#include "pairing_coop.cuh"
 #include "selftest.cuh"
 #include "launch.cuh"
 
@@ -11,9 +12,15 @@ template <class C> int launch_ctx_decode(const CtxDecodeArgs& a, uint32_t n, rt_
 template <class C> int launch_ctx_domain(const CtxDomainArgs& a, uint32_t n, rt_stream_t s);
 template <class C> int launch_ctx_table(const CtxTableArgs& a, uint32_t n, rt_stream_t s);
 template <class C> int launch_ctx_lines(const CtxLinesArgs& a, uint32_t n, rt_stream_t s);
+template <class C> int launch_ctx_lines_coop(const CtxLinesCoopArgs& a, uint32_t n, rt_stream_t s);
 template <class C> int launch_h2s(const H2sArgs& a, uint32_t n, rt_stream_t s);
 template <class C> int launch_verify_g1(const VerifyG1Args& a, uint32_t n, rt_stream_t s);
 template <class C> int launch_pairing(const PairingArgs& a, uint32_t n, rt_stream_t s);
+#ifndef BBS_HOSTSIM
+// cooperative kernel (BLS12-381 only so far); gscratch must hold coop_gscratch_bytes(n)
+int launch_pairing_coop_bls(const CoopArgs& a, rt_stream_t s);
+size_t coop_gscratch_bytes_bls(size_t n);
+#endif
 template <class C> int launch_sign(const SignArgs& a, uint32_t n, rt_stream_t s);
 template <class C> int launch_proof_g1(const ProofG1Args& a, uint32_t n, rt_stream_t s);
 template <class C> int launch_field_test(const FieldTestArgs& a, uint32_t n, rt_stream_t s);

@@ -1,0 +1,285 @@
+// Cooperative pairing kernel: "e(P0, Q0) e(P1, Q1) == 1" for 32 items per thread block, SIX warps per block.
+// Warp k (a ROLE) owns the Fp2 coefficient c_k of every Fp12 value f = sum c_k w^k in Fp2[w]/(w^6 - xi); lane =
+// item.  All values live in shared-memory cells; each role interprets its own instruction stream
+// (gen_pairing_prog.cuh, built and verified against the oracle by tools/coop_prog.py):
+//     EP  : acc_R +-= X*Y, acc_I +-= X*Y     one 12x12-limb product (two fresh half products on IMAD.WIDE chains)
+//                                            fed to the double-width real / imaginary accumulators
+//     FIN : cell = canon(REDC(3^t acc +- 2^d Z R + KP))   ONE Montgomery reduction per output coefficient
+// so an Fp12 product costs 18 EPs + 2 reductions per role (Karatsuba at the Fp2 level, schoolbook above, lazy
+// reduction) with no operand pre-additions beyond c0 +- c1, and the Fp12 state never touches local memory.
+// Replaces the per-thread pairing_item for BLS12-381 (verify.rs:88-92, proof_verify.rs:112-115).
+#pragma once
+#include "kernels.cuh"
+
+#ifdef __CUDACC__
+#include "gen_coop.cuh"
+#include "gen_pairing_prog.cuh"
+
+namespace bbs {
+
+constexpr int COOP_ROLES = 6;
+constexpr int COOP_ITEMS = 32;                 // items per block = lanes
+constexpr int COOP_CELLS = 24;
+constexpr int COOP_TPB = COOP_ROLES * 32;
+
+struct CoopArgs {
+    const uint32_t* lines;     // per ate line: B'0, A'0, B'1, A'1 (Fp2 each, Montgomery): 8N words
+    const uint32_t* pair;      // per item: P0 = (x, y, 1), P1 = (x, y, 1) affine Montgomery (6N words)
+    const uint32_t* flags;
+    uint8_t* status;
+    uint32_t* gscratch;        // per block: COOP_ROLES cells
+    uint32_t n;
+};
+
+// ---- per-curve bindings of the generated primitives ---------------------------------------------------------
+template <class C> struct Coop;
+template <> struct Coop<Bls> {
+    static constexpr int N = 12;
+    static __device__ __forceinline__ const uint32_t* prog() { return COOP_PROG_BLS; }
+    static __device__ __forceinline__ const uint32_t* prog_off() { return COOP_PROG_OFF_BLS; }
+    static __device__ __forceinline__ const uint32_t* consts() { return COOP_CONSTS_BLS; }
+    static __device__ __forceinline__ const uint32_t* kp() { return COOP_KP_BLS; }
+    static __device__ __forceinline__ void wmul_e(uint32_t* w, const uint32_t* a, const uint32_t* b) { coop_wmul_e12(w, a, b); }
+    static __device__ __forceinline__ void wmul_o(uint32_t* w, const uint32_t* a, const uint32_t* b) { coop_wmul_o12(w, a, b); }
+    static __device__ __forceinline__ void add_e(uint32_t* acc, const uint32_t* w) { coop_acc_add_e12(acc, w); }
+    static __device__ __forceinline__ void sub_e(uint32_t* acc, const uint32_t* w) { coop_acc_sub_e12(acc, w); }
+    static __device__ __forceinline__ void add_o(uint32_t* acc, const uint32_t* w) { coop_acc_add_o12(acc, w); }
+    static __device__ __forceinline__ void sub_o(uint32_t* acc, const uint32_t* w) { coop_acc_sub_o12(acc, w); }
+    static __device__ __forceinline__ void add_hi(uint32_t* acc, const uint32_t* z) { coop_acc_add_hi12(acc, z); }
+    static __device__ __forceinline__ void sub_hi(uint32_t* acc, const uint32_t* z) { coop_acc_sub_hi12(acc, z); }
+    static __device__ __forceinline__ void addn(uint32_t* d, const uint32_t* s) { coop_addn12(d, s); }
+    static __device__ __forceinline__ void subn(uint32_t* d, const uint32_t* s) { coop_subn12(d, s); }
+    static __device__ __forceinline__ void add_p(uint32_t* d) { coop_add_p_bls(d); }
+    static __device__ __forceinline__ void redc(uint32_t* r, uint32_t* t) { coop_redc_bls(r, t); }
+    template <int K> static __device__ __forceinline__ uint32_t sub_kp(uint32_t* d, const uint32_t* r) {
+        if (K == 8) return coop_sub_8p_bls(d, r);
+        if (K == 4) return coop_sub_4p_bls(d, r);
+        if (K == 2) return coop_sub_2p_bls(d, r);
+        return coop_sub_1p_bls(d, r);
+    }
+};
+
+// ---- shared-memory cells: cell c = [comp 2][quad N/4][lane 32] uint4 ---------------------------------------------
+template <int N> __device__ __forceinline__ void coop_load(uint32_t* x, const uint4* p) {
+#pragma unroll
+    for (int q = 0; q < N / 4; q++) {
+        uint4 v = p[q * 32];
+        x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+    }
+}
+template <int N> __device__ __forceinline__ void coop_store(uint4* p, const uint32_t* x) {
+#pragma unroll
+    for (int q = 0; q < N / 4; q++) p[q * 32] = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+}
+template <int N> __device__ __forceinline__ void coop_load_g(uint32_t* x, const uint32_t* p) {
+#pragma unroll
+    for (int q = 0; q < N / 4; q++) {
+        uint4 v = __ldg((const uint4*)p + q);
+        x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+    }
+}
+template <int N> __device__ __forceinline__ void coop_shl(uint32_t* x, int s) {
+#pragma unroll
+    for (int i = N - 1; i > 0; i--) x[i] = __funnelshift_l(x[i - 1], x[i], s);
+    x[0] <<= s;
+}
+
+// operand in one of the four forms of the instruction set (tools/coop_prog.py): c0, c1, c0 + c1, c0 - c1 + p
+template <class C, bool GLOBAL> __device__ __forceinline__ void coop_operand(uint32_t* x, const void* cellp, int form, int shift) {
+    constexpr int N = Coop<C>::N;
+    uint32_t t[N];
+    if (GLOBAL) {
+        const uint32_t* g = (const uint32_t*)cellp;
+        if (form == 1) coop_load_g<N>(x, g + N); else coop_load_g<N>(x, g);
+        if (form >= 2) {
+            coop_load_g<N>(t, g + N);
+            if (form == 2) Coop<C>::addn(x, t); else { Coop<C>::subn(x, t); Coop<C>::add_p(x); }
+        }
+    } else {
+        const uint4* s = (const uint4*)cellp;
+        if (form == 1) coop_load<N>(x, s + (N / 4) * 32); else coop_load<N>(x, s);
+        if (form >= 2) {
+            coop_load<N>(t, s + (N / 4) * 32);
+            if (form == 2) Coop<C>::addn(x, t); else { Coop<C>::subn(x, t); Coop<C>::add_p(x); }
+        }
+    }
+    if (shift) coop_shl<N>(x, shift);
+}
+
+// one output component: acc -> canonical Fp
+template <class C> __device__ __forceinline__ void coop_finish(uint32_t* r, uint32_t* acc, uint32_t ins, const uint4* zp) {
+    constexpr int N = Coop<C>::N;
+    if ((ins >> 10) & 1) {                       // triple
+        uint32_t t[2 * N + 1];
+#pragma unroll
+        for (int i = 2 * N; i > 0; i--) t[i] = __funnelshift_l(acc[i - 1], acc[i], 1);
+        t[0] = acc[0] << 1;
+        Coop<C>::add_e(acc, t);                  // low 2N words + carry into the top word
+        acc[2 * N] += t[2 * N];
+    }
+    uint32_t zs = (ins >> 11) & 3;
+    if (zs) {
+        uint32_t z[N];
+        coop_load<N>(z, zp);
+        if ((ins >> 13) & 1) coop_shl<N>(z, 1);
+        if (zs == 1) Coop<C>::add_hi(acc, z); else Coop<C>::sub_hi(acc, z);
+    }
+    uint32_t kp = (ins >> 22) & 3;
+    if (kp) {
+        uint32_t k[2 * N];
+        const uint32_t* kt = Coop<C>::kp() + kp * (2 * N + 1);
+#pragma unroll
+        for (int i = 0; i < 2 * N; i++) k[i] = kt[i];
+        Coop<C>::add_e(acc, k);
+    }
+    Coop<C>::redc(r, acc);
+    uint32_t canon = (ins >> 24) & 3;
+    uint32_t d[N], b;
+    if (canon >= 3) { b = Coop<C>::template sub_kp<8>(d, r);
+#pragma unroll
+        for (int i = 0; i < N; i++) r[i] = b ? r[i] : d[i]; }
+    if (canon >= 2) { b = Coop<C>::template sub_kp<4>(d, r);
+#pragma unroll
+        for (int i = 0; i < N; i++) r[i] = b ? r[i] : d[i]; }
+    if (canon >= 1) { b = Coop<C>::template sub_kp<2>(d, r);
+#pragma unroll
+        for (int i = 0; i < N; i++) r[i] = b ? r[i] : d[i]; }
+    b = Coop<C>::template sub_kp<1>(d, r);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = b ? r[i] : d[i];
+}
+
+#ifndef BBS_COOP_MAXREG
+#define BBS_COOP_MAXREG 112
+#endif
+
+template <class C>
+__global__ void __maxnreg__(BBS_COOP_MAXREG) pairing_coop_kernel(const CoopArgs a) {
+    constexpr int N = Coop<C>::N;
+    constexpr int Q = N / 4;
+    constexpr int CELL = 2 * Q * 32;           // uint4 per cell
+    extern __shared__ uint4 smem[];
+    uint32_t* votes = (uint32_t*)(smem + COOP_CELLS * CELL);      // [role][lane]
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    const uint32_t item = blockIdx.x * COOP_ITEMS + lane;
+    const bool valid = item < a.n;
+    const uint32_t fl = valid ? a.flags[item] : (uint32_t)(FL_DONE | FL_SKIP0 | FL_SKIP1);
+    uint4* cells = smem + lane;
+
+    // prologue: f = 1 in slot 0 (cells 0..5), P0 -> cell 16, P1 -> cell 17 (x in c0, y in c1)
+    {
+        uint32_t v[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) v[i] = (role == 0) ? C::Fp::ONE()[i] : 0u;
+        coop_store<N>(cells + role * CELL, v);
+#pragma unroll
+        for (int i = 0; i < N; i++) v[i] = 0u;
+        coop_store<N>(cells + role * CELL + Q * 32, v);
+        if (role < 4) {
+            // role r loads coordinate (r & 1) of point (r >> 1)
+            const uint32_t* src = a.pair + (size_t)(valid ? item : 0) * (6 * N) + (role >> 1) * 3 * N + (role & 1) * N;
+#pragma unroll
+            for (int i = 0; i < N; i++) v[i] = valid ? src[i] : 0u;
+            coop_store<N>(cells + (16 + (role >> 1)) * CELL + (role & 1) * Q * 32, v);
+        }
+    }
+    __syncthreads();
+
+    const uint32_t* prog = Coop<C>::prog() + Coop<C>::prog_off()[role];
+    uint32_t pc = 0, line = 0;
+    uint32_t rep_pc[2], rep_cnt[2];
+    int rep_sp = 0;
+    uint32_t R[2 * N + 1], I[2 * N + 1];
+#pragma unroll
+    for (int i = 0; i <= 2 * N; i++) { R[i] = 0; I[i] = 0; }
+    uint32_t ins = __ldg(prog);
+    for (;;) {
+        const uint32_t cur = ins;
+        pc++;
+        ins = __ldg(prog + pc);                  // prefetch (streams end with END, one word of slack is harmless)
+        const uint32_t kind = cur & 3;
+        if (kind == 0) {
+            // ---- EP ------------------------------------------------------------------------------------------
+            uint32_t x[N], y[N], w[2 * N];
+            coop_operand<C, false>(x, cells + ((cur >> 6) & 255) * CELL, (cur >> 14) & 3, (cur >> 16) & 3);
+            const uint32_t yc = (cur >> 18) & 255;
+            if ((cur >> 30) & 1) {
+                const uint32_t* g = yc >= 128 ? a.lines + ((size_t)line * 4 + (yc - 128)) * (2 * N)
+                                              : Coop<C>::consts() + yc * (2 * N);
+                coop_operand<C, true>(y, g, (cur >> 26) & 3, (cur >> 28) & 3);
+            } else {
+                coop_operand<C, false>(y, cells + yc * CELL, (cur >> 26) & 3, (cur >> 28) & 3);
+            }
+            const uint32_t sR = (cur >> 2) & 3, sI = (cur >> 4) & 3;
+            Coop<C>::wmul_e(w, x, y);
+            if (sR == 1) Coop<C>::add_e(R, w); else if (sR == 2) Coop<C>::sub_e(R, w);
+            if (sI == 1) Coop<C>::add_e(I, w); else if (sI == 2) Coop<C>::sub_e(I, w);
+            Coop<C>::wmul_o(w, x, y);
+            if (sR == 1) Coop<C>::add_o(R, w); else if (sR == 2) Coop<C>::sub_o(R, w);
+            if (sI == 1) Coop<C>::add_o(I, w); else if (sI == 2) Coop<C>::sub_o(I, w);
+        } else if (kind == 1) {
+            // ---- FIN -----------------------------------------------------------------------------------------
+            uint32_t r[N];
+            const uint4* zp = cells + ((cur >> 14) & 255) * CELL;
+            uint4* dp = cells + ((cur >> 2) & 255) * CELL;
+            const uint32_t sk = (cur >> 27) & 3;
+            const bool zero = (sk & 1) && (fl & ((sk & 2) ? FL_SKIP1 : FL_SKIP0));
+            coop_finish<C>(r, R, cur, zp);
+#pragma unroll
+            for (int i = 0; i < N; i++) r[i] = zero ? 0u : r[i];
+            coop_store<N>(dp, r);
+            if ((cur >> 29) & 1) {               // Fp only
+#pragma unroll
+                for (int i = 0; i < N; i++) r[i] = 0u;
+            } else {
+                coop_finish<C>(r, I, cur, zp + Q * 32);
+#pragma unroll
+                for (int i = 0; i < N; i++) r[i] = zero ? 0u : r[i];
+            }
+            coop_store<N>(dp + Q * 32, r);
+#pragma unroll
+            for (int i = 0; i <= 2 * N; i++) { R[i] = 0; I[i] = 0; }
+            if ((cur >> 26) & 1) __syncthreads();
+        } else {
+            // ---- CTL -----------------------------------------------------------------------------------------
+            const uint32_t sub = (cur >> 2) & 15, arg = cur >> 6;
+            if (sub == 0) break;                                           // END
+            if (sub == 1) { rep_pc[rep_sp] = pc; rep_cnt[rep_sp] = arg; rep_sp++; }           // REP
+            else if (sub == 2) {                                           // ENDREP
+                if (--rep_cnt[rep_sp - 1] > 0) { pc = rep_pc[rep_sp - 1]; ins = __ldg(prog + pc); } else rep_sp--;
+            }
+            else if (sub == 3) line++;                                     // NEXTLINE
+            else if (sub == 4) __syncthreads();                            // BAR
+            else if (sub == 5 || sub == 6) {                               // GSAVE / GLOAD (own cell <-> global)
+                uint4* g = (uint4*)a.gscratch + ((size_t)blockIdx.x * COOP_ROLES + role) * CELL + lane;
+                uint4* c = cells + arg * CELL;
+#pragma unroll
+                for (int q = 0; q < 2 * Q; q++) { if (sub == 5) g[q * 32] = c[q * 32]; else c[q * 32] = g[q * 32]; }
+            }
+            else if (sub == 7) {                                           // CHECK: result == 1 ?
+                uint32_t v[N], o = 0;
+                coop_load<N>(v, cells + arg * CELL);
+#pragma unroll
+                for (int i = 0; i < N; i++) o |= v[i] ^ ((role == 0) ? C::Fp::ONE()[i] : 0u);
+                coop_load<N>(v, cells + arg * CELL + Q * 32);
+#pragma unroll
+                for (int i = 0; i < N; i++) o |= v[i];
+                votes[role * 32 + lane] = o;
+                __syncthreads();
+                if (role == 0) {
+                    uint32_t all = 0;
+#pragma unroll
+                    for (int k = 0; k < COOP_ROLES; k++) all |= votes[k * 32 + lane];
+                    if (valid && !(fl & FL_DONE)) a.status[item] = all == 0 ? ST_ACCEPT : ST_REJECT;
+                }
+            }
+        }
+    }
+}
+
+template <class C> constexpr size_t coop_smem_bytes() {
+    return (size_t)COOP_CELLS * (2 * (Coop<C>::N / 4) * 32) * sizeof(uint4) + COOP_ROLES * 32 * sizeof(uint32_t);
+}
+
+}  // namespace bbs
+#endif  // __CUDACC__

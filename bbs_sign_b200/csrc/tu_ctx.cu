@@ -17,13 +17,19 @@ template <class C> int launch_ctx_lines(const CtxLinesArgs& a, uint32_t n, rt_st
     return rt_launch<CtxLinesArgs, &ctx_lines_item<C>, 32>(a, n, s);
 }
 
+template <class C> int launch_ctx_lines_coop(const CtxLinesCoopArgs& a, uint32_t n, rt_stream_t s) {
+    return rt_launch<CtxLinesCoopArgs, &ctx_lines_coop_item<C>, 32>(a, n, s);
+}
+
 #if defined(BBS_TU_BLS) || !defined(BBS_TU_BN)
+template int launch_ctx_lines_coop<Bls>(const CtxLinesCoopArgs&, uint32_t, rt_stream_t);
 template int launch_ctx_decode<Bls>(const CtxDecodeArgs&, uint32_t, rt_stream_t);
 template int launch_ctx_domain<Bls>(const CtxDomainArgs&, uint32_t, rt_stream_t);
 template int launch_ctx_table<Bls>(const CtxTableArgs&, uint32_t, rt_stream_t);
 template int launch_ctx_lines<Bls>(const CtxLinesArgs&, uint32_t, rt_stream_t);
 #endif
 #if defined(BBS_TU_BN) || !defined(BBS_TU_BLS)
+template int launch_ctx_lines_coop<Bn>(const CtxLinesCoopArgs&, uint32_t, rt_stream_t);
 template int launch_ctx_decode<Bn>(const CtxDecodeArgs&, uint32_t, rt_stream_t);
 template int launch_ctx_domain<Bn>(const CtxDomainArgs&, uint32_t, rt_stream_t);
 template int launch_ctx_table<Bn>(const CtxTableArgs&, uint32_t, rt_stream_t);

@@ -1,0 +1,660 @@
+#!/usr/bin/env python3
+"""Program builder + big-int emulator for the cooperative pairing kernel (bbs_sign_b200/csrc/pairing_coop.cuh).
+
+The kernel is an interpreter: a thread block owns 32 items (lane = item) and has one warp per ROLE; role k
+owns the Fp2 coefficient c_k of every Fp12 value  f = sum c_k w^k  in  Fp2[w]/(w^6 - xi).  All values live in
+shared-memory CELLS (one Fp2 per cell and item, Montgomery form, canonical).  A role executes its own stream:
+
+  EP   acc_R += sR * X*Y, acc_I += sI * X*Y      X, Y = Fp operands derived from a cell:
+                                                 form 0: c0, 1: c1, 2: c0+c1, 3: c0-c1+p, shifted left by 0..2;
+                                                 Y may come from the global constant table instead of a cell
+  FIN  cell[dst] = canon( REDC( 3^t * acc + zs * 2^zd * Z * R + KP[k] ) )   per component, then acc = 0
+  CTL  REP n / ENDREP / NEXTLINE / BAR / GSAVE / GLOAD / CHECK / END
+
+i.e. every output coefficient is ONE lazily-reduced sum of double-width products (Karatsuba at the Fp2 level:
+three EPs per Fp2 product, each feeding the real and/or imaginary accumulator with a sign).  This file builds the
+per-role streams for  "e(P0,Q0) e(P1,Q1) == 1"  (two-pair Miller loop over precomputed, Fp2-normalised lines +
+final exponentiation), emulates them on Python integers exactly as the kernel computes (Montgomery domain, same
+accumulator / REDC / canonicalisation arithmetic, with range assertions and a barrier-hazard checker), and is
+imported by tools/gen_pairing_prog.py (emission) and tests/test_coop_program.py (parity with the oracle).
+
+Replaces, together with the kernel, the two `E::pairing` calls of verify.rs:88-92 / proof_verify.rs:112-115.
+"""
+from dataclasses import dataclass
+from fractions import Fraction
+
+ROLES = 6
+NCELLS = 24            # shared-memory cells per block (4 Fp12 values)
+
+K_EP, K_FIN, K_CTL = 0, 1, 2
+C_END, C_REP, C_ENDREP, C_NEXTLINE, C_BAR, C_GSAVE, C_GLOAD, C_CHECK = range(8)
+F_C0, F_C1, F_SUM, F_DIFF = range(4)
+FORM_BOUND = {F_C0: 1, F_C1: 1, F_SUM: 2, F_DIFF: 2}     # in units of p (cells are canonical)
+LINE_BASE = 128        # global-constant ids >= LINE_BASE address the line table relative to the line counter
+KP_MULT = (0, 8, 24, 40)         # KP[k] = KP_MULT[k] * p^2, added before REDC so the accumulator is >= 0
+CANON_STEPS = (1, 2, 3, 4)       # canon level l: output < 2^(l+1) p, conditional subtractions of 2^l p ... p
+
+
+@dataclass
+class Operand:
+    cell: int
+    form: int = F_C0
+    shift: int = 0
+    glob: bool = False     # Y only: global constant table
+
+
+def enc_ep(sR, sI, x, y):
+    assert not x.glob
+    sg = {0: 0, 1: 1, -1: 2}
+    assert 0 <= x.cell < 256 and 0 <= y.cell < 256 and x.shift <= 2 and y.shift <= 2
+    return (K_EP | (sg[sR] << 2) | (sg[sI] << 4) | (x.cell << 6) | (x.form << 14) | (x.shift << 16) |
+            (y.cell << 18) | (y.form << 26) | (y.shift << 28) | ((1 if y.glob else 0) << 30))
+
+
+def enc_fin(dst, triple=0, zsign=0, zdouble=0, zcell=0, kp=0, canon=3, bar=0, skip_pair=None, fp_only=0):
+    zs = {0: 0, 1: 1, -1: 2}[zsign]
+    sk = 0 if skip_pair is None else (1 | (skip_pair << 1))
+    return (K_FIN | (dst << 2) | (triple << 10) | (zs << 11) | (zdouble << 13) | (zcell << 14) | (kp << 22) |
+            (canon << 24) | (bar << 26) | (sk << 27) | (fp_only << 29))
+
+
+def enc_ctl(sub, arg=0):
+    return K_CTL | (sub << 2) | (arg << 6)
+
+
+def dec(word):
+    kind = word & 3
+    sg = {0: 0, 1: 1, 2: -1}
+    if kind == K_EP:
+        return ("EP", sg[(word >> 2) & 3], sg[(word >> 4) & 3],
+                Operand((word >> 6) & 255, (word >> 14) & 3, (word >> 16) & 3),
+                Operand((word >> 18) & 255, (word >> 26) & 3, (word >> 28) & 3, bool((word >> 30) & 1)))
+    if kind == K_FIN:
+        return ("FIN", dict(dst=(word >> 2) & 255, triple=(word >> 10) & 1, zsign=sg[(word >> 11) & 3],
+                            zdouble=(word >> 13) & 1, zcell=(word >> 14) & 255, kp=(word >> 22) & 3,
+                            canon=(word >> 24) & 3, bar=(word >> 26) & 1, skip=(word >> 27) & 3,
+                            fp_only=(word >> 29) & 1))
+    return ("CTL", (word >> 2) & 15, word >> 6)
+
+
+@dataclass
+class Curve:
+    name: str
+    p: int
+    n_limbs: int
+    xi_c: int        # xi = xi_c + u
+
+    @property
+    def R(self):
+        return 1 << (32 * self.n_limbs)
+
+
+class ProgramError(Exception):
+    pass
+
+
+class Builder:
+    """Emits the six per-role instruction streams op by op and does the static (worst-case) bound analysis."""
+
+    def __init__(self, curve):
+        self.cv = curve
+        self.streams = [[] for _ in range(ROLES)]
+        self.max_t = Fraction((curve.R - curve.p) * curve.R, curve.p * curve.p)     # accumulator limit in p^2
+        self.work = {"ep": [0] * ROLES, "fin": [0] * ROLES, "bar": 0}
+        self._mult = [1]
+
+    def ctl_all(self, sub, arg=0):
+        for r in range(ROLES):
+            self.streams[r].append(enc_ctl(sub, arg))
+
+    def ctl_roles(self, sub, args):
+        for r in range(ROLES):
+            self.streams[r].append(enc_ctl(sub, args[r]))
+
+    def rep(self, n):
+        assert 1 <= n < (1 << 20)
+        self.ctl_all(C_REP, n)
+        self._mult.append(self._mult[-1] * n)
+
+    def endrep(self):
+        self.ctl_all(C_ENDREP)
+        self._mult.pop()
+
+    def op(self, per_role, bar=True):
+        """per_role: role -> dict(dst=cell, eps=[(sR, sI, X, Y)], z=(sign, double, cell) | None, triple=bool,
+        skip_pair=None|0|1, fp_only=bool).  Roles without an entry only take part in the barrier."""
+        pu = Fraction(self.cv.p, self.cv.R)
+        if bar:
+            self.work["bar"] += self._mult[-1]
+        for r in range(ROLES):
+            d = per_role.get(r)
+            if d is None:
+                if bar:
+                    self.streams[r].append(enc_ctl(C_BAR))
+                continue
+            pos = {"R": Fraction(0), "I": Fraction(0)}
+            neg = {"R": Fraction(0), "I": Fraction(0)}
+            for (sR, sI, x, y) in d["eps"]:
+                bx, by = FORM_BOUND[x.form] << x.shift, FORM_BOUND[y.form] << y.shift
+                if max(bx, by) * self.cv.p >= self.cv.R:
+                    raise ProgramError("operand overflows the limb array")
+                for acc, s in (("R", sR), ("I", sI)):
+                    if s > 0:
+                        pos[acc] += bx * by
+                    elif s < 0:
+                        neg[acc] += bx * by
+                self.streams[r].append(enc_ep(sR, sI, x, y))
+                self.work["ep"][r] += self._mult[-1]
+            tr = 3 if d.get("triple") else 1
+            z = d.get("z")
+            zpos = zneg = Fraction(0)
+            if z:
+                zb = Fraction(1 << z[1]) / pu          # (2^zd p) R in units of p^2
+                if z[0] > 0:
+                    zpos = zb
+                else:
+                    zneg = zb
+            worst_neg = max(neg["R"], neg["I"]) * tr + zneg
+            worst_pos = max(pos["R"], pos["I"]) * tr + zpos
+            kp = next((i for i, m in enumerate(KP_MULT) if m >= worst_neg), None)
+            if kp is None:
+                raise ProgramError(f"negative part {float(worst_neg):.1f} p^2 exceeds the KP table")
+            total = worst_pos + KP_MULT[kp]
+            if total >= self.max_t:
+                raise ProgramError(f"accumulator bound {float(total):.1f} p^2 >= limit {float(self.max_t):.1f}")
+            out_bound = total * pu + 1          # REDC output < T/R + p, in units of p
+            canon = next((i for i, st in enumerate(CANON_STEPS) if (1 << st) >= out_bound), None)
+            if canon is None:
+                raise ProgramError("output bound too large to canonicalise")
+            self.streams[r].append(enc_fin(d["dst"], triple=1 if d.get("triple") else 0, zsign=z[0] if z else 0,
+                                           zdouble=z[1] if z else 0, zcell=z[2] if z else 0, kp=kp, canon=canon,
+                                           bar=1 if bar else 0, skip_pair=d.get("skip_pair"),
+                                           fp_only=1 if d.get("fp_only") else 0))
+            self.work["fin"][r] += self._mult[-1]
+
+    def finish(self):
+        self.ctl_all(C_END)
+        return [list(s) for s in self.streams]
+
+
+# ---- Fp2-level decompositions into EPs (Karatsuba, 3 EPs per Fp2 product) --------------------------------
+def _emit(coefs_forms, xc, yc, sign, yglob):
+    eps = []
+    for c, xf, yf in coefs_forms:
+        cr, ci = sign * c["R"], sign * c["I"]
+        mags = {abs(v) for v in (cr, ci) if v}
+        if not mags:
+            continue
+        assert len(mags) == 1, (cr, ci)
+        sh = {1: 0, 2: 1, 4: 2}[mags.pop()]
+        eps.append(((cr > 0) - (cr < 0), (ci > 0) - (ci < 0), Operand(xc, xf, sh), Operand(yc, yf, 0, yglob)))
+    return eps
+
+
+def _xi(cs):
+    for c in cs:                 # (r, i) -> (r - i, r + i)   [xi = 1 + u]
+        c["R"], c["I"] = c["R"] - c["I"], c["R"] + c["I"]
+
+
+def fp2_mul_eps(xc, yc, sign=1, xi=False, xconj=False, yconj=False, yglob=False):
+    """EPs adding  sign * [xi] * conj?(x) * conj?(y)  to (R, I); x, y are cells.  sign in {+-1, +-2}."""
+    sx = -1 if xconj else 1
+    sy = -1 if yconj else 1
+    # real = A - sx sy B ; imag = s (S - A - B) if sx == sy == s, else sy (S' - A + B) with S' = (x0 - x1)(y0 + y1)
+    cA = {"R": 1, "I": 0}
+    cB = {"R": -sx * sy, "I": 0}
+    cS = {"R": 0, "I": 0}
+    if sx == sy:
+        cA["I"], cB["I"], cS["I"] = -sx, -sx, sx
+        sform = F_SUM
+    else:
+        cA["I"], cB["I"], cS["I"] = -sy, sy, sy
+        sform = F_DIFF
+    if xi:
+        _xi((cA, cB, cS))
+    return _emit(((cA, F_C0, F_C0), (cB, F_C1, F_C1), (cS, sform, F_SUM)), xc, yc, sign, yglob)
+
+
+def fp2_sqr_eps(xc, sign=1, xi=False):
+    """EPs adding sign * [xi] * x^2:  real = (x0+x1)(x0-x1+p), imag = (2 x0) x1."""
+    cP = {"R": 1, "I": 0}
+    cQ = {"R": 0, "I": 2}
+    if xi:
+        _xi((cP, cQ))
+    return _emit(((cP, F_SUM, F_DIFF), (cQ, F_C0, F_C1)), xc, xc, sign, False)
+
+
+def fp2_mul_fp_eps(xc, yc, yform=F_C0, sign=1, xconj=False, yglob=False):
+    """EPs adding sign * conj?(x) * y  with y in Fp (component `yform` of cell yc)."""
+    return [(sign, 0, Operand(xc, F_C0), Operand(yc, yform, 0, yglob)),
+            (0, -sign if xconj else sign, Operand(xc, F_C1), Operand(yc, yform, 0, yglob))]
+
+
+# ---- symbolic Fp12 values ---------------------------------------------------------------------------------
+@dataclass
+class V12:
+    base: int            # first of six consecutive cells
+    conj: bool = False   # the value is the p^6-conjugate (odd coefficients negated) of what the cells hold
+
+    def cell(self, k):
+        return self.base + k
+
+    def sgn(self, k):
+        return -1 if (self.conj and (k & 1)) else 1
+
+
+def conj(v):
+    return V12(v.base, not v.conj)
+
+
+class PairingProgram:
+    """Streams for one curve.  Cell map: four Fp12 slots (cells 0..23); during the Miller loop slot 2 holds the
+    evaluated line coefficients (cells 12..15) and the two G1 points (cells 16, 17: x in c0, y in c1).  The kernel
+    prologue stores f = 1 in slot 0 and the points in cells 16, 17."""
+
+    SLOTS = (0, 6, 12, 18)
+    LINE_CELLS = (12, 13, 14, 15)      # pair 0: l2, l3 ; pair 1: l2, l3
+    P_CELLS = (16, 17)
+
+    def __init__(self, curve, ate_abs, const_index, inv_exp):
+        self.cv = curve
+        self.b = Builder(curve)
+        self.ate_bits = bin(ate_abs)[3:]
+        self.ate_abs = ate_abs
+        self.ci = const_index      # name -> global constant id (< LINE_BASE)
+        self.inv_exp = inv_exp     # p - 2
+        self.free = []
+        assert curve.xi_c == 1, "xi = c + u with c != 1 needs pre-multiplied operand forms (not implemented)"
+
+    # -- Fp12 ops --------------------------------------------------------------------------------------------
+    def mul(self, dst, A, B, roles=range(ROLES), bar=True, b_coeffs=range(ROLES)):
+        """cells[dst + k] = (A * B)_k for k in roles; only coefficients j in b_coeffs of B are non-zero."""
+        if A.conj == B.conj:
+            out_conj, sa, sb = A.conj, (lambda k: 1), (lambda k: 1)
+        else:
+            out_conj, sa, sb = False, A.sgn, B.sgn
+        per = {}
+        for k in roles:
+            eps = []
+            for j in b_coeffs:
+                i = (k - j) % 6
+                eps += fp2_mul_eps(A.cell(i), B.cell(j), sign=sa(i) * sb(j), xi=(i + j >= 6))
+            per[k] = dict(dst=dst + k, eps=eps)
+        self.b.op(per, bar=bar)
+        return V12(dst, out_conj)
+
+    def sqr(self, dst, A, extra=None):
+        per = {}
+        for k in range(ROLES):
+            eps = []
+            for i in range(6):
+                j = (k - i) % 6
+                if i > j:
+                    continue
+                if i == j:
+                    eps += fp2_sqr_eps(A.cell(i), xi=(i + j >= 6))
+                else:
+                    eps += fp2_mul_eps(A.cell(i), A.cell(j), sign=2, xi=(i + j >= 6))
+            per[k] = dict(dst=dst + k, eps=eps)
+        if extra:
+            self.b.op(per, bar=False)
+            self.b.op(extra, bar=True)
+        else:
+            self.b.op(per)
+        return V12(dst, A.conj)
+
+    def sparse(self, dst, F, l2c, l3c):
+        """F * (1 + l2 w^2 + l3 w^3), l2 / l3 = line cells (M-type twist, line normalised to constant term 1)."""
+        assert not F.conj
+        per = {}
+        for k in range(ROLES):
+            eps = []
+            for (j, lc) in ((2, l2c), (3, l3c)):
+                i = (k - j) % 6
+                eps += fp2_mul_eps(F.cell(i), lc, xi=(i + j >= 6))
+            per[k] = dict(dst=dst + k, eps=eps, z=(1, 0, F.cell(k)))
+        self.b.op(per)
+        return V12(dst)
+
+    def line_eval(self):
+        """LINE_CELLS[r] = lineconst[r] (Fp2, global, at the line counter) * P coordinate (Fp); 0 for skipped pairs."""
+        per = {}
+        for r in range(4):
+            pair, which = r // 2, r % 2
+            pc = Operand(self.P_CELLS[pair], F_C0 if which == 0 else F_C1)
+            eps = [(1, 0, pc, Operand(LINE_BASE + r, F_C0, 0, True)), (0, 1, pc, Operand(LINE_BASE + r, F_C1, 0, True))]
+            per[r] = dict(dst=self.LINE_CELLS[r], eps=eps, skip_pair=pair)
+        return per
+
+    def cyc_sqr(self, dst, A):
+        """Granger-Scott squaring in the w-basis; the Fp4 pairs are (g_k, g_{k+3})."""
+        g = A.cell
+        plan = {0: ("A", g(0), g(3), False), 3: ("B", g(0), g(3), False),
+                2: ("A", g(1), g(4), False), 5: ("B", g(1), g(4), False),
+                4: ("A", g(2), g(5), False), 1: ("B", g(2), g(5), True)}
+        per = {}
+        for k, (kind, x, y, xi) in plan.items():
+            if kind == "A":      # 3 (x^2 + xi y^2) - 2 g_k
+                per[k] = dict(dst=dst + k, eps=fp2_sqr_eps(x) + fp2_sqr_eps(y, xi=True), triple=True, z=(-1, 1, g(k)))
+            else:                # 3 [xi] (2 x y) + 2 g_k
+                per[k] = dict(dst=dst + k, eps=fp2_mul_eps(x, y, sign=2, xi=xi), triple=True, z=(1, 1, g(k)))
+        self.b.op(per)
+        return V12(dst, A.conj)
+
+    def frob(self, dst, A, j):
+        """A^(p^j): coefficient-wise Fp2-conjugation^j times gamma_{j,k} = xi^(k (p^j - 1) / 6)."""
+        per = {}
+        for k in range(ROLES):
+            cid = self.ci[f"frob{j}_{k}"]
+            if j % 2 == 0:
+                eps = fp2_mul_fp_eps(A.cell(k), cid, sign=A.sgn(k), yglob=True)       # gamma in Fp
+            else:
+                eps = fp2_mul_eps(A.cell(k), cid, sign=A.sgn(k), xconj=True, yglob=True)
+            per[k] = dict(dst=dst + k, eps=eps)
+        self.b.op(per)
+        return V12(dst)
+
+    # -- Miller loop -------------------------------------------------------------------------------------------
+    def miller(self):
+        S0, S1 = self.SLOTS[0], self.SLOTS[1]
+        b = self.b
+        lc = self.LINE_CELLS
+        st = {"f": V12(S0)}
+
+        def other():
+            return S1 if st["f"].base == S0 else S0
+
+        def mul_lines():
+            for pair in range(2):
+                st["f"] = self.sparse(other(), st["f"], lc[2 * pair], lc[2 * pair + 1])
+
+        def dbl_step():
+            st["f"] = self.sqr(other(), st["f"], extra=self.line_eval())
+            b.ctl_all(C_NEXTLINE)
+            mul_lines()
+
+        def add_step():
+            b.op(self.line_eval())
+            b.ctl_all(C_NEXTLINE)
+            mul_lines()
+
+        bits = self.ate_bits
+        add_step()                       # f = 1 before the first doubling: its squaring is skipped
+        if bits[0] == "1":
+            add_step()
+        i = 1
+        while i < len(bits):
+            run = 0
+            while i + run < len(bits) and bits[i + run] == "0":
+                run += 1
+            if run >= 4:
+                # a doubling step flips the slot, so REP over pairs of steps
+                b.rep(run // 2)
+                dbl_step()
+                dbl_step()
+                b.endrep()
+                if run % 2:
+                    dbl_step()
+                i += run
+                continue
+            dbl_step()
+            if bits[i] == "1":
+                add_step()
+            i += 1
+        return st["f"]
+
+    # -- final exponentiation ------------------------------------------------------------------------------------
+    def take(self, *keep):
+        """a slot not used by any of the values in `keep`"""
+        used = {v.base for v in keep if v is not None}
+        for s in self.SLOTS:
+            if s not in used:
+                return s
+        raise ProgramError("out of slots")
+
+    def pow_abs_x(self, base, keep=()):
+        """base^|x| by cyclotomic squarings (base must be in the cyclotomic subgroup)."""
+        b = self.b
+        sa = self.take(base, *keep)
+        sb = self.take(base, V12(sa), *keep)
+        bits = self.ate_bits
+        acc = base
+        i = 0
+
+        def nxt():
+            return sb if acc.base == sa else sa
+
+        while i < len(bits):
+            run = 0
+            while i + run < len(bits) and bits[i + run] == "0":
+                run += 1
+            if run >= 4 and acc.base in (sa, sb):
+                b.rep(run // 2)
+                acc = self.cyc_sqr(nxt(), acc)
+                acc = self.cyc_sqr(nxt(), acc)
+                b.endrep()
+                if run % 2:
+                    acc = self.cyc_sqr(nxt(), acc)
+                i += run
+                continue
+            acc = self.cyc_sqr(nxt(), acc)
+            if bits[i] == "1":
+                acc = self.mul(nxt(), acc, base)
+            i += 1
+        return acc
+
+    def fp_inverse(self, xcell, acc_cell, tab_cells):
+        """role 0: cell[acc_cell].c0 = cell[xcell].c0^(p-2), fixed 3-bit windows; no barriers."""
+        b = self.b
+        assert len(tab_cells) == 6
+        tab = {1: xcell}
+
+        def fp_mul(dst, a, c):
+            b.op({0: dict(dst=dst, eps=[(1, 0, Operand(a, F_C0), Operand(c, F_C0))], fp_only=True)}, bar=False)
+
+        for d in range(2, 8):
+            tab[d] = tab_cells[d - 2]
+            fp_mul(tab[d], tab[d - 1], xcell)
+        e = self.inv_exp
+        nwin = (e.bit_length() + 2) // 3
+        digits = [(e >> (3 * w)) & 7 for w in range(nwin)]
+        top = digits[-1]
+        assert top != 0
+        # acc = tab[top]: copy via a product with the Montgomery one constant
+        b.op({0: dict(dst=acc_cell, eps=[(1, 0, Operand(tab[top], F_C0), Operand(self.ci["one"], F_C0, 0, True))],
+                      fp_only=True)}, bar=False)
+        for w in range(nwin - 2, -1, -1):
+            for _ in range(3):
+                fp_mul(acc_cell, acc_cell, acc_cell)
+            if digits[w]:
+                fp_mul(acc_cell, acc_cell, tab[digits[w]])
+
+    def final_exp(self, f):
+        b = self.b
+        assert not f.conj
+        # ---- easy part: g = f^(p^6 - 1) = conj(f) * f^-1 ; e = g^(p^2 + 1) --------------------------------------
+        sn = self.take(f)
+        n = self.mul(sn, f, conj(f), roles=(0, 2, 4))              # N = f conj(f) in Fp6: n0, n1, n2 at w^0, w^2, w^4
+        n0, n1, n2 = sn, sn + 2, sn + 4
+        t0, t1, t2 = sn + 1, sn + 3, sn + 5
+        b.op({0: dict(dst=t0, eps=fp2_sqr_eps(n0) + fp2_mul_eps(n1, n2, sign=-1, xi=True)),
+              1: dict(dst=t1, eps=fp2_sqr_eps(n2, xi=True) + fp2_mul_eps(n0, n1, sign=-1)),
+              2: dict(dst=t2, eps=fp2_sqr_eps(n1) + fp2_mul_eps(n0, n2, sign=-1))})
+        sx = self.take(f, V12(sn))
+        sy = self.take(f, V12(sn), V12(sx))
+        D, ACC, DI = sx, sx + 1, sy + 2
+        tabc = [sx + 2, sx + 3, sx + 4, sx + 5, sy, sy + 1]
+        b.op({0: dict(dst=D, eps=fp2_mul_eps(n0, t0) + fp2_mul_eps(n2, t1, xi=True) + fp2_mul_eps(n1, t2, xi=True))},
+             bar=False)
+        DN = sy + 3
+        b.op({0: dict(dst=DN, eps=[(1, 0, Operand(D, F_C0), Operand(D, F_C0)), (1, 0, Operand(D, F_C1), Operand(D, F_C1))],
+                      fp_only=True)}, bar=False)
+        self.fp_inverse(DN, ACC, tabc)
+        b.op({0: dict(dst=DI, eps=[(1, 0, Operand(D, F_C0), Operand(ACC, F_C0)), (0, -1, Operand(D, F_C1), Operand(ACC, F_C0))])})
+        # N^-1 = (t0, t1, t2) / d   ->  even cells of slot sx (D, tab are dead after the barrier above)
+        b.op({k: dict(dst=sx + 2 * k, eps=fp2_mul_eps((t0, t1, t2)[k], DI)) for k in range(3)})
+        ninv = V12(sx)
+        # DI lives in slot sy until here; h = conj(f) * N^-1 goes to slot sn (N, t are dead)
+        h = self.mul(sn, conj(f), ninv, b_coeffs=(0, 2, 4))        # = f^-1
+        g = self.mul(sy, conj(f), h)
+        g2 = self.frob(self.take(g), g, 2)
+        e = self.mul(self.take(g, g2), g2, g)
+        # ---- hard part (BLS12, x < 0):  3 (p^4 - p^2 + 1) / r = (x-1)^2 (x+p) (x^2+p^2-1) + 3 ---------------------
+        b.ctl_roles(C_GSAVE, [e.cell(k) for k in range(ROLES)])
+        t = self.pow_abs_x(e)
+        a = conj(self.mul(self.take(t, e), t, e))                   # e^x * e^-1 = conj(e^|x| * e)
+        t = self.pow_abs_x(a)
+        a = conj(self.mul(self.take(t, a), t, a))                   # a^(x-1)
+        t = self.pow_abs_x(a)
+        c = self.frob(self.take(t, a), a, 1)
+        a = self.mul(self.take(t, c), conj(t), c)                   # a^(x+p)
+        t = self.pow_abs_x(a)
+        t = self.pow_abs_x(conj(t), keep=(a,))                      # a^(x^2)   (conj twice = identity up to the flag)
+        t = conj(t)
+        c = self.frob(self.take(t, a), a, 2)
+        bb = self.mul(self.take(t, a, c), t, c)
+        a = self.mul(self.take(bb, a), bb, conj(a))                 # a^(x^2 + p^2 - 1)
+        s = self.take(a)
+        b.ctl_roles(C_GLOAD, [s + k for k in range(ROLES)])
+        b.ctl_all(C_BAR)
+        e = V12(s)
+        e2 = self.cyc_sqr(self.take(a, e), e)
+        e3 = self.mul(self.take(a, e, e2), e2, e)
+        r = self.mul(self.take(a, e3), a, e3)
+        b.ctl_roles(C_CHECK, [r.cell(k) for k in range(ROLES)])
+        return r
+
+    def build(self):
+        f = self.miller()
+        self.final_exp(f)
+        return self.b.finish()
+
+
+# ---- emulator ------------------------------------------------------------------------------------------------
+class Emulator:
+    """Executes the streams on integers exactly as the kernel does (Montgomery domain, canonical cells)."""
+
+    def __init__(self, curve, streams, consts, lines):
+        """consts: id -> (c0, c1) normal-domain ints; lines: list over line index of 4 Fp2 tuples."""
+        self.cv = curve
+        self.streams = streams
+        p, R = curve.p, curve.R
+        self.mont = lambda v: (v * R) % p
+        self.consts = {k: (self.mont(v[0]), self.mont(v[1])) for k, v in consts.items()}
+        self.lines = [[(self.mont(c[0]), self.mont(c[1])) for c in ln] for ln in lines]
+        self.cells = {}
+        self.gscratch = {}
+        self.kp = [m * p * p for m in KP_MULT]
+        self.max_out = 0
+        self.n_intervals = 0
+
+    def set_cell(self, c, v):            # v normal-domain (c0, c1)
+        self.cells[c] = (self.mont(v[0]), self.mont(v[1]))
+
+    def get_cell(self, c):
+        p, R = self.cv.p, self.cv.R
+        ri = pow(R, -1, p)
+        v = self.cells[c]
+        return (v[0] * ri % p, v[1] * ri % p)
+
+    def _operand(self, o, line_ctr, reads):
+        p = self.cv.p
+        if o.glob:
+            v = self.lines[line_ctr][o.cell - LINE_BASE] if o.cell >= LINE_BASE else self.consts[o.cell]
+        else:
+            v = self.cells[o.cell]
+            reads.add(o.cell)
+        x = {F_C0: v[0], F_C1: v[1], F_SUM: v[0] + v[1], F_DIFF: v[0] - v[1] + p}[o.form] << o.shift
+        assert 0 <= x < self.cv.R
+        return x
+
+    def _redc(self, T):
+        p, R = self.cv.p, self.cv.R
+        assert 0 <= T < (R - p) * R, "accumulator out of range"
+        m = (-T * pow(p, -1, R)) % R
+        return (T + m * p) // R
+
+    def run(self, skip=(False, False)):
+        p, R = self.cv.p, self.cv.R
+        st = [dict(pc=0, stack=[], line=0, R=0, I=0, done=False, check=None) for _ in range(ROLES)]
+        while not all(s["done"] for s in st):
+            reads = [set() for _ in range(ROLES)]
+            writes = [set() for _ in range(ROLES)]
+            pending = [[] for _ in range(ROLES)]
+            for r in range(ROLES):
+                s = st[r]
+                prog = self.streams[r]
+                while not s["done"]:
+                    ins = dec(prog[s["pc"]])
+                    s["pc"] += 1
+                    if ins[0] == "EP":
+                        _, sR, sI, x, y = ins
+                        pr = self._operand(x, s["line"], reads[r]) * self._operand(y, s["line"], reads[r])
+                        s["R"] += sR * pr
+                        s["I"] += sI * pr
+                    elif ins[0] == "FIN":
+                        d = ins[1]
+                        out = []
+                        z = None
+                        if d["zsign"]:
+                            z = self.cells[d["zcell"]]
+                            reads[r].add(d["zcell"])
+                        for comp, acc in ((0, s["R"]), (1, s["I"])):
+                            if comp == 1 and d["fp_only"]:
+                                out.append(0)
+                                continue
+                            T = acc * (3 if d["triple"] else 1)
+                            if z is not None:
+                                T += d["zsign"] * (z[comp] << d["zdouble"]) * R
+                            T += self.kp[d["kp"]]
+                            o = self._redc(T)
+                            lim = (1 << CANON_STEPS[d["canon"]]) * p
+                            assert o < lim, "canonicalisation depth too small"
+                            self.max_out = max(self.max_out, o / p)
+                            out.append(o % p)
+                        if d["skip"] & 1 and skip[(d["skip"] >> 1) & 1]:
+                            out = [0, 0]
+                        self.cells[d["dst"]] = tuple(out)
+                        writes[r].add(d["dst"])
+                        s["R"] = s["I"] = 0
+                        if d["bar"]:
+                            break
+                    else:
+                        _, sub, arg = ins
+                        if sub == C_END:
+                            s["done"] = True
+                        elif sub == C_REP:
+                            s["stack"].append([s["pc"], arg])
+                        elif sub == C_ENDREP:
+                            s["stack"][-1][1] -= 1
+                            if s["stack"][-1][1] > 0:
+                                s["pc"] = s["stack"][-1][0]
+                            else:
+                                s["stack"].pop()
+                        elif sub == C_NEXTLINE:
+                            s["line"] += 1
+                        elif sub == C_BAR:
+                            break
+                        elif sub == C_GSAVE:
+                            self.gscratch[r] = self.cells[arg]
+                            reads[r].add(arg)
+                        elif sub == C_GLOAD:
+                            self.cells[arg] = self.gscratch[r]
+                            writes[r].add(arg)
+                        elif sub == C_CHECK:
+                            v = self.cells[arg]
+                            reads[r].add(arg)
+                            one = self.mont(1)
+                            s["check"] = (v == ((one, 0) if r == 0 else (0, 0)))
+                            break        # CHECK contains a barrier
+                        else:
+                            raise ValueError(sub)
+            # hazard check of this barrier interval.  Roles run sequentially here, so a cross-role conflict would
+            # silently read a value the GPU may or may not see: forbid every cross-role read/write overlap.
+            for a in range(ROLES):
+                for c in range(ROLES):
+                    if a != c and (writes[a] & (reads[c] | writes[c])):
+                        raise ProgramError(f"barrier hazard between roles {a} and {c}: cells {writes[a] & (reads[c] | writes[c])}")
+            self.n_intervals += 1
+        assert len({s["line"] for s in st}) == 1
+        return all(s["check"] for s in st)
