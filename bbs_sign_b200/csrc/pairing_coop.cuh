@@ -13,14 +13,22 @@
 
 #ifdef __CUDACC__
 #include "gen_coop.cuh"
+#ifdef BBS_COOP_PROG_HEADER
+#include BBS_COOP_PROG_HEADER              // timing experiments: alternative (not result-correct) programs
+#else
 #include "gen_pairing_prog.cuh"
+#endif
 
 namespace bbs {
 
 constexpr int COOP_ROLES = 6;
 constexpr int COOP_ITEMS = 32;                 // items per block = lanes
 constexpr int COOP_CELLS = 24;
-constexpr int COOP_TPB = COOP_ROLES * 32;
+#ifndef BBS_COOP_GROUPS
+#define BBS_COOP_GROUPS 2                      // independent 32-item groups per block (each with its own named barrier)
+#endif
+constexpr int COOP_GROUPS = BBS_COOP_GROUPS;
+constexpr int COOP_TPB = COOP_ROLES * 32 * COOP_GROUPS;
 
 struct CoopArgs {
     const uint32_t* lines;     // per ate line: B'0, A'0, B'1, A'1 (Fp2 each, Montgomery): 8N words
@@ -45,6 +53,8 @@ template <> struct Coop<Bls> {
     static __device__ __forceinline__ void sub_e(uint32_t* acc, const uint32_t* w) { coop_acc_sub_e12(acc, w); }
     static __device__ __forceinline__ void add_o(uint32_t* acc, const uint32_t* w) { coop_acc_add_o12(acc, w); }
     static __device__ __forceinline__ void sub_o(uint32_t* acc, const uint32_t* w) { coop_acc_sub_o12(acc, w); }
+    static __device__ __forceinline__ void accm_e(uint32_t* acc, const uint32_t* t, uint32_t cin, uint32_t ext) { coop_accm_e12(acc, t, cin, ext); }
+    static __device__ __forceinline__ void accm_o(uint32_t* acc, const uint32_t* t, uint32_t cin, uint32_t ext) { coop_accm_o12(acc, t, cin, ext); }
     static __device__ __forceinline__ void add_hi(uint32_t* acc, const uint32_t* z) { coop_acc_add_hi12(acc, z); }
     static __device__ __forceinline__ void sub_hi(uint32_t* acc, const uint32_t* z) { coop_acc_sub_hi12(acc, z); }
     static __device__ __forceinline__ void addn(uint32_t* d, const uint32_t* s) { coop_addn12(d, s); }
@@ -106,51 +116,55 @@ template <class C, bool GLOBAL> __device__ __forceinline__ void coop_operand(uin
     if (shift) coop_shl<N>(x, shift);
 }
 
-// one output component: acc -> canonical Fp
-template <class C> __device__ __forceinline__ void coop_finish(uint32_t* r, uint32_t* acc, uint32_t ins, const uint4* zp) {
+// both output components: (accR, accI) -> canonical Fp2.  The two reductions are independent; they are written
+// step by step side by side (one basic block per step) so that their dependency chains overlap.
+template <class C> __device__ __forceinline__ void coop_finish2(uint32_t* r0, uint32_t* r1, uint32_t* R, uint32_t* I,
+                                                                uint32_t ins, const uint4* zp) {
     constexpr int N = Coop<C>::N;
+    constexpr int Q = N / 4;
     if ((ins >> 10) & 1) {                       // triple
-        uint32_t t[2 * N + 1];
+        uint32_t t[2 * N + 1], u[2 * N + 1];
 #pragma unroll
-        for (int i = 2 * N; i > 0; i--) t[i] = __funnelshift_l(acc[i - 1], acc[i], 1);
-        t[0] = acc[0] << 1;
-        Coop<C>::add_e(acc, t);                  // low 2N words + carry into the top word
-        acc[2 * N] += t[2 * N];
+        for (int i = 2 * N; i > 0; i--) { t[i] = __funnelshift_l(R[i - 1], R[i], 1); u[i] = __funnelshift_l(I[i - 1], I[i], 1); }
+        t[0] = R[0] << 1; u[0] = I[0] << 1;
+        Coop<C>::add_e(R, t);                    // low 2N words + carry into the top word
+        Coop<C>::add_e(I, u);
+        R[2 * N] += t[2 * N];
+        I[2 * N] += u[2 * N];
     }
-    uint32_t zs = (ins >> 11) & 3;
+    const uint32_t zs = (ins >> 11) & 3;
     if (zs) {
-        uint32_t z[N];
-        coop_load<N>(z, zp);
-        if ((ins >> 13) & 1) coop_shl<N>(z, 1);
-        if (zs == 1) Coop<C>::add_hi(acc, z); else Coop<C>::sub_hi(acc, z);
+        uint32_t z0[N], z1[N];
+        coop_load<N>(z0, zp);
+        coop_load<N>(z1, zp + Q * 32);
+        if ((ins >> 13) & 1) { coop_shl<N>(z0, 1); coop_shl<N>(z1, 1); }
+        if (zs == 1) { Coop<C>::add_hi(R, z0); Coop<C>::add_hi(I, z1); } else { Coop<C>::sub_hi(R, z0); Coop<C>::sub_hi(I, z1); }
     }
-    uint32_t kp = (ins >> 22) & 3;
+    const uint32_t kp = (ins >> 22) & 3;
     if (kp) {
         uint32_t k[2 * N];
         const uint32_t* kt = Coop<C>::kp() + kp * (2 * N + 1);
 #pragma unroll
         for (int i = 0; i < 2 * N; i++) k[i] = kt[i];
-        Coop<C>::add_e(acc, k);
+        Coop<C>::add_e(R, k);
+        Coop<C>::add_e(I, k);
     }
-    Coop<C>::redc(r, acc);
-    uint32_t canon = (ins >> 24) & 3;
-    uint32_t d[N], b;
-    if (canon >= 3) { b = Coop<C>::template sub_kp<8>(d, r);
-#pragma unroll
-        for (int i = 0; i < N; i++) r[i] = b ? r[i] : d[i]; }
-    if (canon >= 2) { b = Coop<C>::template sub_kp<4>(d, r);
-#pragma unroll
-        for (int i = 0; i < N; i++) r[i] = b ? r[i] : d[i]; }
-    if (canon >= 1) { b = Coop<C>::template sub_kp<2>(d, r);
-#pragma unroll
-        for (int i = 0; i < N; i++) r[i] = b ? r[i] : d[i]; }
-    b = Coop<C>::template sub_kp<1>(d, r);
-#pragma unroll
-    for (int i = 0; i < N; i++) r[i] = b ? r[i] : d[i];
+    Coop<C>::redc(r0, R);
+    Coop<C>::redc(r1, I);
+    const uint32_t canon = (ins >> 24) & 3;
+    uint32_t d0[N], d1[N], b0, b1;
+#define COOP_CANON_STEP(K)                                                                     \
+    b0 = Coop<C>::template sub_kp<K>(d0, r0); b1 = Coop<C>::template sub_kp<K>(d1, r1);         \
+    _Pragma("unroll") for (int i = 0; i < N; i++) { r0[i] = b0 ? r0[i] : d0[i]; r1[i] = b1 ? r1[i] : d1[i]; }
+    if (canon >= 3) { COOP_CANON_STEP(8) }
+    if (canon >= 2) { COOP_CANON_STEP(4) }
+    if (canon >= 1) { COOP_CANON_STEP(2) }
+    COOP_CANON_STEP(1)
+#undef COOP_CANON_STEP
 }
 
 #ifndef BBS_COOP_MAXREG
-#define BBS_COOP_MAXREG 112
+#define BBS_COOP_MAXREG 128
 #endif
 
 template <class C>
@@ -158,10 +172,13 @@ __global__ void __maxnreg__(BBS_COOP_MAXREG) pairing_coop_kernel(const CoopArgs 
     constexpr int N = Coop<C>::N;
     constexpr int Q = N / 4;
     constexpr int CELL = 2 * Q * 32;           // uint4 per cell
-    extern __shared__ uint4 smem[];
+    extern __shared__ uint4 smem_all[];
+    const int lane = threadIdx.x & 31, role = (threadIdx.x >> 5) % COOP_ROLES, group = threadIdx.x / (COOP_ROLES * 32);
+    uint4* smem = smem_all + (size_t)group * (COOP_CELLS * CELL + COOP_ROLES * 32 / 4);
     uint32_t* votes = (uint32_t*)(smem + COOP_CELLS * CELL);      // [role][lane]
-    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-    const uint32_t item = blockIdx.x * COOP_ITEMS + lane;
+    const uint32_t gblock = blockIdx.x * COOP_GROUPS + group;      // 32-item group index
+    const uint32_t item = gblock * COOP_ITEMS + lane;
+#define COOP_BAR() asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(COOP_ROLES * 32) : "memory")
     const bool valid = item < a.n;
     const uint32_t fl = valid ? a.flags[item] : (uint32_t)(FL_DONE | FL_SKIP0 | FL_SKIP1);
     uint4* cells = smem + lane;
@@ -183,7 +200,7 @@ __global__ void __maxnreg__(BBS_COOP_MAXREG) pairing_coop_kernel(const CoopArgs 
             coop_store<N>(cells + (16 + (role >> 1)) * CELL + (role & 1) * Q * 32, v);
         }
     }
-    __syncthreads();
+    COOP_BAR();
 
     const uint32_t* prog = Coop<C>::prog() + Coop<C>::prog_off()[role];
     uint32_t pc = 0, line = 0;
@@ -200,7 +217,7 @@ __global__ void __maxnreg__(BBS_COOP_MAXREG) pairing_coop_kernel(const CoopArgs 
         const uint32_t kind = cur & 3;
         if (kind == 0) {
             // ---- EP ------------------------------------------------------------------------------------------
-            uint32_t x[N], y[N], w[2 * N];
+            uint32_t x[N], y[N], w[2 * N], v[2 * N];
             coop_operand<C, false>(x, cells + ((cur >> 6) & 255) * CELL, (cur >> 14) & 3, (cur >> 16) & 3);
             const uint32_t yc = (cur >> 18) & 255;
             if ((cur >> 30) & 1) {
@@ -211,35 +228,28 @@ __global__ void __maxnreg__(BBS_COOP_MAXREG) pairing_coop_kernel(const CoopArgs 
                 coop_operand<C, false>(y, cells + yc * CELL, (cur >> 26) & 3, (cur >> 28) & 3);
             }
             const uint32_t sR = (cur >> 2) & 3, sI = (cur >> 4) & 3;
+            // the two half products are independent carry chains: issued back to back they interleave on the IMAD pipe
             Coop<C>::wmul_e(w, x, y);
+            Coop<C>::wmul_o(v, x, y);
             if (sR == 1) Coop<C>::add_e(R, w); else if (sR == 2) Coop<C>::sub_e(R, w);
             if (sI == 1) Coop<C>::add_e(I, w); else if (sI == 2) Coop<C>::sub_e(I, w);
-            Coop<C>::wmul_o(w, x, y);
-            if (sR == 1) Coop<C>::add_o(R, w); else if (sR == 2) Coop<C>::sub_o(R, w);
-            if (sI == 1) Coop<C>::add_o(I, w); else if (sI == 2) Coop<C>::sub_o(I, w);
+            if (sR == 1) Coop<C>::add_o(R, v); else if (sR == 2) Coop<C>::sub_o(R, v);
+            if (sI == 1) Coop<C>::add_o(I, v); else if (sI == 2) Coop<C>::sub_o(I, v);
         } else if (kind == 1) {
             // ---- FIN -----------------------------------------------------------------------------------------
-            uint32_t r[N];
+            uint32_t r0[N], r1[N];
             const uint4* zp = cells + ((cur >> 14) & 255) * CELL;
             uint4* dp = cells + ((cur >> 2) & 255) * CELL;
             const uint32_t sk = (cur >> 27) & 3;
-            const bool zero = (sk & 1) && (fl & ((sk & 2) ? FL_SKIP1 : FL_SKIP0));
-            coop_finish<C>(r, R, cur, zp);
+            const bool zero = ((sk & 1) && (fl & ((sk & 2) ? FL_SKIP1 : FL_SKIP0))), fp_only = (cur >> 29) & 1;
+            coop_finish2<C>(r0, r1, R, I, cur, zp);
 #pragma unroll
-            for (int i = 0; i < N; i++) r[i] = zero ? 0u : r[i];
-            coop_store<N>(dp, r);
-            if ((cur >> 29) & 1) {               // Fp only
-#pragma unroll
-                for (int i = 0; i < N; i++) r[i] = 0u;
-            } else {
-                coop_finish<C>(r, I, cur, zp + Q * 32);
-#pragma unroll
-                for (int i = 0; i < N; i++) r[i] = zero ? 0u : r[i];
-            }
-            coop_store<N>(dp + Q * 32, r);
+            for (int i = 0; i < N; i++) { r0[i] = zero ? 0u : r0[i]; r1[i] = (zero || fp_only) ? 0u : r1[i]; }
+            coop_store<N>(dp, r0);
+            coop_store<N>(dp + Q * 32, r1);
 #pragma unroll
             for (int i = 0; i <= 2 * N; i++) { R[i] = 0; I[i] = 0; }
-            if ((cur >> 26) & 1) __syncthreads();
+            if ((cur >> 26) & 1) COOP_BAR();
         } else {
             // ---- CTL -----------------------------------------------------------------------------------------
             const uint32_t sub = (cur >> 2) & 15, arg = cur >> 6;
@@ -249,9 +259,9 @@ __global__ void __maxnreg__(BBS_COOP_MAXREG) pairing_coop_kernel(const CoopArgs 
                 if (--rep_cnt[rep_sp - 1] > 0) { pc = rep_pc[rep_sp - 1]; ins = __ldg(prog + pc); } else rep_sp--;
             }
             else if (sub == 3) line++;                                     // NEXTLINE
-            else if (sub == 4) __syncthreads();                            // BAR
+            else if (sub == 4) COOP_BAR();                            // BAR
             else if (sub == 5 || sub == 6) {                               // GSAVE / GLOAD (own cell <-> global)
-                uint4* g = (uint4*)a.gscratch + ((size_t)blockIdx.x * COOP_ROLES + role) * CELL + lane;
+                uint4* g = (uint4*)a.gscratch + ((size_t)gblock * COOP_ROLES + role) * CELL + lane;
                 uint4* c = cells + arg * CELL;
 #pragma unroll
                 for (int q = 0; q < 2 * Q; q++) { if (sub == 5) g[q * 32] = c[q * 32]; else c[q * 32] = g[q * 32]; }
@@ -265,7 +275,7 @@ __global__ void __maxnreg__(BBS_COOP_MAXREG) pairing_coop_kernel(const CoopArgs 
 #pragma unroll
                 for (int i = 0; i < N; i++) o |= v[i];
                 votes[role * 32 + lane] = o;
-                __syncthreads();
+                COOP_BAR();
                 if (role == 0) {
                     uint32_t all = 0;
 #pragma unroll
@@ -278,7 +288,7 @@ __global__ void __maxnreg__(BBS_COOP_MAXREG) pairing_coop_kernel(const CoopArgs 
 }
 
 template <class C> constexpr size_t coop_smem_bytes() {
-    return (size_t)COOP_CELLS * (2 * (Coop<C>::N / 4) * 32) * sizeof(uint4) + COOP_ROLES * 32 * sizeof(uint32_t);
+    return COOP_GROUPS * ((size_t)COOP_CELLS * (2 * (Coop<C>::N / 4) * 32) * sizeof(uint4) + COOP_ROLES * 32 * sizeof(uint32_t));
 }
 
 }  // namespace bbs

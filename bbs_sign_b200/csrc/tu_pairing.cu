@@ -20,13 +20,16 @@ template <class C> int launch_pairing(const PairingArgs& a, uint32_t n, rt_strea
 template int launch_pairing<Bls>(const PairingArgs&, uint32_t, rt_stream_t);
 #ifndef BBS_HOSTSIM
 size_t coop_gscratch_bytes_bls(size_t n) {
-    return ((n + COOP_ITEMS - 1) / COOP_ITEMS) * COOP_ROLES * (2 * (Coop<Bls>::N / 4) * 32) * sizeof(uint4);
+    const size_t per_block = (size_t)COOP_ITEMS * COOP_GROUPS;
+    return ((n + per_block - 1) / per_block) * COOP_GROUPS * COOP_ROLES * (2 * (Coop<Bls>::N / 4) * 32) * sizeof(uint4);
 }
 int launch_pairing_coop_bls(const CoopArgs& a, rt_stream_t s) {
     if (a.n == 0) return 0;
     constexpr size_t smem = coop_smem_bytes<Bls>();
     RT_CHECK(cudaFuncSetAttribute(pairing_coop_kernel<Bls>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pairing_coop_kernel<Bls><<<(a.n + COOP_ITEMS - 1) / COOP_ITEMS, COOP_TPB, smem, s>>>(a);
+    RT_CHECK(cudaFuncSetAttribute(pairing_coop_kernel<Bls>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    const uint32_t per_block = COOP_ITEMS * COOP_GROUPS;
+    pairing_coop_kernel<Bls><<<(a.n + per_block - 1) / per_block, COOP_TPB, smem, s>>>(a);
     RT_CHECK(cudaGetLastError());
     return 0;
 }

@@ -489,7 +489,11 @@ class PairingProgram:
         DN = sy + 3
         b.op({0: dict(dst=DN, eps=[(1, 0, Operand(D, F_C0), Operand(D, F_C0)), (1, 0, Operand(D, F_C1), Operand(D, F_C1))],
                       fp_only=True)}, bar=False)
-        self.fp_inverse(DN, ACC, tabc)
+        import os as _os
+        if "noinv" in _os.environ.get("COOP_EXP", ""):      # timing experiment only (results are wrong)
+            b.op({0: dict(dst=ACC, eps=[(1, 0, Operand(DN, F_C0), Operand(DN, F_C0))], fp_only=True)}, bar=False)
+        else:
+            self.fp_inverse(DN, ACC, tabc)
         b.op({0: dict(dst=DI, eps=[(1, 0, Operand(D, F_C0), Operand(ACC, F_C0)), (0, -1, Operand(D, F_C1), Operand(ACC, F_C0))])})
         # N^-1 = (t0, t1, t2) / d   ->  even cells of slot sx (D, tab are dead after the barrier above)
         b.op({k: dict(dst=sx + 2 * k, eps=fp2_mul_eps((t0, t1, t2)[k], DI)) for k in range(3)})

@@ -219,6 +219,51 @@ def addsub_prog(dst, src, sub, chunk=13, final_wrap=True):
     return P
 
 
+def accm_prog(dst, src, chunk=13):
+    """dst[k] += src[k] (k < len(src)), dst[k] += ext above, with the carry flag seeded from `cy` (0 or 1) on entry:
+    the sign-masked accumulate  acc += (w ^ m) + (m & 1)  with ext = m, i.e. acc +-= w without a branch."""
+    P = Prog()
+    P.wrap_ok = {"cy"}
+    n = len(dst)
+    srcs = list(src) + ["ext"] * (n - len(src))
+    k = 0
+    while k < n:
+        m = min(chunk, n - k)
+        ops = [("add.cc", "cy", "cy", MASK)]
+        for q in range(m):
+            idx = k + q
+            lastword = idx == n - 1
+            ops.append(("addc" if lastword else "addc.cc", dst[idx], dst[idx], srcs[idx]))
+            if lastword:
+                P.wrap_ok.add(dst[idx])
+        if k + m < n:
+            ops.append(("addc", "cy", 0, 0))
+        P.stmt(ops)
+        k += m
+    return P
+
+
+def check_accm():
+    rnd = random.Random(9)
+    for n, ns in ((25, 24), (24, 23), (17, 16), (16, 15)):
+        dst = [f"d{i}" for i in range(n)]
+        src = [f"s{i}" for i in range(ns)]
+        P = accm_prog(dst, src)
+        for t in range(300):
+            d = rnd.getrandbits(32 * n)
+            w = rnd.getrandbits(32 * ns)
+            neg = t & 1
+            m = MASK if neg else 0
+            env = {"cy": 1 if neg else 0, "ext": m}
+            for i in range(n):
+                env[f"d{i}"] = limbs(d, n)[i]
+            for i in range(ns):
+                env[f"s{i}"] = limbs(w, ns)[i] ^ m
+            P.run(env)
+            want = (d - w if neg else d + w) % (1 << (32 * n))
+            assert from_limbs(env, "d", n) == want, (n, ns, t)
+
+
 def check_addsub():
     rnd = random.Random(7)
     for n, ns in ((25, 24), (25, 23), (17, 16), (13, 12), (9, 8)):
@@ -321,7 +366,7 @@ def arr(mapping):
         for prefix, expr in mapping:
             if v.startswith(prefix) and v[len(prefix):].isdigit():
                 return expr % int(v[len(prefix):])
-        if v in ("m", "cy", "x0"):
+        if v in ("m", "cy", "x0", "ext"):
             return v
         raise KeyError(v)
     return f
@@ -350,6 +395,16 @@ def emit_all():
                 s.append("    uint32_t cy = 0; (void)cy;")
                 s.append(prog.emit(arr([("d", "acc[%d]"), ("s", "w[%d]")])))
                 s.append("}\n")
+        # branch-free signed accumulate: acc += (w ^ m) + cin, sign extension `ext` above w
+        for nm, ns, off in (("e", 2 * n, 0), ("o", 2 * n - 1, 1)):
+            dst = [f"d{i}" for i in range(off, 2 * n + 1)]
+            src = [f"s{i}" for i in range(ns)]
+            prog = accm_prog(dst, src)
+            s.append(f"// acc[{off}..{2 * n}] += t[0..{ns - 1}] + cin, words above t += ext  (t = w ^ m, cin = m & 1, ext = m: acc +-= w)")
+            s.append(f"__device__ __forceinline__ void coop_accm_{nm}{n}(uint32_t* acc, const uint32_t* t, uint32_t cin, uint32_t ext) {{")
+            s.append("    uint32_t cy = cin;")
+            s.append(prog.emit(arr([("d", "acc[%d]"), ("s", "t[%d]")])))
+            s.append("}\n")
         # plain n-word add / sub (operand forms), returning nothing (no overflow by construction)
         for sub in (False, True):
             dst = [f"d{i}" for i in range(n)]
@@ -414,6 +469,7 @@ def main():
     for n in (8, 12):
         check_wmul(n)
     check_addsub()
+    check_accm()
     for cname, (n, p) in CURVES.items():
         check_redc(n, p)
     txt = emit_all()
