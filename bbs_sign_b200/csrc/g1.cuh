@@ -144,6 +144,109 @@ template <class C> BBS_HDN void g1_mul_affine(uint32_t* r, const uint32_t* a, co
     g1_copy<C>(r, acc);
 }
 
+// ---- windowed scalar multiplication with the GLV endomorphism ----------------------------------------------
+// Variable-base k*P for the per-item points (e*A in core_verify, D*r3^ in proof_verify_init).  ark-ec's
+// `Projective * Fr` is a bit-serial double-and-add; on a GPU its data-dependent additions diverge inside a warp
+// (every lane pays for every addition), so this uses fixed 4-bit windows (one table look-up and one addition per
+// window for every lane) and, on BLS12-381, the curve endomorphism phi(x, y) = (beta x, y) = lambda P with
+// lambda = x^2 - 1 and r = lambda^2 + lambda + 1:  k = k1 + k2 lambda with k2 = floor(k / lambda), k1 = k mod lambda,
+// both below 2^128, so k P = k1 P + k2 phi(P) needs 128 doublings instead of 255.  Same group element as the
+// reference computes; only the addition chain differs.
+BBS_HD uint32_t win4_digit(const uint32_t* k, int w) { return (k[w >> 3] >> (4 * (w & 7))) & 15u; }
+
+// r = k1 * P (+ k2 * phi(P) when beta != nullptr); P affine; `bits` = bit length bound of k1 and k2
+template <class C> BBS_HDN void g1_mul_win4(uint32_t* r, const uint32_t* a, const uint32_t* k1, const uint32_t* k2,
+                                            int bits, const uint32_t* beta) {
+    using F = typename C::Fp;
+    uint32_t tab[15][3 * C::Fp::N];            // d * P, d = 1..15 (Jacobian)
+    g1_from_affine<C>(tab[0], a);
+    g1_dbl<C>(tab[1], tab[0]);
+    for (int d = 3; d <= 15; d++) g1_add_mixed<C>(tab[d - 1], tab[d - 2], a);
+    uint32_t acc[G1J];
+    g1_set_inf<C>(acc);
+    for (int w = (bits + 3) / 4 - 1; w >= 0; w--) {
+        if (!g1_is_inf<C>(acc)) { g1_dbl<C>(acc, acc); g1_dbl<C>(acc, acc); g1_dbl<C>(acc, acc); g1_dbl<C>(acc, acc); }
+        uint32_t d1 = win4_digit(k1, w);
+        if (d1) g1_add<C>(acc, acc, tab[d1 - 1]);
+        if (beta) {
+            uint32_t d2 = win4_digit(k2, w);
+            if (d2) {
+                uint32_t t[G1J];
+                fe_mul<F>(t, tab[d2 - 1], beta);
+                bn_copy<2 * C::Fp::N>(t + FPN, tab[d2 - 1] + FPN);
+                g1_add<C>(acc, acc, t);
+            }
+        }
+    }
+    g1_copy<C>(r, acc);
+}
+
+// k (8 canonical limbs, < r) = k1 + k2 * lambda, 0 <= k1 < lambda, k2 <= lambda + 1   [BLS12-381]
+BBS_HD void bls_glv_split(uint32_t* k1, uint32_t* k2, const uint32_t* k) {
+    const uint32_t* lam = BLS_GLV_LAMBDA();
+    const uint32_t* mu = BLS_GLV_MU();       // floor(2^256 / lambda), 5 limbs
+    uint32_t prod[13];
+    for (int i = 0; i < 13; i++) prod[i] = 0;
+    for (int i = 0; i < 8; i++) {
+        uint64_t c = 0;
+        for (int j = 0; j < 5; j++) {
+            c += (uint64_t)k[i] * mu[j] + prod[i + j];
+            prod[i + j] = (uint32_t)c;
+            c >>= 32;
+        }
+        prod[i + 5] = (uint32_t)c;
+    }
+    uint32_t q[5];
+    for (int i = 0; i < 5; i++) q[i] = prod[8 + i];          // q^ = floor(k mu / 2^256) in {q - 1, q}
+    uint32_t ql[9];
+    for (int i = 0; i < 9; i++) ql[i] = 0;
+    for (int i = 0; i < 5; i++) {
+        uint64_t c = 0;
+        for (int j = 0; j < 4; j++) {
+            c += (uint64_t)q[i] * lam[j] + ql[i + j];
+            ql[i + j] = (uint32_t)c;
+            c >>= 32;
+        }
+        if (i + 4 < 9) ql[i + 4] = (uint32_t)c;
+    }
+    uint32_t rem[5];
+    {
+        int64_t c = 0;
+        for (int i = 0; i < 5; i++) {
+            c += (int64_t)(i < 8 ? k[i] : 0) - (int64_t)ql[i];
+            rem[i] = (uint32_t)c;
+            c >>= 32;
+        }
+    }
+    for (int it = 0; it < 2; it++) {          // at most one correction is needed; two for safety
+        uint32_t d[5];
+        int64_t c = 0;
+        for (int i = 0; i < 5; i++) {
+            c += (int64_t)rem[i] - (int64_t)(i < 4 ? lam[i] : 0);
+            d[i] = (uint32_t)c;
+            c >>= 32;
+        }
+        if (c == 0) {                          // rem >= lambda
+            for (int i = 0; i < 5; i++) rem[i] = d[i];
+            uint64_t cc = 1;
+            for (int i = 0; i < 5; i++) { cc += q[i]; q[i] = (uint32_t)cc; cc >>= 32; }
+        }
+    }
+    for (int i = 0; i < 4; i++) { k1[i] = rem[i]; k2[i] = q[i]; }
+    k1[4] = rem[4]; k2[4] = q[4];              // k1[4] == 0; k2[4] == 0 (k2 <= lambda + 1 < 2^128)
+}
+
+// r = k * P for an affine P and a canonical scalar k (8 limbs)
+template <class C> BBS_HDN void g1_mul_scalar(uint32_t* r, const uint32_t* a, const uint32_t* k);
+template <> BBS_HDN void g1_mul_scalar<Bls>(uint32_t* r, const uint32_t* a, const uint32_t* k) {
+    uint32_t k1[5], k2[5];
+    bls_glv_split(k1, k2, k);
+    g1_mul_win4<Bls>(r, a, k1, k2, 128, BLS_GLV_BETA());
+}
+template <> BBS_HDN void g1_mul_scalar<Bn>(uint32_t* r, const uint32_t* a, const uint32_t* k) {
+    g1_mul_win4<Bn>(r, a, k, nullptr, BnFr::BITS, nullptr);
+}
+
 // ---- encodings -------------------------------------------------------
 enum : int { PT_OK = 0, PT_INF = 1, PT_BAD = 2 };
 

@@ -23,8 +23,24 @@ enum : uint8_t {
     ST_ERR_MALFORMED = 5,     // undecodable point / non-canonical scalar / the reference's panic cases
 };
 
-constexpr int TAB_WINDOWS = 32;   // 8-bit windows over a 256-bit scalar
-constexpr int TAB_ENTRIES = 255;  // digits 1..255
+// fixed-base tables: TAB_BITS-bit windows over a 256-bit scalar.  12-bit windows: 22 mixed additions per generator
+// instead of 32, 95 MB of tables at L = 10 (L2-resident on B200), 285 MB at L = 32 (gathered from HBM: 96 B per add).
+#ifndef BBS_TAB_BITS
+#ifdef BBS_HOSTSIM
+#define BBS_TAB_BITS 8      // the host simulation (tests only) builds its tables on CPU cores
+#else
+#define BBS_TAB_BITS 12
+#endif
+#endif
+constexpr int TAB_BITS = BBS_TAB_BITS;
+constexpr int TAB_WINDOWS = (256 + TAB_BITS - 1) / TAB_BITS;
+constexpr int TAB_ENTRIES = (1 << TAB_BITS) - 1;  // digits 1..2^TAB_BITS-1
+BBS_HD uint32_t tab_digit(const uint32_t* s, int w) {      // s: 8 canonical limbs
+    const int bit = w * TAB_BITS, word = bit >> 5, off = bit & 31;
+    uint64_t v = s[word];
+    if (word + 1 < 8) v |= (uint64_t)s[word + 1] << 32;
+    return (uint32_t)(v >> off) & (uint32_t)TAB_ENTRIES;
+}
 constexpr int MAX_L = 256;
 
 // Read-only per-issuer state living in device memory (built once by bbs_ctx_create)
@@ -85,11 +101,16 @@ struct CtxTableArgs { const uint32_t* K; const uint32_t* gens; uint32_t* tab; };
 template <class C> BBS_HD void ctx_table_item(const CtxTableArgs& a, uint32_t i) {
     uint32_t d = i % TAB_ENTRIES + 1, w = (i / TAB_ENTRIES) % TAB_WINDOWS, g = i / (TAB_ENTRIES * TAB_WINDOWS);
     const uint32_t* base = g == 0 ? a.K : a.gens + g * G1A;
-    uint32_t k[9];
-    for (int j = 0; j < 9; j++) k[j] = 0;
-    k[w >> 2] = d << (8 * (w & 3));
+    uint32_t k[10];
+    for (int j = 0; j < 10; j++) k[j] = 0;
+    {
+        const int bit = (int)w * TAB_BITS;
+        uint64_t v = (uint64_t)d << (bit & 31);
+        k[bit >> 5] = (uint32_t)v;
+        k[(bit >> 5) + 1] = (uint32_t)(v >> 32);
+    }
     uint32_t acc[G1J];
-    g1_mul_affine<C>(acc, base, k, 8 * (int)w + 8);
+    g1_mul_affine<C>(acc, base, k, TAB_BITS * (int)w + TAB_BITS);
     g1_to_affine<C>(a.tab + (size_t)i * G1A, acc);
 }
 
@@ -133,7 +154,7 @@ template <class C> BBS_HD void h2s_item(const H2sArgs& a, uint32_t t) {
 template <class C> BBS_HDN void tab_accumulate(uint32_t* acc, const uint32_t* tab, uint32_t g, const uint32_t* s) {
     const uint32_t* tg = tab + (size_t)g * TAB_WINDOWS * TAB_ENTRIES * G1A;
     for (int w = 0; w < TAB_WINDOWS; w++) {
-        uint32_t d = (s[w >> 2] >> (8 * (w & 3))) & 0xff;
+        uint32_t d = tab_digit(s, w);
         if (d) {
             uint32_t e[G1A];
             const uint32_t* src = tg + ((size_t)w * TAB_ENTRIES + (d - 1)) * G1A;
@@ -177,7 +198,7 @@ template <class C> BBS_HD void verify_g1_item(const VerifyG1Args& a, uint32_t i)
     g1_neg<C>(Cc, B);
     if (pa == PT_OK) {
         uint32_t eA[G1J];
-        g1_mul_affine<C>(eA, A, e, C::Fr::BITS);
+        g1_mul_scalar<C>(eA, A, e);
         g1_add<C>(Cc, Cc, eA);
     }
     // both pairing arguments leave this kernel affine: (x, y, 1).  The cooperative pairing kernel normalises its
@@ -321,7 +342,7 @@ template <class C> BBS_HD void proof_g1_item(const ProofG1Args& a, uint32_t i) {
     }
     if (pD == PT_OK) {
         uint32_t t[G1J];
-        g1_mul_affine<C>(t, D, r3cap, Fr::BITS);
+        g1_mul_scalar<C>(t, D, r3cap);
         g1_add<C>(T2, T2, t);
     }
     // challenge (proof_gen.rs:272-328)
