@@ -266,6 +266,12 @@ __global__ void __maxnreg__(BBS_COOP_MAXREG) pairing_coop_kernel(const CoopArgs 
 #pragma unroll
                 for (int q = 0; q < 2 * Q; q++) { if (sub == 5) g[q * 32] = c[q * 32]; else c[q * 32] = g[q * 32]; }
             }
+            else if (sub == 8) {                                           // INV: cell.c0 = cell.c0^-1 (Fermat, fe_inv)
+                uint32_t v[N], o[N];
+                coop_load<N>(v, cells + arg * CELL);
+                fe_inv<typename C::Fp>(o, v);
+                coop_store<N>(cells + arg * CELL, o);
+            }
             else if (sub == 7) {                                           // CHECK: result == 1 ?
                 uint32_t v[N], o = 0;
                 coop_load<N>(v, cells + arg * CELL);

@@ -9,7 +9,7 @@ shared-memory CELLS (one Fp2 per cell and item, Montgomery form, canonical).  A 
                                                  form 0: c0, 1: c1, 2: c0+c1, 3: c0-c1+p, shifted left by 0..2;
                                                  Y may come from the global constant table instead of a cell
   FIN  cell[dst] = canon( REDC( 3^t * acc + zs * 2^zd * Z * R + KP[k] ) )   per component, then acc = 0
-  CTL  REP n / ENDREP / NEXTLINE / BAR / GSAVE / GLOAD / CHECK / END
+  CTL  REP n / ENDREP / NEXTLINE / BAR / GSAVE / GLOAD / CHECK / INV (Fp inversion of a cell, in place) / END
 
 i.e. every output coefficient is ONE lazily-reduced sum of double-width products (Karatsuba at the Fp2 level:
 three EPs per Fp2 product, each feeding the real and/or imaginary accumulator with a sign).  This file builds the
@@ -27,7 +27,7 @@ ROLES = 6
 NCELLS = 24            # shared-memory cells per block (4 Fp12 values)
 
 K_EP, K_FIN, K_CTL = 0, 1, 2
-C_END, C_REP, C_ENDREP, C_NEXTLINE, C_BAR, C_GSAVE, C_GLOAD, C_CHECK = range(8)
+C_END, C_REP, C_ENDREP, C_NEXTLINE, C_BAR, C_GSAVE, C_GLOAD, C_CHECK, C_INV = range(9)
 F_C0, F_C1, F_SUM, F_DIFF = range(4)
 FORM_BOUND = {F_C0: 1, F_C1: 1, F_SUM: 2, F_DIFF: 2}     # in units of p (cells are canonical)
 LINE_BASE = 128        # global-constant ids >= LINE_BASE address the line table relative to the line counter
@@ -443,31 +443,10 @@ class PairingProgram:
             i += 1
         return acc
 
-    def fp_inverse(self, xcell, acc_cell, tab_cells):
-        """role 0: cell[acc_cell].c0 = cell[xcell].c0^(p-2), fixed 3-bit windows; no barriers."""
-        b = self.b
-        assert len(tab_cells) == 6
-        tab = {1: xcell}
-
-        def fp_mul(dst, a, c):
-            b.op({0: dict(dst=dst, eps=[(1, 0, Operand(a, F_C0), Operand(c, F_C0))], fp_only=True)}, bar=False)
-
-        for d in range(2, 8):
-            tab[d] = tab_cells[d - 2]
-            fp_mul(tab[d], tab[d - 1], xcell)
-        e = self.inv_exp
-        nwin = (e.bit_length() + 2) // 3
-        digits = [(e >> (3 * w)) & 7 for w in range(nwin)]
-        top = digits[-1]
-        assert top != 0
-        # acc = tab[top]: copy via a product with the Montgomery one constant
-        b.op({0: dict(dst=acc_cell, eps=[(1, 0, Operand(tab[top], F_C0), Operand(self.ci["one"], F_C0, 0, True))],
-                      fp_only=True)}, bar=False)
-        for w in range(nwin - 2, -1, -1):
-            for _ in range(3):
-                fp_mul(acc_cell, acc_cell, acc_cell)
-            if digits[w]:
-                fp_mul(acc_cell, acc_cell, tab[digits[w]])
+    def fp_inverse(self, xcell):
+        """role 0: cell[xcell].c0 = cell[xcell].c0^-1 in place (one INV instruction: Fermat inversion on registers,
+        field.cuh fe_inv, instead of ~500 interpreted multiply + reduce steps); no barrier."""
+        self.b.streams[0].append(enc_ctl(C_INV, xcell))
 
     def final_exp(self, f):
         b = self.b
@@ -482,25 +461,19 @@ class PairingProgram:
               2: dict(dst=t2, eps=fp2_sqr_eps(n1) + fp2_mul_eps(n0, n2, sign=-1))})
         sx = self.take(f, V12(sn))
         sy = self.take(f, V12(sn), V12(sx))
-        D, ACC, DI = sx, sx + 1, sy + 2
-        tabc = [sx + 2, sx + 3, sx + 4, sx + 5, sy, sy + 1]
+        D, DN, DI = sx, sx + 1, sx + 3
         b.op({0: dict(dst=D, eps=fp2_mul_eps(n0, t0) + fp2_mul_eps(n2, t1, xi=True) + fp2_mul_eps(n1, t2, xi=True))},
              bar=False)
-        DN = sy + 3
         b.op({0: dict(dst=DN, eps=[(1, 0, Operand(D, F_C0), Operand(D, F_C0)), (1, 0, Operand(D, F_C1), Operand(D, F_C1))],
                       fp_only=True)}, bar=False)
-        import os as _os
-        if "noinv" in _os.environ.get("COOP_EXP", ""):      # timing experiment only (results are wrong)
-            b.op({0: dict(dst=ACC, eps=[(1, 0, Operand(DN, F_C0), Operand(DN, F_C0))], fp_only=True)}, bar=False)
-        else:
-            self.fp_inverse(DN, ACC, tabc)
-        b.op({0: dict(dst=DI, eps=[(1, 0, Operand(D, F_C0), Operand(ACC, F_C0)), (0, -1, Operand(D, F_C1), Operand(ACC, F_C0))])})
-        # N^-1 = (t0, t1, t2) / d   ->  even cells of slot sx (D, tab are dead after the barrier above)
-        b.op({k: dict(dst=sx + 2 * k, eps=fp2_mul_eps((t0, t1, t2)[k], DI)) for k in range(3)})
-        ninv = V12(sx)
-        # DI lives in slot sy until here; h = conj(f) * N^-1 goes to slot sn (N, t are dead)
+        self.fp_inverse(DN)
+        b.op({0: dict(dst=DI, eps=[(1, 0, Operand(D, F_C0), Operand(DN, F_C0)), (0, -1, Operand(D, F_C1), Operand(DN, F_C0))])})
+        # N^-1 = (t0, t1, t2) / d   ->  even cells of slot sy
+        b.op({k: dict(dst=sy + 2 * k, eps=fp2_mul_eps((t0, t1, t2)[k], DI)) for k in range(3)})
+        ninv = V12(sy)
+        # h = conj(f) * N^-1 goes to slot sn (N, t are dead after the barrier above)
         h = self.mul(sn, conj(f), ninv, b_coeffs=(0, 2, 4))        # = f^-1
-        g = self.mul(sy, conj(f), h)
+        g = self.mul(sx, conj(f), h)
         g2 = self.frob(self.take(g), g, 2)
         e = self.mul(self.take(g, g2), g2, g)
         # ---- hard part (BLS12, x < 0):  3 (p^4 - p^2 + 1) / r = (x-1)^2 (x+p) (x^2+p^2-1) + 3 ---------------------
@@ -645,6 +618,13 @@ class Emulator:
                         elif sub == C_GLOAD:
                             self.cells[arg] = self.gscratch[r]
                             writes[r].add(arg)
+                        elif sub == C_INV:
+                            v = self.cells[arg]
+                            reads[r].add(arg)
+                            writes[r].add(arg)
+                            ri = pow(R, -1, p)
+                            xn = v[0] * ri % p
+                            self.cells[arg] = (pow(xn, p - 2, p) * R % p, v[1])
                         elif sub == C_CHECK:
                             v = self.cells[arg]
                             reads[r].add(arg)
