@@ -49,6 +49,7 @@ template <> struct Coop<Bls> {
     static __device__ __forceinline__ const uint32_t* kp() { return COOP_KP_BLS; }
     static __device__ __forceinline__ void wmul_e(uint32_t* w, const uint32_t* a, const uint32_t* b) { coop_wmul_e12(w, a, b); }
     static __device__ __forceinline__ void wmul_o(uint32_t* w, const uint32_t* a, const uint32_t* b) { coop_wmul_o12(w, a, b); }
+    static __device__ __forceinline__ void merge(uint32_t* w, const uint32_t* v) { coop_merge12(w, v); }
     static __device__ __forceinline__ void add_e(uint32_t* acc, const uint32_t* w) { coop_acc_add_e12(acc, w); }
     static __device__ __forceinline__ void sub_e(uint32_t* acc, const uint32_t* w) { coop_acc_sub_e12(acc, w); }
     static __device__ __forceinline__ void add_o(uint32_t* acc, const uint32_t* w) { coop_acc_add_o12(acc, w); }
@@ -231,10 +232,9 @@ __global__ void __maxnreg__(BBS_COOP_MAXREG) pairing_coop_kernel(const CoopArgs 
             // the two half products are independent carry chains: issued back to back they interleave on the IMAD pipe
             Coop<C>::wmul_e(w, x, y);
             Coop<C>::wmul_o(v, x, y);
+            Coop<C>::merge(w, v);            // full product: one 2N-word addition per accumulator instead of two
             if (sR == 1) Coop<C>::add_e(R, w); else if (sR == 2) Coop<C>::sub_e(R, w);
             if (sI == 1) Coop<C>::add_e(I, w); else if (sI == 2) Coop<C>::sub_e(I, w);
-            if (sR == 1) Coop<C>::add_o(R, v); else if (sR == 2) Coop<C>::sub_o(R, v);
-            if (sI == 1) Coop<C>::add_o(I, v); else if (sI == 2) Coop<C>::sub_o(I, v);
         } else if (kind == 1) {
             // ---- FIN -----------------------------------------------------------------------------------------
             uint32_t r0[N], r1[N];

@@ -264,6 +264,37 @@ def check_accm():
             assert from_limbs(env, "d", n) == want, (n, ns, t)
 
 
+def merge_prog(n):
+    """w[1 + k] += v[k], k = 0..2n-2: the two half products of coop_wmul_{e,o} -> the full 2n-word product in w."""
+    dst = [f"w{k + 1}" for k in range(2 * n - 1)]
+    src = [f"v{k}" for k in range(2 * n - 1)]
+    P = addsub_prog(dst, src, False)
+    P.wrap_ok = {"cy"}          # the product fits 2n words: a lost carry at the top is an error
+    return P
+
+
+def check_merge(n, trials=200):
+    rnd = random.Random(300 + n)
+    pe, _ = wmul_prog(n, False)
+    po, _ = wmul_prog(n, True)
+    pm = merge_prog(n)
+    for t in range(trials):
+        a = (1 << (32 * n)) - 1 if t == 0 else rnd.getrandbits(32 * n)
+        b = (1 << (32 * n)) - 1 if t == 0 else rnd.getrandbits(32 * n)
+        env = {}
+        for i in range(n):
+            env[f"a{i}"], env[f"b{i}"] = limbs(a, n)[i], limbs(b, n)[i]
+        e1 = pe.run(dict(env))
+        e2 = po.run(dict(env))
+        env2 = {"cy": 0}
+        for k in range(2 * n):
+            env2[f"w{k}"] = e1[f"w{k}"]
+        for k in range(2 * n - 1):
+            env2[f"v{k}"] = e2[f"w{k}"]
+        pm.run(env2)
+        assert from_limbs(env2, "w", 2 * n) == a * b
+
+
 def check_addsub():
     rnd = random.Random(7)
     for n, ns in ((25, 24), (25, 23), (17, 16), (13, 12), (9, 8)):
@@ -395,6 +426,12 @@ def emit_all():
                 s.append("    uint32_t cy = 0; (void)cy;")
                 s.append(prog.emit(arr([("d", "acc[%d]"), ("s", "w[%d]")])))
                 s.append("}\n")
+        prog = merge_prog(n)
+        s.append(f"// w[1..{2 * n - 1}] += v[0..{2 * n - 2}]: even + odd half products -> full product in w")
+        s.append(f"__device__ __forceinline__ void coop_merge{n}(uint32_t* w, const uint32_t* v) {{")
+        s.append("    uint32_t cy = 0; (void)cy;")
+        s.append(prog.emit(arr([("w", "w[%d]"), ("v", "v[%d]")])))
+        s.append("}\n")
         # branch-free signed accumulate: acc += (w ^ m) + cin, sign extension `ext` above w
         for nm, ns, off in (("e", 2 * n, 0), ("o", 2 * n - 1, 1)):
             dst = [f"d{i}" for i in range(off, 2 * n + 1)]
@@ -470,6 +507,8 @@ def main():
         check_wmul(n)
     check_addsub()
     check_accm()
+    for n in (8, 12):
+        check_merge(n)
     for cname, (n, p) in CURVES.items():
         check_redc(n, p)
     txt = emit_all()
