@@ -101,14 +101,14 @@ template <class C, bool GLOBAL> __device__ __forceinline__ void coop_operand(uin
     uint32_t t[N];
     if (GLOBAL) {
         const uint32_t* g = (const uint32_t*)cellp;
-        if (form == 1) coop_load_g<N>(x, g + N); else coop_load_g<N>(x, g);
+        coop_load_g<N>(x, g + (form == 1 ? N : 0));
         if (form >= 2) {
             coop_load_g<N>(t, g + N);
             if (form == 2) Coop<C>::addn(x, t); else { Coop<C>::subn(x, t); Coop<C>::add_p(x); }
         }
     } else {
         const uint4* s = (const uint4*)cellp;
-        if (form == 1) coop_load<N>(x, s + (N / 4) * 32); else coop_load<N>(x, s);
+        coop_load<N>(x, s + (form == 1 ? (N / 4) * 32 : 0));
         if (form >= 2) {
             coop_load<N>(t, s + (N / 4) * 32);
             if (form == 2) Coop<C>::addn(x, t); else { Coop<C>::subn(x, t); Coop<C>::add_p(x); }
@@ -212,7 +212,9 @@ __global__ void __maxnreg__(BBS_COOP_MAXREG) pairing_coop_kernel(const CoopArgs 
     for (int i = 0; i <= 2 * N; i++) { R[i] = 0; I[i] = 0; }
     uint32_t ins = __ldg(prog);
     for (;;) {
-        const uint32_t cur = ins;
+        // every lane of a role-warp holds the same word; the redux makes that visible to the compiler (uniform register),
+        // so the decode runs on the uniform datapath and the branches below need no reconvergence bookkeeping
+        const uint32_t cur = __reduce_or_sync(0xffffffffu, ins);
         pc++;
         ins = __ldg(prog + pc);                  // prefetch (streams end with END, one word of slack is harmless)
         const uint32_t kind = cur & 3;
@@ -243,8 +245,10 @@ __global__ void __maxnreg__(BBS_COOP_MAXREG) pairing_coop_kernel(const CoopArgs 
             const uint32_t sk = (cur >> 27) & 3;
             const bool zero = ((sk & 1) && (fl & ((sk & 2) ? FL_SKIP1 : FL_SKIP0))), fp_only = (cur >> 29) & 1;
             coop_finish2<C>(r0, r1, R, I, cur, zp);
+            if ((sk & 1) || fp_only) {
 #pragma unroll
-            for (int i = 0; i < N; i++) { r0[i] = zero ? 0u : r0[i]; r1[i] = (zero || fp_only) ? 0u : r1[i]; }
+                for (int i = 0; i < N; i++) { r0[i] = zero ? 0u : r0[i]; r1[i] = (zero || fp_only) ? 0u : r1[i]; }
+            }
             coop_store<N>(dp, r0);
             coop_store<N>(dp + Q * 32, r1);
 #pragma unroll
