@@ -154,27 +154,34 @@ template <class C> BBS_HDN void g1_mul_affine(uint32_t* r, const uint32_t* a, co
 // reference computes; only the addition chain differs.
 BBS_HD uint32_t win4_digit(const uint32_t* k, int w) { return (k[w >> 3] >> (4 * (w & 7))) & 15u; }
 
-// r = k1 * P (+ k2 * phi(P) when beta != nullptr); P affine; `bits` = bit length bound of k1 and k2
-template <class C> BBS_HDN void g1_mul_win4(uint32_t* r, const uint32_t* a, const uint32_t* k1, const uint32_t* k2,
-                                            int bits, const uint32_t* beta) {
+// r = sum_j k1[j] * P_j (+ k2[j] * phi(P_j) when beta != nullptr) over NP affine points (pts[j] == nullptr: the
+// identity, skipped), Straus with shared doublings; `bits` = bit length bound of all k1[j], k2[j]
+template <class C, int NP> BBS_HDN void g1_msm_win4(uint32_t* r, const uint32_t* const* pts, const uint32_t (*k1)[9],
+                                                    const uint32_t (*k2)[9], int bits, const uint32_t* beta) {
     using F = typename C::Fp;
-    uint32_t tab[15][3 * C::Fp::N];            // d * P, d = 1..15 (Jacobian)
-    g1_from_affine<C>(tab[0], a);
-    g1_dbl<C>(tab[1], tab[0]);
-    for (int d = 3; d <= 15; d++) g1_add_mixed<C>(tab[d - 1], tab[d - 2], a);
+    uint32_t tab[NP][15][3 * C::Fp::N];            // d * P_j, d = 1..15 (Jacobian)
+    for (int j = 0; j < NP; j++) {
+        if (!pts[j]) continue;
+        g1_from_affine<C>(tab[j][0], pts[j]);
+        g1_dbl<C>(tab[j][1], tab[j][0]);
+        for (int d = 3; d <= 15; d++) g1_add_mixed<C>(tab[j][d - 1], tab[j][d - 2], pts[j]);
+    }
     uint32_t acc[G1J];
     g1_set_inf<C>(acc);
     for (int w = (bits + 3) / 4 - 1; w >= 0; w--) {
         if (!g1_is_inf<C>(acc)) { g1_dbl<C>(acc, acc); g1_dbl<C>(acc, acc); g1_dbl<C>(acc, acc); g1_dbl<C>(acc, acc); }
-        uint32_t d1 = win4_digit(k1, w);
-        if (d1) g1_add<C>(acc, acc, tab[d1 - 1]);
-        if (beta) {
-            uint32_t d2 = win4_digit(k2, w);
-            if (d2) {
-                uint32_t t[G1J];
-                fe_mul<F>(t, tab[d2 - 1], beta);
-                bn_copy<2 * C::Fp::N>(t + FPN, tab[d2 - 1] + FPN);
-                g1_add<C>(acc, acc, t);
+        for (int j = 0; j < NP; j++) {
+            if (!pts[j]) continue;
+            uint32_t d1 = win4_digit(k1[j], w);
+            if (d1) g1_add<C>(acc, acc, tab[j][d1 - 1]);
+            if (beta) {
+                uint32_t d2 = win4_digit(k2[j], w);
+                if (d2) {
+                    uint32_t t[G1J];
+                    fe_mul<F>(t, tab[j][d2 - 1], beta);
+                    bn_copy<2 * C::Fp::N>(t + FPN, tab[j][d2 - 1] + FPN);
+                    g1_add<C>(acc, acc, t);
+                }
             }
         }
     }
@@ -236,15 +243,37 @@ BBS_HD void bls_glv_split(uint32_t* k1, uint32_t* k2, const uint32_t* k) {
     k1[4] = rem[4]; k2[4] = q[4];              // k1[4] == 0; k2[4] == 0 (k2 <= lambda + 1 < 2^128)
 }
 
-// r = k * P for an affine P and a canonical scalar k (8 limbs)
-template <class C> BBS_HDN void g1_mul_scalar(uint32_t* r, const uint32_t* a, const uint32_t* k);
-template <> BBS_HDN void g1_mul_scalar<Bls>(uint32_t* r, const uint32_t* a, const uint32_t* k) {
-    uint32_t k1[5], k2[5];
-    bls_glv_split(k1, k2, k);
-    g1_mul_win4<Bls>(r, a, k1, k2, 128, BLS_GLV_BETA());
+// r = sum_j k_j * P_j for NP affine points (nullptr = identity) and canonical scalars k_j (8 limbs each)
+template <class C, int NP> BBS_HDN void g1_msm_scalar(uint32_t* r, const uint32_t* const* pts, const uint32_t* const* ks);
+template <class C, int NP> struct G1Msm;
+template <int NP> struct G1Msm<Bls, NP> {
+    static BBS_HD void run(uint32_t* r, const uint32_t* const* pts, const uint32_t* const* ks) {
+        uint32_t k1[NP][9], k2[NP][9];
+        for (int j = 0; j < NP; j++) {
+            for (int i = 0; i < 9; i++) { k1[j][i] = 0; k2[j][i] = 0; }
+            bls_glv_split(k1[j], k2[j], ks[j]);
+        }
+        g1_msm_win4<Bls, NP>(r, pts, k1, k2, 128, BLS_GLV_BETA());   // k1 < lambda, k2 <= lambda + 1 < 2^128
+    }
+};
+template <int NP> struct G1Msm<Bn, NP> {
+    static BBS_HD void run(uint32_t* r, const uint32_t* const* pts, const uint32_t* const* ks) {
+        uint32_t k1[NP][9];
+        for (int j = 0; j < NP; j++) {
+            for (int i = 0; i < 8; i++) k1[j][i] = ks[j][i];
+            k1[j][8] = 0;
+        }
+        g1_msm_win4<Bn, NP>(r, pts, k1, nullptr, BnFr::BITS, nullptr);
+    }
+};
+template <class C, int NP> BBS_HDN void g1_msm_scalar(uint32_t* r, const uint32_t* const* pts, const uint32_t* const* ks) {
+    G1Msm<C, NP>::run(r, pts, ks);
 }
-template <> BBS_HDN void g1_mul_scalar<Bn>(uint32_t* r, const uint32_t* a, const uint32_t* k) {
-    g1_mul_win4<Bn>(r, a, k, nullptr, BnFr::BITS, nullptr);
+// r = k * P for an affine P and a canonical scalar k (8 limbs)
+template <class C> BBS_HDN void g1_mul_scalar(uint32_t* r, const uint32_t* a, const uint32_t* k) {
+    const uint32_t* pts[1] = {a};
+    const uint32_t* ks[1] = {k};
+    G1Msm<C, 1>::run(r, pts, ks);
 }
 
 // ---- encodings -------------------------------------------------------

@@ -310,14 +310,12 @@ template <class C> BBS_HD void proof_g1_item(const ProofG1Args& a, uint32_t i) {
     ok = ok && fr_from_le32<C>(ecap, pf + 3 * GB) && fr_from_le32<C>(r1cap, pf + 3 * GB + 32) &&
          fr_from_le32<C>(r3cap, pf + 3 * GB + 64) && fr_from_le32<C>(c, pf + 3 * GB + 96);
     if (!ok) PROOF_FAIL(ST_ERR_MALFORMED)
-    // T1 = Bbar*c + Abar*e^ + D*r1^   (proof_verify.rs:163-164), shared doublings
+    // T1 = Bbar*c + Abar*e^ + D*r1^   (proof_verify.rs:163-164): one windowed three-point multi-scalar product
     uint32_t T1[G1J], T2[G1J];
-    g1_set_inf<C>(T1);
-    for (int b = Fr::BITS - 1; b >= 0; b--) {
-        g1_dbl<C>(T1, T1);
-        if (pB == PT_OK && ((c[b >> 5] >> (b & 31)) & 1)) g1_add_mixed<C>(T1, T1, Bb);
-        if (pA == PT_OK && ((ecap[b >> 5] >> (b & 31)) & 1)) g1_add_mixed<C>(T1, T1, Ab);
-        if (pD == PT_OK && ((r1cap[b >> 5] >> (b & 31)) & 1)) g1_add_mixed<C>(T1, T1, D);
+    {
+        const uint32_t* pts[3] = {pB == PT_OK ? Bb : nullptr, pA == PT_OK ? Ab : nullptr, pD == PT_OK ? D : nullptr};
+        const uint32_t* ks[3] = {c, ecap, r1cap};
+        g1_msm_scalar<C, 3>(T1, pts, ks);
     }
     // T2 = Bv*c + D*r3^ + sum H_undisclosed m^   with Bv*c = K*c + sum H_disclosed (c m)   (:165-182)
     uint32_t cm[8];

@@ -51,3 +51,37 @@ def test_proof_verify(lib, curve, L, dis):
 @pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
 def test_proof_errors(lib, curve):
     P.case_proof_errors(None, curve)
+
+
+def test_proof_fixture_l32(lib):
+    """tests/golden/proofs_bls_L32_R16.npz (tools/gen_proof_fixture.py): config-4-shaped proofs, L = 32, 16 disclosed,
+    valid and corrupted, against the verdicts the oracle recorded when the fixture was made."""
+    import os
+    import numpy as np
+    from bbs_sign_b200 import api as A
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "proofs_bls_L32_R16.npz"))
+    ctx = A.BatchContext(A.BLS12_381, bytes(fx["pk"]), header=b"", n_messages=32)
+    n = fx["fixed"].shape[0]
+    proofs = [A.ProofBytes(bytes(fx["fixed"][i]), bytes(fx["commitments"][i])) for i in range(n)]
+    dis = [int(x) for x in fx["disclosed_idx"]]
+    msgs = [[bytes(fx["disclosed_msgs"][i][32 * k: 32 * k + 32]) for k in range(len(dis))] for i in range(n)]
+    got = ctx.proof_verify_batch(proofs, b"", msgs, [dis] * n)
+    assert got.tolist() == fx["expect"].tolist()
+    ctx.close()
+
+
+def test_large_batch_consistency(lib):
+    """Size-independent property at a bench-like size: sign 4,096 synthetic message sets on the GPU, corrupt every
+    16th item in one of four ways, and require accept exactly for the untouched items (the same check bench.py
+    applies to its 65,536-signature batch on every run)."""
+    import numpy as np
+    import ctypes as C
+    import bench
+    from bbs_sign_b200 import api as A
+    ctx = A.BatchContext(A.BLS12_381, bench.IRTF_PK, header=b"", n_messages=10)
+    msgs, offs, sigs, expect = bench.make_workload(ctx, lib, 4096, 10, seed=7)
+    st = np.zeros(4096, dtype=np.uint8)
+    rc = lib.bbs_verify_batch(ctx.handle, 4096, bench.ptr(sigs), bench.ptr(msgs), bench.ptr(offs), 10, bench.ptr(st))
+    assert rc == 0
+    assert np.array_equal(st, expect)
+    ctx.close()
