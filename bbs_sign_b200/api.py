@@ -187,6 +187,30 @@ class BatchContext:
         return st
 
     # ---- sign.rs ----
+    # ---- random-linear-combination batch mode (not in the reference; include/bbs_b200.h) -------------------
+    def rlc_partial(self, signatures, messages: Sequence[Sequence[bytes]], seed: bytes, index_base: int = 0):
+        """This shard's two partial G1 points (compressed) and a status byte (ACCEPT = well-formed shard)."""
+        n = len(messages)
+        n_msgs = len(messages[0]) if n else 0
+        flat, offs = _pack_ragged([m for ms in messages for m in ms])
+        sigs = _buf(b"".join(signatures) if not isinstance(signatures, (bytes, bytearray)) else signatures)
+        parts = np.zeros(2 * self.suite.g1_bytes, dtype=np.uint8)
+        st = np.zeros(1, dtype=np.uint8)
+        self._check(self.lib.bbs_rlc_partial(self._h, n, _ptr(sigs), _ptr(flat), _ptr(offs), n_msgs, _ptr(_buf(seed)),
+                                             index_base, _ptr(parts), _ptr(st)), "bbs_rlc_partial")
+        return parts.tobytes(), int(st[0])
+
+    def rlc_combine(self, parts: Sequence[bytes]) -> int:
+        blob = _buf(b"".join(parts))
+        v = np.zeros(1, dtype=np.uint8)
+        self._check(self.lib.bbs_rlc_combine(self._h, len(parts), _ptr(blob), _ptr(v)), "bbs_rlc_combine")
+        return int(v[0])
+
+    def rlc_verify_batch(self, signatures, messages: Sequence[Sequence[bytes]], seed: bytes) -> int:
+        """One verdict (ST_ACCEPT / ST_REJECT / ST_ERR_*) for the whole batch; see include/bbs_b200.h."""
+        parts, st = self.rlc_partial(signatures, messages, seed, 0)
+        return st if st != ST_ACCEPT else self.rlc_combine([parts])
+
     def core_sign_batch(self, sk_le32: bytes, msg_scalars, n: int, n_msgs: int, want_b: bool = False):
         sc = _buf(msg_scalars)
         if sc.size != n * n_msgs * 32:

@@ -54,12 +54,12 @@ struct Ctx {
     bool coop = false;               // cooperative pairing kernel usable (BLS12-381, no degenerate line)
     CtxView view{};
     // grow-only scratch for the batch calls
-    DevBuf s_gscr;
+    DevBuf s_gscr, s_rlc_pt, s_rlc_sc, s_rlc_parts, s_rlc_bad;
     DevBuf s_sigs, s_scalars, s_msgs, s_offsets, s_pair, s_flags, s_status, s_out, s_out2;
     DevBuf s_commit, s_commit_off, s_dis_idx, s_dis_scalars, s_dis_off, s_ph, s_dis_msgs, s_dis_msg_off;
     void release_all() {
         DevBuf* all[] = {&pk_comp, &gens_comp, &api_id, &header, &dst_h2s, &dst_map, &gens, &W, &K, &domain, &tab,
-                         &lines, &lines_coop, &s_gscr, &misc, &s_sigs, &s_scalars, &s_msgs, &s_offsets, &s_pair, &s_flags, &s_status, &s_out,
+                         &lines, &lines_coop, &s_gscr, &s_rlc_pt, &s_rlc_sc, &s_rlc_parts, &s_rlc_bad, &misc, &s_sigs, &s_scalars, &s_msgs, &s_offsets, &s_pair, &s_flags, &s_status, &s_out,
                          &s_out2, &s_commit, &s_commit_off, &s_dis_idx, &s_dis_scalars, &s_dis_off, &s_ph, &s_dis_msgs,
                          &s_dis_msg_off};
         for (DevBuf* b : all) b->release();
@@ -240,6 +240,77 @@ struct Impl {
         PROF(c, 3, s);
         return BBS_OK;
     }
+
+    // ---- random-linear-combination batch mode (rlc.cuh) ---------------------------------------------
+#ifndef BBS_HOSTSIM
+    // shard -> comp(S1) || comp(S2) in c->s_rlc_parts; *bad != 0 when an item was malformed
+    static int rlc_partial_dev(Ctx* c, size_t n, const uint8_t* d_sigs, const uint8_t* d_scalars, uint32_t n_msgs,
+                               const uint8_t* seed, uint64_t index_base, uint32_t* bad, rt_stream_t s) {
+        const uint32_t blocks = (uint32_t)((n + RLC_TPB - 1) / RLC_TPB);
+        TRY(c->s_rlc_pt.reserve((size_t)(blocks ? blocks : 1) * 2 * 3 * C::Fp::N * 4));
+        TRY(c->s_rlc_sc.reserve((size_t)(blocks ? blocks : 1) * (n_msgs + 1) * 32));
+        TRY(c->s_rlc_parts.reserve(2 * C::G1_BYTES));
+        TRY(c->s_rlc_bad.reserve(4));
+        TRY(rt_memset(c->s_rlc_bad.p, 0, 4, s));
+        RlcArgs a{};
+        a.ctx = c->view; a.sigs = d_sigs; a.scalars = d_scalars; a.n_msgs = n_msgs; a.n = (uint32_t)n;
+        a.index_base = index_base;
+        for (int i = 0; i < 8; i++)
+            a.seed[i] = ((uint32_t)seed[4 * i] << 24) | ((uint32_t)seed[4 * i + 1] << 16) | ((uint32_t)seed[4 * i + 2] << 8) | seed[4 * i + 3];
+        a.pt_part = (uint32_t*)c->s_rlc_pt.p; a.sc_part = (uint32_t*)c->s_rlc_sc.p; a.bad = (uint32_t*)c->s_rlc_bad.p;
+        TRY((launch_rlc_partial<C>(a, blocks, s)));
+        RlcFinishArgs f{c->view, (const uint32_t*)c->s_rlc_pt.p, (const uint32_t*)c->s_rlc_sc.p, blocks, n_msgs,
+                        (uint8_t*)c->s_rlc_parts.p};
+        TRY((launch_rlc_finish<C>(f, s)));
+        c->launches += 2;
+        TRY(rt_d2h(bad, c->s_rlc_bad.p, 4, s));
+        return BBS_OK;
+    }
+    static int rlc_partial(Ctx* c, size_t n, const uint8_t* sigs, const uint8_t* scalars, uint32_t n_msgs,
+                           const uint8_t* seed, uint64_t index_base, uint8_t* parts_out, uint8_t* status) {
+        rt_stream_t s = c->stream;
+        if (n_msgs != c->L) { *status = ST_ERR_MSG_GEN_LEN; return BBS_OK; }
+        TRY(stage(c->s_sigs, sigs, n * SIG, s));
+        TRY(stage(c->s_scalars, scalars, n * n_msgs * 32, s));
+        uint32_t bad = 0;
+        TRY(rlc_partial_dev(c, n, (const uint8_t*)c->s_sigs.p, (const uint8_t*)c->s_scalars.p, n_msgs, seed, index_base, &bad, s));
+        TRY(rt_d2h(parts_out, c->s_rlc_parts.p, 2 * C::G1_BYTES, s));
+        TRY(rt_sync(s));
+        *status = bad ? ST_ERR_MALFORMED : ST_ACCEPT;
+        return BBS_OK;
+    }
+    static int rlc_partial_msgs(Ctx* c, size_t n, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off,
+                                uint32_t n_msgs, const uint8_t* seed, uint64_t index_base, uint8_t* parts_out, uint8_t* status) {
+        rt_stream_t s = c->stream;
+        if (n_msgs != c->L) { *status = ST_ERR_MSG_GEN_LEN; return BBS_OK; }
+        const size_t count = n * n_msgs;
+        TRY(stage(c->s_sigs, sigs, n * SIG, s));
+        TRY(stage(c->s_msgs, msgs, off[count], s));
+        TRY(stage(c->s_offsets, off, (count + 1) * 8, s));
+        TRY(c->s_scalars.reserve(count * 32));
+        TRY(h2s_dev(c, count, (const uint8_t*)c->s_msgs.p, (const uint64_t*)c->s_offsets.p, (uint8_t*)c->s_scalars.p, s));
+        uint32_t bad = 0;
+        TRY(rlc_partial_dev(c, n, (const uint8_t*)c->s_sigs.p, (const uint8_t*)c->s_scalars.p, n_msgs, seed, index_base, &bad, s));
+        TRY(rt_d2h(parts_out, c->s_rlc_parts.p, 2 * C::G1_BYTES, s));
+        TRY(rt_sync(s));
+        *status = bad ? ST_ERR_MALFORMED : ST_ACCEPT;
+        return BBS_OK;
+    }
+    // n_parts x (comp(S1) || comp(S2)) -> one verdict byte
+    static int rlc_combine(Ctx* c, size_t n_parts, const uint8_t* parts, uint8_t* verdict) {
+        rt_stream_t s = c->stream;
+        TRY(stage(c->s_sigs, parts, n_parts * 2 * C::G1_BYTES, s));
+        TRY(c->s_pair.reserve(6 * C::Fp::N * 4));
+        TRY(c->s_flags.reserve(4));
+        TRY(c->s_status.reserve(1));
+        RlcCombineArgs a{c->view, (const uint8_t*)c->s_sigs.p, (uint32_t)n_parts, (uint32_t*)c->s_pair.p,
+                         (uint32_t*)c->s_flags.p, (uint8_t*)c->s_status.p};
+        TRY((launch_rlc_combine<C>(a, s)));
+        c->launches += 1;
+        TRY(pairing_dev(c, 1, (uint8_t*)c->s_status.p, s));
+        return finish_status(c, 1, verdict);
+    }
+#endif
 
     // ---- host-buffer wrappers ---------------------------------------------------------------------
     static int stage(DevBuf& b, const void* h, size_t bytes, rt_stream_t s) {
@@ -479,6 +550,49 @@ int bbs_proof_verify_batch(bbs_ctx* p, size_t n, const uint8_t* proofs, const ui
     if (!proofs || !commit_off || !dis_off || !dis_msg_off || !status) return arg_error("null");
     DISPATCH(c, proof_verify(c, n, proofs, commit, commit_off, idx, dis_msgs, dis_msg_off, dis_off, ph, ph_len, status));
 }
+
+// ---- random-linear-combination batch mode ----------------------------------------------------------------
+#ifndef BBS_HOSTSIM
+int bbs_rlc_partial_core(bbs_ctx* p, size_t n, const uint8_t* sigs, const uint8_t* scalars, uint32_t n_msgs,
+                         const uint8_t seed[32], uint64_t index_base, uint8_t* parts_out, uint8_t* status) {
+    Ctx* c = as_ctx(p);
+    if (!seed || !parts_out || !status || (n && !sigs) || (n && n_msgs && !scalars)) return arg_error("null");
+    DISPATCH(c, rlc_partial(c, n, sigs, scalars, n_msgs, seed, index_base, parts_out, status));
+}
+int bbs_rlc_partial(bbs_ctx* p, size_t n, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off, uint32_t n_msgs,
+                    const uint8_t seed[32], uint64_t index_base, uint8_t* parts_out, uint8_t* status) {
+    Ctx* c = as_ctx(p);
+    if (!seed || !parts_out || !status || !off || (n && !sigs)) return arg_error("null");
+    DISPATCH(c, rlc_partial_msgs(c, n, sigs, msgs, off, n_msgs, seed, index_base, parts_out, status));
+}
+int bbs_rlc_combine(bbs_ctx* p, size_t n_parts, const uint8_t* parts, uint8_t* verdict) {
+    Ctx* c = as_ctx(p);
+    if (!parts || !verdict || !n_parts) return arg_error("null");
+    DISPATCH(c, rlc_combine(c, n_parts, parts, verdict));
+}
+int bbs_rlc_core_verify_batch(bbs_ctx* p, size_t n, const uint8_t* sigs, const uint8_t* scalars, uint32_t n_msgs,
+                              const uint8_t seed[32], uint8_t* verdict) {
+    uint8_t parts[2 * 48], st = 0;
+    int rc = bbs_rlc_partial_core(p, n, sigs, scalars, n_msgs, seed, 0, parts, &st);
+    if (rc) return rc;
+    if (st != BBS_ST_ACCEPT) { *verdict = st; return BBS_OK; }
+    return bbs_rlc_combine(p, 1, parts, verdict);
+}
+int bbs_rlc_verify_batch(bbs_ctx* p, size_t n, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off,
+                         uint32_t n_msgs, const uint8_t seed[32], uint8_t* verdict) {
+    uint8_t parts[2 * 48], st = 0;
+    int rc = bbs_rlc_partial(p, n, sigs, msgs, off, n_msgs, seed, 0, parts, &st);
+    if (rc) return rc;
+    if (st != BBS_ST_ACCEPT) { *verdict = st; return BBS_OK; }
+    return bbs_rlc_combine(p, 1, parts, verdict);
+}
+#else
+int bbs_rlc_partial_core(bbs_ctx*, size_t, const uint8_t*, const uint8_t*, uint32_t, const uint8_t*, uint64_t, uint8_t*, uint8_t*) { rt_set_error("rlc", "needs the CUDA build"); return BBS_E_CUDA; }
+int bbs_rlc_partial(bbs_ctx*, size_t, const uint8_t*, const uint8_t*, const uint64_t*, uint32_t, const uint8_t*, uint64_t, uint8_t*, uint8_t*) { rt_set_error("rlc", "needs the CUDA build"); return BBS_E_CUDA; }
+int bbs_rlc_combine(bbs_ctx*, size_t, const uint8_t*, uint8_t*) { rt_set_error("rlc", "needs the CUDA build"); return BBS_E_CUDA; }
+int bbs_rlc_core_verify_batch(bbs_ctx*, size_t, const uint8_t*, const uint8_t*, uint32_t, const uint8_t*, uint8_t*) { rt_set_error("rlc", "needs the CUDA build"); return BBS_E_CUDA; }
+int bbs_rlc_verify_batch(bbs_ctx*, size_t, const uint8_t*, const uint8_t*, const uint64_t*, uint32_t, const uint8_t*, uint8_t*) { rt_set_error("rlc", "needs the CUDA build"); return BBS_E_CUDA; }
+#endif
 
 int bbs_msg_to_scalars_dev(bbs_ctx* p, size_t count, const uint8_t* d_msgs, const uint64_t* d_off, uint8_t* d_out, void* stream) {
     Ctx* c = as_ctx(p);

@@ -3,6 +3,7 @@
 #pragma once
 #include "kernels.cuh"
 #include "pairing_coop.cuh"
+#include "rlc.cuh"
 #include "selftest.cuh"
 #include "launch.cuh"
 
@@ -17,6 +18,10 @@ template <class C> int launch_h2s(const H2sArgs& a, uint32_t n, rt_stream_t s);
 template <class C> int launch_verify_g1(const VerifyG1Args& a, uint32_t n, rt_stream_t s);
 template <class C> int launch_pairing(const PairingArgs& a, uint32_t n, rt_stream_t s);
 #ifndef BBS_HOSTSIM
+// random-linear-combination batch mode (rlc.cuh)
+template <class C> int launch_rlc_partial(const RlcArgs& a, uint32_t n_blocks, rt_stream_t s);
+template <class C> int launch_rlc_finish(const RlcFinishArgs& a, rt_stream_t s);
+template <class C> int launch_rlc_combine(const RlcCombineArgs& a, rt_stream_t s);
 // cooperative kernel (BLS12-381 only so far); gscratch must hold coop_gscratch_bytes(n)
 int launch_pairing_coop_bls(const CoopArgs& a, rt_stream_t s);
 size_t coop_gscratch_bytes_bls(size_t n);

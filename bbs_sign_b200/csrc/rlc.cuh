@@ -1,0 +1,201 @@
+// Random-linear-combination batch verification (the north star's optional mode): n signatures
+// under one issuer key are accepted together iff
+//     e( sum r_i A_i , W ) * e( sum r_i (e_i A_i - B_i) , BP2 ) == 1,      B_i = K + sum_j m_ij H_j  (verify.rs:81-92)
+// with public-coin 128-bit coefficients r_i = first 16 bytes (big-endian integer) of SHA-256(seed || BE64(i)), r_i = 1
+// if that is 0.  A batch-level, probabilistic verdict (a false accept needs a 2^-128 event over the seed); the per-item
+// entry points remain the reference-exact path.  The B_i terms collapse to L+1 fixed-base products:
+//     sum r_i B_i = (sum r_i) K + sum_j (sum_i r_i m_ij) H_j
+// so the per-item work is one decompression and two scalar multiplications of A_i.  Every GPU reduces its shard to
+// two G1 points (rlc_partial_kernel + rlc_finish_kernel); the partial points of all shards are added and checked with
+// ONE pairing product by rlc_combine (no collective: 2 compressed points per GPU travel through the host).
+#pragma once
+#include "kernels.cuh"
+
+#ifdef __CUDACC__
+namespace bbs {
+
+constexpr int RLC_TPB = 128;
+
+struct RlcArgs {
+    CtxView ctx;
+    const uint8_t* sigs;        // n x (G1 compressed || LE32 e)
+    const uint8_t* scalars;     // n x n_msgs x LE32
+    uint32_t n_msgs, n;
+    uint64_t index_base;        // global index of item 0 of this shard (coefficients depend on the global index)
+    uint32_t seed[8];           // the 32-byte seed as big-endian words
+    uint32_t* pt_part;          // [blocks][2][Jacobian]
+    uint32_t* sc_part;          // [blocks][n_msgs + 1][8]  canonical Fr limbs
+    uint32_t* bad;              // != 0: some item was malformed
+};
+
+// r_i (8 limbs, upper 4 zero)
+__device__ __forceinline__ void rlc_coeff(uint32_t* r, const uint32_t* seed_be, uint64_t index) {
+    Sha256 s;
+    s.init();
+    s.update_words(seed_be, 8);
+    s.put_be64(index);
+    uint32_t h[8];
+    s.finish(h);
+    r[0] = h[3]; r[1] = h[2]; r[2] = h[1]; r[3] = h[0];
+    for (int i = 4; i < 8; i++) r[i] = 0;
+    if ((r[0] | r[1] | r[2] | r[3]) == 0) r[0] = 1;
+}
+
+// block-wide sum of one Jacobian point per thread (result in sp[0])
+template <class C> __device__ __forceinline__ void rlc_block_sum_points(uint32_t (*sp)[3 * C::Fp::N], uint32_t* mine) {
+    const int t = threadIdx.x;
+    g1_copy<C>(sp[t], mine);
+    __syncthreads();
+    for (int s = RLC_TPB / 2; s >= 1; s >>= 1) {
+        if (t < s) g1_add<C>(sp[t], sp[t], sp[t + s]);
+        __syncthreads();
+    }
+}
+// block-wide sum mod r of one Fr value per thread (result in ss[0])
+template <class C> __device__ __forceinline__ void rlc_block_sum_fr(uint32_t (*ss)[8], const uint32_t* mine) {
+    const int t = threadIdx.x;
+    bn_copy<8>(ss[t], mine);
+    __syncthreads();
+    for (int s = RLC_TPB / 2; s >= 1; s >>= 1) {
+        if (t < s) fe_add<typename C::Fr>(ss[t], ss[t], ss[t + s]);
+        __syncthreads();
+    }
+}
+
+template <class C> __global__ void __launch_bounds__(RLC_TPB, 4) rlc_partial_kernel(const RlcArgs a) {
+    using Fr = typename C::Fr;
+    __shared__ uint32_t sp[RLC_TPB][3 * C::Fp::N];
+    __shared__ uint32_t ss[RLC_TPB][8];
+    const CtxView& cx = a.ctx;
+    const uint32_t i = blockIdx.x * RLC_TPB + threadIdx.x;
+    const bool valid = i < a.n;
+    uint32_t P1[G1J], P2[G1J], rm[8];
+    g1_set_inf<C>(P1);
+    g1_set_inf<C>(P2);
+    bn_zero<8>(rm);
+    bool ok = true;
+    const uint8_t* sc = a.scalars + (size_t)(valid ? i : 0) * a.n_msgs * 32;
+    uint32_t r[8];
+    bn_zero<8>(r);
+    if (valid) {
+        const uint8_t* sig = a.sigs + (size_t)i * (C::G1_BYTES + 32);
+        uint32_t A[G1A], e[8];
+        int pa = g1_decompress<C>(A, sig);
+        ok = pa != PT_BAD && fr_from_le32<C>(e, sig + C::G1_BYTES);
+        rlc_coeff(r, a.seed, a.index_base + i);
+        fe_to_mont<Fr>(rm, r);
+        if (ok && pa == PT_OK) {
+            uint32_t ae[8];
+            fe_mul<Fr>(ae, rm, e);                  // r_i e_i mod r, canonical
+            g1_mul_scalar<C>(P1, A, r);
+            g1_mul_scalar<C>(P2, A, ae);
+        }
+    }
+    // points
+    rlc_block_sum_points<C>(sp, P1);
+    if (threadIdx.x == 0) g1_copy<C>(a.pt_part + (size_t)blockIdx.x * 2 * G1J, sp[0]);
+    __syncthreads();
+    rlc_block_sum_points<C>(sp, P2);
+    if (threadIdx.x == 0) g1_copy<C>(a.pt_part + ((size_t)blockIdx.x * 2 + 1) * G1J, sp[0]);
+    __syncthreads();
+    // scalars: sum r_i, sum r_i m_ij
+    uint32_t* scp = a.sc_part + (size_t)blockIdx.x * (a.n_msgs + 1) * 8;
+    rlc_block_sum_fr<C>(ss, r);
+    if (threadIdx.x == 0) bn_copy<8>(scp, ss[0]);
+    __syncthreads();
+    for (uint32_t j = 0; j < a.n_msgs; j++) {
+        uint32_t t[8];
+        bn_zero<8>(t);
+        if (valid && ok) {
+            uint32_t m[8];
+            if (fr_from_le32<C>(m, sc + j * 32)) fe_mul<Fr>(t, rm, m); else ok = false;
+        }
+        rlc_block_sum_fr<C>(ss, t);
+        if (threadIdx.x == 0) bn_copy<8>(scp + (j + 1) * 8, ss[0]);
+        __syncthreads();
+    }
+    if (valid && !ok) atomicOr(a.bad, 1u);
+}
+
+struct RlcFinishArgs {
+    CtxView ctx;
+    const uint32_t* pt_part; const uint32_t* sc_part;
+    uint32_t n_blocks, n_msgs;
+    uint8_t* parts_out;        // comp(S1) || comp(S2)
+};
+// one block: adds the per-block partial sums, subtracts the fixed-base term, compresses the two points
+template <class C> __global__ void __launch_bounds__(RLC_TPB, 1) rlc_finish_kernel(const RlcFinishArgs a) {
+    using Fr = typename C::Fr;
+    __shared__ uint32_t sp[RLC_TPB][3 * C::Fp::N];
+    __shared__ uint32_t ss[RLC_TPB][8];
+    __shared__ uint32_t s1[3 * C::Fp::N];
+    const CtxView& cx = a.ctx;
+    uint32_t acc[G1J];
+    for (int which = 0; which < 2; which++) {
+        g1_set_inf<C>(acc);
+        for (uint32_t b = threadIdx.x; b < a.n_blocks; b += RLC_TPB) g1_add<C>(acc, acc, a.pt_part + ((size_t)b * 2 + which) * G1J);
+        rlc_block_sum_points<C>(sp, acc);
+        if (threadIdx.x == 0 && which == 0) g1_copy<C>(s1, sp[0]);
+        __syncthreads();
+    }
+    // sp[0] = sum r_i e_i A_i.  F = (sum r_i) K + sum_j (sum_i r_i m_ij) H_j on the fixed-base tables
+    uint32_t F[G1J];
+    g1_set_inf<C>(F);
+    for (uint32_t j = 0; j <= a.n_msgs; j++) {
+        uint32_t t[8];
+        bn_zero<8>(t);
+        for (uint32_t b = threadIdx.x; b < a.n_blocks; b += RLC_TPB) fe_add<Fr>(t, t, a.sc_part + ((size_t)b * (a.n_msgs + 1) + j) * 8);
+        rlc_block_sum_fr<C>(ss, t);
+        if (threadIdx.x == 0) {
+            uint32_t sj[8];
+            bn_copy<8>(sj, ss[0]);
+            if (!(j == 0 && cx.k_inf)) tab_accumulate<C>(F, cx.tab, j, sj);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        uint32_t S2[G1J], nF[G1J], S1[G1J];
+        g1_neg<C>(nF, F);
+        g1_copy<C>(S2, sp[0]);
+        g1_add<C>(S2, S2, nF);
+        g1_copy<C>(S1, s1);
+        g1_compress<C>(a.parts_out, S1);
+        g1_compress<C>(a.parts_out + C::G1_BYTES, S2);
+    }
+}
+
+struct RlcCombineArgs {
+    CtxView ctx;
+    const uint8_t* parts; uint32_t n_parts;      // n_parts x (comp(S1) || comp(S2))
+    uint32_t* pair; uint32_t* flags; uint8_t* status;
+};
+// one thread: adds the shards' partial points and prepares the single pairing check
+template <class C> BBS_HD void rlc_combine_item(const RlcCombineArgs& a, uint32_t) {
+    using F = typename C::Fp;
+    const CtxView& cx = a.ctx;
+    uint32_t S[2][G1J];
+    g1_set_inf<C>(S[0]);
+    g1_set_inf<C>(S[1]);
+    for (uint32_t k = 0; k < a.n_parts; k++)
+        for (int w = 0; w < 2; w++) {
+            uint32_t p[G1A];
+            int st = g1_decompress<C>(p, a.parts + ((size_t)k * 2 + w) * C::G1_BYTES);
+            if (st == PT_BAD) { a.status[0] = ST_ERR_MALFORMED; a.flags[0] = FL_DONE; return; }
+            if (st == PT_OK) g1_add_mixed<C>(S[w], S[w], p);
+        }
+    uint32_t* pr = a.pair;
+    uint32_t fl = 0;
+    for (int w = 0; w < 2; w++) {
+        uint32_t aff[G1A];
+        bool fin = g1_to_affine<C>(aff, S[w]);
+        bn_copy<2 * C::Fp::N>(pr + w * 3 * FPN, aff);
+        fe_set_one<F>(pr + w * 3 * FPN + 2 * FPN);
+        if (!fin) fl |= (w == 0 ? FL_SKIP0 : FL_SKIP1);
+    }
+    if (cx.w_inf) fl |= FL_SKIP0;
+    a.flags[0] = fl;
+    a.status[0] = ST_REJECT;
+}
+
+}  // namespace bbs
+#endif  // __CUDACC__

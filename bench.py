@@ -384,6 +384,72 @@ def run_proof(args):
     return out
 
 
+def run_rlc(args):
+    """Optional random-linear-combination mode (BASELINE configs[4] shape, one GPU per rank): n valid signatures
+    under one issuer, one batch verdict per step through the host-buffer call bbs_rlc_verify_batch (copies inside)."""
+    import torch
+    import torch.distributed as dist
+    from bbs_sign_b200 import api, _native
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    lib = _native.load()
+    n, L = args.n, args.L
+    ctx = api.BatchContext(api.BLS12_381, IRTF_PK, header=b"", n_messages=L, device=local)
+    rng = np.random.default_rng(99 + rank)
+    msgs = rng.integers(0, 256, size=n * L * MSG_BYTES, dtype=np.uint8)
+    offs = (np.arange(n * L + 1, dtype=np.uint64) * MSG_BYTES)
+    sigs = np.zeros(n * SIG_BYTES, dtype=np.uint8)
+    st = np.zeros(n, dtype=np.uint8)
+    sk = np.frombuffer(IRTF_SK.to_bytes(32, "little"), dtype=np.uint8).copy()
+    if lib.bbs_sign_batch(ctx.handle, ptr(sk), n, ptr(msgs), ptr(offs), L, ptr(sigs), None, ptr(st)) != 0:
+        raise RuntimeError(lib.bbs_last_error().decode())
+    seed = np.frombuffer(bytes(range(32)), dtype=np.uint8).copy()
+    verdict = np.zeros(1, dtype=np.uint8)
+
+    def step():
+        if lib.bbs_rlc_verify_batch(ctx.handle, n, ptr(sigs), ptr(msgs), ptr(offs), L, ptr(seed), ptr(verdict)) != 0:
+            raise RuntimeError(lib.bbs_last_error().decode())
+        if verdict[0] != 1:
+            raise RuntimeError(f"rlc verdict {verdict[0]} on a valid batch")
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=torch.device("cuda", local))
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    # a corrupted batch must be rejected
+    sigs[48] ^= 1
+    lib.bbs_rlc_verify_batch(ctx.handle, n, ptr(sigs), ptr(msgs), ptr(offs), L, ptr(seed), ptr(verdict))
+    if verdict[0] != 0:
+        raise RuntimeError("rlc accepted a corrupted batch")
+    out = None
+    if rank == 0:
+        v = world * n * args.steps / float(dt.item())
+        out = {"metric": "bls12_381_bbs_rlc_batch_verified_signatures_per_sec_L10", "value": v, "unit": "signatures/s",
+               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(dt.item()) / args.steps * 1e3,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+               "config": {"workload": f"random-linear-combination batch verify: {n} valid signatures x L={L}, one verdict per batch "
+                                      "(optional mode; host buffers, copies inside the timed region)", "n_per_gpu": n},
+               "e2e": {"value": v, "unit": "signatures/s", "h2d_bytes_per_step": int(msgs.nbytes + offs.nbytes + sigs.nbytes),
+                       "d2h_bytes_per_step": 2 * 48 + 1}, "gpu_launches": 6}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return out
+
+
 def cpu_baseline(args, sample):
     """The oracle port of the reference's per-item path (msg_to_scalars + core_verify with two pairings) on
     the host.  Uses oracle/_ref/ (compiled C restatement, all cores) when present, else the big-int Python
@@ -429,12 +495,14 @@ def main():
     ap.add_argument("--L", type=int, default=L_DEFAULT)
     ap.add_argument("--cpu-sample", type=int, default=0, help="signatures per CPU-baseline step (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="verify", choices=["verify", "proof"],
+    ap.add_argument("--workload", default="verify", choices=["verify", "proof", "rlc"],
                     help="verify = BASELINE configs[1] (the headline); proof = configs[3]-shaped proof_verify")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.workload == "proof" and args.impl == "ours":
         out = run_proof(args)
+    elif args.workload == "rlc" and args.impl == "ours":
+        out = run_rlc(args)
     else:
         out = run_reference(args) if args.impl == "reference" else run_ours(args)
     if out is not None:

@@ -64,8 +64,8 @@ const char* bbs_last_error(void);
  *   decodes `pk` (G2) and the `n_generators` = L+1 generators Q1, H_1..H_L (G1) -- the `generators: &[E::G1]`
  *   argument of core_verify / core_sign / core_proof_verify (src/verify.rs:53-60, src/sign.rs:63-69,
  *   src/proof_verify.rs:64-73); computes `calculate_domain` (src/utils/core_utilities.rs:24-63) for
- *   (pk, generators, header, api_id) once; K = P1 + Q1*domain; 8-bit fixed-base window tables for K and
- *   every H_j; and the Miller-loop line tables of pk and BP2.
+ *   (pk, generators, header, api_id) once; K = P1 + Q1*domain; fixed-base window tables for K and
+ *   every H_j (12-bit windows); and the Miller-loop line tables of pk and BP2.
  * `api_id` is the reference's `api_id` (CIPHERSUITE_ID || "H2G_HM2S_" in the interface functions,
  * arbitrary in the core tests).  Identity pk is allowed (the reference returns Ok(false) for it).
  * Generators must be non-identity points of G1. */
@@ -121,6 +121,25 @@ int bbs_proof_verify_batch(bbs_ctx* ctx, size_t n, const uint8_t* proofs_fixed, 
                            const uint64_t* commit_off, const uint32_t* disclosed_idx, const uint8_t* dis_msgs,
                            const uint64_t* dis_msg_off, const uint64_t* dis_off, const uint8_t* ph, size_t ph_len,
                            uint8_t* status);
+
+/* ---- random-linear-combination batch mode (the optional mode of the north star; not in the reference) ----------
+ * One verdict for n signatures under the context's issuer key:
+ *     e( sum r_i A_i , W ) * e( sum r_i (e_i A_i - B_i) , BP2 ) == 1,   B_i as in src/verify.rs:81-86,
+ * r_i = the first 16 bytes, as a big-endian integer, of SHA-256(seed || BE64(index_base + i)) (1 if that is 0).
+ * ACCEPT means every item verifies except with probability 2^-128 over the seed (choose the seed after the batch
+ * is fixed); REJECT means at least one item does not; ERR_MALFORMED / ERR_MSG_GEN_LEN as in bbs_core_verify_batch.
+ * Sharding: every GPU reduces its shard to two compressed G1 points with bbs_rlc_partial[_core] (index_base = the
+ * shard's first global index); bbs_rlc_combine adds the shards' points on one GPU and does the single pairing check.
+ * bbs_rlc_[core_]verify_batch = one shard + combine. */
+int bbs_rlc_partial_core(bbs_ctx* ctx, size_t n, const uint8_t* sigs, const uint8_t* msg_scalars, uint32_t n_msgs,
+                         const uint8_t seed[32], uint64_t index_base, uint8_t* parts_out /* 2 x G1 */, uint8_t* status);
+int bbs_rlc_partial(bbs_ctx* ctx, size_t n, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* offsets,
+                    uint32_t n_msgs, const uint8_t seed[32], uint64_t index_base, uint8_t* parts_out, uint8_t* status);
+int bbs_rlc_combine(bbs_ctx* ctx, size_t n_parts, const uint8_t* parts /* n_parts x 2 x G1 */, uint8_t* verdict);
+int bbs_rlc_core_verify_batch(bbs_ctx* ctx, size_t n, const uint8_t* sigs, const uint8_t* msg_scalars, uint32_t n_msgs,
+                              const uint8_t seed[32], uint8_t* verdict);
+int bbs_rlc_verify_batch(bbs_ctx* ctx, size_t n, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* offsets,
+                         uint32_t n_msgs, const uint8_t seed[32], uint8_t* verdict);
 
 /* ---- device-buffer entry points (no copies; all pointers are device pointers on the context's GPU;
  *      work is enqueued on `stream` (a cudaStream_t, NULL = default stream) and NOT synchronized) ------ */

@@ -337,3 +337,63 @@ def case_proof_errors(lib_path, curve_name):
     want = int(O.proof_verify(ocs, pk, p0, b"", b"", dm, [0, 2]))
     assert got.tolist() == [want]
     ctx.close()
+
+
+def rlc_coeff(seed: bytes, i: int) -> int:
+    """coefficient definition of include/bbs_b200.h (random-linear-combination mode)"""
+    import hashlib
+    r = int.from_bytes(hashlib.sha256(seed + i.to_bytes(8, "big")).digest()[:16], "big")
+    return r or 1
+
+
+def case_rlc(lib_path, curve_name, L=3, n=9):
+    """Random-linear-combination batch mode against the oracle: the two partial sums of a shard are compared bit-exactly
+    with sum r_i A_i and sum r_i (e_i A_i - B_i) computed by the oracle, and the verdicts with the per-item truth."""
+    suite, ocs = SUITES[curve_name]
+    sk, pk = keypair(ocs, 1)
+    header = b"rlc"
+    ctx, gens = make_ctx(lib_path, suite, ocs, pk, header, L)
+    msgs = [[rng_bytes(f"rlc{i}.{j}", 32) for j in range(L)] for i in range(n)]
+    sigs = [O.sign(ocs, sk, m, header) for m in msgs]
+    seed = rng_bytes("rlc-seed", 32)
+    F1 = ocs.F1
+    dom = O.calculate_domain(ocs, pk, gens[0], gens[1:], header, ocs.api_id)
+
+    def expected_parts(sig_list, base):
+        S1, S2 = None, None
+        for i, (sg, m) in enumerate(zip(sig_list, msgs)):
+            A, e = sg
+            r = rlc_coeff(seed, base + i)
+            B = O.compute_B(ocs, gens, dom, O.msg_to_scalars(ocs, m, ocs.api_id))
+            if A is not None:
+                S1 = O.ec_add(F1, S1, O.ec_mul(F1, A, r))
+                S2 = O.ec_add(F1, S2, O.ec_mul(F1, A, r * e % ocs.r))
+            S2 = O.ec_add(F1, S2, O.ec_neg(F1, O.ec_mul(F1, B, r)))
+        return ocs.g1_compress(S1) + ocs.g1_compress(S2)
+
+    enc = [O.signature_to_bytes(ocs, s) for s in sigs]
+    parts, st = ctx.rlc_partial(enc, msgs, seed, 5)
+    assert st == A.ST_ACCEPT
+    assert parts == expected_parts(sigs, 5), "partial sums differ from the oracle"
+    assert ctx.rlc_verify_batch(enc, msgs, seed) == A.ST_ACCEPT
+    # two shards with consistent global indexes combine to the same verdict
+    p0, _ = ctx.rlc_partial(enc[:4], msgs[:4], seed, 0)
+    p1, _ = ctx.rlc_partial(enc[4:], msgs[4:], seed, 4)
+    assert ctx.rlc_combine([p0, p1]) == A.ST_ACCEPT
+    # one bad signature anywhere -> REJECT; identity A -> REJECT; malformed -> ERR
+    bad = list(sigs)
+    bad[3] = (bad[3][0], (bad[3][1] + 1) % ocs.r)
+    assert ctx.rlc_verify_batch([O.signature_to_bytes(ocs, s) for s in bad], msgs, seed) == A.ST_REJECT
+    bad = list(sigs)
+    bad[7] = (None, bad[7][1])
+    encb = [O.signature_to_bytes(ocs, s) for s in bad]
+    assert ctx.rlc_verify_batch(encb, msgs, seed) == A.ST_REJECT
+    assert ctx.rlc_partial(encb, msgs, seed, 0)[0] == expected_parts(bad, 0)
+    if L > 0:
+        m2 = [list(m) for m in msgs]
+        m2[0][0] = m2[0][0] + b"x"
+        assert ctx.rlc_verify_batch(enc, m2, seed) == A.ST_REJECT
+    mal = list(enc)
+    mal[2] = b"\xff" * len(mal[2])
+    assert ctx.rlc_verify_batch(mal, msgs, seed) == A.ST_ERR_MALFORMED
+    ctx.close()

@@ -85,3 +85,8 @@ def test_large_batch_consistency(lib):
     assert rc == 0
     assert np.array_equal(st, expect)
     ctx.close()
+
+
+@pytest.mark.parametrize("curve,L", [("BLS12_381", 3), ("BN254", 2), ("BLS12_381", 0)])
+def test_rlc(lib, curve, L):
+    P.case_rlc(None, curve, L=L, n=9)
