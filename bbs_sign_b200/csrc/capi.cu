@@ -98,7 +98,7 @@ struct Impl {
         TRY(c->K.reserve(2 * C::Fp::N * 4));
         TRY(c->domain.reserve(32));
         TRY(c->misc.reserve((n_gens + 2) * 4));
-        const size_t tab_entries = (size_t)(L + 1) * TAB_WINDOWS * TAB_ENTRIES;
+        const size_t tab_entries = (size_t)(L + 1) * TabGeom<C>::WINDOWS * TabGeom<C>::ENTRIES;
         TRY(c->tab.reserve(tab_entries * 2 * C::Fp::N * 4));
         const int n_lines = ate_line_count<C>();
         TRY(c->lines.reserve((size_t)n_lines * 2 * 4 * C::Fp::N * 4));

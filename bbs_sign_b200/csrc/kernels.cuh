@@ -23,23 +23,39 @@ enum : uint8_t {
     ST_ERR_MALFORMED = 5,     // undecodable point / non-canonical scalar / the reference's panic cases
 };
 
-// fixed-base tables: TAB_BITS-bit windows over a 256-bit scalar.  12-bit windows: 22 mixed additions per generator
-// instead of 32, 95 MB of tables at L = 10 (L2-resident on B200), 285 MB at L = 32 (gathered from HBM: 96 B per add).
-#ifndef BBS_TAB_BITS
+// Fixed-base tables: entry (g, w, d) = (d * 2^(BITS w)) * base_g in affine form, d = 1 .. 2^BITS - 1.
+//   BLS12-381: the scalar is split with the GLV endomorphism (g1.cuh: k = k1 + k2 lambda, both < 2^128) and BOTH halves
+//   use the same table (phi of an entry is (beta x, y): one extra multiplication), so 16-bit windows need only 8
+//   windows: 16 mixed additions per generator from a 50 MB table (550 MB at L = 10, 96-byte gathers from HBM).
+//   BN254 (no endomorphism constants here): 12-bit windows over the 254-bit scalar, 22 additions per generator.
+//   The host simulation (tests only) builds its tables on CPU cores and uses 8-bit windows.
+#ifndef BBS_TAB_BITS_GLV
 #ifdef BBS_HOSTSIM
-#define BBS_TAB_BITS 8      // the host simulation (tests only) builds its tables on CPU cores
+#define BBS_TAB_BITS_GLV 8
+#define BBS_TAB_BITS_PLAIN 8
 #else
-#define BBS_TAB_BITS 12
+#define BBS_TAB_BITS_GLV 16
+#define BBS_TAB_BITS_PLAIN 12
 #endif
 #endif
-constexpr int TAB_BITS = BBS_TAB_BITS;
-constexpr int TAB_WINDOWS = (256 + TAB_BITS - 1) / TAB_BITS;
-constexpr int TAB_ENTRIES = (1 << TAB_BITS) - 1;  // digits 1..2^TAB_BITS-1
-BBS_HD uint32_t tab_digit(const uint32_t* s, int w) {      // s: 8 canonical limbs
-    const int bit = w * TAB_BITS, word = bit >> 5, off = bit & 31;
+template <class C> struct TabGeom;
+template <> struct TabGeom<Bls> {
+    static constexpr bool GLV = true;
+    static constexpr int BITS = BBS_TAB_BITS_GLV;
+    static constexpr int WINDOWS = (128 + BITS - 1) / BITS;
+    static constexpr int ENTRIES = (1 << BITS) - 1;
+};
+template <> struct TabGeom<Bn> {
+    static constexpr bool GLV = false;
+    static constexpr int BITS = BBS_TAB_BITS_PLAIN;
+    static constexpr int WINDOWS = (256 + BITS - 1) / BITS;
+    static constexpr int ENTRIES = (1 << BITS) - 1;
+};
+template <class C> BBS_HD uint32_t tab_digit(const uint32_t* s, int nlimbs, int w) {      // s: canonical limbs
+    const int bit = w * TabGeom<C>::BITS, word = bit >> 5, off = bit & 31;
     uint64_t v = s[word];
-    if (word + 1 < 8) v |= (uint64_t)s[word + 1] << 32;
-    return (uint32_t)(v >> off) & (uint32_t)TAB_ENTRIES;
+    if (word + 1 < nlimbs) v |= (uint64_t)s[word + 1] << 32;
+    return (uint32_t)(v >> off) & (uint32_t)TabGeom<C>::ENTRIES;
 }
 constexpr int MAX_L = 256;
 
@@ -99,6 +115,8 @@ template <class C> BBS_HD void ctx_domain_item(const CtxDomainArgs& a, uint32_t)
 struct CtxTableArgs { const uint32_t* K; const uint32_t* gens; uint32_t* tab; };
 // entry (g, w, d) = (d * 2^(8w)) * base_g in affine form
 template <class C> BBS_HD void ctx_table_item(const CtxTableArgs& a, uint32_t i) {
+    constexpr uint32_t TAB_ENTRIES = TabGeom<C>::ENTRIES, TAB_WINDOWS = TabGeom<C>::WINDOWS;
+    constexpr int TAB_BITS = TabGeom<C>::BITS;
     uint32_t d = i % TAB_ENTRIES + 1, w = (i / TAB_ENTRIES) % TAB_WINDOWS, g = i / (TAB_ENTRIES * TAB_WINDOWS);
     const uint32_t* base = g == 0 ? a.K : a.gens + g * G1A;
     uint32_t k[10];
@@ -152,14 +170,37 @@ template <class C> BBS_HD void h2s_item(const H2sArgs& a, uint32_t t) {
 // ---- fixed-base MSM over the window tables -------------------------------------------------------------
 // acc += s * base_g, s canonical limbs (8)
 template <class C> BBS_HDN void tab_accumulate(uint32_t* acc, const uint32_t* tab, uint32_t g, const uint32_t* s) {
-    const uint32_t* tg = tab + (size_t)g * TAB_WINDOWS * TAB_ENTRIES * G1A;
-    for (int w = 0; w < TAB_WINDOWS; w++) {
-        uint32_t d = tab_digit(s, w);
-        if (d) {
-            uint32_t e[G1A];
-            const uint32_t* src = tg + ((size_t)w * TAB_ENTRIES + (d - 1)) * G1A;
-            for (int j = 0; j < G1A; j++) e[j] = src[j];
-            g1_add_mixed<C>(acc, acc, e);
+    using G = TabGeom<C>;
+    const uint32_t* tg = tab + (size_t)g * G::WINDOWS * G::ENTRIES * G1A;
+    if (G::GLV) {
+        uint32_t k1[5], k2[5];
+        bls_glv_split(k1, k2, s);
+        for (int w = 0; w < G::WINDOWS; w++) {
+            uint32_t d1 = tab_digit<C>(k1, 5, w), d2 = tab_digit<C>(k2, 5, w);
+            if (d1) {
+                uint32_t e[G1A];
+                const uint32_t* src = tg + ((size_t)w * G::ENTRIES + (d1 - 1)) * G1A;
+                for (int j = 0; j < G1A; j++) e[j] = src[j];
+                g1_add_mixed<C>(acc, acc, e);
+            }
+            if (d2) {
+                uint32_t e[G1A], t[FPN];
+                const uint32_t* src = tg + ((size_t)w * G::ENTRIES + (d2 - 1)) * G1A;
+                for (int j = 0; j < G1A; j++) e[j] = src[j];
+                fe_mul<typename C::Fp>(t, e, C::GLV_BETA());            // phi(x, y) = (beta x, y)
+                bn_copy<C::Fp::N>(e, t);
+                g1_add_mixed<C>(acc, acc, e);
+            }
+        }
+    } else {
+        for (int w = 0; w < G::WINDOWS; w++) {
+            uint32_t d = tab_digit<C>(s, 8, w);
+            if (d) {
+                uint32_t e[G1A];
+                const uint32_t* src = tg + ((size_t)w * G::ENTRIES + (d - 1)) * G1A;
+                for (int j = 0; j < G1A; j++) e[j] = src[j];
+                g1_add_mixed<C>(acc, acc, e);
+            }
         }
     }
 }
