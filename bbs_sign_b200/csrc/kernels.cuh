@@ -304,11 +304,14 @@ template <class C> BBS_HD void sign_item(const SignArgs& a, uint32_t i) {
     fe_add<Fr>(s, a.sk, e);
     if (bn_is_zero<8>(s)) { a.status[i] = ST_ERR_MALFORMED; return; }               // sign.rs:129 panics
     fe_to_mont<Fr>(sm, s); fe_inv<Fr>(sm, sm); fe_from_mont<Fr>(s, sm);              // (sk+e)^-1
-    uint32_t Aj[G1J];
-    g1_mul<C>(Aj, B, s, Fr::BITS);                                                   // sign.rs:130
+    // A = B * (sk + e)^-1 (sign.rs:130) with the windowed GLV multiplication; B is normalised first (its affine
+    // form is also what the optional B output serialises)
+    uint32_t Aj[G1J], Baff[G1A];
+    bool bfin = g1_to_affine<C>(Baff, B);
+    if (bfin) g1_mul_scalar<C>(Aj, Baff, s); else g1_set_inf<C>(Aj);
     g1_compress<C>(out, Aj);
     limbs_to_le<8>(out + C::G1_BYTES, e);
-    if (a.b_out) g1_compress<C>(a.b_out + (size_t)i * C::G1_BYTES, B);
+    if (a.b_out) g1_compress_affine<C>(a.b_out + (size_t)i * C::G1_BYTES, Baff, !bfin);
     a.status[i] = ST_ACCEPT;
 }
 
