@@ -384,6 +384,78 @@ def run_proof(args):
     return out
 
 
+def run_bn254(args):
+    """BASELINE configs[2] shape: BN254 core_verify over pre-hashed scalar messages (L = 31), device-resident inputs.
+    Key pair: tests/golden/bn254_bench_key.npz (made once with the oracle's key_gen / sk_to_pk); signatures are made on
+    the GPU by bbs_core_sign_batch.  BN254 still runs the per-thread pairing kernel."""
+    import torch
+    import torch.distributed as dist
+    from bbs_sign_b200 import api, _native
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    lib = _native.load()
+    key = np.load(os.path.join(ROOT, "tests", "golden", "bn254_bench_key.npz"))
+    n, L = args.n, 31
+    ctx = api.BatchContext(api.BN254, bytes(key["pk"]), header=b"", n_messages=L, device=local)
+    rng = np.random.default_rng(5 + rank)
+    sc = rng.integers(0, 256, size=(n * L, 32), dtype=np.uint8)
+    sc[:, 31] &= 0x0f                                   # < 2^252 < r: canonical scalars
+    sc = np.ascontiguousarray(sc.reshape(-1))
+    sigs = np.zeros(n * 64, dtype=np.uint8)
+    st = np.zeros(n, dtype=np.uint8)
+    if lib.bbs_core_sign_batch(ctx.handle, ptr(np.ascontiguousarray(key["sk"])), n, ptr(sc), L, ptr(sigs), None, ptr(st)) != 0:
+        raise RuntimeError(lib.bbs_last_error().decode())
+    expect = np.ones(n, dtype=np.uint8)
+    sg = sigs.reshape(n, 64)
+    for i in range(5, n, 16):
+        sg[i, 32] ^= 1                                  # e ^ 1
+        expect[i] = 0
+    dev = torch.device("cuda", local)
+    d_sigs = torch.from_numpy(sigs).to(dev)
+    d_sc = torch.from_numpy(sc).to(dev)
+    d_status = torch.zeros(n, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        if lib.bbs_core_verify_batch_dev(ctx.handle, n, ptr(d_sigs), ptr(d_sc), L, ptr(d_status), C.c_void_p(stream.cuda_stream)) != 0:
+            raise RuntimeError(lib.bbs_last_error().decode())
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if not np.array_equal(d_status.cpu().numpy(), expect):
+        raise RuntimeError("bn254 status vector mismatch")
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = None
+    if rank == 0:
+        v = world * n * args.steps / float(t.item())
+        out = {"metric": "bn254_bbs_core_verifies_per_sec_L31", "value": v, "unit": "verifies/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(t.item()) / args.steps * 1e3,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+               "config": {"workload": f"BN254 core_verify: {n} signatures x L=31 pre-hashed scalar messages, one issuer key, "
+                                      "1/16 corrupted (BASELINE configs[2] shape); per-thread pairing kernel", "n_per_gpu": n},
+               "gpu_launches": 2}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return out
+
+
 def run_rlc(args):
     """Optional random-linear-combination mode (BASELINE configs[4] shape, one GPU per rank): n valid signatures
     under one issuer, one batch verdict per step through the host-buffer call bbs_rlc_verify_batch (copies inside)."""
@@ -495,7 +567,7 @@ def main():
     ap.add_argument("--L", type=int, default=L_DEFAULT)
     ap.add_argument("--cpu-sample", type=int, default=0, help="signatures per CPU-baseline step (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="verify", choices=["verify", "proof", "rlc"],
+    ap.add_argument("--workload", default="verify", choices=["verify", "proof", "rlc", "bn254"],
                     help="verify = BASELINE configs[1] (the headline); proof = configs[3]-shaped proof_verify")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -503,6 +575,8 @@ def main():
         out = run_proof(args)
     elif args.workload == "rlc" and args.impl == "ours":
         out = run_rlc(args)
+    elif args.workload == "bn254" and args.impl == "ours":
+        out = run_bn254(args)
     else:
         out = run_reference(args) if args.impl == "reference" else run_ours(args)
     if out is not None:
