@@ -121,19 +121,9 @@ template <class C> BBS_HDN bool g1_on_curve(const uint32_t* a) {
     return bn_eq<C::Fp::N>(l, rr);
 }
 
-// r = k * P  (P Jacobian), k = canonical little-endian limbs, `bits` significant bits; MSB-first
-// double-and-add (what ark-ec's `Projective * Fr` does; variable time like the reference).
-template <class C> BBS_HDN void g1_mul(uint32_t* r, const uint32_t* p, const uint32_t* k, int bits) {
-    uint32_t acc[G1J], base[G1J];
-    g1_copy<C>(base, p);
-    g1_set_inf<C>(acc);
-    for (int i = bits - 1; i >= 0; i--) {
-        g1_dbl<C>(acc, acc);
-        if ((k[i >> 5] >> (i & 31)) & 1) g1_add<C>(acc, acc, base);
-    }
-    g1_copy<C>(r, acc);
-}
-// same with an affine base (mixed additions)
+// r = k * P, k = little-endian limbs, `bits` significant bits; MSB-first double-and-add (what ark-ec's
+// `Projective * Fr` does).  Used where the scalar is a public constant (context creation, self tests); the per-item
+// multiplications use g1_msm_win4 below.
 template <class C> BBS_HDN void g1_mul_affine(uint32_t* r, const uint32_t* a, const uint32_t* k, int bits) {
     uint32_t acc[G1J];
     g1_set_inf<C>(acc);

@@ -98,16 +98,6 @@ template <class C> BBS_HDN void f12_mul_line(uint32_t* f, const uint32_t* line, 
     else            f12_mul_by_034<C>(f, y, b, a);   // py + (Bc px) w + A (v w)
 }
 
-// Jacobian point -> (X*Z, Y, Z^3)
-template <class C> BBS_HDN void g1_to_line_arg(uint32_t* out, const uint32_t* p) {
-    using F = typename C::Fp;
-    uint32_t z2[FPN];
-    fe_mul<F>(out, p, p + 2 * FPN);
-    bn_copy<C::Fp::N>(out + FPN, p + FPN);
-    fe_sqr<F>(z2, p + 2 * FPN);
-    fe_mul<F>(out + 2 * FPN, z2, p + 2 * FPN);
-}
-
 // f = f_{Q0}(P0) * f_{Q1}(P1) over the shared loop; a skipped pair contributes 1 (ark-ec filters pairs
 // with an identity argument: SURVEY 4 / Appendix C).
 template <class C> BBS_HDN void miller2(uint32_t* f, const uint32_t* lines, const uint32_t* P0, bool skip0,

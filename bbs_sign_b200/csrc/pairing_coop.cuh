@@ -52,10 +52,6 @@ template <> struct Coop<Bls> {
     static __device__ __forceinline__ void merge(uint32_t* w, const uint32_t* v) { coop_merge12(w, v); }
     static __device__ __forceinline__ void add_e(uint32_t* acc, const uint32_t* w) { coop_acc_add_e12(acc, w); }
     static __device__ __forceinline__ void sub_e(uint32_t* acc, const uint32_t* w) { coop_acc_sub_e12(acc, w); }
-    static __device__ __forceinline__ void add_o(uint32_t* acc, const uint32_t* w) { coop_acc_add_o12(acc, w); }
-    static __device__ __forceinline__ void sub_o(uint32_t* acc, const uint32_t* w) { coop_acc_sub_o12(acc, w); }
-    static __device__ __forceinline__ void accm_e(uint32_t* acc, const uint32_t* t, uint32_t cin, uint32_t ext) { coop_accm_e12(acc, t, cin, ext); }
-    static __device__ __forceinline__ void accm_o(uint32_t* acc, const uint32_t* t, uint32_t cin, uint32_t ext) { coop_accm_o12(acc, t, cin, ext); }
     static __device__ __forceinline__ void add_hi(uint32_t* acc, const uint32_t* z) { coop_acc_add_hi12(acc, z); }
     static __device__ __forceinline__ void sub_hi(uint32_t* acc, const uint32_t* z) { coop_acc_sub_hi12(acc, z); }
     static __device__ __forceinline__ void addn(uint32_t* d, const uint32_t* s) { coop_addn12(d, s); }

@@ -42,7 +42,10 @@ template <class C> BBS_HD void g1_mul_test_item(const G1MulTestArgs& t, uint32_t
     int st = g1_decompress<C>(A, t.pts + (size_t)i * C::G1_BYTES);
     limbs_from_le<8>(k, t.sc + (size_t)i * 32);
     if (st == PT_BAD) { for (int j = 0; j < C::G1_BYTES; j++) o[j] = 0xff; return; }
-    if (st == PT_INF) g1_set_inf<C>(R); else g1_mul_affine<C>(R, A, k, 256);
+    // canonical scalars take the production path (windowed GLV, g1_mul_scalar); others the plain double-and-add
+    if (st == PT_INF) g1_set_inf<C>(R);
+    else if (fe_is_canonical<typename C::Fr>(k)) g1_mul_scalar<C>(R, A, k);
+    else g1_mul_affine<C>(R, A, k, 256);
     g1_compress<C>(o, R);
 }
 

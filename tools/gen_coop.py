@@ -8,7 +8,8 @@ instead of one per product.  Primitives (N = limbs of Fp: 12 for BLS12-381, 8 fo
 
   coop_wmul_e<N>(w, a, b)   w[0..2N-1]  = sum_{i+j even} a_j b_i 2^(32(i+j))      (fresh, even-aligned pairs)
   coop_wmul_o<N>(v, a, b)   v[0..2N-2]  = sum_{i+j odd } a_j b_i 2^(32(i+j-1))    (fresh, value sits at word 1)
-  coop_acc_{add,sub}_{e,o}<N>(acc, w)   acc[0..2N] +-= w  (o: shifted up one word), two's complement
+  coop_merge<N>(w, v)       w += v << 32: the full 2N-word product
+  coop_acc_{add,sub}_e<N>(acc, w)       acc[0..2N] +-= w, two's complement
   coop_acc_{add,sub}_hi<N>(acc, z)      acc[N..2N] +-= z[0..N-1]                  (adds z*R before REDC)
   coop_redc_<curve>(r, acc)             r[0..N-1] = (acc + M p) / R,  needs 0 <= acc < (2^(32N) - p) R
   coop_sub_kp_<curve><K>(d, r)          d = r - K p, returns the borrow mask      (canonicalisation steps)
@@ -219,51 +220,6 @@ def addsub_prog(dst, src, sub, chunk=13, final_wrap=True):
     return P
 
 
-def accm_prog(dst, src, chunk=13):
-    """dst[k] += src[k] (k < len(src)), dst[k] += ext above, with the carry flag seeded from `cy` (0 or 1) on entry:
-    the sign-masked accumulate  acc += (w ^ m) + (m & 1)  with ext = m, i.e. acc +-= w without a branch."""
-    P = Prog()
-    P.wrap_ok = {"cy"}
-    n = len(dst)
-    srcs = list(src) + ["ext"] * (n - len(src))
-    k = 0
-    while k < n:
-        m = min(chunk, n - k)
-        ops = [("add.cc", "cy", "cy", MASK)]
-        for q in range(m):
-            idx = k + q
-            lastword = idx == n - 1
-            ops.append(("addc" if lastword else "addc.cc", dst[idx], dst[idx], srcs[idx]))
-            if lastword:
-                P.wrap_ok.add(dst[idx])
-        if k + m < n:
-            ops.append(("addc", "cy", 0, 0))
-        P.stmt(ops)
-        k += m
-    return P
-
-
-def check_accm():
-    rnd = random.Random(9)
-    for n, ns in ((25, 24), (24, 23), (17, 16), (16, 15)):
-        dst = [f"d{i}" for i in range(n)]
-        src = [f"s{i}" for i in range(ns)]
-        P = accm_prog(dst, src)
-        for t in range(300):
-            d = rnd.getrandbits(32 * n)
-            w = rnd.getrandbits(32 * ns)
-            neg = t & 1
-            m = MASK if neg else 0
-            env = {"cy": 1 if neg else 0, "ext": m}
-            for i in range(n):
-                env[f"d{i}"] = limbs(d, n)[i]
-            for i in range(ns):
-                env[f"s{i}"] = limbs(w, ns)[i] ^ m
-            P.run(env)
-            want = (d - w if neg else d + w) % (1 << (32 * n))
-            assert from_limbs(env, "d", n) == want, (n, ns, t)
-
-
 def merge_prog(n):
     """w[1 + k] += v[k], k = 0..2n-2: the two half products of coop_wmul_{e,o} -> the full 2n-word product in w."""
     dst = [f"w{k + 1}" for k in range(2 * n - 1)]
@@ -415,7 +371,7 @@ def emit_all():
             s.append(prog.emit(arr([("w", "w[%d]"), ("a", "a[%d]"), ("b", "b[%d]")])))
             s.append("}\n")
         # accumulate: acc has 2n+1 words
-        for nm, ns, off in (("e", 2 * n, 0), ("o", 2 * n - 1, 1), ("hi", n, n)):
+        for nm, ns, off in (("e", 2 * n, 0), ("hi", n, n)):
             for sub in (False, True):
                 dst = [f"d{i}" for i in range(off, 2 * n + 1)]
                 src = [f"s{i}" for i in range(ns)]
@@ -432,16 +388,6 @@ def emit_all():
         s.append("    uint32_t cy = 0; (void)cy;")
         s.append(prog.emit(arr([("w", "w[%d]"), ("v", "v[%d]")])))
         s.append("}\n")
-        # branch-free signed accumulate: acc += (w ^ m) + cin, sign extension `ext` above w
-        for nm, ns, off in (("e", 2 * n, 0), ("o", 2 * n - 1, 1)):
-            dst = [f"d{i}" for i in range(off, 2 * n + 1)]
-            src = [f"s{i}" for i in range(ns)]
-            prog = accm_prog(dst, src)
-            s.append(f"// acc[{off}..{2 * n}] += t[0..{ns - 1}] + cin, words above t += ext  (t = w ^ m, cin = m & 1, ext = m: acc +-= w)")
-            s.append(f"__device__ __forceinline__ void coop_accm_{nm}{n}(uint32_t* acc, const uint32_t* t, uint32_t cin, uint32_t ext) {{")
-            s.append("    uint32_t cy = cin;")
-            s.append(prog.emit(arr([("d", "acc[%d]"), ("s", "t[%d]")])))
-            s.append("}\n")
         # plain n-word add / sub (operand forms), returning nothing (no overflow by construction)
         for sub in (False, True):
             dst = [f"d{i}" for i in range(n)]
@@ -506,7 +452,6 @@ def main():
     for n in (8, 12):
         check_wmul(n)
     check_addsub()
-    check_accm()
     for n in (8, 12):
         check_merge(n)
     for cname, (n, p) in CURVES.items():
