@@ -255,7 +255,10 @@ def run_ours(args):
                          "peak_by_form_tprod_s": {k: v / 1e12 for k, v in peak_modes.items()},
                          "algorithmic_products_per_item": PRODUCTS_PAIRING,
                          "whole_step_frac": value / world * PRODUCTS_PER_VERIFY / peak,
-                         "traffic": None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of pairing_coop_kernel from the ncu --set full capture
+                         # of this command at n = 65,536 (profiles/summary_r01.md: 20.3 MB + 34.6 MB), scaled to n
+                         "traffic": {"dram_bytes_per_launch": int(54.9e6 * n / 65536), "source": "ncu --set full, profiles/summary_r01.md"},
+                         "algorithmic_bytes_per_launch": int(alg_bytes),
                          "hbm": {"achieved_gbs": alg_bytes / pairing_s / 1e9, "peak_gbs": hbm_peak,
                                  "frac": alg_bytes / pairing_s / 1e9 / hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
@@ -550,7 +553,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": f"BLS12-381-SHA-256 batch verify, L={args.L} messages of 32 B, one issuer key "
-                               f"(bounded sample of {args.cpu_sample} signatures per step of BASELINE configs[1])"},
+                               f"(bounded sample per step of BASELINE configs[1]: {last['sample'].split(':')[0]})"},
         "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
