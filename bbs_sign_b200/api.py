@@ -29,6 +29,7 @@ import numpy as np
 from . import _native
 
 ST_REJECT, ST_ACCEPT, ST_ERR_MSG_GEN_LEN, ST_ERR_DISCLOSED_INDEX, ST_ERR_IDX_MSG_LEN, ST_ERR_MALFORMED = range(6)
+ST_ERR_DISCLOSED_LEN, ST_ERR_RANDOM_LEN = 6, 7
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
@@ -238,6 +239,42 @@ class BatchContext:
         return sigs, b, st
 
     # ---- proof_verify.rs ----
+    def proof_gen_batch(self, signatures, messages: Sequence[Sequence[bytes]], disclosed_indexes: Sequence[Sequence[int]],
+                        random_scalars: Sequence[Sequence[bytes]], ph: bytes = b""):
+        """Batch form of `proof_gen` (proof_gen.rs:78-113) with caller-supplied random scalars (LE32 each, 5 + U per
+        item).  Returns (list of ProofBytes or None, status array)."""
+        n = len(messages)
+        n_msgs = len(messages[0]) if n else 0
+        flat, offs = _pack_ragged([m for ms in messages for m in ms])
+        sigs = _buf(b"".join(signatures))
+        idx = np.array([i for d in disclosed_indexes for i in d], dtype=np.uint32)
+        if idx.size == 0:
+            idx = np.zeros(1, np.uint32)
+        dis_off = np.zeros(n + 1, dtype=np.uint64)
+        rand_off = np.zeros(n + 1, dtype=np.uint64)
+        commit_off = np.zeros(n + 1, dtype=np.uint64)
+        if n:
+            dis_off[1:] = np.cumsum([len(d) for d in disclosed_indexes], dtype=np.uint64)
+            rand_off[1:] = np.cumsum([len(r) for r in random_scalars], dtype=np.uint64)
+            commit_off[1:] = np.cumsum([max(len(r) - 5, 0) for r in random_scalars], dtype=np.uint64)
+        rand = _buf(b"".join(s for r in random_scalars for s in r) or b"\0")
+        fixed = np.zeros(max(n, 1) * self.suite.proof_fixed_bytes, dtype=np.uint8)
+        commit = np.zeros(max(int(commit_off[n]), 1) * 32, dtype=np.uint8)
+        st = np.full(n, 255, dtype=np.uint8)
+        phb = _buf(ph) if ph else None
+        self._check(self.lib.bbs_proof_gen_batch(self._h, n, _ptr(sigs), _ptr(flat), _ptr(offs), n_msgs, _ptr(idx),
+                                                 _ptr(dis_off), _ptr(rand), _ptr(rand_off), _ptr(commit_off), _ptr(phb),
+                                                 len(ph), _ptr(fixed), _ptr(commit), _ptr(st)), "bbs_proof_gen_batch")
+        pf = self.suite.proof_fixed_bytes
+        out = []
+        for i in range(n):
+            if st[i] != ST_ACCEPT:
+                out.append(None)
+                continue
+            out.append(ProofBytes(fixed[i * pf:(i + 1) * pf].tobytes(),
+                                  commit[int(commit_off[i]) * 32:int(commit_off[i + 1]) * 32].tobytes()))
+        return out, st
+
     def _pack_proofs(self, proofs: Sequence["ProofBytes"], disclosed_indexes: Sequence[Sequence[int]]):
         n = len(proofs)
         fixed = np.frombuffer(b"".join(p.fixed for p in proofs), dtype=np.uint8) if n else np.zeros(1, np.uint8)

@@ -54,12 +54,13 @@ struct Ctx {
     bool coop = false;               // cooperative pairing kernel usable (BLS12-381, no degenerate line)
     CtxView view{};
     // grow-only scratch for the batch calls
+    DevBuf s_rand, s_rand_off;
     DevBuf s_gscr, s_rlc_pt, s_rlc_sc, s_rlc_parts, s_rlc_bad;
     DevBuf s_sigs, s_scalars, s_msgs, s_offsets, s_pair, s_flags, s_status, s_out, s_out2;
     DevBuf s_commit, s_commit_off, s_dis_idx, s_dis_scalars, s_dis_off, s_ph, s_dis_msgs, s_dis_msg_off;
     void release_all() {
         DevBuf* all[] = {&pk_comp, &gens_comp, &api_id, &header, &dst_h2s, &dst_map, &gens, &W, &K, &domain, &tab,
-                         &lines, &lines_coop, &s_gscr, &s_rlc_pt, &s_rlc_sc, &s_rlc_parts, &s_rlc_bad, &misc, &s_sigs, &s_scalars, &s_msgs, &s_offsets, &s_pair, &s_flags, &s_status, &s_out,
+                         &lines, &lines_coop, &s_rand, &s_rand_off, &s_gscr, &s_rlc_pt, &s_rlc_sc, &s_rlc_parts, &s_rlc_bad, &misc, &s_sigs, &s_scalars, &s_msgs, &s_offsets, &s_pair, &s_flags, &s_status, &s_out,
                          &s_out2, &s_commit, &s_commit_off, &s_dis_idx, &s_dis_scalars, &s_dis_off, &s_ph, &s_dis_msgs,
                          &s_dis_msg_off};
         for (DevBuf* b : all) b->release();
@@ -239,6 +240,56 @@ struct Impl {
         TRY(pairing_dev(c, n, d_status, s));
         PROF(c, 3, s);
         return BBS_OK;
+    }
+
+    // ---- core_proof_gen (proof_gen.rs:116-365) -----------------------------------------------------------
+    static int proof_gen_common(Ctx* c, size_t n, const uint8_t* sigs, uint32_t n_msgs, const uint32_t* idx,
+                                const uint64_t* dis_off, const uint8_t* rand, const uint64_t* rand_off,
+                                const uint64_t* commit_off, const uint8_t* ph, size_t ph_len, uint8_t* proofs_out,
+                                uint8_t* commitments_out, uint8_t* status) {
+        rt_stream_t s = c->stream;
+        TRY(stage(c->s_sigs, sigs, n * SIG, s));
+        TRY(stage(c->s_dis_idx, idx, dis_off[n] * 4, s));
+        TRY(stage(c->s_dis_off, dis_off, (n + 1) * 8, s));
+        TRY(stage(c->s_rand, rand, rand_off[n] * 32, s));
+        TRY(stage(c->s_rand_off, rand_off, (n + 1) * 8, s));
+        TRY(stage(c->s_commit_off, commit_off, (n + 1) * 8, s));
+        TRY(stage(c->s_ph, ph, ph_len, s));
+        TRY(c->s_out.reserve(n * PROOF));
+        TRY(c->s_commit.reserve(commit_off[n] * 32));
+        TRY(c->s_status.reserve(n));
+        TRY(rt_memset(c->s_out.p, 0, n * PROOF, s));
+        TRY(rt_memset(c->s_commit.p, 0, commit_off[n] * 32, s));
+        ProofGenArgs a{c->view, (const uint8_t*)c->s_sigs.p, (const uint8_t*)c->s_scalars.p, n_msgs,
+                       (const uint32_t*)c->s_dis_idx.p, (const uint64_t*)c->s_dis_off.p, (const uint8_t*)c->s_rand.p,
+                       (const uint64_t*)c->s_rand_off.p, (const uint64_t*)c->s_commit_off.p, (const uint8_t*)c->s_ph.p,
+                       (uint32_t)ph_len, (uint8_t*)c->s_out.p, (uint8_t*)c->s_commit.p, (uint8_t*)c->s_status.p};
+        TRY((launch_proof_gen<C>(a, (uint32_t)n, s)));
+        c->launches += n ? 1 : 0;
+        TRY(rt_d2h(proofs_out, c->s_out.p, n * PROOF, s));
+        TRY(rt_d2h(commitments_out, c->s_commit.p, commit_off[n] * 32, s));
+        return finish_status(c, n, status);
+    }
+    static int core_proof_gen(Ctx* c, size_t n, const uint8_t* sigs, const uint8_t* scalars, uint32_t n_msgs,
+                              const uint32_t* idx, const uint64_t* dis_off, const uint8_t* rand, const uint64_t* rand_off,
+                              const uint64_t* commit_off, const uint8_t* ph, size_t ph_len, uint8_t* proofs_out,
+                              uint8_t* commitments_out, uint8_t* status) {
+        TRY(stage(c->s_scalars, scalars, n * n_msgs * 32, c->stream));
+        return proof_gen_common(c, n, sigs, n_msgs, idx, dis_off, rand, rand_off, commit_off, ph, ph_len, proofs_out,
+                                commitments_out, status);
+    }
+    static int proof_gen(Ctx* c, size_t n, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off, uint32_t n_msgs,
+                         const uint32_t* idx, const uint64_t* dis_off, const uint8_t* rand, const uint64_t* rand_off,
+                         const uint64_t* commit_off, const uint8_t* ph, size_t ph_len, uint8_t* proofs_out,
+                         uint8_t* commitments_out, uint8_t* status) {
+        rt_stream_t s = c->stream;
+        const size_t count = n * n_msgs;
+        TRY(stage(c->s_msgs, msgs, off[count], s));
+        TRY(stage(c->s_offsets, off, (count + 1) * 8, s));
+        TRY(c->s_scalars.reserve(count * 32));
+        TRY(h2s_dev(c, count, (const uint8_t*)c->s_msgs.p, (const uint64_t*)c->s_offsets.p, (uint8_t*)c->s_scalars.p, s));
+        return proof_gen_common(c, n, sigs, n_msgs, idx, dis_off, rand, rand_off, commit_off, ph, ph_len, proofs_out,
+                                commitments_out, status);
     }
 
     // ---- random-linear-combination batch mode (rlc.cuh) ---------------------------------------------
@@ -549,6 +600,27 @@ int bbs_proof_verify_batch(bbs_ctx* p, size_t n, const uint8_t* proofs, const ui
     if (!n) return BBS_OK;
     if (!proofs || !commit_off || !dis_off || !dis_msg_off || !status) return arg_error("null");
     DISPATCH(c, proof_verify(c, n, proofs, commit, commit_off, idx, dis_msgs, dis_msg_off, dis_off, ph, ph_len, status));
+}
+
+int bbs_core_proof_gen_batch(bbs_ctx* p, size_t n, const uint8_t* sigs, const uint8_t* scalars, uint32_t n_msgs,
+                             const uint32_t* idx, const uint64_t* dis_off, const uint8_t* rand, const uint64_t* rand_off,
+                             const uint64_t* commit_off, const uint8_t* ph, size_t ph_len, uint8_t* proofs_out,
+                             uint8_t* commitments_out, uint8_t* status) {
+    Ctx* c = as_ctx(p);
+    if (!n) return BBS_OK;
+    if (!sigs || !dis_off || !rand || !rand_off || !commit_off || !proofs_out || !status) return arg_error("null");
+    DISPATCH(c, core_proof_gen(c, n, sigs, scalars, n_msgs, idx, dis_off, rand, rand_off, commit_off, ph, ph_len,
+                               proofs_out, commitments_out, status));
+}
+int bbs_proof_gen_batch(bbs_ctx* p, size_t n, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off, uint32_t n_msgs,
+                        const uint32_t* idx, const uint64_t* dis_off, const uint8_t* rand, const uint64_t* rand_off,
+                        const uint64_t* commit_off, const uint8_t* ph, size_t ph_len, uint8_t* proofs_out,
+                        uint8_t* commitments_out, uint8_t* status) {
+    Ctx* c = as_ctx(p);
+    if (!n) return BBS_OK;
+    if (!sigs || !off || !dis_off || !rand || !rand_off || !commit_off || !proofs_out || !status) return arg_error("null");
+    DISPATCH(c, proof_gen(c, n, sigs, msgs, off, n_msgs, idx, dis_off, rand, rand_off, commit_off, ph, ph_len, proofs_out,
+                          commitments_out, status));
 }
 
 // ---- random-linear-combination batch mode ----------------------------------------------------------------

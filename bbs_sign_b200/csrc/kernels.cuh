@@ -21,6 +21,8 @@ enum : uint8_t {
     ST_ERR_DISCLOSED_INDEX = 3,  // InvalidDisclosedIndex (proof_gen.rs:62-65)
     ST_ERR_IDX_MSG_LEN = 4,   // InvalidIndicesAndMessagesLength (proof_gen.rs:72-74)
     ST_ERR_MALFORMED = 5,     // undecodable point / non-canonical scalar / the reference's panic cases
+    ST_ERR_DISCLOSED_LEN = 6, // InvalidDisclosedIndicesLength (proof_gen.rs:139-141)
+    ST_ERR_RANDOM_LEN = 7,    // InvalidRandomScalarsAndUndisclosedIndicesLength (proof_gen.rs:232-234)
 };
 
 // Fixed-base tables: entry (g, w, d) = (d * 2^(BITS w)) * base_g in affine form, d = 1 .. 2^BITS - 1.
@@ -429,6 +431,174 @@ template <class C> BBS_HD void proof_g1_item(const ProofG1Args& a, uint32_t i) {
     if (pB == PT_INF) fl |= FL_SKIP1;
     a.flags[i] = fl;
 #undef PROOF_FAIL
+}
+
+// ---- core_proof_gen (proof_gen.rs:116-365: proof_init, proof_challenge_calculate, proof_finalize) ---------------
+// The reference draws its random scalars from the thread RNG (or the mocked stream with feature testvector_bls12_381);
+// here the caller supplies them (5 + U per item), which is what makes the output reproducible and comparable.
+struct ProofGenArgs {
+    CtxView ctx;
+    const uint8_t* sigs;           // n x (G1 compressed || LE32 e)
+    const uint8_t* scalars;        // n x n_msgs x LE32 message scalars (all messages)
+    uint32_t n_msgs;
+    const uint32_t* dis_idx;       // flat disclosed indexes
+    const uint64_t* dis_off;       // n+1
+    const uint8_t* rand;           // flat LE32 random scalars
+    const uint64_t* rand_off;      // n+1 (item i owns 5 + U_i scalars)
+    const uint64_t* commit_off;    // n+1: where item i's U_i commitments go in commitments_out
+    const uint8_t* ph; uint32_t ph_len;
+    uint8_t* proofs_out;           // n x (3 G1 compressed || LE32 e^, r1^, r3^, c)
+    uint8_t* commitments_out;      // flat LE32
+    uint8_t* status;
+};
+template <class C> BBS_HD void proof_gen_item(const ProofGenArgs& a, uint32_t i) {
+    using F = typename C::Fp;
+    using Fr = typename C::Fr;
+    const CtxView& cx = a.ctx;
+    constexpr int GB = C::G1_BYTES;
+    const uint64_t L = a.n_msgs;
+    const uint64_t db = a.dis_off[i], R = a.dis_off[i + 1] - db;
+    const uint64_t rb = a.rand_off[i], NR = a.rand_off[i + 1] - rb;
+    const uint64_t cb = a.commit_off[i], U = a.commit_off[i + 1] - cb;
+#define GEN_FAIL(code) { a.status[i] = (code); return; }
+    if (R > L) GEN_FAIL(ST_ERR_DISCLOSED_LEN)                                   // proof_gen.rs:139-141
+    uint32_t mask[MAX_L / 32];
+    for (int k = 0; k < MAX_L / 32; k++) mask[k] = 0;
+    uint64_t distinct = 0;
+    for (uint64_t k = 0; k < R; k++) {
+        uint32_t idx = a.dis_idx[db + k];
+        if (idx >= L) GEN_FAIL(ST_ERR_DISCLOSED_INDEX)                          // :143-147
+        if (!((mask[idx >> 5] >> (idx & 31)) & 1)) { mask[idx >> 5] |= 1u << (idx & 31); distinct++; }
+    }
+    if (L != cx.L) GEN_FAIL(ST_ERR_MSG_GEN_LEN)                                 // :228-230
+    // the reference de-duplicates the disclosed set (:154-158); its scalar count check is :232-234
+    if (NR != (L - distinct) + 5 || U != L - distinct) GEN_FAIL(ST_ERR_RANDOM_LEN)
+    const uint8_t* sig = a.sigs + (size_t)i * (GB + 32);
+    const uint8_t* sc = a.scalars + (size_t)i * L * 32;
+    uint32_t A[G1A], e[8], rs[5][8];
+    int pa = g1_decompress<C>(A, sig);
+    bool ok = pa != PT_BAD && fr_from_le32<C>(e, sig + GB);
+    for (int k = 0; k < 5 && ok; k++) ok = fr_from_le32<C>(rs[k], a.rand + (rb + k) * 32);
+    if (!ok) GEN_FAIL(ST_ERR_MALFORMED)
+    // B = P1 + Q1*domain + sum H_j m_j   (:247-253)
+    uint32_t B[G1J];
+    if (cx.k_inf) g1_set_inf<C>(B); else g1_from_affine<C>(B, cx.K);
+    for (uint32_t j = 0; j < (uint32_t)L; j++) {
+        uint32_t m[8];
+        if (!fr_from_le32<C>(m, sc + j * 32)) GEN_FAIL(ST_ERR_MALFORMED)
+        tab_accumulate<C>(B, cx.tab, j + 1, m);
+    }
+    // D = B r1 ; Abar = A (r0 r1)   (:254-255)
+    uint32_t r0m[8], r01[8], Baff[G1A], Dj[G1J], Abj[G1J];
+    fe_to_mont<Fr>(r0m, rs[0]);
+    fe_mul<Fr>(r01, r0m, rs[1]);                               // r0 r1, canonical
+    bool bfin = g1_to_affine<C>(Baff, B);
+    if (bfin) g1_mul_scalar<C>(Dj, Baff, rs[1]); else g1_set_inf<C>(Dj);
+    if (pa == PT_OK) g1_mul_scalar<C>(Abj, A, r01); else g1_set_inf<C>(Abj);
+    // normalise D and Abar with one inversion (they are multiplied again and serialised)
+    uint32_t Daff[G1A], Abaff[G1A];
+    bool dfin = !g1_is_inf<C>(Dj), afin = !g1_is_inf<C>(Abj);
+    {
+        uint32_t z1[FPN], z2[FPN], zz[FPN], t[FPN];
+        if (dfin) bn_copy<C::Fp::N>(z1, Dj + 2 * FPN); else fe_set_one<F>(z1);
+        if (afin) bn_copy<C::Fp::N>(z2, Abj + 2 * FPN); else fe_set_one<F>(z2);
+        fe_mul<F>(zz, z1, z2); fe_inv<F>(zz, zz);
+        fe_mul<F>(t, zz, z2);                                   // 1/z1
+        fe_mul<F>(zz, zz, z1);                                  // 1/z2
+        fe_sqr<F>(z1, t); fe_mul<F>(Daff, Dj, z1); fe_mul<F>(z1, z1, t); fe_mul<F>(Daff + FPN, Dj + FPN, z1);
+        fe_sqr<F>(z2, zz); fe_mul<F>(Abaff, Abj, z2); fe_mul<F>(z2, z2, zz); fe_mul<F>(Abaff + FPN, Abj + FPN, z2);
+    }
+    // Bbar = D r0 - Abar e ; T1 = Abar r2 + D r3   (:256-257)
+    uint32_t ne[8], Bbj[G1J], T1[G1J], T2[G1J];
+    fe_neg<Fr>(ne, e);
+    const uint32_t* pts[2] = {dfin ? Daff : nullptr, afin ? Abaff : nullptr};
+    {
+        const uint32_t* ks[2] = {rs[0], ne};
+        g1_msm_scalar<C, 2>(Bbj, pts, ks);
+        const uint32_t* kt[2] = {rs[3], rs[2]};
+        g1_msm_scalar<C, 2>(T1, pts, kt);
+    }
+    // T2 = D r4 + sum_{undisclosed} H_j r_{5+k}   (:258-263)
+    if (dfin) g1_mul_scalar<C>(T2, Daff, rs[4]); else g1_set_inf<C>(T2);
+    {
+        uint64_t k = 0;
+        for (uint32_t j = 0; j < (uint32_t)L; j++) {
+            if ((mask[j >> 5] >> (j & 31)) & 1) continue;
+            uint32_t m[8];
+            if (!fr_from_le32<C>(m, a.rand + (rb + 5 + k) * 32)) GEN_FAIL(ST_ERR_MALFORMED)
+            tab_accumulate<C>(T2, cx.tab, j + 1, m);
+            k++;
+        }
+    }
+    // serialise Bbar, T1, T2 with one shared inversion
+    uint8_t* out = a.proofs_out + (size_t)i * (3 * GB + 128);
+    uint8_t encT1[GB], encT2[GB];
+    {
+        uint32_t* P[3] = {Bbj, T1, T2};
+        bool inf[3];
+        uint32_t z[3][FPN], pre[3][FPN], inv[FPN], t[FPN], aff[G1A];
+        for (int k = 0; k < 3; k++) {
+            inf[k] = g1_is_inf<C>(P[k]);
+            if (inf[k]) fe_set_one<F>(z[k]); else bn_copy<C::Fp::N>(z[k], P[k] + 2 * FPN);
+        }
+        bn_copy<C::Fp::N>(pre[0], z[0]);
+        fe_mul<F>(pre[1], pre[0], z[1]);
+        fe_mul<F>(pre[2], pre[1], z[2]);
+        fe_inv<F>(inv, pre[2]);
+        for (int k = 2; k >= 0; k--) {
+            uint32_t zi[FPN], zi2[FPN];
+            if (k > 0) { fe_mul<F>(zi, inv, pre[k - 1]); fe_mul<F>(t, inv, z[k]); bn_copy<C::Fp::N>(inv, t); }
+            else bn_copy<C::Fp::N>(zi, inv);
+            fe_sqr<F>(zi2, zi); fe_mul<F>(aff, P[k], zi2); fe_mul<F>(zi2, zi2, zi); fe_mul<F>(aff + FPN, P[k] + FPN, zi2);
+            uint8_t* dst = k == 0 ? out + GB : (k == 1 ? encT1 : encT2);
+            g1_compress_affine<C>(dst, aff, inf[k]);
+        }
+    }
+    g1_compress_affine<C>(out, Abaff, !afin);
+    g1_compress_affine<C>(out + 2 * GB, Daff, !dfin);
+    // challenge (:272-328): disclosed indexes sorted and de-duplicated (:154-158), messages looked up by index (:186-189)
+    Xmd48 x;
+    x.begin();
+    x.s.put_be64(distinct);
+    for (uint32_t j = 0; j < (uint32_t)L; j++) {
+        if (!((mask[j >> 5] >> (j & 31)) & 1)) continue;
+        uint32_t m[8];
+        x.s.put_be64(j);
+        limbs_from_le<8>(m, sc + j * 32);
+        for (int q = 7; q >= 0; q--) x.s.update_words(&m[q], 1);
+    }
+    x.s.update(out, 3 * GB);
+    x.s.update(encT1, GB);
+    x.s.update(encT2, GB);
+    for (int q = 7; q >= 0; q--) x.s.update_words(&cx.domain[q], 1);
+    x.s.put_be64(a.ph_len);
+    x.s.update(a.ph, a.ph_len);
+    uint32_t okm[12], c[8], cm[8];
+    x.finish(cx.dst_h2s, cx.dst_h2s_len, okm);
+    okm48_to_scalar<Fr>(c, okm);
+    fe_to_mont<Fr>(cm, c);
+    // proof_finalize (:331-365)
+    uint32_t r1m[8], r3[8], t[8], v[8];
+    if (bn_is_zero<8>(rs[1])) GEN_FAIL(ST_ERR_MALFORMED)                       // :347 `inverse().unwrap()` panics
+    fe_to_mont<Fr>(r1m, rs[1]); fe_inv<Fr>(r1m, r1m); fe_from_mont<Fr>(r3, r1m);
+    fe_mul<Fr>(t, cm, e); fe_add<Fr>(v, rs[2], t); limbs_to_le<8>(out + 3 * GB, v);             // e^ = r2 + e c
+    fe_mul<Fr>(t, cm, rs[0]); fe_sub<Fr>(v, rs[3], t); limbs_to_le<8>(out + 3 * GB + 32, v);     // r1^ = r3 - r0 c
+    fe_mul<Fr>(t, cm, r3); fe_sub<Fr>(v, rs[4], t); limbs_to_le<8>(out + 3 * GB + 64, v);        // r3^ = r4 - c / r1
+    limbs_to_le<8>(out + 3 * GB + 96, c);
+    {
+        uint64_t k = 0;
+        for (uint32_t j = 0; j < (uint32_t)L; j++) {
+            if ((mask[j >> 5] >> (j & 31)) & 1) continue;
+            uint32_t m[8], rk[8];
+            limbs_from_le<8>(m, sc + j * 32);
+            limbs_from_le<8>(rk, a.rand + (rb + 5 + k) * 32);
+            fe_mul<Fr>(t, cm, m); fe_add<Fr>(v, rk, t);                                          // m^ = r_{5+k} + m c
+            limbs_to_le<8>(a.commitments_out + (cb + k) * 32, v);
+            k++;
+        }
+    }
+    a.status[i] = ST_ACCEPT;
+#undef GEN_FAIL
 }
 
 }  // namespace bbs

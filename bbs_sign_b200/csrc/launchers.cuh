@@ -28,6 +28,7 @@ size_t coop_gscratch_bytes_bls(size_t n);
 #endif
 template <class C> int launch_sign(const SignArgs& a, uint32_t n, rt_stream_t s);
 template <class C> int launch_proof_g1(const ProofG1Args& a, uint32_t n, rt_stream_t s);
+template <class C> int launch_proof_gen(const ProofGenArgs& a, uint32_t n, rt_stream_t s);
 template <class C> int launch_field_test(const FieldTestArgs& a, uint32_t n, rt_stream_t s);
 template <class C> int launch_g1_mul_test(const G1MulTestArgs& a, uint32_t n, rt_stream_t s);
 template <class C> int launch_pair_test_prep(const PairTestPrepArgs& a, uint32_t n, rt_stream_t s);

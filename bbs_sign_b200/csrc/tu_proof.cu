@@ -16,10 +16,16 @@ template <class C> int launch_proof_g1(const ProofG1Args& a, uint32_t n, rt_stre
     return rt_launch<ProofG1Args, &proof_g1_item<C>, BBS_PROOF_G1_TPB, BBS_PROOF_G1_MINB>(a, n, s);
 }
 
+template <class C> int launch_proof_gen(const ProofGenArgs& a, uint32_t n, rt_stream_t s) {
+    return rt_launch<ProofGenArgs, &proof_gen_item<C>, BBS_PROOF_G1_TPB, BBS_PROOF_G1_MINB>(a, n, s);
+}
+
 #if defined(BBS_TU_BLS) || !defined(BBS_TU_BN)
+template int launch_proof_gen<Bls>(const ProofGenArgs&, uint32_t, rt_stream_t);
 template int launch_proof_g1<Bls>(const ProofG1Args&, uint32_t, rt_stream_t);
 #endif
 #if defined(BBS_TU_BN) || !defined(BBS_TU_BLS)
+template int launch_proof_gen<Bn>(const ProofGenArgs&, uint32_t, rt_stream_t);
 template int launch_proof_g1<Bn>(const ProofG1Args&, uint32_t, rt_stream_t);
 #endif
 

@@ -49,6 +49,9 @@ typedef struct bbs_ctx bbs_ctx;
                                         panics (duplicate disclosed index src/proof_verify.rs:179; sk+e == 0
                                         src/sign.rs:129) */
 
+#define BBS_ST_ERR_DISCLOSED_LEN 6   /* Err(InvalidDisclosedIndicesLength)      src/proof_gen.rs:139-141 */
+#define BBS_ST_ERR_RANDOM_LEN 7      /* Err(InvalidRandomScalarsAndUndisclosedIndicesLength)  src/proof_gen.rs:232-234 */
+
 #define BBS_MAX_MESSAGES 256
 
 /* Sizes of the encodings for a curve (bytes). */
@@ -122,6 +125,31 @@ int bbs_proof_verify_batch(bbs_ctx* ctx, size_t n, const uint8_t* proofs_fixed, 
                            const uint64_t* commit_off, const uint32_t* disclosed_idx, const uint8_t* dis_msgs,
                            const uint64_t* dis_msg_off, const uint64_t* dis_off, const uint8_t* ph, size_t ph_len,
                            uint8_t* status);
+
+/* core_proof_gen (src/proof_gen.rs:116-365: proof_init, proof_challenge_calculate, proof_finalize) for n signatures.
+ *   sigs, msg_scalars : as bbs_core_verify_batch (ALL n_msgs message scalars of every item)
+ *   disclosed_idx     : flat indexes, item i discloses disclosed_idx[dis_off[i] .. dis_off[i+1]) (duplicates are
+ *                       de-duplicated and the set is sorted, as the reference does, :154-158)
+ *   random_scalars    : flat LE32; item i owns random_scalars[rand_off[i] .. rand_off[i+1]) = 5 + U_i scalars in the
+ *                       order of proof_init (:254-263).  The reference draws them from the thread RNG
+ *                       (`calculate_random_scalars`) or the mocked stream (feature testvector_bls12_381); here the
+ *                       caller supplies them, so a proof is a deterministic function of its inputs.
+ *   commit_off        : n+1 offsets (in scalars) into commitments_out; U_i = commit_off[i+1] - commit_off[i] must be
+ *                       n_msgs - |disclosed set|
+ *   outputs           : proofs_fixed_out = n x Proof-fixed encoding, commitments_out = flat LE32 (the two halves of
+ *                       ark's serialisation of Proof, the format bbs_proof_verify_batch consumes)
+ * status[i] in {ACCEPT (= Ok(proof)), ERR_DISCLOSED_LEN, ERR_DISCLOSED_INDEX, ERR_MSG_GEN_LEN, ERR_RANDOM_LEN,
+ *               ERR_MALFORMED}. */
+int bbs_core_proof_gen_batch(bbs_ctx* ctx, size_t n, const uint8_t* sigs, const uint8_t* msg_scalars, uint32_t n_msgs,
+                             const uint32_t* disclosed_idx, const uint64_t* dis_off, const uint8_t* random_scalars,
+                             const uint64_t* rand_off, const uint64_t* commit_off, const uint8_t* ph, size_t ph_len,
+                             uint8_t* proofs_fixed_out, uint8_t* commitments_out, uint8_t* status);
+/* proof_gen (src/proof_gen.rs:78-113): byte messages, layout as bbs_verify_batch. */
+int bbs_proof_gen_batch(bbs_ctx* ctx, size_t n, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* offsets,
+                        uint32_t n_msgs, const uint32_t* disclosed_idx, const uint64_t* dis_off,
+                        const uint8_t* random_scalars, const uint64_t* rand_off, const uint64_t* commit_off,
+                        const uint8_t* ph, size_t ph_len, uint8_t* proofs_fixed_out, uint8_t* commitments_out,
+                        uint8_t* status);
 
 /* ---- random-linear-combination batch mode (the optional mode of the north star; not in the reference) ----------
  * One verdict for n signatures under the context's issuer key:

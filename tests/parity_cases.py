@@ -156,6 +156,12 @@ def case_irtf_kat(lib_path):
     pb = A.ProofBytes.from_canonical(suite, O.proof_to_bytes(ocs, proof))
     assert ctx.proof_verify_batch([pb], PH, [[MSG]], [[0]]).tolist() == [1]
     assert ctx.proof_verify_batch([pb], b"", [[MSG]], [[0]]).tolist() == [0]
+    # ... and produced by the library itself from the mocked random scalars (core_utilities.rs:84-113, the stream the
+    # reference uses under feature testvector_bls12_381): byte-identical to the IRTF proof fixture
+    rs = [ocs.scalar_le(x) for x in O.mocked_calculate_random_scalars(ocs, 5)]
+    gen, gst = ctx.proof_gen_batch([sigs[0].tobytes()], [[MSG]], [[0]], [rs], PH)
+    assert gst.tolist() == [1]
+    assert gen[0].fixed == pb.fixed and gen[0].commitments == pb.commitments
     ctx.close()
 
 
@@ -396,4 +402,45 @@ def case_rlc(lib_path, curve_name, L=3, n=9):
     mal = list(enc)
     mal[2] = b"\xff" * len(mal[2])
     assert ctx.rlc_verify_batch(mal, msgs, seed) == A.ST_ERR_MALFORMED
+    ctx.close()
+
+
+def case_proof_gen(lib_path, curve_name, L, disclosed, n=5, header=b"hg", ph=b"ph-gen"):
+    """core_proof_gen / proof_gen (proof_gen.rs:78-365) with caller-supplied random scalars: byte-identical proofs
+    to the oracle's, which the library then verifies; plus the Err(..) classes of proof_gen.rs:139-147, :228-234."""
+    suite, ocs = SUITES[curve_name]
+    sk, pk = keypair(ocs, 1)
+    ctx, gens = make_ctx(lib_path, suite, ocs, pk, header, L)
+    U = L - len(set(disclosed))
+    msgs = [[rng_bytes(f"g{i}.{j}", 32) for j in range(L)] for i in range(n)]
+    sigs = [O.sign(ocs, sk, m, header) for m in msgs]
+    if n > 2:
+        sigs[2] = (None, sigs[2][1])              # identity A: the reference still produces a (useless) proof
+    rss = [O.seeded_random_scalars(ocs, f"gen{i}".encode(), b"rs-dst", 5 + U) for i in range(n)]
+    enc = [O.signature_to_bytes(ocs, s) for s in sigs]
+    got, st = ctx.proof_gen_batch(enc, msgs, [list(disclosed)] * n, [[ocs.scalar_le(x) for x in rs] for rs in rss], ph)
+    assert st.tolist() == [1] * n, st.tolist()
+    dis = sorted(set(disclosed))
+    for i in range(n):
+        want = O.proof_gen(ocs, pk, sigs[i], header, ph, msgs[i], list(disclosed), random_scalars=rss[i])
+        wb = A.ProofBytes.from_canonical(suite, O.proof_to_bytes(ocs, want))
+        assert got[i].fixed == wb.fixed, (curve_name, i, "fixed part differs")
+        assert got[i].commitments == wb.commitments, (curve_name, i, "commitments differ")
+    ver = ctx.proof_verify_batch(got, ph, [[m[j] for j in dis] for m in msgs], [dis] * n)
+    assert ver.tolist() == [0 if (i == 2 and n > 2) else 1 for i in range(n)], ver.tolist()
+    # error classes
+    one = [enc[0]]
+    rs_ok = [[ocs.scalar_le(x) for x in rss[0]]]
+    if L >= 1:
+        _, st = ctx.proof_gen_batch(one, [msgs[0]], [[L]], [[ocs.scalar_le(1)] * (5 + L - 1)], ph)
+        assert st.tolist() == [A.ST_ERR_DISCLOSED_INDEX]
+        _, st = ctx.proof_gen_batch(one, [msgs[0]], [list(range(L)) + [0]], [[ocs.scalar_le(1)] * 5], ph)
+        assert st.tolist() == [A.ST_ERR_DISCLOSED_LEN]
+    _, st = ctx.proof_gen_batch(one, [msgs[0]], [list(disclosed)], [rs_ok[0] + [ocs.scalar_le(7)]], ph)
+    assert st.tolist() == [A.ST_ERR_RANDOM_LEN]
+    if L >= 2:
+        # a duplicated disclosed index: the reference de-duplicates the set but sizes the random scalars by the raw
+        # list, so proof_init refuses (proof_gen.rs:232-234)
+        _, st = ctx.proof_gen_batch(one, [msgs[0]], [[0, 0]], [[ocs.scalar_le(3)] * (5 + L - 2)], ph)
+        assert st.tolist() == [A.ST_ERR_RANDOM_LEN]
     ctx.close()

@@ -90,3 +90,9 @@ def test_large_batch_consistency(lib):
 @pytest.mark.parametrize("curve,L", [("BLS12_381", 3), ("BN254", 2), ("BLS12_381", 0)])
 def test_rlc(lib, curve, L):
     P.case_rlc(None, curve, L=L, n=9)
+
+
+@pytest.mark.parametrize("curve,L,dis", [("BLS12_381", 5, [0, 2, 3]), ("BN254", 3, [1]), ("BLS12_381", 2, []),
+                                         ("BLS12_381", 3, [0, 1, 2]), ("BLS12_381", 0, [])])
+def test_proof_gen(lib, curve, L, dis):
+    P.case_proof_gen(None, curve, L, dis, n=5)
