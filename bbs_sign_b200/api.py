@@ -187,7 +187,6 @@ class BatchContext:
         self._check(self.lib.bbs_verify_batch(self._h, n, _ptr(sigs), _ptr(flat), _ptr(offs), n_msgs, _ptr(st)), "bbs_verify_batch")
         return st
 
-    # ---- sign.rs ----
     # ---- random-linear-combination batch mode (not in the reference; include/bbs_b200.h) -------------------
     def rlc_partial(self, signatures, messages: Sequence[Sequence[bytes]], seed: bytes, index_base: int = 0):
         """This shard's two partial G1 points (compressed) and a status byte (ACCEPT = well-formed shard)."""
@@ -212,6 +211,7 @@ class BatchContext:
         parts, st = self.rlc_partial(signatures, messages, seed, 0)
         return st if st != ST_ACCEPT else self.rlc_combine([parts])
 
+    # ---- sign.rs ----
     def core_sign_batch(self, sk_le32: bytes, msg_scalars, n: int, n_msgs: int, want_b: bool = False):
         sc = _buf(msg_scalars)
         if sc.size != n * n_msgs * 32:

@@ -444,3 +444,20 @@ def case_proof_gen(lib_path, curve_name, L, disclosed, n=5, header=b"hg", ph=b"p
         _, st = ctx.proof_gen_batch(one, [msgs[0]], [[0, 0]], [[ocs.scalar_le(3)] * (5 + L - 2)], ph)
         assert st.tolist() == [A.ST_ERR_RANDOM_LEN]
     ctx.close()
+
+
+def case_h2s_ragged(lib_path, curve_name):
+    """msg_to_scalars (interface_utilities.rs:76-88) over ragged message lengths around every SHA-256 padding boundary
+    of expand_message_xmd's first block chain, and an empty batch."""
+    suite, ocs = SUITES[curve_name]
+    sk, pk = keypair(ocs, 1)
+    ctx, gens = make_ctx(lib_path, suite, ocs, pk, b"", 1)
+    lens = [0, 1, 2, 31, 32, 33, 54, 55, 56, 57, 63, 64, 65, 118, 119, 120, 121, 127, 128, 129, 255, 256, 1000, 4099]
+    msgs = [rng_bytes(f"ragged{n}", n) for n in lens]
+    got = ctx.msg_to_scalars(msgs)
+    want = O.msg_to_scalars(ocs, msgs, ocs.api_id)
+    for i, n in enumerate(lens):
+        assert got[i].tobytes() == ocs.scalar_le(want[i]), (curve_name, n)
+    assert len(ctx.msg_to_scalars([])) == 0
+    assert ctx.verify_batch(b"", []).tolist() == []
+    ctx.close()

@@ -96,3 +96,8 @@ def test_rlc(lib, curve, L):
                                          ("BLS12_381", 3, [0, 1, 2]), ("BLS12_381", 0, [])])
 def test_proof_gen(lib, curve, L, dis):
     P.case_proof_gen(None, curve, L, dis, n=5)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_h2s_ragged(lib, curve):
+    P.case_h2s_ragged(None, curve)

@@ -61,3 +61,8 @@ def test_proof_errors(lib_path, curve):
 @pytest.mark.parametrize("curve,L,dis", [("BLS12_381", 3, [0, 2]), ("BN254", 2, [1])])
 def test_proof_gen(lib_path, curve, L, dis):
     P.case_proof_gen(lib_path, curve, L, dis, n=3)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_h2s_ragged(lib_path, curve):
+    P.case_h2s_ragged(lib_path, curve)
