@@ -461,3 +461,27 @@ def case_h2s_ragged(lib_path, curve_name):
     assert len(ctx.msg_to_scalars([])) == 0
     assert ctx.verify_batch(b"", []).tolist() == []
     ctx.close()
+
+
+def case_readme_example(lib_path, curve_name):
+    """The reference's README example (README.md:64-130, BASELINE configs[0]): key_material = [5; 32], four messages,
+    sign -> verify -> proof_gen with {0, 2} disclosed -> proof_verify, as batches of one through the library, every
+    byte compared with the oracle."""
+    suite, ocs = SUITES[curve_name]
+    sk = O.key_gen(ocs, bytes([5] * 32), b"", b"BBS-SIG-KEYGEN-SALT-")
+    pk = O.sk_to_pk(ocs, sk)
+    msgs = [b"message1", b"message2", b"msg3", b"msg4"]
+    ctx, gens = make_ctx(lib_path, suite, ocs, pk, b"", len(msgs))
+    sigs, _, st = ctx.sign_batch(ocs.scalar_le(sk), [msgs])
+    assert st.tolist() == [1]
+    want_sig = O.sign(ocs, sk, msgs, b"")
+    assert sigs[0].tobytes() == O.signature_to_bytes(ocs, want_sig)
+    assert ctx.verify_batch(sigs, [msgs]).tolist() == [1]
+    rs = O.seeded_random_scalars(ocs, b"readme", b"rs-dst", 5 + 2)
+    got, st = ctx.proof_gen_batch([sigs[0].tobytes()], [msgs], [[0, 2]], [[ocs.scalar_le(x) for x in rs]], b"")
+    assert st.tolist() == [1]
+    want = A.ProofBytes.from_canonical(suite, O.proof_to_bytes(ocs, O.proof_gen(ocs, pk, want_sig, b"", b"", msgs, [0, 2], random_scalars=rs)))
+    assert got[0].fixed == want.fixed and got[0].commitments == want.commitments
+    assert ctx.proof_verify_batch(got, b"", [[msgs[0], msgs[2]]], [[0, 2]]).tolist() == [1]
+    assert ctx.proof_verify_batch(got, b"", [[msgs[0], msgs[3]]], [[0, 2]]).tolist() == [0]
+    ctx.close()

@@ -101,3 +101,8 @@ def test_proof_gen(lib, curve, L, dis):
 @pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
 def test_h2s_ragged(lib, curve):
     P.case_h2s_ragged(None, curve)
+
+
+@pytest.mark.parametrize("curve", ["BN254", "BLS12_381"])
+def test_readme_example(lib, curve):
+    P.case_readme_example(None, curve)

@@ -66,3 +66,8 @@ def test_proof_gen(lib_path, curve, L, dis):
 @pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
 def test_h2s_ragged(lib_path, curve):
     P.case_h2s_ragged(lib_path, curve)
+
+
+@pytest.mark.parametrize("curve", ["BN254", "BLS12_381"])
+def test_readme_example(lib_path, curve):
+    P.case_readme_example(lib_path, curve)
