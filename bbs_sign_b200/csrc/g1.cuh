@@ -11,6 +11,14 @@ namespace bbs {
 #define G1J (3 * C::Fp::N)
 
 template <class C> BBS_HD bool g1_is_inf(const uint32_t* p) { return bn_is_zero<C::Fp::N>(p + 2 * FPN); }
+// out-of-line identity test for points that were just written through pointers by other out-of-line functions: cicc 12.9
+// has folded such comparisons when they were inlined into the caller (field.cuh, BBS_OPAQUE_CALL_BARRIER)
+template <class C> BBS_HDN bool g1_is_inf_ool(const uint32_t* p) {
+    BBS_OPAQUE_CALL_BARRIER();
+    bool r = bn_is_zero<C::Fp::N>(p + 2 * FPN);
+    BBS_OPAQUE_CALL_BARRIER();
+    return r;
+}
 template <class C> BBS_HD void g1_set_inf(uint32_t* p) {
     fe_set_one<typename C::Fp>(p); fe_set_one<typename C::Fp>(p + FPN); bn_zero<C::Fp::N>(p + 2 * FPN);
 }

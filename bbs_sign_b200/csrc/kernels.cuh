@@ -219,12 +219,13 @@ struct VerifyG1Args {
     uint32_t n_msgs;
     uint32_t* pair; uint32_t* flags; uint8_t* status;
 };
-template <class C> BBS_HD void verify_g1_item(const VerifyG1Args& a, uint32_t i) {
+// Part 1: everything up to the Jacobian point Cc = e A - B.  Returns false when the item's status is already final.
+template <class C> BBS_HD bool verify_g1_head(const VerifyG1Args& a, uint32_t i, uint32_t* Cc, int& pa) {
     const CtxView& cx = a.ctx;
-    if (a.n_msgs != cx.L) { a.status[i] = ST_ERR_MSG_GEN_LEN; a.flags[i] = FL_DONE; return; }   // verify.rs:68-71
+    if (a.n_msgs != cx.L) { a.status[i] = ST_ERR_MSG_GEN_LEN; a.flags[i] = FL_DONE; return false; }   // verify.rs:68-71
     const uint8_t* sig = a.sigs + (size_t)i * (C::G1_BYTES + 32);
     uint32_t A[G1A], e[8];
-    int pa = g1_decompress<C>(A, sig);
+    pa = g1_decompress<C>(A, sig);
     bool ok = pa != PT_BAD && fr_from_le32<C>(e, sig + C::G1_BYTES);
     // B = P1 + Q1*domain + sum H_j m_j  (verify.rs:81-86), K = P1 + Q1*domain hoisted into the context
     uint32_t B[G1J];
@@ -235,27 +236,101 @@ template <class C> BBS_HD void verify_g1_item(const VerifyG1Args& a, uint32_t i)
         ok = fr_from_le32<C>(m, sc + j * 32);
         if (ok) tab_accumulate<C>(B, cx.tab, j + 1, m);
     }
-    if (!ok) { a.status[i] = ST_ERR_MALFORMED; a.flags[i] = FL_DONE; return; }
+    if (!ok) { a.status[i] = ST_ERR_MALFORMED; a.flags[i] = FL_DONE; return false; }
     // e(A, W + e BP2) e(B, -BP2) == 1  <=>  e(A, W) e(eA - B, BP2) == 1   (SURVEY 8a note (i))
-    uint32_t Cc[G1J];
     g1_neg<C>(Cc, B);
     if (pa == PT_OK) {
         uint32_t eA[G1J];
         g1_mul_scalar<C>(eA, A, e);
         g1_add<C>(Cc, Cc, eA);
     }
-    // both pairing arguments leave this kernel affine: (x, y, 1).  The cooperative pairing kernel normalises its
-    // lines to constant term 1, which needs Z = 1 (pairing_coop.cuh); the per-thread kernel accepts it as (XZ, Y, Z^3).
+    // first pairing argument: A itself (affine)
     uint32_t* pr = a.pair + (size_t)i * PAIR_WORDS;
     bn_copy<2 * C::Fp::N>(pr, A); fe_set_one<typename C::Fp>(pr + 2 * FPN);
-    uint32_t caff[G1A];
-    bool cfin = g1_to_affine<C>(caff, Cc);
-    bn_copy<2 * C::Fp::N>(pr + 3 * FPN, caff); fe_set_one<typename C::Fp>(pr + 5 * FPN);
+    return true;
+}
+// Part 2: both pairing arguments leave the kernel affine, (x, y, 1): the cooperative pairing kernel normalises its
+// lines to constant term 1, which needs Z = 1 (pairing_coop.cuh).  zinv = 1 / Z of Cc (unused for the identity).
+template <class C> BBS_HD void verify_g1_tail(const VerifyG1Args& a, uint32_t i, const uint32_t* Cc, const uint32_t* zinv, int pa) {
+    using F = typename C::Fp;
+    uint32_t* pr = a.pair + (size_t)i * PAIR_WORDS;
+    const bool cfin = !g1_is_inf_ool<C>(Cc);
+    if (cfin) {
+        uint32_t zi2[FPN];
+        fe_sqr<F>(zi2, zinv);
+        fe_mul<F>(pr + 3 * FPN, Cc, zi2);
+        fe_mul<F>(zi2, zi2, zinv);
+        fe_mul<F>(pr + 4 * FPN, Cc + FPN, zi2);
+    } else {
+        bn_zero<2 * C::Fp::N>(pr + 3 * FPN);
+    }
+    fe_set_one<F>(pr + 5 * FPN);
     uint32_t fl = 0;
-    if (pa == PT_INF || cx.w_inf) fl |= FL_SKIP0;
+    if (pa == PT_INF || a.ctx.w_inf) fl |= FL_SKIP0;
     if (!cfin) fl |= FL_SKIP1;
     a.flags[i] = fl;
 }
+// one item, its own inversion (host simulation; the CUDA build uses verify_g1_kernel below)
+template <class C> BBS_HD void verify_g1_item(const VerifyG1Args& a, uint32_t i) {
+    uint32_t Cc[G1J], zinv[FPN];
+    int pa = PT_BAD;
+    if (!verify_g1_head<C>(a, i, Cc, pa)) return;
+    if (!g1_is_inf_ool<C>(Cc)) fe_inv<typename C::Fp>(zinv, Cc + 2 * FPN);
+    verify_g1_tail<C>(a, i, Cc, zinv, pa);
+}
+
+#if defined(__CUDACC__) && !defined(BBS_HOSTSIM)
+// Block-wide simultaneous inversion (Montgomery's trick as a product tree in shared memory): one Fermat inversion per
+// block instead of one per thread.  On a SIMT machine an inversion costs the warp the same whether one lane or all
+// 32 need it, so the saving comes from the other warps of the block: 7 of 8 skip their ~490 multiplications and pay
+// ~25 for the tree instead.  z must be non-zero in every thread (pass 1 for items without a point); TPB a power of 2.
+template <class F, int TPB> __device__ __forceinline__ void block_batch_inverse(uint32_t* z, uint32_t (*tree)[F::N]) {
+    constexpr int N = F::N;
+    const int t = threadIdx.x;
+    // leaves at tree[TPB + t], node k = product of its children 2k, 2k+1, root at tree[1]
+    bn_copy<N>(tree[TPB + t], z);
+    __syncthreads();
+    for (int w = TPB / 2; w >= 1; w >>= 1) {
+        if (t < w) fe_mul<F>(tree[w + t], tree[2 * (w + t)], tree[2 * (w + t) + 1]);
+        __syncthreads();
+    }
+    if (t == 0) {
+        uint32_t r[N];
+        fe_inv<F>(r, tree[1]);
+        bn_copy<N>(tree[1], r);
+    }
+    __syncthreads();
+    // going down: inv(left) = inv(parent) * right, inv(right) = inv(parent) * left
+    for (int w = 1; w < TPB; w <<= 1) {
+        if (t < w) {
+            uint32_t l[N], r[N], ip[N];
+            bn_copy<N>(ip, tree[w + t]);
+            bn_copy<N>(l, tree[2 * (w + t)]);
+            bn_copy<N>(r, tree[2 * (w + t) + 1]);
+            fe_mul<F>(tree[2 * (w + t)], ip, r);
+            fe_mul<F>(tree[2 * (w + t) + 1], ip, l);
+        }
+        __syncthreads();
+    }
+    bn_copy<N>(z, tree[TPB + t]);
+}
+
+template <class C, int TPB, int MINB> __global__ void __launch_bounds__(TPB, MINB) verify_g1_kernel(const VerifyG1Args a, uint32_t n) {
+    using F = typename C::Fp;
+    __shared__ uint32_t tree[2 * TPB][C::Fp::N];
+    const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+    uint32_t Cc[G1J], z[FPN];
+    int pa = PT_BAD;
+    const bool live = i < n && verify_g1_head<C>(a, i, Cc, pa);
+    if (live && !g1_is_inf_ool<C>(Cc)) bn_copy<C::Fp::N>(z, Cc + 2 * FPN); else fe_set_one<F>(z);
+#ifdef BBS_NO_BATCH_INV
+    { uint32_t zz[FPN]; fe_inv<F>(zz, z); bn_copy<C::Fp::N>(z, zz); (void)tree; }
+#else
+    block_batch_inverse<F, TPB>(z, tree);
+#endif
+    if (live) verify_g1_tail<C>(a, i, Cc, z, pa);
+}
+#endif
 
 // ---- pairing half (shared by verify and proof verify) ----------------------------------------------------
 struct PairingArgs { const uint32_t* lines; const uint32_t* pair; const uint32_t* flags; uint8_t* status; };
@@ -402,7 +477,7 @@ template <class C> BBS_HD void proof_g1_item(const ProofG1Args& a, uint32_t i) {
     x.s.update(pf, 3 * GB);                                     // canonical encodings of Abar, Bbar, D
     {
         // one shared inversion for T1, T2 (Montgomery's trick)
-        bool i1 = g1_is_inf<C>(T1), i2 = g1_is_inf<C>(T2);
+        bool i1 = g1_is_inf_ool<C>(T1), i2 = g1_is_inf_ool<C>(T2);
         uint32_t z1[FPN], z2[FPN], zz[FPN], t[FPN], aff[G1A];
         uint8_t enc[GB];
         if (i1) fe_set_one<F>(z1); else bn_copy<C::Fp::N>(z1, T1 + 2 * FPN);
@@ -497,7 +572,7 @@ template <class C> BBS_HD void proof_gen_item(const ProofGenArgs& a, uint32_t i)
     if (pa == PT_OK) g1_mul_scalar<C>(Abj, A, r01); else g1_set_inf<C>(Abj);
     // normalise D and Abar with one inversion (they are multiplied again and serialised)
     uint32_t Daff[G1A], Abaff[G1A];
-    bool dfin = !g1_is_inf<C>(Dj), afin = !g1_is_inf<C>(Abj);
+    bool dfin = !g1_is_inf_ool<C>(Dj), afin = !g1_is_inf_ool<C>(Abj);
     {
         uint32_t z1[FPN], z2[FPN], zz[FPN], t[FPN];
         if (dfin) bn_copy<C::Fp::N>(z1, Dj + 2 * FPN); else fe_set_one<F>(z1);
@@ -538,7 +613,7 @@ template <class C> BBS_HD void proof_gen_item(const ProofGenArgs& a, uint32_t i)
         bool inf[3];
         uint32_t z[3][FPN], pre[3][FPN], inv[FPN], t[FPN], aff[G1A];
         for (int k = 0; k < 3; k++) {
-            inf[k] = g1_is_inf<C>(P[k]);
+            inf[k] = g1_is_inf_ool<C>(P[k]);
             if (inf[k]) fe_set_one<F>(z[k]); else bn_copy<C::Fp::N>(z[k], P[k] + 2 * FPN);
         }
         bn_copy<C::Fp::N>(pre[0], z[0]);

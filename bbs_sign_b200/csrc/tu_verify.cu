@@ -4,16 +4,23 @@
 
 // occupancy knobs (threads per block, min resident blocks per SM -> register cap); -D overridable
 #ifndef BBS_VERIFY_G1_TPB
-#define BBS_VERIFY_G1_TPB 128
+#define BBS_VERIFY_G1_TPB 256
 #endif
 #ifndef BBS_VERIFY_G1_MINB
-#define BBS_VERIFY_G1_MINB 4
+#define BBS_VERIFY_G1_MINB 2
 #endif
 
 namespace bbs {
 
 template <class C> int launch_verify_g1(const VerifyG1Args& a, uint32_t n, rt_stream_t s) {
+#ifdef BBS_HOSTSIM
     return rt_launch<VerifyG1Args, &verify_g1_item<C>, BBS_VERIFY_G1_TPB, BBS_VERIFY_G1_MINB>(a, n, s);
+#else
+    if (n == 0) return 0;
+    verify_g1_kernel<C, BBS_VERIFY_G1_TPB, BBS_VERIFY_G1_MINB><<<(n + BBS_VERIFY_G1_TPB - 1) / BBS_VERIFY_G1_TPB, BBS_VERIFY_G1_TPB, 0, s>>>(a, n);
+    RT_CHECK(cudaGetLastError());
+    return 0;
+#endif
 }
 
 #if defined(BBS_TU_BLS) || !defined(BBS_TU_BN)
