@@ -29,6 +29,7 @@ struct ProfEvents {
     int read(float* ms, int n) {
         for (int i = 0; i < n; i++) ms[i] = 0.f;
         for (int i = 0; i + 1 < used && i < n; i++) {
+            if (!ev[i] || !ev[i + 1]) continue;       // slot never marked by the last call (e.g. no hashing kernel)
             RT_CHECK(cudaEventSynchronize(ev[i + 1]));
             RT_CHECK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
         }

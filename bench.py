@@ -427,9 +427,13 @@ def run_bn254(args):
         if lib.bbs_core_verify_batch_dev(ctx.handle, n, ptr(d_sigs), ptr(d_sc), L, ptr(d_status), C.c_void_p(stream.cuda_stream)) != 0:
             raise RuntimeError(lib.bbs_last_error().decode())
 
+    lib.bbs_ctx_set_profiling(ctx.handle, 1)
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
+    kt = (C.c_float * 3)()
+    lib.bbs_ctx_kernel_times(ctx.handle, kt, 3)
+    lib.bbs_ctx_set_profiling(ctx.handle, 0)
     if not np.array_equal(d_status.cpu().numpy(), expect):
         raise RuntimeError("bn254 status vector mismatch")
     if world > 1:
@@ -451,7 +455,7 @@ def run_bn254(args):
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
                "config": {"workload": f"BN254 core_verify: {n} signatures x L=31 pre-hashed scalar messages, one issuer key, "
                                       "1/16 corrupted (BASELINE configs[2] shape); per-thread pairing kernel", "n_per_gpu": n},
-               "gpu_launches": 2}
+               "kernels_ms": {"verify_g1": float(kt[1]), "pairing": float(kt[2])}, "gpu_launches": 2}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
