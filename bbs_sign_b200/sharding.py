@@ -46,6 +46,53 @@ class ShardedVerifier:
             raise errs[0]
         return out
 
+    def _run_sharded(self, n, work):
+        errs: list = []
+
+        def guarded(ctx, g, lo, hi):
+            try:
+                if hi > lo:
+                    work(ctx, g, lo, hi)
+            except Exception as e:  # pragma: no cover
+                errs.append(e)
+
+        ts = [threading.Thread(target=guarded, args=(c, g, lo, hi))
+              for g, (c, (lo, hi)) in enumerate(zip(self.ctxs, shard_bounds(n, len(self.ctxs))))]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def proof_verify_batch(self, proofs, ph: bytes, disclosed_messages, disclosed_indexes) -> np.ndarray:
+        """`proof_verify_batch` split by proof index (same contract as BatchContext.proof_verify_batch)."""
+        n = len(proofs)
+        out = np.full(n, 255, dtype=np.uint8)
+
+        def work(ctx, g, lo, hi):
+            out[lo:hi] = ctx.proof_verify_batch(proofs[lo:hi], ph, disclosed_messages[lo:hi], disclosed_indexes[lo:hi])
+
+        self._run_sharded(n, work)
+        return out
+
+    def rlc_verify_batch(self, signatures: Sequence[bytes], messages: Sequence[Sequence[bytes]], seed: bytes) -> int:
+        """Random-linear-combination verdict for the whole batch: every GPU reduces its slice to two compressed G1
+        points (coefficients are indexed globally), GPU 0 adds them and does the single pairing check."""
+        n = len(messages)
+        parts: list = [None] * len(self.ctxs)
+        status: list = [1] * len(self.ctxs)
+
+        def work(ctx, g, lo, hi):
+            parts[g], status[g] = ctx.rlc_partial(signatures[lo:hi], messages[lo:hi], seed, index_base=lo)
+
+        self._run_sharded(n, work)
+        bad = [s for s in status if s != 1]
+        if bad:
+            return bad[0]
+        got = [p for p in parts if p is not None]
+        return self.ctxs[0].rlc_combine(got) if got else 1
+
     def close(self):
         for c in self.ctxs:
             c.close()
