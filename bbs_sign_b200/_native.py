@@ -22,6 +22,7 @@ SYMBOLS = {
     "bbs_signature_bytes": (C.c_size_t, [C.c_int]),
     "bbs_proof_fixed_bytes": (C.c_size_t, [C.c_int]),
     "bbs_last_error": (C.c_char_p, []),
+    "bbs_create_generators": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]),
     "bbs_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t,
                                  C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "bbs_ctx_destroy": (None, [C.c_void_p]),

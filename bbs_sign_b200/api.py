@@ -59,19 +59,29 @@ class Ciphersuite:
     def proof_fixed_bytes(self) -> int:
         return 3 * self.g1_bytes + 128
 
-    def create_generators(self, count: int) -> bytes:
-        """`create_generators(count, api_id)` (interface_utilities.rs:47-73) for this suite's api_id, as
-        `count` compressed G1 points.  Generators are constants of the ciphersuite (prefix-stable); the
-        first 129 are shipped as a table (tools/gen_generators.py).  Deriving them on the device is the
-        'next' row SURVEY 8f-4."""
-        path = os.path.join(_DATA, f"generators_{self.name.lower()}.bin")
-        with open(path, "rb") as f:
-            blob = f.read()
-        have = len(blob) // self.g1_bytes
-        if count > have:
-            raise BbsError(f"only {have} precomputed generators are shipped for {self.name}; "
-                           "pass caller-supplied generators to BatchContext for more")
-        return blob[: count * self.g1_bytes]
+    def create_generators(self, count: int, api_id: Optional[bytes] = None, device: int = 0,
+                          lib_path: Optional[str] = None) -> bytes:
+        """`create_generators(count, api_id)` (interface_utilities.rs:47-73) as `count` compressed G1 points.
+        For the suite's own api_id the first 129 are shipped as a table (tools/gen_generators.py: they are constants
+        of the ciphersuite, prefix-stable); anything else is derived on the GPU by bbs_create_generators."""
+        if api_id is None or api_id == self.api_id:
+            path = os.path.join(_DATA, f"generators_{self.name.lower()}.bin")
+            with open(path, "rb") as f:
+                blob = f.read()
+            if count <= len(blob) // self.g1_bytes:
+                return blob[: count * self.g1_bytes]
+        return self.derive_generators(count, api_id, device, lib_path)
+
+    def derive_generators(self, count: int, api_id: Optional[bytes] = None, device: int = 0,
+                          lib_path: Optional[str] = None) -> bytes:
+        """create_generators on the device (hash-to-G1 of the suite, csrc/h2c.cuh)."""
+        lib = _native.load(lib_path)
+        aid = self.api_id if api_id is None else api_id
+        out = np.zeros(max(count, 1) * self.g1_bytes, dtype=np.uint8)
+        rc = lib.bbs_create_generators(self.curve_id, device, _ptr(_buf(aid)) if aid else None, len(aid), count, _ptr(out))
+        if rc != 0:
+            raise BbsError(f"bbs_create_generators failed ({rc}): {lib.bbs_last_error().decode()}")
+        return out[: count * self.g1_bytes].tobytes()
 
 
 BLS12_381 = Ciphersuite("BLS12_381", 1, 48, 96, b"BBS_BLS12381G1_XMD:SHA-256_SSWU_RO_")

@@ -492,6 +492,33 @@ size_t bbs_signature_bytes(int curve) { return bbs_g1_bytes(curve) ? bbs_g1_byte
 size_t bbs_proof_fixed_bytes(int curve) { return bbs_g1_bytes(curve) ? 3 * bbs_g1_bytes(curve) + 128 : 0; }
 const char* bbs_last_error(void) { return rt_errbuf(); }
 
+int bbs_create_generators(int curve, int device, const uint8_t* api_id, size_t api_id_len, uint32_t count, uint8_t* out) {
+    if (curve != BBS_CURVE_BLS12_381 && curve != BBS_CURVE_BN254) return arg_error("unknown curve id");
+    if (!out || (api_id_len && !api_id)) return arg_error("null");
+    if (api_id_len > 128) return arg_error("api_id too long");
+    if (count == 0) return BBS_OK;
+    if (rt_set_device(device)) return BBS_E_CUDA;
+    if (rt_set_stack(48 * 1024)) return BBS_E_CUDA;
+    const size_t gb = bbs_g1_bytes(curve);
+    DevBuf d_api, d_v, d_out;
+    int rc = d_api.reserve(api_id_len + 1);
+    if (!rc) rc = d_v.reserve((size_t)count * 48);
+    if (!rc) rc = d_out.reserve((size_t)count * gb);
+    if (!rc) rc = rt_h2d(d_api.p, api_id, api_id_len, nullptr);
+    if (!rc) {
+        GenSeedArgs sa{(const uint8_t*)d_api.p, (uint32_t)api_id_len, count, (uint8_t*)d_v.p};
+        rc = launch_gen_seed(sa, nullptr);
+    }
+    if (!rc) {
+        GenPointArgs pa{(const uint8_t*)d_api.p, (uint32_t)api_id_len, (const uint8_t*)d_v.p, (uint8_t*)d_out.p};
+        rc = curve == BBS_CURVE_BLS12_381 ? launch_gen_point<Bls>(pa, count, nullptr) : launch_gen_point<Bn>(pa, count, nullptr);
+    }
+    if (!rc) rc = rt_d2h(out, d_out.p, (size_t)count * gb, nullptr);
+    if (!rc) rc = rt_sync(nullptr);
+    d_api.release(); d_v.release(); d_out.release();
+    return rc;
+}
+
 int bbs_ctx_create(int curve, int device, const uint8_t* pk, const uint8_t* generators, uint32_t n_generators,
                    const uint8_t* header, size_t header_len, const uint8_t* api_id, size_t api_id_len, bbs_ctx** out) {
     if (!out) return arg_error("out is null");

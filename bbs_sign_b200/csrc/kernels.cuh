@@ -10,6 +10,7 @@
 #pragma once
 #include "g2.cuh"
 #include "sha256.cuh"
+#include "h2c.cuh"
 
 namespace bbs {
 

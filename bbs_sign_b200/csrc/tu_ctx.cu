@@ -17,6 +17,17 @@ template <class C> int launch_ctx_lines(const CtxLinesArgs& a, uint32_t n, rt_st
     return rt_launch<CtxLinesArgs, &ctx_lines_item<C>, 32>(a, n, s);
 }
 
+template <class C> int launch_gen_point(const GenPointArgs& a, uint32_t n, rt_stream_t s) {
+    return rt_launch<GenPointArgs, &gen_point_item<C>, 32>(a, n, s);
+}
+#if defined(BBS_TU_BLS) || !defined(BBS_TU_BN)
+int launch_gen_seed(const GenSeedArgs& a, rt_stream_t s) { return rt_launch<GenSeedArgs, &gen_seed_item, 32>(a, 1, s); }
+template int launch_gen_point<Bls>(const GenPointArgs&, uint32_t, rt_stream_t);
+#endif
+#if defined(BBS_TU_BN) || !defined(BBS_TU_BLS)
+template int launch_gen_point<Bn>(const GenPointArgs&, uint32_t, rt_stream_t);
+#endif
+
 template <class C> int launch_ctx_lines_coop(const CtxLinesCoopArgs& a, uint32_t n, rt_stream_t s) {
     return rt_launch<CtxLinesCoopArgs, &ctx_lines_coop_item<C>, 32>(a, n, s);
 }

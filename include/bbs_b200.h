@@ -63,6 +63,12 @@ size_t bbs_proof_fixed_bytes(int curve_id); /* 3*g1 + 4*32 */
 /* Last error text of the calling thread ("" if none). */
 const char* bbs_last_error(void);
 
+/* create_generators(count, api_id) (src/utils/interface_utilities.rs:47-73) on the device, with the suite's hash-to-G1
+ * (:24-44: BLS12381G1_XMD:SHA-256_SSWU_RO_ / BN254G1_XMD:SHA-256_SVDW_RO_): out = count compressed G1 points
+ * Q1, H_1, .., H_{count-1}, ready for bbs_ctx_create. */
+int bbs_create_generators(int curve_id, int device, const uint8_t* api_id, size_t api_id_len, uint32_t count,
+                          uint8_t* out);
+
 /* Builds the per-issuer state on `device`:
  *   decodes `pk` (G2) and the `n_generators` = L+1 generators Q1, H_1..H_L (G1) -- the `generators: &[E::G1]`
  *   argument of core_verify / core_sign / core_proof_verify (src/verify.rs:53-60, src/sign.rs:63-69,

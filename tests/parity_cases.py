@@ -485,3 +485,22 @@ def case_readme_example(lib_path, curve_name):
     assert ctx.proof_verify_batch(got, b"", [[msgs[0], msgs[2]]], [[0, 2]]).tolist() == [1]
     assert ctx.proof_verify_batch(got, b"", [[msgs[0], msgs[3]]], [[0, 2]]).tolist() == [0]
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+def case_create_generators(lib_path, curve_name, count=5):
+    """create_generators on the device (interface_utilities.rs:47-73, hash-to-G1 :24-44) against the oracle: the
+    suite's own api_id (for BLS12-381 these are the IRTF generators of test_vector.rs:124-136), a foreign api_id, and
+    the shipped table as a prefix of the derived list."""
+    suite, ocs = SUITES[curve_name]
+    want = gens_bytes(ocs, O.create_generators_cached(ocs, count, ocs.api_id))
+    got = suite.derive_generators(count, lib_path=lib_path)
+    assert got == want
+    assert suite.create_generators(count) == want                      # the shipped table
+    if curve_name == "BLS12_381":
+        assert got[:48].hex() == ("a9ec65b70a7fbe40c874c9eb041c2cb0a7af36ccec1bea48fa2ba4c2eb67ef7f"
+                                  "9ecb17ed27d38d27cdeddff44c8137be")       # Q1, test_vector.rs:132
+    other = b"OTHER_API_ID_" + ocs.api_id[:7]
+    want2 = gens_bytes(ocs, O.create_generators(ocs, 3, other))
+    assert suite.create_generators(3, api_id=other, lib_path=lib_path) == want2
+    assert suite.derive_generators(0, lib_path=lib_path) == b""

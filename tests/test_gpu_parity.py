@@ -131,3 +131,8 @@ def test_sharded_helpers(lib):
     assert sv.rlc_verify_batch(bad, msgs, seed) == A.ST_REJECT
     assert sv.verify_batch(b"".join(bad), msgs).tolist() == [1, 1, 1, 1, 1, 0, 1]
     sv.close()
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_create_generators(lib, curve):
+    P.case_create_generators(None, curve, count=40)

@@ -71,3 +71,8 @@ def test_h2s_ragged(lib_path, curve):
 @pytest.mark.parametrize("curve", ["BN254", "BLS12_381"])
 def test_readme_example(lib_path, curve):
     P.case_readme_example(lib_path, curve)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_create_generators(lib_path, curve):
+    P.case_create_generators(lib_path, curve, count=3)
