@@ -33,19 +33,36 @@ BBS_HDN void xmd_expand(uint32_t* out, int len_bytes, const uint8_t* m1, uint32_
     }
 }
 
-// big-endian words (nwords = N + 4: the low N limbs and 128 more bits) -> Montgomery element = value mod p
+// big-endian words (nwords = N + 4) -> Montgomery element = value mod p.  The value is cut into c0 (low N-1 limbs) and c1
+// (the 5 limbs above): both are < p, which the device Montgomery product requires of its operands (field.cuh fe_mul).
 template <class F> BBS_HDN void fe_from_wide_be(uint32_t* r, const uint32_t* be, int nwords) {
     constexpr int N = F::N;
-    uint32_t lo[N], hi[N], t[N];
-    for (int i = 0; i < N; i++) lo[i] = be[nwords - 1 - i];
-    for (int i = 0; i < N; i++) hi[i] = (i < nwords - N) ? be[nwords - 1 - N - i] : 0u;
-    fe_mul<F>(lo, lo, F::R2());            // lo R mod p      (lo < R, R2 < p: the CIOS bound holds)
-    fe_mul<F>(t, hi, F::R2());             // hi R
-    fe_mul<F>(hi, t, F::R2());             // hi R^2  = Montgomery form of hi * R
-    fe_add<F>(r, lo, hi);
+    uint32_t c0[N], c1[N], sh[N];
+    for (int i = 0; i < N; i++) {
+        c0[i] = i < N - 1 ? be[nwords - 1 - i] : 0u;
+        c1[i] = (N - 1 + i) < nwords ? be[nwords - 1 - (N - 1) - i] : 0u;
+        sh[i] = i == N - 1 ? 1u : 0u;          // 2^(32 (N-1))
+    }
+    fe_mul<F>(c0, c0, F::R2());
+    fe_mul<F>(c1, c1, F::R2());
+    fe_mul<F>(sh, sh, F::R2());
+    fe_mul<F>(c1, c1, sh);
+    fe_add<F>(r, c0, c1);
 }
 
-BBS_HD bool fe_parity(const uint32_t* canon) { return canon[0] & 1u; }
+// out of line on purpose: cicc folds comparisons of values an out-of-line callee has just written (DESIGN.md compiler note)
+template <int N> BBS_HDN bool h2c_is_zero(const uint32_t* a) {
+    uint32_t o = 0;
+    for (int i = 0; i < N; i++) o |= a[i];
+    return o == 0;
+}
+// sgn0(u) != sgn0(y) for Montgomery inputs (sgn0 = parity of the canonical integer)
+template <class F> BBS_HDN bool h2c_sgn_differs(const uint32_t* u, const uint32_t* y) {
+    uint32_t uc[F::N], yc[F::N];
+    fe_from_mont<F>(uc, u);
+    fe_from_mont<F>(yc, y);
+    return ((uc[0] ^ yc[0]) & 1u) != 0;
+}
 
 // ---- BLS12-381: simplified SWU onto E', 11-isogeny by Velu's formulas, cofactor clearing by h_eff ---------------------
 BBS_HDN void bls_sswu(uint32_t* X, uint32_t* Y, const uint32_t* u) {
@@ -58,7 +75,7 @@ BBS_HDN void bls_sswu(uint32_t* X, uint32_t* Y, const uint32_t* u) {
     fe_sqr<F>(tv, t);                          // Z^2 u^4
     fe_add<F>(tv, tv, t);
     fe_inv<F>(tv1, tv);                        // inv0
-    if (bn_is_zero<N>(tv1)) bn_copy<N>(x1, BLS_H2C_BZA());
+    if (h2c_is_zero<N>(tv1)) bn_copy<N>(x1, BLS_H2C_BZA());
     else { fe_add<F>(x1, one, tv1); fe_mul<F>(x1, x1, BLS_H2C_NBA()); }
     // g(x1) = x1^3 + A x1 + B
     fe_sqr<F>(g, x1); fe_add<F>(g, g, BLS_H2C_A()); fe_mul<F>(g, g, x1); fe_add<F>(g, g, BLS_H2C_B());
@@ -69,10 +86,7 @@ BBS_HDN void bls_sswu(uint32_t* X, uint32_t* Y, const uint32_t* u) {
         fe_sqr<F>(g, X); fe_add<F>(g, g, BLS_H2C_A()); fe_mul<F>(g, g, X); fe_add<F>(g, g, BLS_H2C_B());
         fe_sqrt<F>(y, g);
     }
-    uint32_t uc[N], yc[N];
-    fe_from_mont<F>(uc, u);
-    fe_from_mont<F>(yc, y);
-    if (fe_parity(uc) != fe_parity(yc)) fe_neg<F>(y, y);
+    if (h2c_sgn_differs<F>(u, y)) fe_neg<F>(y, y);
     bn_copy<N>(Y, y);
 }
 BBS_HDN void bls_iso11(uint32_t* xo, uint32_t* yo, const uint32_t* X, const uint32_t* Y) {
@@ -144,10 +158,7 @@ BBS_HDN void bn_svdw(uint32_t* X, uint32_t* Y, const uint32_t* u) {
             bn_copy<N>(X, x3);
         }
     }
-    uint32_t uc[N], yc[N];
-    fe_from_mont<F>(uc, u);
-    fe_from_mont<F>(yc, y);
-    if (fe_parity(uc) != fe_parity(yc)) fe_neg<F>(y, y);
+    if (h2c_sgn_differs<F>(u, y)) fe_neg<F>(y, y);
     bn_copy<N>(Y, y);
     (void)t;
 }
