@@ -56,12 +56,12 @@ struct Ctx {
     CtxView view{};
     // grow-only scratch for the batch calls
     DevBuf s_rand, s_rand_off;
-    DevBuf s_gscr, s_rlc_pt, s_rlc_sc, s_rlc_parts, s_rlc_bad;
+    DevBuf s_gscr, s_rlc_pt, s_rlc_sc, s_rlc_parts, s_rlc_bad, s_msm_pts, s_msm_kv, s_msm_idx, s_msm_entries, s_msm_buckets;
     DevBuf s_sigs, s_scalars, s_msgs, s_offsets, s_pair, s_flags, s_status, s_out, s_out2;
     DevBuf s_commit, s_commit_off, s_dis_idx, s_dis_scalars, s_dis_off, s_ph, s_dis_msgs, s_dis_msg_off;
     void release_all() {
         DevBuf* all[] = {&pk_comp, &gens_comp, &api_id, &header, &dst_h2s, &dst_map, &gens, &W, &K, &domain, &tab,
-                         &lines, &lines_coop, &s_rand, &s_rand_off, &s_gscr, &s_rlc_pt, &s_rlc_sc, &s_rlc_parts, &s_rlc_bad, &misc, &s_sigs, &s_scalars, &s_msgs, &s_offsets, &s_pair, &s_flags, &s_status, &s_out,
+                         &lines, &lines_coop, &s_rand, &s_rand_off, &s_gscr, &s_rlc_pt, &s_rlc_sc, &s_rlc_parts, &s_rlc_bad, &s_msm_pts, &s_msm_kv, &s_msm_idx, &s_msm_entries, &s_msm_buckets, &misc, &s_sigs, &s_scalars, &s_msgs, &s_offsets, &s_pair, &s_flags, &s_status, &s_out,
                          &s_out2, &s_commit, &s_commit_off, &s_dis_idx, &s_dis_scalars, &s_dis_off, &s_ph, &s_dis_msgs,
                          &s_dis_msg_off};
         for (DevBuf* b : all) b->release();
@@ -295,26 +295,83 @@ struct Impl {
 
     // ---- random-linear-combination batch mode (rlc.cuh) ---------------------------------------------
 #ifndef BBS_HOSTSIM
+    // digits per 128-bit value for the bucket MSM.  Cost in field multiplications: 11 per bucket addition, inflated by the
+    // quantisation of buckets over the persistent threads of msm_bucket_kernel (u buckets per thread), plus ~47 per bucket
+    // for the reduction (measured on B200 at n = 65,536 and 524,288: profiles/summary_r01.md)
+    static MsmPlan rlc_plan(size_t n) {
+        uint32_t best = 32;
+        double best_cost = 1e300;
+        const char* force = getenv("BBS_RLC_WINDOWS");        // tests: exercise other geometries
+        for (uint32_t W = 8; W <= 32; W++) {
+            const uint32_t c = (128 + W - 1) / W, rows = MsmGeom<C>::PHI ? 2 * W : 3 * W;
+            double used = 0;                                   // buckets that can be non-empty
+            for (uint32_t w = 0; w < W; w++) used += (double)(1u << (((w + 1) * 128) / W - (w * 128) / W));
+            used *= rows / W;
+            const double u = used / (148.0 * 512.0);
+            const double cost = 11.0 * 3.0 * W * (double)n * (1.0 + 1.0 / u) + 47.0 * rows * (double)(1u << c);
+            if ((force && atoi(force) > 0) ? (uint32_t)atoi(force) == W : cost < best_cost) { best = W; best_cost = cost; }
+        }
+        MsmPlan p;
+        p.W = best;
+        p.c = (128 + best - 1) / best;
+        p.rows = MsmGeom<C>::PHI ? 2 * p.W : 3 * p.W;
+        p.chunk = 16u;
+        const uint32_t threads = (1u << p.c) / p.chunk;
+        p.red_blocks = (threads + RLC_TPB - 1) / RLC_TPB;
+        return p;
+    }
     // shard -> comp(S1) || comp(S2) in c->s_rlc_parts; *bad != 0 when an item was malformed
     static int rlc_partial_dev(Ctx* c, size_t n, const uint8_t* d_sigs, const uint8_t* d_scalars, uint32_t n_msgs,
                                const uint8_t* seed, uint64_t index_base, uint32_t* bad, rt_stream_t s) {
+        if (n >= (1ull << 31)) return arg_error("rlc shard too large");
         const uint32_t blocks = (uint32_t)((n + RLC_TPB - 1) / RLC_TPB);
-        TRY(c->s_rlc_pt.reserve((size_t)(blocks ? blocks : 1) * 2 * 3 * C::Fp::N * 4));
+        const MsmPlan plan = rlc_plan(n);
+        const size_t nb = (size_t)plan.rows << plan.c, PT = 3 * C::Fp::N * 4;
         TRY(c->s_rlc_sc.reserve((size_t)(blocks ? blocks : 1) * (n_msgs + 1) * 32));
         TRY(c->s_rlc_parts.reserve(2 * C::G1_BYTES));
         TRY(c->s_rlc_bad.reserve(4));
+        TRY(c->s_msm_pts.reserve((n ? n : 1) * 2 * C::Fp::N * 4));
+        TRY(c->s_msm_kv.reserve((n ? n : 1) * 48));
+        TRY(c->s_msm_idx.reserve((3 * nb + 5) * 4));                        // next (4 words) | counts | offsets (nb + 1) | cursor
+        TRY(c->s_msm_entries.reserve((n ? n : 1) * 3 * plan.W * 4));
+        TRY(c->s_msm_buckets.reserve(nb * PT));
+        TRY(c->s_rlc_pt.reserve((size_t)plan.rows * plan.red_blocks * PT));
+        uint32_t* next = (uint32_t*)c->s_msm_idx.p;
+        uint32_t* counts = next + 4;
+        uint32_t* offsets = counts + nb;
+        uint32_t* cursor = offsets + nb + 1;
         TRY(rt_memset(c->s_rlc_bad.p, 0, 4, s));
-        RlcArgs a{};
+        TRY(rt_memset(next, 0, (nb + 4) * 4, s));
+        RlcPrepArgs pa{};
+        RlcArgs& a = pa.base;
         a.ctx = c->view; a.sigs = d_sigs; a.scalars = d_scalars; a.n_msgs = n_msgs; a.n = (uint32_t)n;
         a.index_base = index_base;
         for (int i = 0; i < 8; i++)
             a.seed[i] = ((uint32_t)seed[4 * i] << 24) | ((uint32_t)seed[4 * i + 1] << 16) | ((uint32_t)seed[4 * i + 2] << 8) | seed[4 * i + 3];
-        a.pt_part = (uint32_t*)c->s_rlc_pt.p; a.sc_part = (uint32_t*)c->s_rlc_sc.p; a.bad = (uint32_t*)c->s_rlc_bad.p;
-        TRY((launch_rlc_partial<C>(a, blocks, s)));
-        RlcFinishArgs f{c->view, (const uint32_t*)c->s_rlc_pt.p, (const uint32_t*)c->s_rlc_sc.p, blocks, n_msgs,
-                        (uint8_t*)c->s_rlc_parts.p};
-        TRY((launch_rlc_finish<C>(f, s)));
-        c->launches += 2;
+        a.sc_part = (uint32_t*)c->s_rlc_sc.p; a.bad = (uint32_t*)c->s_rlc_bad.p;
+        pa.plan = plan; pa.pts = (uint32_t*)c->s_msm_pts.p; pa.kv = (uint32_t*)c->s_msm_kv.p; pa.counts = counts;
+        PROF(c, 1, s);
+        TRY((launch_rlc_prep<C>(pa, blocks, s)));
+        PROF(c, 2, s);
+        TRY(launch_msm_scan(counts, offsets, cursor, (uint32_t)nb, s));
+        MsmScatterArgs sa{plan, (const uint32_t*)c->s_msm_kv.p, cursor, (uint32_t*)c->s_msm_entries.p, (uint32_t)n};
+        TRY((launch_msm_scatter<C>(sa, s)));
+        PROF(c, 3, s);
+        MsmBucketArgs ba{offsets, (const uint32_t*)c->s_msm_entries.p, (const uint32_t*)c->s_msm_pts.p,
+                         (uint32_t*)c->s_msm_buckets.p, next, (uint32_t)nb};
+        TRY((launch_msm_bucket<C>(ba, s)));
+        PROF(c, 4, s);
+        MsmReduceArgs ra{plan, (const uint32_t*)c->s_msm_buckets.p, (uint32_t*)c->s_rlc_pt.p};
+        TRY((launch_msm_reduce<C>(ra, s)));
+        PROF(c, 5, s);
+        TRY(c->s_pair.reserve(6 * C::Fp::N * 4));
+        TRY(c->s_flags.reserve(4));
+        TRY(c->s_status.reserve(1));
+        RlcMsmFinishArgs f{c->view, plan, (const uint32_t*)c->s_rlc_pt.p, (const uint32_t*)c->s_rlc_sc.p, blocks, n_msgs,
+                           (uint8_t*)c->s_rlc_parts.p, (uint32_t*)c->s_pair.p, (uint32_t*)c->s_flags.p, (uint8_t*)c->s_status.p};
+        TRY((launch_rlc_msm_finish<C>(f, s)));
+        PROF(c, 6, s);
+        c->launches += (n ? 6 : 4);
         TRY(rt_d2h(bad, c->s_rlc_bad.p, 4, s));
         return BBS_OK;
     }
@@ -340,12 +397,37 @@ struct Impl {
         TRY(stage(c->s_msgs, msgs, off[count], s));
         TRY(stage(c->s_offsets, off, (count + 1) * 8, s));
         TRY(c->s_scalars.reserve(count * 32));
+        PROF(c, 0, s);
         TRY(h2s_dev(c, count, (const uint8_t*)c->s_msgs.p, (const uint64_t*)c->s_offsets.p, (uint8_t*)c->s_scalars.p, s));
         uint32_t bad = 0;
         TRY(rlc_partial_dev(c, n, (const uint8_t*)c->s_sigs.p, (const uint8_t*)c->s_scalars.p, n_msgs, seed, index_base, &bad, s));
         TRY(rt_d2h(parts_out, c->s_rlc_parts.p, 2 * C::G1_BYTES, s));
         TRY(rt_sync(s));
         *status = bad ? ST_ERR_MALFORMED : ST_ACCEPT;
+        return BBS_OK;
+    }
+    // one shard = the whole batch: the finish kernel's pairing record goes straight to the pairing kernel
+    static int rlc_verify(Ctx* c, size_t n, const uint8_t* sigs, const uint8_t* scalars, const uint8_t* msgs, const uint64_t* off,
+                          uint32_t n_msgs, const uint8_t* seed, uint8_t* verdict) {
+        rt_stream_t s = c->stream;
+        if (n_msgs != c->L) { *verdict = ST_ERR_MSG_GEN_LEN; return BBS_OK; }
+        const size_t count = n * n_msgs;
+        TRY(stage(c->s_sigs, sigs, n * SIG, s));
+        if (off) {
+            TRY(stage(c->s_msgs, msgs, off[count], s));
+            TRY(stage(c->s_offsets, off, (count + 1) * 8, s));
+            TRY(c->s_scalars.reserve(count * 32));
+            PROF(c, 0, s);
+            TRY(h2s_dev(c, count, (const uint8_t*)c->s_msgs.p, (const uint64_t*)c->s_offsets.p, (uint8_t*)c->s_scalars.p, s));
+        } else {
+            TRY(stage(c->s_scalars, scalars, count * 32, s));
+        }
+        uint32_t bad = 0;
+        TRY(rlc_partial_dev(c, n, (const uint8_t*)c->s_sigs.p, (const uint8_t*)c->s_scalars.p, n_msgs, seed, 0, &bad, s));
+        TRY(pairing_dev(c, 1, (uint8_t*)c->s_status.p, s));
+        PROF(c, 7, s);
+        TRY(finish_status(c, 1, verdict));             // synchronises: `bad` has arrived too
+        if (bad) *verdict = ST_ERR_MALFORMED;
         return BBS_OK;
     }
     // n_parts x (comp(S1) || comp(S2)) -> one verdict byte
@@ -672,19 +754,15 @@ int bbs_rlc_combine(bbs_ctx* p, size_t n_parts, const uint8_t* parts, uint8_t* v
 }
 int bbs_rlc_core_verify_batch(bbs_ctx* p, size_t n, const uint8_t* sigs, const uint8_t* scalars, uint32_t n_msgs,
                               const uint8_t seed[32], uint8_t* verdict) {
-    uint8_t parts[2 * 48], st = 0;
-    int rc = bbs_rlc_partial_core(p, n, sigs, scalars, n_msgs, seed, 0, parts, &st);
-    if (rc) return rc;
-    if (st != BBS_ST_ACCEPT) { *verdict = st; return BBS_OK; }
-    return bbs_rlc_combine(p, 1, parts, verdict);
+    Ctx* c = as_ctx(p);
+    if (!seed || !verdict || (n && !sigs) || (n && n_msgs && !scalars)) return arg_error("null");
+    DISPATCH(c, rlc_verify(c, n, sigs, scalars, nullptr, nullptr, n_msgs, seed, verdict));
 }
 int bbs_rlc_verify_batch(bbs_ctx* p, size_t n, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off,
                          uint32_t n_msgs, const uint8_t seed[32], uint8_t* verdict) {
-    uint8_t parts[2 * 48], st = 0;
-    int rc = bbs_rlc_partial(p, n, sigs, msgs, off, n_msgs, seed, 0, parts, &st);
-    if (rc) return rc;
-    if (st != BBS_ST_ACCEPT) { *verdict = st; return BBS_OK; }
-    return bbs_rlc_combine(p, 1, parts, verdict);
+    Ctx* c = as_ctx(p);
+    if (!seed || !verdict || !off || (n && !sigs)) return arg_error("null");
+    DISPATCH(c, rlc_verify(c, n, sigs, nullptr, msgs, off, n_msgs, seed, verdict));
 }
 #else
 int bbs_rlc_partial_core(bbs_ctx*, size_t, const uint8_t*, const uint8_t*, uint32_t, const uint8_t*, uint64_t, uint8_t*, uint8_t*) { rt_set_error("rlc", "needs the CUDA build"); return BBS_E_CUDA; }

@@ -4,6 +4,7 @@
 #include "kernels.cuh"
 #include "pairing_coop.cuh"
 #include "rlc.cuh"
+#include "rlc_msm.cuh"
 #include "selftest.cuh"
 #include "launch.cuh"
 
@@ -21,8 +22,12 @@ template <class C> int launch_verify_g1(const VerifyG1Args& a, uint32_t n, rt_st
 template <class C> int launch_pairing(const PairingArgs& a, uint32_t n, rt_stream_t s);
 #ifndef BBS_HOSTSIM
 // random-linear-combination batch mode (rlc.cuh)
-template <class C> int launch_rlc_partial(const RlcArgs& a, uint32_t n_blocks, rt_stream_t s);
-template <class C> int launch_rlc_finish(const RlcFinishArgs& a, rt_stream_t s);
+template <class C> int launch_rlc_prep(const RlcPrepArgs& a, uint32_t n_blocks, rt_stream_t s);
+int launch_msm_scan(const uint32_t* counts, uint32_t* offsets, uint32_t* cursor, uint32_t nb, rt_stream_t s);
+template <class C> int launch_msm_scatter(const MsmScatterArgs& a, rt_stream_t s);
+template <class C> int launch_msm_bucket(const MsmBucketArgs& a, rt_stream_t s);
+template <class C> int launch_msm_reduce(const MsmReduceArgs& a, rt_stream_t s);
+template <class C> int launch_rlc_msm_finish(const RlcMsmFinishArgs& a, rt_stream_t s);
 template <class C> int launch_rlc_combine(const RlcCombineArgs& a, rt_stream_t s);
 // cooperative kernel (BLS12-381 only so far); gscratch must hold coop_gscratch_bytes(n)
 int launch_pairing_coop_bls(const CoopArgs& a, rt_stream_t s);

@@ -5,9 +5,9 @@
 // if that is 0.  A batch-level, probabilistic verdict (a false accept needs a 2^-128 event over the seed); the per-item
 // entry points remain the reference-exact path.  The B_i terms collapse to L+1 fixed-base products:
 //     sum r_i B_i = (sum r_i) K + sum_j (sum_i r_i m_ij) H_j
-// so the per-item work is one decompression and two scalar multiplications of A_i.  Every GPU reduces its shard to
-// two G1 points (rlc_partial_kernel + rlc_finish_kernel); the partial points of all shards are added and checked with
-// ONE pairing product by rlc_combine (no collective: 2 compressed points per GPU travel through the host).
+// so the per-item work is one decompression and the item's share of two bucket MSMs (rlc_msm.cuh).  Every GPU reduces
+// its shard to two G1 points; the partial points of all shards are added and checked with ONE pairing product by
+// rlc_combine (no collective: 2 compressed points per GPU travel through the host).
 #pragma once
 #include "kernels.cuh"
 
@@ -23,7 +23,6 @@ struct RlcArgs {
     uint32_t n_msgs, n;
     uint64_t index_base;        // global index of item 0 of this shard (coefficients depend on the global index)
     uint32_t seed[8];           // the 32-byte seed as big-endian words
-    uint32_t* pt_part;          // [blocks][2][Jacobian]
     uint32_t* sc_part;          // [blocks][n_msgs + 1][8]  canonical Fr limbs
     uint32_t* bad;              // != 0: some item was malformed
 };
@@ -59,108 +58,6 @@ template <class C> __device__ __forceinline__ void rlc_block_sum_fr(uint32_t (*s
     for (int s = RLC_TPB / 2; s >= 1; s >>= 1) {
         if (t < s) fe_add<typename C::Fr>(ss[t], ss[t], ss[t + s]);
         __syncthreads();
-    }
-}
-
-template <class C> __global__ void __launch_bounds__(RLC_TPB, 4) rlc_partial_kernel(const RlcArgs a) {
-    using Fr = typename C::Fr;
-    __shared__ uint32_t sp[RLC_TPB][3 * C::Fp::N];
-    __shared__ uint32_t ss[RLC_TPB][8];
-    const CtxView& cx = a.ctx;
-    const uint32_t i = blockIdx.x * RLC_TPB + threadIdx.x;
-    const bool valid = i < a.n;
-    uint32_t P1[G1J], P2[G1J], rm[8];
-    g1_set_inf<C>(P1);
-    g1_set_inf<C>(P2);
-    bn_zero<8>(rm);
-    bool ok = true;
-    const uint8_t* sc = a.scalars + (size_t)(valid ? i : 0) * a.n_msgs * 32;
-    uint32_t r[8];
-    bn_zero<8>(r);
-    if (valid) {
-        const uint8_t* sig = a.sigs + (size_t)i * (C::G1_BYTES + 32);
-        uint32_t A[G1A], e[8];
-        int pa = g1_decompress<C>(A, sig);
-        ok = pa != PT_BAD && fr_from_le32<C>(e, sig + C::G1_BYTES);
-        rlc_coeff(r, a.seed, a.index_base + i);
-        fe_to_mont<Fr>(rm, r);
-        if (ok && pa == PT_OK) {
-            uint32_t ae[8];
-            fe_mul<Fr>(ae, rm, e);                  // r_i e_i mod r, canonical
-            g1_mul_scalar<C>(P1, A, r);
-            g1_mul_scalar<C>(P2, A, ae);
-        }
-    }
-    // points
-    rlc_block_sum_points<C>(sp, P1);
-    if (threadIdx.x == 0) g1_copy<C>(a.pt_part + (size_t)blockIdx.x * 2 * G1J, sp[0]);
-    __syncthreads();
-    rlc_block_sum_points<C>(sp, P2);
-    if (threadIdx.x == 0) g1_copy<C>(a.pt_part + ((size_t)blockIdx.x * 2 + 1) * G1J, sp[0]);
-    __syncthreads();
-    // scalars: sum r_i, sum r_i m_ij
-    uint32_t* scp = a.sc_part + (size_t)blockIdx.x * (a.n_msgs + 1) * 8;
-    rlc_block_sum_fr<C>(ss, r);
-    if (threadIdx.x == 0) bn_copy<8>(scp, ss[0]);
-    __syncthreads();
-    for (uint32_t j = 0; j < a.n_msgs; j++) {
-        uint32_t t[8];
-        bn_zero<8>(t);
-        if (valid && ok) {
-            uint32_t m[8];
-            if (fr_from_le32<C>(m, sc + j * 32)) fe_mul<Fr>(t, rm, m); else ok = false;
-        }
-        rlc_block_sum_fr<C>(ss, t);
-        if (threadIdx.x == 0) bn_copy<8>(scp + (j + 1) * 8, ss[0]);
-        __syncthreads();
-    }
-    if (valid && !ok) atomicOr(a.bad, 1u);
-}
-
-struct RlcFinishArgs {
-    CtxView ctx;
-    const uint32_t* pt_part; const uint32_t* sc_part;
-    uint32_t n_blocks, n_msgs;
-    uint8_t* parts_out;        // comp(S1) || comp(S2)
-};
-// one block: adds the per-block partial sums, subtracts the fixed-base term, compresses the two points
-template <class C> __global__ void __launch_bounds__(RLC_TPB, 1) rlc_finish_kernel(const RlcFinishArgs a) {
-    using Fr = typename C::Fr;
-    __shared__ uint32_t sp[RLC_TPB][3 * C::Fp::N];
-    __shared__ uint32_t ss[RLC_TPB][8];
-    __shared__ uint32_t s1[3 * C::Fp::N];
-    const CtxView& cx = a.ctx;
-    uint32_t acc[G1J];
-    for (int which = 0; which < 2; which++) {
-        g1_set_inf<C>(acc);
-        for (uint32_t b = threadIdx.x; b < a.n_blocks; b += RLC_TPB) g1_add<C>(acc, acc, a.pt_part + ((size_t)b * 2 + which) * G1J);
-        rlc_block_sum_points<C>(sp, acc);
-        if (threadIdx.x == 0 && which == 0) g1_copy<C>(s1, sp[0]);
-        __syncthreads();
-    }
-    // sp[0] = sum r_i e_i A_i.  F = (sum r_i) K + sum_j (sum_i r_i m_ij) H_j on the fixed-base tables
-    uint32_t F[G1J];
-    g1_set_inf<C>(F);
-    for (uint32_t j = 0; j <= a.n_msgs; j++) {
-        uint32_t t[8];
-        bn_zero<8>(t);
-        for (uint32_t b = threadIdx.x; b < a.n_blocks; b += RLC_TPB) fe_add<Fr>(t, t, a.sc_part + ((size_t)b * (a.n_msgs + 1) + j) * 8);
-        rlc_block_sum_fr<C>(ss, t);
-        if (threadIdx.x == 0) {
-            uint32_t sj[8];
-            bn_copy<8>(sj, ss[0]);
-            if (!(j == 0 && cx.k_inf)) tab_accumulate<C>(F, cx.tab, j, sj);
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        uint32_t S2[G1J], nF[G1J], S1[G1J];
-        g1_neg<C>(nF, F);
-        g1_copy<C>(S2, sp[0]);
-        g1_add<C>(S2, S2, nF);
-        g1_copy<C>(S1, s1);
-        g1_compress<C>(a.parts_out, S1);
-        g1_compress<C>(a.parts_out + C::G1_BYTES, S2);
     }
 }
 

@@ -488,6 +488,11 @@ def run_rlc(args):
         raise RuntimeError(lib.bbs_last_error().decode())
     seed = np.frombuffer(bytes(range(32)), dtype=np.uint8).copy()
     verdict = np.zeros(1, dtype=np.uint8)
+    # pinned host buffers (the caller's side of the C ABI), as in the verify arm
+    p_msgs = torch.from_numpy(msgs).pin_memory()
+    p_offs = torch.from_numpy(offs.view(np.int64)).pin_memory()
+    p_sigs = torch.from_numpy(sigs).pin_memory()
+    msgs, offs, sigs = p_msgs.numpy(), p_offs.numpy().view(np.uint64), p_sigs.numpy()
 
     def step():
         if lib.bbs_rlc_verify_batch(ctx.handle, n, ptr(sigs), ptr(msgs), ptr(offs), L, ptr(seed), ptr(verdict)) != 0:
@@ -495,9 +500,13 @@ def run_rlc(args):
         if verdict[0] != 1:
             raise RuntimeError(f"rlc verdict {verdict[0]} on a valid batch")
 
+    lib.bbs_ctx_set_profiling(ctx.handle, 1)
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
+    kt = (C.c_float * 7)()
+    lib.bbs_ctx_kernel_times(ctx.handle, kt, 7)
+    lib.bbs_ctx_set_profiling(ctx.handle, 0)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
@@ -521,7 +530,9 @@ def run_rlc(args):
                "config": {"workload": f"random-linear-combination batch verify: {n} valid signatures x L={L}, one verdict per batch "
                                       "(optional mode; host buffers, copies inside the timed region)", "n_per_gpu": n},
                "e2e": {"value": v, "unit": "signatures/s", "h2d_bytes_per_step": int(msgs.nbytes + offs.nbytes + sigs.nbytes),
-                       "d2h_bytes_per_step": 2 * 48 + 1}, "gpu_launches": 6}
+                       "d2h_bytes_per_step": 2 * 48 + 1}, "gpu_launches": 9,
+               "kernels_ms": dict(zip(["msg_to_scalars", "rlc_prep", "msm_scan_scatter", "msm_bucket", "msm_reduce", "rlc_msm_finish", "pairing"],
+                                      [float(x) for x in kt]))}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -570,7 +581,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=N_DEFAULT)
+    ap.add_argument("--n", type=int, default=None, help="items per GPU (default 65,536; rlc: 524,288 = configs[4] per GPU)")
     ap.add_argument("--L", type=int, default=L_DEFAULT)
     ap.add_argument("--cpu-sample", type=int, default=0, help="signatures per CPU-baseline step (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -578,6 +589,8 @@ def main():
                     help="verify = BASELINE configs[1] (the headline); proof = configs[3]-shaped proof_verify")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.n is None:
+        args.n = 524288 if (args.workload == "rlc" and args.impl == "ours") else N_DEFAULT
     if args.workload == "proof" and args.impl == "ours":
         out = run_proof(args)
     elif args.workload == "rlc" and args.impl == "ours":

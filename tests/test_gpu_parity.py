@@ -92,6 +92,16 @@ def test_rlc(lib, curve, L):
     P.case_rlc(None, curve, L=L, n=9)
 
 
+@pytest.mark.parametrize("curve,windows,n", [("BLS12_381", 8, 9), ("BN254", 8, 9), ("BLS12_381", 13, 40), ("BN254", 19, 40),
+                                             ("BLS12_381", 32, 9), ("BN254", 32, 9), ("BLS12_381", 0, 150)])
+def test_rlc_msm_geometries(lib, curve, windows, n, monkeypatch):
+    """bucket MSM (rlc_msm.cuh) with other digit counts than the cost model's pick (0 = the model), incl. uneven digit
+    widths and the 16-bit rows: partial sums stay bit-exact against the oracle"""
+    if windows:
+        monkeypatch.setenv("BBS_RLC_WINDOWS", str(windows))
+    P.case_rlc(None, curve, L=2, n=n)
+
+
 @pytest.mark.parametrize("curve,L,dis", [("BLS12_381", 5, [0, 2, 3]), ("BN254", 3, [1]), ("BLS12_381", 2, []),
                                          ("BLS12_381", 3, [0, 1, 2]), ("BLS12_381", 0, [])])
 def test_proof_gen(lib, curve, L, dis):
