@@ -52,7 +52,7 @@ struct Ctx {
     ProfEvents prof;
     DevBuf pk_comp, gens_comp, api_id, header, dst_h2s, dst_map;
     DevBuf gens, W, K, domain, tab, lines, lines_coop, misc;
-    bool coop = false;               // cooperative pairing kernel usable (BLS12-381, no degenerate line)
+    bool coop = false;               // cooperative pairing kernel usable (no degenerate line)
     CtxView view{};
     // grow-only scratch for the batch calls
     DevBuf s_rand, s_rand_off;
@@ -143,7 +143,7 @@ struct Impl {
         // 5. normalised line table of the cooperative pairing kernel
         c->coop = false;
 #ifndef BBS_HOSTSIM
-        if (C::ID == Bls::ID) {
+        {
             TRY(c->lines_coop.reserve((size_t)n_lines * 2 * 4 * C::Fp::N * 4));
             uint32_t* d_deg = d_status;
             TRY(rt_memset(d_deg, 0, 4, s));
@@ -176,10 +176,10 @@ struct Impl {
     static int pairing_dev(Ctx* c, size_t n, uint8_t* d_status, rt_stream_t s) {
 #ifndef BBS_HOSTSIM
         if (c->coop) {
-            TRY(c->s_gscr.reserve(coop_gscratch_bytes_bls(n)));
+            TRY(c->s_gscr.reserve(coop_gscratch_size<C>(n)));
             CoopArgs ca{(const uint32_t*)c->lines_coop.p, (const uint32_t*)c->s_pair.p, (const uint32_t*)c->s_flags.p,
                         d_status, (uint32_t*)c->s_gscr.p, (uint32_t)n};
-            TRY(launch_pairing_coop_bls(ca, s));
+            TRY((launch_pairing_coop<C>(ca, s)));
             c->launches += n ? 1 : 0;
             return BBS_OK;
         }

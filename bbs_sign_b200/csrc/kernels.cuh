@@ -141,7 +141,7 @@ template <class C> BBS_HD void ctx_lines_item(const CtxLinesArgs& a, uint32_t i)
     else g2_precompute_lines<C>(a.lines, C::G2(), 1);
 }
 
-// Line table of the cooperative pairing kernel: entry (line, pair) = (Bc / A, 1 / A), i.e. the line scaled to
+// Line table of the cooperative pairing kernel (M-type twist): entry (line, pair) = (Bc / A, 1 / A), i.e. the line scaled to
 // constant term 1 (any Fp2 factor dies in the final exponentiation).  A == 0 (a tangent / chord through the origin,
 // impossible for an honest key) is reported so that the context falls back to the per-thread kernel.
 struct CtxLinesCoopArgs { const uint32_t* lines; uint32_t* lines2; uint32_t* degenerate; uint32_t w_inf; };
@@ -149,6 +149,13 @@ template <class C> BBS_HD void ctx_lines_coop_item(const CtxLinesCoopArgs& a, ui
     const uint32_t* src = a.lines + (size_t)i * LINE_WORDS;
     uint32_t* dst = a.lines2 + ((size_t)(i >> 1) * 4 + (i & 1) * 2) * F2N;
     if ((i & 1) == 0 && a.w_inf) { bn_zero<4 * C::Fp::N>(dst); return; }
+    if (!C::M_TWIST) {
+        // D-type twist (BN254): the constant term of the line is the item's y, so the line is normalised per item
+        // (pairing_coop.cuh POINT_RATIO) and the table keeps (Bc, A) as they are: never degenerate
+        f2_copy<C>(dst, src + F2N);
+        f2_copy<C>(dst + F2N, src);
+        return;
+    }
     if (f2_is_zero<C>(src)) { *a.degenerate = 1; bn_zero<4 * C::Fp::N>(dst); return; }
     uint32_t ai[F2N], bp[F2N];
     f2_inv<C>(ai, src);

@@ -29,9 +29,9 @@ template <class C> int launch_msm_bucket(const MsmBucketArgs& a, rt_stream_t s);
 template <class C> int launch_msm_reduce(const MsmReduceArgs& a, rt_stream_t s);
 template <class C> int launch_rlc_msm_finish(const RlcMsmFinishArgs& a, rt_stream_t s);
 template <class C> int launch_rlc_combine(const RlcCombineArgs& a, rt_stream_t s);
-// cooperative kernel (BLS12-381 only so far); gscratch must hold coop_gscratch_bytes(n)
-int launch_pairing_coop_bls(const CoopArgs& a, rt_stream_t s);
-size_t coop_gscratch_bytes_bls(size_t n);
+// cooperative pairing kernel; gscratch must hold coop_gscratch_size<C>(n) bytes
+template <class C> int launch_pairing_coop(const CoopArgs& a, rt_stream_t s);
+template <class C> size_t coop_gscratch_size(size_t n);
 #endif
 template <class C> int launch_sign(const SignArgs& a, uint32_t n, rt_stream_t s);
 template <class C> int launch_proof_g1(const ProofG1Args& a, uint32_t n, rt_stream_t s);

@@ -43,6 +43,13 @@ struct CoopArgs {
 template <class C> struct Coop;
 template <> struct Coop<Bls> {
     static constexpr int N = 12;
+    static constexpr int RW = 12;              // words of a reduction result
+    static constexpr int MAXK = 8;             // largest canonicalisation step (multiples of p)
+    static constexpr int PARK = 1;             // Fp12 values a group parks in HBM (GSAVE / GLOAD slots)
+    static constexpr bool ACC_XI = false;      // xi = 1 + u: multiplication by xi is routed through the EP signs
+    static constexpr bool POINT_RATIO = false; // the item's points enter as (x, y)
+    static __device__ __forceinline__ void add_kp(uint32_t* acc, const uint32_t* k) { coop_acc_add_e12(acc, k); }
+    static __device__ __forceinline__ void xi(uint32_t*, uint32_t*) {}
     static __device__ __forceinline__ const uint32_t* prog() { return COOP_PROG_BLS; }
     static __device__ __forceinline__ const uint32_t* prog_off() { return COOP_PROG_OFF_BLS; }
     static __device__ __forceinline__ const uint32_t* consts() { return COOP_CONSTS_BLS; }
@@ -63,6 +70,56 @@ template <> struct Coop<Bls> {
         if (K == 4) return coop_sub_4p_bls(d, r);
         if (K == 2) return coop_sub_2p_bls(d, r);
         return coop_sub_1p_bls(d, r);
+    }
+};
+
+// BN254: 8 limbs, Montgomery radix 2^256 as everywhere else.  R - p leaves no head-room for lazy sums and xi = 9 + u is not
+// a sign choice, so (i) the accumulators use all 17 words, xi multiplies the ACCUMULATORS (instruction XI, after the
+// wrap-around products of a coefficient), (ii) the reduction returns 9 words (< 128 p) and canonicalises in up to 7 steps.
+template <> struct Coop<Bn> {
+    static constexpr int N = 8;
+    static constexpr int RW = 9;
+    static constexpr int MAXK = 64;
+    static constexpr int PARK = 3;
+    static constexpr bool ACC_XI = true;
+    static constexpr bool POINT_RATIO = true;  // D-type twist: the line is normalised by 1/y, the points enter as (x/y, 1/y)
+    static __device__ __forceinline__ const uint32_t* prog() { return COOP_PROG_BN; }
+    static __device__ __forceinline__ const uint32_t* prog_off() { return COOP_PROG_OFF_BN; }
+    static __device__ __forceinline__ const uint32_t* consts() { return COOP_CONSTS_BN; }
+    static __device__ __forceinline__ const uint32_t* kp() { return COOP_KP_BN; }
+    static __device__ __forceinline__ void wmul_e(uint32_t* w, const uint32_t* a, const uint32_t* b) { coop_wmul_e8(w, a, b); }
+    static __device__ __forceinline__ void wmul_o(uint32_t* w, const uint32_t* a, const uint32_t* b) { coop_wmul_o8(w, a, b); }
+    static __device__ __forceinline__ void merge(uint32_t* w, const uint32_t* v) { coop_merge8(w, v); }
+    static __device__ __forceinline__ void add_e(uint32_t* acc, const uint32_t* w) { coop_acc_add_e8(acc, w); }
+    static __device__ __forceinline__ void sub_e(uint32_t* acc, const uint32_t* w) { coop_acc_sub_e8(acc, w); }
+    static __device__ __forceinline__ void add_hi(uint32_t* acc, const uint32_t* z) { coop_acc_add_hi8(acc, z); }
+    static __device__ __forceinline__ void sub_hi(uint32_t* acc, const uint32_t* z) { coop_acc_sub_hi8(acc, z); }
+    static __device__ __forceinline__ void addn(uint32_t* d, const uint32_t* s) { coop_addn8(d, s); }
+    static __device__ __forceinline__ void subn(uint32_t* d, const uint32_t* s) { coop_subn8(d, s); }
+    static __device__ __forceinline__ void add_p(uint32_t* d) { coop_add_p_bn(d); }
+    static __device__ __forceinline__ void redc(uint32_t* r, uint32_t* t) { coop_redc_wide_bn(r, t); }
+    static __device__ __forceinline__ void add_kp(uint32_t* acc, const uint32_t* k) { coop_acc_add_f8(acc, k); }
+    template <int K> static __device__ __forceinline__ uint32_t sub_kp(uint32_t* d, const uint32_t* r) {
+        if (K == 64) return coop_sub_64p_bn9(d, r);
+        if (K == 32) return coop_sub_32p_bn9(d, r);
+        if (K == 16) return coop_sub_16p_bn9(d, r);
+        if (K == 8) return coop_sub_8p_bn9(d, r);
+        if (K == 4) return coop_sub_4p_bn9(d, r);
+        if (K == 2) return coop_sub_2p_bn9(d, r);
+        return coop_sub_1p_bn9(d, r);
+    }
+    // (R, I) <- xi (R, I) = (9R - I, 9I + R) on the 17-word two's-complement accumulators
+    static __device__ __forceinline__ void xi(uint32_t* R, uint32_t* I) {
+        uint32_t t[17], u[17];
+#pragma unroll
+        for (int i = 16; i > 0; i--) { t[i] = __funnelshift_l(R[i - 1], R[i], 3); u[i] = __funnelshift_l(I[i - 1], I[i], 3); }
+        t[0] = R[0] << 3; u[0] = I[0] << 3;
+        coop_acc_add_f8(t, R);
+        coop_acc_add_f8(u, I);
+        coop_acc_sub_f8(t, I);
+        coop_acc_add_f8(u, R);
+#pragma unroll
+        for (int i = 0; i < 17; i++) { R[i] = t[i]; I[i] = u[i]; }
     }
 };
 
@@ -137,27 +194,36 @@ template <class C> __device__ __forceinline__ void coop_finish2(uint32_t* r0, ui
         if ((ins >> 13) & 1) { coop_shl<N>(z0, 1); coop_shl<N>(z1, 1); }
         if (zs == 1) { Coop<C>::add_hi(R, z0); Coop<C>::add_hi(I, z1); } else { Coop<C>::sub_hi(R, z0); Coop<C>::sub_hi(I, z1); }
     }
-    const uint32_t kp = (ins >> 22) & 3;
+    const uint32_t kp = ((ins >> 22) & 3) | (((ins >> 31) & 1) << 2);
     if (kp) {
-        uint32_t k[2 * N];
+        uint32_t k[2 * N + 1];
         const uint32_t* kt = Coop<C>::kp() + kp * (2 * N + 1);
 #pragma unroll
-        for (int i = 0; i < 2 * N; i++) k[i] = kt[i];
-        Coop<C>::add_e(R, k);
-        Coop<C>::add_e(I, k);
+        for (int i = 0; i <= 2 * N; i++) k[i] = kt[i];
+        Coop<C>::add_kp(R, k);
+        Coop<C>::add_kp(I, k);
     }
-    Coop<C>::redc(r0, R);
-    Coop<C>::redc(r1, I);
-    const uint32_t canon = (ins >> 24) & 3;
-    uint32_t d0[N], d1[N], b0, b1;
+    constexpr int RW = Coop<C>::RW;
+    uint32_t w0[RW], w1[RW];
+    Coop<C>::redc(w0, R);
+    Coop<C>::redc(w1, I);
+    const uint32_t canon = ((ins >> 24) & 3) | (((ins >> 30) & 1) << 2);
+    uint32_t d0[RW], d1[RW], b0, b1;
 #define COOP_CANON_STEP(K)                                                                     \
-    b0 = Coop<C>::template sub_kp<K>(d0, r0); b1 = Coop<C>::template sub_kp<K>(d1, r1);         \
-    _Pragma("unroll") for (int i = 0; i < N; i++) { r0[i] = b0 ? r0[i] : d0[i]; r1[i] = b1 ? r1[i] : d1[i]; }
+    b0 = Coop<C>::template sub_kp<K>(d0, w0); b1 = Coop<C>::template sub_kp<K>(d1, w1);         \
+    _Pragma("unroll") for (int i = 0; i < RW; i++) { w0[i] = b0 ? w0[i] : d0[i]; w1[i] = b1 ? w1[i] : d1[i]; }
+    if constexpr (Coop<C>::MAXK >= 64) {
+        if (canon >= 6) { COOP_CANON_STEP(64) }
+        if (canon >= 5) { COOP_CANON_STEP(32) }
+        if (canon >= 4) { COOP_CANON_STEP(16) }
+    }
     if (canon >= 3) { COOP_CANON_STEP(8) }
     if (canon >= 2) { COOP_CANON_STEP(4) }
     if (canon >= 1) { COOP_CANON_STEP(2) }
     COOP_CANON_STEP(1)
 #undef COOP_CANON_STEP
+#pragma unroll
+    for (int i = 0; i < N; i++) { r0[i] = w0[i]; r1[i] = w1[i]; }
 }
 
 #ifndef BBS_COOP_MAXREG
@@ -196,6 +262,19 @@ __global__ void __maxnreg__(BBS_COOP_MAXREG) pairing_coop_kernel(const CoopArgs 
             for (int i = 0; i < N; i++) v[i] = valid ? src[i] : 0u;
             coop_store<N>(cells + (16 + (role >> 1)) * CELL + (role & 1) * Q * 32, v);
         }
+        if constexpr (Coop<C>::POINT_RATIO) {
+            // (x, y) -> (x / y, 1 / y), one point per role-warp (y != 0 on a curve of odd order; skipped pairs hold zeros)
+            COOP_BAR();
+            if (role < 2) {
+                uint32_t x[N], y[N], yi[N];
+                coop_load<N>(x, cells + (16 + role) * CELL);
+                coop_load<N>(y, cells + (16 + role) * CELL + Q * 32);
+                fe_inv<typename C::Fp>(yi, y);
+                fe_mul<typename C::Fp>(x, x, yi);
+                coop_store<N>(cells + (16 + role) * CELL, x);
+                coop_store<N>(cells + (16 + role) * CELL + Q * 32, yi);
+            }
+        }
     }
     COOP_BAR();
 
@@ -233,6 +312,9 @@ __global__ void __maxnreg__(BBS_COOP_MAXREG) pairing_coop_kernel(const CoopArgs 
             Coop<C>::merge(w, v);            // full product: one 2N-word addition per accumulator instead of two
             if (sR == 1) Coop<C>::add_e(R, w); else if (sR == 2) Coop<C>::sub_e(R, w);
             if (sI == 1) Coop<C>::add_e(I, w); else if (sI == 2) Coop<C>::sub_e(I, w);
+        } else if (kind == 3) {
+            // ---- XI: accumulators *= xi (curves whose xi is not a sign choice) ----------------------------------
+            if constexpr (Coop<C>::ACC_XI) Coop<C>::xi(R, I);
         } else if (kind == 1) {
             // ---- FIN -----------------------------------------------------------------------------------------
             uint32_t r0[N], r1[N];
@@ -261,8 +343,8 @@ __global__ void __maxnreg__(BBS_COOP_MAXREG) pairing_coop_kernel(const CoopArgs 
             else if (sub == 3) line++;                                     // NEXTLINE
             else if (sub == 4) COOP_BAR();                            // BAR
             else if (sub == 5 || sub == 6) {                               // GSAVE / GLOAD (own cell <-> global)
-                uint4* g = (uint4*)a.gscratch + ((size_t)gblock * COOP_ROLES + role) * CELL + lane;
-                uint4* c = cells + arg * CELL;
+                uint4* g = (uint4*)a.gscratch + (((size_t)gblock * Coop<C>::PARK + (arg >> 8)) * COOP_ROLES + role) * CELL + lane;
+                uint4* c = cells + (arg & 255) * CELL;
 #pragma unroll
                 for (int q = 0; q < 2 * Q; q++) { if (sub == 5) g[q * 32] = c[q * 32]; else c[q * 32] = g[q * 32]; }
             }
@@ -293,6 +375,10 @@ __global__ void __maxnreg__(BBS_COOP_MAXREG) pairing_coop_kernel(const CoopArgs 
     }
 }
 
+template <class C> constexpr size_t coop_gscratch_bytes(size_t n) {
+    const size_t per_block = (size_t)COOP_ITEMS * COOP_GROUPS;
+    return ((n + per_block - 1) / per_block) * COOP_GROUPS * Coop<C>::PARK * COOP_ROLES * (2 * (Coop<C>::N / 4) * 32) * sizeof(uint4);
+}
 template <class C> constexpr size_t coop_smem_bytes() {
     return COOP_GROUPS * ((size_t)COOP_CELLS * (2 * (Coop<C>::N / 4) * 32) * sizeof(uint4) + COOP_ROLES * 32 * sizeof(uint32_t));
 }

@@ -26,13 +26,17 @@ from fractions import Fraction
 ROLES = 6
 NCELLS = 24            # shared-memory cells per block (4 Fp12 values)
 
-K_EP, K_FIN, K_CTL = 0, 1, 2
+K_EP, K_FIN, K_CTL, K_XI = 0, 1, 2, 3
 C_END, C_REP, C_ENDREP, C_NEXTLINE, C_BAR, C_GSAVE, C_GLOAD, C_CHECK, C_INV = range(9)
 F_C0, F_C1, F_SUM, F_DIFF = range(4)
 FORM_BOUND = {F_C0: 1, F_C1: 1, F_SUM: 2, F_DIFF: 2}     # in units of p (cells are canonical)
 LINE_BASE = 128        # global-constant ids >= LINE_BASE address the line table relative to the line counter
-KP_MULT = (0, 8, 24, 40)         # KP[k] = KP_MULT[k] * p^2, added before REDC so the accumulator is >= 0
+KP_MULT = (0, 8, 24, 40)         # KP[k] = KP_MULT[k] * p^2, added before REDC so the accumulator is >= 0   (BLS12-381)
 CANON_STEPS = (1, 2, 3, 4)       # canon level l: output < 2^(l+1) p, conditional subtractions of 2^l p ... p
+# BN254: xi = 9 + u is applied to the ACCUMULATORS (instruction XI: (R, I) <- (9R - I, 9I + R)), so sums reach a few
+# hundred p^2; the reduction there returns N+1 limbs (< 128 p) and canonicalises in up to 7 steps
+KP_MULT_WIDE = (0, 8, 16, 32, 64, 128, 256, 512)
+CANON_STEPS_WIDE = (1, 2, 3, 4, 5, 6, 7)
 
 
 @dataclass
@@ -54,8 +58,9 @@ def enc_ep(sR, sI, x, y):
 def enc_fin(dst, triple=0, zsign=0, zdouble=0, zcell=0, kp=0, canon=3, bar=0, skip_pair=None, fp_only=0):
     zs = {0: 0, 1: 1, -1: 2}[zsign]
     sk = 0 if skip_pair is None else (1 | (skip_pair << 1))
-    return (K_FIN | (dst << 2) | (triple << 10) | (zs << 11) | (zdouble << 13) | (zcell << 14) | (kp << 22) |
-            (canon << 24) | (bar << 26) | (sk << 27) | (fp_only << 29))
+    assert kp < 8 and canon < 8
+    return (K_FIN | (dst << 2) | (triple << 10) | (zs << 11) | (zdouble << 13) | (zcell << 14) | ((kp & 3) << 22) |
+            ((canon & 3) << 24) | (bar << 26) | (sk << 27) | (fp_only << 29) | ((canon >> 2) << 30) | ((kp >> 2) << 31))
 
 
 def enc_ctl(sub, arg=0):
@@ -71,9 +76,12 @@ def dec(word):
                 Operand((word >> 18) & 255, (word >> 26) & 3, (word >> 28) & 3, bool((word >> 30) & 1)))
     if kind == K_FIN:
         return ("FIN", dict(dst=(word >> 2) & 255, triple=(word >> 10) & 1, zsign=sg[(word >> 11) & 3],
-                            zdouble=(word >> 13) & 1, zcell=(word >> 14) & 255, kp=(word >> 22) & 3,
-                            canon=(word >> 24) & 3, bar=(word >> 26) & 1, skip=(word >> 27) & 3,
-                            fp_only=(word >> 29) & 1))
+                            zdouble=(word >> 13) & 1, zcell=(word >> 14) & 255,
+                            kp=((word >> 22) & 3) | (((word >> 31) & 1) << 2),
+                            canon=((word >> 24) & 3) | (((word >> 30) & 1) << 2), bar=(word >> 26) & 1,
+                            skip=(word >> 27) & 3, fp_only=(word >> 29) & 1))
+    if kind == K_XI:
+        return ("XI",)
     return ("CTL", (word >> 2) & 15, word >> 6)
 
 
@@ -83,10 +91,27 @@ class Curve:
     p: int
     n_limbs: int
     xi_c: int        # xi = xi_c + u
+    twist: str = "M"     # M: line = 1 + l2 w^2 + l3 w^3 ; D: line = 1 + l1 w + l3 w^3  (normalised, see coop_consts.py)
+    wide: bool = False   # reduction returns N+1 limbs (R - p is too small a head-room for lazy sums: BN254)
 
     @property
     def R(self):
         return 1 << (32 * self.n_limbs)
+
+    @property
+    def kp_mult(self):
+        return KP_MULT_WIDE if self.wide else KP_MULT
+
+    @property
+    def canon_steps(self):
+        return CANON_STEPS_WIDE if self.wide else CANON_STEPS
+
+    @property
+    def acc_limit(self):
+        """accumulator bound at REDC time, in units of p^2"""
+        if self.wide:         # REDC output < T/R + p must stay below 2^max_step p
+            return Fraction(((1 << self.canon_steps[-1]) - 1) * self.R, self.p)
+        return Fraction((self.R - self.p) * self.R, self.p * self.p)
 
 
 class ProgramError(Exception):
@@ -99,7 +124,7 @@ class Builder:
     def __init__(self, curve):
         self.cv = curve
         self.streams = [[] for _ in range(ROLES)]
-        self.max_t = Fraction((curve.R - curve.p) * curve.R, curve.p * curve.p)     # accumulator limit in p^2
+        self.max_t = curve.acc_limit                                                # accumulator limit in p^2
         self.work = {"ep": [0] * ROLES, "fin": [0] * ROLES, "bar": 0}
         self._mult = [1]
 
@@ -134,17 +159,26 @@ class Builder:
                 continue
             pos = {"R": Fraction(0), "I": Fraction(0)}
             neg = {"R": Fraction(0), "I": Fraction(0)}
-            for (sR, sI, x, y) in d["eps"]:
-                bx, by = FORM_BOUND[x.form] << x.shift, FORM_BOUND[y.form] << y.shift
-                if max(bx, by) * self.cv.p >= self.cv.R:
-                    raise ProgramError("operand overflows the limb array")
-                for acc, s in (("R", sR), ("I", sI)):
-                    if s > 0:
-                        pos[acc] += bx * by
-                    elif s < 0:
-                        neg[acc] += bx * by
-                self.streams[r].append(enc_ep(sR, sI, x, y))
-                self.work["ep"][r] += self._mult[-1]
+            groups = [(d.get("eps_xi") or [], True), (d["eps"], False)]
+            for eps, is_xi in groups:
+                for (sR, sI, x, y) in eps:
+                    bx, by = FORM_BOUND[x.form] << x.shift, FORM_BOUND[y.form] << y.shift
+                    if max(bx, by) * self.cv.p >= self.cv.R:
+                        raise ProgramError("operand overflows the limb array")
+                    for acc, s in (("R", sR), ("I", sI)):
+                        if s > 0:
+                            pos[acc] += bx * by
+                        elif s < 0:
+                            neg[acc] += bx * by
+                    self.streams[r].append(enc_ep(sR, sI, x, y))
+                    self.work["ep"][r] += self._mult[-1]
+                if is_xi and eps:
+                    # (R, I) <- (c R - I, c I + R)
+                    c = self.cv.xi_c
+                    pos, neg = ({"R": c * pos["R"] + neg["I"], "I": c * pos["I"] + pos["R"]},
+                                {"R": c * neg["R"] + pos["I"], "I": c * neg["I"] + neg["R"]})
+                    self.streams[r].append(K_XI)
+                    self.work["xi"] = self.work.get("xi", 0) + self._mult[-1]
             tr = 3 if d.get("triple") else 1
             z = d.get("z")
             zpos = zneg = Fraction(0)
@@ -156,14 +190,15 @@ class Builder:
                     zneg = zb
             worst_neg = max(neg["R"], neg["I"]) * tr + zneg
             worst_pos = max(pos["R"], pos["I"]) * tr + zpos
-            kp = next((i for i, m in enumerate(KP_MULT) if m >= worst_neg), None)
+            KPM, CST = self.cv.kp_mult, self.cv.canon_steps
+            kp = next((i for i, m in enumerate(KPM) if m >= worst_neg), None)
             if kp is None:
                 raise ProgramError(f"negative part {float(worst_neg):.1f} p^2 exceeds the KP table")
-            total = worst_pos + KP_MULT[kp]
+            total = worst_pos + KPM[kp]
             if total >= self.max_t:
                 raise ProgramError(f"accumulator bound {float(total):.1f} p^2 >= limit {float(self.max_t):.1f}")
             out_bound = total * pu + 1          # REDC output < T/R + p, in units of p
-            canon = next((i for i, st in enumerate(CANON_STEPS) if (1 << st) >= out_bound), None)
+            canon = next((i for i, st in enumerate(CST) if (1 << st) >= out_bound), None)
             if canon is None:
                 raise ProgramError("output bound too large to canonicalise")
             self.streams[r].append(enc_fin(d["dst"], triple=1 if d.get("triple") else 0, zsign=z[0] if z else 0,
@@ -256,15 +291,34 @@ class PairingProgram:
     LINE_CELLS = (12, 13, 14, 15)      # pair 0: l2, l3 ; pair 1: l2, l3
     P_CELLS = (16, 17)
 
-    def __init__(self, curve, ate_abs, const_index, inv_exp):
+    def __init__(self, curve, ate_abs, const_index, inv_exp, miller_digits=None, miller_tail=0):
+        """ate_abs: |x| (BLS12: also the Miller loop count; BN: the exponent t of the hard part).  miller_digits: string
+        over '0'/'1' below the leading digit of the loop count, '1' = an addition step follows the doubling step
+        (default: the bits of ate_abs); miller_tail: extra addition steps after the loop (BN: pi(Q), -pi^2(Q))."""
         self.cv = curve
         self.b = Builder(curve)
         self.ate_bits = bin(ate_abs)[3:]
+        self.miller_digits = miller_digits if miller_digits is not None else self.ate_bits
+        self.miller_tail = miller_tail
         self.ate_abs = ate_abs
         self.ci = const_index      # name -> global constant id (< LINE_BASE)
         self.inv_exp = inv_exp     # p - 2
         self.free = []
-        assert curve.xi_c == 1, "xi = c + u with c != 1 needs pre-multiplied operand forms (not implemented)"
+        self.acc_xi = curve.xi_c != 1      # xi applied to the accumulators (XI) instead of by sign routing
+        self.line_exps = (2, 3) if curve.twist == "M" else (1, 3)
+
+    # -- EP emission with the two ways of multiplying by xi -----------------------------------------------------
+    def _put(self, d, eps_fn, xi, **kw):
+        if xi and self.acc_xi:
+            d.setdefault("eps_xi", []).extend(eps_fn(xi=False, **kw))
+        else:
+            d.setdefault("eps", []).extend(eps_fn(xi=xi, **kw))
+
+    def fmul(self, d, xc, yc, sign=1, xi=False, **kw):
+        self._put(d, lambda xi, **k: fp2_mul_eps(xc, yc, sign=sign, xi=xi, **k), xi, **kw)
+
+    def fsqr(self, d, xc, sign=1, xi=False):
+        self._put(d, lambda xi: fp2_sqr_eps(xc, sign=sign, xi=xi), xi)
 
     # -- Fp12 ops --------------------------------------------------------------------------------------------
     def mul(self, dst, A, B, roles=range(ROLES), bar=True, b_coeffs=range(ROLES)):
@@ -275,27 +329,27 @@ class PairingProgram:
             out_conj, sa, sb = False, A.sgn, B.sgn
         per = {}
         for k in roles:
-            eps = []
+            d = dict(dst=dst + k, eps=[])
             for j in b_coeffs:
                 i = (k - j) % 6
-                eps += fp2_mul_eps(A.cell(i), B.cell(j), sign=sa(i) * sb(j), xi=(i + j >= 6))
-            per[k] = dict(dst=dst + k, eps=eps)
+                self.fmul(d, A.cell(i), B.cell(j), sign=sa(i) * sb(j), xi=(i + j >= 6))
+            per[k] = d
         self.b.op(per, bar=bar)
         return V12(dst, out_conj)
 
     def sqr(self, dst, A, extra=None):
         per = {}
         for k in range(ROLES):
-            eps = []
+            d = dict(dst=dst + k, eps=[])
             for i in range(6):
                 j = (k - i) % 6
                 if i > j:
                     continue
                 if i == j:
-                    eps += fp2_sqr_eps(A.cell(i), xi=(i + j >= 6))
+                    self.fsqr(d, A.cell(i), xi=(i + j >= 6))
                 else:
-                    eps += fp2_mul_eps(A.cell(i), A.cell(j), sign=2, xi=(i + j >= 6))
-            per[k] = dict(dst=dst + k, eps=eps)
+                    self.fmul(d, A.cell(i), A.cell(j), sign=2, xi=(i + j >= 6))
+            per[k] = d
         if extra:
             self.b.op(per, bar=False)
             self.b.op(extra, bar=True)
@@ -304,15 +358,16 @@ class PairingProgram:
         return V12(dst, A.conj)
 
     def sparse(self, dst, F, l2c, l3c):
-        """F * (1 + l2 w^2 + l3 w^3), l2 / l3 = line cells (M-type twist, line normalised to constant term 1)."""
+        """F * (1 + la w^a + lb w^b), la / lb = line cells, (a, b) = (2, 3) on an M-type twist, (1, 3) on a D-type
+        twist (line normalised to constant term 1)."""
         assert not F.conj
         per = {}
         for k in range(ROLES):
-            eps = []
-            for (j, lc) in ((2, l2c), (3, l3c)):
+            d = dict(dst=dst + k, eps=[], z=(1, 0, F.cell(k)))
+            for (j, lc) in ((self.line_exps[0], l2c), (self.line_exps[1], l3c)):
                 i = (k - j) % 6
-                eps += fp2_mul_eps(F.cell(i), lc, xi=(i + j >= 6))
-            per[k] = dict(dst=dst + k, eps=eps, z=(1, 0, F.cell(k)))
+                self.fmul(d, F.cell(i), lc, xi=(i + j >= 6))
+            per[k] = d
         self.b.op(per)
         return V12(dst)
 
@@ -335,9 +390,13 @@ class PairingProgram:
         per = {}
         for k, (kind, x, y, xi) in plan.items():
             if kind == "A":      # 3 (x^2 + xi y^2) - 2 g_k
-                per[k] = dict(dst=dst + k, eps=fp2_sqr_eps(x) + fp2_sqr_eps(y, xi=True), triple=True, z=(-1, 1, g(k)))
+                d = dict(dst=dst + k, eps=[], triple=True, z=(-1, 1, g(k)))
+                self.fsqr(d, x)
+                self.fsqr(d, y, xi=True)
             else:                # 3 [xi] (2 x y) + 2 g_k
-                per[k] = dict(dst=dst + k, eps=fp2_mul_eps(x, y, sign=2, xi=xi), triple=True, z=(1, 1, g(k)))
+                d = dict(dst=dst + k, eps=[], triple=True, z=(1, 1, g(k)))
+                self.fmul(d, x, y, sign=2, xi=xi)
+            per[k] = d
         self.b.op(per)
         return V12(dst, A.conj)
 
@@ -378,7 +437,7 @@ class PairingProgram:
             b.ctl_all(C_NEXTLINE)
             mul_lines()
 
-        bits = self.ate_bits
+        bits = self.miller_digits
         add_step()                       # f = 1 before the first doubling: its squaring is skipped
         if bits[0] == "1":
             add_step()
@@ -401,6 +460,8 @@ class PairingProgram:
             if bits[i] == "1":
                 add_step()
             i += 1
+        for _ in range(self.miller_tail):
+            add_step()
         return st["f"]
 
     # -- final exponentiation ------------------------------------------------------------------------------------
@@ -456,14 +517,17 @@ class PairingProgram:
         n = self.mul(sn, f, conj(f), roles=(0, 2, 4))              # N = f conj(f) in Fp6: n0, n1, n2 at w^0, w^2, w^4
         n0, n1, n2 = sn, sn + 2, sn + 4
         t0, t1, t2 = sn + 1, sn + 3, sn + 5
-        b.op({0: dict(dst=t0, eps=fp2_sqr_eps(n0) + fp2_mul_eps(n1, n2, sign=-1, xi=True)),
-              1: dict(dst=t1, eps=fp2_sqr_eps(n2, xi=True) + fp2_mul_eps(n0, n1, sign=-1)),
-              2: dict(dst=t2, eps=fp2_sqr_eps(n1) + fp2_mul_eps(n0, n2, sign=-1))})
+        d0, d1, d2 = dict(dst=t0, eps=[]), dict(dst=t1, eps=[]), dict(dst=t2, eps=[])
+        self.fsqr(d0, n0); self.fmul(d0, n1, n2, sign=-1, xi=True)
+        self.fsqr(d1, n2, xi=True); self.fmul(d1, n0, n1, sign=-1)
+        self.fsqr(d2, n1); self.fmul(d2, n0, n2, sign=-1)
+        b.op({0: d0, 1: d1, 2: d2})
         sx = self.take(f, V12(sn))
         sy = self.take(f, V12(sn), V12(sx))
         D, DN, DI = sx, sx + 1, sx + 3
-        b.op({0: dict(dst=D, eps=fp2_mul_eps(n0, t0) + fp2_mul_eps(n2, t1, xi=True) + fp2_mul_eps(n1, t2, xi=True))},
-             bar=False)
+        dd = dict(dst=D, eps=[])
+        self.fmul(dd, n0, t0); self.fmul(dd, n2, t1, xi=True); self.fmul(dd, n1, t2, xi=True)
+        b.op({0: dd}, bar=False)
         b.op({0: dict(dst=DN, eps=[(1, 0, Operand(D, F_C0), Operand(D, F_C0)), (1, 0, Operand(D, F_C1), Operand(D, F_C1))],
                       fp_only=True)}, bar=False)
         self.fp_inverse(DN)
@@ -476,6 +540,55 @@ class PairingProgram:
         g = self.mul(sx, conj(f), h)
         g2 = self.frob(self.take(g), g, 2)
         e = self.mul(self.take(g, g2), g2, g)
+        r = self.hard_bn(e) if self.cv.twist == "D" else self.hard_bls12(e)
+        b.ctl_roles(C_CHECK, [r.cell(k) for k in range(ROLES)])
+        return r
+
+    def gsave(self, v, slot=0):
+        self.b.ctl_roles(C_GSAVE, [v.cell(k) | (slot << 8) for k in range(ROLES)])
+
+    def gload(self, base, slot=0, conj_flag=False):
+        self.b.ctl_roles(C_GLOAD, [(base + k) | (slot << 8) for k in range(ROLES)])
+        self.b.ctl_all(C_BAR)
+        return V12(base, conj_flag)
+
+    def hard_bn(self, f):
+        """BN, x = t > 0: the Fuentes-Castaneda et al. chain (pairing.cuh final_exp_hard<Bn>, the one ark-ec's bn model
+        uses): f^(t-exponents) with three parked values (f, y1, y3) so that four resident slots suffice."""
+        assert not f.conj
+        self.gsave(f, 0)
+        t = self.pow_abs_x(f)
+        y0 = conj(t)
+        y1 = self.cyc_sqr(self.take(f, y0), y0)
+        y2 = self.cyc_sqr(self.take(f, y1), y1)
+        y3 = self.mul(self.take(f, y1, y2), y2, y1)
+        self.gsave(y1, 1)                        # (the conj flag of a parked value is carried by the program, see gload)
+        y1_conj = y1.conj
+        t = self.pow_abs_x(y3)
+        y4 = conj(t)
+        y5 = self.cyc_sqr(self.take(y3, y4), y4)
+        self.gsave(y3, 2)
+        y3_conj = y3.conj
+        t = self.pow_abs_x(y5, keep=(y4,))
+        y6 = conj(t)
+        y7 = self.mul(self.take(y4, y6), conj(y6), y4)
+        y3 = self.gload(self.take(y4, y7), 2, y3_conj)
+        y8 = self.mul(self.take(y4, y7, y3), y7, conj(y3))
+        y1 = self.gload(self.take(y4, y8), 1, y1_conj)
+        y9 = self.mul(self.take(y4, y8, y1), y8, y1)
+        y10 = self.mul(self.take(y4, y8, y9), y8, y4)
+        y8f = self.frob(self.take(y8, y9, y10), y8, 2)
+        a = self.mul(self.take(y8f, y9, y10), y8f, y10)
+        f = self.gload(self.take(a, y9), 0)
+        bb = self.mul(self.take(a, y9, f), a, f)
+        c = self.mul(self.take(bb, y9, f), conj(f), y9)
+        y12 = self.frob(self.take(bb, c, y9), y9, 1)
+        dd = self.mul(self.take(bb, c, y12), y12, bb)
+        y15 = self.frob(self.take(c, dd), c, 3)
+        return self.mul(self.take(y15, dd), y15, dd)
+
+    def hard_bls12(self, e):
+        b = self.b
         # ---- hard part (BLS12, x < 0):  3 (p^4 - p^2 + 1) / r = (x-1)^2 (x+p) (x^2+p^2-1) + 3 ---------------------
         b.ctl_roles(C_GSAVE, [e.cell(k) for k in range(ROLES)])
         t = self.pow_abs_x(e)
@@ -497,9 +610,7 @@ class PairingProgram:
         e = V12(s)
         e2 = self.cyc_sqr(self.take(a, e), e)
         e3 = self.mul(self.take(a, e, e2), e2, e)
-        r = self.mul(self.take(a, e3), a, e3)
-        b.ctl_roles(C_CHECK, [r.cell(k) for k in range(ROLES)])
-        return r
+        return self.mul(self.take(a, e3), a, e3)
 
     def build(self):
         f = self.miller()
@@ -521,7 +632,7 @@ class Emulator:
         self.lines = [[(self.mont(c[0]), self.mont(c[1])) for c in ln] for ln in lines]
         self.cells = {}
         self.gscratch = {}
-        self.kp = [m * p * p for m in KP_MULT]
+        self.kp = [m * p * p for m in curve.kp_mult]
         self.max_out = 0
         self.n_intervals = 0
 
@@ -547,7 +658,7 @@ class Emulator:
 
     def _redc(self, T):
         p, R = self.cv.p, self.cv.R
-        assert 0 <= T < (R - p) * R, "accumulator out of range"
+        assert 0 <= T < self.cv.acc_limit * p * p, "accumulator out of range"
         m = (-T * pow(p, -1, R)) % R
         return (T + m * p) // R
 
@@ -569,6 +680,11 @@ class Emulator:
                         pr = self._operand(x, s["line"], reads[r]) * self._operand(y, s["line"], reads[r])
                         s["R"] += sR * pr
                         s["I"] += sI * pr
+                    elif ins[0] == "XI":
+                        c = self.cv.xi_c
+                        s["R"], s["I"] = c * s["R"] - s["I"], c * s["I"] + s["R"]
+                        lim = 1 << (32 * (2 * self.cv.n_limbs + 1) - 1)
+                        assert -lim <= s["R"] < lim and -lim <= s["I"] < lim
                     elif ins[0] == "FIN":
                         d = ins[1]
                         out = []
@@ -585,7 +701,7 @@ class Emulator:
                                 T += d["zsign"] * (z[comp] << d["zdouble"]) * R
                             T += self.kp[d["kp"]]
                             o = self._redc(T)
-                            lim = (1 << CANON_STEPS[d["canon"]]) * p
+                            lim = (1 << self.cv.canon_steps[d["canon"]]) * p
                             assert o < lim, "canonicalisation depth too small"
                             self.max_out = max(self.max_out, o / p)
                             out.append(o % p)
@@ -613,11 +729,11 @@ class Emulator:
                         elif sub == C_BAR:
                             break
                         elif sub == C_GSAVE:
-                            self.gscratch[r] = self.cells[arg]
-                            reads[r].add(arg)
+                            self.gscratch[(r, arg >> 8)] = self.cells[arg & 255]
+                            reads[r].add(arg & 255)
                         elif sub == C_GLOAD:
-                            self.cells[arg] = self.gscratch[r]
-                            writes[r].add(arg)
+                            self.cells[arg & 255] = self.gscratch[(r, arg >> 8)]
+                            writes[r].add(arg & 255)
                         elif sub == C_INV:
                             v = self.cells[arg]
                             reads[r].add(arg)

@@ -253,7 +253,7 @@ def check_merge(n, trials=200):
 
 def check_addsub():
     rnd = random.Random(7)
-    for n, ns in ((25, 24), (25, 23), (17, 16), (13, 12), (9, 8)):
+    for n, ns in ((25, 24), (25, 23), (17, 16), (17, 17), (13, 12), (9, 8)):
         for sub in (False, True):
             dst = [f"d{i}" for i in range(n)]
             src = [f"s{i}" for i in range(ns)]
@@ -332,6 +332,40 @@ def redc_prog(n, p):
     return P
 
 
+def redc_wide_prog(n, p):
+    """redc_prog for accumulators that use the top word t_{2n}: the result has n + 1 words, r < T / R + p."""
+    P = redc_prog(n, p)
+    # drop the two final n-word additions and redo them with a carry word
+    final2 = P.stmts[-2:]
+    P.stmts = P.stmts[:-2]
+    O = P.result
+    Esrc = [op[3] for op in final2[0]]
+    ops = [("add.cc" if j == 0 else "addc.cc", O[j], O[j], Esrc[j]) for j in range(n)]
+    ops.append(("addc", "x1", 0, 0))
+    P.stmt(ops)
+    ops = [("add.cc" if j == 0 else "addc.cc", O[j], O[j], f"t{n + j}") for j in range(n)]
+    ops.append(("addc", "x1", "x1", f"t{2 * n}"))
+    P.stmt(ops)
+    P.result = list(O) + ["x1"]
+    return P
+
+
+def check_redc_wide(n, p, limit_p2, trials=300):
+    R = 1 << (32 * n)
+    rnd = random.Random(900 + n)
+    P = redc_wide_prog(n, p)
+    lim = limit_p2 * p * p
+    assert lim < 1 << (32 * (2 * n + 1))
+    for t in range(trials):
+        T = [0, lim - 1, R - 1, p * p * 12][t] if t < 4 else rnd.randrange(lim)
+        env = {"m": 0}
+        for i in range(2 * n + 1):
+            env[f"t{i}"] = limbs(T, 2 * n + 1)[i]
+        P.run(env)
+        r = sum(env[v] << (32 * j) for j, v in enumerate(P.result))
+        assert (r * R - T) % p == 0 and r < T // R + p + 1, (n, t)
+
+
 def check_redc(n, p, trials=300):
     R = 1 << (32 * n)
     rnd = random.Random(200 + n)
@@ -353,7 +387,7 @@ def arr(mapping):
         for prefix, expr in mapping:
             if v.startswith(prefix) and v[len(prefix):].isdigit():
                 return expr % int(v[len(prefix):])
-        if v in ("m", "cy", "x0", "ext"):
+        if v in ("m", "cy", "x0", "x1", "ext"):
             return v
         raise KeyError(v)
     return f
@@ -434,6 +468,48 @@ def emit_all():
             s.append(P.emit(arr([("d", "d[%d]"), ("r", "r[%d]")])))
             s.append("    return cy;")
             s.append("}\n")
+        if cname == "bn":
+            # wide variant: accumulators use all 2n+1 words (xi = 9 + u is applied to them), the reduction returns n+1 words
+            prog = redc_wide_prog(n, p)
+            s.append(f"// r[0..{n}] = (t + M p) / 2^{32 * n} for t[0..{2 * n}] (destroyed): r < t / 2^{32 * n} + p")
+            s.append(f"__device__ __forceinline__ void coop_redc_wide_{cname}(uint32_t* r, uint32_t* t) {{")
+            s.append(f"    uint32_t o[{n}], m, x0, x1;")
+            amap = arr([("t", "t[%d]"), ("o", "o[%d]")])
+            s.append(prog.emit(amap))
+            s.append("    " + " ".join(f"r[{j}] = {amap(v)};" for j, v in enumerate(prog.result)))
+            s.append("}\n")
+            for K in (1, 2, 4, 8, 16, 32, 64):
+                kp = limbs(K * p, n + 1)
+                P = Prog()
+                P.wrap_ok = {"cy"}
+                ops = [("sub.cc" if j == 0 else "subc.cc", f"d{j}", f"r{j}", kp[j]) for j in range(n + 1)]
+                ops.append(("subc", "cy", 0, 0))
+                P.stmt(ops)
+                rnd = random.Random(K + 50)
+                R9 = 1 << (32 * (n + 1))
+                for t in range(100):
+                    r = rnd.randrange(128 * p)
+                    env = {"cy": 0}
+                    for j in range(n + 1):
+                        env[f"r{j}"] = limbs(r, n + 1)[j]
+                    P.run(env)
+                    assert from_limbs(env, "d", n + 1) == (r - K * p) % R9 and env["cy"] == (MASK if r < K * p else 0)
+                s.append(f"// d = r - {K}p on {n + 1} words; returns 0xffffffff when r < {K}p (borrow)")
+                s.append(f"__device__ __forceinline__ uint32_t coop_sub_{K}p_{cname}{n + 1}(uint32_t* d, const uint32_t* r) {{")
+                s.append("    uint32_t cy = 0; (void)cy;")
+                s.append(P.emit(arr([("d", "d[%d]"), ("r", "r[%d]")])))
+                s.append("    return cy;")
+                s.append("}\n")
+            for sub in (False, True):
+                dst = [f"d{i}" for i in range(2 * n + 1)]
+                src = [f"s{i}" for i in range(2 * n + 1)]
+                prog = addsub_prog(dst, src, sub)
+                op = "sub" if sub else "add"
+                s.append(f"// acc[0..{2 * n}] {'-' if sub else '+'}= w[0..{2 * n}] (two's complement, wraps at the top)")
+                s.append(f"__device__ __forceinline__ void coop_acc_{op}_f{n}(uint32_t* acc, const uint32_t* w) {{")
+                s.append("    uint32_t cy = 0; (void)cy;")
+                s.append(prog.emit(arr([("d", "acc[%d]"), ("s", "w[%d]")])))
+                s.append("}\n")
         # r += p (for the difference form c0 - c1 + p)
         P = Prog()
         pl = limbs(p, n)
@@ -456,6 +532,7 @@ def main():
         check_merge(n)
     for cname, (n, p) in CURVES.items():
         check_redc(n, p)
+    check_redc_wide(8, P_BN, 127 * (1 << 256) // P_BN)
     txt = emit_all()
     with open(OUT, "w") as f:
         f.write(txt)
