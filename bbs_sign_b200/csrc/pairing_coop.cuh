@@ -24,11 +24,21 @@ namespace bbs {
 constexpr int COOP_ROLES = 6;
 constexpr int COOP_ITEMS = 32;                 // items per block = lanes
 constexpr int COOP_CELLS = 24;
-#ifndef BBS_COOP_GROUPS
-#define BBS_COOP_GROUPS 2                      // independent 32-item groups per block (each with its own named barrier)
+// occupancy knobs per curve (-D overridable): independent 32-item groups per block (each with its own named barrier) and
+// the register cap.  BLS12-381: 2 groups (73 KB of cells each), 128 registers.  BN254: 4 groups (49 KB each), 80 registers:
+// its EPs are short (64 products), so twice the warps hide more of the shared-memory and barrier latency (measured).
+#ifndef BBS_COOP_GROUPS_BLS
+#define BBS_COOP_GROUPS_BLS 2
 #endif
-constexpr int COOP_GROUPS = BBS_COOP_GROUPS;
-constexpr int COOP_TPB = COOP_ROLES * 32 * COOP_GROUPS;
+#ifndef BBS_COOP_GROUPS_BN
+#define BBS_COOP_GROUPS_BN 4
+#endif
+#ifndef BBS_COOP_MAXREG_BLS
+#define BBS_COOP_MAXREG_BLS 128
+#endif
+#ifndef BBS_COOP_MAXREG_BN
+#define BBS_COOP_MAXREG_BN 80
+#endif
 
 struct CoopArgs {
     const uint32_t* lines;     // per ate line: B'0, A'0, B'1, A'1 (Fp2 each, Montgomery): 8N words
@@ -43,6 +53,8 @@ struct CoopArgs {
 template <class C> struct Coop;
 template <> struct Coop<Bls> {
     static constexpr int N = 12;
+    static constexpr int GROUPS = BBS_COOP_GROUPS_BLS;
+    static constexpr int MAXREG = BBS_COOP_MAXREG_BLS;
     static constexpr int RW = 12;              // words of a reduction result
     static constexpr int MAXK = 8;             // largest canonicalisation step (multiples of p)
     static constexpr int PARK = 1;             // Fp12 values a group parks in HBM (GSAVE / GLOAD slots)
@@ -78,6 +90,8 @@ template <> struct Coop<Bls> {
 // wrap-around products of a coefficient), (ii) the reduction returns 9 words (< 128 p) and canonicalises in up to 7 steps.
 template <> struct Coop<Bn> {
     static constexpr int N = 8;
+    static constexpr int GROUPS = BBS_COOP_GROUPS_BN;
+    static constexpr int MAXREG = BBS_COOP_MAXREG_BN;
     static constexpr int RW = 9;
     static constexpr int MAXK = 64;
     static constexpr int PARK = 3;
@@ -226,12 +240,9 @@ template <class C> __device__ __forceinline__ void coop_finish2(uint32_t* r0, ui
     for (int i = 0; i < N; i++) { r0[i] = w0[i]; r1[i] = w1[i]; }
 }
 
-#ifndef BBS_COOP_MAXREG
-#define BBS_COOP_MAXREG 128
-#endif
-
 template <class C>
-__global__ void __maxnreg__(BBS_COOP_MAXREG) pairing_coop_kernel(const CoopArgs a) {
+__global__ void __maxnreg__(Coop<C>::MAXREG) pairing_coop_kernel(const CoopArgs a) {
+    constexpr int COOP_GROUPS = Coop<C>::GROUPS;
     constexpr int N = Coop<C>::N;
     constexpr int Q = N / 4;
     constexpr int CELL = 2 * Q * 32;           // uint4 per cell
@@ -376,11 +387,12 @@ __global__ void __maxnreg__(BBS_COOP_MAXREG) pairing_coop_kernel(const CoopArgs 
 }
 
 template <class C> constexpr size_t coop_gscratch_bytes(size_t n) {
+    constexpr int COOP_GROUPS = Coop<C>::GROUPS;
     const size_t per_block = (size_t)COOP_ITEMS * COOP_GROUPS;
     return ((n + per_block - 1) / per_block) * COOP_GROUPS * Coop<C>::PARK * COOP_ROLES * (2 * (Coop<C>::N / 4) * 32) * sizeof(uint4);
 }
 template <class C> constexpr size_t coop_smem_bytes() {
-    return COOP_GROUPS * ((size_t)COOP_CELLS * (2 * (Coop<C>::N / 4) * 32) * sizeof(uint4) + COOP_ROLES * 32 * sizeof(uint32_t));
+    return Coop<C>::GROUPS * ((size_t)COOP_CELLS * (2 * (Coop<C>::N / 4) * 32) * sizeof(uint4) + COOP_ROLES * 32 * sizeof(uint32_t));
 }
 
 }  // namespace bbs

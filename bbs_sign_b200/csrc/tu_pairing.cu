@@ -23,8 +23,8 @@ template <class C> int launch_pairing_coop(const CoopArgs& a, rt_stream_t s) {
     constexpr size_t smem = coop_smem_bytes<C>();
     RT_CHECK(cudaFuncSetAttribute(pairing_coop_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RT_CHECK(cudaFuncSetAttribute(pairing_coop_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    const uint32_t per_block = COOP_ITEMS * COOP_GROUPS;
-    pairing_coop_kernel<C><<<(a.n + per_block - 1) / per_block, COOP_TPB, smem, s>>>(a);
+    const uint32_t per_block = COOP_ITEMS * Coop<C>::GROUPS;
+    pairing_coop_kernel<C><<<(a.n + per_block - 1) / per_block, COOP_ROLES * 32 * Coop<C>::GROUPS, smem, s>>>(a);
     RT_CHECK(cudaGetLastError());
     return 0;
 }

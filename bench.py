@@ -454,7 +454,7 @@ def run_bn254(args):
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(t.item()) / args.steps * 1e3,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
                "config": {"workload": f"BN254 core_verify: {n} signatures x L=31 pre-hashed scalar messages, one issuer key, "
-                                      "1/16 corrupted (BASELINE configs[2] shape); per-thread pairing kernel", "n_per_gpu": n},
+                                      "1/16 corrupted (BASELINE configs[2] shape); cooperative pairing kernel", "n_per_gpu": n},
                "kernels_ms": {"verify_g1": float(kt[1]), "pairing": float(kt[2])}, "gpu_launches": 2}
     if world > 1:
         dist.barrier()
