@@ -1,5 +1,6 @@
 """Multi-GPU sharding of a batch by signature index: contiguous split, one context and one
-host thread per GPU, statuses written straight into the caller's slice, no collective on the data path."""
+host thread per GPU, statuses written straight into the caller's slice, no collective on the data path.
+MultiIssuerVerifier: batches whose items name different issuer keys, grouped per key."""
 from __future__ import annotations
 
 import threading
@@ -96,3 +97,63 @@ class ShardedVerifier:
     def close(self):
         for c in self.ctxs:
             c.close()
+
+
+class MultiIssuerVerifier:
+    """Batches with a public key PER ITEM ("multi-issuer batches").  Everything that is per issuer in
+    the reference call -- `self.pk`, the generators, `calculate_domain` (verify.rs:53-79) -- lives in a BatchContext; this
+    helper keeps one context per distinct key (built on first use, spread round-robin over `devices`), groups the items
+    of a batch by key, runs every group through its context on its own host thread and scatters the statuses back to the
+    callers' order.  Per item the result is exactly `PublicKey::verify` under that item's key."""
+
+    def __init__(self, suite: Ciphersuite, header: bytes, n_messages: int, devices: Sequence[int] = (0,),
+                 lib_path: Optional[str] = None):
+        self.suite, self.header, self.n_messages = suite, header, n_messages
+        self.devices, self.lib_path = list(devices), lib_path
+        self.ctxs: dict = {}
+
+    def context(self, pk: bytes) -> BatchContext:
+        pk = bytes(pk)
+        if pk not in self.ctxs:
+            dev = self.devices[len(self.ctxs) % len(self.devices)]
+            self.ctxs[pk] = BatchContext(self.suite, pk, self.header, self.n_messages, device=dev, lib_path=self.lib_path)
+        return self.ctxs[pk]
+
+    def _grouped(self, pks: Sequence[bytes], run) -> np.ndarray:
+        n = len(pks)
+        out = np.full(n, 255, dtype=np.uint8)
+        groups: dict = {}
+        for i, pk in enumerate(pks):
+            groups.setdefault(bytes(pk), []).append(i)
+        ctxs = {pk: self.context(pk) for pk in groups}          # built before the threads start
+        errs: list = []
+
+        def work(pk, idx):
+            try:
+                out[np.asarray(idx)] = run(ctxs[pk], idx)
+            except Exception as e:  # pragma: no cover
+                errs.append(e)
+
+        ts = [threading.Thread(target=work, args=(pk, idx)) for pk, idx in groups.items()]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errs:
+            raise errs[0]
+        return out
+
+    def verify_batch(self, pks: Sequence[bytes], signatures: Sequence[bytes], messages: Sequence[Sequence[bytes]]) -> np.ndarray:
+        """status[i] = verify of signatures[i] over messages[i] under pks[i] (compressed G2)"""
+        return self._grouped(pks, lambda ctx, idx: ctx.verify_batch(b"".join(bytes(signatures[i]) for i in idx),
+                                                                   [messages[i] for i in idx]))
+
+    def proof_verify_batch(self, pks: Sequence[bytes], proofs, ph: bytes, disclosed_messages, disclosed_indexes) -> np.ndarray:
+        return self._grouped(pks, lambda ctx, idx: ctx.proof_verify_batch([proofs[i] for i in idx], ph,
+                                                                         [disclosed_messages[i] for i in idx],
+                                                                         [disclosed_indexes[i] for i in idx]))
+
+    def close(self):
+        for c in self.ctxs.values():
+            c.close()
+        self.ctxs = {}

@@ -146,3 +146,29 @@ def test_sharded_helpers(lib):
 @pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
 def test_create_generators(lib, curve):
     P.case_create_generators(None, curve, count=40)
+
+
+def test_multi_issuer_batch(lib):
+    """per-item public keys: three issuers interleaved in one batch, one wrong-issuer item, one forged
+    signature; every status equals the oracle's verify under that item's key"""
+    from bbs_sign_b200.sharding import MultiIssuerVerifier
+    from oracle import bbs_oracle as O
+    suite, ocs = P.SUITES["BLS12_381"]
+    keys = [P.keypair(ocs, s) for s in (1, 2, 3)]
+    L, n = 2, 9
+    msgs = [[P.rng_bytes(f"mi{i}.{j}", 32) for j in range(L)] for i in range(n)]
+    owner = [i % 3 for i in range(n)]
+    sigs = [O.sign(ocs, keys[owner[i]][0], msgs[i], b"mi") for i in range(n)]
+    claimed = list(owner)
+    claimed[4] = (owner[4] + 1) % 3                       # verified under another issuer's key
+    sigs[7] = (sigs[7][0], (sigs[7][1] + 1) % ocs.r)      # forged
+    pks = [ocs.g2_compress(keys[k][1]) for k in claimed]
+    enc = [O.signature_to_bytes(ocs, s) for s in sigs]
+    mv = MultiIssuerVerifier(suite, b"mi", L)
+    got = mv.verify_batch(pks, enc, msgs)
+    want = [1 if O.verify(ocs, keys[claimed[i]][1], sigs[i], b"mi", msgs[i], trapdoor_sk=keys[claimed[i]][0]) else 0
+            for i in range(n)]
+    assert O.verify(ocs, keys[claimed[4]][1], sigs[4], b"mi", msgs[4]) is False        # and once with the pairing oracle
+    assert got.tolist() == want == [1, 1, 1, 1, 0, 1, 1, 0, 1]
+    assert len(mv.ctxs) == 3
+    mv.close()
