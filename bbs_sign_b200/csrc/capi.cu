@@ -303,7 +303,7 @@ struct Impl {
         double best_cost = 1e300;
         const char* force = getenv("BBS_RLC_WINDOWS");        // tests: exercise other geometries
         for (uint32_t W = 8; W <= 32; W++) {
-            const uint32_t c = (128 + W - 1) / W, rows = MsmGeom<C>::PHI ? 2 * W : 3 * W;
+            const uint32_t c = (128 + W - 1) / W, rows = 2 * W;
             double used = 0;                                   // buckets that can be non-empty
             for (uint32_t w = 0; w < W; w++) used += (double)(1u << (((w + 1) * 128) / W - (w * 128) / W));
             used *= rows / W;
@@ -314,7 +314,7 @@ struct Impl {
         MsmPlan p;
         p.W = best;
         p.c = (128 + best - 1) / best;
-        p.rows = MsmGeom<C>::PHI ? 2 * p.W : 3 * p.W;
+        p.rows = 2 * p.W;
         p.chunk = 16u;
         const uint32_t threads = (1u << p.c) / p.chunk;
         p.red_blocks = (threads + RLC_TPB - 1) / RLC_TPB;

@@ -146,10 +146,11 @@ template <class C> BBS_HDN void g1_mul_affine(uint32_t* r, const uint32_t* a, co
 // Variable-base k*P for the per-item points (e*A in core_verify, D*r3^ in proof_verify_init).  ark-ec's
 // `Projective * Fr` is a bit-serial double-and-add; on a GPU its data-dependent additions diverge inside a warp
 // (every lane pays for every addition), so this uses fixed 4-bit windows (one table look-up and one addition per
-// window for every lane) and, on BLS12-381, the curve endomorphism phi(x, y) = (beta x, y) = lambda P with
-// lambda = x^2 - 1 and r = lambda^2 + lambda + 1:  k = k1 + k2 lambda with k2 = floor(k / lambda), k1 = k mod lambda,
-// both below 2^128, so k P = k1 P + k2 phi(P) needs 128 doublings instead of 255.  Same group element as the
-// reference computes; only the addition chain differs.
+// window for every lane) and the curve endomorphism phi(x, y) = (beta x, y) = lambda P (both curves have j = 0):
+// k = k1 + k2 lambda with both halves below 2^128, so k P = k1 P + k2 phi(P) needs 128 doublings instead of 255.  On
+// BLS12-381 lambda = x^2 - 1 is itself 128 bits and k2 = floor(k / lambda), k1 = k mod lambda; on BN254 lambda is 254 bits and
+// the halves come from a lattice reduction (bn_glv_split).  Same group element as the reference computes; only the
+// addition chain differs.
 BBS_HD uint32_t win4_digit(const uint32_t* k, int w) { return (k[w >> 3] >> (4 * (w & 7))) & 15u; }
 
 // r = sum_j k1[j] * P_j (+ k2[j] * phi(P_j) when beta != nullptr) over NP affine points (pts[j] == nullptr: the
@@ -241,27 +242,81 @@ BBS_HD void bls_glv_split(uint32_t* k1, uint32_t* k2, const uint32_t* k) {
     k1[4] = rem[4]; k2[4] = q[4];              // k1[4] == 0; k2[4] == 0 (k2 <= lambda + 1 < 2^128)
 }
 
+// out[0 .. NX + NY) = x * y (schoolbook on 32-bit limbs; setup-sized operands)
+template <int NX, int NY> BBS_HD void mp_mul(uint32_t* out, const uint32_t* x, const uint32_t* y) {
+    for (int i = 0; i < NX + NY; i++) out[i] = 0;
+    for (int i = 0; i < NX; i++) {
+        uint64_t c = 0;
+        for (int j = 0; j < NY; j++) {
+            c += (uint64_t)x[i] * y[j] + out[i + j];
+            out[i + j] = (uint32_t)c;
+            c >>= 32;
+        }
+        out[i + NY] = (uint32_t)c;
+    }
+}
+
+// k (8 canonical limbs, < r) = k1 + k2 * lambda mod r with 0 <= k1, k2 < 2^128   [BN254]
+// lambda is a 254-bit root of x^2 + x + 1, so the halves come from the lattice {(x, y): x + y lambda = 0 mod r} with basis
+// v1 = (a, -b), v2 = (b, a + b), a = 6t^2 + 2t, b = 2t + 1 (det = r):  (k1, k2) = (k + r, 0) - c1 v1 - c2 v2  with
+//   c1 = floor(((a + b)(k + r) + 2 b^2) / r),   c2 = floor((b (k + r) - 2 a b) / r)
+// i.e. the coordinates of (k + r, -2b) rounded DOWN, which puts the remainder into the fundamental parallelogram shifted by
+// (0, 2b): both halves non-negative (no signed digits, no point negations).  The two quotients are taken with reciprocals
+// floor(2^384 / r), floor(2^320 / r): each may come out one too small, which adds one basis vector to the remainder; the
+// halves stay below 2 (a + 2b) < 2^128 (tools/gen_constants.py checks the constants; the split is checked against
+// k1 + k2 lambda = k on the device by the G1 self test and against the oracle by every BN254 parity test).
+BBS_HD void bn_glv_split(uint32_t* k1, uint32_t* k2, const uint32_t* k) {
+    uint32_t kp[8];
+    {
+        uint64_t c = 0;
+        for (int i = 0; i < 8; i++) { c += (uint64_t)k[i] + BN_FR_P()[i]; kp[i] = (uint32_t)c; c >>= 32; }   // < 2^255
+    }
+    uint32_t n1[12], n2[10];
+    mp_mul<4, 8>(n1, BN_GLV_AB(), kp);
+    {
+        uint64_t c = 0;
+        for (int i = 0; i < 12; i++) { c += (uint64_t)n1[i] + (i < 5 ? BN_GLV_2BB()[i] : 0u); n1[i] = (uint32_t)c; c >>= 32; }
+    }
+    mp_mul<2, 8>(n2, BN_GLV_B(), kp);
+    {
+        int64_t c = 0;
+        for (int i = 0; i < 10; i++) { c += (int64_t)n2[i] - (int64_t)(i < 6 ? BN_GLV_2AB()[i] : 0u); n2[i] = (uint32_t)c; c >>= 32; }
+    }
+    uint32_t q1[17], q2[13];
+    mp_mul<12, 5>(q1, n1, BN_GLV_G384());
+    mp_mul<10, 3>(q2, n2, BN_GLV_G320());
+    const uint32_t* c1 = q1 + 12;      // 5 limbs
+    const uint32_t* c2 = q2 + 10;      // 3 limbs
+    uint32_t c1a[9], c2b[5], c1b[7], c2ab[7];
+    mp_mul<5, 4>(c1a, c1, BN_GLV_A());
+    mp_mul<3, 2>(c2b, c2, BN_GLV_B());
+    mp_mul<5, 2>(c1b, c1, BN_GLV_B());
+    mp_mul<3, 4>(c2ab, c2, BN_GLV_AB());
+    int64_t ca = 0, cb = 0;
+    for (int i = 0; i < 5; i++) {      // mod 2^160: both results are below 2^128
+        ca += (int64_t)kp[i] - (int64_t)c1a[i] - (int64_t)c2b[i];
+        k1[i] = (uint32_t)ca;
+        ca >>= 32;
+        cb += (int64_t)c1b[i] - (int64_t)c2ab[i];
+        k2[i] = (uint32_t)cb;
+        cb >>= 32;
+    }
+}
+
+template <class C> BBS_HD void glv_split(uint32_t* k1, uint32_t* k2, const uint32_t* k);
+template <> BBS_HD void glv_split<Bls>(uint32_t* k1, uint32_t* k2, const uint32_t* k) { bls_glv_split(k1, k2, k); }
+template <> BBS_HD void glv_split<Bn>(uint32_t* k1, uint32_t* k2, const uint32_t* k) { bn_glv_split(k1, k2, k); }
+
 // r = sum_j k_j * P_j for NP affine points (nullptr = identity) and canonical scalars k_j (8 limbs each)
 template <class C, int NP> BBS_HDN void g1_msm_scalar(uint32_t* r, const uint32_t* const* pts, const uint32_t* const* ks);
-template <class C, int NP> struct G1Msm;
-template <int NP> struct G1Msm<Bls, NP> {
+template <class C, int NP> struct G1Msm {
     static BBS_HD void run(uint32_t* r, const uint32_t* const* pts, const uint32_t* const* ks) {
         uint32_t k1[NP][9], k2[NP][9];
         for (int j = 0; j < NP; j++) {
             for (int i = 0; i < 9; i++) { k1[j][i] = 0; k2[j][i] = 0; }
-            bls_glv_split(k1[j], k2[j], ks[j]);
+            glv_split<C>(k1[j], k2[j], ks[j]);
         }
-        g1_msm_win4<Bls, NP>(r, pts, k1, k2, 128, BLS_GLV_BETA());   // k1 < lambda, k2 <= lambda + 1 < 2^128
-    }
-};
-template <int NP> struct G1Msm<Bn, NP> {
-    static BBS_HD void run(uint32_t* r, const uint32_t* const* pts, const uint32_t* const* ks) {
-        uint32_t k1[NP][9];
-        for (int j = 0; j < NP; j++) {
-            for (int i = 0; i < 8; i++) k1[j][i] = ks[j][i];
-            k1[j][8] = 0;
-        }
-        g1_msm_win4<Bn, NP>(r, pts, k1, nullptr, BnFr::BITS, nullptr);
+        g1_msm_win4<C, NP>(r, pts, k1, k2, 128, C::GLV_BETA());   // both halves < 2^128
     }
 };
 template <class C, int NP> BBS_HDN void g1_msm_scalar(uint32_t* r, const uint32_t* const* pts, const uint32_t* const* ks) {

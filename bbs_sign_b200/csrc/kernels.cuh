@@ -27,31 +27,20 @@ enum : uint8_t {
 };
 
 // Fixed-base tables: entry (g, w, d) = (d * 2^(BITS w)) * base_g in affine form, d = 1 .. 2^BITS - 1.
-//   BLS12-381: the scalar is split with the GLV endomorphism (g1.cuh: k = k1 + k2 lambda, both < 2^128) and BOTH halves
-//   use the same table (phi of an entry is (beta x, y): one extra multiplication), so 16-bit windows need only 8
-//   windows: 16 mixed additions per generator from a 50 MB table (550 MB at L = 10, 96-byte gathers from HBM).
-//   BN254 (no endomorphism constants here): 12-bit windows over the 254-bit scalar, 22 additions per generator.
+//   The scalar is split with the GLV endomorphism (g1.cuh: k = k1 + k2 lambda, both < 2^128) and BOTH halves use the same
+//   table (phi of an entry is (beta x, y): one extra multiplication), so 16-bit windows need only 8 windows: 16 mixed
+//   additions per generator from a 50 MB (BLS12-381) / 34 MB (BN254) table per generator, 96- / 64-byte gathers from HBM.
 //   The host simulation (tests only) builds its tables on CPU cores and uses 8-bit windows.
 #ifndef BBS_TAB_BITS_GLV
 #ifdef BBS_HOSTSIM
 #define BBS_TAB_BITS_GLV 8
-#define BBS_TAB_BITS_PLAIN 8
 #else
 #define BBS_TAB_BITS_GLV 16
-#define BBS_TAB_BITS_PLAIN 12
 #endif
 #endif
-template <class C> struct TabGeom;
-template <> struct TabGeom<Bls> {
-    static constexpr bool GLV = true;
+template <class C> struct TabGeom {
     static constexpr int BITS = BBS_TAB_BITS_GLV;
     static constexpr int WINDOWS = (128 + BITS - 1) / BITS;
-    static constexpr int ENTRIES = (1 << BITS) - 1;
-};
-template <> struct TabGeom<Bn> {
-    static constexpr bool GLV = false;
-    static constexpr int BITS = BBS_TAB_BITS_PLAIN;
-    static constexpr int WINDOWS = (256 + BITS - 1) / BITS;
     static constexpr int ENTRIES = (1 << BITS) - 1;
 };
 template <class C> BBS_HD uint32_t tab_digit(const uint32_t* s, int nlimbs, int w) {      // s: canonical limbs
@@ -182,35 +171,23 @@ template <class C> BBS_HD void h2s_item(const H2sArgs& a, uint32_t t) {
 template <class C> BBS_HDN void tab_accumulate(uint32_t* acc, const uint32_t* tab, uint32_t g, const uint32_t* s) {
     using G = TabGeom<C>;
     const uint32_t* tg = tab + (size_t)g * G::WINDOWS * G::ENTRIES * G1A;
-    if (G::GLV) {
-        uint32_t k1[5], k2[5];
-        bls_glv_split(k1, k2, s);
-        for (int w = 0; w < G::WINDOWS; w++) {
-            uint32_t d1 = tab_digit<C>(k1, 5, w), d2 = tab_digit<C>(k2, 5, w);
-            if (d1) {
-                uint32_t e[G1A];
-                const uint32_t* src = tg + ((size_t)w * G::ENTRIES + (d1 - 1)) * G1A;
-                for (int j = 0; j < G1A; j++) e[j] = src[j];
-                g1_add_mixed<C>(acc, acc, e);
-            }
-            if (d2) {
-                uint32_t e[G1A], t[FPN];
-                const uint32_t* src = tg + ((size_t)w * G::ENTRIES + (d2 - 1)) * G1A;
-                for (int j = 0; j < G1A; j++) e[j] = src[j];
-                fe_mul<typename C::Fp>(t, e, C::GLV_BETA());            // phi(x, y) = (beta x, y)
-                bn_copy<C::Fp::N>(e, t);
-                g1_add_mixed<C>(acc, acc, e);
-            }
+    uint32_t k1[5], k2[5];
+    glv_split<C>(k1, k2, s);
+    for (int w = 0; w < G::WINDOWS; w++) {
+        uint32_t d1 = tab_digit<C>(k1, 5, w), d2 = tab_digit<C>(k2, 5, w);
+        if (d1) {
+            uint32_t e[G1A];
+            const uint32_t* src = tg + ((size_t)w * G::ENTRIES + (d1 - 1)) * G1A;
+            for (int j = 0; j < G1A; j++) e[j] = src[j];
+            g1_add_mixed<C>(acc, acc, e);
         }
-    } else {
-        for (int w = 0; w < G::WINDOWS; w++) {
-            uint32_t d = tab_digit<C>(s, 8, w);
-            if (d) {
-                uint32_t e[G1A];
-                const uint32_t* src = tg + ((size_t)w * G::ENTRIES + (d - 1)) * G1A;
-                for (int j = 0; j < G1A; j++) e[j] = src[j];
-                g1_add_mixed<C>(acc, acc, e);
-            }
+        if (d2) {
+            uint32_t e[G1A], t[FPN];
+            const uint32_t* src = tg + ((size_t)w * G::ENTRIES + (d2 - 1)) * G1A;
+            for (int j = 0; j < G1A; j++) e[j] = src[j];
+            fe_mul<typename C::Fp>(t, e, C::GLV_BETA());            // phi(x, y) = (beta x, y)
+            bn_copy<C::Fp::N>(e, t);
+            g1_add_mixed<C>(acc, acc, e);
         }
     }
 }

@@ -2,8 +2,7 @@
 //     S1 = sum r_i A_i          S2' = sum (r_i e_i) A_i            (verify.rs:88-92 folded over the batch)
 // are the north star's "two large MSMs per GPU".  Every item contributes three 128-bit values:
 //     v0 = r_i                                  -> bucket rows [0, W)            (S1)
-//     BLS12-381: (v1, v2) = GLV halves of r_i e_i, v2 acting on phi(A_i) = (beta x, y)  -> rows [W, 2W), shared
-//     BN254:     (v1, v2) = low / high 128 bits of r_i e_i                             -> rows [W, 2W) and [2W, 3W)
+//     (v1, v2) = GLV halves of r_i e_i (g1.cuh glv_split), v2 acting on phi(A_i) = (beta x, y)  -> rows [W, 2W), shared
 // cut into W digits of near-equal width (digit w = bits [128 w / W, 128 (w + 1) / W), at most c bits: equal bucket loads in
 // every row, whatever W).  Pipeline (all on the context's stream):
 //     rlc_prep_kernel    decompress A_i, coefficients, GLV split; histogram of the non-zero digits; Fr partial sums
@@ -22,14 +21,10 @@ namespace bbs {
 struct MsmPlan {
     uint32_t c;          // widest digit, bits: a row holds 2^c buckets
     uint32_t W;          // digits per 128-bit value
-    uint32_t rows;       // bucket rows: 2W with the endomorphism, 3W without
+    uint32_t rows;       // bucket rows: 2W
     uint32_t chunk;      // buckets per thread in msm_reduce_kernel
     uint32_t red_blocks; // blocks per row in msm_reduce_kernel
 };
-template <class C> struct MsmGeom;
-template <> struct MsmGeom<Bls> { static constexpr bool PHI = true; };
-template <> struct MsmGeom<Bn> { static constexpr bool PHI = false; };
-
 __device__ __forceinline__ uint32_t msm_digit_start(uint32_t w, uint32_t W) { return (w * 128u) / W; }
 __device__ __forceinline__ uint32_t msm_digit_bits(uint32_t w, uint32_t W) { return msm_digit_start(w + 1, W) - msm_digit_start(w, W); }
 __device__ __forceinline__ uint32_t msm_digit(const uint32_t* v /*4 words, global*/, uint32_t w, uint32_t W) {
@@ -38,9 +33,7 @@ __device__ __forceinline__ uint32_t msm_digit(const uint32_t* v /*4 words, globa
     if (word < 3) x |= (uint64_t)v[word + 1] << 32;
     return (uint32_t)(x >> off) & ((1u << msm_digit_bits(w, W)) - 1u);
 }
-template <class C> __device__ __forceinline__ uint32_t msm_row(uint32_t stream, uint32_t w, uint32_t W) {
-    return (stream == 0 ? 0u : (stream == 1 || MsmGeom<C>::PHI) ? W : 2 * W) + w;
-}
+__device__ __forceinline__ uint32_t msm_row(uint32_t stream, uint32_t w, uint32_t W) { return (stream == 0 ? 0u : W) + w; }
 
 struct RlcPrepArgs {
     RlcArgs base;            // pt_part unused
@@ -72,13 +65,9 @@ template <class C> __global__ void __launch_bounds__(RLC_TPB, 4) rlc_prep_kernel
             uint32_t ae[8];
             fe_mul<Fr>(ae, rm, e);                  // r_i e_i mod r, canonical
             for (int k = 0; k < 4; k++) kv[k] = r[k];
-            if (MsmGeom<C>::PHI) {
-                uint32_t k1[5], k2[5];
-                bls_glv_split(k1, k2, ae);
-                for (int k = 0; k < 4; k++) { kv[4 + k] = k1[k]; kv[8 + k] = k2[k]; }
-            } else {
-                for (int k = 0; k < 8; k++) kv[4 + k] = ae[k];
-            }
+            uint32_t k1[5], k2[5];
+            glv_split<C>(k1, k2, ae);
+            for (int k = 0; k < 4; k++) { kv[4 + k] = k1[k]; kv[8 + k] = k2[k]; }
             uint32_t* dst = pa.pts + (size_t)i * G1A;
             for (int k = 0; k < G1A; k++) dst[k] = A[k];
         }
@@ -89,7 +78,7 @@ template <class C> __global__ void __launch_bounds__(RLC_TPB, 4) rlc_prep_kernel
             for (uint32_t s = 0; s < 3; s++)
                 for (uint32_t w = 0; w < W; w++) {
                     const uint32_t d = msm_digit(kd + 4 * s, w, W);
-                    if (d) atomicAdd(pa.counts + ((size_t)msm_row<C>(s, w, W) << c) + d, 1u);
+                    if (d) atomicAdd(pa.counts + ((size_t)msm_row(s, w, W) << c) + d, 1u);
                 }
         }
     }
@@ -148,8 +137,8 @@ template <class C> __global__ void __launch_bounds__(128) msm_scatter_kernel(con
         for (uint32_t w = 0; w < W; w++) {
             const uint32_t d = msm_digit(kd + 4 * s, w, W);
             if (d) {
-                const uint32_t pos = atomicAdd(a.cursor + ((size_t)msm_row<C>(s, w, W) << c) + d, 1u);
-                a.entries[pos] = i | ((s == 2 && MsmGeom<C>::PHI) ? 0x80000000u : 0u);
+                const uint32_t pos = atomicAdd(a.cursor + ((size_t)msm_row(s, w, W) << c) + d, 1u);
+                a.entries[pos] = i | (s == 2 ? 0x80000000u : 0u);
             }
         }
 }
@@ -231,7 +220,7 @@ struct RlcMsmFinishArgs {
     uint8_t* parts_out;            // comp(S1) || comp(S2)
     uint32_t* pair; uint32_t* flags; uint8_t* status;     // pairing record of (S1, S2) for the single-shard verdict
 };
-// one block: rows -> S1 and S2' by Horner over the windows (three independent chains in warps 0..2) while warp 3 sums
+// one block: rows -> S1 and S2' by Horner over the windows (two independent chains in warps 0 and 1) while warp 3 sums
 // the fixed-base term F = (sum r_i) K + sum_j (sum_i r_i m_ij) H_j, one generator per lane; then S2 = S2' - F, and the two
 // points are normalised in two warps: compressed for the host-combined multi-GPU path (rlc_combine) and written as the
 // pairing record (x, y, 1) that the single-shard verdict feeds straight to the pairing kernel.
@@ -241,7 +230,7 @@ template <class C> __global__ void __launch_bounds__(RLC_TPB, 1) rlc_msm_finish_
     __shared__ uint32_t sp[RLC_TPB][3 * C::Fp::N];
     __shared__ uint32_t ss[RLC_TPB][8];
     __shared__ uint32_t sums[MAX_L + 1][8];
-    __shared__ uint32_t res[4][3 * C::Fp::N];
+    __shared__ uint32_t res[3][3 * C::Fp::N];        // S1, S2', F
     __shared__ uint32_t skip[2];
     const CtxView& cx = a.ctx;
     const uint32_t t = threadIdx.x, W = a.plan.W, rows = a.plan.rows;
@@ -254,7 +243,7 @@ template <class C> __global__ void __launch_bounds__(RLC_TPB, 1) rlc_msm_finish_
         if (t == 0) bn_copy<8>(sums[j], ss[0]);
         __syncthreads();
     }
-    // row totals: thread = row (rows <= 96)
+    // row totals: thread = row (rows <= 64)
     uint32_t acc[G1J];
     g1_set_inf<C>(acc);
     if (t < rows)
@@ -263,16 +252,15 @@ template <class C> __global__ void __launch_bounds__(RLC_TPB, 1) rlc_msm_finish_
     __syncthreads();
     const uint32_t job = t >> 5, lane = t & 31;
     g1_set_inf<C>(acc);
-    if (job < 3) {
-        if (lane == 0 && job < rows / W) {                  // 2 or 3 Horner chains
+    if (job < 2) {
+        if (lane == 0) {
             for (int w = (int)W - 1; w >= 0; w--) {
                 for (uint32_t k = msm_digit_bits(w, W); k > 0; k--) g1_dbl<C>(acc, acc);
                 g1_add<C>(acc, acc, sp[job * W + w]);
             }
-            if (job == 2) for (int k = 0; k < 128; k++) g1_dbl<C>(acc, acc);      // high half of r_i e_i (no endomorphism)
+            g1_copy<C>(res[job], acc);
         }
-        if (lane == 0) g1_copy<C>(res[job], acc);
-    } else {
+    } else if (job == 3) {
         for (uint32_t j = lane; j <= a.n_msgs; j += 32)
             if (!(j == 0 && cx.k_inf)) tab_accumulate<C>(acc, cx.tab, j, sums[j]);
         g1_copy<C>(sp[t], acc);                              // sp[96..127]: warp 3 only
@@ -281,7 +269,7 @@ template <class C> __global__ void __launch_bounds__(RLC_TPB, 1) rlc_msm_finish_
             if (lane < (uint32_t)st) g1_add<C>(sp[t], sp[t], sp[t + st]);
             __syncwarp();
         }
-        if (lane == 0) g1_copy<C>(res[3], sp[t]);
+        if (lane == 0) g1_copy<C>(res[2], sp[t]);
     }
     __syncthreads();
     if (lane == 0 && job < 2) {
@@ -289,9 +277,8 @@ template <class C> __global__ void __launch_bounds__(RLC_TPB, 1) rlc_msm_finish_
         if (job == 0) g1_copy<C>(S, res[0]);
         else {
             uint32_t nF[G1J];
-            g1_add<C>(S, res[1], res[2]);
-            g1_neg<C>(nF, res[3]);
-            g1_add<C>(S, S, nF);
+            g1_neg<C>(nF, res[2]);
+            g1_add<C>(S, res[1], nF);
         }
         const bool fin = g1_to_affine<C>(aff, S);
         g1_compress_affine<C>(a.parts_out + job * C::G1_BYTES, aff, !fin);

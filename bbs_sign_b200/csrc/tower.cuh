@@ -43,7 +43,7 @@ struct Bn {
     static BBS_HD const uint32_t* B() { return BN_B(); }
     static BBS_HD const uint32_t* P1() { return BN_P1(); }
     static BBS_HD const uint32_t* G2() { return BN_G2(); }
-    static BBS_HD const uint32_t* GLV_BETA() { return BN_B(); }   // unused (TabGeom<Bn>::GLV == false)
+    static BBS_HD const uint32_t* GLV_BETA() { return BN_GLV_BETA(); }
     static BBS_HD const uint32_t* FROB(int j) { return j == 1 ? BN_FROB1() : (j == 2 ? BN_FROB2() : BN_FROB3()); }
     // r = a * (9+u) = (9a0 - a1) + (9a1 + a0) u
     static BBS_HD void mul_xi(uint32_t* r, const uint32_t* a) {
