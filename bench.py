@@ -390,7 +390,7 @@ def run_proof(args):
 def run_bn254(args):
     """BASELINE configs[2] shape: BN254 core_verify over pre-hashed scalar messages (L = 31), device-resident inputs.
     Key pair: tests/golden/bn254_bench_key.npz (made once with the oracle's key_gen / sk_to_pk); signatures are made on
-    the GPU by bbs_core_sign_batch.  BN254 still runs the per-thread pairing kernel."""
+    the GPU by bbs_core_sign_batch."""
     import torch
     import torch.distributed as dist
     from bbs_sign_b200 import api, _native
