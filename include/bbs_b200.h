@@ -74,7 +74,7 @@ int bbs_create_generators(int curve_id, int device, const uint8_t* api_id, size_
  *   argument of core_verify / core_sign / core_proof_verify (src/verify.rs:53-60, src/sign.rs:63-69,
  *   src/proof_verify.rs:64-73); computes `calculate_domain` (src/utils/core_utilities.rs:24-63) for
  *   (pk, generators, header, api_id) once; K = P1 + Q1*domain; fixed-base window tables for K and
- *   every H_j (BLS12-381: 16-bit windows over GLV half scalars, 50 MB per generator; BN254: 12-bit windows);
+ *   every H_j (16-bit windows over GLV half scalars: 50 MB per generator on BLS12-381, 34 MB on BN254);
  *   and the Miller-loop line tables of pk and BP2.
  * `api_id` is the reference's `api_id` (CIPHERSUITE_ID || "H2G_HM2S_" in the interface functions,
  * arbitrary in the core tests).  Identity pk is allowed (the reference returns Ok(false) for it).

@@ -504,3 +504,40 @@ def case_create_generators(lib_path, curve_name, count=5):
     want2 = gens_bytes(ocs, O.create_generators(ocs, 3, other))
     assert suite.create_generators(3, api_id=other, lib_path=lib_path) == want2
     assert suite.derive_generators(0, lib_path=lib_path) == b""
+
+
+# ---------------------------------------------------------------------------------------------------
+def case_core_api_id(lib_path, curve_name, L=5):
+    """core_sign_tests.rs: core_sign / core_verify over SCALAR messages with an arbitrary api_id ("" and "abc",
+    :38-65), generators made for that api_id (on the device: bbs_create_generators), and its rejections: wrong api_id,
+    wrong header, message[0] = 0 (:67-155).  Signatures and B points are compared byte for byte with the oracle."""
+    suite, ocs = SUITES[curve_name]
+    sk, pk = keypair(ocs, 1)
+    n = 4
+    for api_id in (b"", b"abc"):
+        gens = O.create_generators(ocs, L + 1, api_id)
+        gb = gens_bytes(ocs, gens)
+        if lib_path is None:          # GPU run: the device derivation must give the same generators
+            assert suite.derive_generators(L + 1, api_id=api_id) == gb
+        ctx = A.BatchContext(suite, ocs.g2_compress(pk), b"h", generators=gb, api_id=api_id, lib_path=lib_path)
+        scal = [[(7 * i + j + 1) % ocs.r for j in range(L)] for i in range(n)]        # Fr::from(u64) style messages
+        flat = np.frombuffer(b"".join(ocs.scalar_le(x) for row in scal for x in row), dtype=np.uint8)
+        sigs, _, st = ctx.core_sign_batch(sk.to_bytes(32, "little"), flat, n, L)
+        assert st.tolist() == [1] * n
+        osigs = [O.core_sign(ocs, sk, gens, b"h", row, api_id) for row in scal]
+        for i in range(n):
+            assert sigs[i].tobytes() == O.signature_to_bytes(ocs, osigs[i])
+        blob = np.frombuffer(b"".join(O.signature_to_bytes(ocs, s) for s in osigs), dtype=np.uint8)
+        assert ctx.core_verify_batch(blob, flat, L).tolist() == [1] * n
+        # message[0] = 0 on item 2
+        bad = [list(r) for r in scal]
+        bad[2][0] = 0
+        flat_bad = np.frombuffer(b"".join(ocs.scalar_le(x) for row in bad for x in row), dtype=np.uint8)
+        assert ctx.core_verify_batch(blob, flat_bad, L).tolist() == [1, 1, 0, 1]
+        ctx.close()
+        # wrong api_id (same generators) and wrong header: the domain changes -> Ok(false)
+        for other_api, other_hdr in ((api_id + b"x", b"h"), (api_id, b"other")):
+            ctx2 = A.BatchContext(suite, ocs.g2_compress(pk), other_hdr, generators=gb, api_id=other_api, lib_path=lib_path)
+            want = [int(O.core_verify(ocs, pk, s, gens, other_hdr, row, other_api, trapdoor_sk=sk)) for s, row in zip(osigs, scal)]
+            assert ctx2.core_verify_batch(blob, flat, L).tolist() == want == [0] * n
+            ctx2.close()

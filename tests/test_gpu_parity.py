@@ -172,3 +172,8 @@ def test_multi_issuer_batch(lib):
     assert got.tolist() == want == [1, 1, 1, 1, 0, 1, 1, 0, 1]
     assert len(mv.ctxs) == 3
     mv.close()
+
+
+@pytest.mark.parametrize("curve", ["BN254", "BLS12_381"])
+def test_core_api_id(lib, curve):
+    P.case_core_api_id(None, curve, L=5)

@@ -76,3 +76,8 @@ def test_readme_example(lib_path, curve):
 @pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
 def test_create_generators(lib_path, curve):
     P.case_create_generators(lib_path, curve, count=3)
+
+
+@pytest.mark.parametrize("curve", ["BN254", "BLS12_381"])
+def test_core_api_id(lib_path, curve):
+    P.case_core_api_id(lib_path, curve, L=3)
