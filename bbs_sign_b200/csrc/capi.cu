@@ -3,6 +3,7 @@
 #include "../../include/bbs_b200.h"
 #include "launchers.cuh"
 
+#include <algorithm>
 #include <new>
 #include <vector>
 
@@ -47,6 +48,10 @@ struct Ctx {
     int curve = 0, device = 0;
     uint32_t L = 0;
     rt_stream_t stream = nullptr;
+#ifndef BBS_HOSTSIM
+    cudaStream_t copy_stream = nullptr;        // uploads of the chunked host-buffer paths (rlc): overlap with compute
+    cudaEvent_t copy_done[8] = {};
+#endif
     uint64_t launches = 0;
     bool profile = false;            // bbs_ctx_set_profiling: CUDA events around each kernel of a batch call
     ProfEvents prof;
@@ -320,9 +325,15 @@ struct Impl {
         p.red_blocks = (threads + RLC_TPB - 1) / RLC_TPB;
         return p;
     }
-    // shard -> comp(S1) || comp(S2) in c->s_rlc_parts; *bad != 0 when an item was malformed
+    // Host buffers of a shard, fed in up to 8 chunks: chunk k + 1 is uploaded on the copy stream while chunk k is hashed
+    // (msg_to_scalars) and prepared on the compute stream.  msgs == nullptr: `scalars` holds the n * L message scalars.
+    struct RlcFeed { const uint8_t* sigs; const uint8_t* scalars; const uint8_t* msgs; const uint64_t* off; };
+
+    // shard -> comp(S1) || comp(S2) in c->s_rlc_parts (and the pairing record of the two sums); *bad != 0 when an item was
+    // malformed.  With `feed` the inputs come from host memory, otherwise d_sigs / d_scalars are already on the device.
     static int rlc_partial_dev(Ctx* c, size_t n, const uint8_t* d_sigs, const uint8_t* d_scalars, uint32_t n_msgs,
-                               const uint8_t* seed, uint64_t index_base, uint32_t* bad, rt_stream_t s) {
+                               const uint8_t* seed, uint64_t index_base, uint32_t* bad, rt_stream_t s,
+                               const RlcFeed* feed = nullptr) {
         if (n >= (1ull << 31)) return arg_error("rlc shard too large");
         const uint32_t blocks = (uint32_t)((n + RLC_TPB - 1) / RLC_TPB);
         const MsmPlan plan = rlc_plan(n);
@@ -336,6 +347,18 @@ struct Impl {
         TRY(c->s_msm_entries.reserve((n ? n : 1) * 3 * plan.W * 4));
         TRY(c->s_msm_buckets.reserve(nb * PT));
         TRY(c->s_rlc_pt.reserve((size_t)plan.rows * plan.red_blocks * PT));
+        const size_t count = n * n_msgs;
+        if (feed) {
+            TRY(c->s_sigs.reserve(n * SIG));
+            TRY(c->s_scalars.reserve(count * 32));
+            if (feed->msgs) {
+                TRY(c->s_msgs.reserve(feed->off[count]));
+                TRY(c->s_offsets.reserve((count + 1) * 8));
+            }
+            d_sigs = (const uint8_t*)c->s_sigs.p;
+            d_scalars = (const uint8_t*)c->s_scalars.p;
+            if (!c->copy_stream) RT_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        }
         uint32_t* next = (uint32_t*)c->s_msm_idx.p;
         uint32_t* counts = next + 4;
         uint32_t* offsets = counts + nb;
@@ -344,14 +367,56 @@ struct Impl {
         TRY(rt_memset(next, 0, (nb + 4) * 4, s));
         RlcPrepArgs pa{};
         RlcArgs& a = pa.base;
-        a.ctx = c->view; a.sigs = d_sigs; a.scalars = d_scalars; a.n_msgs = n_msgs; a.n = (uint32_t)n;
-        a.index_base = index_base;
+        a.ctx = c->view; a.n_msgs = n_msgs;
         for (int i = 0; i < 8; i++)
             a.seed[i] = ((uint32_t)seed[4 * i] << 24) | ((uint32_t)seed[4 * i + 1] << 16) | ((uint32_t)seed[4 * i + 2] << 8) | seed[4 * i + 3];
-        a.sc_part = (uint32_t*)c->s_rlc_sc.p; a.bad = (uint32_t*)c->s_rlc_bad.p;
-        pa.plan = plan; pa.pts = (uint32_t*)c->s_msm_pts.p; pa.kv = (uint32_t*)c->s_msm_kv.p; pa.counts = counts;
-        PROF(c, 1, s);
-        TRY((launch_rlc_prep<C>(pa, blocks, s)));
+        a.bad = (uint32_t*)c->s_rlc_bad.p;
+        pa.plan = plan; pa.counts = counts;
+        // chunk = a whole number of waves of the prep kernel (4 blocks of RLC_TPB items per SM), at most 8 chunks; chunk
+        // boundaries are multiples of the block size, so the blocks' partial sums keep their global index
+        size_t per_chunk = n ? n : 1;
+        if (feed) {
+            int sms = 0;
+            RT_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+            const size_t wave = (size_t)4 * sms * RLC_TPB;
+            const size_t waves = std::max<size_t>(2, ((n + 7) / 8 + wave - 1) / wave);
+            per_chunk = waves * wave;
+        }
+        if (feed) {
+            // all uploads are queued on the copy stream up front, one event per chunk; the copy stream first waits for the
+            // compute stream (the memsets above and, transitively, the previous call) so that no buffer is overwritten early
+            if (!c->copy_done[0]) for (auto& e : c->copy_done) RT_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            RT_CHECK(cudaEventRecord(c->copy_done[7], s));
+            RT_CHECK(cudaStreamWaitEvent(c->copy_stream, c->copy_done[7], 0));
+            for (size_t k = 0, i0 = 0; i0 < n; k++, i0 += per_chunk) {
+                const size_t i1 = std::min(n, i0 + per_chunk), m0 = i0 * n_msgs, m1 = i1 * n_msgs;
+                TRY(rt_h2d((uint8_t*)c->s_sigs.p + i0 * SIG, feed->sigs + i0 * SIG, (i1 - i0) * SIG, c->copy_stream));
+                if (feed->msgs) {
+                    TRY(rt_h2d((uint8_t*)c->s_msgs.p + feed->off[m0], feed->msgs + feed->off[m0], feed->off[m1] - feed->off[m0], c->copy_stream));
+                    TRY(rt_h2d((uint64_t*)c->s_offsets.p + m0, feed->off + m0, (m1 - m0 + 1) * 8, c->copy_stream));
+                } else {
+                    TRY(rt_h2d((uint8_t*)c->s_scalars.p + m0 * 32, feed->scalars + m0 * 32, (m1 - m0) * 32, c->copy_stream));
+                }
+                RT_CHECK(cudaEventRecord(c->copy_done[k], c->copy_stream));
+            }
+        }
+        PROF(c, 0, s);
+        for (size_t k = 0, i0 = 0; i0 < n; k++, i0 += per_chunk) {
+            const size_t i1 = std::min(n, i0 + per_chunk), m0 = i0 * n_msgs, m1 = i1 * n_msgs;
+            if (feed) {
+                RT_CHECK(cudaStreamWaitEvent(s, c->copy_done[k], 0));
+                if (feed->msgs)
+                    TRY(h2s_dev(c, m1 - m0, (const uint8_t*)c->s_msgs.p, (const uint64_t*)c->s_offsets.p + m0,
+                                (uint8_t*)c->s_scalars.p + m0 * 32, s));
+            }
+            if (k == 0) PROF(c, 1, s);          // slot 0: first chunk's upload wait + hashing; slot 1: everything chunked after it
+            a.sigs = d_sigs + i0 * SIG; a.scalars = d_scalars + m0 * 32; a.n = (uint32_t)(i1 - i0);
+            a.index_base = index_base + i0;
+            a.sc_part = (uint32_t*)c->s_rlc_sc.p + (i0 / RLC_TPB) * (n_msgs + 1) * 8;
+            pa.pts = (uint32_t*)c->s_msm_pts.p + i0 * 2 * C::Fp::N; pa.kv = (uint32_t*)c->s_msm_kv.p + i0 * 12;
+            TRY((launch_rlc_prep<C>(pa, (uint32_t)((i1 - i0 + RLC_TPB - 1) / RLC_TPB), s)));
+            c->launches += 1;
+        }
         PROF(c, 2, s);
         TRY(launch_msm_scan(counts, offsets, cursor, (uint32_t)nb, s));
         MsmScatterArgs sa{plan, (const uint32_t*)c->s_msm_kv.p, cursor, (uint32_t*)c->s_msm_entries.p, (uint32_t)n};
@@ -371,7 +436,7 @@ struct Impl {
                            (uint8_t*)c->s_rlc_parts.p, (uint32_t*)c->s_pair.p, (uint32_t*)c->s_flags.p, (uint8_t*)c->s_status.p};
         TRY((launch_rlc_msm_finish<C>(f, s)));
         PROF(c, 6, s);
-        c->launches += (n ? 6 : 4);
+        c->launches += (n ? 5 : 3);
         TRY(rt_d2h(bad, c->s_rlc_bad.p, 4, s));
         return BBS_OK;
     }
@@ -379,10 +444,9 @@ struct Impl {
                            const uint8_t* seed, uint64_t index_base, uint8_t* parts_out, uint8_t* status) {
         rt_stream_t s = c->stream;
         if (n_msgs != c->L) { *status = ST_ERR_MSG_GEN_LEN; return BBS_OK; }
-        TRY(stage(c->s_sigs, sigs, n * SIG, s));
-        TRY(stage(c->s_scalars, scalars, n * n_msgs * 32, s));
+        const RlcFeed feed{sigs, scalars, nullptr, nullptr};
         uint32_t bad = 0;
-        TRY(rlc_partial_dev(c, n, (const uint8_t*)c->s_sigs.p, (const uint8_t*)c->s_scalars.p, n_msgs, seed, index_base, &bad, s));
+        TRY(rlc_partial_dev(c, n, nullptr, nullptr, n_msgs, seed, index_base, &bad, s, &feed));
         TRY(rt_d2h(parts_out, c->s_rlc_parts.p, 2 * C::G1_BYTES, s));
         TRY(rt_sync(s));
         *status = bad ? ST_ERR_MALFORMED : ST_ACCEPT;
@@ -392,15 +456,9 @@ struct Impl {
                                 uint32_t n_msgs, const uint8_t* seed, uint64_t index_base, uint8_t* parts_out, uint8_t* status) {
         rt_stream_t s = c->stream;
         if (n_msgs != c->L) { *status = ST_ERR_MSG_GEN_LEN; return BBS_OK; }
-        const size_t count = n * n_msgs;
-        TRY(stage(c->s_sigs, sigs, n * SIG, s));
-        TRY(stage(c->s_msgs, msgs, off[count], s));
-        TRY(stage(c->s_offsets, off, (count + 1) * 8, s));
-        TRY(c->s_scalars.reserve(count * 32));
-        PROF(c, 0, s);
-        TRY(h2s_dev(c, count, (const uint8_t*)c->s_msgs.p, (const uint64_t*)c->s_offsets.p, (uint8_t*)c->s_scalars.p, s));
+        const RlcFeed feed{sigs, nullptr, msgs, off};
         uint32_t bad = 0;
-        TRY(rlc_partial_dev(c, n, (const uint8_t*)c->s_sigs.p, (const uint8_t*)c->s_scalars.p, n_msgs, seed, index_base, &bad, s));
+        TRY(rlc_partial_dev(c, n, nullptr, nullptr, n_msgs, seed, index_base, &bad, s, &feed));
         TRY(rt_d2h(parts_out, c->s_rlc_parts.p, 2 * C::G1_BYTES, s));
         TRY(rt_sync(s));
         *status = bad ? ST_ERR_MALFORMED : ST_ACCEPT;
@@ -411,19 +469,9 @@ struct Impl {
                           uint32_t n_msgs, const uint8_t* seed, uint8_t* verdict) {
         rt_stream_t s = c->stream;
         if (n_msgs != c->L) { *verdict = ST_ERR_MSG_GEN_LEN; return BBS_OK; }
-        const size_t count = n * n_msgs;
-        TRY(stage(c->s_sigs, sigs, n * SIG, s));
-        if (off) {
-            TRY(stage(c->s_msgs, msgs, off[count], s));
-            TRY(stage(c->s_offsets, off, (count + 1) * 8, s));
-            TRY(c->s_scalars.reserve(count * 32));
-            PROF(c, 0, s);
-            TRY(h2s_dev(c, count, (const uint8_t*)c->s_msgs.p, (const uint64_t*)c->s_offsets.p, (uint8_t*)c->s_scalars.p, s));
-        } else {
-            TRY(stage(c->s_scalars, scalars, count * 32, s));
-        }
+        const RlcFeed feed{sigs, scalars, off ? msgs : nullptr, off};
         uint32_t bad = 0;
-        TRY(rlc_partial_dev(c, n, (const uint8_t*)c->s_sigs.p, (const uint8_t*)c->s_scalars.p, n_msgs, seed, 0, &bad, s));
+        TRY(rlc_partial_dev(c, n, nullptr, nullptr, n_msgs, seed, 0, &bad, s, &feed));
         TRY(pairing_dev(c, 1, (uint8_t*)c->s_status.p, s));
         PROF(c, 7, s);
         TRY(finish_status(c, 1, verdict));             // synchronises: `bad` has arrived too
@@ -632,6 +680,10 @@ void bbs_ctx_destroy(bbs_ctx* p) {
     rt_sync(c->stream);
     c->release_all();
     c->prof.release();
+#ifndef BBS_HOSTSIM
+    for (auto& e : c->copy_done) if (e) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+#endif
     rt_stream_destroy(c->stream);
     delete c;
 }
