@@ -605,7 +605,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=None, help="items per GPU (default 65,536; rlc: 524,288 = configs[4] per GPU)")
+    ap.add_argument("--n", type=int, default=None, help="items per GPU (default 65,536; rlc: 524,288, bn254: 131,072 = configs[4] / configs[2] per GPU of 8)")
     ap.add_argument("--L", type=int, default=L_DEFAULT)
     ap.add_argument("--cpu-sample", type=int, default=0, help="signatures per CPU-baseline step (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -614,7 +614,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.n is None:
-        args.n = 524288 if (args.workload == "rlc" and args.impl == "ours") else N_DEFAULT
+        # rlc: configs[4] per GPU (4M / 8); bn254: configs[2] per GPU (1M / 8); verify / proof: 65,536
+        args.n = {"rlc": 524288, "bn254": 131072}.get(args.workload, N_DEFAULT) if args.impl == "ours" else N_DEFAULT
     if args.workload == "proof" and args.impl == "ours":
         out = run_proof(args)
     elif args.workload == "rlc" and args.impl == "ours":
