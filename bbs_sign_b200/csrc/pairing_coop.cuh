@@ -13,6 +13,7 @@
 
 #ifdef __CUDACC__
 #include "gen_coop.cuh"
+#define COOP_BN_QCANON_M 1354u                 // floor(2^32 / ((p_bn254 >> 232) + 1)), checked by tools/gen_coop.py
 #ifdef BBS_COOP_PROG_HEADER
 #include BBS_COOP_PROG_HEADER              // timing experiments: alternative (not result-correct) programs
 #else
@@ -60,6 +61,8 @@ template <> struct Coop<Bls> {
     static constexpr int PARK = 1;             // Fp12 values a group parks in HBM (GSAVE / GLOAD slots)
     static constexpr bool ACC_XI = false;      // xi = 1 + u: multiplication by xi is routed through the EP signs
     static constexpr bool POINT_RATIO = false; // the item's points enter as (x, y)
+    static constexpr bool QCANON = false;      // canonicalisation by the step ladder only (at most 4 steps here)
+    static __device__ __forceinline__ void canon_q(uint32_t*) {}
     static __device__ __forceinline__ void add_kp(uint32_t* acc, const uint32_t* k) { coop_acc_add_e12(acc, k); }
     static __device__ __forceinline__ void xi(uint32_t*, uint32_t*) {}
     static __device__ __forceinline__ const uint32_t* prog() { return COOP_PROG_BLS; }
@@ -93,7 +96,7 @@ template <> struct Coop<Bn> {
     static constexpr int GROUPS = BBS_COOP_GROUPS_BN;
     static constexpr int MAXREG = BBS_COOP_MAXREG_BN;
     static constexpr int RW = 9;
-    static constexpr int MAXK = 64;
+    static constexpr int MAXK = 64;            // (bound of the reduction output: 128 p)
     static constexpr int PARK = 3;
     static constexpr bool ACC_XI = true;
     static constexpr bool POINT_RATIO = true;  // D-type twist: the line is normalised by 1/y, the points enter as (x/y, 1/y)
@@ -121,6 +124,28 @@ template <> struct Coop<Bn> {
         if (K == 4) return coop_sub_4p_bn9(d, r);
         if (K == 2) return coop_sub_2p_bn9(d, r);
         return coop_sub_1p_bn9(d, r);
+    }
+    // w (9 words, < 128 p) -> w mod p by a quotient estimate: q^ = floor(top 29 bits of w * floor(2^32 / (top 22 bits of
+    // p + 1)) / 2^32) is q or q - 1 (q = floor(w / p) < 128; bound in tools/gen_coop.py check_canon_q), so one multiply-
+    // subtract by q^ p and ONE conditional subtraction replace the 5..7 conditional subtractions of the step ladder
+    static constexpr bool QCANON = true;
+    static __device__ __forceinline__ void canon_q(uint32_t* w) {
+        const uint32_t* p = BN_FP_P();
+        const uint32_t v = (w[8] << 24) | (w[7] >> 8);
+        const uint32_t q = __umulhi(v, COOP_BN_QCANON_M);
+        uint32_t t[9];
+        uint64_t c = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { c += (uint64_t)p[i] * q; t[i] = (uint32_t)c; c >>= 32; }
+        t[8] = (uint32_t)c;
+        asm("sub.cc.u32 %0, %0, %9; subc.cc.u32 %1, %1, %10; subc.cc.u32 %2, %2, %11; subc.cc.u32 %3, %3, %12; subc.cc.u32 %4, %4, %13; "
+            "subc.cc.u32 %5, %5, %14; subc.cc.u32 %6, %6, %15; subc.cc.u32 %7, %7, %16; subc.u32 %8, %8, %17;"
+            : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]), "+r"(w[8])
+            : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]), "r"(t[8]));
+        uint32_t d[9];
+        const uint32_t b = coop_sub_1p_bn9(d, w);
+#pragma unroll
+        for (int i = 0; i < 9; i++) w[i] = b ? w[i] : d[i];
     }
     // (R, I) <- xi (R, I) = (9R - I, 9I + R) on the 17-word two's-complement accumulators
     static __device__ __forceinline__ void xi(uint32_t* R, uint32_t* I) {
@@ -226,15 +251,17 @@ template <class C> __device__ __forceinline__ void coop_finish2(uint32_t* r0, ui
 #define COOP_CANON_STEP(K)                                                                     \
     b0 = Coop<C>::template sub_kp<K>(d0, w0); b1 = Coop<C>::template sub_kp<K>(d1, w1);         \
     _Pragma("unroll") for (int i = 0; i < RW; i++) { w0[i] = b0 ? w0[i] : d0[i]; w1[i] = b1 ? w1[i] : d1[i]; }
-    if constexpr (Coop<C>::MAXK >= 64) {
-        if (canon >= 6) { COOP_CANON_STEP(64) }
-        if (canon >= 5) { COOP_CANON_STEP(32) }
-        if (canon >= 4) { COOP_CANON_STEP(16) }
+    if (Coop<C>::QCANON && canon >= 2) {
+        Coop<C>::canon_q(w0);
+        Coop<C>::canon_q(w1);
+    } else {
+        if constexpr (!Coop<C>::QCANON) {
+            if (canon >= 3) { COOP_CANON_STEP(8) }
+            if (canon >= 2) { COOP_CANON_STEP(4) }
+        }
+        if (canon >= 1) { COOP_CANON_STEP(2) }
+        COOP_CANON_STEP(1)
     }
-    if (canon >= 3) { COOP_CANON_STEP(8) }
-    if (canon >= 2) { COOP_CANON_STEP(4) }
-    if (canon >= 1) { COOP_CANON_STEP(2) }
-    COOP_CANON_STEP(1)
 #undef COOP_CANON_STEP
 #pragma unroll
     for (int i = 0; i < N; i++) { r0[i] = w0[i]; r1[i] = w1[i]; }

@@ -366,6 +366,20 @@ def check_redc_wide(n, p, limit_p2, trials=300):
         assert (r * R - T) % p == 0 and r < T // R + p + 1, (n, t)
 
 
+def check_canon_q(p, trials=200000):
+    """pairing_coop.cuh Coop<Bn>::canon_q: the quotient estimate from the top 29 bits is q or q - 1 for every w < 128 p"""
+    M = (1 << 32) // ((p >> 232) + 1)
+    assert M == 1354
+    rnd = random.Random(77)
+    cases = [k * p + d for k in range(128) for d in (-1, 0, 1, 1 << 200, -(1 << 200)) if 0 <= k * p + d < 128 * p]
+    cases += [rnd.randrange(128 * p) for _ in range(trials)]
+    for w in cases:
+        v = ((w >> 256) << 24) | (((w >> 224) & MASK) >> 8)
+        assert v < 1 << 32
+        q = (v * M) >> 32
+        assert q in (w // p, w // p - 1), (w, q)
+
+
 def check_redc(n, p, trials=300):
     R = 1 << (32 * n)
     rnd = random.Random(200 + n)
@@ -533,6 +547,7 @@ def main():
     for cname, (n, p) in CURVES.items():
         check_redc(n, p)
     check_redc_wide(8, P_BN, 127 * (1 << 256) // P_BN)
+    check_canon_q(P_BN)
     txt = emit_all()
     with open(OUT, "w") as f:
         f.write(txt)
