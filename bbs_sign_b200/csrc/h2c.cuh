@@ -12,8 +12,7 @@ namespace bbs {
 BBS_HDN void xmd_expand(uint32_t* out, int len_bytes, const uint8_t* m1, uint32_t m1_len, const uint8_t* m2,
                         uint32_t m2_len, const uint8_t* dst, uint32_t dst_len) {
     Sha256 s;
-    s.init();
-    for (int i = 0; i < 64; i++) s.put(0);
+    s.init_after_zpad();
     s.update(m1, m1_len);
     s.update(m2, m2_len);
     s.put((uint8_t)(len_bytes >> 8)); s.put((uint8_t)len_bytes); s.put(0);

@@ -66,14 +66,32 @@ struct Sha256 {
         fill++; total++;
         if (fill == 64) compress();
     }
+    // one big-endian word; the block position must be word-aligned
+    BBS_HD void put_word(uint32_t x) {
+        w[fill >> 2] = x;
+        fill += 4; total += 4;
+        if (fill == 64) compress();
+    }
     BBS_HDN void update(const uint8_t* p, uint32_t n) {
-        for (uint32_t i = 0; i < n; i++) put(p[i]);
+        uint32_t i = 0;
+        while (i < n && (fill & 3)) put(p[i++]);
+        for (; i + 4 <= n; i += 4)
+            put_word(((uint32_t)p[i] << 24) | ((uint32_t)p[i + 1] << 16) | ((uint32_t)p[i + 2] << 8) | p[i + 3]);
+        for (; i < n; i++) put(p[i]);
     }
     // 32 bytes given as 8 big-endian words
     BBS_HD void update_words(const uint32_t* x, int nwords) {
         for (int i = 0; i < nwords; i++) {
-            put((uint8_t)(x[i] >> 24)); put((uint8_t)(x[i] >> 16)); put((uint8_t)(x[i] >> 8)); put((uint8_t)x[i]);
+            if ((fill & 3) == 0) put_word(x[i]);
+            else { put((uint8_t)(x[i] >> 24)); put((uint8_t)(x[i] >> 16)); put((uint8_t)(x[i] >> 8)); put((uint8_t)x[i]); }
         }
+    }
+    // state after absorbing the 64 zero bytes Z_pad of expand_message_xmd (utilities_helper.rs:55): a constant
+    BBS_HD void init_after_zpad() {
+        h[0] = 0xda5698beu; h[1] = 0x17b9b469u; h[2] = 0x62335799u; h[3] = 0x779fbecau;
+        h[4] = 0x8ce5d491u; h[5] = 0xc0d26243u; h[6] = 0xbafef9eau; h[7] = 0x1837a9d8u;
+        for (int i = 0; i < 16; i++) w[i] = 0;
+        fill = 0; total = 64;
     }
     BBS_HD void put_be64(uint64_t v) {
         for (int i = 7; i >= 0; i--) put((uint8_t)(v >> (8 * i)));
@@ -82,7 +100,8 @@ struct Sha256 {
         uint32_t bits_lo = total << 3, bits_hi = total >> 29;
         uint32_t t = total;
         put(0x80);
-        while (fill != 56) put(0);
+        while (fill & 3) put(0);
+        while (fill != 56) put_word(0);
         w[14] = bits_hi; w[15] = bits_lo;
         compress();
         total = t;
@@ -94,10 +113,7 @@ struct Sha256 {
 // finish().  Output: 48 uniform bytes as 12 big-endian words.
 struct Xmd48 {
     Sha256 s;
-    BBS_HD void begin() {
-        s.init();
-        for (int i = 0; i < 64; i++) s.put(0);   // Z_pad (utilities_helper.rs:55)
-    }
+    BBS_HD void begin() { s.init_after_zpad(); }     // Z_pad (utilities_helper.rs:55) absorbed as a precomputed midstate
     BBS_HDN void finish(const uint8_t* dst, uint32_t dst_len, uint32_t* out12) {
         s.put(0); s.put(48); s.put(0);           // I2OSP(48, 2) || 0x00 (utilities_helper.rs:57)
         s.update(dst, dst_len); s.put((uint8_t)dst_len);
