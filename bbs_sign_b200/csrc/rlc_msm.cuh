@@ -183,7 +183,7 @@ template <class C> __global__ void __launch_bounds__(128, 4) msm_bucket_kernel(c
 struct MsmReduceArgs { MsmPlan plan; const uint32_t* buckets; uint32_t* row_part; };     // row_part[row][block][Jacobian]
 // grid (red_blocks, rows): thread t of a row owns the digits t*chunk + 1 .. t*chunk + chunk and produces
 // sum_j (t*chunk + j) bucket[t*chunk + j] = tot + (t*chunk) run  by running sums; the block adds its threads' points
-template <class C> __global__ void __launch_bounds__(RLC_TPB, 2) msm_reduce_kernel(const MsmReduceArgs a) {
+template <class C> __global__ void __launch_bounds__(RLC_TPB, 4) msm_reduce_kernel(const MsmReduceArgs a) {
     __shared__ uint32_t sp[RLC_TPB][3 * C::Fp::N];
     const uint32_t c = a.plan.c, chunk = a.plan.chunk, row = blockIdx.y;
     const uint32_t t = blockIdx.x * RLC_TPB + threadIdx.x, base = t * chunk, nd = 1u << msm_digit_bits(row % a.plan.W, a.plan.W);
@@ -231,6 +231,7 @@ template <class C> __global__ void __launch_bounds__(RLC_TPB, 1) rlc_msm_finish_
     __shared__ uint32_t ss[RLC_TPB][8];
     __shared__ uint32_t sums[MAX_L + 1][8];
     __shared__ uint32_t res[3][3 * C::Fp::N];        // S1, S2', F
+    __shared__ uint32_t sf[32][3 * C::Fp::N];        // warp 3: partial sums of F
     __shared__ uint32_t skip[2];
     const CtxView& cx = a.ctx;
     const uint32_t t = threadIdx.x, W = a.plan.W, rows = a.plan.rows;
@@ -243,33 +244,41 @@ template <class C> __global__ void __launch_bounds__(RLC_TPB, 1) rlc_msm_finish_
         if (t == 0) bn_copy<8>(sums[j], ss[0]);
         __syncthreads();
     }
-    // row totals: thread = row (rows <= 64)
+    // row totals (rows <= 64): tpr threads per row add the reduce blocks' partial points, then a small tree per row
+    const uint32_t tpr = rows <= 16 ? 8u : rows <= 32 ? 4u : rows <= 64 ? 2u : 1u;
     uint32_t acc[G1J];
-    g1_set_inf<C>(acc);
-    if (t < rows)
-        for (uint32_t b = 0; b < a.plan.red_blocks; b++) g1_add<C>(acc, acc, a.row_part + ((size_t)t * a.plan.red_blocks + b) * G1J);
-    if (t < 96) g1_copy<C>(sp[t], acc);
-    __syncthreads();
+    {
+        const uint32_t row = t / tpr, sub = t % tpr;
+        g1_set_inf<C>(acc);
+        if (row < rows)
+            for (uint32_t b = sub; b < a.plan.red_blocks; b += tpr) g1_add<C>(acc, acc, a.row_part + ((size_t)row * a.plan.red_blocks + b) * G1J);
+        g1_copy<C>(sp[t], acc);
+        __syncthreads();
+        for (uint32_t st = tpr / 2; st >= 1; st >>= 1) {
+            if (row < rows && sub < st) g1_add<C>(sp[t], sp[t], sp[t + st]);
+            __syncthreads();
+        }
+    }
     const uint32_t job = t >> 5, lane = t & 31;
     g1_set_inf<C>(acc);
     if (job < 2) {
         if (lane == 0) {
             for (int w = (int)W - 1; w >= 0; w--) {
                 for (uint32_t k = msm_digit_bits(w, W); k > 0; k--) g1_dbl<C>(acc, acc);
-                g1_add<C>(acc, acc, sp[job * W + w]);
+                g1_add<C>(acc, acc, sp[(job * W + w) * tpr]);
             }
             g1_copy<C>(res[job], acc);
         }
     } else if (job == 3) {
         for (uint32_t j = lane; j <= a.n_msgs; j += 32)
             if (!(j == 0 && cx.k_inf)) tab_accumulate<C>(acc, cx.tab, j, sums[j]);
-        g1_copy<C>(sp[t], acc);                              // sp[96..127]: warp 3 only
+        g1_copy<C>(sf[lane], acc);                           // warp 3 only
         __syncwarp();
         for (int st = 16; st >= 1; st >>= 1) {
-            if (lane < (uint32_t)st) g1_add<C>(sp[t], sp[t], sp[t + st]);
+            if (lane < (uint32_t)st) g1_add<C>(sf[lane], sf[lane], sf[lane + st]);
             __syncwarp();
         }
-        if (lane == 0) g1_copy<C>(res[2], sp[t]);
+        if (lane == 0) g1_copy<C>(res[2], sf[0]);
     }
     __syncthreads();
     if (lane == 0 && job < 2) {
