@@ -280,6 +280,7 @@ __global__ void __maxnreg__(Coop<C>::MAXREG) pairing_coop_kernel(const CoopArgs 
     const uint32_t gblock = blockIdx.x * COOP_GROUPS + group;      // 32-item group index
     const uint32_t item = gblock * COOP_ITEMS + lane;
 #define COOP_BAR() asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(COOP_ROLES * 32) : "memory")
+    if (gblock * COOP_ITEMS >= a.n) return;          // a whole group without items (its named barrier is its own)
     const bool valid = item < a.n;
     const uint32_t fl = valid ? a.flags[item] : (uint32_t)(FL_DONE | FL_SKIP0 | FL_SKIP1);
     uint4* cells = smem + lane;
