@@ -7,7 +7,7 @@
 //     sum r_i B_i = (sum r_i) K + sum_j (sum_i r_i m_ij) H_j
 // so the per-item work is one decompression and the item's share of two bucket MSMs (rlc_msm.cuh).  Every GPU reduces
 // its shard to two G1 points; the partial points of all shards are added and checked with ONE pairing product by
-// rlc_combine (no collective: 2 compressed points per GPU travel through the host).
+// rlc_combine_kernel (no collective: 2 compressed points per GPU travel through the host).
 #pragma once
 #include "kernels.cuh"
 
@@ -66,32 +66,50 @@ struct RlcCombineArgs {
     const uint8_t* parts; uint32_t n_parts;      // n_parts x (comp(S1) || comp(S2))
     uint32_t* pair; uint32_t* flags; uint8_t* status;
 };
-// one thread: adds the shards' partial points and prepares the single pairing check
-template <class C> BBS_HD void rlc_combine_item(const RlcCombineArgs& a, uint32_t) {
+// one block: the shards' compressed partial points are decompressed one per thread (a square root each, all at once),
+// added per sum by a block tree, normalised in two warps and handed to the single pairing check
+template <class C> __global__ void __launch_bounds__(RLC_TPB, 1) rlc_combine_kernel(const RlcCombineArgs a) {
     using F = typename C::Fp;
+    __shared__ uint32_t sp[RLC_TPB][3 * C::Fp::N];
+    __shared__ uint32_t S[2][3 * C::Fp::N];
+    __shared__ uint32_t bad, skip[2];
     const CtxView& cx = a.ctx;
-    uint32_t S[2][G1J];
-    g1_set_inf<C>(S[0]);
-    g1_set_inf<C>(S[1]);
-    for (uint32_t k = 0; k < a.n_parts; k++)
-        for (int w = 0; w < 2; w++) {
-            uint32_t p[G1A];
-            int st = g1_decompress<C>(p, a.parts + ((size_t)k * 2 + w) * C::G1_BYTES);
-            if (st == PT_BAD) { a.status[0] = ST_ERR_MALFORMED; a.flags[0] = FL_DONE; return; }
-            if (st == PT_OK) g1_add_mixed<C>(S[w], S[w], p);
-        }
-    uint32_t* pr = a.pair;
-    uint32_t fl = 0;
-    for (int w = 0; w < 2; w++) {
-        uint32_t aff[G1A];
-        bool fin = g1_to_affine<C>(aff, S[w]);
-        bn_copy<2 * C::Fp::N>(pr + w * 3 * FPN, aff);
-        fe_set_one<F>(pr + w * 3 * FPN + 2 * FPN);
-        if (!fin) fl |= (w == 0 ? FL_SKIP0 : FL_SKIP1);
+    const uint32_t t = threadIdx.x;
+    if (t == 0) bad = 0;
+    __syncthreads();
+    uint32_t acc[G1J];
+    g1_set_inf<C>(acc);
+    for (uint32_t idx = t; idx < 2 * a.n_parts; idx += RLC_TPB) {     // RLC_TPB is even: a thread only meets its own sum
+        uint32_t p[G1A];
+        const int st = g1_decompress<C>(p, a.parts + (size_t)idx * C::G1_BYTES);
+        if (st == PT_BAD) atomicOr(&bad, 1u);
+        if (st == PT_OK) g1_add_mixed<C>(acc, acc, p);
     }
-    if (cx.w_inf) fl |= FL_SKIP0;
-    a.flags[0] = fl;
-    a.status[0] = ST_REJECT;
+    for (uint32_t w = 0; w < 2; w++) {
+        uint32_t mine[G1J];
+        if ((t & 1) == w) g1_copy<C>(mine, acc); else g1_set_inf<C>(mine);
+        rlc_block_sum_points<C>(sp, mine);
+        if (t == 0) g1_copy<C>(S[w], sp[0]);
+        __syncthreads();
+    }
+    if (bad) {
+        if (t == 0) { a.status[0] = ST_ERR_MALFORMED; a.flags[0] = FL_DONE; }
+        return;
+    }
+    if ((t & 31) == 0 && (t >> 5) < 2) {
+        const uint32_t w = t >> 5;
+        uint32_t aff[G1A];
+        const bool fin = g1_to_affine<C>(aff, S[w]);
+        uint32_t* pr = a.pair + w * 3 * FPN;
+        bn_copy<2 * C::Fp::N>(pr, aff);
+        fe_set_one<F>(pr + 2 * FPN);
+        skip[w] = fin ? 0u : 1u;
+    }
+    __syncthreads();
+    if (t == 0) {
+        a.flags[0] = ((skip[0] || cx.w_inf) ? FL_SKIP0 : 0u) | (skip[1] ? FL_SKIP1 : 0u);
+        a.status[0] = ST_REJECT;
+    }
 }
 
 }  // namespace bbs

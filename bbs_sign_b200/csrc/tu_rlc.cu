@@ -47,7 +47,9 @@ template <class C> int launch_rlc_msm_finish(const RlcMsmFinishArgs& a, rt_strea
     return 0;
 }
 template <class C> int launch_rlc_combine(const RlcCombineArgs& a, rt_stream_t s) {
-    return rt_launch<RlcCombineArgs, &rlc_combine_item<C>, 32>(a, 1, s);
+    rlc_combine_kernel<C><<<1, RLC_TPB, 0, s>>>(a);
+    RT_CHECK(cudaGetLastError());
+    return 0;
 }
 
 #if defined(BBS_TU_BLS) || !defined(BBS_TU_BN)
