@@ -559,6 +559,7 @@ struct Impl {
         TRY(stage(c->s_msgs, msgs, off[count], s));
         TRY(stage(c->s_offsets, off, (count + 1) * 8, s));
         TRY(c->s_scalars.reserve(count * 32));
+        PROF(c, 0, s);
         TRY(h2s_dev(c, count, (const uint8_t*)c->s_msgs.p, (const uint64_t*)c->s_offsets.p, (uint8_t*)c->s_scalars.p, s));
         return sign_common(c, sk, n, n_msgs, sigs_out, b_out, status);
     }

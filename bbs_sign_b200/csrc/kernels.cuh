@@ -338,17 +338,18 @@ struct SignArgs {
     uint8_t* b_out;            // optional: n x G1 compressed B (row a7)
     uint8_t* status;
 };
-template <class C> BBS_HD void sign_item(const SignArgs& a, uint32_t i) {
+// core_sign in three parts around its three inversions (1 / B.Z, 1 / (sk + e), 1 / A.Z), so that the CUDA build can take
+// each of them once per block (sign_kernel below) while the host simulation inverts per item (sign_item).
+// Part 1: B (Jacobian), e, and sk + e in Montgomery form.  false: the item's status is final.
+template <class C> BBS_HD bool sign_head(const SignArgs& a, uint32_t i, uint32_t* B, uint32_t* e, uint32_t* sm) {
     using Fr = typename C::Fr;
     const CtxView& cx = a.ctx;
-    uint8_t* out = a.sigs_out + (size_t)i * (C::G1_BYTES + 32);
-    if (a.n_msgs != cx.L) { a.status[i] = ST_ERR_MSG_GEN_LEN; return; }            // sign.rs:76-79
+    if (a.n_msgs != cx.L) { a.status[i] = ST_ERR_MSG_GEN_LEN; return false; }     // sign.rs:76-79
     const uint8_t* sc = a.scalars + (size_t)i * a.n_msgs * 32;
     // e = H2S(BE(sk) || BE(m_1..m_L) || BE(domain), api_id || "H2S_")   (sign.rs:90-118)
     Xmd48 x;
     x.begin();
     for (int k = 7; k >= 0; k--) x.s.update_words(&a.sk[k], 1);
-    uint32_t B[G1J];
     if (cx.k_inf) g1_set_inf<C>(B); else g1_from_affine<C>(B, cx.K);
     bool ok = true;
     for (uint32_t j = 0; j < a.n_msgs && ok; j++) {
@@ -358,24 +359,92 @@ template <class C> BBS_HD void sign_item(const SignArgs& a, uint32_t i) {
         for (int k = 7; k >= 0; k--) x.s.update_words(&m[k], 1);
         tab_accumulate<C>(B, cx.tab, j + 1, m);                                      // sign.rs:120-126
     }
-    if (!ok) { a.status[i] = ST_ERR_MALFORMED; return; }
+    if (!ok) { a.status[i] = ST_ERR_MALFORMED; return false; }
     for (int k = 7; k >= 0; k--) x.s.update_words(&cx.domain[k], 1);
-    uint32_t okm[12], e[8], s[8], sm[8];
+    uint32_t okm[12], s[8];
     x.finish(cx.dst_h2s, cx.dst_h2s_len, okm);
     okm48_to_scalar<Fr>(e, okm);
     fe_add<Fr>(s, a.sk, e);
-    if (bn_is_zero<8>(s)) { a.status[i] = ST_ERR_MALFORMED; return; }               // sign.rs:129 panics
-    fe_to_mont<Fr>(sm, s); fe_inv<Fr>(sm, sm); fe_from_mont<Fr>(s, sm);              // (sk+e)^-1
-    // A = B * (sk + e)^-1 (sign.rs:130) with the windowed GLV multiplication; B is normalised first (its affine
-    // form is also what the optional B output serialises)
-    uint32_t Aj[G1J], Baff[G1A];
-    bool bfin = g1_to_affine<C>(Baff, B);
-    if (bfin) g1_mul_scalar<C>(Aj, Baff, s); else g1_set_inf<C>(Aj);
-    g1_compress<C>(out, Aj);
+    if (bn_is_zero<8>(s)) { a.status[i] = ST_ERR_MALFORMED; return false; }        // sign.rs:129 panics
+    fe_to_mont<Fr>(sm, s);
+    return true;
+}
+// Part 2: A = B * (sk + e)^-1 (sign.rs:130) with the windowed GLV multiplication; B is normalised first (its affine form is
+// also what the optional B output serialises).  zinv = 1 / B.Z (unused for the identity), sinv = (sk + e)^-1 (Montgomery).
+template <class C> BBS_HD void sign_mid(uint32_t* Aj, uint32_t* Baff, bool& bfin, const uint32_t* B, const uint32_t* zinv,
+                                        const uint32_t* sinv) {
+    using F = typename C::Fp;
+    uint32_t s[8];
+    fe_from_mont<typename C::Fr>(s, sinv);
+    bfin = !g1_is_inf_ool<C>(B);
+    if (bfin) {
+        uint32_t zi2[FPN];
+        fe_sqr<F>(zi2, zinv);
+        fe_mul<F>(Baff, B, zi2);
+        fe_mul<F>(zi2, zi2, zinv);
+        fe_mul<F>(Baff + FPN, B + FPN, zi2);
+        g1_mul_scalar<C>(Aj, Baff, s);
+    } else {
+        bn_zero<2 * C::Fp::N>(Baff);
+        g1_set_inf<C>(Aj);
+    }
+}
+// Part 3: serialise.  zinv = 1 / A.Z (unused for the identity)
+template <class C> BBS_HD void sign_tail(const SignArgs& a, uint32_t i, const uint32_t* Aj, const uint32_t* zinv, const uint32_t* e,
+                                         const uint32_t* Baff, bool bfin) {
+    using F = typename C::Fp;
+    uint8_t* out = a.sigs_out + (size_t)i * (C::G1_BYTES + 32);
+    uint32_t aff[G1A];
+    const bool afin = !g1_is_inf_ool<C>(Aj);
+    if (afin) {
+        uint32_t zi2[FPN];
+        fe_sqr<F>(zi2, zinv);
+        fe_mul<F>(aff, Aj, zi2);
+        fe_mul<F>(zi2, zi2, zinv);
+        fe_mul<F>(aff + FPN, Aj + FPN, zi2);
+    } else {
+        bn_zero<2 * C::Fp::N>(aff);
+    }
+    g1_compress_affine<C>(out, aff, !afin);
     limbs_to_le<8>(out + C::G1_BYTES, e);
     if (a.b_out) g1_compress_affine<C>(a.b_out + (size_t)i * C::G1_BYTES, Baff, !bfin);
     a.status[i] = ST_ACCEPT;
 }
+// one item, its own inversions (host simulation; the CUDA build uses sign_kernel below)
+template <class C> BBS_HD void sign_item(const SignArgs& a, uint32_t i) {
+    using F = typename C::Fp;
+    uint32_t B[G1J], e[8], sm[8], zinv[FPN], Aj[G1J], Baff[G1A];
+    if (!sign_head<C>(a, i, B, e, sm)) return;
+    if (!g1_is_inf_ool<C>(B)) fe_inv<F>(zinv, B + 2 * FPN);
+    fe_inv<typename C::Fr>(sm, sm);
+    bool bfin;
+    sign_mid<C>(Aj, Baff, bfin, B, zinv, sm);
+    if (!g1_is_inf_ool<C>(Aj)) fe_inv<F>(zinv, Aj + 2 * FPN);
+    sign_tail<C>(a, i, Aj, zinv, e, Baff, bfin);
+}
+
+#if defined(__CUDACC__) && !defined(BBS_HOSTSIM)
+// the three inversions of core_sign, each taken once per block (block_batch_inverse: Montgomery's trick as a product tree)
+template <class C, int TPB, int MINB> __global__ void __launch_bounds__(TPB, MINB) sign_kernel(const SignArgs a, uint32_t n) {
+    using F = typename C::Fp;
+    using Fr = typename C::Fr;
+    __shared__ uint32_t tree[2 * TPB][C::Fp::N];
+    const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+    uint32_t B[G1J], e[8], sm[8], z[FPN], Aj[G1J], Baff[G1A];
+    const bool live = i < n && sign_head<C>(a, i, B, e, sm);
+    if (live && !g1_is_inf_ool<C>(B)) bn_copy<C::Fp::N>(z, B + 2 * FPN); else fe_set_one<F>(z);
+    if (!live) fe_set_one<Fr>(sm);
+    block_batch_inverse<F, TPB>(z, tree);
+    __syncthreads();
+    block_batch_inverse<Fr, TPB>(sm, (uint32_t (*)[Fr::N])tree);
+    __syncthreads();
+    bool bfin = false;
+    if (live) sign_mid<C>(Aj, Baff, bfin, B, z, sm);
+    if (live && !g1_is_inf_ool<C>(Aj)) bn_copy<C::Fp::N>(z, Aj + 2 * FPN); else fe_set_one<F>(z);
+    block_batch_inverse<F, TPB>(z, tree);
+    if (live) sign_tail<C>(a, i, Aj, z, e, Baff, bfin);
+}
+#endif
 
 // ---- core_proof_verify, G1 half ---------------------------------------------------------------------------
 struct ProofG1Args {
