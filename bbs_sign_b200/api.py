@@ -31,7 +31,6 @@ from . import _native
 ST_REJECT, ST_ACCEPT, ST_ERR_MSG_GEN_LEN, ST_ERR_DISCLOSED_INDEX, ST_ERR_IDX_MSG_LEN, ST_ERR_MALFORMED = range(6)
 ST_ERR_DISCLOSED_LEN, ST_ERR_RANDOM_LEN = 6, 7
 
-_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
 
 class BbsError(RuntimeError):
@@ -61,20 +60,8 @@ class Ciphersuite:
 
     def create_generators(self, count: int, api_id: Optional[bytes] = None, device: int = 0,
                           lib_path: Optional[str] = None) -> bytes:
-        """`create_generators(count, api_id)` (interface_utilities.rs:47-73) as `count` compressed G1 points.
-        For the suite's own api_id the first 129 are shipped as a table (tools/gen_generators.py: they are constants
-        of the ciphersuite, prefix-stable); anything else is derived on the GPU by bbs_create_generators."""
-        if api_id is None or api_id == self.api_id:
-            path = os.path.join(_DATA, f"generators_{self.name.lower()}.bin")
-            with open(path, "rb") as f:
-                blob = f.read()
-            if count <= len(blob) // self.g1_bytes:
-                return blob[: count * self.g1_bytes]
-        return self.derive_generators(count, api_id, device, lib_path)
-
-    def derive_generators(self, count: int, api_id: Optional[bytes] = None, device: int = 0,
-                          lib_path: Optional[str] = None) -> bytes:
-        """create_generators on the device (hash-to-G1 of the suite, csrc/h2c.cuh)."""
+        """`create_generators(count, api_id)` (interface_utilities.rs:47-73) as `count` compressed G1 points, derived on
+        the GPU by bbs_create_generators with the suite's hash-to-G1 (csrc/h2c.cuh).  `api_id` defaults to the suite's."""
         lib = _native.load(lib_path)
         aid = self.api_id if api_id is None else api_id
         out = np.zeros(max(count, 1) * self.g1_bytes, dtype=np.uint8)
@@ -82,6 +69,8 @@ class Ciphersuite:
         if rc != 0:
             raise BbsError(f"bbs_create_generators failed ({rc}): {lib.bbs_last_error().decode()}")
         return out[: count * self.g1_bytes].tobytes()
+
+    derive_generators = create_generators
 
 
 BLS12_381 = Ciphersuite("BLS12_381", 1, 48, 96, b"BBS_BLS12381G1_XMD:SHA-256_SSWU_RO_")
@@ -118,7 +107,7 @@ class BatchContext:
         if generators is None:
             if n_messages is None:
                 raise BbsError("n_messages or generators required")
-            generators = suite.create_generators(n_messages + 1)
+            generators = suite.create_generators(n_messages + 1, device=device, lib_path=lib_path)
         if len(generators) % suite.g1_bytes:
             raise BbsError("generators must be a whole number of compressed G1 points")
         self.n_generators = len(generators) // suite.g1_bytes

@@ -491,12 +491,17 @@ def case_readme_example(lib_path, curve_name):
 def case_create_generators(lib_path, curve_name, count=5):
     """create_generators on the device (interface_utilities.rs:47-73, hash-to-G1 :24-44) against the oracle: the
     suite's own api_id (for BLS12-381 these are the IRTF generators of test_vector.rs:124-136), a foreign api_id, and
-    the shipped table as a prefix of the derived list."""
+    the fixture tests/golden/generators_<suite>.bin (129 generators made by the oracle, tools/gen_generators.py)."""
+    import os
     suite, ocs = SUITES[curve_name]
     want = gens_bytes(ocs, O.create_generators_cached(ocs, count, ocs.api_id))
-    got = suite.derive_generators(count, lib_path=lib_path)
+    got = suite.create_generators(count, lib_path=lib_path)
     assert got == want
-    assert suite.create_generators(count) == want                      # the shipped table
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"generators_{suite.name.lower()}.bin"), "rb") as f:
+        fixture = f.read()
+    assert fixture[: len(want)] == want
+    if lib_path is None:                    # GPU: all 129 fixture generators
+        assert suite.create_generators(129) == fixture
     if curve_name == "BLS12_381":
         assert got[:48].hex() == ("a9ec65b70a7fbe40c874c9eb041c2cb0a7af36ccec1bea48fa2ba4c2eb67ef7f"
                                   "9ecb17ed27d38d27cdeddff44c8137be")       # Q1, test_vector.rs:132
