@@ -20,7 +20,6 @@ importing works anywhere, creating a context needs the built library and a GPU.
 from __future__ import annotations
 
 import ctypes as C
-import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
