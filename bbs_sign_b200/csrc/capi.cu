@@ -56,7 +56,7 @@ struct Ctx {
     bool profile = false;            // bbs_ctx_set_profiling: CUDA events around each kernel of a batch call
     ProfEvents prof;
     DevBuf pk_comp, gens_comp, api_id, header, dst_h2s, dst_map;
-    DevBuf gens, W, K, domain, tab, lines, lines_coop, misc;
+    DevBuf gens, W, K, domain, tab, wbase, lines, lines_coop, misc;
     bool coop = false;               // cooperative pairing kernel usable (no degenerate line)
     CtxView view{};
     // grow-only scratch for the batch calls
@@ -65,7 +65,7 @@ struct Ctx {
     DevBuf s_sigs, s_scalars, s_msgs, s_offsets, s_pair, s_flags, s_status, s_out, s_out2;
     DevBuf s_commit, s_commit_off, s_dis_idx, s_dis_scalars, s_dis_off, s_ph, s_dis_msgs, s_dis_msg_off;
     void release_all() {
-        DevBuf* all[] = {&pk_comp, &gens_comp, &api_id, &header, &dst_h2s, &dst_map, &gens, &W, &K, &domain, &tab,
+        DevBuf* all[] = {&pk_comp, &gens_comp, &api_id, &header, &dst_h2s, &dst_map, &gens, &W, &K, &domain, &tab, &wbase,
                          &lines, &lines_coop, &s_rand, &s_rand_off, &s_gscr, &s_rlc_pt, &s_rlc_sc, &s_rlc_parts, &s_rlc_bad, &s_msm_pts, &s_msm_kv, &s_msm_idx, &s_msm_entries, &s_msm_buckets, &misc, &s_sigs, &s_scalars, &s_msgs, &s_offsets, &s_pair, &s_flags, &s_status, &s_out,
                          &s_out2, &s_commit, &s_commit_off, &s_dis_idx, &s_dis_scalars, &s_dis_off, &s_ph, &s_dis_msgs,
                          &s_dis_msg_off};
@@ -139,8 +139,9 @@ struct Impl {
         TRY(rt_d2h(&k_inf, d_kinf, 4, s));
         TRY(rt_sync(s));
         // 3. window tables, 4. line tables
-        CtxTableArgs ta{(const uint32_t*)c->K.p, (const uint32_t*)c->gens.p, (uint32_t*)c->tab.p};
-        TRY((launch_ctx_table<C>(ta, (uint32_t)tab_entries, s)));
+        TRY(c->wbase.reserve((size_t)(L + 1) * TabGeom<C>::WINDOWS * 2 * C::Fp::N * 4));
+        CtxTableArgs ta{(const uint32_t*)c->K.p, (const uint32_t*)c->gens.p, (uint32_t*)c->tab.p, (uint32_t*)c->wbase.p};
+        TRY((launch_ctx_table<C>(ta, L + 1, s)));
         CtxLinesArgs la{(const uint32_t*)c->W.p, w_inf, (uint32_t*)c->lines.p};
         TRY((launch_ctx_lines<C>(la, 2, s)));
         TRY(rt_sync(s));

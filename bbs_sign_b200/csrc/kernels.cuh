@@ -104,23 +104,36 @@ template <class C> BBS_HD void ctx_domain_item(const CtxDomainArgs& a, uint32_t)
     *a.k_inf = g1_to_affine<C>(a.K, acc) ? 0u : 1u;
 }
 
-struct CtxTableArgs { const uint32_t* K; const uint32_t* gens; uint32_t* tab; };
-// entry (g, w, d) = (d * 2^(8w)) * base_g in affine form
-template <class C> BBS_HD void ctx_table_item(const CtxTableArgs& a, uint32_t i) {
-    constexpr uint32_t TAB_ENTRIES = TabGeom<C>::ENTRIES, TAB_WINDOWS = TabGeom<C>::WINDOWS;
+struct CtxTableArgs { const uint32_t* K; const uint32_t* gens; uint32_t* tab; uint32_t* wbase; };
+// entry (g, w, d) = (d * 2^(BITS w)) * base_g in affine form, in two steps:
+//   ctx_wbase_item: the window bases 2^(BITS w) * base_g, affine (one thread per (g, w); a K at infinity gives zeros);
+//   ctx_table_item: d * window base by a BITS-bit double-and-add, then to affine.
+template <class C> BBS_HD void ctx_wbase_item(const CtxTableArgs& a, uint32_t i) {
+    constexpr uint32_t TAB_WINDOWS = TabGeom<C>::WINDOWS;
     constexpr int TAB_BITS = TabGeom<C>::BITS;
-    uint32_t d = i % TAB_ENTRIES + 1, w = (i / TAB_ENTRIES) % TAB_WINDOWS, g = i / (TAB_ENTRIES * TAB_WINDOWS);
+    const uint32_t w = i % TAB_WINDOWS, g = i / TAB_WINDOWS;
     const uint32_t* base = g == 0 ? a.K : a.gens + g * G1A;
-    uint32_t k[10];
-    for (int j = 0; j < 10; j++) k[j] = 0;
-    {
-        const int bit = (int)w * TAB_BITS;
-        uint64_t v = (uint64_t)d << (bit & 31);
-        k[bit >> 5] = (uint32_t)v;
-        k[(bit >> 5) + 1] = (uint32_t)(v >> 32);
-    }
     uint32_t acc[G1J];
-    g1_mul_affine<C>(acc, base, k, TAB_BITS * (int)w + TAB_BITS);
+    g1_from_affine<C>(acc, base);
+    if (bn_is_zero<2 * C::Fp::N>(base)) g1_set_inf<C>(acc);          // K at infinity is stored as zeros
+    for (uint32_t k = 0; k < w * TAB_BITS; k++) g1_dbl<C>(acc, acc);
+    g1_to_affine<C>(a.wbase + (size_t)i * G1A, acc);
+}
+// Jacobian d * window base for table entry i; false when the base is the identity
+template <class C> BBS_HD bool ctx_table_head(uint32_t* acc, const CtxTableArgs& a, uint32_t i) {
+    constexpr uint32_t TAB_ENTRIES = TabGeom<C>::ENTRIES;
+    constexpr int TAB_BITS = TabGeom<C>::BITS;
+    const uint32_t d = i % TAB_ENTRIES + 1;
+    const uint32_t* wb = a.wbase + (size_t)(i / TAB_ENTRIES) * G1A;      // (g, w) = i / ENTRIES
+    if (bn_is_zero<2 * C::Fp::N>(wb)) { g1_set_inf<C>(acc); return false; }
+    uint32_t k[1] = {d};
+    g1_mul_affine<C>(acc, wb, k, TAB_BITS);
+    return true;
+}
+// one entry with its own inversion (host simulation; the CUDA build uses ctx_table_kernel below)
+template <class C> BBS_HD void ctx_table_item(const CtxTableArgs& a, uint32_t i) {
+    uint32_t acc[G1J];
+    ctx_table_head<C>(acc, a, i);
     g1_to_affine<C>(a.tab + (size_t)i * G1A, acc);
 }
 
@@ -298,6 +311,29 @@ template <class F, int TPB> __device__ __forceinline__ void block_batch_inverse(
         __syncthreads();
     }
     bn_copy<N>(z, tree[TPB + t]);
+}
+
+// table entries with one inversion per block
+template <class C, int TPB> __global__ void __launch_bounds__(TPB, 4) ctx_table_kernel(const CtxTableArgs a, uint32_t n) {
+    using F = typename C::Fp;
+    __shared__ uint32_t tree[2 * TPB][C::Fp::N];
+    const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+    uint32_t acc[G1J], z[FPN];
+    const bool live = i < n && ctx_table_head<C>(acc, a, i) && !g1_is_inf_ool<C>(acc);
+    if (live) bn_copy<C::Fp::N>(z, acc + 2 * FPN); else fe_set_one<F>(z);
+    block_batch_inverse<F, TPB>(z, tree);
+    if (i < n) {
+        uint32_t* dst = a.tab + (size_t)i * G1A;
+        if (live) {
+            uint32_t zi2[FPN];
+            fe_sqr<F>(zi2, z);
+            fe_mul<F>(dst, acc, zi2);
+            fe_mul<F>(zi2, zi2, z);
+            fe_mul<F>(dst + FPN, acc + FPN, zi2);
+        } else {
+            bn_zero<2 * C::Fp::N>(dst);
+        }
+    }
 }
 
 template <class C, int TPB, int MINB> __global__ void __launch_bounds__(TPB, MINB) verify_g1_kernel(const VerifyG1Args a, uint32_t n) {

@@ -10,8 +10,17 @@ template <class C> int launch_ctx_decode(const CtxDecodeArgs& a, uint32_t n, rt_
 template <class C> int launch_ctx_domain(const CtxDomainArgs& a, uint32_t n, rt_stream_t s) {
     return rt_launch<CtxDomainArgs, &ctx_domain_item<C>, 32>(a, n, s);
 }
-template <class C> int launch_ctx_table(const CtxTableArgs& a, uint32_t n, rt_stream_t s) {
+template <class C> int launch_ctx_table(const CtxTableArgs& a, uint32_t n_generators, rt_stream_t s) {
+    const uint32_t n_bases = n_generators * TabGeom<C>::WINDOWS, n = n_bases * TabGeom<C>::ENTRIES;
+    int rc = rt_launch<CtxTableArgs, &ctx_wbase_item<C>, 32>(a, n_bases, s);
+    if (rc) return rc;
+#ifdef BBS_HOSTSIM
     return rt_launch<CtxTableArgs, &ctx_table_item<C>, 128>(a, n, s);
+#else
+    ctx_table_kernel<C, 128><<<(n + 127) / 128, 128, 0, s>>>(a, n);
+    RT_CHECK(cudaGetLastError());
+    return 0;
+#endif
 }
 template <class C> int launch_ctx_lines(const CtxLinesArgs& a, uint32_t n, rt_stream_t s) {
     return rt_launch<CtxLinesArgs, &ctx_lines_item<C>, 32>(a, n, s);
