@@ -546,3 +546,31 @@ def case_core_api_id(lib_path, curve_name, L=5):
             want = [int(O.core_verify(ocs, pk, s, gens, other_hdr, row, other_api, trapdoor_sk=sk)) for s, row in zip(osigs, scal)]
             assert ctx2.core_verify_batch(blob, flat, L).tolist() == want == [0] * n
             ctx2.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+def case_g1_mul_edges(lib, curve_name):
+    """GLV split edge scalars through the production scalar multiplication (g1.cuh bls_glv_split / bn_glv_split): values
+    around the endomorphism eigenvalue, powers of two around 2^128, the BN254 lattice constants, r - small."""
+    suite, ocs = SUITES[curve_name]
+    r = ocs.r
+    if curve_name == "BLS12_381":
+        x = 0xD201000000010000
+        lam = x * x - 1
+        special = [lam, lam - 1, lam + 1, lam * lam % r, r - lam, 2 * lam, lam * (lam - 1) % r]
+    else:
+        t = 4965661367192848881
+        lam = 0x30644e72e131a029048b6e193fd84104cc37a73fec2bc5e9b8ca0b2d36636f23
+        a, b = 6 * t * t + 2 * t, 2 * t + 1
+        special = [lam, lam - 1, (lam + 1) % r, r - lam, a, b, a + b, a * b % r, 2 * b * b, r - a, r - b, (a * lam) % r]
+    special += [(1 << 128) - 1, 1 << 128, (1 << 128) + 1, 1 << 127, (1 << 64) - 1, r - 1, r - 2, r // 2, r // 3]
+    P = O.ec_mul(ocs.F1, ocs.BP1, 0x1234567)
+    n = len(special)
+    a_ = np.frombuffer(ocs.g1_compress(P) * n, dtype=np.uint8)
+    b_ = np.frombuffer(b"".join(k.to_bytes(32, "little") for k in special), dtype=np.uint8)
+    out = np.zeros(n * suite.g1_bytes, dtype=np.uint8)
+    rc = lib.bbs_selftest_g1_mul(suite.curve_id, 0, n, ptr(a_), ptr(b_), ptr(out))
+    assert rc == 0, lib.bbs_last_error()
+    for i, k in enumerate(special):
+        want = ocs.g1_compress(O.ec_mul(ocs.F1, P, k))
+        assert out[i * suite.g1_bytes:(i + 1) * suite.g1_bytes].tobytes() == want, (curve_name, hex(k))

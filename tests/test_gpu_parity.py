@@ -177,3 +177,8 @@ def test_multi_issuer_batch(lib):
 @pytest.mark.parametrize("curve", ["BN254", "BLS12_381"])
 def test_core_api_id(lib, curve):
     P.case_core_api_id(None, curve, L=5)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_g1_mul_edges(lib, curve):
+    P.case_g1_mul_edges(lib, curve)

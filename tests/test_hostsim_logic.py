@@ -81,3 +81,8 @@ def test_create_generators(lib_path, curve):
 @pytest.mark.parametrize("curve", ["BN254", "BLS12_381"])
 def test_core_api_id(lib_path, curve):
     P.case_core_api_id(lib_path, curve, L=3)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_g1_mul_edges(lib, curve):
+    P.case_g1_mul_edges(lib, curve)
