@@ -120,6 +120,19 @@ template <class C> BBS_HDN bool g1_to_affine(uint32_t* r, const uint32_t* p) {
     return true;
 }
 
+// the same with the variable-time inversion: for one-thread tails and context creation (public points)
+template <class C> BBS_HDN bool g1_to_affine_vt(uint32_t* r, const uint32_t* p) {
+    using F = typename C::Fp;
+    if (g1_is_inf<C>(p)) { bn_zero<2 * C::Fp::N>(r); return false; }
+    uint32_t zi[FPN], zi2[FPN];
+    fe_inv_vt<F>(zi, p + 2 * FPN);
+    fe_sqr<F>(zi2, zi);
+    fe_mul<F>(r, p, zi2);
+    fe_mul<F>(zi2, zi2, zi);
+    fe_mul<F>(r + FPN, p + FPN, zi2);
+    return true;
+}
+
 // y^2 == x^3 + b  (affine, Montgomery)
 template <class C> BBS_HDN bool g1_on_curve(const uint32_t* a) {
     using F = typename C::Fp;

@@ -73,7 +73,7 @@ BBS_HDN void bls_sswu(uint32_t* X, uint32_t* Y, const uint32_t* u) {
     fe_mul<F>(t, u2, BLS_H2C_Z());             // Z u^2
     fe_sqr<F>(tv, t);                          // Z^2 u^4
     fe_add<F>(tv, tv, t);
-    fe_inv<F>(tv1, tv);                        // inv0
+    fe_inv_vt<F>(tv1, tv);                     // inv0
     if (h2c_is_zero<N>(tv1)) bn_copy<N>(x1, BLS_H2C_BZA());
     else { fe_add<F>(x1, one, tv1); fe_mul<F>(x1, x1, BLS_H2C_NBA()); }
     // g(x1) = x1^3 + A x1 + B
@@ -98,7 +98,7 @@ BBS_HDN void bls_iso11(uint32_t* xo, uint32_t* yo, const uint32_t* X, const uint
         const uint32_t* tb = BLS_H2C_VELU() + q * 5 * N;      // xq, yq, gx*gy, vq, uq
         uint32_t d[N], d2[N], d3[N], t[N], s[N];
         fe_sub<F>(d, X, tb);
-        fe_inv<F>(d, d);
+        fe_inv_vt<F>(d, d);
         fe_sqr<F>(d2, d);
         fe_mul<F>(d3, d2, d);
         fe_mul<F>(t, tb + 3 * N, d); fe_add<F>(ax, ax, t);            // + vq d
@@ -124,10 +124,10 @@ template <> BBS_HDN void hash_to_g1<Bls>(uint32_t* out_aff, const uint8_t* msg, 
     uint32_t R[36], Ra[24], acc[36];
     g1_from_affine<Bls>(R, P0);
     g1_add_mixed<Bls>(R, R, P1);
-    g1_to_affine<Bls>(Ra, R);
+    g1_to_affine_vt<Bls>(Ra, R);
     uint32_t k[2] = {(uint32_t)BLS_H2C_HEFF, (uint32_t)(BLS_H2C_HEFF >> 32)};
     g1_mul_affine<Bls>(acc, Ra, k, 64);
-    g1_to_affine<Bls>(out_aff, acc);
+    g1_to_affine_vt<Bls>(out_aff, acc);
 }
 
 // ---- BN254: Shallue-van de Woestijne, Z = 1 (cofactor 1) -------------------------------------------------------------
@@ -139,7 +139,7 @@ BBS_HDN void bn_svdw(uint32_t* X, uint32_t* Y, const uint32_t* u) {
     fe_sqr<F>(tv1, u); fe_mul<F>(tv1, tv1, BN_H2C_C1());
     fe_add<F>(tv2, one, tv1);
     fe_sub<F>(tv1, one, tv1);
-    fe_mul<F>(tv3, tv1, tv2); fe_inv<F>(tv3, tv3);
+    fe_mul<F>(tv3, tv1, tv2); fe_inv_vt<F>(tv3, tv3);
     fe_mul<F>(tv4, u, tv1); fe_mul<F>(tv4, tv4, tv3); fe_mul<F>(tv4, tv4, BN_H2C_C3());
     fe_sub<F>(x1, BN_H2C_C2(), tv4);
     fe_add<F>(x2, BN_H2C_C2(), tv4);
@@ -172,7 +172,7 @@ template <> BBS_HDN void hash_to_g1<Bn>(uint32_t* out_aff, const uint8_t* msg, u
     uint32_t R[24];
     g1_from_affine<Bn>(R, P0);
     g1_add_mixed<Bn>(R, R, P1);
-    g1_to_affine<Bn>(out_aff, R);
+    g1_to_affine_vt<Bn>(out_aff, R);
 }
 
 // ---- create_generators -----------------------------------------------------------------------------------------------

@@ -101,7 +101,7 @@ template <class C> BBS_HD void ctx_domain_item(const CtxDomainArgs& a, uint32_t)
     g1_mul_affine<C>(acc, a.gens, dom, 256);
     g1_from_affine<C>(p1, C::P1());
     g1_add<C>(acc, acc, p1);
-    *a.k_inf = g1_to_affine<C>(a.K, acc) ? 0u : 1u;
+    *a.k_inf = g1_to_affine_vt<C>(a.K, acc) ? 0u : 1u;
 }
 
 struct CtxTableArgs { const uint32_t* K; const uint32_t* gens; uint32_t* tab; uint32_t* wbase; };
@@ -117,7 +117,7 @@ template <class C> BBS_HD void ctx_wbase_item(const CtxTableArgs& a, uint32_t i)
     g1_from_affine<C>(acc, base);
     if (bn_is_zero<2 * C::Fp::N>(base)) g1_set_inf<C>(acc);          // K at infinity is stored as zeros
     for (uint32_t k = 0; k < w * TAB_BITS; k++) g1_dbl<C>(acc, acc);
-    g1_to_affine<C>(a.wbase + (size_t)i * G1A, acc);
+    g1_to_affine_vt<C>(a.wbase + (size_t)i * G1A, acc);
 }
 // Jacobian d * window base for table entry i; false when the base is the identity
 template <class C> BBS_HD bool ctx_table_head(uint32_t* acc, const CtxTableArgs& a, uint32_t i) {
@@ -160,7 +160,7 @@ template <class C> BBS_HD void ctx_lines_coop_item(const CtxLinesCoopArgs& a, ui
     }
     if (f2_is_zero<C>(src)) { *a.degenerate = 1; bn_zero<4 * C::Fp::N>(dst); return; }
     uint32_t ai[F2N], bp[F2N];
-    f2_inv<C>(ai, src);
+    f2_inv_vt<C>(ai, src);
     f2_mul<C>(bp, src + F2N, ai);
     f2_copy<C>(dst, bp);
     f2_copy<C>(dst + F2N, ai);
@@ -282,7 +282,10 @@ template <class C> BBS_HD void verify_g1_item(const VerifyG1Args& a, uint32_t i)
 // block instead of one per thread.  On a SIMT machine an inversion costs the warp the same whether one lane or all
 // 32 need it, so the saving comes from the other warps of the block: 7 of 8 skip their ~490 multiplications and pay
 // ~25 for the tree instead.  z must be non-zero in every thread (pass 1 for items without a point); TPB a power of 2.
-template <class F, int TPB> __device__ __forceinline__ void block_batch_inverse(uint32_t* z, uint32_t (*tree)[F::N]) {
+// VT: the root is inverted by the variable-time binary Euclid instead of the Fermat ladder (public data only).  Measured:
+// context creation 2x, sign_kernel -6.5 %, verify_g1_kernel<Bn> (64-thread blocks) -2.8 %, but verify_g1_kernel<Bls>
+// (256-thread blocks) +5 %, so the callers choose.
+template <class F, int TPB, bool VT> __device__ __forceinline__ void block_batch_inverse(uint32_t* z, uint32_t (*tree)[F::N]) {
     constexpr int N = F::N;
     const int t = threadIdx.x;
     // leaves at tree[TPB + t], node k = product of its children 2k, 2k+1, root at tree[1]
@@ -294,7 +297,7 @@ template <class F, int TPB> __device__ __forceinline__ void block_batch_inverse(
     }
     if (t == 0) {
         uint32_t r[N];
-        fe_inv<F>(r, tree[1]);
+        if (VT) fe_inv_vt<F>(r, tree[1]); else fe_inv<F>(r, tree[1]);
         bn_copy<N>(tree[1], r);
     }
     __syncthreads();
@@ -321,7 +324,7 @@ template <class C, int TPB> __global__ void __launch_bounds__(TPB, 4) ctx_table_
     uint32_t acc[G1J], z[FPN];
     const bool live = i < n && ctx_table_head<C>(acc, a, i) && !g1_is_inf_ool<C>(acc);
     if (live) bn_copy<C::Fp::N>(z, acc + 2 * FPN); else fe_set_one<F>(z);
-    block_batch_inverse<F, TPB>(z, tree);
+    block_batch_inverse<F, TPB, true>(z, tree);
     if (i < n) {
         uint32_t* dst = a.tab + (size_t)i * G1A;
         if (live) {
@@ -347,7 +350,7 @@ template <class C, int TPB, int MINB> __global__ void __launch_bounds__(TPB, MIN
 #ifdef BBS_NO_BATCH_INV
     { uint32_t zz[FPN]; fe_inv<F>(zz, z); bn_copy<C::Fp::N>(z, zz); (void)tree; }
 #else
-    block_batch_inverse<F, TPB>(z, tree);
+    block_batch_inverse<F, TPB, (TPB < 256)>(z, tree);
 #endif
     if (live) verify_g1_tail<C>(a, i, Cc, z, pa);
 }
@@ -470,14 +473,14 @@ template <class C, int TPB, int MINB> __global__ void __launch_bounds__(TPB, MIN
     const bool live = i < n && sign_head<C>(a, i, B, e, sm);
     if (live && !g1_is_inf_ool<C>(B)) bn_copy<C::Fp::N>(z, B + 2 * FPN); else fe_set_one<F>(z);
     if (!live) fe_set_one<Fr>(sm);
-    block_batch_inverse<F, TPB>(z, tree);
+    block_batch_inverse<F, TPB, true>(z, tree);
     __syncthreads();
-    block_batch_inverse<Fr, TPB>(sm, (uint32_t (*)[Fr::N])tree);
+    block_batch_inverse<Fr, TPB, false>(sm, (uint32_t (*)[Fr::N])tree);      // 1 / (sk + e): secret, constant-time ladder
     __syncthreads();
     bool bfin = false;
     if (live) sign_mid<C>(Aj, Baff, bfin, B, z, sm);
     if (live && !g1_is_inf_ool<C>(Aj)) bn_copy<C::Fp::N>(z, Aj + 2 * FPN); else fe_set_one<F>(z);
-    block_batch_inverse<F, TPB>(z, tree);
+    block_batch_inverse<F, TPB, true>(z, tree);
     if (live) sign_tail<C>(a, i, Aj, z, e, Baff, bfin);
 }
 #endif

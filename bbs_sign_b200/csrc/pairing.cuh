@@ -40,7 +40,7 @@ template <class C> BBS_HD int ate_line_count() {
 template <class C> BBS_HDN void g2_dbl_step(uint32_t* line, uint32_t* T) {
     uint32_t lam[F2N], t[F2N], x3[F2N], y3[F2N];
     f2_sqr<C>(lam, T); f2_dbl<C>(t, lam); f2_add<C>(lam, lam, t);
-    f2_dbl<C>(t, T + F2N); f2_inv<C>(t, t);
+    f2_dbl<C>(t, T + F2N); f2_inv_vt<C>(t, t);
     f2_mul<C>(lam, lam, t);
     f2_mul<C>(line, lam, T); f2_sub<C>(line, line, T + F2N);       // A = lambda xT - yT
     f2_neg<C>(line + F2N, lam);                                    // Bc = -lambda
@@ -52,7 +52,7 @@ template <class C> BBS_HDN void g2_dbl_step(uint32_t* line, uint32_t* T) {
 template <class C> BBS_HDN void g2_add_step(uint32_t* line, uint32_t* T, const uint32_t* Q) {
     uint32_t lam[F2N], t[F2N], x3[F2N], y3[F2N];
     f2_sub<C>(lam, Q + F2N, T + F2N);
-    f2_sub<C>(t, Q, T); f2_inv<C>(t, t);
+    f2_sub<C>(t, Q, T); f2_inv_vt<C>(t, t);
     f2_mul<C>(lam, lam, t);
     f2_mul<C>(line, lam, T); f2_sub<C>(line, line, T + F2N);
     f2_neg<C>(line + F2N, lam);

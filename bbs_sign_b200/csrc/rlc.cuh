@@ -99,7 +99,7 @@ template <class C> __global__ void __launch_bounds__(RLC_TPB, 1) rlc_combine_ker
     if ((t & 31) == 0 && (t >> 5) < 2) {
         const uint32_t w = t >> 5;
         uint32_t aff[G1A];
-        const bool fin = g1_to_affine<C>(aff, S[w]);
+        const bool fin = g1_to_affine_vt<C>(aff, S[w]);
         uint32_t* pr = a.pair + w * 3 * FPN;
         bn_copy<2 * C::Fp::N>(pr, aff);
         fe_set_one<F>(pr + 2 * FPN);

@@ -289,7 +289,7 @@ template <class C> __global__ void __launch_bounds__(RLC_TPB, 1) rlc_msm_finish_
             g1_neg<C>(nF, res[2]);
             g1_add<C>(S, res[1], nF);
         }
-        const bool fin = g1_to_affine<C>(aff, S);
+        const bool fin = g1_to_affine_vt<C>(aff, S);
         g1_compress_affine<C>(a.parts_out + job * C::G1_BYTES, aff, !fin);
         uint32_t* pr = a.pair + job * 3 * FPN;
         bn_copy<2 * C::Fp::N>(pr, aff);

@@ -10,7 +10,7 @@ struct FieldTestArgs { int op; const uint8_t* a; const uint8_t* b; uint8_t* out;
 template <class C> BBS_HD void field_test_item(const FieldTestArgs& t, uint32_t i) {
     using Fp = typename C::Fp;
     using Fr = typename C::Fr;
-    if (t.op <= 4) {
+    if (t.op <= 4 || t.op == 7) {
         constexpr int N = Fp::N;
         uint32_t a[N], b[N], r[N];
         limbs_from_le<N>(a, t.a + (size_t)i * 4 * N);
@@ -20,6 +20,7 @@ template <class C> BBS_HD void field_test_item(const FieldTestArgs& t, uint32_t 
         else if (t.op == 1) fe_add<Fp>(r, a, b);
         else if (t.op == 2) fe_sub<Fp>(r, a, b);
         else if (t.op == 3) fe_inv<Fp>(r, a);
+        else if (t.op == 7) fe_inv_vt<Fp>(r, a);
         else { if (!fe_sqrt<Fp>(r, a)) bn_zero<N>(r); }
         fe_from_mont<Fp>(r, r);
         limbs_to_le<N>(t.out + (size_t)i * 4 * N, r);
@@ -28,7 +29,7 @@ template <class C> BBS_HD void field_test_item(const FieldTestArgs& t, uint32_t 
         limbs_from_le<8>(a, t.a + (size_t)i * 32);
         limbs_from_le<8>(b, t.b + (size_t)i * 32);
         fe_to_mont<Fr>(a, a); fe_to_mont<Fr>(b, b);
-        if (t.op == 5) fe_mul<Fr>(r, a, b); else fe_inv<Fr>(r, a);
+        if (t.op == 5) fe_mul<Fr>(r, a, b); else if (t.op == 6) fe_inv<Fr>(r, a); else fe_inv_vt<Fr>(r, a);
         fe_from_mont<Fr>(r, r);
         limbs_to_le<8>(t.out + (size_t)i * 32, r);
     }

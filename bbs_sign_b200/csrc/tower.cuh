@@ -119,6 +119,19 @@ template <class C> BBS_HDN void f2_inv(uint32_t* r, const uint32_t* a) {
     fe_neg<F>(r + FPN, t);
 }
 
+// variable-time variant for context creation (one thread, public data): field.cuh fe_inv_vt
+template <class C> BBS_HDN void f2_inv_vt(uint32_t* r, const uint32_t* a) {
+    using F = typename C::Fp;
+    uint32_t n[FPN], t[FPN];
+    fe_sqr<F>(n, a);
+    fe_sqr<F>(t, a + FPN);
+    fe_add<F>(n, n, t);
+    fe_inv_vt<F>(n, n);
+    fe_mul<F>(r, a, n);
+    fe_mul<F>(t, a + FPN, n);
+    fe_neg<F>(r + FPN, t);
+}
+
 // ---- Fp6 -----------------------------------------------------------------------------------------
 template <class C> BBS_HD void f6_add(uint32_t* r, const uint32_t* a, const uint32_t* b) {
     for (int i = 0; i < 3; i++) f2_add<C>(r + i * F2N, a + i * F2N, b + i * F2N);

@@ -207,7 +207,8 @@ int bbs_ctx_kernel_times(bbs_ctx* ctx, float* ms, int n);
 int bbs_imad_peak(int device, int iters, int mode, double* gprod_per_s, float* ms);
 
 /* ---- arithmetic self-test hooks (parity tests of the field / curve layers against the oracle) ------
- * op: 0 = Fp mul, 1 = Fp add, 2 = Fp sub, 3 = Fp inv, 4 = Fp sqrt (0 if none), 5 = Fr mul, 6 = Fr inv.
+ * op: 0 = Fp mul, 1 = Fp add, 2 = Fp sub, 3 = Fp inv, 4 = Fp sqrt (0 if none), 5 = Fr mul, 6 = Fr inv,
+ *     7 = Fp inv / 8 = Fr inv by the variable-time binary Euclid used where one thread inverts public data.
  * a, b, out: n x field-size canonical little-endian values (48 / 32 bytes for Fp, 32 for Fr). */
 int bbs_selftest_field(int curve_id, int device, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out);
 /* out[i] = comp(k_i * P_i) for compressed G1 points and LE32 scalars. */

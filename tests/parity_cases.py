@@ -61,7 +61,8 @@ def case_field(lib, curve_name, n=64):
     suite, ocs = SUITES[curve_name]
     rnd = random.Random(7)
     for op, mod, width in [(0, ocs.p, ocs.fp_bytes), (1, ocs.p, ocs.fp_bytes), (2, ocs.p, ocs.fp_bytes),
-                           (3, ocs.p, ocs.fp_bytes), (4, ocs.p, ocs.fp_bytes), (5, ocs.r, 32), (6, ocs.r, 32)]:
+                           (3, ocs.p, ocs.fp_bytes), (4, ocs.p, ocs.fp_bytes), (5, ocs.r, 32), (6, ocs.r, 32),
+                           (7, ocs.p, ocs.fp_bytes), (8, ocs.r, 32)]:     # 7, 8: the variable-time inversion
         edge = [0, 1, 2, mod - 1, mod - 2, (1 << (8 * width)) % mod, (mod - 1) // 2, (mod + 1) // 2]
         xs = edge + [rnd.randrange(mod) for _ in range(n - len(edge))]
         ys = list(reversed(edge)) + [rnd.randrange(mod) for _ in range(n - len(edge))]
@@ -80,7 +81,7 @@ def case_field(lib, curve_name, n=64):
                 want = (x + y) % mod
             elif op == 2:
                 want = (x - y) % mod
-            elif op in (3, 6):
+            elif op in (3, 6, 7, 8):
                 want = pow(x, mod - 2, mod)
             else:
                 s = pow(x, (mod + 1) // 4, mod)
