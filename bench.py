@@ -564,6 +564,82 @@ def run_rlc(args):
     return out
 
 
+def run_sign(args):
+    """BASELINE configs[4], first leg: batch signing (core_sign: B, e = H2S(sk || msgs || domain), A = B * 1/(sk + e)) of n
+    message sets x L = 10 through the host-buffer call bbs_sign_batch (pinned buffers, copies inside the timed region).
+    Every step's signatures are checked once: the RLC verdict of the produced batch must be ACCEPT."""
+    import torch
+    import torch.distributed as dist
+    from bbs_sign_b200 import api, _native
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    lib = _native.load()
+    n, L = args.n, args.L
+    ctx = api.BatchContext(api.BLS12_381, IRTF_PK, header=b"", n_messages=L, device=local)
+    rng = np.random.default_rng(7 + rank)
+    pin = lambda a: torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a).pin_memory().numpy()
+    msgs = pin(rng.integers(0, 256, size=n * L * MSG_BYTES, dtype=np.uint8))
+    offs = pin(np.arange(n * L + 1, dtype=np.uint64) * MSG_BYTES).view(np.uint64)
+    sigs = pin(np.zeros(n * SIG_BYTES, dtype=np.uint8))
+    st = pin(np.zeros(n, dtype=np.uint8))
+    sk = np.frombuffer(IRTF_SK.to_bytes(32, "little"), dtype=np.uint8).copy()
+
+    def step():
+        if lib.bbs_sign_batch(ctx.handle, ptr(sk), n, ptr(msgs), ptr(offs), L, ptr(sigs), None, ptr(st)) != 0:
+            raise RuntimeError(lib.bbs_last_error().decode())
+
+    lib.bbs_ctx_set_profiling(ctx.handle, 1)
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    kt = (C.c_float * 2)()
+    lib.bbs_ctx_kernel_times(ctx.handle, kt, 2)
+    lib.bbs_ctx_set_profiling(ctx.handle, 0)
+    if not (st == 1).all():
+        raise RuntimeError("sign status vector is not all ACCEPT")
+    seed = np.frombuffer(bytes(range(32)), dtype=np.uint8).copy()
+    verdict = np.zeros(1, dtype=np.uint8)
+    if lib.bbs_rlc_verify_batch(ctx.handle, n, ptr(sigs), ptr(msgs), ptr(offs), L, ptr(seed), ptr(verdict)) != 0 or verdict[0] != 1:
+        raise RuntimeError("the signed batch does not verify")
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=torch.device("cuda", local))
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    out = None
+    if rank == 0:
+        v = world * n * args.steps / float(dt.item())
+        kernel_v = n / (float(kt[1]) * 1e-3) if kt[1] > 0 else None
+        out = {"metric": "bls12_381_bbs_signatures_per_sec_L10", "value": v, "unit": "signatures/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(dt.item()) / args.steps * 1e3,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+               "config": {"workload": f"batch sign: {n} message sets x L={L} of 32 B under one key (BASELINE configs[4], first leg; "
+                                      "host buffers, copies inside the timed region)", "n_per_gpu": n},
+               "e2e": {"value": v, "unit": "signatures/s", "h2d_bytes_per_step": int(msgs.nbytes + offs.nbytes),
+                       "d2h_bytes_per_step": int(sigs.nbytes + st.nbytes)}, "gpu_launches": 2,
+               "kernels_ms": {"msg_to_scalars": float(kt[0]), "sign_kernel": float(kt[1])},
+               "roofline": {"kernel": "sign_kernel<Bls>", "bound": "imad", "unit": "T(32x32->64 products)/s",
+                            "achieved": (kernel_v or 0) * 1.85e6 / 1e12, "peak": 9.30624,
+                            "frac": (kernel_v or 0) * 1.85e6 / 9.30624e12,
+                            "algorithmic_products_per_item": 1850000, "traffic": None,
+                            "note": "products per item are SURVEY 8d's model (8-bit fixed-base windows, 255-bit variable-base "
+                                    "multiplication); the kernel needs fewer (GLV halves, 16-bit tables, one inversion per block), "
+                                    "so the fraction can exceed 1"}}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return out
+
+
 def cpu_baseline(args, sample):
     """The oracle port of the reference's per-item path (msg_to_scalars + core_verify with two pairings) on
     the host.  Uses oracle/_ref/ (compiled C restatement, all cores) when present, else the big-int Python
@@ -609,19 +685,21 @@ def main():
     ap.add_argument("--L", type=int, default=L_DEFAULT)
     ap.add_argument("--cpu-sample", type=int, default=0, help="signatures per CPU-baseline step (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="verify", choices=["verify", "proof", "rlc", "bn254"],
+    ap.add_argument("--workload", default="verify", choices=["verify", "proof", "rlc", "bn254", "sign"],
                     help="verify = BASELINE configs[1] (the headline); proof = configs[3]-shaped proof_verify")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.n is None:
         # rlc: configs[4] per GPU (4M / 8); bn254: configs[2] per GPU (1M / 8); verify / proof: 65,536
-        args.n = {"rlc": 524288, "bn254": 131072}.get(args.workload, N_DEFAULT) if args.impl == "ours" else N_DEFAULT
+        args.n = {"rlc": 524288, "sign": 524288, "bn254": 131072}.get(args.workload, N_DEFAULT) if args.impl == "ours" else N_DEFAULT
     if args.workload == "proof" and args.impl == "ours":
         out = run_proof(args)
     elif args.workload == "rlc" and args.impl == "ours":
         out = run_rlc(args)
     elif args.workload == "bn254" and args.impl == "ours":
         out = run_bn254(args)
+    elif args.workload == "sign" and args.impl == "ours":
+        out = run_sign(args)
     else:
         out = run_reference(args) if args.impl == "reference" else run_ours(args)
     if out is not None:
