@@ -158,40 +158,67 @@ template <class C> BBS_HDN void g1_mul_affine(uint32_t* r, const uint32_t* a, co
 // ---- windowed scalar multiplication with the GLV endomorphism ----------------------------------------------
 // Variable-base k*P for the per-item points (e*A in core_verify, D*r3^ in proof_verify_init).  ark-ec's
 // `Projective * Fr` is a bit-serial double-and-add; on a GPU its data-dependent additions diverge inside a warp
-// (every lane pays for every addition), so this uses fixed 4-bit windows (one table look-up and one addition per
+// (every lane pays for every addition), so this uses fixed signed 5-bit windows (one table look-up and one addition per
 // window for every lane) and the curve endomorphism phi(x, y) = (beta x, y) = lambda P (both curves have j = 0):
 // k = k1 + k2 lambda with both halves below 2^128, so k P = k1 P + k2 phi(P) needs 128 doublings instead of 255.  On
 // BLS12-381 lambda = x^2 - 1 is itself 128 bits and k2 = floor(k / lambda), k1 = k mod lambda; on BN254 lambda is 254 bits and
 // the halves come from a lattice reduction (bn_glv_split).  Same group element as the reference computes; only the
 // addition chain differs.
-BBS_HD uint32_t win4_digit(const uint32_t* k, int w) { return (k[w >> 3] >> (4 * (w & 7))) & 15u; }
+// Signed 5-bit windows without carries: with C = sum_w 16 * 32^w, the base-32 digits u_w of k + C give
+// k = sum_w (u_w - 16) 32^w, digits in [-16, 15]: 26 windows for k < 2^128 (k + C < 2^130), a table of 1..16 times the point,
+// one addition per non-zero digit (the negative ones negate y).
+constexpr int WIN5_WINDOWS = 26;
+BBS_HD void win5_recode(uint32_t* kk /*5 limbs*/, const uint32_t* k /*>= 4 limbs, value < 2^128*/) {
+    const uint32_t C[5] = {0x21084210u, 0x08421084u, 0x42108421u, 0x10842108u, 0x2u};
+    uint64_t c = 0;
+    for (int i = 0; i < 5; i++) { c += (uint64_t)(i < 4 ? k[i] : 0u) + C[i]; kk[i] = (uint32_t)c; c >>= 32; }
+}
+BBS_HD int win5_digit(const uint32_t* kk, int w) {
+    const int bit = 5 * w, word = bit >> 5, off = bit & 31;
+    uint64_t v = kk[word];
+    if (word < 4) v |= (uint64_t)kk[word + 1] << 32;
+    return (int)((uint32_t)(v >> off) & 31u) - 16;
+}
 
 // r = sum_j k1[j] * P_j (+ k2[j] * phi(P_j) when beta != nullptr) over NP affine points (pts[j] == nullptr: the
-// identity, skipped), Straus with shared doublings; `bits` = bit length bound of all k1[j], k2[j]
+// identity, skipped), Straus with shared doublings; all k1[j], k2[j] below 2^128 (`bits` <= 128)
 template <class C, int NP> BBS_HDN void g1_msm_win4(uint32_t* r, const uint32_t* const* pts, const uint32_t (*k1)[9],
                                                     const uint32_t (*k2)[9], int bits, const uint32_t* beta) {
     using F = typename C::Fp;
-    uint32_t tab[NP][15][3 * C::Fp::N];            // d * P_j, d = 1..15 (Jacobian)
+    (void)bits;
+    uint32_t tab[NP][16][3 * C::Fp::N];            // d * P_j, d = 1..16 (Jacobian)
+    uint32_t kk1[NP][5], kk2[NP][5];
     for (int j = 0; j < NP; j++) {
         if (!pts[j]) continue;
         g1_from_affine<C>(tab[j][0], pts[j]);
         g1_dbl<C>(tab[j][1], tab[j][0]);
-        for (int d = 3; d <= 15; d++) g1_add_mixed<C>(tab[j][d - 1], tab[j][d - 2], pts[j]);
+        for (int d = 3; d <= 16; d++) g1_add_mixed<C>(tab[j][d - 1], tab[j][d - 2], pts[j]);
+        win5_recode(kk1[j], k1[j]);
+        if (beta) win5_recode(kk2[j], k2[j]);
     }
     uint32_t acc[G1J];
     g1_set_inf<C>(acc);
-    for (int w = (bits + 3) / 4 - 1; w >= 0; w--) {
-        if (!g1_is_inf<C>(acc)) { g1_dbl<C>(acc, acc); g1_dbl<C>(acc, acc); g1_dbl<C>(acc, acc); g1_dbl<C>(acc, acc); }
+    for (int w = WIN5_WINDOWS - 1; w >= 0; w--) {
+        if (!g1_is_inf<C>(acc)) { g1_dbl<C>(acc, acc); g1_dbl<C>(acc, acc); g1_dbl<C>(acc, acc); g1_dbl<C>(acc, acc); g1_dbl<C>(acc, acc); }
         for (int j = 0; j < NP; j++) {
             if (!pts[j]) continue;
-            uint32_t d1 = win4_digit(k1[j], w);
-            if (d1) g1_add<C>(acc, acc, tab[j][d1 - 1]);
+            const int d1 = win5_digit(kk1[j], w);
+            if (d1) {
+                uint32_t t[G1J];
+                const uint32_t* e = tab[j][(d1 > 0 ? d1 : -d1) - 1];
+                bn_copy<C::Fp::N>(t, e);
+                if (d1 > 0) bn_copy<C::Fp::N>(t + FPN, e + FPN); else fe_neg<F>(t + FPN, e + FPN);
+                bn_copy<C::Fp::N>(t + 2 * FPN, e + 2 * FPN);
+                g1_add<C>(acc, acc, t);
+            }
             if (beta) {
-                uint32_t d2 = win4_digit(k2[j], w);
+                const int d2 = win5_digit(kk2[j], w);
                 if (d2) {
                     uint32_t t[G1J];
-                    fe_mul<F>(t, tab[j][d2 - 1], beta);
-                    bn_copy<2 * C::Fp::N>(t + FPN, tab[j][d2 - 1] + FPN);
+                    const uint32_t* e = tab[j][(d2 > 0 ? d2 : -d2) - 1];
+                    fe_mul<F>(t, e, beta);
+                    if (d2 > 0) bn_copy<C::Fp::N>(t + FPN, e + FPN); else fe_neg<F>(t + FPN, e + FPN);
+                    bn_copy<C::Fp::N>(t + 2 * FPN, e + 2 * FPN);
                     g1_add<C>(acc, acc, t);
                 }
             }
