@@ -99,3 +99,20 @@ def test_two_rank_sharding_gloo(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(script), ROOT],
                        capture_output=True, text=True, env=env, timeout=600)
     assert "SHARD_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the reference's CPU path: oracle/_ref C port on the host cores) prints one JSON line
+    with the keys the driver reads; runs on the CPU."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-sample", "64"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-500:]
+    d = json.loads(p.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["metric"] == "bls12_381_bbs_verifies_per_sec_L10" and d["unit"] == "verifies/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
