@@ -108,6 +108,7 @@ def test_reference_arm_prints_the_contract_line():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "oracle", "cref")], check=True, capture_output=True)   # oracle/_ref C port
     p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
                         "--cpu-sample", "64"], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stderr[-500:]
