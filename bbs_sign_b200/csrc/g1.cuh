@@ -372,9 +372,45 @@ template <class C> BBS_HDN void g1_mul_scalar(uint32_t* r, const uint32_t* a, co
 // ---- encodings -------------------------------------------------------
 enum : int { PT_OK = 0, PT_INF = 1, PT_BAD = 2 };
 
+// ---- subgroup membership -----------------------------------------------------------------------------
+// ark-serialize `deserialize_compressed` (Validate::Yes; derived for Signature sign.rs:18, Proof proof_gen.rs:29,
+// PublicKey key_gen.rs:12) ends with `is_in_correct_subgroup_assuming_on_curve`.  BN254's G1 has cofactor 1.  On
+// BLS12-381 (cofactor (x-1)^2/3) the test is the endomorphism identity of G1 [Scott, "A note on group membership tests"]:
+// with phi(x, y) = (beta x, y) acting as lambda = x^2 - 1 on G1 (the GLV map above), phi^2 acts as -x^2, so
+//     P in G1  <=>  [x^2] P == -phi^2(P) = (beta^2 x, -y),   beta^2 = -beta - 1.
+// Sufficient because phi^2 + phi + 1 = 0 on all of E(Fp): the identity forces (x^4 - x^2 + 1) P = r P = O.
+// Cost: two passes over |x| (Hamming weight 6): 126 doublings + 10 additions.  Every variable-base product of the path
+// relies on it: the GLV split is only a scalar multiplication on G1.
+template <class C> BBS_HDN bool g1_in_subgroup(const uint32_t* a /*affine, on the curve*/);
+template <> BBS_HDN bool g1_in_subgroup<Bn>(const uint32_t*) { return true; }
+template <> BBS_HDN bool g1_in_subgroup<Bls>(const uint32_t* a) {
+    using C = Bls;
+    using F = BlsFp;
+    uint32_t acc[G1J], base[G1J];
+    g1_from_affine<C>(acc, a);
+    for (int i = 62; i >= 0; i--) {                      // |x| P
+        g1_dbl<C>(acc, acc);
+        if ((BLS_X_ABS >> i) & 1) g1_add_mixed<C>(acc, acc, a);
+    }
+    g1_copy<C>(base, acc);
+    for (int i = 62; i >= 0; i--) {                      // x^2 P
+        g1_dbl<C>(acc, acc);
+        if ((BLS_X_ABS >> i) & 1) g1_add<C>(acc, acc, base);
+    }
+    if (g1_is_inf_ool<C>(acc)) return false;
+    // (X, Y, Z) == (beta^2 x, -y)  <=>  X + (beta x + x) Z^2 == 0  and  Y + y Z^3 == 0
+    uint32_t zz[FPN], t[FPN], s[FPN];
+    fe_sqr<F>(zz, acc + 2 * FPN);
+    fe_mul<F>(t, a, C::GLV_BETA()); fe_add<F>(t, t, a); fe_mul<F>(t, t, zz); fe_add<F>(t, t, acc);
+    fe_mul<F>(zz, zz, acc + 2 * FPN); fe_mul<F>(s, a + FPN, zz); fe_add<F>(s, s, acc + FPN);
+    BBS_OPAQUE_CALL_BARRIER();
+    const bool ok = bn_is_zero<12>(t) && bn_is_zero<12>(s);
+    BBS_OPAQUE_CALL_BARRIER();
+    return ok;
+}
+
 // compressed bytes -> affine Montgomery point.  PT_INF for the identity encoding, PT_BAD for anything
-// ark's deserializer would refuse (bad flags, x >= p, x not on the curve).  No subgroup check: the
-// reference's verify functions take already-typed points and perform none.
+// ark's deserializer would refuse (bad flags, x >= p, x not on the curve, point outside the prime-order subgroup).
 template <class C> BBS_HDN int g1_decompress(uint32_t* r /*affine*/, const uint8_t* in);
 template <class C> BBS_HDN void g1_compress_affine(uint8_t* out, const uint32_t* a /*affine*/, bool inf);
 
@@ -387,7 +423,7 @@ template <class C> BBS_HDN int g1_finish_decompress(uint32_t* r, uint32_t* x_can
     if (!fe_sqrt<F>(y, rhs)) return PT_BAD;
     if (fe_is_high<F>(y) != want_high) fe_neg<F>(y, y);
     bn_copy<C::Fp::N>(r, x); bn_copy<C::Fp::N>(r + FPN, y);
-    return PT_OK;
+    return g1_in_subgroup<C>(r) ? PT_OK : PT_BAD;
 }
 
 // BLS12-381: zcash / IETF format, 48 bytes big-endian x, flags in the top 3 bits of byte 0

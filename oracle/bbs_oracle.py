@@ -211,13 +211,13 @@ class Suite:
     def g1_compress(self, P) -> bytes:
         raise NotImplementedError
 
-    def g1_decompress(self, b: bytes):
+    def g1_decompress(self, b: bytes, validate: bool = True):
         raise NotImplementedError
 
     def g2_compress(self, Q) -> bytes:
         raise NotImplementedError
 
-    def g2_decompress(self, b: bytes):
+    def g2_decompress(self, b: bytes, validate: bool = True):
         raise NotImplementedError
 
     def hash_to_g1(self, msg: bytes, dst: bytes):
@@ -225,6 +225,15 @@ class Suite:
 
     def g1_on_curve(self, P) -> bool:
         return P is None or (P[1] * P[1] - P[0] ** 3 - self.b) % self.p == 0
+
+    # ark-serialize 0.4.2 `deserialize_compressed` = Validate::Yes: after the curve equation it calls
+    # `is_in_correct_subgroup_assuming_on_curve`; the derived impls for Signature (sign.rs:18), Proof (proof_gen.rs:29)
+    # and PublicKey (key_gen.rs:12) inherit it.  Restated here as the definition, [r]P == O.
+    def g1_in_subgroup(self, P) -> bool:
+        return P is None or ec_mul(self.F1, P, self.r) is None
+
+    def g2_in_subgroup(self, Q) -> bool:
+        return Q is None or ec_mul(self.F2, Q, self.r) is None
 
     def g2_on_curve(self, Q) -> bool:
         if Q is None:
@@ -245,7 +254,7 @@ class BlsSuite(Suite):
             b[0] |= 0x20
         return bytes(b)
 
-    def g1_decompress(self, b: bytes):
+    def g1_decompress(self, b: bytes, validate: bool = True):
         assert len(b) == 48
         if not b[0] & 0x80:
             raise ValueError("uncompressed flag")
@@ -263,6 +272,8 @@ class BlsSuite(Suite):
             raise ValueError("not on curve")
         if (y > (self.p - 1) // 2) != bool(s):
             y = self.p - y
+        if validate and not self.g1_in_subgroup((x, y)):
+            raise ValueError("not in the prime-order subgroup")
         return (x, y)
 
     def g2_compress(self, Q) -> bytes:
@@ -274,7 +285,7 @@ class BlsSuite(Suite):
             b[0] |= 0x20
         return bytes(b)
 
-    def g2_decompress(self, b: bytes):
+    def g2_decompress(self, b: bytes, validate: bool = True):
         assert len(b) == 96
         if not b[0] & 0x80:
             raise ValueError("uncompressed flag")
@@ -291,6 +302,8 @@ class BlsSuite(Suite):
             raise ValueError("not on curve")
         if F.gt(y, F.neg(y)) != bool(s):
             y = F.neg(y)
+        if validate and not self.g2_in_subgroup((X, y)):
+            raise ValueError("not in the prime-order subgroup")
         return (X, y)
 
     # ---- RFC 9380 BLS12381G1_XMD:SHA-256_SSWU_RO_ (zkcrypto bls12_381, interface_utilities.rs:30-44)
@@ -377,7 +390,7 @@ class BnSuite(Suite):
             b[31] |= 0x80
         return bytes(b)
 
-    def g1_decompress(self, b: bytes):
+    def g1_decompress(self, b: bytes, validate: bool = True):
         assert len(b) == 32
         flags = b[31] & 0xC0
         if flags == 0xC0:
@@ -394,6 +407,8 @@ class BnSuite(Suite):
         neg = bool(flags & 0x80)
         if (y > (self.p - y) % self.p) != neg:
             y = (self.p - y) % self.p
+        if validate and not self.g1_in_subgroup((x, y)):      # cofactor 1: always true, kept for symmetry
+            raise ValueError("not in the prime-order subgroup")
         return (x, y)
 
     def g2_compress(self, Q) -> bytes:
@@ -406,7 +421,7 @@ class BnSuite(Suite):
             b[63] |= 0x80
         return bytes(b)
 
-    def g2_decompress(self, b: bytes):
+    def g2_decompress(self, b: bytes, validate: bool = True):
         assert len(b) == 64
         flags = b[63] & 0xC0
         if flags == 0xC0:
@@ -423,6 +438,8 @@ class BnSuite(Suite):
             raise ValueError("not on curve")
         if F.gt(y, F.neg(y)) != bool(flags & 0x80):
             y = F.neg(y)
+        if validate and not self.g2_in_subgroup((X, y)):
+            raise ValueError("not in the prime-order subgroup")
         return (X, y)
 
     # ---- bn254_hash2curve 0.1.2: RFC 9380 6.6.1 SvdW, Z=1 (interface_utilities.rs:24-28)

@@ -278,7 +278,22 @@ static int g1_decompress(g1* r, const uint8_t in[48]) { /* 0 ok, 1 identity, -1 
     u64 e[6], c = 0; /* (p+1)/4 */ { u64 tmp[6]; memcpy(tmp, P, 48); tmp[0] += 1; for (int i = 5; i >= 0; i--) { u64 v = tmp[i]; e[i] = (v >> 2) | (c << 62); c = v & 3; } }
     fp_pow(&y, &rhs, e, 6); fp chk; fp_sqr(&chk, &y); if (!fp_eq(&chk, &rhs)) return -1;
     if (fp_is_high(&y) != ((in[0] & 0x20) != 0)) fp_neg(&y, &y);
-    r->x = x; r->y = y; r->z = FP_ONE; return 0;
+    r->x = x; r->y = y; r->z = FP_ONE;
+    /* Validate::Yes: ark-bls12-381 0.4.0 `is_in_correct_subgroup_assuming_on_curve` for G1 = the endomorphism test
+       -[x^2]P == endomorphism(P) (two multiplications by the 64-bit |x|); here against beta^2: [x^2]P == (beta^2 x, -y) */
+    {
+        static const uint8_t BETA2_BE[48] = {0x00,0x00,0x00,0x00,0x00,0x00,0x00,0x00,0x5f,0x19,0x67,0x2f,0xdf,0x76,0xce,0x51,0xba,0x69,0xc6,0x07,
+            0x6a,0x0f,0x77,0xea,0xdd,0xb3,0xa9,0x3b,0xe6,0xf8,0x96,0x88,0xde,0x17,0xd8,0x13,0x62,0x0a,0x00,0x02,0x2e,0x01,0xff,0xff,
+            0xff,0xfe,0xff,0xfe};
+        fr k; memset(&k, 0, sizeof k); k.l[0] = 0xd201000000010000ull;
+        g1 q; g1_mul(&q, r, &k); g1_mul(&q, &q, &k);
+        if (g1_inf(&q)) return -1;
+        fp b2, zz, t; fp_from_be48(&b2, BETA2_BE); fp_sqr(&zz, &q.z); fp_mul(&t, &b2, &x); fp_mul(&t, &t, &zz);
+        if (!fp_eq(&t, &q.x)) return -1;
+        fp_mul(&zz, &zz, &q.z); fp_mul(&t, &y, &zz); fp_neg(&t, &t);
+        if (!fp_eq(&t, &q.y)) return -1;
+    }
+    return 0;
 }
 static int g2_inf(const g2* p) { return f2_is_zero(&p->z); }
 static void g2_dbl(g2* r, const g2* p) {

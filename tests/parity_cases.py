@@ -575,3 +575,119 @@ def case_g1_mul_edges(lib, curve_name):
     for i, k in enumerate(special):
         want = ocs.g1_compress(O.ec_mul(ocs.F1, P, k))
         assert out[i * suite.g1_bytes:(i + 1) * suite.g1_bytes].tobytes() == want, (curve_name, hex(k))
+
+
+# ---------------------------------------------------------------------------------------------------
+def off_subgroup_g1(ocs, seed=0):
+    """an on-curve point of E(Fp) outside the prime-order subgroup (no cofactor clearing): small x until on curve"""
+    x = 5 + seed
+    while True:
+        rhs = (x ** 3 + ocs.b) % ocs.p
+        y = pow(rhs, (ocs.p + 1) // 4, ocs.p)
+        if y * y % ocs.p == rhs and O.ec_mul(ocs.F1, (x, y), ocs.r) is not None:
+            return (x, y)
+        x += 1
+
+
+def off_subgroup_g2(ocs, seed=0):
+    x = 3 + seed
+    F = ocs.F2
+    while True:
+        X = (x, 1)
+        y = F.sqrt(F.add(F.mul(F.mul(X, X), X), ocs.b2))
+        if y is not None and O.ec_mul(F, (X, y), ocs.r) is not None:
+            return (X, y)
+        x += 1
+
+
+def case_subgroup(lib_path, curve_name):
+    """ark-serialize `deserialize_compressed` (Validate::Yes; derived for Signature sign.rs:18, Proof proof_gen.rs:29,
+    PublicKey key_gen.rs:12) refuses points outside the prime-order subgroup.  On-curve off-subgroup points (and valid
+    points shifted by cofactor torsion, which the pairing cannot see) must give ERR_MALFORMED at every entry point that
+    takes G1 bytes, and BBS_E_ARG from bbs_ctx_create for the public key and the generators."""
+    suite, ocs = SUITES[curve_name]
+    sk, pk = keypair(ocs, 1)
+    L = 2
+    header, ph = b"sg", b"sg-ph"
+    ctx, gens = make_ctx(lib_path, suite, ocs, pk, header, L)
+    gb = gens_bytes(ocs, gens)
+    # --- public key / generators at context creation
+    Qbad = off_subgroup_g2(ocs)
+    assert ocs.g2_on_curve(Qbad)
+    try:
+        ocs.g2_decompress(ocs.g2_compress(Qbad))
+        assert False, "oracle accepted an off-subgroup G2 point"
+    except ValueError:
+        pass
+    assert ocs.g2_decompress(ocs.g2_compress(Qbad), validate=False) == Qbad
+    for bad_pk in (Qbad, O.ec_add(ocs.F2, pk, Qbad)):
+        try:
+            A.BatchContext(suite, ocs.g2_compress(bad_pk), header, generators=gb, lib_path=lib_path)
+            assert False, "off-subgroup public key accepted"
+        except A.BbsError as e:
+            assert "(-1)" in str(e), str(e)               # BBS_E_ARG
+    if curve_name != "BLS12_381":
+        ctx.close()       # BN254: E(Fp) has prime order r, every on-curve G1 point is in the subgroup
+        return
+    T = off_subgroup_g1(ocs)
+    T3 = (0, 2)                                           # a point of order 3 on y^2 = x^3 + 4
+    assert ocs.g1_on_curve(T) and ocs.g1_on_curve(T3) and O.ec_mul(ocs.F1, T3, 3) is None
+    h = (ocs.p + 1 - (-0xD201000000010000 + 1)) // ocs.r  # cofactor of G1
+    Ttor = O.ec_mul(ocs.F1, T, ocs.r)                     # pure cofactor torsion
+    assert Ttor is not None and O.ec_mul(ocs.F1, Ttor, h) is None
+    for Pb in (T, T3, Ttor):
+        try:
+            ocs.g1_decompress(ocs.g1_compress(Pb))
+            assert False, "oracle accepted an off-subgroup G1 point"
+        except ValueError:
+            pass
+    try:
+        A.BatchContext(suite, ocs.g2_compress(pk), header, generators=gb[:48] + ocs.g1_compress(T) + gb[96:], lib_path=lib_path)
+        assert False, "off-subgroup generator accepted"
+    except A.BbsError as e:
+        assert "(-1)" in str(e), str(e)
+    # --- signatures: A replaced by torsion-shifted copies (the pairing equation still holds for A + Ttor)
+    msgs = [[rng_bytes(f"sg{i}.{j}", 32) for j in range(L)] for i in range(6)]
+    sigs = [O.sign(ocs, sk, m, header) for m in msgs]
+    mall = [sigs[0],
+            (O.ec_add(ocs.F1, sigs[1][0], Ttor), sigs[1][1]),
+            (O.ec_add(ocs.F1, sigs[2][0], T3), sigs[2][1]),
+            (T, sigs[3][1]),
+            (T3, sigs[4][1]),
+            sigs[5]]
+    # without validation the malleated signature satisfies the verification equation: that is the hole being closed
+    assert O.verify(ocs, pk, mall[2], header, msgs[2]) is True
+    enc = [O.signature_to_bytes(ocs, s) for s in mall]
+    want = [1, A.ST_ERR_MALFORMED, A.ST_ERR_MALFORMED, A.ST_ERR_MALFORMED, A.ST_ERR_MALFORMED, 1]
+    blob = np.frombuffer(b"".join(enc), dtype=np.uint8)
+    assert ctx.verify_batch(blob, msgs).tolist() == want
+    sc = np.frombuffer(b"".join(ocs.scalar_le(x) for m in msgs for x in O.msg_to_scalars(ocs, m, ocs.api_id)), dtype=np.uint8)
+    assert ctx.core_verify_batch(blob, sc, L).tolist() == want
+    # --- proof_gen from a malleated signature
+    rs = [[ocs.scalar_le(x) for x in O.seeded_random_scalars(ocs, f"sg{i}".encode(), b"rs-dst", 5 + L - 1)] for i in range(6)]
+    proofs, st = ctx.proof_gen_batch(enc, msgs, [[0]] * 6, rs, ph)
+    assert st.tolist() == want
+    # --- proof_verify: each of Abar, Bbar, D off the subgroup
+    good = proofs[0]
+    assert ctx.proof_verify_batch([good], ph, [[msgs[0][0]]], [[0]]).tolist() == [1]
+    g = suite.g1_bytes
+    bad_proofs = []
+    for slot in range(3):
+        for Pb in (T, T3):
+            f = bytearray(good.fixed)
+            f[slot * g:(slot + 1) * g] = ocs.g1_compress(Pb)
+            bad_proofs.append(A.ProofBytes(bytes(f), good.commitments))
+        P0 = ocs.g1_decompress(good.fixed[slot * g:(slot + 1) * g])
+        f = bytearray(good.fixed)
+        f[slot * g:(slot + 1) * g] = ocs.g1_compress(O.ec_add(ocs.F1, P0, Ttor))
+        bad_proofs.append(A.ProofBytes(bytes(f), good.commitments))
+    nb = len(bad_proofs)
+    got = ctx.proof_verify_batch(bad_proofs + [good], ph, [[msgs[0][0]]] * (nb + 1), [[0]] * (nb + 1))
+    assert got.tolist() == [A.ST_ERR_MALFORMED] * nb + [1], got.tolist()
+    # --- random-linear-combination mode (CUDA build only)
+    if lib_path is None:
+        seed = rng_bytes("sg-seed", 32)
+        assert ctx.rlc_verify_batch([enc[0], enc[5]], [msgs[0], msgs[5]], seed) == A.ST_ACCEPT
+        assert ctx.rlc_verify_batch(enc, msgs, seed) == A.ST_ERR_MALFORMED
+        assert ctx.rlc_verify_batch([enc[0], enc[2]], [msgs[0], msgs[2]], seed) == A.ST_ERR_MALFORMED
+    ctx.close()
