@@ -1,8 +1,8 @@
 """ctypes binding of the C ABI declared in include/bbs_b200.h.
 
 `load()` opens the CUDA library built in-tree (`bbs_sign_b200/libbbs_b200.so`) and fails loudly when
-it is missing: there is no CPU fallback on the product path.  (`load(path)` with an explicit path is
-used by the GPU-less logic tests to bind the host-simulation build of the same sources.)"""
+it is missing or is not a CUDA build: there is no CPU fallback on the product path.  (The GPU-less logic tests bind the
+host-simulation build of the same sources with `load(path, allow_host_simulation=True)`.)"""
 from __future__ import annotations
 
 import ctypes as C
@@ -22,12 +22,15 @@ SYMBOLS = {
     "bbs_signature_bytes": (C.c_size_t, [C.c_int]),
     "bbs_proof_fixed_bytes": (C.c_size_t, [C.c_int]),
     "bbs_last_error": (C.c_char_p, []),
+    "bbs_build_info": (C.c_char_p, []),
     "bbs_create_generators": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]),
     "bbs_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t,
                                  C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "bbs_ctx_destroy": (None, [C.c_void_p]),
     "bbs_ctx_domain": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bbs_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
+    "bbs_ctx_use_per_thread_pairing": (C.c_int, [C.c_void_p, C.c_int]),
+    "bbs_ctx_set_rlc_windows": (C.c_int, [C.c_void_p, C.c_uint32]),
     "bbs_msg_to_scalars": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bbs_core_verify_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "bbs_verify_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
@@ -80,8 +83,11 @@ class NativeLibraryMissing(RuntimeError):
 _CACHE = {}
 
 
-def load(path: str | None = None) -> C.CDLL:
-    path = path or os.environ.get("BBS_B200_LIB") or LIB_PATH   # BBS_B200_LIB: alternative CUDA builds (tuning experiments)
+def load(path: str | None = None, allow_host_simulation: bool = False) -> C.CDLL:
+    """Binds the library.  Only a CUDA build is accepted: a library whose `bbs_build_info()` is not "cuda ..." (the host
+    simulation tests/hostsim.py makes from the same sources) is refused unless the caller is a test that says so
+    explicitly (`allow_host_simulation=True`, tests/test_hostsim_logic.py); there is no environment-variable override."""
+    path = path or LIB_PATH
     if path in _CACHE:
         return _CACHE[path]
     if not os.path.exists(path):
@@ -93,5 +99,8 @@ def load(path: str | None = None) -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    info = lib.bbs_build_info().decode()
+    if not info.startswith("cuda") and not allow_host_simulation:
+        raise NativeLibraryMissing(f"{path} is not a CUDA build ({info}); bbs_sign_b200 has no CPU fallback")
     _CACHE[path] = lib
     return lib

@@ -187,7 +187,8 @@ class BatchContext:
 
     # ---- random-linear-combination batch mode (not in the reference; include/bbs_b200.h) -------------------
     def rlc_partial(self, signatures, messages: Sequence[Sequence[bytes]], seed: bytes, index_base: int = 0):
-        """This shard's two partial G1 points (compressed) and a status byte (ACCEPT = well-formed shard)."""
+        """This shard's two partial G1 points (compressed) and a status byte (ACCEPT = well-formed shard).  All shards of
+        a batch share `seed`, which the coordinator draws (os.urandom) AFTER the whole batch is fixed."""
         n = len(messages)
         n_msgs = len(messages[0]) if n else 0
         flat, offs = _pack_ragged([m for ms in messages for m in ms])
@@ -204,10 +205,25 @@ class BatchContext:
         self._check(self.lib.bbs_rlc_combine(self._h, len(parts), _ptr(blob), _ptr(v)), "bbs_rlc_combine")
         return int(v[0])
 
-    def rlc_verify_batch(self, signatures, messages: Sequence[Sequence[bytes]], seed: bytes) -> int:
-        """One verdict (ST_ACCEPT / ST_REJECT / ST_ERR_*) for the whole batch; see include/bbs_b200.h."""
-        parts, st = self.rlc_partial(signatures, messages, seed, 0)
-        return st if st != ST_ACCEPT else self.rlc_combine([parts])
+    def rlc_verify_batch(self, signatures, messages: Sequence[Sequence[bytes]], seed: Optional[bytes] = None) -> int:
+        """One verdict (ST_ACCEPT / ST_REJECT / ST_ERR_*) for the whole batch; see include/bbs_b200.h.  `seed=None` (the
+        default) lets the library draw the coefficient seed from the OS CSPRNG after it has the batch; pass a seed only
+        for reproducible tests: a seed the submitter of the batch can predict voids the verdict's soundness."""
+        n = len(messages)
+        n_msgs = len(messages[0]) if n else 0
+        flat, offs = _pack_ragged([m for ms in messages for m in ms])
+        sigs = _buf(b"".join(signatures) if not isinstance(signatures, (bytes, bytearray)) else signatures)
+        v = np.zeros(1, dtype=np.uint8)
+        self._check(self.lib.bbs_rlc_verify_batch(self._h, n, _ptr(sigs), _ptr(flat), _ptr(offs), n_msgs,
+                                                  _ptr(_buf(seed)) if seed is not None else None, _ptr(v)), "bbs_rlc_verify_batch")
+        return int(v[0])
+
+    # ---- test hooks (include/bbs_b200.h) ----
+    def use_per_thread_pairing(self, on: bool = True):
+        self._check(self.lib.bbs_ctx_use_per_thread_pairing(self._h, 1 if on else 0), "bbs_ctx_use_per_thread_pairing")
+
+    def set_rlc_windows(self, windows: int):
+        self._check(self.lib.bbs_ctx_set_rlc_windows(self._h, windows), "bbs_ctx_set_rlc_windows")
 
     # ---- sign.rs ----
     def core_sign_batch(self, sk_le32: bytes, msg_scalars, n: int, n_msgs: int, want_b: bool = False):

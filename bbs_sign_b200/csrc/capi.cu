@@ -58,15 +58,17 @@ struct Ctx {
     DevBuf pk_comp, gens_comp, api_id, header, dst_h2s, dst_map;
     DevBuf gens, W, K, domain, tab, wbase, lines, lines_coop, misc;
     bool coop = false;               // cooperative pairing kernel usable (no degenerate line)
+    bool force_per_thread = false;   // bbs_ctx_use_per_thread_pairing: the fallback kernel on request (tests)
+    uint32_t rlc_windows = 0;        // bbs_ctx_set_rlc_windows: digits per 128-bit value of the bucket MSM (0 = cost model)
     CtxView view{};
     // grow-only scratch for the batch calls
-    DevBuf s_rand, s_rand_off;
+    DevBuf s_rand, s_rand_off, s_sk;
     DevBuf s_gscr, s_rlc_pt, s_rlc_sc, s_rlc_parts, s_rlc_bad, s_msm_pts, s_msm_kv, s_msm_idx, s_msm_entries, s_msm_buckets;
     DevBuf s_sigs, s_scalars, s_msgs, s_offsets, s_pair, s_flags, s_status, s_out, s_out2;
     DevBuf s_commit, s_commit_off, s_dis_idx, s_dis_scalars, s_dis_off, s_ph, s_dis_msgs, s_dis_msg_off;
     void release_all() {
         DevBuf* all[] = {&pk_comp, &gens_comp, &api_id, &header, &dst_h2s, &dst_map, &gens, &W, &K, &domain, &tab, &wbase,
-                         &lines, &lines_coop, &s_rand, &s_rand_off, &s_gscr, &s_rlc_pt, &s_rlc_sc, &s_rlc_parts, &s_rlc_bad, &s_msm_pts, &s_msm_kv, &s_msm_idx, &s_msm_entries, &s_msm_buckets, &misc, &s_sigs, &s_scalars, &s_msgs, &s_offsets, &s_pair, &s_flags, &s_status, &s_out,
+                         &lines, &lines_coop, &s_rand, &s_rand_off, &s_sk, &s_gscr, &s_rlc_pt, &s_rlc_sc, &s_rlc_parts, &s_rlc_bad, &s_msm_pts, &s_msm_kv, &s_msm_idx, &s_msm_entries, &s_msm_buckets, &misc, &s_sigs, &s_scalars, &s_msgs, &s_offsets, &s_pair, &s_flags, &s_status, &s_out,
                          &s_out2, &s_commit, &s_commit_off, &s_dis_idx, &s_dis_scalars, &s_dis_off, &s_ph, &s_dis_msgs,
                          &s_dis_msg_off};
         for (DevBuf* b : all) b->release();
@@ -77,6 +79,13 @@ struct Ctx {
 #define PROF(c, slot, s) do { if ((c)->profile) TRY((c)->prof.mark(slot, s)); } while (0)
 
 int arg_error(const char* what) { rt_set_error("bad argument", what); return BBS_E_ARG; }
+
+// The kernels index items and flat message slots with 32-bit counters.
+bool counts_fit(size_t n, size_t per_item) {
+    if (n > 0xffffffffull) return false;
+    return per_item == 0 || n <= 0xffffffffull / per_item;
+}
+#define CHECK_COUNTS(n, per_item) do { if (!counts_fit((n), (per_item))) return arg_error("batch too large: n and n * n_msgs must fit in 32 bits"); } while (0)
 
 template <class C>
 struct Impl {
@@ -159,7 +168,7 @@ struct Impl {
             TRY(rt_d2h(&deg, d_deg, 4, s));
             TRY(rt_sync(s));
             c->launches += 1;
-            c->coop = deg == 0 && !getenv("BBS_NO_COOP");
+            c->coop = deg == 0;
         }
 #endif
         CtxView& v = c->view;
@@ -181,7 +190,7 @@ struct Impl {
 
     static int pairing_dev(Ctx* c, size_t n, uint8_t* d_status, rt_stream_t s) {
 #ifndef BBS_HOSTSIM
-        if (c->coop) {
+        if (c->coop && !c->force_per_thread) {
             TRY(c->s_gscr.reserve(coop_gscratch_size<C>(n)));
             CoopArgs ca{(const uint32_t*)c->lines_coop.p, (const uint32_t*)c->s_pair.p, (const uint32_t*)c->s_flags.p,
                         d_status, (uint32_t*)c->s_gscr.p, (uint32_t)n};
@@ -222,12 +231,22 @@ struct Impl {
                              uint8_t* d_sigs, uint8_t* d_b, uint8_t* d_status, rt_stream_t s) {
         SignArgs a{};
         a.ctx = c->view;
-        limbs_from_le<8>(a.sk, sk);
-        if (!fe_is_canonical<typename C::Fr>(a.sk)) return arg_error("secret key scalar is not canonical");
+        uint32_t skl[8];
+        limbs_from_le<8>(skl, sk);
+        const bool canon = fe_is_canonical<typename C::Fr>(skl);
+        int rc = canon ? c->s_sk.reserve(32) : arg_error("secret key scalar is not canonical");
+        if (!rc) rc = rt_h2d(c->s_sk.p, skl, 32, s);       // pageable source: staged before the call returns
+        volatile uint32_t* wipe = skl;
+        for (int i = 0; i < 8; i++) wipe[i] = 0;
+        TRY(rc);
+        a.sk = (const uint32_t*)c->s_sk.p;
         a.scalars = d_scalars; a.n_msgs = n_msgs; a.sigs_out = d_sigs; a.b_out = d_b; a.status = d_status;
         PROF(c, 1, s);
-        TRY((launch_sign<C>(a, (uint32_t)n, s)));
+        rc = launch_sign<C>(a, (uint32_t)n, s);
         c->launches += n ? 1 : 0;
+        int rc2 = rt_memset(c->s_sk.p, 0, 32, s);           // SecretKey is ZeroizeOnDrop (key_gen.rs:29)
+        TRY(rc);
+        TRY(rc2);
         PROF(c, 2, s);
         return BBS_OK;
     }
@@ -304,10 +323,9 @@ struct Impl {
     // digits per 128-bit value for the bucket MSM.  Cost in field multiplications: 11 per bucket addition, inflated by the
     // quantisation of buckets over the persistent threads of msm_bucket_kernel (u buckets per thread), plus ~47 per bucket
     // for the reduction (measured on B200 at n = 65,536 and 524,288: profiles/summary_r01.md)
-    static MsmPlan rlc_plan(size_t n) {
+    static MsmPlan rlc_plan(size_t n, uint32_t force) {      // force != 0: bbs_ctx_set_rlc_windows (tests: other geometries)
         uint32_t best = 32;
         double best_cost = 1e300;
-        const char* force = getenv("BBS_RLC_WINDOWS");        // tests: exercise other geometries
         for (uint32_t W = 8; W <= 32; W++) {
             const uint32_t c = (128 + W - 1) / W, rows = 2 * W;
             double used = 0;                                   // buckets that can be non-empty
@@ -315,7 +333,7 @@ struct Impl {
             used *= rows / W;
             const double u = used / (148.0 * 512.0);
             const double cost = 11.0 * 3.0 * W * (double)n * (1.0 + 1.0 / u) + 47.0 * rows * (double)(1u << c);
-            if ((force && atoi(force) > 0) ? (uint32_t)atoi(force) == W : cost < best_cost) { best = W; best_cost = cost; }
+            if (force ? force == W : cost < best_cost) { best = W; best_cost = cost; }
         }
         MsmPlan p;
         p.W = best;
@@ -337,7 +355,7 @@ struct Impl {
                                const RlcFeed* feed = nullptr) {
         if (n >= (1ull << 31)) return arg_error("rlc shard too large");
         const uint32_t blocks = (uint32_t)((n + RLC_TPB - 1) / RLC_TPB);
-        const MsmPlan plan = rlc_plan(n);
+        const MsmPlan plan = rlc_plan(n, c->rlc_windows);
         const size_t nb = (size_t)plan.rows << plan.c, PT = 3 * C::Fp::N * 4;
         TRY(c->s_rlc_sc.reserve((size_t)(blocks ? blocks : 1) * (n_msgs + 1) * 32));
         TRY(c->s_rlc_parts.reserve(2 * C::G1_BYTES));
@@ -546,6 +564,9 @@ struct Impl {
                           b_out ? (uint8_t*)c->s_out2.p : nullptr, (uint8_t*)c->s_status.p, s));
         TRY(rt_d2h(sigs_out, c->s_out.p, n * SIG, s));
         if (b_out) TRY(rt_d2h(b_out, c->s_out2.p, n * C::G1_BYTES, s));
+        // the signer's staging copies of the messages and their scalars do not outlive the call
+        TRY(rt_memset(c->s_scalars.p, 0, n * (size_t)n_msgs * 32, s));
+        if (c->s_msgs.p && c->s_msgs.cap) TRY(rt_memset(c->s_msgs.p, 0, c->s_msgs.cap, s));
         return finish_status(c, n, status);
     }
     static int core_sign(Ctx* c, const uint8_t* sk, size_t n, const uint8_t* scalars, uint32_t n_msgs, uint8_t* sigs_out,
@@ -606,6 +627,16 @@ struct Impl {
 
 Ctx* as_ctx(bbs_ctx* p) { return reinterpret_cast<Ctx*>(p); }
 
+// 32 bytes from the operating system's CSPRNG: the default coefficient seed of the random-linear-combination mode, drawn
+// after the batch has been handed over (a seed the submitter of the batch can predict voids the mode's soundness)
+int fresh_seed(uint8_t out[32]) {
+    FILE* f = fopen("/dev/urandom", "rb");
+    const size_t got = f ? fread(out, 1, 32, f) : 0;
+    if (f) fclose(f);
+    if (got != 32) { rt_set_error("rlc", "cannot read /dev/urandom for the coefficient seed"); return -1; }
+    return 0;
+}
+
 #define DISPATCH(c, call)                                              \
     do {                                                               \
         if (!(c)) return arg_error("null context");                    \
@@ -630,7 +661,6 @@ int bbs_create_generators(int curve, int device, const uint8_t* api_id, size_t a
     if (api_id_len > 128) return arg_error("api_id too long");
     if (count == 0) return BBS_OK;
     if (rt_set_device(device)) return BBS_E_CUDA;
-    if (rt_set_stack(48 * 1024)) return BBS_E_CUDA;
     const size_t gb = bbs_g1_bytes(curve);
     DevBuf d_api, d_v, d_out;
     int rc = d_api.reserve(api_id_len + 1);
@@ -660,7 +690,6 @@ int bbs_ctx_create(int curve, int device, const uint8_t* pk, const uint8_t* gene
     if (n_generators - 1 > BBS_MAX_MESSAGES) return arg_error("too many generators");
     if ((header_len && !header) || (api_id_len && !api_id)) return arg_error("null header / api_id");
     if (rt_set_device(device)) return BBS_E_CUDA;
-    if (rt_set_stack(48 * 1024)) return BBS_E_CUDA;
     Ctx* c = new (std::nothrow) Ctx();
     if (!c) return arg_error("out of host memory");
     c->curve = curve; c->device = device;
@@ -679,6 +708,11 @@ void bbs_ctx_destroy(bbs_ctx* p) {
     Ctx* c = as_ctx(p);
     if (!c) return;
     rt_set_device(c->device);
+    rt_sync(c->stream);
+    // batch inputs (messages, scalars, signatures, random scalars of the prover) are wiped before the memory goes back
+    for (DevBuf* b : {&c->s_sk, &c->s_rand, &c->s_scalars, &c->s_msgs, &c->s_sigs, &c->s_dis_scalars, &c->s_dis_msgs, &c->s_commit,
+                      &c->s_out, &c->s_out2, &c->s_rlc_sc, &c->s_msm_kv})
+        if (b->p && b->cap) rt_memset(b->p, 0, b->cap, c->stream);
     rt_sync(c->stream);
     c->release_all();
     c->prof.release();
@@ -700,6 +734,27 @@ int bbs_ctx_domain(bbs_ctx* p, uint8_t out[32]) {
 
 uint64_t bbs_ctx_launch_count(bbs_ctx* p) { return p ? as_ctx(p)->launches : 0; }
 
+const char* bbs_build_info(void) {
+#ifdef BBS_HOSTSIM
+    return "host-simulation (tests only; not a product build)";
+#else
+    return "cuda sm_100a";
+#endif
+}
+
+int bbs_ctx_set_rlc_windows(bbs_ctx* p, uint32_t windows) {
+    if (!p) return arg_error("null context");
+    if (windows != 0 && (windows < 8 || windows > 32)) return arg_error("windows must be 0 (cost model) or 8..32");
+    as_ctx(p)->rlc_windows = windows;
+    return BBS_OK;
+}
+
+int bbs_ctx_use_per_thread_pairing(bbs_ctx* p, int on) {
+    if (!p) return arg_error("null context");
+    as_ctx(p)->force_per_thread = on != 0;
+    return BBS_OK;
+}
+
 int bbs_ctx_set_profiling(bbs_ctx* p, int on) {
     if (!p) return arg_error("null context");
     as_ctx(p)->profile = on != 0;
@@ -720,12 +775,14 @@ int bbs_msg_to_scalars(bbs_ctx* p, size_t count, const uint8_t* msgs, const uint
     Ctx* c = as_ctx(p);
     if (count && (!off || !out)) return arg_error("null");
     if (!count) return BBS_OK;
+    CHECK_COUNTS(count, 1);
     DISPATCH(c, msg_to_scalars(c, count, msgs, off, out));
 }
 int bbs_core_verify_batch(bbs_ctx* p, size_t n, const uint8_t* sigs, const uint8_t* scalars, uint32_t n_msgs, uint8_t* status) {
     Ctx* c = as_ctx(p);
     if (!n) return BBS_OK;
     if (!sigs || !status || (n_msgs && !scalars)) return arg_error("null");
+    CHECK_COUNTS(n, n_msgs);
     DISPATCH(c, core_verify(c, n, sigs, scalars, n_msgs, status));
 }
 int bbs_verify_batch(bbs_ctx* p, size_t n, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off, uint32_t n_msgs,
@@ -733,6 +790,7 @@ int bbs_verify_batch(bbs_ctx* p, size_t n, const uint8_t* sigs, const uint8_t* m
     Ctx* c = as_ctx(p);
     if (!n) return BBS_OK;
     if (!sigs || !status || !off) return arg_error("null");
+    CHECK_COUNTS(n, n_msgs);
     DISPATCH(c, verify(c, n, sigs, msgs, off, n_msgs, status));
 }
 int bbs_core_sign_batch(bbs_ctx* p, const uint8_t sk[32], size_t n, const uint8_t* scalars, uint32_t n_msgs,
@@ -740,6 +798,7 @@ int bbs_core_sign_batch(bbs_ctx* p, const uint8_t sk[32], size_t n, const uint8_
     Ctx* c = as_ctx(p);
     if (!n) return BBS_OK;
     if (!sk || !sigs_out || !status || (n_msgs && !scalars)) return arg_error("null");
+    CHECK_COUNTS(n, n_msgs);
     DISPATCH(c, core_sign(c, sk, n, scalars, n_msgs, sigs_out, b_out, status));
 }
 int bbs_sign_batch(bbs_ctx* p, const uint8_t sk[32], size_t n, const uint8_t* msgs, const uint64_t* off, uint32_t n_msgs,
@@ -747,6 +806,7 @@ int bbs_sign_batch(bbs_ctx* p, const uint8_t sk[32], size_t n, const uint8_t* ms
     Ctx* c = as_ctx(p);
     if (!n) return BBS_OK;
     if (!sk || !sigs_out || !status || !off) return arg_error("null");
+    CHECK_COUNTS(n, n_msgs);
     DISPATCH(c, sign(c, sk, n, msgs, off, n_msgs, sigs_out, b_out, status));
 }
 int bbs_core_proof_verify_batch(bbs_ctx* p, size_t n, const uint8_t* proofs, const uint8_t* commit,
@@ -755,6 +815,8 @@ int bbs_core_proof_verify_batch(bbs_ctx* p, size_t n, const uint8_t* proofs, con
     Ctx* c = as_ctx(p);
     if (!n) return BBS_OK;
     if (!proofs || !commit_off || !dis_off || !status) return arg_error("null");
+    CHECK_COUNTS(n, 1);
+    if (commit_off[n] > 0xffffffffull || dis_off[n] > 0xffffffffull) return arg_error("batch too large: flat counts must fit in 32 bits");
     DISPATCH(c, core_proof_verify(c, n, proofs, commit, commit_off, idx, dis_scalars, dis_off, ph, ph_len, status));
 }
 int bbs_proof_verify_batch(bbs_ctx* p, size_t n, const uint8_t* proofs, const uint8_t* commit, const uint64_t* commit_off,
@@ -763,6 +825,8 @@ int bbs_proof_verify_batch(bbs_ctx* p, size_t n, const uint8_t* proofs, const ui
     Ctx* c = as_ctx(p);
     if (!n) return BBS_OK;
     if (!proofs || !commit_off || !dis_off || !dis_msg_off || !status) return arg_error("null");
+    CHECK_COUNTS(n, 1);
+    if (commit_off[n] > 0xffffffffull || dis_off[n] > 0xffffffffull) return arg_error("batch too large: flat counts must fit in 32 bits");
     DISPATCH(c, proof_verify(c, n, proofs, commit, commit_off, idx, dis_msgs, dis_msg_off, dis_off, ph, ph_len, status));
 }
 
@@ -773,6 +837,8 @@ int bbs_core_proof_gen_batch(bbs_ctx* p, size_t n, const uint8_t* sigs, const ui
     Ctx* c = as_ctx(p);
     if (!n) return BBS_OK;
     if (!sigs || !dis_off || !rand || !rand_off || !commit_off || !proofs_out || !status) return arg_error("null");
+    CHECK_COUNTS(n, n_msgs);
+    if (n_msgs > BBS_MAX_MESSAGES) return arg_error("n_msgs exceeds BBS_MAX_MESSAGES");
     DISPATCH(c, core_proof_gen(c, n, sigs, scalars, n_msgs, idx, dis_off, rand, rand_off, commit_off, ph, ph_len,
                                proofs_out, commitments_out, status));
 }
@@ -783,6 +849,8 @@ int bbs_proof_gen_batch(bbs_ctx* p, size_t n, const uint8_t* sigs, const uint8_t
     Ctx* c = as_ctx(p);
     if (!n) return BBS_OK;
     if (!sigs || !off || !dis_off || !rand || !rand_off || !commit_off || !proofs_out || !status) return arg_error("null");
+    CHECK_COUNTS(n, n_msgs);
+    if (n_msgs > BBS_MAX_MESSAGES) return arg_error("n_msgs exceeds BBS_MAX_MESSAGES");
     DISPATCH(c, proof_gen(c, n, sigs, msgs, off, n_msgs, idx, dis_off, rand, rand_off, commit_off, ph, ph_len, proofs_out,
                           commitments_out, status));
 }
@@ -792,13 +860,15 @@ int bbs_proof_gen_batch(bbs_ctx* p, size_t n, const uint8_t* sigs, const uint8_t
 int bbs_rlc_partial_core(bbs_ctx* p, size_t n, const uint8_t* sigs, const uint8_t* scalars, uint32_t n_msgs,
                          const uint8_t seed[32], uint64_t index_base, uint8_t* parts_out, uint8_t* status) {
     Ctx* c = as_ctx(p);
-    if (!seed || !parts_out || !status || (n && !sigs) || (n && n_msgs && !scalars)) return arg_error("null");
+    if (!seed || !parts_out || !status || (n && !sigs) || (n && n_msgs && !scalars)) return arg_error("null (shards must share one seed)");
+    CHECK_COUNTS(n, n_msgs);
     DISPATCH(c, rlc_partial(c, n, sigs, scalars, n_msgs, seed, index_base, parts_out, status));
 }
 int bbs_rlc_partial(bbs_ctx* p, size_t n, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off, uint32_t n_msgs,
                     const uint8_t seed[32], uint64_t index_base, uint8_t* parts_out, uint8_t* status) {
     Ctx* c = as_ctx(p);
-    if (!seed || !parts_out || !status || !off || (n && !sigs)) return arg_error("null");
+    if (!seed || !parts_out || !status || !off || (n && !sigs)) return arg_error("null (shards must share one seed)");
+    CHECK_COUNTS(n, n_msgs);
     DISPATCH(c, rlc_partial_msgs(c, n, sigs, msgs, off, n_msgs, seed, index_base, parts_out, status));
 }
 int bbs_rlc_combine(bbs_ctx* p, size_t n_parts, const uint8_t* parts, uint8_t* verdict) {
@@ -809,13 +879,19 @@ int bbs_rlc_combine(bbs_ctx* p, size_t n_parts, const uint8_t* parts, uint8_t* v
 int bbs_rlc_core_verify_batch(bbs_ctx* p, size_t n, const uint8_t* sigs, const uint8_t* scalars, uint32_t n_msgs,
                               const uint8_t seed[32], uint8_t* verdict) {
     Ctx* c = as_ctx(p);
-    if (!seed || !verdict || (n && !sigs) || (n && n_msgs && !scalars)) return arg_error("null");
+    if (!verdict || (n && !sigs) || (n && n_msgs && !scalars)) return arg_error("null");
+    CHECK_COUNTS(n, n_msgs);
+    uint8_t fresh[32];
+    if (!seed) { if (fresh_seed(fresh)) return BBS_E_ARG; seed = fresh; }
     DISPATCH(c, rlc_verify(c, n, sigs, scalars, nullptr, nullptr, n_msgs, seed, verdict));
 }
 int bbs_rlc_verify_batch(bbs_ctx* p, size_t n, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off,
                          uint32_t n_msgs, const uint8_t seed[32], uint8_t* verdict) {
     Ctx* c = as_ctx(p);
-    if (!seed || !verdict || !off || (n && !sigs)) return arg_error("null");
+    if (!verdict || !off || (n && !sigs)) return arg_error("null");
+    CHECK_COUNTS(n, n_msgs);
+    uint8_t fresh[32];
+    if (!seed) { if (fresh_seed(fresh)) return BBS_E_ARG; seed = fresh; }
     DISPATCH(c, rlc_verify(c, n, sigs, nullptr, msgs, off, n_msgs, seed, verdict));
 }
 #else
@@ -828,22 +904,26 @@ int bbs_rlc_verify_batch(bbs_ctx*, size_t, const uint8_t*, const uint8_t*, const
 
 int bbs_msg_to_scalars_dev(bbs_ctx* p, size_t count, const uint8_t* d_msgs, const uint64_t* d_off, uint8_t* d_out, void* stream) {
     Ctx* c = as_ctx(p);
+    CHECK_COUNTS(count, 1);
     DISPATCH(c, h2s_dev(c, count, d_msgs, d_off, d_out, (rt_stream_t)stream));
 }
 int bbs_core_verify_batch_dev(bbs_ctx* p, size_t n, const uint8_t* d_sigs, const uint8_t* d_scalars, uint32_t n_msgs,
                               uint8_t* d_status, void* stream) {
     Ctx* c = as_ctx(p);
+    CHECK_COUNTS(n, n_msgs);
     DISPATCH(c, core_verify_dev(c, n, d_sigs, d_scalars, n_msgs, d_status, (rt_stream_t)stream));
 }
 int bbs_verify_batch_dev(bbs_ctx* p, size_t n, const uint8_t* d_sigs, const uint8_t* d_msgs, const uint64_t* d_off,
                          uint32_t n_msgs, uint8_t* d_status, void* stream) {
     Ctx* c = as_ctx(p);
+    CHECK_COUNTS(n, n_msgs);
     DISPATCH(c, verify_dev(c, n, d_sigs, d_msgs, d_off, n_msgs, d_status, (rt_stream_t)stream));
 }
 int bbs_core_sign_batch_dev(bbs_ctx* p, const uint8_t sk[32], size_t n, const uint8_t* d_scalars, uint32_t n_msgs,
                             uint8_t* d_sigs, uint8_t* d_b, uint8_t* d_status, void* stream) {
     Ctx* c = as_ctx(p);
     if (!sk) return arg_error("null");
+    CHECK_COUNTS(n, n_msgs);
     DISPATCH(c, core_sign_dev(c, sk, n, d_scalars, n_msgs, d_sigs, d_b, d_status, (rt_stream_t)stream));
 }
 int bbs_core_proof_verify_batch_dev(bbs_ctx* p, size_t n, const uint8_t* d_proofs, const uint8_t* d_commit,
@@ -851,6 +931,7 @@ int bbs_core_proof_verify_batch_dev(bbs_ctx* p, size_t n, const uint8_t* d_proof
                                     const uint64_t* d_dis_off, const uint8_t* d_ph, size_t ph_len, uint8_t* d_status,
                                     void* stream) {
     Ctx* c = as_ctx(p);
+    CHECK_COUNTS(n, 1);
     DISPATCH(c, core_proof_verify_dev(c, n, d_proofs, d_commit, d_commit_off, d_idx, d_dis_scalars, d_dis_off, d_ph,
                                       ph_len, d_status, (rt_stream_t)stream));
 }
@@ -863,7 +944,6 @@ int bbs_selftest_field(int curve, int device, int op, size_t n, const uint8_t* a
 }
 int bbs_selftest_g1_mul(int curve, int device, size_t n, const uint8_t* pts, const uint8_t* sc, uint8_t* out) {
     if (rt_set_device(device)) return BBS_E_CUDA;
-    if (rt_set_stack(48 * 1024)) return BBS_E_CUDA;
     if (curve == BBS_CURVE_BLS12_381) return selftest_g1_mul<Bls>(n, pts, sc, out);
     if (curve == BBS_CURVE_BN254) return selftest_g1_mul<Bn>(n, pts, sc, out);
     return arg_error("unknown curve id");
@@ -871,7 +951,6 @@ int bbs_selftest_g1_mul(int curve, int device, size_t n, const uint8_t* pts, con
 int bbs_selftest_pairing(int curve, int device, size_t n, const uint8_t* p_points, const uint8_t* r_points,
                          const uint8_t* q_point, uint8_t* status) {
     if (rt_set_device(device)) return BBS_E_CUDA;
-    if (rt_set_stack(48 * 1024)) return BBS_E_CUDA;
     if (curve == BBS_CURVE_BLS12_381) return selftest_pairing<Bls>(n, p_points, r_points, q_point, status);
     if (curve == BBS_CURVE_BN254) return selftest_pairing<Bn>(n, p_points, r_points, q_point, status);
     return arg_error("unknown curve id");

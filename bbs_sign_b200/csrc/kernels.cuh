@@ -371,7 +371,8 @@ template <class C> BBS_HD void pairing_item(const PairingArgs& a, uint32_t i) {
 // ---- core_sign -----------------------------------------------------------------------------------------
 struct SignArgs {
     CtxView ctx;
-    uint32_t sk[8];            // canonical limbs
+    const uint32_t* sk;        // canonical limbs (8) in a device buffer that the host clears after the call: the secret never
+                               // travels in the kernel-parameter bank (key_gen.rs:29: SecretKey is Zeroize + ZeroizeOnDrop)
     const uint8_t* scalars; uint32_t n_msgs;
     uint8_t* sigs_out;         // n x (G1 compressed || LE32 e)
     uint8_t* b_out;            // optional: n x G1 compressed B (row a7)
@@ -388,7 +389,9 @@ template <class C> BBS_HD bool sign_head(const SignArgs& a, uint32_t i, uint32_t
     // e = H2S(BE(sk) || BE(m_1..m_L) || BE(domain), api_id || "H2S_")   (sign.rs:90-118)
     Xmd48 x;
     x.begin();
-    for (int k = 7; k >= 0; k--) x.s.update_words(&a.sk[k], 1);
+    uint32_t sk[8];
+    for (int k = 0; k < 8; k++) sk[k] = a.sk[k];
+    for (int k = 7; k >= 0; k--) x.s.update_words(&sk[k], 1);
     if (cx.k_inf) g1_set_inf<C>(B); else g1_from_affine<C>(B, cx.K);
     bool ok = true;
     for (uint32_t j = 0; j < a.n_msgs && ok; j++) {
@@ -403,7 +406,7 @@ template <class C> BBS_HD bool sign_head(const SignArgs& a, uint32_t i, uint32_t
     uint32_t okm[12], s[8];
     x.finish(cx.dst_h2s, cx.dst_h2s_len, okm);
     okm48_to_scalar<Fr>(e, okm);
-    fe_add<Fr>(s, a.sk, e);
+    fe_add<Fr>(s, sk, e);
     if (bn_is_zero<8>(s)) { a.status[i] = ST_ERR_MALFORMED; return false; }        // sign.rs:129 panics
     fe_to_mont<Fr>(sm, s);
     return true;
@@ -482,6 +485,9 @@ template <class C, int TPB, int MINB> __global__ void __launch_bounds__(TPB, MIN
     if (live && !g1_is_inf_ool<C>(Aj)) bn_copy<C::Fp::N>(z, Aj + 2 * FPN); else fe_set_one<F>(z);
     block_batch_inverse<F, TPB, true>(z, tree);
     if (live) sign_tail<C>(a, i, Aj, z, e, Baff, bfin);
+    // the tree held products and inverses of the secret values sk + e: leave no trace in shared memory
+    __syncthreads();
+    bn_zero<C::Fp::N>(tree[threadIdx.x]); bn_zero<C::Fp::N>(tree[TPB + threadIdx.x]);
 }
 #endif
 
@@ -636,7 +642,7 @@ template <class C> BBS_HD void proof_gen_item(const ProofGenArgs& a, uint32_t i)
     for (uint64_t k = 0; k < R; k++) {
         uint32_t idx = a.dis_idx[db + k];
         if (idx >= L) GEN_FAIL(ST_ERR_DISCLOSED_INDEX)                          // :143-147
-        if (!((mask[idx >> 5] >> (idx & 31)) & 1)) { mask[idx >> 5] |= 1u << (idx & 31); distinct++; }
+        if (idx < MAX_L && !((mask[idx >> 5] >> (idx & 31)) & 1)) { mask[idx >> 5] |= 1u << (idx & 31); distinct++; }
     }
     if (L != cx.L) GEN_FAIL(ST_ERR_MSG_GEN_LEN)                                 // :228-230
     // the reference de-duplicates the disclosed set (:154-158); its scalar count check is :232-234

@@ -3,6 +3,7 @@ host thread per GPU, statuses written straight into the caller's slice, no colle
 MultiIssuerVerifier: batches whose items name different issuer keys, grouped per key."""
 from __future__ import annotations
 
+import os
 import threading
 from typing import List, Optional, Sequence, Tuple
 
@@ -77,9 +78,13 @@ class ShardedVerifier:
         self._run_sharded(n, work)
         return out
 
-    def rlc_verify_batch(self, signatures: Sequence[bytes], messages: Sequence[Sequence[bytes]], seed: bytes) -> int:
+    def rlc_verify_batch(self, signatures: Sequence[bytes], messages: Sequence[Sequence[bytes]],
+                         seed: Optional[bytes] = None) -> int:
         """Random-linear-combination verdict for the whole batch: every GPU reduces its slice to two compressed G1
-        points (coefficients are indexed globally), GPU 0 adds them and does the single pairing check."""
+        points (coefficients are indexed globally), GPU 0 adds them and does the single pairing check.  The coefficient
+        seed is drawn here (os.urandom), after the batch has been handed over; pass one only for reproducible tests."""
+        if seed is None:
+            seed = os.urandom(32)
         n = len(messages)
         parts: list = [None] * len(self.ctxs)
         status: list = [1] * len(self.ctxs)

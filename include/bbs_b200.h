@@ -15,8 +15,21 @@
  *   Proof fixed : comp(Abar) || comp(Bbar) || comp(D) || LE32(e^) || LE32(r1^) || LE32(r3^) || LE32(c)
  *                 (the fixed-size fields of src/proof_gen.rs:29-39; commitments travel separately)
  *
- * Threading: one context per (GPU, issuer key, header, L).  Calls on one context are serialized by the
- * caller; different contexts are independent (one host thread per GPU for multi-GPU sharding).
+ * Threading: one context per (GPU, issuer key, header, L).  A context is SINGLE-STREAM: every call on it (host-buffer or
+ * *_dev) shares the context's grow-only device scratch, so calls on one context must be serialized by the caller and
+ * consecutive *_dev calls on one context must use the same stream (or be ordered by the caller's events).  Different
+ * contexts are independent (one host thread per GPU for multi-GPU sharding).
+ *
+ * Sizes: n and n * n_msgs (and every flat count) must fit in 32 bits; larger batches return BBS_E_ARG and must be split.
+ *
+ * Validation: every G1 / G2 encoding that enters (signatures, proofs, generators, public key) is checked like ark-serialize
+ * `deserialize_compressed` (Validate::Yes: derived for Signature src/sign.rs:18, Proof src/proof_gen.rs:29, PublicKey
+ * src/key_gen.rs:12): canonical x, flags, on the curve AND in the prime-order subgroup.  Failures: BBS_ST_ERR_MALFORMED
+ * per item, BBS_E_ARG from bbs_ctx_create.
+ *
+ * Secrets: the signing key is copied into a device buffer that is cleared when the call's kernel has run, shared memory
+ * that held sk-derived values is zeroed by the kernel, and the staged messages / scalars are wiped after signing and at
+ * bbs_ctx_destroy (the reference's SecretKey is Zeroize + ZeroizeOnDrop, src/key_gen.rs:29).
  */
 #ifndef BBS_B200_H
 #define BBS_B200_H
@@ -45,9 +58,9 @@ typedef struct bbs_ctx bbs_ctx;
 #define BBS_ST_ERR_MSG_GEN_LEN 2     /* Err(InvalidMessageAndGeneratorsLength)  src/sign.rs:24-28, src/proof_gen.rs:66 */
 #define BBS_ST_ERR_DISCLOSED_INDEX 3 /* Err(InvalidDisclosedIndex)              src/proof_gen.rs:62-65 */
 #define BBS_ST_ERR_IDX_MSG_LEN 4     /* Err(InvalidIndicesAndMessagesLength)    src/proof_gen.rs:72-74 */
-#define BBS_ST_ERR_MALFORMED 5       /* undecodable point, scalar >= r, or an input on which the reference
-                                        panics (duplicate disclosed index src/proof_verify.rs:179; sk+e == 0
-                                        src/sign.rs:129) */
+#define BBS_ST_ERR_MALFORMED 5       /* undecodable point (bad flags, x >= p, not on the curve, not in the prime-order
+                                        subgroup), scalar >= r, or an input on which the reference panics (duplicate
+                                        disclosed index src/proof_verify.rs:179; sk+e == 0 src/sign.rs:129) */
 
 #define BBS_ST_ERR_DISCLOSED_LEN 6   /* Err(InvalidDisclosedIndicesLength)      src/proof_gen.rs:139-141 */
 #define BBS_ST_ERR_RANDOM_LEN 7      /* Err(InvalidRandomScalarsAndUndisclosedIndicesLength)  src/proof_gen.rs:232-234 */
@@ -62,6 +75,10 @@ size_t bbs_proof_fixed_bytes(int curve_id); /* 3*g1 + 4*32 */
 
 /* Last error text of the calling thread ("" if none). */
 const char* bbs_last_error(void);
+
+/* What this library was compiled as: "cuda sm_100a" for the product, anything else (the host simulation that the
+ * GPU-less logic tests build from the same sources) must never be bound by a product loader. */
+const char* bbs_build_info(void);
 
 /* create_generators(count, api_id) (src/utils/interface_utilities.rs:47-73) on the device, with the suite's hash-to-G1
  * (:24-44: BLS12381G1_XMD:SHA-256_SSWU_RO_ / BN254G1_XMD:SHA-256_SVDW_RO_): out = count compressed G1 points
@@ -161,8 +178,15 @@ int bbs_proof_gen_batch(bbs_ctx* ctx, size_t n, const uint8_t* sigs, const uint8
  * One verdict for n signatures under the context's issuer key:
  *     e( sum r_i A_i , W ) * e( sum r_i (e_i A_i - B_i) , BP2 ) == 1,   B_i as in src/verify.rs:81-86,
  * r_i = the first 16 bytes, as a big-endian integer, of SHA-256(seed || BE64(index_base + i)) (1 if that is 0).
- * ACCEPT means every item verifies except with probability 2^-128 over the seed (choose the seed after the batch
- * is fixed); REJECT means at least one item does not; ERR_MALFORMED / ERR_MSG_GEN_LEN as in bbs_core_verify_batch.
+ * ACCEPT means every item verifies except with probability 2^-128 over the seed; REJECT means at least one item does
+ * not; ERR_MALFORMED / ERR_MSG_GEN_LEN as in bbs_core_verify_batch.
+ * THE SEED MUST BE UNPREDICTABLE TO WHOEVER SUBMITS THE BATCH.  With a known seed three colluding items
+ * (A_i + a_i X with sum r_i a_i = sum r_i e_i a_i = 0) pass although none verifies, and deriving r_i from the item's own
+ * bytes does not help (a generalised-birthday search over a large batch finds such a_i).  Therefore:
+ *   - bbs_rlc_[core_]verify_batch: pass seed = NULL and the library draws 32 bytes from the OS CSPRNG after it has received
+ *     the batch (the safe default; an explicit seed is for reproducible tests);
+ *   - sharded use (bbs_rlc_partial* on every GPU + bbs_rlc_combine): the coordinator draws ONE fresh seed after the
+ *     whole batch is fixed and hands it to every shard; it is never reused and never revealed before that.
  * Sharding: every GPU reduces its shard to two compressed G1 points with bbs_rlc_partial[_core] (index_base = the
  * shard's first global index); bbs_rlc_combine adds the shards' points on one GPU and does the single pairing check.
  * bbs_rlc_[core_]verify_batch = one shard + combine. */
@@ -172,9 +196,9 @@ int bbs_rlc_partial(bbs_ctx* ctx, size_t n, const uint8_t* sigs, const uint8_t* 
                     uint32_t n_msgs, const uint8_t seed[32], uint64_t index_base, uint8_t* parts_out, uint8_t* status);
 int bbs_rlc_combine(bbs_ctx* ctx, size_t n_parts, const uint8_t* parts /* n_parts x 2 x G1 */, uint8_t* verdict);
 int bbs_rlc_core_verify_batch(bbs_ctx* ctx, size_t n, const uint8_t* sigs, const uint8_t* msg_scalars, uint32_t n_msgs,
-                              const uint8_t seed[32], uint8_t* verdict);
+                              const uint8_t* seed32_or_null, uint8_t* verdict);
 int bbs_rlc_verify_batch(bbs_ctx* ctx, size_t n, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* offsets,
-                         uint32_t n_msgs, const uint8_t seed[32], uint8_t* verdict);
+                         uint32_t n_msgs, const uint8_t* seed32_or_null, uint8_t* verdict);
 
 /* ---- device-buffer entry points (no copies; all pointers are device pointers on the context's GPU;
  *      work is enqueued on `stream` (a cudaStream_t, NULL = default stream) and NOT synchronized) ------ */
@@ -194,6 +218,15 @@ int bbs_core_proof_verify_batch_dev(bbs_ctx* ctx, size_t n, const uint8_t* d_pro
 
 /* Number of kernels the library has launched on this context since creation (for bench accounting). */
 uint64_t bbs_ctx_launch_count(bbs_ctx* ctx);
+
+/* ---- test hooks (CUDA kernels either way; results are identical) ---------------------------------------
+ * bbs_ctx_use_per_thread_pairing: run the pairing check with the one-thread-per-item kernel that a context with a
+ *   degenerate line (a tangent / chord of the public key's ate walk through the origin; impossible for an honest key)
+ *   falls back to, instead of the cooperative role-warp kernel.
+ * bbs_ctx_set_rlc_windows: digits per 128-bit value of the bucket MSM of the random-linear-combination mode
+ *   (8..32; 0 = the cost model's choice). */
+int bbs_ctx_use_per_thread_pairing(bbs_ctx* ctx, int on);
+int bbs_ctx_set_rlc_windows(bbs_ctx* ctx, uint32_t windows);
 
 /* ---- measurement hooks ------------------------------------------------------------------------------
  * With profiling on, every *_dev batch call records CUDA events on its launching stream around each of its

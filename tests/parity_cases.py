@@ -177,12 +177,14 @@ def _corrupt_sig(ocs, sig, kind, other_sig):
     return sig
 
 
-def case_verify(lib_path, curve_name, L, n=10, header=b"hdr", use_pairing_oracle_on=2):
+def case_verify(lib_path, curve_name, L, n=10, header=b"hdr", use_pairing_oracle_on=2, per_thread_pairing=False):
     """sign -> verify round trips and the rejection classes of sign_verify_tests.rs / core_sign_tests.rs."""
     suite, ocs = SUITES[curve_name]
     sk, pk = keypair(ocs, 1)
     sk2, pk2 = keypair(ocs, 2)
     ctx, gens = make_ctx(lib_path, suite, ocs, pk, header, L)
+    if per_thread_pairing:
+        ctx.use_per_thread_pairing(True)
     msgs = [[rng_bytes(f"m{i}.{j}", 32 if j % 3 else 5) for j in range(L)] for i in range(n)]
     if L:
         msgs[0][0] = b""   # empty message (test_vector.rs:115-119)
@@ -274,11 +276,13 @@ def make_proofs(ocs, sk, pk, header, ph, L, disclosed, n, seed="p"):
     return out
 
 
-def case_proof_verify(lib_path, curve_name, L, disclosed, n=8, header=b"h", ph=b"ph", pairing_on=1):
+def case_proof_verify(lib_path, curve_name, L, disclosed, n=8, header=b"h", ph=b"ph", pairing_on=1, per_thread_pairing=False):
     """proof_verify_tests.rs / bbs_over_bls_tests.rs: happy paths and forged inputs."""
     suite, ocs = SUITES[curve_name]
     sk, pk = keypair(ocs, 1)
     ctx, gens = make_ctx(lib_path, suite, ocs, pk, header, L)
+    if per_thread_pairing:
+        ctx.use_per_thread_pairing(True)
     base = make_proofs(ocs, sk, pk, header, ph, L, disclosed, n)
     dis = sorted(set(disclosed))
     kinds = ["ok", "Abar=identity", "challenge+1", "swap-commit", "wrong-msg", "ok", "Bbar-mutated", "e_cap+1"]
@@ -353,13 +357,15 @@ def rlc_coeff(seed: bytes, i: int) -> int:
     return r or 1
 
 
-def case_rlc(lib_path, curve_name, L=3, n=9):
+def case_rlc(lib_path, curve_name, L=3, n=9, windows=0):
     """Random-linear-combination batch mode against the oracle: the two partial sums of a shard are compared bit-exactly
     with sum r_i A_i and sum r_i (e_i A_i - B_i) computed by the oracle, and the verdicts with the per-item truth."""
     suite, ocs = SUITES[curve_name]
     sk, pk = keypair(ocs, 1)
     header = b"rlc"
     ctx, gens = make_ctx(lib_path, suite, ocs, pk, header, L)
+    if windows:
+        ctx.set_rlc_windows(windows)
     msgs = [[rng_bytes(f"rlc{i}.{j}", 32) for j in range(L)] for i in range(n)]
     sigs = [O.sign(ocs, sk, m, header) for m in msgs]
     seed = rng_bytes("rlc-seed", 32)
@@ -383,6 +389,7 @@ def case_rlc(lib_path, curve_name, L=3, n=9):
     assert st == A.ST_ACCEPT
     assert parts == expected_parts(sigs, 5), "partial sums differ from the oracle"
     assert ctx.rlc_verify_batch(enc, msgs, seed) == A.ST_ACCEPT
+    assert ctx.rlc_verify_batch(enc, msgs) == A.ST_ACCEPT           # seed drawn inside the library (the safe default)
     # two shards with consistent global indexes combine to the same verdict
     p0, _ = ctx.rlc_partial(enc[:4], msgs[:4], seed, 0)
     p1, _ = ctx.rlc_partial(enc[4:], msgs[4:], seed, 4)
@@ -395,6 +402,7 @@ def case_rlc(lib_path, curve_name, L=3, n=9):
     bad[7] = (None, bad[7][1])
     encb = [O.signature_to_bytes(ocs, s) for s in bad]
     assert ctx.rlc_verify_batch(encb, msgs, seed) == A.ST_REJECT
+    assert ctx.rlc_verify_batch(encb, msgs) == A.ST_REJECT
     assert ctx.rlc_partial(encb, msgs, seed, 0)[0] == expected_parts(bad, 0)
     if L > 0:
         m2 = [list(m) for m in msgs]

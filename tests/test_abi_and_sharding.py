@@ -79,6 +79,8 @@ sigs[1] = (sigs[1][0], (sigs[1][1] + 1) % ocs.r)
 sigs[4] = (None, sigs[4][1])
 blob = b"".join(O.signature_to_bytes(ocs, s) for s in sigs)
 lo, hi = shard_bounds(n, world)[rank]
+from bbs_sign_b200 import _native
+_native.load(hostsim.build(), allow_host_simulation=True)     # tests only
 ctx, _ = P.make_ctx(hostsim.build(), suite, ocs, pk, b"", L)
 st = ctx.verify_batch(np.frombuffer(blob[lo * 80: hi * 80], dtype=np.uint8), msgs[lo:hi])
 parts = [None] * world
@@ -117,3 +119,6 @@ def test_reference_arm_prints_the_contract_line():
     assert d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    sys.path.insert(0, root)
+    import bench
+    assert d["config"] == bench.verify_config(65536, 10)        # the same config dict as our arm (bounded sample per step)

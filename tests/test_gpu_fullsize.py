@@ -55,24 +55,100 @@ def test_config2_bls_verify_65536(lib):
 
 
 def test_config3_bn254_core_verify_1m(lib):
-    """configs[2]: 1,048,576 signatures x L = 31 pre-hashed scalars on BN254; bench.run_bn254 raises on any status that
-    differs from the construction (every 16th item has e ^ 1)"""
+    """configs[2]: 1,048,576 signatures x L = 31 pre-hashed scalars on BN254, 1/16 corrupted over all four signature
+    rejection classes; the status vector must equal the construction, and 12 items (every class + random ones) are
+    re-derived by the oracle without pairings: accept <=> A (sk + e) == B."""
     import bench
-    out = bench.run_bn254(argparse.Namespace(n=1 << 20, steps=1, warmup=1))
-    assert out["config"]["n_per_gpu"] == 1 << 20 and out["value"] > 0
+    from bbs_sign_b200 import api as A
+    from oracle import bbs_oracle as O
+    n, L = 1 << 20, 31
+    key = np.load(os.path.join(ROOT, "tests", "golden", "bn254_bench_key.npz"))
+    ctx = A.BatchContext(A.BN254, bytes(key["pk"]), header=b"", n_messages=L)
+    sc, sigs, expect, _ = bench.make_bn254_workload(ctx, lib, n, seed=21, L=L)
+    st = np.zeros(n, dtype=np.uint8)
+    assert lib.bbs_core_verify_batch(ctx.handle, n, bench.ptr(sigs), bench.ptr(sc), L, bench.ptr(st)) == 0
+    assert np.array_equal(st, expect)
+    assert int(expect.sum()) == n - len(range(5, n, 16))
+    cs = O.BN254
+    sk = int.from_bytes(bytes(key["sk"]), "little")
+    pk = cs.g2_decompress(bytes(key["pk"]))
+    assert O.sk_to_pk(cs, sk) == pk
+    gens = O.create_generators_cached(cs, L + 1, cs.api_id)
+    dom = O.calculate_domain(cs, pk, gens[0], gens[1:], b"", cs.api_id)
+    assert ctx.domain() == cs.scalar_le(dom)
+    rnd = random.Random(4)
+    sample = [5, 21, 37, 53, 69, 85, 101, 117] + [rnd.randrange(n) for _ in range(4)]      # 2 x the four kinds + random items
+    sg = sigs.reshape(n, 64)
+    scm = sc.reshape(n, L, 32)
+    for i in sample:
+        m = [int.from_bytes(bytes(scm[i, j]), "little") for j in range(L)]
+        B = O.compute_B(cs, gens, dom, m)
+        Apt = cs.g1_decompress(bytes(sg[i, :32]))
+        e = int.from_bytes(bytes(sg[i, 32:64]), "little")
+        truth = Apt is not None and O.ec_mul(cs.F1, Apt, (sk + e) % cs.r) == B
+        assert bool(st[i]) == truth, i
+    ctx.close()
 
 
 def test_config4_bls_proof_verify_262144(lib):
-    """configs[3]: 262,144 proofs, L = 32, 16 disclosed: the oracle-made fixture (valid + every rejection class) tiled to
-    full size; bench.run_proof raises unless every verdict equals the one the oracle recorded"""
+    """configs[3]: 262,144 DISTINCT proofs (L = 32, 16 disclosed) made by bbs_sign_batch + bbs_proof_gen_batch, 1/16
+    corrupted over the seven rejection classes; statuses must equal the construction.  A sample is checked against the
+    oracle: the proof bytes equal the oracle's proof_gen for the same signature and random scalars, the untouched ones
+    satisfy the pairing-free trapdoor Bbar == sk * Abar, and the oracle's proof_verify (trapdoor mode) agrees."""
     import bench
-    out = bench.run_proof(argparse.Namespace(n=262144, steps=1, warmup=1))
-    assert out["value"] > 0
+    from bbs_sign_b200 import api as A
+    from oracle import bbs_oracle as O
+    n, L, R = 262144, 32, 16
+    U = L - R
+    ctx = A.BatchContext(A.BLS12_381, bench.IRTF_PK, header=b"", n_messages=L)
+    w = bench.make_proof_workload(ctx, lib, n, seed=31, L=L, R=R)
+    st = np.zeros(n, dtype=np.uint8)
+    rc = lib.bbs_proof_verify_batch(ctx.handle, n, bench.ptr(w["fixed"]), bench.ptr(w["commit"]), bench.ptr(w["commit_off"]),
+                                    bench.ptr(w["idx"]), bench.ptr(w["dmsg"]), bench.ptr(w["moff"]), bench.ptr(w["dis_off"]),
+                                    None, 0, bench.ptr(st))
+    assert rc == 0
+    assert np.array_equal(st, w["expect"])
+    assert int(w["expect"].sum()) == n - len(range(5, n, 16))
+    cs = O.BLS12_381
+    sk = bench.IRTF_SK
+    pk = O.sk_to_pk(cs, sk)
+    dis = list(range(0, L, 2))
+    fx = w["fixed"].reshape(n, bench.PROOF_FIXED)
+    cm = w["commit"].reshape(n, U * 32)
+    msgs = w["msgs"].reshape(n, L, 32)
+    dm = w["dmsg"].reshape(n, R, 32)
+    rand = w["rand"].reshape(n, 5 + U, 32)
+    sg = w["sigs"].reshape(n, 80)
+    rnd = random.Random(9)
+    corrupted = [5 + 16 * k for k in range(7)]
+    for i in corrupted + [rnd.randrange(n) for _ in range(3)]:
+        pr = O.Proof(cs.g1_decompress(bytes(fx[i, 0:48])), cs.g1_decompress(bytes(fx[i, 48:96])), cs.g1_decompress(bytes(fx[i, 96:144])),
+                     int.from_bytes(bytes(fx[i, 144:176]), "little"), int.from_bytes(bytes(fx[i, 176:208]), "little"),
+                     int.from_bytes(bytes(fx[i, 208:240]), "little"),
+                     [int.from_bytes(bytes(cm[i, 32 * k:32 * k + 32]), "little") for k in range(U)],
+                     int.from_bytes(bytes(fx[i, 240:272]), "little"))
+        truth = O.proof_verify(cs, pk, pr, b"", b"", [bytes(dm[i, k]) for k in range(R)], dis, trapdoor_sk=sk)
+        assert bool(st[i] == 1) == bool(truth), i
+        if w["expect"][i]:
+            assert pr.b_bar == O.ec_mul(cs.F1, pr.a_bar, sk), i                           # trapdoor: Bbar == sk * Abar
+            sig = (cs.g1_decompress(bytes(sg[i, :48])), int.from_bytes(bytes(sg[i, 48:80]), "little"))
+            rs = [int.from_bytes(bytes(rand[i, k]), "little") for k in range(5 + U)]
+            want = O.proof_gen(cs, pk, sig, b"", b"", [bytes(msgs[i, j]) for j in range(L)], dis, random_scalars=rs)
+            wb = A.ProofBytes.from_canonical(A.BLS12_381, O.proof_to_bytes(cs, want))
+            assert wb.fixed == bytes(fx[i]) and wb.commitments == bytes(cm[i]), i
+    ctx.close()
 
 
 def test_config5_bls_sign_and_rlc_524288(lib):
-    """configs[4] per-GPU share (4M / 8): sign 524,288 message sets, one random-linear-combination verdict; the valid batch
-    must be accepted and the same batch with one flipped bit rejected (bench.run_rlc raises otherwise)"""
+    """configs[4] per-GPU share (4M / 8): sign 524,288 message sets (device-resident and host-buffer paths must agree byte
+    for byte and the batch must pass the random-linear-combination check), then one RLC verdict per step; the valid batch
+    must be accepted and the same batch with one flipped bit rejected (bench_sign / bench_rlc raise otherwise)"""
     import bench
-    out = bench.run_rlc(argparse.Namespace(n=524288, L=10, steps=1, warmup=1))
-    assert out["value"] > 0
+    env = bench.Env()
+    try:
+        out = bench.bench_sign(env, 524288, 1, 3)
+        assert out["value"] > 0 and out["checked"]
+        out = bench.bench_rlc(env, 524288, 1, 3)
+        assert out["value"] > 0 and out["checked"]
+    finally:
+        env.close()

@@ -94,12 +94,10 @@ def test_rlc(lib, curve, L):
 
 @pytest.mark.parametrize("curve,windows,n", [("BLS12_381", 8, 9), ("BN254", 8, 9), ("BLS12_381", 13, 40), ("BN254", 19, 40),
                                              ("BLS12_381", 32, 9), ("BN254", 32, 9), ("BLS12_381", 0, 150)])
-def test_rlc_msm_geometries(lib, curve, windows, n, monkeypatch):
+def test_rlc_msm_geometries(lib, curve, windows, n):
     """bucket MSM (rlc_msm.cuh) with other digit counts than the cost model's pick (0 = the model), incl. uneven digit
     widths and the 16-bit rows: partial sums stay bit-exact against the oracle"""
-    if windows:
-        monkeypatch.setenv("BBS_RLC_WINDOWS", str(windows))
-    P.case_rlc(None, curve, L=2, n=n)
+    P.case_rlc(None, curve, L=2, n=n, windows=windows)
 
 
 @pytest.mark.parametrize("curve,L,dis", [("BLS12_381", 5, [0, 2, 3]), ("BN254", 3, [1]), ("BLS12_381", 2, []),
@@ -187,3 +185,11 @@ def test_g1_mul_edges(lib, curve):
 @pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
 def test_subgroup_validation(lib, curve):
     P.case_subgroup(None, curve)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_per_thread_pairing_kernel(lib, curve):
+    """the one-thread-per-item pairing kernel (the fallback of a context with a degenerate line) gives the same verdicts as
+    the cooperative kernel and the oracle on valid items and every rejection class"""
+    P.case_verify(None, curve, 3, n=12, use_pairing_oracle_on=1, per_thread_pairing=True)
+    P.case_proof_verify(None, curve, 4, [0, 2], n=8, pairing_on=1, per_thread_pairing=True)

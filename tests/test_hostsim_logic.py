@@ -10,12 +10,21 @@ from bbs_sign_b200 import _native
 
 @pytest.fixture(scope="module")
 def lib_path():
-    return hostsim.build()
+    path = hostsim.build()
+    _native.load(path, allow_host_simulation=True)      # tests only: the product loader refuses non-CUDA builds
+    return path
 
 
 @pytest.fixture(scope="module")
 def lib(lib_path):
-    return _native.load(lib_path)
+    return _native.load(lib_path, allow_host_simulation=True)
+
+
+def test_product_loader_refuses_the_host_simulation(lib_path):
+    _native._CACHE.pop(lib_path, None)
+    with pytest.raises(_native.NativeLibraryMissing):
+        _native.load(lib_path)
+    _native.load(lib_path, allow_host_simulation=True)
 
 
 @pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
