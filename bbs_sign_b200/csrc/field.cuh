@@ -22,10 +22,19 @@
 #endif
 #endif
 
+// Field elements are moved with 128-bit loads / stores on the device (fe_ld / fe_st below), so every array that can hold
+// one -- local arrays, shared-memory trees, constant tables, records in global memory -- is 16-byte aligned: local arrays
+// are declared with BBS_A16, element sizes (32 / 48 bytes) keep sub-arrays aligned.
+#if defined(__CUDACC__)
+#define BBS_A16 __align__(16)
+#else
+#define BBS_A16 __attribute__((aligned(16)))
+#endif
+
 #if defined(__CUDACC__)
 #define BBS_CONST_ARRAY(name, n, ...)                                   \
-    static __constant__ uint32_t name##_dev[n] = {__VA_ARGS__};          \
-    static const uint32_t name##_host[n] = {__VA_ARGS__};                \
+    static __constant__ BBS_A16 uint32_t name##_dev[n] = {__VA_ARGS__};  \
+    static const BBS_A16 uint32_t name##_host[n] = {__VA_ARGS__};        \
     BBS_HD const uint32_t* name() {                                      \
         return BBS_SELECT_DEV(name##_dev, name##_host);                  \
     }
@@ -36,7 +45,7 @@
 #endif
 #else
 #define BBS_CONST_ARRAY(name, n, ...)                                   \
-    static const uint32_t name##_host[n] = {__VA_ARGS__};                \
+    static const BBS_A16 uint32_t name##_host[n] = {__VA_ARGS__};        \
     inline const uint32_t* name() { return name##_host; }
 #endif
 
@@ -100,11 +109,44 @@ struct BnFr {
     static BBS_HD const uint32_t* EXP_INV() { return BN_FR_EXP_INV(); }
 };
 
+// ---- 128-bit moves between memory and register arrays (memory operands of the out-of-line functions) ----------
+#ifdef __CUDA_ARCH__
+template <int N> __device__ __forceinline__ void fe_ld(uint32_t* x, const uint32_t* p) {
+    static_assert(N % 4 == 0, "limb count");
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < N / 4; i++) { uint4 v = q[i]; x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w; }
+}
+template <int N> __device__ __forceinline__ void fe_st(uint32_t* p, const uint32_t* x) {
+    static_assert(N % 4 == 0, "limb count");
+    uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < N / 4; i++) q[i] = make_uint4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+}
+#endif
+
+#ifdef __CUDA_ARCH__
+template <int N> __device__ __forceinline__ void bn_ld(uint32_t* x, const uint32_t* p) {
+    if constexpr (N % 4 == 0) fe_ld<N>(x, p);
+    else {
+#pragma unroll
+        for (int i = 0; i < N; i++) x[i] = p[i];
+    }
+}
+template <int N> __device__ __forceinline__ void bn_st(uint32_t* p, const uint32_t* x) {
+    if constexpr (N % 4 == 0) fe_st<N>(p, x);
+    else {
+#pragma unroll
+        for (int i = 0; i < N; i++) p[i] = x[i];
+    }
+}
+#endif
+
 // ---- raw multi-limb helpers ----------------------------------------------------------------------
 template <int N>
 BBS_HD uint32_t bn_add(uint32_t* r, const uint32_t* a, const uint32_t* b) {  // returns carry
 #ifdef __CUDA_ARCH__
-    uint32_t x[N], y[N], z[N];
+    BBS_A16 uint32_t x[N], y[N], z[N];
 #pragma unroll
     for (int i = 0; i < N; i++) { x[i] = a[i]; y[i] = b[i]; }
     uint32_t c = bbs_addn<N>(z, x, y);
@@ -125,7 +167,7 @@ BBS_HD uint32_t bn_add(uint32_t* r, const uint32_t* a, const uint32_t* b) {  // 
 template <int N>
 BBS_HD uint32_t bn_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {  // returns borrow mask
 #ifdef __CUDA_ARCH__
-    uint32_t x[N], y[N], z[N];
+    BBS_A16 uint32_t x[N], y[N], z[N];
 #pragma unroll
     for (int i = 0; i < N; i++) { x[i] = a[i]; y[i] = b[i]; }
     uint32_t c = bbs_subn<N>(z, x, y);
@@ -146,16 +188,29 @@ BBS_HD uint32_t bn_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {  // 
 template <int N>
 BBS_HD bool bn_is_zero(const uint32_t* a) {
     uint32_t o = 0;
+#ifdef __CUDA_ARCH__
+    uint32_t x[N];
+    bn_ld<N>(x, a);
 #pragma unroll
+    for (int i = 0; i < N; i++) o |= x[i];
+#else
     for (int i = 0; i < N; i++) o |= a[i];
+#endif
     return o == 0;
 }
 
 template <int N>
 BBS_HD bool bn_eq(const uint32_t* a, const uint32_t* b) {
     uint32_t o = 0;
+#ifdef __CUDA_ARCH__
+    uint32_t x[N], y[N];
+    bn_ld<N>(x, a);
+    bn_ld<N>(y, b);
 #pragma unroll
+    for (int i = 0; i < N; i++) o |= x[i] ^ y[i];
+#else
     for (int i = 0; i < N; i++) o |= a[i] ^ b[i];
+#endif
     return o == 0;
 }
 
@@ -164,26 +219,33 @@ BBS_HD bool bn_eq(const uint32_t* a, const uint32_t* b) {
 // fe_sqrt's final comparison constant-folded to false; tools/dbg/).
 template <int N>
 BBS_HD void bn_copy(uint32_t* r, const uint32_t* a) {
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-        uint32_t x = a[i];
 #ifdef __CUDA_ARCH__
-        asm volatile("" : "+r"(x));
+    uint32_t x[N];
+    bn_ld<N>(x, a);
+#pragma unroll
+    for (int i = 0; i < N; i++) asm volatile("" : "+r"(x[i]));
+    bn_st<N>(r, x);
+#else
+    for (int i = 0; i < N; i++) r[i] = a[i];
 #endif
-        r[i] = x;
-    }
 }
 
 template <int N>
 BBS_HD void bn_zero(uint32_t* r) {
+#ifdef __CUDA_ARCH__
+    uint32_t x[N];
 #pragma unroll
+    for (int i = 0; i < N; i++) x[i] = 0;
+    bn_st<N>(r, x);
+#else
     for (int i = 0; i < N; i++) r[i] = 0;
+#endif
 }
 
 // a > b as little-endian integers
 template <int N>
 BBS_HD bool bn_gt(const uint32_t* a, const uint32_t* b) {
-    uint32_t t[N];
+    BBS_A16 uint32_t t[N];
     return bn_sub<N>(t, b, a) != 0;  // b - a borrows  <=>  a > b
 }
 
@@ -191,31 +253,34 @@ BBS_HD bool bn_gt(const uint32_t* a, const uint32_t* b) {
 template <class F>
 BBS_HD void fe_add(uint32_t* r, const uint32_t* a, const uint32_t* b) {
     constexpr int N = F::N;
-    uint32_t s[N], d[N];
+    BBS_A16 uint32_t s[N], d[N];
     bn_add<N>(s, a, b);  // 2p < 2^(32N) for every modulus here: no carry out
     uint32_t borrow = bn_sub<N>(d, s, F::P());
 #pragma unroll
-    for (int i = 0; i < N; i++) r[i] = borrow ? s[i] : d[i];
+    for (int i = 0; i < N; i++) d[i] = borrow ? s[i] : d[i];
+    bn_copy<N>(r, d);
 }
 
 template <class F>
 BBS_HD void fe_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {
     constexpr int N = F::N;
-    uint32_t d[N], s[N];
+    BBS_A16 uint32_t d[N], s[N];
     uint32_t borrow = bn_sub<N>(d, a, b);
     bn_add<N>(s, d, F::P());
 #pragma unroll
-    for (int i = 0; i < N; i++) r[i] = borrow ? s[i] : d[i];
+    for (int i = 0; i < N; i++) d[i] = borrow ? s[i] : d[i];
+    bn_copy<N>(r, d);
 }
 
 template <class F>
 BBS_HD void fe_neg(uint32_t* r, const uint32_t* a) {
     constexpr int N = F::N;
-    uint32_t d[N];
+    BBS_A16 uint32_t d[N];
     bool z = bn_is_zero<N>(a);
     bn_sub<N>(d, F::P(), a);
 #pragma unroll
-    for (int i = 0; i < N; i++) r[i] = z ? 0u : d[i];
+    for (int i = 0; i < N; i++) d[i] = z ? 0u : d[i];
+    bn_copy<N>(r, d);
 }
 
 template <class F>
@@ -228,17 +293,19 @@ template <class F>
 BBS_HD void fe_mul_inl(uint32_t* r, const uint32_t* a, const uint32_t* b) {
     constexpr int N = F::N;
 #ifdef __CUDA_ARCH__
-    uint32_t A[N], B[N], M[N], t[N];
+    BBS_A16 uint32_t A[N], B[N], M[N], t[N];
     const uint32_t* pm = F::P();
-#pragma unroll
-    for (int i = 0; i < N; i++) { A[i] = a[i]; B[i] = b[i]; M[i] = pm[i]; }
+    fe_ld<N>(A, a);                           // memory operands: 128-bit loads (16-byte aligned arrays, see BBS_A16)
+    fe_ld<N>(B, b);
+    fe_ld<N>(M, pm);
     bbs_mont_mul<N>(t, A, B, M, F::INV);      // two-accumulator CIOS, result < 2p (gen_mont_mul.cuh)
-    uint32_t d[N];
+    BBS_A16 uint32_t d[N];
     uint32_t borrow = bbs_subn<N>(d, t, M);
 #pragma unroll
-    for (int i = 0; i < N; i++) r[i] = borrow ? t[i] : d[i];
+    for (int i = 0; i < N; i++) t[i] = borrow ? t[i] : d[i];
+    fe_st<N>(r, t);
 #else
-    uint32_t t[N + 2];
+    BBS_A16 uint32_t t[N + 2];
     const uint32_t* pm = F::P();
     for (int i = 0; i < N + 2; i++) t[i] = 0;
     for (int i = 0; i < N; i++) {
@@ -262,7 +329,7 @@ BBS_HD void fe_mul_inl(uint32_t* r, const uint32_t* a, const uint32_t* b) {
         t[N - 1] = (uint32_t)c;
         t[N] = t[N + 1] + (uint32_t)(c >> 32);
     }
-    uint32_t d[N];
+    BBS_A16 uint32_t d[N];
     uint32_t borrow = bn_sub<N>(d, t, pm);
     bool ge = (t[N] != 0) || !borrow;
     for (int i = 0; i < N; i++) r[i] = ge ? d[i] : t[i];
@@ -286,7 +353,7 @@ BBS_HD void fe_to_mont(uint32_t* r, const uint32_t* a) { fe_mul<F>(r, a, F::R2()
 
 template <class F>
 BBS_HD void fe_from_mont(uint32_t* r, const uint32_t* a) {
-    uint32_t one[F::N];
+    BBS_A16 uint32_t one[F::N];
     bn_zero<F::N>(one);
     one[0] = 1;
     fe_mul<F>(r, a, one);
@@ -300,11 +367,11 @@ BBS_HD void fe_set_one(uint32_t* r) { bn_copy<F::N>(r, F::ONE()); }
 template <class F>
 BBS_HDN void fe_pow(uint32_t* r, const uint32_t* a, const uint32_t* e, int ebits) {
     constexpr int N = F::N;
-    uint32_t tab[16][N];
+    BBS_A16 uint32_t tab[16][N];
     fe_set_one<F>(tab[0]);
     bn_copy<N>(tab[1], a);
     for (int i = 2; i < 16; i++) fe_mul<F>(tab[i], tab[i - 1], a);
-    uint32_t acc[N];
+    BBS_A16 uint32_t acc[N];
     int top = (ebits + 3) / 4 - 1;
     {
         uint32_t d = (e[(top * 4) >> 5] >> ((top * 4) & 31)) & 15;
@@ -342,7 +409,7 @@ template <class F>
 BBS_HDN void fe_inv_vt(uint32_t* r, const uint32_t* a) {
     constexpr int N = F::N;
     if (bn_is_zero<N>(a)) { bn_zero<N>(r); return; }
-    uint32_t u[N], v[N], x1[N], x2[N], t[N];
+    BBS_A16 uint32_t u[N], v[N], x1[N], x2[N], t[N];
     bn_copy<N>(u, a); bn_copy<N>(v, F::P());
     bn_zero<N>(x1); x1[0] = 1; bn_zero<N>(x2);
     // invariants: x1 * a = u, x2 * a = v (mod p); u, v odd-or-being-halved, gcd(u, v) = 1
@@ -375,7 +442,7 @@ BBS_HDN void fe_inv_vt(uint32_t* r, const uint32_t* a) {
 // square root for p = 3 mod 4; returns false when a is a non-residue
 template <class F>
 BBS_HDN bool fe_sqrt(uint32_t* r, const uint32_t* a) {
-    uint32_t s[F::N], q[F::N];
+    BBS_A16 uint32_t s[F::N], q[F::N];
     fe_pow<F>(s, a, F::EXP_SQRT(), F::BITS - 1);
     fe_sqr<F>(q, s);
     bool ok = bn_eq<F::N>(q, a);
@@ -386,7 +453,7 @@ BBS_HDN bool fe_sqrt(uint32_t* r, const uint32_t* a) {
 // canonical(a) > (p-1)/2   (the "y is lexicographically largest / negative" flag of both encodings)
 template <class F>
 BBS_HDN bool fe_is_high(const uint32_t* a_mont) {
-    uint32_t c[F::N];
+    BBS_A16 uint32_t c[F::N];
     fe_from_mont<F>(c, a_mont);
     return bn_gt<F::N>(c, F::HALF());
 }

@@ -34,7 +34,7 @@ template <class C> BBS_HD void g1_neg(uint32_t* r, const uint32_t* p) {
 template <class C> BBS_HDN void g1_dbl(uint32_t* r, const uint32_t* p) {
     using F = typename C::Fp;
     const uint32_t *X = p, *Y = p + FPN, *Z = p + 2 * FPN;
-    uint32_t A[FPN], B[FPN], Cc[FPN], D[FPN], E[FPN], Fq[FPN], t[FPN], Z3[FPN];
+    BBS_A16 uint32_t A[FPN], B[FPN], Cc[FPN], D[FPN], E[FPN], Fq[FPN], t[FPN], Z3[FPN];
     fe_sqr<F>(A, X);
     fe_sqr<F>(B, Y);
     fe_sqr<F>(Cc, B);
@@ -54,7 +54,7 @@ template <class C> BBS_HDN void g1_add_mixed(uint32_t* r, const uint32_t* p, con
     using F = typename C::Fp;
     if (g1_is_inf<C>(p)) { g1_from_affine<C>(r, q); return; }
     const uint32_t *X1 = p, *Y1 = p + FPN, *Z1 = p + 2 * FPN, *X2 = q, *Y2 = q + FPN;
-    uint32_t Z1Z1[FPN], U2[FPN], S2[FPN], H[FPN], HH[FPN], I[FPN], J[FPN], rr[FPN], V[FPN], t[FPN], X3[FPN], Y3[FPN], Z3[FPN];
+    BBS_A16 uint32_t Z1Z1[FPN], U2[FPN], S2[FPN], H[FPN], HH[FPN], I[FPN], J[FPN], rr[FPN], V[FPN], t[FPN], X3[FPN], Y3[FPN], Z3[FPN];
     fe_sqr<F>(Z1Z1, Z1);
     fe_mul<F>(U2, X2, Z1Z1);
     fe_mul<F>(S2, Y2, Z1); fe_mul<F>(S2, S2, Z1Z1);
@@ -82,7 +82,7 @@ template <class C> BBS_HDN void g1_add(uint32_t* r, const uint32_t* p, const uin
     if (g1_is_inf<C>(p)) { g1_copy<C>(r, q); return; }
     if (g1_is_inf<C>(q)) { g1_copy<C>(r, p); return; }
     const uint32_t *X1 = p, *Y1 = p + FPN, *Z1 = p + 2 * FPN, *X2 = q, *Y2 = q + FPN, *Z2 = q + 2 * FPN;
-    uint32_t Z1Z1[FPN], Z2Z2[FPN], U1[FPN], U2[FPN], S1[FPN], S2[FPN], H[FPN], I[FPN], J[FPN], rr[FPN], V[FPN], t[FPN],
+    BBS_A16 uint32_t Z1Z1[FPN], Z2Z2[FPN], U1[FPN], U2[FPN], S1[FPN], S2[FPN], H[FPN], I[FPN], J[FPN], rr[FPN], V[FPN], t[FPN],
         X3[FPN], Y3[FPN], Z3[FPN];
     fe_sqr<F>(Z1Z1, Z1);
     fe_sqr<F>(Z2Z2, Z2);
@@ -111,7 +111,7 @@ template <class C> BBS_HDN void g1_add(uint32_t* r, const uint32_t* p, const uin
 template <class C> BBS_HDN bool g1_to_affine(uint32_t* r, const uint32_t* p) {
     using F = typename C::Fp;
     if (g1_is_inf<C>(p)) { bn_zero<2 * C::Fp::N>(r); return false; }
-    uint32_t zi[FPN], zi2[FPN];
+    BBS_A16 uint32_t zi[FPN], zi2[FPN];
     fe_inv<F>(zi, p + 2 * FPN);
     fe_sqr<F>(zi2, zi);
     fe_mul<F>(r, p, zi2);
@@ -124,7 +124,7 @@ template <class C> BBS_HDN bool g1_to_affine(uint32_t* r, const uint32_t* p) {
 template <class C> BBS_HDN bool g1_to_affine_vt(uint32_t* r, const uint32_t* p) {
     using F = typename C::Fp;
     if (g1_is_inf<C>(p)) { bn_zero<2 * C::Fp::N>(r); return false; }
-    uint32_t zi[FPN], zi2[FPN];
+    BBS_A16 uint32_t zi[FPN], zi2[FPN];
     fe_inv_vt<F>(zi, p + 2 * FPN);
     fe_sqr<F>(zi2, zi);
     fe_mul<F>(r, p, zi2);
@@ -136,7 +136,7 @@ template <class C> BBS_HDN bool g1_to_affine_vt(uint32_t* r, const uint32_t* p) 
 // y^2 == x^3 + b  (affine, Montgomery)
 template <class C> BBS_HDN bool g1_on_curve(const uint32_t* a) {
     using F = typename C::Fp;
-    uint32_t l[FPN], rr[FPN];
+    BBS_A16 uint32_t l[FPN], rr[FPN];
     fe_sqr<F>(l, a + FPN);
     fe_sqr<F>(rr, a); fe_mul<F>(rr, rr, a); fe_add<F>(rr, rr, C::B());
     return bn_eq<C::Fp::N>(l, rr);
@@ -146,7 +146,7 @@ template <class C> BBS_HDN bool g1_on_curve(const uint32_t* a) {
 // `Projective * Fr` does).  Used where the scalar is a public constant (context creation, self tests); the per-item
 // multiplications use g1_msm_win4 below.
 template <class C> BBS_HDN void g1_mul_affine(uint32_t* r, const uint32_t* a, const uint32_t* k, int bits) {
-    uint32_t acc[G1J];
+    BBS_A16 uint32_t acc[G1J];
     g1_set_inf<C>(acc);
     for (int i = bits - 1; i >= 0; i--) {
         g1_dbl<C>(acc, acc);
@@ -186,8 +186,8 @@ template <class C, int NP> BBS_HDN void g1_msm_win4(uint32_t* r, const uint32_t*
                                                     const uint32_t (*k2)[9], int bits, const uint32_t* beta) {
     using F = typename C::Fp;
     (void)bits;
-    uint32_t tab[NP][16][3 * C::Fp::N];            // d * P_j, d = 1..16 (Jacobian)
-    uint32_t kk1[NP][5], kk2[NP][5];
+    BBS_A16 uint32_t tab[NP][16][3 * C::Fp::N];            // d * P_j, d = 1..16 (Jacobian)
+    BBS_A16 uint32_t kk1[NP][5], kk2[NP][5];
     for (int j = 0; j < NP; j++) {
         if (!pts[j]) continue;
         g1_from_affine<C>(tab[j][0], pts[j]);
@@ -196,7 +196,7 @@ template <class C, int NP> BBS_HDN void g1_msm_win4(uint32_t* r, const uint32_t*
         win5_recode(kk1[j], k1[j]);
         if (beta) win5_recode(kk2[j], k2[j]);
     }
-    uint32_t acc[G1J];
+    BBS_A16 uint32_t acc[G1J];
     g1_set_inf<C>(acc);
     for (int w = WIN5_WINDOWS - 1; w >= 0; w--) {
         if (!g1_is_inf<C>(acc)) { g1_dbl<C>(acc, acc); g1_dbl<C>(acc, acc); g1_dbl<C>(acc, acc); g1_dbl<C>(acc, acc); g1_dbl<C>(acc, acc); }
@@ -204,7 +204,7 @@ template <class C, int NP> BBS_HDN void g1_msm_win4(uint32_t* r, const uint32_t*
             if (!pts[j]) continue;
             const int d1 = win5_digit(kk1[j], w);
             if (d1) {
-                uint32_t t[G1J];
+                BBS_A16 uint32_t t[G1J];
                 const uint32_t* e = tab[j][(d1 > 0 ? d1 : -d1) - 1];
                 bn_copy<C::Fp::N>(t, e);
                 if (d1 > 0) bn_copy<C::Fp::N>(t + FPN, e + FPN); else fe_neg<F>(t + FPN, e + FPN);
@@ -214,7 +214,7 @@ template <class C, int NP> BBS_HDN void g1_msm_win4(uint32_t* r, const uint32_t*
             if (beta) {
                 const int d2 = win5_digit(kk2[j], w);
                 if (d2) {
-                    uint32_t t[G1J];
+                    BBS_A16 uint32_t t[G1J];
                     const uint32_t* e = tab[j][(d2 > 0 ? d2 : -d2) - 1];
                     fe_mul<F>(t, e, beta);
                     if (d2 > 0) bn_copy<C::Fp::N>(t + FPN, e + FPN); else fe_neg<F>(t + FPN, e + FPN);
@@ -231,7 +231,7 @@ template <class C, int NP> BBS_HDN void g1_msm_win4(uint32_t* r, const uint32_t*
 BBS_HD void bls_glv_split(uint32_t* k1, uint32_t* k2, const uint32_t* k) {
     const uint32_t* lam = BLS_GLV_LAMBDA();
     const uint32_t* mu = BLS_GLV_MU();       // floor(2^256 / lambda), 5 limbs
-    uint32_t prod[13];
+    BBS_A16 uint32_t prod[13];
     for (int i = 0; i < 13; i++) prod[i] = 0;
     for (int i = 0; i < 8; i++) {
         uint64_t c = 0;
@@ -242,9 +242,9 @@ BBS_HD void bls_glv_split(uint32_t* k1, uint32_t* k2, const uint32_t* k) {
         }
         prod[i + 5] = (uint32_t)c;
     }
-    uint32_t q[5];
+    BBS_A16 uint32_t q[5];
     for (int i = 0; i < 5; i++) q[i] = prod[8 + i];          // q^ = floor(k mu / 2^256) in {q - 1, q}
-    uint32_t ql[9];
+    BBS_A16 uint32_t ql[9];
     for (int i = 0; i < 9; i++) ql[i] = 0;
     for (int i = 0; i < 5; i++) {
         uint64_t c = 0;
@@ -255,7 +255,7 @@ BBS_HD void bls_glv_split(uint32_t* k1, uint32_t* k2, const uint32_t* k) {
         }
         if (i + 4 < 9) ql[i + 4] = (uint32_t)c;
     }
-    uint32_t rem[5];
+    BBS_A16 uint32_t rem[5];
     {
         int64_t c = 0;
         for (int i = 0; i < 5; i++) {
@@ -265,7 +265,7 @@ BBS_HD void bls_glv_split(uint32_t* k1, uint32_t* k2, const uint32_t* k) {
         }
     }
     for (int it = 0; it < 2; it++) {          // at most one correction is needed; two for safety
-        uint32_t d[5];
+        BBS_A16 uint32_t d[5];
         int64_t c = 0;
         for (int i = 0; i < 5; i++) {
             c += (int64_t)rem[i] - (int64_t)(i < 4 ? lam[i] : 0);
@@ -306,12 +306,12 @@ template <int NX, int NY> BBS_HD void mp_mul(uint32_t* out, const uint32_t* x, c
 // halves stay below 2 (a + 2b) < 2^128 (tools/gen_constants.py checks the constants; the split is checked against
 // k1 + k2 lambda = k on the device by the G1 self test and against the oracle by every BN254 parity test).
 BBS_HD void bn_glv_split(uint32_t* k1, uint32_t* k2, const uint32_t* k) {
-    uint32_t kp[8];
+    BBS_A16 uint32_t kp[8];
     {
         uint64_t c = 0;
         for (int i = 0; i < 8; i++) { c += (uint64_t)k[i] + BN_FR_P()[i]; kp[i] = (uint32_t)c; c >>= 32; }   // < 2^255
     }
-    uint32_t n1[12], n2[10];
+    BBS_A16 uint32_t n1[12], n2[10];
     mp_mul<4, 8>(n1, BN_GLV_AB(), kp);
     {
         uint64_t c = 0;
@@ -322,12 +322,12 @@ BBS_HD void bn_glv_split(uint32_t* k1, uint32_t* k2, const uint32_t* k) {
         int64_t c = 0;
         for (int i = 0; i < 10; i++) { c += (int64_t)n2[i] - (int64_t)(i < 6 ? BN_GLV_2AB()[i] : 0u); n2[i] = (uint32_t)c; c >>= 32; }
     }
-    uint32_t q1[17], q2[13];
+    BBS_A16 uint32_t q1[17], q2[13];
     mp_mul<12, 5>(q1, n1, BN_GLV_G384());
     mp_mul<10, 3>(q2, n2, BN_GLV_G320());
     const uint32_t* c1 = q1 + 12;      // 5 limbs
     const uint32_t* c2 = q2 + 10;      // 3 limbs
-    uint32_t c1a[9], c2b[5], c1b[7], c2ab[7];
+    BBS_A16 uint32_t c1a[9], c2b[5], c1b[7], c2ab[7];
     mp_mul<5, 4>(c1a, c1, BN_GLV_A());
     mp_mul<3, 2>(c2b, c2, BN_GLV_B());
     mp_mul<5, 2>(c1b, c1, BN_GLV_B());
@@ -351,7 +351,7 @@ template <> BBS_HD void glv_split<Bn>(uint32_t* k1, uint32_t* k2, const uint32_t
 template <class C, int NP> BBS_HDN void g1_msm_scalar(uint32_t* r, const uint32_t* const* pts, const uint32_t* const* ks);
 template <class C, int NP> struct G1Msm {
     static BBS_HD void run(uint32_t* r, const uint32_t* const* pts, const uint32_t* const* ks) {
-        uint32_t k1[NP][9], k2[NP][9];
+        BBS_A16 uint32_t k1[NP][9], k2[NP][9];
         for (int j = 0; j < NP; j++) {
             for (int i = 0; i < 9; i++) { k1[j][i] = 0; k2[j][i] = 0; }
             glv_split<C>(k1[j], k2[j], ks[j]);
@@ -386,7 +386,7 @@ template <> BBS_HDN bool g1_in_subgroup<Bn>(const uint32_t*) { return true; }
 template <> BBS_HDN bool g1_in_subgroup<Bls>(const uint32_t* a) {
     using C = Bls;
     using F = BlsFp;
-    uint32_t acc[G1J], base[G1J];
+    BBS_A16 uint32_t acc[G1J], base[G1J];
     g1_from_affine<C>(acc, a);
     for (int i = 62; i >= 0; i--) {                      // |x| P
         g1_dbl<C>(acc, acc);
@@ -399,7 +399,7 @@ template <> BBS_HDN bool g1_in_subgroup<Bls>(const uint32_t* a) {
     }
     if (g1_is_inf_ool<C>(acc)) return false;
     // (X, Y, Z) == (beta^2 x, -y)  <=>  X + (beta x + x) Z^2 == 0  and  Y + y Z^3 == 0
-    uint32_t zz[FPN], t[FPN], s[FPN];
+    BBS_A16 uint32_t zz[FPN], t[FPN], s[FPN];
     fe_sqr<F>(zz, acc + 2 * FPN);
     fe_mul<F>(t, a, C::GLV_BETA()); fe_add<F>(t, t, a); fe_mul<F>(t, t, zz); fe_add<F>(t, t, acc);
     fe_mul<F>(zz, zz, acc + 2 * FPN); fe_mul<F>(s, a + FPN, zz); fe_add<F>(s, s, acc + FPN);
@@ -417,7 +417,7 @@ template <class C> BBS_HDN void g1_compress_affine(uint8_t* out, const uint32_t*
 template <class C> BBS_HDN int g1_finish_decompress(uint32_t* r, uint32_t* x_canon, bool want_high) {
     using F = typename C::Fp;
     if (!fe_is_canonical<F>(x_canon)) return PT_BAD;
-    uint32_t x[FPN], rhs[FPN], y[FPN];
+    BBS_A16 uint32_t x[FPN], rhs[FPN], y[FPN];
     fe_to_mont<F>(x, x_canon);
     fe_sqr<F>(rhs, x); fe_mul<F>(rhs, rhs, x); fe_add<F>(rhs, rhs, C::B());
     if (!fe_sqrt<F>(y, rhs)) return PT_BAD;
@@ -439,13 +439,13 @@ template <> BBS_HDN int g1_decompress<Bls>(uint32_t* r, const uint8_t* in) {
     uint8_t tmp[48];
     for (int i = 0; i < 48; i++) tmp[i] = in[i];
     tmp[0] = b0 & 0x1f;
-    uint32_t x[12];
+    BBS_A16 uint32_t x[12];
     limbs_from_be<12>(x, tmp);
     return g1_finish_decompress<Bls>(r, x, (b0 & 0x20) != 0);
 }
 template <> BBS_HDN void g1_compress_affine<Bls>(uint8_t* out, const uint32_t* a, bool inf) {
     if (inf) { out[0] = 0xc0; for (int i = 1; i < 48; i++) out[i] = 0; return; }
-    uint32_t x[12];
+    BBS_A16 uint32_t x[12];
     fe_from_mont<BlsFp>(x, a);
     limbs_to_be<12>(out, x);
     out[0] |= 0x80;
@@ -459,13 +459,13 @@ template <> BBS_HDN int g1_decompress<Bn>(uint32_t* r, const uint8_t* in) {
     uint8_t tmp[32];
     for (int i = 0; i < 32; i++) tmp[i] = in[i];
     tmp[31] &= 0x3f;
-    uint32_t x[8];
+    BBS_A16 uint32_t x[8];
     limbs_from_le<8>(x, tmp);
     return g1_finish_decompress<Bn>(r, x, (fl & 0x80) != 0);
 }
 template <> BBS_HDN void g1_compress_affine<Bn>(uint8_t* out, const uint32_t* a, bool inf) {
     if (inf) { for (int i = 0; i < 32; i++) out[i] = 0; out[31] = 0x40; return; }
-    uint32_t x[8];
+    BBS_A16 uint32_t x[8];
     fe_from_mont<BnFp>(x, a);
     limbs_to_le<8>(out, x);
     if (fe_is_high<BnFp>(a + 8)) out[31] |= 0x80;
@@ -473,7 +473,7 @@ template <> BBS_HDN void g1_compress_affine<Bn>(uint8_t* out, const uint32_t* a,
 
 // Jacobian -> compressed bytes (one inversion)
 template <class C> BBS_HDN void g1_compress(uint8_t* out, const uint32_t* p) {
-    uint32_t a[G1A];
+    BBS_A16 uint32_t a[G1A];
     bool ok = g1_to_affine<C>(a, p);
     g1_compress_affine<C>(out, a, !ok);
 }

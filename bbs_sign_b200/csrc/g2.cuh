@@ -6,7 +6,7 @@
 namespace bbs {
 
 template <class C> BBS_HDN void f2_pow(uint32_t* r, const uint32_t* a, const uint32_t* e, int ebits) {
-    uint32_t acc[F2N];
+    BBS_A16 uint32_t acc[F2N];
     f2_one<C>(acc);
     for (int i = ebits - 1; i >= 0; i--) {
         f2_sqr<C>(acc, acc);
@@ -19,7 +19,7 @@ template <class C> BBS_HDN void f2_pow(uint32_t* r, const uint32_t* a, const uin
 template <class C> BBS_HDN bool f2_sqrt(uint32_t* r, const uint32_t* a) {
     using F = typename C::Fp;
     if (f2_is_zero<C>(a)) { f2_zero<C>(r); return true; }
-    uint32_t a1[F2N], alpha[F2N], x0[F2N], m1[F2N], cand[F2N], chk[F2N];
+    BBS_A16 uint32_t a1[F2N], alpha[F2N], x0[F2N], m1[F2N], cand[F2N], chk[F2N];
     f2_pow<C>(a1, a, F::EXP_PM3D4(), F::BITS);
     f2_sqr<C>(alpha, a1); f2_mul<C>(alpha, alpha, a);
     f2_mul<C>(x0, a1, a);
@@ -28,7 +28,7 @@ template <class C> BBS_HDN bool f2_sqrt(uint32_t* r, const uint32_t* a) {
         // cand = u * x0
         fe_neg<F>(cand, x0 + FPN); bn_copy<C::Fp::N>(cand + FPN, x0);
     } else {
-        uint32_t b[F2N];
+        BBS_A16 uint32_t b[F2N];
         f2_one<C>(b); f2_add<C>(b, b, alpha);
         f2_pow<C>(b, b, F::HALF(), F::BITS);
         f2_mul<C>(cand, b, x0);
@@ -48,12 +48,12 @@ template <class C> BBS_HD bool f2_is_high(const uint32_t* y) {
 
 template <class C> BBS_HDN void g2_twist_b(uint32_t* b2);
 template <> BBS_HDN void g2_twist_b<Bls>(uint32_t* b2) {   // 4 (1+u)
-    uint32_t four[12];
+    BBS_A16 uint32_t four[12];
     fe_set_one<BlsFp>(four); fe_dbl<BlsFp>(four, four); fe_dbl<BlsFp>(four, four);
     bn_copy<12>(b2, four); bn_copy<12>(b2 + 12, four);
 }
 template <> BBS_HDN void g2_twist_b<Bn>(uint32_t* b2) {    // 3 / (9+u)
-    uint32_t xi[16], three[16];
+    BBS_A16 uint32_t xi[16], three[16];
     bn_copy<16>(xi, BN_XI());
     f2_inv<Bn>(xi, xi);
     fe_set_one<BnFp>(three); fe_dbl<BnFp>(three + 8, three); fe_add<BnFp>(three, three, three + 8); bn_zero<8>(three + 8);
@@ -69,7 +69,7 @@ template <> BBS_HDN void g2_twist_b<Bn>(uint32_t* b2) {    // 3 / (9+u)
 #define G2J (6 * C::Fp::N)
 template <class C> BBS_HDN void g2j_dbl(uint32_t* r, const uint32_t* p) {          // dbl-2009-l
     const uint32_t *X = p, *Y = p + F2N, *Z = p + 2 * F2N;
-    uint32_t A[F2N], B[F2N], Cc[F2N], D[F2N], E[F2N], Fq[F2N], t[F2N], Z3[F2N];
+    BBS_A16 uint32_t A[F2N], B[F2N], Cc[F2N], D[F2N], E[F2N], Fq[F2N], t[F2N], Z3[F2N];
     f2_sqr<C>(A, X);
     f2_sqr<C>(B, Y);
     f2_sqr<C>(Cc, B);
@@ -86,7 +86,7 @@ template <class C> BBS_HDN void g2j_dbl(uint32_t* r, const uint32_t* p) {       
 template <class C> BBS_HDN void g2j_add_mixed(uint32_t* r, const uint32_t* p, const uint32_t* q /*affine*/) {   // madd-2007-bl
     const uint32_t *X1 = p, *Y1 = p + F2N, *Z1 = p + 2 * F2N, *X2 = q, *Y2 = q + F2N;
     if (f2_is_zero<C>(Z1)) { f2_copy<C>(r, X2); f2_copy<C>(r + F2N, Y2); f2_one<C>(r + 2 * F2N); return; }
-    uint32_t Z1Z1[F2N], U2[F2N], S2[F2N], H[F2N], HH[F2N], I[F2N], J[F2N], rr[F2N], V[F2N], t[F2N], X3[F2N], Y3[F2N], Z3[F2N];
+    BBS_A16 uint32_t Z1Z1[F2N], U2[F2N], S2[F2N], H[F2N], HH[F2N], I[F2N], J[F2N], rr[F2N], V[F2N], t[F2N], X3[F2N], Y3[F2N], Z3[F2N];
     f2_sqr<C>(Z1Z1, Z1);
     f2_mul<C>(U2, X2, Z1Z1);
     f2_mul<C>(S2, Y2, Z1); f2_mul<C>(S2, S2, Z1Z1);
@@ -121,7 +121,7 @@ template <> struct G2Check<Bn> {
     }
 };
 template <class C> BBS_HDN bool g2_in_subgroup(const uint32_t* q /*affine [x|y], on the twist*/) {
-    uint32_t acc[G2J];
+    BBS_A16 uint32_t acc[G2J];
     f2_one<C>(acc); f2_one<C>(acc + F2N); f2_zero<C>(acc + 2 * F2N);
     for (int i = G2Check<C>::BITS - 1; i >= 0; i--) {
         g2j_dbl<C>(acc, acc);
@@ -132,7 +132,7 @@ template <class C> BBS_HDN bool g2_in_subgroup(const uint32_t* q /*affine [x|y],
     // their inverses on the M-type twist (BLS12-381); compared cross-multiplied, so no inversion:
     //   D: X == conj(x) g_x Z^2,  Y == conj(y) g_y Z^3          M (and the sign of x < 0): X g_x == conj(x) Z^2,  Y g_y == -conj(y) Z^3
     const uint32_t *gx = C::FROB(1) + 2 * F2N, *gy = C::FROB(1) + 3 * F2N;
-    uint32_t zz[F2N], zzz[F2N], lx[F2N], ly[F2N], rx[F2N], ry[F2N];
+    BBS_A16 uint32_t zz[F2N], zzz[F2N], lx[F2N], ly[F2N], rx[F2N], ry[F2N];
     f2_sqr<C>(zz, acc + 2 * F2N); f2_mul<C>(zzz, zz, acc + 2 * F2N);
     f2_conj<C>(rx, q); f2_mul<C>(rx, rx, zz);
     f2_conj<C>(ry, q + F2N); f2_mul<C>(ry, ry, zzz);
@@ -150,7 +150,7 @@ template <class C> BBS_HDN bool g2_in_subgroup(const uint32_t* q /*affine [x|y],
 template <class C> BBS_HDN int g2_finish_decompress(uint32_t* r, uint32_t* xc0, uint32_t* xc1, bool want_high) {
     using F = typename C::Fp;
     if (!fe_is_canonical<F>(xc0) || !fe_is_canonical<F>(xc1)) return PT_BAD;
-    uint32_t x[F2N], rhs[F2N], y[F2N], b2[F2N];
+    BBS_A16 uint32_t x[F2N], rhs[F2N], y[F2N], b2[F2N];
     fe_to_mont<F>(x, xc0); fe_to_mont<F>(x + FPN, xc1);
     g2_twist_b<C>(b2);
     f2_sqr<C>(rhs, x); f2_mul<C>(rhs, rhs, x); f2_add<C>(rhs, rhs, b2);
@@ -174,7 +174,7 @@ template <> BBS_HDN int g2_decompress<Bls>(uint32_t* r, const uint8_t* in) {
     uint8_t tmp[48];
     for (int i = 0; i < 48; i++) tmp[i] = in[i];
     tmp[0] = b0 & 0x1f;
-    uint32_t c1[12], c0[12];
+    BBS_A16 uint32_t c1[12], c0[12];
     limbs_from_be<12>(c1, tmp);
     limbs_from_be<12>(c0, in + 48);
     return g2_finish_decompress<Bls>(r, c0, c1, (b0 & 0x20) != 0);
@@ -187,7 +187,7 @@ template <> BBS_HDN int g2_decompress<Bn>(uint32_t* r, const uint8_t* in) {
     uint8_t tmp[32];
     for (int i = 0; i < 32; i++) tmp[i] = in[32 + i];
     tmp[31] &= 0x3f;
-    uint32_t c0[8], c1[8];
+    BBS_A16 uint32_t c0[8], c1[8];
     limbs_from_le<8>(c0, in);
     limbs_from_le<8>(c1, tmp);
     return g2_finish_decompress<Bn>(r, c0, c1, (fl & 0x80) != 0);

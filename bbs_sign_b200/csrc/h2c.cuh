@@ -17,11 +17,11 @@ BBS_HDN void xmd_expand(uint32_t* out, int len_bytes, const uint8_t* m1, uint32_
     s.update(m2, m2_len);
     s.put((uint8_t)(len_bytes >> 8)); s.put((uint8_t)len_bytes); s.put(0);
     s.update(dst, dst_len); s.put((uint8_t)dst_len);
-    uint32_t b0[8], bi[8];
+    BBS_A16 uint32_t b0[8], bi[8];
     s.finish(b0);
     const int ell = (len_bytes + 31) / 32;
     for (int i = 1; i <= ell; i++) {
-        uint32_t x[8];
+        BBS_A16 uint32_t x[8];
         for (int k = 0; k < 8; k++) x[k] = i == 1 ? b0[k] : (b0[k] ^ bi[k]);
         s.init(); s.update_words(x, 8); s.put((uint8_t)i); s.update(dst, dst_len); s.put((uint8_t)dst_len);
         s.finish(bi);
@@ -36,7 +36,7 @@ BBS_HDN void xmd_expand(uint32_t* out, int len_bytes, const uint8_t* m1, uint32_
 // (the 5 limbs above): both are < p, which the device Montgomery product requires of its operands (field.cuh fe_mul).
 template <class F> BBS_HDN void fe_from_wide_be(uint32_t* r, const uint32_t* be, int nwords) {
     constexpr int N = F::N;
-    uint32_t c0[N], c1[N], sh[N];
+    BBS_A16 uint32_t c0[N], c1[N], sh[N];
     for (int i = 0; i < N; i++) {
         c0[i] = i < N - 1 ? be[nwords - 1 - i] : 0u;
         c1[i] = (N - 1 + i) < nwords ? be[nwords - 1 - (N - 1) - i] : 0u;
@@ -57,7 +57,7 @@ template <int N> BBS_HDN bool h2c_is_zero(const uint32_t* a) {
 }
 // sgn0(u) != sgn0(y) for Montgomery inputs (sgn0 = parity of the canonical integer)
 template <class F> BBS_HDN bool h2c_sgn_differs(const uint32_t* u, const uint32_t* y) {
-    uint32_t uc[F::N], yc[F::N];
+    BBS_A16 uint32_t uc[F::N], yc[F::N];
     fe_from_mont<F>(uc, u);
     fe_from_mont<F>(yc, y);
     return ((uc[0] ^ yc[0]) & 1u) != 0;
@@ -67,7 +67,7 @@ template <class F> BBS_HDN bool h2c_sgn_differs(const uint32_t* u, const uint32_
 BBS_HDN void bls_sswu(uint32_t* X, uint32_t* Y, const uint32_t* u) {
     using F = BlsFp;
     constexpr int N = 12;
-    uint32_t u2[N], tv[N], tv1[N], x1[N], g[N], t[N], one[N];
+    BBS_A16 uint32_t u2[N], tv[N], tv1[N], x1[N], g[N], t[N], one[N];
     fe_set_one<F>(one);
     fe_sqr<F>(u2, u);
     fe_mul<F>(t, u2, BLS_H2C_Z());             // Z u^2
@@ -78,7 +78,7 @@ BBS_HDN void bls_sswu(uint32_t* X, uint32_t* Y, const uint32_t* u) {
     else { fe_add<F>(x1, one, tv1); fe_mul<F>(x1, x1, BLS_H2C_NBA()); }
     // g(x1) = x1^3 + A x1 + B
     fe_sqr<F>(g, x1); fe_add<F>(g, g, BLS_H2C_A()); fe_mul<F>(g, g, x1); fe_add<F>(g, g, BLS_H2C_B());
-    uint32_t y[N];
+    BBS_A16 uint32_t y[N];
     if (fe_sqrt<F>(y, g)) { bn_copy<N>(X, x1); }
     else {
         fe_mul<F>(X, t, x1);                   // Z u^2 x1
@@ -91,12 +91,12 @@ BBS_HDN void bls_sswu(uint32_t* X, uint32_t* Y, const uint32_t* u) {
 BBS_HDN void bls_iso11(uint32_t* xo, uint32_t* yo, const uint32_t* X, const uint32_t* Y) {
     using F = BlsFp;
     constexpr int N = 12;
-    uint32_t ax[N], ay[N];
+    BBS_A16 uint32_t ax[N], ay[N];
     bn_copy<N>(ax, X);
     bn_copy<N>(ay, Y);
     for (int q = 0; q < 5; q++) {
         const uint32_t* tb = BLS_H2C_VELU() + q * 5 * N;      // xq, yq, gx*gy, vq, uq
-        uint32_t d[N], d2[N], d3[N], t[N], s[N];
+        BBS_A16 uint32_t d[N], d2[N], d3[N], t[N], s[N];
         fe_sub<F>(d, X, tb);
         fe_inv_vt<F>(d, d);
         fe_sqr<F>(d2, d);
@@ -115,17 +115,17 @@ BBS_HDN void bls_iso11(uint32_t* xo, uint32_t* yo, const uint32_t* X, const uint
 template <class C> BBS_HDN void hash_to_g1(uint32_t* out_aff, const uint8_t* msg, uint32_t len, const uint8_t* dst, uint32_t dst_len);
 template <> BBS_HDN void hash_to_g1<Bls>(uint32_t* out_aff, const uint8_t* msg, uint32_t len, const uint8_t* dst, uint32_t dst_len) {
     using F = BlsFp;
-    uint32_t ub[32], u[12], P0[24], P1[24], x[12], y[12];
+    BBS_A16 uint32_t ub[32], u[12], P0[24], P1[24], x[12], y[12];
     xmd_expand(ub, 128, msg, len, nullptr, 0, dst, dst_len);
     fe_from_wide_be<F>(u, ub, 16);
     bls_sswu(x, y, u); bls_iso11(P0, P0 + 12, x, y);
     fe_from_wide_be<F>(u, ub + 16, 16);
     bls_sswu(x, y, u); bls_iso11(P1, P1 + 12, x, y);
-    uint32_t R[36], Ra[24], acc[36];
+    BBS_A16 uint32_t R[36], Ra[24], acc[36];
     g1_from_affine<Bls>(R, P0);
     g1_add_mixed<Bls>(R, R, P1);
     g1_to_affine_vt<Bls>(Ra, R);
-    uint32_t k[2] = {(uint32_t)BLS_H2C_HEFF, (uint32_t)(BLS_H2C_HEFF >> 32)};
+    BBS_A16 uint32_t k[2] = {(uint32_t)BLS_H2C_HEFF, (uint32_t)(BLS_H2C_HEFF >> 32)};
     g1_mul_affine<Bls>(acc, Ra, k, 64);
     g1_to_affine_vt<Bls>(out_aff, acc);
 }
@@ -134,7 +134,7 @@ template <> BBS_HDN void hash_to_g1<Bls>(uint32_t* out_aff, const uint8_t* msg, 
 BBS_HDN void bn_svdw(uint32_t* X, uint32_t* Y, const uint32_t* u) {
     using F = BnFp;
     constexpr int N = 8;
-    uint32_t one[N], tv1[N], tv2[N], tv3[N], tv4[N], x1[N], x2[N], x3[N], g[N], y[N], t[N];
+    BBS_A16 uint32_t one[N], tv1[N], tv2[N], tv3[N], tv4[N], x1[N], x2[N], x3[N], g[N], y[N], t[N];
     fe_set_one<F>(one);
     fe_sqr<F>(tv1, u); fe_mul<F>(tv1, tv1, BN_H2C_C1());
     fe_add<F>(tv2, one, tv1);
@@ -163,13 +163,13 @@ BBS_HDN void bn_svdw(uint32_t* X, uint32_t* Y, const uint32_t* u) {
 }
 template <> BBS_HDN void hash_to_g1<Bn>(uint32_t* out_aff, const uint8_t* msg, uint32_t len, const uint8_t* dst, uint32_t dst_len) {
     using F = BnFp;
-    uint32_t ub[24], u[8], P0[16], P1[16];
+    BBS_A16 uint32_t ub[24], u[8], P0[16], P1[16];
     xmd_expand(ub, 96, msg, len, nullptr, 0, dst, dst_len);
     fe_from_wide_be<F>(u, ub, 12);
     bn_svdw(P0, P0 + 8, u);
     fe_from_wide_be<F>(u, ub + 12, 12);
     bn_svdw(P1, P1 + 8, u);
-    uint32_t R[24];
+    BBS_A16 uint32_t R[24];
     g1_from_affine<Bn>(R, P0);
     g1_add_mixed<Bn>(R, R, P1);
     g1_to_affine_vt<Bn>(out_aff, R);
@@ -190,7 +190,7 @@ BBS_HD void gen_seed_item(const GenSeedArgs& a, uint32_t) {
     uint32_t l1 = 0, l2 = 0;
     while (s1[l1]) { seed[n + l1] = (uint8_t)s1[l1]; l1++; }
     while (s2[l2]) { seed_dst[n + l2] = (uint8_t)s2[l2]; l2++; }
-    uint32_t v[12];
+    BBS_A16 uint32_t v[12];
     xmd_expand(v, 48, seed, n + l1, nullptr, 0, seed_dst, n + l2);
     for (uint32_t i = 1; i <= a.count; i++) {
         uint8_t vb[48], ctr[8];
@@ -213,7 +213,7 @@ template <class C> BBS_HD void gen_point_item(const GenPointArgs& a, uint32_t i)
     const char* s = "SIG_GENERATOR_DST_";
     uint32_t l = 0;
     while (s[l]) { dst[n + l] = (uint8_t)s[l]; l++; }
-    uint32_t P[2 * C::Fp::N];
+    BBS_A16 uint32_t P[2 * C::Fp::N];
     hash_to_g1<C>(P, a.v + (size_t)i * 48, 48, dst, n + l);
     g1_compress_affine<C>(a.out + (size_t)i * C::G1_BYTES, P, false);
 }

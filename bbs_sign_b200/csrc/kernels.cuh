@@ -93,11 +93,11 @@ template <class C> BBS_HD void ctx_domain_item(const CtxDomainArgs& a, uint32_t)
     x.s.update(a.api_id, a.api_id_len);
     x.s.put_be64(a.header_len);
     x.s.update(a.header, a.header_len);
-    uint32_t okm[12], dom[8];
+    BBS_A16 uint32_t okm[12], dom[8];
     x.finish(a.dst_h2s, a.dst_h2s_len, okm);
     okm48_to_scalar<typename C::Fr>(dom, okm);
     bn_copy<8>(a.domain, dom);
-    uint32_t acc[G1J], p1[G1J];
+    BBS_A16 uint32_t acc[G1J], p1[G1J];
     g1_mul_affine<C>(acc, a.gens, dom, 256);
     g1_from_affine<C>(p1, C::P1());
     g1_add<C>(acc, acc, p1);
@@ -113,7 +113,7 @@ template <class C> BBS_HD void ctx_wbase_item(const CtxTableArgs& a, uint32_t i)
     constexpr int TAB_BITS = TabGeom<C>::BITS;
     const uint32_t w = i % TAB_WINDOWS, g = i / TAB_WINDOWS;
     const uint32_t* base = g == 0 ? a.K : a.gens + g * G1A;
-    uint32_t acc[G1J];
+    BBS_A16 uint32_t acc[G1J];
     g1_from_affine<C>(acc, base);
     if (bn_is_zero<2 * C::Fp::N>(base)) g1_set_inf<C>(acc);          // K at infinity is stored as zeros
     for (uint32_t k = 0; k < w * TAB_BITS; k++) g1_dbl<C>(acc, acc);
@@ -126,13 +126,13 @@ template <class C> BBS_HD bool ctx_table_head(uint32_t* acc, const CtxTableArgs&
     const uint32_t d = i % TAB_ENTRIES + 1;
     const uint32_t* wb = a.wbase + (size_t)(i / TAB_ENTRIES) * G1A;      // (g, w) = i / ENTRIES
     if (bn_is_zero<2 * C::Fp::N>(wb)) { g1_set_inf<C>(acc); return false; }
-    uint32_t k[1] = {d};
+    BBS_A16 uint32_t k[1] = {d};
     g1_mul_affine<C>(acc, wb, k, TAB_BITS);
     return true;
 }
 // one entry with its own inversion (host simulation; the CUDA build uses ctx_table_kernel below)
 template <class C> BBS_HD void ctx_table_item(const CtxTableArgs& a, uint32_t i) {
-    uint32_t acc[G1J];
+    BBS_A16 uint32_t acc[G1J];
     ctx_table_head<C>(acc, a, i);
     g1_to_affine<C>(a.tab + (size_t)i * G1A, acc);
 }
@@ -159,7 +159,7 @@ template <class C> BBS_HD void ctx_lines_coop_item(const CtxLinesCoopArgs& a, ui
         return;
     }
     if (f2_is_zero<C>(src)) { *a.degenerate = 1; bn_zero<4 * C::Fp::N>(dst); return; }
-    uint32_t ai[F2N], bp[F2N];
+    BBS_A16 uint32_t ai[F2N], bp[F2N];
     f2_inv_vt<C>(ai, src);
     f2_mul<C>(bp, src + F2N, ai);
     f2_copy<C>(dst, bp);
@@ -173,7 +173,7 @@ struct H2sArgs {
     uint8_t* out;                                   // 32-byte little-endian scalars
 };
 template <class C> BBS_HD void h2s_item(const H2sArgs& a, uint32_t t) {
-    uint32_t s[8];
+    BBS_A16 uint32_t s[8];
     uint64_t b = a.offsets[t], e = a.offsets[t + 1];
     hash_to_scalar<typename C::Fr>(s, a.msgs + b, (uint32_t)(e - b), a.dst, a.dst_len);
     limbs_to_le<8>(a.out + (size_t)t * 32, s);
@@ -184,20 +184,20 @@ template <class C> BBS_HD void h2s_item(const H2sArgs& a, uint32_t t) {
 template <class C> BBS_HDN void tab_accumulate(uint32_t* acc, const uint32_t* tab, uint32_t g, const uint32_t* s) {
     using G = TabGeom<C>;
     const uint32_t* tg = tab + (size_t)g * G::WINDOWS * G::ENTRIES * G1A;
-    uint32_t k1[5], k2[5];
+    BBS_A16 uint32_t k1[5], k2[5];
     glv_split<C>(k1, k2, s);
     for (int w = 0; w < G::WINDOWS; w++) {
         uint32_t d1 = tab_digit<C>(k1, 5, w), d2 = tab_digit<C>(k2, 5, w);
         if (d1) {
-            uint32_t e[G1A];
+            BBS_A16 uint32_t e[G1A];
             const uint32_t* src = tg + ((size_t)w * G::ENTRIES + (d1 - 1)) * G1A;
-            for (int j = 0; j < G1A; j++) e[j] = src[j];
+            bn_copy<2 * C::Fp::N>(e, src);                               // 96- / 64-byte gather as 128-bit loads
             g1_add_mixed<C>(acc, acc, e);
         }
         if (d2) {
-            uint32_t e[G1A], t[FPN];
+            BBS_A16 uint32_t e[G1A], t[FPN];
             const uint32_t* src = tg + ((size_t)w * G::ENTRIES + (d2 - 1)) * G1A;
-            for (int j = 0; j < G1A; j++) e[j] = src[j];
+            bn_copy<2 * C::Fp::N>(e, src);
             fe_mul<typename C::Fp>(t, e, C::GLV_BETA());            // phi(x, y) = (beta x, y)
             bn_copy<C::Fp::N>(e, t);
             g1_add_mixed<C>(acc, acc, e);
@@ -222,15 +222,15 @@ template <class C> BBS_HD bool verify_g1_head(const VerifyG1Args& a, uint32_t i,
     const CtxView& cx = a.ctx;
     if (a.n_msgs != cx.L) { a.status[i] = ST_ERR_MSG_GEN_LEN; a.flags[i] = FL_DONE; return false; }   // verify.rs:68-71
     const uint8_t* sig = a.sigs + (size_t)i * (C::G1_BYTES + 32);
-    uint32_t A[G1A], e[8];
+    BBS_A16 uint32_t A[G1A], e[8];
     pa = g1_decompress<C>(A, sig);
     bool ok = pa != PT_BAD && fr_from_le32<C>(e, sig + C::G1_BYTES);
     // B = P1 + Q1*domain + sum H_j m_j  (verify.rs:81-86), K = P1 + Q1*domain hoisted into the context
-    uint32_t B[G1J];
+    BBS_A16 uint32_t B[G1J];
     if (cx.k_inf) g1_set_inf<C>(B); else g1_from_affine<C>(B, cx.K);
     const uint8_t* sc = a.scalars + (size_t)i * a.n_msgs * 32;
     for (uint32_t j = 0; j < a.n_msgs && ok; j++) {
-        uint32_t m[8];
+        BBS_A16 uint32_t m[8];
         ok = fr_from_le32<C>(m, sc + j * 32);
         if (ok) tab_accumulate<C>(B, cx.tab, j + 1, m);
     }
@@ -238,7 +238,7 @@ template <class C> BBS_HD bool verify_g1_head(const VerifyG1Args& a, uint32_t i,
     // e(A, W + e BP2) e(B, -BP2) == 1  <=>  e(A, W) e(eA - B, BP2) == 1   (SURVEY 8a note (i))
     g1_neg<C>(Cc, B);
     if (pa == PT_OK) {
-        uint32_t eA[G1J];
+        BBS_A16 uint32_t eA[G1J];
         g1_mul_scalar<C>(eA, A, e);
         g1_add<C>(Cc, Cc, eA);
     }
@@ -254,7 +254,7 @@ template <class C> BBS_HD void verify_g1_tail(const VerifyG1Args& a, uint32_t i,
     uint32_t* pr = a.pair + (size_t)i * PAIR_WORDS;
     const bool cfin = !g1_is_inf_ool<C>(Cc);
     if (cfin) {
-        uint32_t zi2[FPN];
+        BBS_A16 uint32_t zi2[FPN];
         fe_sqr<F>(zi2, zinv);
         fe_mul<F>(pr + 3 * FPN, Cc, zi2);
         fe_mul<F>(zi2, zi2, zinv);
@@ -270,7 +270,7 @@ template <class C> BBS_HD void verify_g1_tail(const VerifyG1Args& a, uint32_t i,
 }
 // one item, its own inversion (host simulation; the CUDA build uses verify_g1_kernel below)
 template <class C> BBS_HD void verify_g1_item(const VerifyG1Args& a, uint32_t i) {
-    uint32_t Cc[G1J], zinv[FPN];
+    BBS_A16 uint32_t Cc[G1J], zinv[FPN];
     int pa = PT_BAD;
     if (!verify_g1_head<C>(a, i, Cc, pa)) return;
     if (!g1_is_inf_ool<C>(Cc)) fe_inv<typename C::Fp>(zinv, Cc + 2 * FPN);
@@ -296,7 +296,7 @@ template <class F, int TPB, bool VT> __device__ __forceinline__ void block_batch
         __syncthreads();
     }
     if (t == 0) {
-        uint32_t r[N];
+        BBS_A16 uint32_t r[N];
         if (VT) fe_inv_vt<F>(r, tree[1]); else fe_inv<F>(r, tree[1]);
         bn_copy<N>(tree[1], r);
     }
@@ -304,7 +304,7 @@ template <class F, int TPB, bool VT> __device__ __forceinline__ void block_batch
     // going down: inv(left) = inv(parent) * right, inv(right) = inv(parent) * left
     for (int w = 1; w < TPB; w <<= 1) {
         if (t < w) {
-            uint32_t l[N], r[N], ip[N];
+            BBS_A16 uint32_t l[N], r[N], ip[N];
             bn_copy<N>(ip, tree[w + t]);
             bn_copy<N>(l, tree[2 * (w + t)]);
             bn_copy<N>(r, tree[2 * (w + t) + 1]);
@@ -319,16 +319,16 @@ template <class F, int TPB, bool VT> __device__ __forceinline__ void block_batch
 // table entries with one inversion per block
 template <class C, int TPB> __global__ void __launch_bounds__(TPB, 4) ctx_table_kernel(const CtxTableArgs a, uint32_t n) {
     using F = typename C::Fp;
-    __shared__ uint32_t tree[2 * TPB][C::Fp::N];
+    __shared__ BBS_A16 uint32_t tree[2 * TPB][C::Fp::N];
     const uint32_t i = blockIdx.x * TPB + threadIdx.x;
-    uint32_t acc[G1J], z[FPN];
+    BBS_A16 uint32_t acc[G1J], z[FPN];
     const bool live = i < n && ctx_table_head<C>(acc, a, i) && !g1_is_inf_ool<C>(acc);
     if (live) bn_copy<C::Fp::N>(z, acc + 2 * FPN); else fe_set_one<F>(z);
     block_batch_inverse<F, TPB, true>(z, tree);
     if (i < n) {
         uint32_t* dst = a.tab + (size_t)i * G1A;
         if (live) {
-            uint32_t zi2[FPN];
+            BBS_A16 uint32_t zi2[FPN];
             fe_sqr<F>(zi2, z);
             fe_mul<F>(dst, acc, zi2);
             fe_mul<F>(zi2, zi2, z);
@@ -341,9 +341,9 @@ template <class C, int TPB> __global__ void __launch_bounds__(TPB, 4) ctx_table_
 
 template <class C, int TPB, int MINB> __global__ void __launch_bounds__(TPB, MINB) verify_g1_kernel(const VerifyG1Args a, uint32_t n) {
     using F = typename C::Fp;
-    __shared__ uint32_t tree[2 * TPB][C::Fp::N];
+    __shared__ BBS_A16 uint32_t tree[2 * TPB][C::Fp::N];
     const uint32_t i = blockIdx.x * TPB + threadIdx.x;
-    uint32_t Cc[G1J], z[FPN];
+    BBS_A16 uint32_t Cc[G1J], z[FPN];
     int pa = PT_BAD;
     const bool live = i < n && verify_g1_head<C>(a, i, Cc, pa);
     if (live && !g1_is_inf_ool<C>(Cc)) bn_copy<C::Fp::N>(z, Cc + 2 * FPN); else fe_set_one<F>(z);
@@ -361,7 +361,7 @@ struct PairingArgs { const uint32_t* lines; const uint32_t* pair; const uint32_t
 template <class C> BBS_HD void pairing_item(const PairingArgs& a, uint32_t i) {
     uint32_t fl = a.flags[i];
     if (fl & FL_DONE) return;
-    uint32_t P[PAIR_WORDS], f[F12N];
+    BBS_A16 uint32_t P[PAIR_WORDS], f[F12N];
     const uint32_t* src = a.pair + (size_t)i * PAIR_WORDS;
     for (int j = 0; j < PAIR_WORDS; j++) P[j] = src[j];
     miller2<C>(f, a.lines, P, (fl & FL_SKIP0) != 0, P + 3 * FPN, (fl & FL_SKIP1) != 0);
@@ -389,13 +389,13 @@ template <class C> BBS_HD bool sign_head(const SignArgs& a, uint32_t i, uint32_t
     // e = H2S(BE(sk) || BE(m_1..m_L) || BE(domain), api_id || "H2S_")   (sign.rs:90-118)
     Xmd48 x;
     x.begin();
-    uint32_t sk[8];
+    BBS_A16 uint32_t sk[8];
     for (int k = 0; k < 8; k++) sk[k] = a.sk[k];
     for (int k = 7; k >= 0; k--) x.s.update_words(&sk[k], 1);
     if (cx.k_inf) g1_set_inf<C>(B); else g1_from_affine<C>(B, cx.K);
     bool ok = true;
     for (uint32_t j = 0; j < a.n_msgs && ok; j++) {
-        uint32_t m[8];
+        BBS_A16 uint32_t m[8];
         ok = fr_from_le32<C>(m, sc + j * 32);
         if (!ok) break;
         for (int k = 7; k >= 0; k--) x.s.update_words(&m[k], 1);
@@ -403,7 +403,7 @@ template <class C> BBS_HD bool sign_head(const SignArgs& a, uint32_t i, uint32_t
     }
     if (!ok) { a.status[i] = ST_ERR_MALFORMED; return false; }
     for (int k = 7; k >= 0; k--) x.s.update_words(&cx.domain[k], 1);
-    uint32_t okm[12], s[8];
+    BBS_A16 uint32_t okm[12], s[8];
     x.finish(cx.dst_h2s, cx.dst_h2s_len, okm);
     okm48_to_scalar<Fr>(e, okm);
     fe_add<Fr>(s, sk, e);
@@ -416,11 +416,11 @@ template <class C> BBS_HD bool sign_head(const SignArgs& a, uint32_t i, uint32_t
 template <class C> BBS_HD void sign_mid(uint32_t* Aj, uint32_t* Baff, bool& bfin, const uint32_t* B, const uint32_t* zinv,
                                         const uint32_t* sinv) {
     using F = typename C::Fp;
-    uint32_t s[8];
+    BBS_A16 uint32_t s[8];
     fe_from_mont<typename C::Fr>(s, sinv);
     bfin = !g1_is_inf_ool<C>(B);
     if (bfin) {
-        uint32_t zi2[FPN];
+        BBS_A16 uint32_t zi2[FPN];
         fe_sqr<F>(zi2, zinv);
         fe_mul<F>(Baff, B, zi2);
         fe_mul<F>(zi2, zi2, zinv);
@@ -436,10 +436,10 @@ template <class C> BBS_HD void sign_tail(const SignArgs& a, uint32_t i, const ui
                                          const uint32_t* Baff, bool bfin) {
     using F = typename C::Fp;
     uint8_t* out = a.sigs_out + (size_t)i * (C::G1_BYTES + 32);
-    uint32_t aff[G1A];
+    BBS_A16 uint32_t aff[G1A];
     const bool afin = !g1_is_inf_ool<C>(Aj);
     if (afin) {
-        uint32_t zi2[FPN];
+        BBS_A16 uint32_t zi2[FPN];
         fe_sqr<F>(zi2, zinv);
         fe_mul<F>(aff, Aj, zi2);
         fe_mul<F>(zi2, zi2, zinv);
@@ -455,7 +455,7 @@ template <class C> BBS_HD void sign_tail(const SignArgs& a, uint32_t i, const ui
 // one item, its own inversions (host simulation; the CUDA build uses sign_kernel below)
 template <class C> BBS_HD void sign_item(const SignArgs& a, uint32_t i) {
     using F = typename C::Fp;
-    uint32_t B[G1J], e[8], sm[8], zinv[FPN], Aj[G1J], Baff[G1A];
+    BBS_A16 uint32_t B[G1J], e[8], sm[8], zinv[FPN], Aj[G1J], Baff[G1A];
     if (!sign_head<C>(a, i, B, e, sm)) return;
     if (!g1_is_inf_ool<C>(B)) fe_inv<F>(zinv, B + 2 * FPN);
     fe_inv<typename C::Fr>(sm, sm);
@@ -470,9 +470,9 @@ template <class C> BBS_HD void sign_item(const SignArgs& a, uint32_t i) {
 template <class C, int TPB, int MINB> __global__ void __launch_bounds__(TPB, MINB) sign_kernel(const SignArgs a, uint32_t n) {
     using F = typename C::Fp;
     using Fr = typename C::Fr;
-    __shared__ uint32_t tree[2 * TPB][C::Fp::N];
+    __shared__ BBS_A16 uint32_t tree[2 * TPB][C::Fp::N];
     const uint32_t i = blockIdx.x * TPB + threadIdx.x;
-    uint32_t B[G1J], e[8], sm[8], z[FPN], Aj[G1J], Baff[G1A];
+    BBS_A16 uint32_t B[G1J], e[8], sm[8], z[FPN], Aj[G1J], Baff[G1A];
     const bool live = i < n && sign_head<C>(a, i, B, e, sm);
     if (live && !g1_is_inf_ool<C>(B)) bn_copy<C::Fp::N>(z, B + 2 * FPN); else fe_set_one<F>(z);
     if (!live) fe_set_one<Fr>(sm);
@@ -514,7 +514,7 @@ template <class C> BBS_HD void proof_g1_item(const ProofG1Args& a, uint32_t i) {
     uint64_t L = R + U;
 #define PROOF_FAIL(code) { a.status[i] = (code); a.flags[i] = FL_DONE; return; }
     // proof_verify.rs:139-150, in the reference's order
-    uint32_t mask[MAX_L / 32];
+    BBS_A16 uint32_t mask[MAX_L / 32];
     for (int k = 0; k < MAX_L / 32; k++) mask[k] = 0;
     bool dup = false;
     for (uint64_t k = 0; k < R; k++) {
@@ -524,26 +524,26 @@ template <class C> BBS_HD void proof_g1_item(const ProofG1Args& a, uint32_t i) {
     }
     if (L != cx.L) PROOF_FAIL(ST_ERR_MSG_GEN_LEN)
     if (dup) PROOF_FAIL(ST_ERR_MALFORMED)     // the reference indexes out of bounds and panics (proof_verify.rs:179)
-    uint32_t Ab[G1A], Bb[G1A], D[G1A], ecap[8], r1cap[8], r3cap[8], c[8];
+    BBS_A16 uint32_t Ab[G1A], Bb[G1A], D[G1A], ecap[8], r1cap[8], r3cap[8], c[8];
     int pA = g1_decompress<C>(Ab, pf), pB = g1_decompress<C>(Bb, pf + GB), pD = g1_decompress<C>(D, pf + 2 * GB);
     bool ok = pA != PT_BAD && pB != PT_BAD && pD != PT_BAD;
     ok = ok && fr_from_le32<C>(ecap, pf + 3 * GB) && fr_from_le32<C>(r1cap, pf + 3 * GB + 32) &&
          fr_from_le32<C>(r3cap, pf + 3 * GB + 64) && fr_from_le32<C>(c, pf + 3 * GB + 96);
     if (!ok) PROOF_FAIL(ST_ERR_MALFORMED)
     // T1 = Bbar*c + Abar*e^ + D*r1^   (proof_verify.rs:163-164): one windowed three-point multi-scalar product
-    uint32_t T1[G1J], T2[G1J];
+    BBS_A16 uint32_t T1[G1J], T2[G1J];
     {
         const uint32_t* pts[3] = {pB == PT_OK ? Bb : nullptr, pA == PT_OK ? Ab : nullptr, pD == PT_OK ? D : nullptr};
         const uint32_t* ks[3] = {c, ecap, r1cap};
         g1_msm_scalar<C, 3>(T1, pts, ks);
     }
     // T2 = Bv*c + D*r3^ + sum H_undisclosed m^   with Bv*c = K*c + sum H_disclosed (c m)   (:165-182)
-    uint32_t cm[8];
+    BBS_A16 uint32_t cm[8];
     fe_to_mont<Fr>(cm, c);
     g1_set_inf<C>(T2);
     if (!cx.k_inf) tab_accumulate<C>(T2, cx.tab, 0, c);
     for (uint64_t k = 0; k < R; k++) {
-        uint32_t m[8];
+        BBS_A16 uint32_t m[8];
         if (!fr_from_le32<C>(m, a.dis_scalars + (db + k) * 32)) PROOF_FAIL(ST_ERR_MALFORMED)
         fe_mul<Fr>(m, m, cm);                                   // c * m_k, canonical
         tab_accumulate<C>(T2, cx.tab, a.dis_idx[db + k] + 1, m);
@@ -552,14 +552,14 @@ template <class C> BBS_HD void proof_g1_item(const ProofG1Args& a, uint32_t i) {
         uint64_t k = 0;
         for (uint32_t j = 0; j < (uint32_t)L; j++) {
             if ((mask[j >> 5] >> (j & 31)) & 1) continue;
-            uint32_t m[8];
+            BBS_A16 uint32_t m[8];
             if (!fr_from_le32<C>(m, a.commitments + (cb + k) * 32)) PROOF_FAIL(ST_ERR_MALFORMED)
             tab_accumulate<C>(T2, cx.tab, j + 1, m);
             k++;
         }
     }
     if (pD == PT_OK) {
-        uint32_t t[G1J];
+        BBS_A16 uint32_t t[G1J];
         g1_mul_scalar<C>(t, D, r3cap);
         g1_add<C>(T2, T2, t);
     }
@@ -568,7 +568,7 @@ template <class C> BBS_HD void proof_g1_item(const ProofG1Args& a, uint32_t i) {
     x.begin();
     x.s.put_be64(R);
     for (uint64_t k = 0; k < R; k++) {
-        uint32_t m[8];
+        BBS_A16 uint32_t m[8];
         x.s.put_be64(a.dis_idx[db + k]);
         limbs_from_le<8>(m, a.dis_scalars + (db + k) * 32);
         for (int q = 7; q >= 0; q--) x.s.update_words(&m[q], 1);
@@ -577,7 +577,7 @@ template <class C> BBS_HD void proof_g1_item(const ProofG1Args& a, uint32_t i) {
     {
         // one shared inversion for T1, T2 (Montgomery's trick)
         bool i1 = g1_is_inf_ool<C>(T1), i2 = g1_is_inf_ool<C>(T2);
-        uint32_t z1[FPN], z2[FPN], zz[FPN], t[FPN], aff[G1A];
+        BBS_A16 uint32_t z1[FPN], z2[FPN], zz[FPN], t[FPN], aff[G1A];
         uint8_t enc[GB];
         if (i1) fe_set_one<F>(z1); else bn_copy<C::Fp::N>(z1, T1 + 2 * FPN);
         if (i2) fe_set_one<F>(z2); else bn_copy<C::Fp::N>(z2, T2 + 2 * FPN);
@@ -592,7 +592,7 @@ template <class C> BBS_HD void proof_g1_item(const ProofG1Args& a, uint32_t i) {
     for (int q = 7; q >= 0; q--) x.s.update_words(&cx.domain[q], 1);
     x.s.put_be64(a.ph_len);
     x.s.update(a.ph, a.ph_len);
-    uint32_t okm[12], c2[8];
+    BBS_A16 uint32_t okm[12], c2[8];
     x.finish(cx.dst_h2s, cx.dst_h2s_len, okm);
     okm48_to_scalar<Fr>(c2, okm);
     if (!bn_eq<8>(c2, c)) PROOF_FAIL(ST_REJECT)                 // proof_verify.rs:108-110: no pairing
@@ -636,7 +636,7 @@ template <class C> BBS_HD void proof_gen_item(const ProofGenArgs& a, uint32_t i)
     const uint64_t cb = a.commit_off[i], U = a.commit_off[i + 1] - cb;
 #define GEN_FAIL(code) { a.status[i] = (code); return; }
     if (R > L) GEN_FAIL(ST_ERR_DISCLOSED_LEN)                                   // proof_gen.rs:139-141
-    uint32_t mask[MAX_L / 32];
+    BBS_A16 uint32_t mask[MAX_L / 32];
     for (int k = 0; k < MAX_L / 32; k++) mask[k] = 0;
     uint64_t distinct = 0;
     for (uint64_t k = 0; k < R; k++) {
@@ -649,31 +649,31 @@ template <class C> BBS_HD void proof_gen_item(const ProofGenArgs& a, uint32_t i)
     if (NR != (L - distinct) + 5 || U != L - distinct) GEN_FAIL(ST_ERR_RANDOM_LEN)
     const uint8_t* sig = a.sigs + (size_t)i * (GB + 32);
     const uint8_t* sc = a.scalars + (size_t)i * L * 32;
-    uint32_t A[G1A], e[8], rs[5][8];
+    BBS_A16 uint32_t A[G1A], e[8], rs[5][8];
     int pa = g1_decompress<C>(A, sig);
     bool ok = pa != PT_BAD && fr_from_le32<C>(e, sig + GB);
     for (int k = 0; k < 5 && ok; k++) ok = fr_from_le32<C>(rs[k], a.rand + (rb + k) * 32);
     if (!ok) GEN_FAIL(ST_ERR_MALFORMED)
     // B = P1 + Q1*domain + sum H_j m_j   (:247-253)
-    uint32_t B[G1J];
+    BBS_A16 uint32_t B[G1J];
     if (cx.k_inf) g1_set_inf<C>(B); else g1_from_affine<C>(B, cx.K);
     for (uint32_t j = 0; j < (uint32_t)L; j++) {
-        uint32_t m[8];
+        BBS_A16 uint32_t m[8];
         if (!fr_from_le32<C>(m, sc + j * 32)) GEN_FAIL(ST_ERR_MALFORMED)
         tab_accumulate<C>(B, cx.tab, j + 1, m);
     }
     // D = B r1 ; Abar = A (r0 r1)   (:254-255)
-    uint32_t r0m[8], r01[8], Baff[G1A], Dj[G1J], Abj[G1J];
+    BBS_A16 uint32_t r0m[8], r01[8], Baff[G1A], Dj[G1J], Abj[G1J];
     fe_to_mont<Fr>(r0m, rs[0]);
     fe_mul<Fr>(r01, r0m, rs[1]);                               // r0 r1, canonical
     bool bfin = g1_to_affine<C>(Baff, B);
     if (bfin) g1_mul_scalar<C>(Dj, Baff, rs[1]); else g1_set_inf<C>(Dj);
     if (pa == PT_OK) g1_mul_scalar<C>(Abj, A, r01); else g1_set_inf<C>(Abj);
     // normalise D and Abar with one inversion (they are multiplied again and serialised)
-    uint32_t Daff[G1A], Abaff[G1A];
+    BBS_A16 uint32_t Daff[G1A], Abaff[G1A];
     bool dfin = !g1_is_inf_ool<C>(Dj), afin = !g1_is_inf_ool<C>(Abj);
     {
-        uint32_t z1[FPN], z2[FPN], zz[FPN], t[FPN];
+        BBS_A16 uint32_t z1[FPN], z2[FPN], zz[FPN], t[FPN];
         if (dfin) bn_copy<C::Fp::N>(z1, Dj + 2 * FPN); else fe_set_one<F>(z1);
         if (afin) bn_copy<C::Fp::N>(z2, Abj + 2 * FPN); else fe_set_one<F>(z2);
         fe_mul<F>(zz, z1, z2); fe_inv<F>(zz, zz);
@@ -683,7 +683,7 @@ template <class C> BBS_HD void proof_gen_item(const ProofGenArgs& a, uint32_t i)
         fe_sqr<F>(z2, zz); fe_mul<F>(Abaff, Abj, z2); fe_mul<F>(z2, z2, zz); fe_mul<F>(Abaff + FPN, Abj + FPN, z2);
     }
     // Bbar = D r0 - Abar e ; T1 = Abar r2 + D r3   (:256-257)
-    uint32_t ne[8], Bbj[G1J], T1[G1J], T2[G1J];
+    BBS_A16 uint32_t ne[8], Bbj[G1J], T1[G1J], T2[G1J];
     fe_neg<Fr>(ne, e);
     const uint32_t* pts[2] = {dfin ? Daff : nullptr, afin ? Abaff : nullptr};
     {
@@ -698,7 +698,7 @@ template <class C> BBS_HD void proof_gen_item(const ProofGenArgs& a, uint32_t i)
         uint64_t k = 0;
         for (uint32_t j = 0; j < (uint32_t)L; j++) {
             if ((mask[j >> 5] >> (j & 31)) & 1) continue;
-            uint32_t m[8];
+            BBS_A16 uint32_t m[8];
             if (!fr_from_le32<C>(m, a.rand + (rb + 5 + k) * 32)) GEN_FAIL(ST_ERR_MALFORMED)
             tab_accumulate<C>(T2, cx.tab, j + 1, m);
             k++;
@@ -710,7 +710,7 @@ template <class C> BBS_HD void proof_gen_item(const ProofGenArgs& a, uint32_t i)
     {
         uint32_t* P[3] = {Bbj, T1, T2};
         bool inf[3];
-        uint32_t z[3][FPN], pre[3][FPN], inv[FPN], t[FPN], aff[G1A];
+        BBS_A16 uint32_t z[3][FPN], pre[3][FPN], inv[FPN], t[FPN], aff[G1A];
         for (int k = 0; k < 3; k++) {
             inf[k] = g1_is_inf_ool<C>(P[k]);
             if (inf[k]) fe_set_one<F>(z[k]); else bn_copy<C::Fp::N>(z[k], P[k] + 2 * FPN);
@@ -720,7 +720,7 @@ template <class C> BBS_HD void proof_gen_item(const ProofGenArgs& a, uint32_t i)
         fe_mul<F>(pre[2], pre[1], z[2]);
         fe_inv<F>(inv, pre[2]);
         for (int k = 2; k >= 0; k--) {
-            uint32_t zi[FPN], zi2[FPN];
+            BBS_A16 uint32_t zi[FPN], zi2[FPN];
             if (k > 0) { fe_mul<F>(zi, inv, pre[k - 1]); fe_mul<F>(t, inv, z[k]); bn_copy<C::Fp::N>(inv, t); }
             else bn_copy<C::Fp::N>(zi, inv);
             fe_sqr<F>(zi2, zi); fe_mul<F>(aff, P[k], zi2); fe_mul<F>(zi2, zi2, zi); fe_mul<F>(aff + FPN, P[k] + FPN, zi2);
@@ -736,7 +736,7 @@ template <class C> BBS_HD void proof_gen_item(const ProofGenArgs& a, uint32_t i)
     x.s.put_be64(distinct);
     for (uint32_t j = 0; j < (uint32_t)L; j++) {
         if (!((mask[j >> 5] >> (j & 31)) & 1)) continue;
-        uint32_t m[8];
+        BBS_A16 uint32_t m[8];
         x.s.put_be64(j);
         limbs_from_le<8>(m, sc + j * 32);
         for (int q = 7; q >= 0; q--) x.s.update_words(&m[q], 1);
@@ -747,12 +747,12 @@ template <class C> BBS_HD void proof_gen_item(const ProofGenArgs& a, uint32_t i)
     for (int q = 7; q >= 0; q--) x.s.update_words(&cx.domain[q], 1);
     x.s.put_be64(a.ph_len);
     x.s.update(a.ph, a.ph_len);
-    uint32_t okm[12], c[8], cm[8];
+    BBS_A16 uint32_t okm[12], c[8], cm[8];
     x.finish(cx.dst_h2s, cx.dst_h2s_len, okm);
     okm48_to_scalar<Fr>(c, okm);
     fe_to_mont<Fr>(cm, c);
     // proof_finalize (:331-365)
-    uint32_t r1m[8], r3[8], t[8], v[8];
+    BBS_A16 uint32_t r1m[8], r3[8], t[8], v[8];
     if (bn_is_zero<8>(rs[1])) GEN_FAIL(ST_ERR_MALFORMED)                       // :347 `inverse().unwrap()` panics
     fe_to_mont<Fr>(r1m, rs[1]); fe_inv<Fr>(r1m, r1m); fe_from_mont<Fr>(r3, r1m);
     fe_mul<Fr>(t, cm, e); fe_add<Fr>(v, rs[2], t); limbs_to_le<8>(out + 3 * GB, v);             // e^ = r2 + e c
@@ -763,7 +763,7 @@ template <class C> BBS_HD void proof_gen_item(const ProofGenArgs& a, uint32_t i)
         uint64_t k = 0;
         for (uint32_t j = 0; j < (uint32_t)L; j++) {
             if ((mask[j >> 5] >> (j & 31)) & 1) continue;
-            uint32_t m[8], rk[8];
+            BBS_A16 uint32_t m[8], rk[8];
             limbs_from_le<8>(m, sc + j * 32);
             limbs_from_le<8>(rk, a.rand + (rb + 5 + k) * 32);
             fe_mul<Fr>(t, cm, m); fe_add<Fr>(v, rk, t);                                          // m^ = r_{5+k} + m c

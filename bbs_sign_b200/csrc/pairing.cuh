@@ -38,7 +38,7 @@ template <class C> BBS_HD int ate_line_count() {
 // ---- G2 affine steps on the twist, emitting line coefficients ------------------------------------
 // T <- 2T ; line: lambda = 3 xT^2 / (2 yT)
 template <class C> BBS_HDN void g2_dbl_step(uint32_t* line, uint32_t* T) {
-    uint32_t lam[F2N], t[F2N], x3[F2N], y3[F2N];
+    BBS_A16 uint32_t lam[F2N], t[F2N], x3[F2N], y3[F2N];
     f2_sqr<C>(lam, T); f2_dbl<C>(t, lam); f2_add<C>(lam, lam, t);
     f2_dbl<C>(t, T + F2N); f2_inv_vt<C>(t, t);
     f2_mul<C>(lam, lam, t);
@@ -50,7 +50,7 @@ template <class C> BBS_HDN void g2_dbl_step(uint32_t* line, uint32_t* T) {
 }
 // T <- T + Q ; line through T and Q
 template <class C> BBS_HDN void g2_add_step(uint32_t* line, uint32_t* T, const uint32_t* Q) {
-    uint32_t lam[F2N], t[F2N], x3[F2N], y3[F2N];
+    BBS_A16 uint32_t lam[F2N], t[F2N], x3[F2N], y3[F2N];
     f2_sub<C>(lam, Q + F2N, T + F2N);
     f2_sub<C>(t, Q, T); f2_inv_vt<C>(t, t);
     f2_mul<C>(lam, lam, t);
@@ -64,7 +64,7 @@ template <class C> BBS_HDN void g2_add_step(uint32_t* line, uint32_t* T, const u
 // Q: affine twist point [x(Fp2)|y(Fp2)], must not be the identity and must have order r.
 // out: line k of pair `pair` lives at out + (2k + pair) * LINE_WORDS.
 template <class C> BBS_HDN void g2_precompute_lines(uint32_t* out, const uint32_t* Q, int pair) {
-    uint32_t T[2 * F2N], nQ[2 * F2N];
+    BBS_A16 uint32_t T[2 * F2N], nQ[2 * F2N];
     bn_copy<4 * C::Fp::N>(T, Q);
     f2_copy<C>(nQ, Q); f2_neg<C>(nQ + F2N, Q + F2N);
     int k = 0;
@@ -75,7 +75,7 @@ template <class C> BBS_HDN void g2_precompute_lines(uint32_t* out, const uint32_
     }
     if (Ate<C>::TAIL) {
         // Q1 = pi(Q) = (conj(x) g1[2], conj(y) g1[3]);  Q2 = -pi^2(Q) = (x g2[2], -y g2[3])  (D-type twist)
-        uint32_t Q1[2 * F2N], Q2[2 * F2N], t[F2N];
+        BBS_A16 uint32_t Q1[2 * F2N], Q2[2 * F2N], t[F2N];
         const uint32_t *g1 = C::FROB(1), *g2 = C::FROB(2);
         f2_conj<C>(t, Q); f2_mul<C>(Q1, t, g1 + 2 * F2N);
         f2_conj<C>(t, Q + F2N); f2_mul<C>(Q1 + F2N, t, g1 + 3 * F2N);
@@ -90,7 +90,7 @@ template <class C> BBS_HDN void g2_precompute_lines(uint32_t* out, const uint32_
 // P is given as (px, py, pz) = (X*Z, Y, Z^3) of a Jacobian point (affine: (x, y, 1)); the evaluated line is
 // scaled by Z^3 in Fp, which the final exponentiation kills.
 template <class C> BBS_HDN void f12_mul_line(uint32_t* f, const uint32_t* line, const uint32_t* P) {
-    uint32_t a[F2N], b[F2N], y[F2N];
+    BBS_A16 uint32_t a[F2N], b[F2N], y[F2N];
     f2_mul_fp<C>(a, line, P + 2 * FPN);          // A * pz
     f2_mul_fp<C>(b, line + F2N, P);              // Bc * px
     bn_copy<C::Fp::N>(y, P + FPN); bn_zero<C::Fp::N>(y + FPN);
@@ -127,7 +127,7 @@ template <class C> BBS_HDN void miller2(uint32_t* f, const uint32_t* lines, cons
 // ---- final exponentiation ---------------------------------------------------------------------------
 // r = a^e for a in the cyclotomic subgroup, e > 0 (a public constant)
 template <class C> BBS_HDN void f12_cyc_pow(uint32_t* r, const uint32_t* a, uint64_t e) {
-    uint32_t acc[F12N];
+    BBS_A16 uint32_t acc[F12N];
     f12_copy<C>(acc, a);
     int top = 63;
     while (!((e >> top) & 1)) top--;
@@ -144,7 +144,7 @@ template <class C> BBS_HDN void final_exp_hard(uint32_t* r, const uint32_t* f);
 // f^x = conj(f^|x|) in the cyclotomic subgroup.
 template <> BBS_HDN void final_exp_hard<Bls>(uint32_t* r, const uint32_t* f) {
     using C = Bls;
-    uint32_t a[F12N], b[F12N], c[F12N];
+    BBS_A16 uint32_t a[F12N], b[F12N], c[F12N];
     f12_cyc_pow<C>(a, f, BLS_X_ABS); f12_conj<C>(a, a); f12_conj<C>(b, f); f12_mul<C>(a, a, b);      // f^(x-1)
     f12_cyc_pow<C>(b, a, BLS_X_ABS); f12_conj<C>(b, b); f12_conj<C>(c, a); f12_mul<C>(a, b, c);      // ^(x-1)
     f12_cyc_pow<C>(b, a, BLS_X_ABS); f12_conj<C>(b, b); f12_frob<C>(c, a, 1); f12_mul<C>(a, b, c);   // ^(x+p)
@@ -158,7 +158,7 @@ template <> BBS_HDN void final_exp_hard<Bls>(uint32_t* r, const uint32_t* f) {
 // BN (x = t > 0): Fuentes-Castaneda et al. addition chain (the one ark-ec's bn model uses)
 template <> BBS_HDN void final_exp_hard<Bn>(uint32_t* r, const uint32_t* f) {
     using C = Bn;
-    uint32_t y0[F12N], y1[F12N], y3[F12N], y4[F12N], y6[F12N], y8[F12N], y9[F12N], t[F12N], u[F12N];
+    BBS_A16 uint32_t y0[F12N], y1[F12N], y3[F12N], y4[F12N], y6[F12N], y8[F12N], y9[F12N], t[F12N], u[F12N];
     f12_cyc_pow<C>(y0, f, BN_T); f12_conj<C>(y0, y0);        // f^-x
     f12_cyc_sqr<C>(y1, y0);                                  // y1
     f12_cyc_sqr<C>(t, y1);                                   // y2
@@ -182,7 +182,7 @@ template <> BBS_HDN void final_exp_hard<Bn>(uint32_t* r, const uint32_t* f) {
 
 // f^((p^12-1)/r * c) == 1 ?   (c = 3 for BLS12, 1 for BN; gcd(c, r) = 1 so the verdict is unchanged)
 template <class C> BBS_HDN bool final_exp_is_one(const uint32_t* f) {
-    uint32_t a[F12N], b[F12N];
+    BBS_A16 uint32_t a[F12N], b[F12N];
     f12_inv<C>(a, f);
     f12_conj<C>(b, f);
     f12_mul<C>(a, a, b);            // f^(p^6-1)

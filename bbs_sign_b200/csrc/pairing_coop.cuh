@@ -305,7 +305,7 @@ __global__ void __maxnreg__(Coop<C>::MAXREG) pairing_coop_kernel(const CoopArgs 
             // (x, y) -> (x / y, 1 / y), one point per role-warp (y != 0 on a curve of odd order; skipped pairs hold zeros)
             COOP_BAR();
             if (role < 2) {
-                uint32_t x[N], y[N], yi[N];
+                BBS_A16 uint32_t x[N], y[N], yi[N];
                 coop_load<N>(x, cells + (16 + role) * CELL);
                 coop_load<N>(y, cells + (16 + role) * CELL + Q * 32);
                 fe_inv<typename C::Fp>(yi, y);
@@ -388,7 +388,7 @@ __global__ void __maxnreg__(Coop<C>::MAXREG) pairing_coop_kernel(const CoopArgs 
                 for (int q = 0; q < 2 * Q; q++) { if (sub == 5) g[q * 32] = c[q * 32]; else c[q * 32] = g[q * 32]; }
             }
             else if (sub == 8) {                                           // INV: cell.c0 = cell.c0^-1 (Fermat, fe_inv)
-                uint32_t v[N], o[N];
+                BBS_A16 uint32_t v[N], o[N];
                 coop_load<N>(v, cells + arg * CELL);
                 fe_inv<typename C::Fp>(o, v);
                 coop_store<N>(cells + arg * CELL, o);

@@ -22,7 +22,7 @@ struct RlcArgs {
     const uint8_t* scalars;     // n x n_msgs x LE32
     uint32_t n_msgs, n;
     uint64_t index_base;        // global index of item 0 of this shard (coefficients depend on the global index)
-    uint32_t seed[8];           // the 32-byte seed as big-endian words
+    BBS_A16 uint32_t seed[8];           // the 32-byte seed as big-endian words
     uint32_t* sc_part;          // [blocks][n_msgs + 1][8]  canonical Fr limbs
     uint32_t* bad;              // != 0: some item was malformed
 };
@@ -33,7 +33,7 @@ __device__ __forceinline__ void rlc_coeff(uint32_t* r, const uint32_t* seed_be, 
     s.init();
     s.update_words(seed_be, 8);
     s.put_be64(index);
-    uint32_t h[8];
+    BBS_A16 uint32_t h[8];
     s.finish(h);
     r[0] = h[3]; r[1] = h[2]; r[2] = h[1]; r[3] = h[0];
     for (int i = 4; i < 8; i++) r[i] = 0;
@@ -70,23 +70,23 @@ struct RlcCombineArgs {
 // added per sum by a block tree, normalised in two warps and handed to the single pairing check
 template <class C> __global__ void __launch_bounds__(RLC_TPB, 1) rlc_combine_kernel(const RlcCombineArgs a) {
     using F = typename C::Fp;
-    __shared__ uint32_t sp[RLC_TPB][3 * C::Fp::N];
-    __shared__ uint32_t S[2][3 * C::Fp::N];
+    __shared__ BBS_A16 uint32_t sp[RLC_TPB][3 * C::Fp::N];
+    __shared__ BBS_A16 uint32_t S[2][3 * C::Fp::N];
     __shared__ uint32_t bad, skip[2];
     const CtxView& cx = a.ctx;
     const uint32_t t = threadIdx.x;
     if (t == 0) bad = 0;
     __syncthreads();
-    uint32_t acc[G1J];
+    BBS_A16 uint32_t acc[G1J];
     g1_set_inf<C>(acc);
     for (uint32_t idx = t; idx < 2 * a.n_parts; idx += RLC_TPB) {     // RLC_TPB is even: a thread only meets its own sum
-        uint32_t p[G1A];
+        BBS_A16 uint32_t p[G1A];
         const int st = g1_decompress<C>(p, a.parts + (size_t)idx * C::G1_BYTES);
         if (st == PT_BAD) atomicOr(&bad, 1u);
         if (st == PT_OK) g1_add_mixed<C>(acc, acc, p);
     }
     for (uint32_t w = 0; w < 2; w++) {
-        uint32_t mine[G1J];
+        BBS_A16 uint32_t mine[G1J];
         if ((t & 1) == w) g1_copy<C>(mine, acc); else g1_set_inf<C>(mine);
         rlc_block_sum_points<C>(sp, mine);
         if (t == 0) g1_copy<C>(S[w], sp[0]);
@@ -98,7 +98,7 @@ template <class C> __global__ void __launch_bounds__(RLC_TPB, 1) rlc_combine_ker
     }
     if ((t & 31) == 0 && (t >> 5) < 2) {
         const uint32_t w = t >> 5;
-        uint32_t aff[G1A];
+        BBS_A16 uint32_t aff[G1A];
         const bool fin = g1_to_affine_vt<C>(aff, S[w]);
         uint32_t* pr = a.pair + w * 3 * FPN;
         bn_copy<2 * C::Fp::N>(pr, aff);

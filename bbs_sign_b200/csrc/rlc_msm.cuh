@@ -44,28 +44,28 @@ struct RlcPrepArgs {
 };
 template <class C> __global__ void __launch_bounds__(RLC_TPB, 4) rlc_prep_kernel(const RlcPrepArgs pa) {
     using Fr = typename C::Fr;
-    __shared__ uint32_t ss[RLC_TPB][8];
+    __shared__ BBS_A16 uint32_t ss[RLC_TPB][8];
     const RlcArgs& a = pa.base;
     const uint32_t i = blockIdx.x * RLC_TPB + threadIdx.x;
     const bool valid = i < a.n;
-    uint32_t rm[8], r[8];
+    BBS_A16 uint32_t rm[8], r[8];
     bn_zero<8>(rm);
     bn_zero<8>(r);
     bool ok = true;
     const uint8_t* sc = a.scalars + (size_t)(valid ? i : 0) * a.n_msgs * 32;
     if (valid) {
         const uint8_t* sig = a.sigs + (size_t)i * (C::G1_BYTES + 32);
-        uint32_t A[G1A], e[8], kv[12];
+        BBS_A16 uint32_t A[G1A], e[8], kv[12];
         for (int k = 0; k < 12; k++) kv[k] = 0;
         int st = g1_decompress<C>(A, sig);
         ok = st != PT_BAD && fr_from_le32<C>(e, sig + C::G1_BYTES);
         rlc_coeff(r, a.seed, a.index_base + i);
         fe_to_mont<Fr>(rm, r);
         if (ok && st == PT_OK) {
-            uint32_t ae[8];
+            BBS_A16 uint32_t ae[8];
             fe_mul<Fr>(ae, rm, e);                  // r_i e_i mod r, canonical
             for (int k = 0; k < 4; k++) kv[k] = r[k];
-            uint32_t k1[5], k2[5];
+            BBS_A16 uint32_t k1[5], k2[5];
             glv_split<C>(k1, k2, ae);
             for (int k = 0; k < 4; k++) { kv[4 + k] = k1[k]; kv[8 + k] = k2[k]; }
             uint32_t* dst = pa.pts + (size_t)i * G1A;
@@ -88,10 +88,10 @@ template <class C> __global__ void __launch_bounds__(RLC_TPB, 4) rlc_prep_kernel
     if (threadIdx.x == 0) bn_copy<8>(scp, ss[0]);
     __syncthreads();
     for (uint32_t j = 0; j < a.n_msgs; j++) {
-        uint32_t t[8];
+        BBS_A16 uint32_t t[8];
         bn_zero<8>(t);
         if (valid && ok) {
-            uint32_t m[8];
+            BBS_A16 uint32_t m[8];
             if (fr_from_le32<C>(m, sc + j * 32)) fe_mul<Fr>(t, rm, m); else ok = false;
         }
         rlc_block_sum_fr<C>(ss, t);
@@ -149,7 +149,7 @@ struct MsmBucketArgs { const uint32_t* offsets; const uint32_t* entries; const u
 // the warp keeps adding: bucket sizes (Poisson around n / 2^c) no longer cost max-over-lanes per warp.
 template <class C> __global__ void __launch_bounds__(128, 4) msm_bucket_kernel(const MsmBucketArgs a) {
     using F = typename C::Fp;
-    uint32_t acc[G1J];
+    BBS_A16 uint32_t acc[G1J];
     uint32_t b = 0, j = 0, end = 0;
     bool have = false;
     for (;;) {
@@ -168,11 +168,11 @@ template <class C> __global__ void __launch_bounds__(128, 4) msm_bucket_kernel(c
         }
         const uint32_t e = a.entries[j++];
         const uint4* src = (const uint4*)(a.pts + (size_t)(e & 0x7fffffffu) * G1A);
-        uint32_t p[G1A];
+        BBS_A16 uint32_t p[G1A];
 #pragma unroll
         for (int q = 0; q < G1A / 4; q++) { uint4 v = __ldg(src + q); p[4 * q] = v.x; p[4 * q + 1] = v.y; p[4 * q + 2] = v.z; p[4 * q + 3] = v.w; }
         if (e >> 31) {
-            uint32_t t[FPN];
+            BBS_A16 uint32_t t[FPN];
             fe_mul<F>(t, p, C::GLV_BETA());            // phi(x, y) = (beta x, y)
             bn_copy<C::Fp::N>(p, t);
         }
@@ -184,13 +184,13 @@ struct MsmReduceArgs { MsmPlan plan; const uint32_t* buckets; uint32_t* row_part
 // grid (red_blocks, rows): thread t of a row owns the digits t*chunk + 1 .. t*chunk + chunk and produces
 // sum_j (t*chunk + j) bucket[t*chunk + j] = tot + (t*chunk) run  by running sums; the block adds its threads' points
 template <class C> __global__ void __launch_bounds__(RLC_TPB, 4) msm_reduce_kernel(const MsmReduceArgs a) {
-    __shared__ uint32_t sp[RLC_TPB][3 * C::Fp::N];
+    __shared__ BBS_A16 uint32_t sp[RLC_TPB][3 * C::Fp::N];
     const uint32_t c = a.plan.c, chunk = a.plan.chunk, row = blockIdx.y;
     const uint32_t t = blockIdx.x * RLC_TPB + threadIdx.x, base = t * chunk, nd = 1u << msm_digit_bits(row % a.plan.W, a.plan.W);
-    uint32_t P[G1J];
+    BBS_A16 uint32_t P[G1J];
     g1_set_inf<C>(P);
     if (base < nd) {
-        uint32_t run[G1J];
+        BBS_A16 uint32_t run[G1J];
         g1_set_inf<C>(run);
         const uint32_t* brow = a.buckets + ((size_t)row << c) * G1J;
         for (uint32_t j = chunk; j >= 1; j--) {
@@ -199,7 +199,7 @@ template <class C> __global__ void __launch_bounds__(RLC_TPB, 4) msm_reduce_kern
             g1_add<C>(P, P, run);
         }
         if (base) {
-            uint32_t m[G1J];
+            BBS_A16 uint32_t m[G1J];
             g1_set_inf<C>(m);
             for (int bit = (int)c - 1; bit >= 0; bit--) {
                 g1_dbl<C>(m, m);
@@ -227,17 +227,17 @@ struct RlcMsmFinishArgs {
 template <class C> __global__ void __launch_bounds__(RLC_TPB, 1) rlc_msm_finish_kernel(const RlcMsmFinishArgs a) {
     using Fr = typename C::Fr;
     using F = typename C::Fp;
-    __shared__ uint32_t sp[RLC_TPB][3 * C::Fp::N];
-    __shared__ uint32_t ss[RLC_TPB][8];
-    __shared__ uint32_t sums[MAX_L + 1][8];
-    __shared__ uint32_t res[3][3 * C::Fp::N];        // S1, S2', F
-    __shared__ uint32_t sf[32][3 * C::Fp::N];        // warp 3: partial sums of F
+    __shared__ BBS_A16 uint32_t sp[RLC_TPB][3 * C::Fp::N];
+    __shared__ BBS_A16 uint32_t ss[RLC_TPB][8];
+    __shared__ BBS_A16 uint32_t sums[MAX_L + 1][8];
+    __shared__ BBS_A16 uint32_t res[3][3 * C::Fp::N];        // S1, S2', F
+    __shared__ BBS_A16 uint32_t sf[32][3 * C::Fp::N];        // warp 3: partial sums of F
     __shared__ uint32_t skip[2];
     const CtxView& cx = a.ctx;
     const uint32_t t = threadIdx.x, W = a.plan.W, rows = a.plan.rows;
     // Fr sums over the prep blocks
     for (uint32_t j = 0; j <= a.n_msgs; j++) {
-        uint32_t v[8];
+        BBS_A16 uint32_t v[8];
         bn_zero<8>(v);
         for (uint32_t b = t; b < a.n_blocks; b += RLC_TPB) fe_add<Fr>(v, v, a.sc_part + ((size_t)b * (a.n_msgs + 1) + j) * 8);
         rlc_block_sum_fr<C>(ss, v);
@@ -246,7 +246,7 @@ template <class C> __global__ void __launch_bounds__(RLC_TPB, 1) rlc_msm_finish_
     }
     // row totals (rows <= 64): tpr threads per row add the reduce blocks' partial points, then a small tree per row
     const uint32_t tpr = rows <= 16 ? 8u : rows <= 32 ? 4u : rows <= 64 ? 2u : 1u;
-    uint32_t acc[G1J];
+    BBS_A16 uint32_t acc[G1J];
     {
         const uint32_t row = t / tpr, sub = t % tpr;
         g1_set_inf<C>(acc);
@@ -282,10 +282,10 @@ template <class C> __global__ void __launch_bounds__(RLC_TPB, 1) rlc_msm_finish_
     }
     __syncthreads();
     if (lane == 0 && job < 2) {
-        uint32_t S[G1J], aff[G1A];
+        BBS_A16 uint32_t S[G1J], aff[G1A];
         if (job == 0) g1_copy<C>(S, res[0]);
         else {
-            uint32_t nF[G1J];
+            BBS_A16 uint32_t nF[G1J];
             g1_neg<C>(nF, res[2]);
             g1_add<C>(S, res[1], nF);
         }

@@ -12,7 +12,7 @@ template <class C> BBS_HD void field_test_item(const FieldTestArgs& t, uint32_t 
     using Fr = typename C::Fr;
     if (t.op <= 4 || t.op == 7) {
         constexpr int N = Fp::N;
-        uint32_t a[N], b[N], r[N];
+        BBS_A16 uint32_t a[N], b[N], r[N];
         limbs_from_le<N>(a, t.a + (size_t)i * 4 * N);
         limbs_from_le<N>(b, t.b + (size_t)i * 4 * N);
         fe_to_mont<Fp>(a, a); fe_to_mont<Fp>(b, b);
@@ -25,7 +25,7 @@ template <class C> BBS_HD void field_test_item(const FieldTestArgs& t, uint32_t 
         fe_from_mont<Fp>(r, r);
         limbs_to_le<N>(t.out + (size_t)i * 4 * N, r);
     } else {
-        uint32_t a[8], b[8], r[8];
+        BBS_A16 uint32_t a[8], b[8], r[8];
         limbs_from_le<8>(a, t.a + (size_t)i * 32);
         limbs_from_le<8>(b, t.b + (size_t)i * 32);
         fe_to_mont<Fr>(a, a); fe_to_mont<Fr>(b, b);
@@ -38,7 +38,7 @@ template <class C> BBS_HD void field_test_item(const FieldTestArgs& t, uint32_t 
 
 struct G1MulTestArgs { const uint8_t* pts; const uint8_t* sc; uint8_t* out; };
 template <class C> BBS_HD void g1_mul_test_item(const G1MulTestArgs& t, uint32_t i) {
-    uint32_t A[G1A], k[8], R[G1J];
+    BBS_A16 uint32_t A[G1A], k[8], R[G1J];
     uint8_t* o = t.out + (size_t)i * C::G1_BYTES;
     int st = g1_decompress<C>(A, t.pts + (size_t)i * C::G1_BYTES);
     limbs_from_le<8>(k, t.sc + (size_t)i * 32);
@@ -62,7 +62,7 @@ template <class C> BBS_HD void pair_test_prep_item(const PairTestPrepArgs& t, ui
 }
 struct PairTestArgs { const uint8_t* p; const uint8_t* r; const uint32_t* lines; const uint32_t* st; uint8_t* status; };
 template <class C> BBS_HD void pair_test_item(const PairTestArgs& t, uint32_t i) {
-    uint32_t P[G1A], R[G1A], a0[3 * FPN], a1[3 * FPN], f[F12N];
+    BBS_A16 uint32_t P[G1A], R[G1A], a0[3 * FPN], a1[3 * FPN], f[F12N];
     int sp = g1_decompress<C>(P, t.p + (size_t)i * C::G1_BYTES);
     int sr = g1_decompress<C>(R, t.r + (size_t)i * C::G1_BYTES);
     if (sp == PT_BAD || sr == PT_BAD || t.st[0] == PT_BAD) { t.status[i] = ST_ERR_MALFORMED; return; }

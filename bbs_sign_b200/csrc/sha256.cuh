@@ -135,7 +135,7 @@ struct Xmd48 {
 // < 6r for BN254), hi * 2^256 mod r = mont_mul(hi, R^2) since R = 2^256.
 template <class Fr>
 BBS_HDN void okm48_to_scalar(uint32_t* r, const uint32_t* be12) {
-    uint32_t lo[8], hi[8], t[8];
+    BBS_A16 uint32_t lo[8], hi[8], t[8];
     for (int i = 0; i < 8; i++) lo[i] = be12[11 - i];
     for (int i = 0; i < 4; i++) hi[i] = be12[3 - i];
     for (int i = 4; i < 8; i++) hi[i] = 0;

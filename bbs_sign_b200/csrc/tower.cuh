@@ -25,7 +25,7 @@ struct Bls {
     static BBS_HD const uint32_t* FROB(int j) { return j == 1 ? BLS_FROB1() : (j == 2 ? BLS_FROB2() : BLS_FROB3()); }
     // r = a * (1+u)
     static BBS_HD void mul_xi(uint32_t* r, const uint32_t* a) {
-        uint32_t t0[12], t1[12];
+        BBS_A16 uint32_t t0[12], t1[12];
         fe_sub<Fp>(t0, a, a + 12);
         fe_add<Fp>(t1, a, a + 12);
         bn_copy<12>(r, t0);
@@ -47,7 +47,7 @@ struct Bn {
     static BBS_HD const uint32_t* FROB(int j) { return j == 1 ? BN_FROB1() : (j == 2 ? BN_FROB2() : BN_FROB3()); }
     // r = a * (9+u) = (9a0 - a1) + (9a1 + a0) u
     static BBS_HD void mul_xi(uint32_t* r, const uint32_t* a) {
-        uint32_t t0[8], t1[8], x[8];
+        BBS_A16 uint32_t t0[8], t1[8], x[8];
         fe_dbl<Fp>(x, a); fe_dbl<Fp>(x, x); fe_dbl<Fp>(x, x); fe_add<Fp>(x, x, a);          // 9 a0
         fe_sub<Fp>(t0, x, a + 8);
         fe_dbl<Fp>(x, a + 8); fe_dbl<Fp>(x, x); fe_dbl<Fp>(x, x); fe_add<Fp>(x, x, a + 8);  // 9 a1
@@ -84,7 +84,7 @@ template <class C> BBS_HD void f2_conj(uint32_t* r, const uint32_t* a) {
 // Karatsuba, 3 base-field products
 template <class C> BBS_HDN void f2_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
     using F = typename C::Fp;
-    uint32_t t0[FPN], t1[FPN], s0[FPN], s1[FPN], t2[FPN];
+    BBS_A16 uint32_t t0[FPN], t1[FPN], s0[FPN], s1[FPN], t2[FPN];
     fe_mul<F>(t0, a, b);
     fe_mul<F>(t1, a + FPN, b + FPN);
     fe_add<F>(s0, a, a + FPN);
@@ -97,7 +97,7 @@ template <class C> BBS_HDN void f2_mul(uint32_t* r, const uint32_t* a, const uin
 // (a0+a1)(a0-a1), 2 a0 a1
 template <class C> BBS_HDN void f2_sqr(uint32_t* r, const uint32_t* a) {
     using F = typename C::Fp;
-    uint32_t s[FPN], d[FPN], m[FPN];
+    BBS_A16 uint32_t s[FPN], d[FPN], m[FPN];
     fe_add<F>(s, a, a + FPN);
     fe_sub<F>(d, a, a + FPN);
     fe_mul<F>(m, a, a + FPN);
@@ -109,7 +109,7 @@ template <class C> BBS_HD void f2_mul_fp(uint32_t* r, const uint32_t* a, const u
 }
 template <class C> BBS_HDN void f2_inv(uint32_t* r, const uint32_t* a) {
     using F = typename C::Fp;
-    uint32_t n[FPN], t[FPN];
+    BBS_A16 uint32_t n[FPN], t[FPN];
     fe_sqr<F>(n, a);
     fe_sqr<F>(t, a + FPN);
     fe_add<F>(n, n, t);
@@ -122,7 +122,7 @@ template <class C> BBS_HDN void f2_inv(uint32_t* r, const uint32_t* a) {
 // variable-time variant for context creation (one thread, public data): field.cuh fe_inv_vt
 template <class C> BBS_HDN void f2_inv_vt(uint32_t* r, const uint32_t* a) {
     using F = typename C::Fp;
-    uint32_t n[FPN], t[FPN];
+    BBS_A16 uint32_t n[FPN], t[FPN];
     fe_sqr<F>(n, a);
     fe_sqr<F>(t, a + FPN);
     fe_add<F>(n, n, t);
@@ -145,7 +145,7 @@ template <class C> BBS_HD void f6_neg(uint32_t* r, const uint32_t* a) {
 template <class C> BBS_HD void f6_copy(uint32_t* r, const uint32_t* a) { bn_copy<6 * C::Fp::N>(r, a); }
 // r = a * v  (in place safe)
 template <class C> BBS_HD void f6_mul_by_v(uint32_t* r, const uint32_t* a) {
-    uint32_t t[F2N], a0[F2N], a1[F2N];
+    BBS_A16 uint32_t t[F2N], a0[F2N], a1[F2N];
     C::mul_xi(t, a + 2 * F2N);
     f2_copy<C>(a0, a);
     f2_copy<C>(a1, a + F2N);
@@ -156,7 +156,7 @@ template <class C> BBS_HD void f6_mul_by_v(uint32_t* r, const uint32_t* a) {
 // Karatsuba: 6 Fp2 products
 template <class C> BBS_HDN void f6_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
     const uint32_t *a0 = a, *a1 = a + F2N, *a2 = a + 2 * F2N, *b0 = b, *b1 = b + F2N, *b2 = b + 2 * F2N;
-    uint32_t v0[F2N], v1[F2N], v2[F2N], s[F2N], t[F2N], c0[F2N], c1[F2N], c2[F2N];
+    BBS_A16 uint32_t v0[F2N], v1[F2N], v2[F2N], s[F2N], t[F2N], c0[F2N], c1[F2N], c2[F2N];
     f2_mul<C>(v0, a0, b0);
     f2_mul<C>(v1, a1, b1);
     f2_mul<C>(v2, a2, b2);
@@ -174,7 +174,7 @@ template <class C> BBS_HDN void f6_mul(uint32_t* r, const uint32_t* a, const uin
 // a * (b0 + b1 v): 5 Fp2 products
 template <class C> BBS_HDN void f6_mul_by_01(uint32_t* r, const uint32_t* a, const uint32_t* b0, const uint32_t* b1) {
     const uint32_t *a0 = a, *a1 = a + F2N, *a2 = a + 2 * F2N;
-    uint32_t aa[F2N], bb[F2N], s[F2N], t[F2N], c0[F2N], c1[F2N], c2[F2N];
+    BBS_A16 uint32_t aa[F2N], bb[F2N], s[F2N], t[F2N], c0[F2N], c1[F2N], c2[F2N];
     f2_mul<C>(aa, a0, b0);
     f2_mul<C>(bb, a1, b1);
     f2_add<C>(s, a1, a2); f2_mul<C>(c0, s, b1); f2_sub<C>(c0, c0, bb); C::mul_xi(c0, c0); f2_add<C>(c0, c0, aa);
@@ -184,7 +184,7 @@ template <class C> BBS_HDN void f6_mul_by_01(uint32_t* r, const uint32_t* a, con
 }
 // a * (b1 v): 3 Fp2 products
 template <class C> BBS_HD void f6_mul_by_1(uint32_t* r, const uint32_t* a, const uint32_t* b1) {
-    uint32_t c0[F2N], c1[F2N], c2[F2N];
+    BBS_A16 uint32_t c0[F2N], c1[F2N], c2[F2N];
     f2_mul<C>(c0, a + 2 * F2N, b1); C::mul_xi(c0, c0);
     f2_mul<C>(c1, a, b1);
     f2_mul<C>(c2, a + F2N, b1);
@@ -192,7 +192,7 @@ template <class C> BBS_HD void f6_mul_by_1(uint32_t* r, const uint32_t* a, const
 }
 template <class C> BBS_HDN void f6_inv(uint32_t* r, const uint32_t* a) {
     const uint32_t *a0 = a, *a1 = a + F2N, *a2 = a + 2 * F2N;
-    uint32_t c0[F2N], c1[F2N], c2[F2N], t[F2N], d[F2N];
+    BBS_A16 uint32_t c0[F2N], c1[F2N], c2[F2N], t[F2N], d[F2N];
     // c0 = a0^2 - xi a1 a2 ; c1 = xi a2^2 - a0 a1 ; c2 = a1^2 - a0 a2
     f2_sqr<C>(c0, a0); f2_mul<C>(t, a1, a2); C::mul_xi(t, t); f2_sub<C>(c0, c0, t);
     f2_sqr<C>(c1, a2); C::mul_xi(c1, c1); f2_mul<C>(t, a0, a1); f2_sub<C>(c1, c1, t);
@@ -208,7 +208,7 @@ template <class C> BBS_HDN void f6_inv(uint32_t* r, const uint32_t* a) {
 template <class C> BBS_HD void f12_copy(uint32_t* r, const uint32_t* a) { bn_copy<12 * C::Fp::N>(r, a); }
 template <class C> BBS_HD void f12_one(uint32_t* r) { bn_zero<12 * C::Fp::N>(r); fe_set_one<typename C::Fp>(r); }
 template <class C> BBS_HD bool f12_is_one(const uint32_t* a) {
-    uint32_t one[FPN];
+    BBS_A16 uint32_t one[FPN];
     fe_set_one<typename C::Fp>(one);
     uint32_t o = 0;
     for (int i = 0; i < FPN; i++) o |= a[i] ^ one[i];
@@ -219,7 +219,7 @@ template <class C> BBS_HD void f12_conj(uint32_t* r, const uint32_t* a) {
     f6_copy<C>(r, a); f6_neg<C>(r + F6N, a + F6N);
 }
 template <class C> BBS_HDN void f12_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
-    uint32_t aa[F6N], bb[F6N], s[F6N], t[F6N];
+    BBS_A16 uint32_t aa[F6N], bb[F6N], s[F6N], t[F6N];
     f6_mul<C>(aa, a, b);
     f6_mul<C>(bb, a + F6N, b + F6N);
     f6_add<C>(s, a, a + F6N);
@@ -232,7 +232,7 @@ template <class C> BBS_HDN void f12_mul(uint32_t* r, const uint32_t* a, const ui
 }
 // complex squaring: 2 Fp6 products
 template <class C> BBS_HDN void f12_sqr(uint32_t* r, const uint32_t* a) {
-    uint32_t ab[F6N], s[F6N], t[F6N];
+    BBS_A16 uint32_t ab[F6N], s[F6N], t[F6N];
     f6_mul<C>(ab, a, a + F6N);
     f6_add<C>(s, a, a + F6N);
     f6_mul_by_v<C>(t, a + F6N);
@@ -244,7 +244,7 @@ template <class C> BBS_HDN void f12_sqr(uint32_t* r, const uint32_t* a) {
     f6_add<C>(r + F6N, ab, ab);
 }
 template <class C> BBS_HDN void f12_inv(uint32_t* r, const uint32_t* a) {
-    uint32_t t0[F6N], t1[F6N];
+    BBS_A16 uint32_t t0[F6N], t1[F6N];
     f6_mul<C>(t0, a, a);
     f6_mul<C>(t1, a + F6N, a + F6N);
     f6_mul_by_v<C>(t1, t1);
@@ -259,14 +259,14 @@ template <class C> BBS_HDN void f12_frob(uint32_t* r, const uint32_t* a, int j) 
     const uint32_t* g = C::FROB(j);
     const int wpow[6] = {0, 2, 4, 1, 3, 5};
     for (int s = 0; s < 6; s++) {
-        uint32_t t[F2N];
+        BBS_A16 uint32_t t[F2N];
         if (j & 1) f2_conj<C>(t, a + s * F2N); else f2_copy<C>(t, a + s * F2N);
         f2_mul<C>(r + s * F2N, t, g + wpow[s] * F2N);
     }
 }
 // f *= (c0 + c1 v) + (c4 v) w      [M-type twist line; BLS12-381]
 template <class C> BBS_HDN void f12_mul_by_014(uint32_t* f, const uint32_t* c0, const uint32_t* c1, const uint32_t* c4) {
-    uint32_t aa[F6N], bb[F6N], s[F6N], o[F2N];
+    BBS_A16 uint32_t aa[F6N], bb[F6N], s[F6N], o[F2N];
     f6_mul_by_01<C>(aa, f, c0, c1);
     f6_mul_by_1<C>(bb, f + F6N, c4);
     f2_add<C>(o, c1, c4);
@@ -279,7 +279,7 @@ template <class C> BBS_HDN void f12_mul_by_014(uint32_t* f, const uint32_t* c0, 
 }
 // f *= c0 + (c3 + c4 v) w          [D-type twist line; BN254]
 template <class C> BBS_HDN void f12_mul_by_034(uint32_t* f, const uint32_t* c0, const uint32_t* c3, const uint32_t* c4) {
-    uint32_t a[F6N], b[F6N], e[F6N], o[F2N];
+    BBS_A16 uint32_t a[F6N], b[F6N], e[F6N], o[F2N];
     for (int i = 0; i < 3; i++) f2_mul<C>(a + i * F2N, f + i * F2N, c0);
     f6_mul_by_01<C>(b, f + F6N, c3, c4);
     f2_add<C>(o, c0, c3);
@@ -294,7 +294,7 @@ template <class C> BBS_HDN void f12_mul_by_034(uint32_t* f, const uint32_t* c0, 
 template <class C> BBS_HDN void f12_cyc_sqr(uint32_t* r, const uint32_t* a) {
     // z0=c0.c0 z4=c0.c1 z3=c0.c2 z2=c1.c0 z1=c1.c1 z5=c1.c2
     const uint32_t *z0 = a, *z4 = a + F2N, *z3 = a + 2 * F2N, *z2 = a + 3 * F2N, *z1 = a + 4 * F2N, *z5 = a + 5 * F2N;
-    uint32_t t0[F2N], t1[F2N], t2[F2N], t3[F2N], t4[F2N], t5[F2N], tmp[F2N], s[F2N], u[F2N];
+    BBS_A16 uint32_t t0[F2N], t1[F2N], t2[F2N], t3[F2N], t4[F2N], t5[F2N], tmp[F2N], s[F2N], u[F2N];
     // (x + y Y)^2 in Fp4 = Fp2[Y]/(Y^2 - xi):  (x^2 + xi y^2) + 2xy Y
 #define BBS_FP4_SQR(x, y, lo, hi)                                                     \
     f2_mul<C>(tmp, x, y);                                                             \
@@ -305,7 +305,7 @@ template <class C> BBS_HDN void f12_cyc_sqr(uint32_t* r, const uint32_t* a) {
     BBS_FP4_SQR(z2, z3, t2, t3)
     BBS_FP4_SQR(z4, z5, t4, t5)
 #undef BBS_FP4_SQR
-    uint32_t o[F12N];
+    BBS_A16 uint32_t o[F12N];
     // z0' = 3 t0 - 2 z0 ; z1' = 3 t1 + 2 z1
     f2_sub<C>(s, t0, z0); f2_dbl<C>(s, s); f2_add<C>(o, s, t0);
     f2_add<C>(s, t1, z1); f2_dbl<C>(s, s); f2_add<C>(o + 4 * F2N, s, t1);
