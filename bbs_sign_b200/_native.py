@@ -29,6 +29,14 @@ SYMBOLS = {
     "bbs_ctx_destroy": (None, [C.c_void_p]),
     "bbs_ctx_domain": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bbs_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
+    "bbs_ctx_memory_bytes": (C.c_uint64, [C.c_void_p]),
+    "bbs_issuer_set_create": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t,
+                                        C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "bbs_issuer_set_destroy": (None, [C.c_void_p]),
+    "bbs_issuer_set_memory_bytes": (C.c_uint64, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "bbs_verify_batch_multi": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                         C.c_void_p]),
+    "bbs_core_verify_batch_multi": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "bbs_ctx_use_per_thread_pairing": (C.c_int, [C.c_void_p, C.c_int]),
     "bbs_ctx_set_rlc_windows": (C.c_int, [C.c_void_p, C.c_uint32]),
     "bbs_msg_to_scalars": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -152,6 +152,9 @@ class BatchContext:
     def launch_count(self) -> int:
         return int(self.lib.bbs_ctx_launch_count(self._h))
 
+    def memory_bytes(self) -> int:
+        return int(self.lib.bbs_ctx_memory_bytes(self._h))
+
     # ---- interface_utilities.rs:76-88 ----
     def msg_to_scalars(self, messages: Sequence[bytes]) -> np.ndarray:
         flat, offs = _pack_ragged(messages)
@@ -351,6 +354,89 @@ class BatchContext:
         for i in range(n):
             if bad[i]:
                 st[i] = self._length_error_status(proofs[i], disclosed_indexes[i])
+        return st
+
+
+class IssuerSet:
+    """Many issuer keys over one generator list / header (`bbs_issuer_set_create`): the reference's `PublicKey::verify`
+    takes the key per call (verify.rs:18-30), so a batch may name a different issuer per item.  The generator tables are
+    shared; a key costs ~26 KB (BLS12-381).  `status[i]` = ST_ACCEPT for a usable key, ST_ERR_MALFORMED for one that ark's
+    `PublicKey::deserialize_compressed` refuses; items naming such a key come back ST_ERR_MALFORMED."""
+
+    def __init__(self, suite: Ciphersuite, pks: Sequence[bytes], header: bytes = b"", n_messages: Optional[int] = None,
+                 generators: Optional[bytes] = None, api_id: Optional[bytes] = None, device: int = 0,
+                 lib_path: Optional[str] = None):
+        self.suite = suite
+        self.lib = _native.load(lib_path)
+        if generators is None:
+            if n_messages is None:
+                raise BbsError("n_messages or generators required")
+            generators = suite.create_generators(n_messages + 1, device=device, lib_path=lib_path)
+        self.n_generators = len(generators) // suite.g1_bytes
+        self.L = self.n_generators - 1
+        self.api_id = suite.api_id if api_id is None else api_id
+        self.n_issuers = len(pks)
+        if any(len(pk) != suite.g2_bytes for pk in pks):
+            raise BbsError("public key has the wrong length")
+        blob = _buf(b"".join(bytes(pk) for pk in pks))
+        self.status = np.zeros(self.n_issuers, dtype=np.uint8)
+        h = C.c_void_p()
+        hdr = _buf(header) if header else None
+        aid = _buf(self.api_id) if self.api_id else None
+        rc = self.lib.bbs_issuer_set_create(suite.curve_id, device, self.n_issuers, _ptr(blob), _ptr(_buf(generators)),
+                                            self.n_generators, _ptr(hdr), len(header), _ptr(aid), len(self.api_id),
+                                            _ptr(self.status), C.byref(h))
+        if rc != 0:
+            raise BbsError(f"bbs_issuer_set_create failed ({rc}): {self.lib.bbs_last_error().decode()}")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.bbs_issuer_set_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def memory_bytes(self):
+        """(bytes that grow with the number of issuers, shared bytes: generator tables + batch scratch)"""
+        shared = C.c_uint64()
+        per = self.lib.bbs_issuer_set_memory_bytes(self._h, C.byref(shared))
+        return int(per), int(shared.value)
+
+    def verify_batch(self, item_issuer: Sequence[int], signatures, messages: Sequence[Sequence[bytes]]) -> np.ndarray:
+        """status[i] = `pks[item_issuer[i]].verify(signatures[i], header, messages[i])`"""
+        sigs = _buf(b"".join(signatures) if not isinstance(signatures, (bytes, bytearray, np.ndarray)) else signatures)
+        n = sigs.size // self.suite.signature_bytes
+        if len(messages) != n or len(item_issuer) != n:
+            raise BbsError("one message list and one issuer index per signature required")
+        n_msgs = len(messages[0]) if n else 0
+        if any(len(m) != n_msgs for m in messages):
+            raise BbsError("all items of a batch must carry the same number of messages")
+        flat, offs = _pack_ragged([m for item in messages for m in item])
+        iss = np.ascontiguousarray(np.asarray(item_issuer, dtype=np.uint32))
+        st = np.full(n, 255, dtype=np.uint8)
+        rc = self.lib.bbs_verify_batch_multi(self._h, n, _ptr(iss), _ptr(sigs), _ptr(flat), _ptr(offs), n_msgs, _ptr(st))
+        if rc != 0:
+            raise BbsError(f"bbs_verify_batch_multi failed ({rc}): {self.lib.bbs_last_error().decode()}")
+        return st
+
+    def core_verify_batch(self, item_issuer: Sequence[int], signatures, msg_scalars, n_msgs: int) -> np.ndarray:
+        sigs = _buf(signatures)
+        n = sigs.size // self.suite.signature_bytes
+        sc = _buf(msg_scalars)
+        if sc.size != n * n_msgs * 32 or len(item_issuer) != n:
+            raise BbsError("msg_scalars / item_issuer have the wrong size")
+        if sc.size == 0:
+            sc = np.zeros(1, dtype=np.uint8)
+        iss = np.ascontiguousarray(np.asarray(item_issuer, dtype=np.uint32))
+        st = np.full(n, 255, dtype=np.uint8)
+        rc = self.lib.bbs_core_verify_batch_multi(self._h, n, _ptr(iss), _ptr(sigs), _ptr(sc), n_msgs, _ptr(st))
+        if rc != 0:
+            raise BbsError(f"bbs_core_verify_batch_multi failed ({rc}): {self.lib.bbs_last_error().decode()}")
         return st
 
 

@@ -47,6 +47,7 @@ struct ProfEvents {
 struct Ctx {
     int curve = 0, device = 0;
     uint32_t L = 0;
+    size_t api_id_len = 0, header_len = 0;
     rt_stream_t stream = nullptr;
 #ifndef BBS_HOSTSIM
     cudaStream_t copy_stream = nullptr;        // uploads of the chunked host-buffer paths (rlc): overlap with compute
@@ -66,13 +67,27 @@ struct Ctx {
     DevBuf s_gscr, s_rlc_pt, s_rlc_sc, s_rlc_parts, s_rlc_bad, s_msm_pts, s_msm_kv, s_msm_idx, s_msm_entries, s_msm_buckets;
     DevBuf s_sigs, s_scalars, s_msgs, s_offsets, s_pair, s_flags, s_status, s_out, s_out2;
     DevBuf s_commit, s_commit_off, s_dis_idx, s_dis_scalars, s_dis_off, s_ph, s_dis_msgs, s_dis_msg_off;
-    void release_all() {
+    template <class Fn> void each_buffer(Fn f) {
         DevBuf* all[] = {&pk_comp, &gens_comp, &api_id, &header, &dst_h2s, &dst_map, &gens, &W, &K, &domain, &tab, &wbase,
                          &lines, &lines_coop, &s_rand, &s_rand_off, &s_sk, &s_gscr, &s_rlc_pt, &s_rlc_sc, &s_rlc_parts, &s_rlc_bad, &s_msm_pts, &s_msm_kv, &s_msm_idx, &s_msm_entries, &s_msm_buckets, &misc, &s_sigs, &s_scalars, &s_msgs, &s_offsets, &s_pair, &s_flags, &s_status, &s_out,
                          &s_out2, &s_commit, &s_commit_off, &s_dis_idx, &s_dis_scalars, &s_dis_off, &s_ph, &s_dis_msgs,
                          &s_dis_msg_off};
-        for (DevBuf* b : all) b->release();
+        for (DevBuf* b : all) f(b);
     }
+    void release_all() { each_buffer([](DevBuf* b) { b->release(); }); }
+    size_t bytes() { size_t t = 0; each_buffer([&](DevBuf* b) { t += b->cap; }); return t; }
+};
+
+// Many issuer keys over one generator list (bbs_issuer_set_create): `base` owns everything the issuers share -- decoded
+// generators, the fixed-base tables of H_1..H_L, the BP2 lines, the batch scratch and the stream (its own key is the
+// identity and is never used) -- and the arrays below hold what depends on the key, ~26 KB per issuer on BLS12-381.
+struct IssuerSet {
+    Ctx* base = nullptr;
+    size_t n_issuers = 0;
+    uint32_t line_stride = 0;        // words between two issuers' line tables
+    DevBuf pks, W, K, domains, flags, lines, item_issuer;
+    size_t per_issuer_bytes() const { return pks.cap + W.cap + K.cap + domains.cap + flags.cap + lines.cap; }
+    void release_all() { for (DevBuf* b : {&pks, &W, &K, &domains, &flags, &lines, &item_issuer}) b->release(); }
 };
 
 #define TRY(expr) do { int rc_ = (expr); if (rc_) return rc_; } while (0)
@@ -96,6 +111,7 @@ struct Impl {
                       size_t header_len, const uint8_t* api_id, size_t api_id_len) {
         const uint32_t L = n_gens - 1;
         c->L = L;
+        c->api_id_len = api_id_len; c->header_len = header_len;
         rt_stream_t s = c->stream;
         std::vector<uint8_t> dsth(api_id, api_id + api_id_len), dstm(api_id, api_id + api_id_len);
         const char* h2s = "H2S_";                            // verify.rs / core_utilities.rs:60
@@ -188,35 +204,127 @@ struct Impl {
         return BBS_OK;
     }
 
-    static int pairing_dev(Ctx* c, size_t n, uint8_t* d_status, rt_stream_t s) {
+    // S != nullptr: multi-issuer batch, item i is checked against the lines of issuer d_item_issuer[i] of the set
+    static int pairing_dev(Ctx* c, size_t n, uint8_t* d_status, rt_stream_t s, const IssuerSet* S = nullptr) {
+        const uint32_t* d_issuer = S ? (const uint32_t*)S->item_issuer.p : nullptr;
 #ifndef BBS_HOSTSIM
-        if (c->coop && !c->force_per_thread) {
+        if (S || (c->coop && !c->force_per_thread)) {
             TRY(c->s_gscr.reserve(coop_gscratch_size<C>(n)));
-            CoopArgs ca{(const uint32_t*)c->lines_coop.p, (const uint32_t*)c->s_pair.p, (const uint32_t*)c->s_flags.p,
-                        d_status, (uint32_t*)c->s_gscr.p, (uint32_t)n};
+            CoopArgs ca{(const uint32_t*)(S ? S->lines.p : c->lines_coop.p), (const uint32_t*)c->s_pair.p,
+                        (const uint32_t*)c->s_flags.p, d_status, (uint32_t*)c->s_gscr.p, (uint32_t)n, d_issuer,
+                        S ? S->line_stride : 0u};
             TRY((launch_pairing_coop<C>(ca, s)));
             c->launches += n ? 1 : 0;
             return BBS_OK;
         }
 #endif
-        PairingArgs pa{c->view.lines, (const uint32_t*)c->s_pair.p, (const uint32_t*)c->s_flags.p, d_status};
+        PairingArgs pa{S ? (const uint32_t*)S->lines.p : c->view.lines, (const uint32_t*)c->s_pair.p,
+                       (const uint32_t*)c->s_flags.p, d_status, d_issuer, S ? S->line_stride : 0u};
         TRY((launch_pairing<C>(pa, (uint32_t)n, s)));
         c->launches += n ? 1 : 0;
         return BBS_OK;
     }
 
     static int core_verify_dev(Ctx* c, size_t n, const uint8_t* d_sigs, const uint8_t* d_scalars, uint32_t n_msgs,
-                               uint8_t* d_status, rt_stream_t s) {
+                               uint8_t* d_status, rt_stream_t s, const IssuerSet* S = nullptr) {
         TRY(c->s_pair.reserve(n * 6 * C::Fp::N * 4));
         TRY(c->s_flags.reserve(n * 4));
         VerifyG1Args a{c->view, d_sigs, d_scalars, n_msgs, (uint32_t*)c->s_pair.p, (uint32_t*)c->s_flags.p, d_status};
+        if (S) {
+            a.item_issuer = (const uint32_t*)S->item_issuer.p;
+            a.iss = IssuerSetView{(const uint32_t*)S->K.p, (const uint32_t*)S->flags.p, (const uint32_t*)S->lines.p,
+                                  S->line_stride, (uint32_t)S->n_issuers};
+        }
         PROF(c, 1, s);
         TRY((launch_verify_g1<C>(a, (uint32_t)n, s)));
         c->launches += n ? 1 : 0;
         PROF(c, 2, s);
-        TRY(pairing_dev(c, n, d_status, s));
+        TRY(pairing_dev(c, n, d_status, s, S));
         PROF(c, 3, s);
         return BBS_OK;
+    }
+
+    // ---- issuer sets ------------------------------------------------------------------------------------
+    // per-issuer state for n keys on top of an existing base context: decode + subgroup test, domain and K, the ate walk
+    // of every key (one thread per issuer), normalised for the cooperative kernel
+    static int issuer_set_build(IssuerSet* S, const uint8_t* pks, size_t n, uint8_t* issuer_status) {
+        Ctx* c = S->base;
+        rt_stream_t s = c->stream;
+        constexpr size_t FN = C::Fp::N;
+        const uint32_t n_lines = (uint32_t)ate_line_count<C>();
+        const uint32_t stride = n_lines * 2 * 4 * (uint32_t)FN;          // words per issuer: lines x 2 pairs x (2 Fp2)
+        S->n_issuers = n;
+        S->line_stride = stride;
+        TRY(S->pks.reserve(n * C::G2_BYTES));
+        TRY(S->W.reserve(n * 4 * FN * 4));
+        TRY(S->K.reserve(n * 2 * FN * 4));
+        TRY(S->domains.reserve(n * 32));
+        TRY(S->flags.reserve(n * 4));
+        TRY(S->lines.reserve(n * (size_t)stride * 4));
+        TRY(rt_h2d(S->pks.p, pks, n * C::G2_BYTES, s));
+        IssDecodeArgs da{(const uint8_t*)S->pks.p, (uint32_t*)S->W.p, (uint32_t*)S->flags.p};
+        TRY((launch_iss_decode<C>(da, (uint32_t)n, s)));
+        IssDomainArgs dom{};
+        dom.base = CtxDomainArgs{nullptr, (const uint8_t*)c->gens_comp.p, c->L, (const uint8_t*)c->api_id.p, (uint32_t)c->api_id_len,
+                                 (const uint8_t*)c->header.p, (uint32_t)c->header_len, c->view.dst_h2s, c->view.dst_h2s_len,
+                                 c->view.gens, nullptr, nullptr, nullptr};
+        dom.pks = (const uint8_t*)S->pks.p; dom.domains = (uint32_t*)S->domains.p; dom.K = (uint32_t*)S->K.p;
+        dom.flags = (uint32_t*)S->flags.p;
+        TRY((launch_iss_domain<C>(dom, (uint32_t)n, s)));
+        c->launches += 2;
+        const size_t chunk = std::min<size_t>(n, 4096);
+        DevBuf raw;
+        int rc = raw.reserve(chunk * (size_t)stride * 4);
+        for (size_t first = 0; !rc && first < n; first += chunk) {
+            const uint32_t cnt = (uint32_t)std::min(chunk, n - first);
+            IssLinesArgs la{(const uint32_t*)S->W.p, (const uint32_t*)S->flags.p, (uint32_t*)raw.p, stride, (uint32_t)first};
+            rc = launch_iss_lines<C>(la, cnt, s);
+#ifndef BBS_HOSTSIM
+            IssLinesCoopArgs lc{(const uint32_t*)raw.p, stride, (const uint32_t*)c->lines_coop.p, (uint32_t*)S->lines.p, stride,
+                                (uint32_t*)S->flags.p, (uint32_t)first, n_lines};
+            if (!rc) rc = launch_iss_lines_coop<C>(lc, cnt * 2 * n_lines, s);
+#else
+            // host simulation: the per-thread pairing kernel reads the raw (A, Bc) layout; pair 1 = the base context's BP2 lines
+            for (uint32_t t = 0; t < cnt; t++) {
+                uint32_t* dst = (uint32_t*)S->lines.p + (first + t) * (size_t)stride;
+                const uint32_t* src = (const uint32_t*)raw.p + t * (size_t)stride;
+                const uint32_t* bp2 = (const uint32_t*)c->lines.p;
+                for (uint32_t k = 0; k < n_lines; k++) {
+                    memcpy(dst + (2 * k) * 4 * FN, src + (2 * k) * 4 * FN, 4 * FN * 4);
+                    memcpy(dst + (2 * k + 1) * 4 * FN, bp2 + (2 * k + 1) * 4 * FN, 4 * FN * 4);
+                }
+            }
+#endif
+            c->launches += 2;
+        }
+        if (!rc) rc = rt_sync(s);
+        raw.release();
+        TRY(rc);
+        std::vector<uint32_t> fl(n);
+        TRY(rt_d2h(fl.data(), S->flags.p, n * 4, s));
+        TRY(rt_sync(s));
+        for (size_t i = 0; i < n; i++) issuer_status[i] = (fl[i] & ISS_BAD) ? (uint8_t)ST_ERR_MALFORMED : (uint8_t)ST_ACCEPT;
+        return BBS_OK;
+    }
+    static int verify_multi(IssuerSet* S, size_t n, const uint32_t* item_issuer, const uint8_t* sigs, const uint8_t* scalars,
+                            const uint8_t* msgs, const uint64_t* off, uint32_t n_msgs, uint8_t* status) {
+        Ctx* c = S->base;
+        rt_stream_t s = c->stream;
+        const size_t count = n * n_msgs;
+        TRY(stage(S->item_issuer, item_issuer, n * 4, s));
+        TRY(stage(c->s_sigs, sigs, n * SIG, s));
+        TRY(c->s_status.reserve(n));
+        if (off) {
+            TRY(stage(c->s_msgs, msgs, off[count], s));
+            TRY(stage(c->s_offsets, off, (count + 1) * 8, s));
+            TRY(c->s_scalars.reserve(count * 32));
+            PROF(c, 0, s);
+            TRY(h2s_dev(c, count, (const uint8_t*)c->s_msgs.p, (const uint64_t*)c->s_offsets.p, (uint8_t*)c->s_scalars.p, s));
+        } else {
+            TRY(stage(c->s_scalars, scalars, count * 32, s));
+        }
+        TRY(core_verify_dev(c, n, (const uint8_t*)c->s_sigs.p, (const uint8_t*)c->s_scalars.p, n_msgs, (uint8_t*)c->s_status.p, s, S));
+        return finish_status(c, n, status);
     }
 
     static int verify_dev(Ctx* c, size_t n, const uint8_t* d_sigs, const uint8_t* d_msgs, const uint64_t* d_off,
@@ -853,6 +961,74 @@ int bbs_proof_gen_batch(bbs_ctx* p, size_t n, const uint8_t* sigs, const uint8_t
     if (n_msgs > BBS_MAX_MESSAGES) return arg_error("n_msgs exceeds BBS_MAX_MESSAGES");
     DISPATCH(c, proof_gen(c, n, sigs, msgs, off, n_msgs, idx, dis_off, rand, rand_off, commit_off, ph, ph_len, proofs_out,
                           commitments_out, status));
+}
+
+// ---- issuer sets (multi-issuer batches) -------------------------------------------------------------------
+int bbs_issuer_set_create(int curve, int device, size_t n_issuers, const uint8_t* pks, const uint8_t* generators,
+                          uint32_t n_generators, const uint8_t* header, size_t header_len, const uint8_t* api_id,
+                          size_t api_id_len, uint8_t* issuer_status, bbs_issuer_set** out) {
+    if (!out) return arg_error("out is null");
+    *out = nullptr;
+    if (!n_issuers || !pks || !issuer_status) return arg_error("issuer keys / status missing");
+    if (n_issuers > 0xffffffffull) return arg_error("too many issuers");
+    // the shared part is an ordinary context whose own key is the identity (never used by the multi-issuer calls)
+    uint8_t ident[96] = {0};
+    if (curve == BBS_CURVE_BLS12_381) ident[0] = 0xc0; else ident[63] = 0x40;
+    bbs_ctx* base = nullptr;
+    int rc = bbs_ctx_create(curve, device, ident, generators, n_generators, header, header_len, api_id, api_id_len, &base);
+    if (rc) return rc;
+    IssuerSet* S = new (std::nothrow) IssuerSet();
+    if (!S) { bbs_ctx_destroy(base); return arg_error("out of host memory"); }
+    S->base = as_ctx(base);
+#ifndef BBS_HOSTSIM
+    if (!S->base->coop) rc = arg_error("degenerate BP2 line table");
+#endif
+    if (!rc) rc = curve == BBS_CURVE_BLS12_381 ? Impl<Bls>::issuer_set_build(S, pks, n_issuers, issuer_status)
+                                               : Impl<Bn>::issuer_set_build(S, pks, n_issuers, issuer_status);
+    if (rc) { S->release_all(); bbs_ctx_destroy(base); delete S; return rc; }
+    *out = reinterpret_cast<bbs_issuer_set*>(S);
+    return BBS_OK;
+}
+void bbs_issuer_set_destroy(bbs_issuer_set* p) {
+    IssuerSet* S = reinterpret_cast<IssuerSet*>(p);
+    if (!S) return;
+    rt_set_device(S->base->device);
+    rt_sync(S->base->stream);
+    S->release_all();
+    bbs_ctx_destroy(reinterpret_cast<bbs_ctx*>(S->base));
+    delete S;
+}
+uint64_t bbs_issuer_set_memory_bytes(bbs_issuer_set* p, uint64_t* shared_bytes) {
+    IssuerSet* S = reinterpret_cast<IssuerSet*>(p);
+    if (!S) return 0;
+    if (shared_bytes) *shared_bytes = S->base->bytes() + S->item_issuer.cap;
+    return S->per_issuer_bytes();
+}
+uint64_t bbs_ctx_memory_bytes(bbs_ctx* p) { return p ? as_ctx(p)->bytes() : 0; }
+
+#define DISPATCH_SET(S, call)                                                    \
+    do {                                                                         \
+        if (!(S)) return arg_error("null issuer set");                           \
+        if (rt_set_device((S)->base->device)) return BBS_E_CUDA;                 \
+        if ((S)->base->curve == BBS_CURVE_BLS12_381) return Impl<Bls>::call;     \
+        return Impl<Bn>::call;                                                   \
+    } while (0)
+
+int bbs_verify_batch_multi(bbs_issuer_set* p, size_t n, const uint32_t* item_issuer, const uint8_t* sigs, const uint8_t* msgs,
+                           const uint64_t* off, uint32_t n_msgs, uint8_t* status) {
+    IssuerSet* S = reinterpret_cast<IssuerSet*>(p);
+    if (!n) return BBS_OK;
+    if (!item_issuer || !sigs || !status || !off) return arg_error("null");
+    CHECK_COUNTS(n, n_msgs);
+    DISPATCH_SET(S, verify_multi(S, n, item_issuer, sigs, nullptr, msgs, off, n_msgs, status));
+}
+int bbs_core_verify_batch_multi(bbs_issuer_set* p, size_t n, const uint32_t* item_issuer, const uint8_t* sigs,
+                                const uint8_t* scalars, uint32_t n_msgs, uint8_t* status) {
+    IssuerSet* S = reinterpret_cast<IssuerSet*>(p);
+    if (!n) return BBS_OK;
+    if (!item_issuer || !sigs || !status || (n_msgs && !scalars)) return arg_error("null");
+    CHECK_COUNTS(n, n_msgs);
+    DISPATCH_SET(S, verify_multi(S, n, item_issuer, sigs, scalars, nullptr, nullptr, n_msgs, status));
 }
 
 // ---- random-linear-combination batch mode ----------------------------------------------------------------

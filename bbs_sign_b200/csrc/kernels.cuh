@@ -50,6 +50,8 @@ template <class C> BBS_HD uint32_t tab_digit(const uint32_t* s, int nlimbs, int 
     return (uint32_t)(v >> off) & (uint32_t)TabGeom<C>::ENTRIES;
 }
 constexpr int MAX_L = 256;
+// per-issuer flags of an issuer set (below): identity public key, identity K, unusable key
+enum : uint32_t { ISS_W_INF = 1, ISS_K_INF = 2, ISS_BAD = 4 };
 
 // Read-only per-issuer state living in device memory (built once by bbs_ctx_create)
 struct CtxView {
@@ -147,23 +149,78 @@ template <class C> BBS_HD void ctx_lines_item(const CtxLinesArgs& a, uint32_t i)
 // constant term 1 (any Fp2 factor dies in the final exponentiation).  A == 0 (a tangent / chord through the origin,
 // impossible for an honest key) is reported so that the context falls back to the per-thread kernel.
 struct CtxLinesCoopArgs { const uint32_t* lines; uint32_t* lines2; uint32_t* degenerate; uint32_t w_inf; };
-template <class C> BBS_HD void ctx_lines_coop_item(const CtxLinesCoopArgs& a, uint32_t i) {
-    const uint32_t* src = a.lines + (size_t)i * LINE_WORDS;
-    uint32_t* dst = a.lines2 + ((size_t)(i >> 1) * 4 + (i & 1) * 2) * F2N;
-    if ((i & 1) == 0 && a.w_inf) { bn_zero<4 * C::Fp::N>(dst); return; }
+// one (line, pair) entry: raw (A, Bc) at `src` -> cooperative entry at `dst`; false when the line is degenerate
+template <class C> BBS_HD bool lines_coop_one(uint32_t* dst, const uint32_t* src, bool skip) {
+    if (skip) { bn_zero<4 * C::Fp::N>(dst); return true; }
     if (!C::M_TWIST) {
         // D-type twist (BN254): the constant term of the line is the item's y, so the line is normalised per item
         // (pairing_coop.cuh POINT_RATIO) and the table keeps (Bc, A) as they are: never degenerate
         f2_copy<C>(dst, src + F2N);
         f2_copy<C>(dst + F2N, src);
-        return;
+        return true;
     }
-    if (f2_is_zero<C>(src)) { *a.degenerate = 1; bn_zero<4 * C::Fp::N>(dst); return; }
+    if (f2_is_zero<C>(src)) { bn_zero<4 * C::Fp::N>(dst); return false; }
     BBS_A16 uint32_t ai[F2N], bp[F2N];
     f2_inv_vt<C>(ai, src);
     f2_mul<C>(bp, src + F2N, ai);
     f2_copy<C>(dst, bp);
     f2_copy<C>(dst + F2N, ai);
+    return true;
+}
+template <class C> BBS_HD void ctx_lines_coop_item(const CtxLinesCoopArgs& a, uint32_t i) {
+    const uint32_t* src = a.lines + (size_t)i * LINE_WORDS;
+    uint32_t* dst = a.lines2 + ((size_t)(i >> 1) * 4 + (i & 1) * 2) * F2N;
+    if (!lines_coop_one<C>(dst, src, (i & 1) == 0 && a.w_inf)) *a.degenerate = 1;
+}
+// the same for a chunk of an issuer set: entry t = (issuer, line, pair); pair 1 (BP2) is copied from the shared table
+struct IssLinesCoopArgs {
+    const uint32_t* raw; uint32_t raw_stride; const uint32_t* bp2_coop; uint32_t* coop; uint32_t coop_stride;
+    uint32_t* flags; uint32_t first; uint32_t n_lines;
+};
+template <class C> BBS_HD void iss_lines_coop_item(const IssLinesCoopArgs& a, uint32_t t) {
+    const uint32_t per = 2 * a.n_lines, local = t / per, j = t % per, i = a.first + local;
+    uint32_t* dst = a.coop + (size_t)i * a.coop_stride + ((size_t)(j >> 1) * 4 + (j & 1) * 2) * F2N;
+    if (j & 1) { bn_copy<4 * C::Fp::N>(dst, a.bp2_coop + ((size_t)(j >> 1) * 4 + 2) * F2N); return; }
+    const uint32_t fl = a.flags[i];
+    const uint32_t* src = a.raw + (size_t)local * a.raw_stride + (size_t)j * LINE_WORDS;
+    if (!lines_coop_one<C>(dst, src, (fl & (ISS_BAD | ISS_W_INF)) != 0)) a.flags[i] = fl | ISS_BAD;   // degenerate line: see bbs_b200.h
+}
+
+// ---- issuer sets: many issuer keys over ONE generator list (multi-issuer batches) -------------------
+// `&self` (the public key) is per call in the reference (verify.rs:18-30): a batch may name a different issuer per item.
+// Everything that depends on the key is small -- W (G2), domain, K = P1 + Q1 * domain, the Miller-loop lines of W -- and
+// lives in per-issuer arrays; the fixed-base tables of H_1..H_L depend only on (suite, api_id, L) and are shared.
+struct IssuerSetView {
+    const uint32_t* K;          // n_issuers x affine K_i
+    const uint32_t* flags;      // n_issuers x ISS_*
+    const uint32_t* lines;      // n_issuers x line table, `line_stride` words apart (cooperative layout on the GPU, raw
+                                // (A, Bc) layout in the host simulation)
+    uint32_t line_stride;
+    uint32_t n_issuers;
+};
+
+struct IssDecodeArgs { const uint8_t* pks; uint32_t* W; uint32_t* flags; };
+template <class C> BBS_HD void iss_decode_item(const IssDecodeArgs& a, uint32_t i) {
+    const int st = g2_decompress<C>(a.W + (size_t)i * 4 * C::Fp::N, a.pks + (size_t)i * C::G2_BYTES);
+    a.flags[i] = st == PT_BAD ? (uint32_t)ISS_BAD : (st == PT_INF ? (uint32_t)ISS_W_INF : 0u);
+}
+struct IssDomainArgs { CtxDomainArgs base; const uint8_t* pks; uint32_t* domains; uint32_t* K; uint32_t* flags; };
+template <class C> BBS_HD void iss_domain_item(const IssDomainArgs& a, uint32_t i) {
+    if (a.flags[i] & ISS_BAD) return;
+    CtxDomainArgs d = a.base;
+    uint32_t kinf = 0;
+    d.pk_comp = a.pks + (size_t)i * C::G2_BYTES;
+    d.domain = a.domains + (size_t)i * 8;
+    d.K = a.K + (size_t)i * G1A;
+    d.k_inf = &kinf;
+    ctx_domain_item<C>(d, 0);
+    if (kinf) a.flags[i] |= ISS_K_INF;
+}
+struct IssLinesArgs { const uint32_t* W; const uint32_t* flags; uint32_t* raw; uint32_t raw_stride; uint32_t first; };
+template <class C> BBS_HD void iss_lines_item(const IssLinesArgs& a, uint32_t t) {
+    const uint32_t i = a.first + t;
+    if (a.flags[i] & (ISS_BAD | ISS_W_INF)) return;
+    g2_precompute_lines<C>(a.raw + (size_t)t * a.raw_stride, a.W + (size_t)i * 4 * C::Fp::N, 0);
 }
 
 // ---- msg_to_scalars ----------------------------------------------------------------------------------
@@ -216,18 +273,31 @@ struct VerifyG1Args {
     const uint8_t* scalars;    // n x n_msgs x LE32
     uint32_t n_msgs;
     uint32_t* pair; uint32_t* flags; uint8_t* status;
+    const uint32_t* item_issuer;   // multi-issuer batches: issuer of item i in `iss` (nullptr: the context's own key)
+    IssuerSetView iss;
 };
+// the key-dependent inputs of item i: K and the two identity flags
+template <class C> BBS_HD uint32_t verify_issuer(const VerifyG1Args& a, uint32_t i, const uint32_t*& K) {
+    if (!a.item_issuer) { K = a.ctx.K; return (a.ctx.w_inf ? ISS_W_INF : 0u) | (a.ctx.k_inf ? ISS_K_INF : 0u); }
+    const uint32_t s = a.item_issuer[i];
+    if (s >= a.iss.n_issuers) { K = a.ctx.K; return ISS_BAD; }
+    K = a.iss.K + (size_t)s * G1A;
+    return a.iss.flags[s];
+}
 // Part 1: everything up to the Jacobian point Cc = e A - B.  Returns false when the item's status is already final.
 template <class C> BBS_HD bool verify_g1_head(const VerifyG1Args& a, uint32_t i, uint32_t* Cc, int& pa) {
     const CtxView& cx = a.ctx;
     if (a.n_msgs != cx.L) { a.status[i] = ST_ERR_MSG_GEN_LEN; a.flags[i] = FL_DONE; return false; }   // verify.rs:68-71
+    const uint32_t* Kp;
+    const uint32_t ifl = verify_issuer<C>(a, i, Kp);
+    if (ifl & ISS_BAD) { a.status[i] = ST_ERR_MALFORMED; a.flags[i] = FL_DONE; return false; }        // undecodable issuer key
     const uint8_t* sig = a.sigs + (size_t)i * (C::G1_BYTES + 32);
     BBS_A16 uint32_t A[G1A], e[8];
     pa = g1_decompress<C>(A, sig);
     bool ok = pa != PT_BAD && fr_from_le32<C>(e, sig + C::G1_BYTES);
     // B = P1 + Q1*domain + sum H_j m_j  (verify.rs:81-86), K = P1 + Q1*domain hoisted into the context
     BBS_A16 uint32_t B[G1J];
-    if (cx.k_inf) g1_set_inf<C>(B); else g1_from_affine<C>(B, cx.K);
+    if (ifl & ISS_K_INF) g1_set_inf<C>(B); else g1_from_affine<C>(B, Kp);
     const uint8_t* sc = a.scalars + (size_t)i * a.n_msgs * 32;
     for (uint32_t j = 0; j < a.n_msgs && ok; j++) {
         BBS_A16 uint32_t m[8];
@@ -264,7 +334,8 @@ template <class C> BBS_HD void verify_g1_tail(const VerifyG1Args& a, uint32_t i,
     }
     fe_set_one<F>(pr + 5 * FPN);
     uint32_t fl = 0;
-    if (pa == PT_INF || a.ctx.w_inf) fl |= FL_SKIP0;
+    const uint32_t* Kp;
+    if (pa == PT_INF || (verify_issuer<C>(a, i, Kp) & ISS_W_INF)) fl |= FL_SKIP0;
     if (!cfin) fl |= FL_SKIP1;
     a.flags[i] = fl;
 }
@@ -357,14 +428,18 @@ template <class C, int TPB, int MINB> __global__ void __launch_bounds__(TPB, MIN
 #endif
 
 // ---- pairing half (shared by verify and proof verify) ----------------------------------------------------
-struct PairingArgs { const uint32_t* lines; const uint32_t* pair; const uint32_t* flags; uint8_t* status; };
+struct PairingArgs {
+    const uint32_t* lines; const uint32_t* pair; const uint32_t* flags; uint8_t* status;
+    const uint32_t* item_issuer; uint32_t line_stride;     // multi-issuer: lines + item_issuer[i] * line_stride
+};
 template <class C> BBS_HD void pairing_item(const PairingArgs& a, uint32_t i) {
     uint32_t fl = a.flags[i];
     if (fl & FL_DONE) return;
+    const uint32_t* lines = a.item_issuer ? a.lines + (size_t)a.item_issuer[i] * a.line_stride : a.lines;
     BBS_A16 uint32_t P[PAIR_WORDS], f[F12N];
     const uint32_t* src = a.pair + (size_t)i * PAIR_WORDS;
     for (int j = 0; j < PAIR_WORDS; j++) P[j] = src[j];
-    miller2<C>(f, a.lines, P, (fl & FL_SKIP0) != 0, P + 3 * FPN, (fl & FL_SKIP1) != 0);
+    miller2<C>(f, lines, P, (fl & FL_SKIP0) != 0, P + 3 * FPN, (fl & FL_SKIP1) != 0);
     a.status[i] = final_exp_is_one<C>(f) ? ST_ACCEPT : ST_REJECT;
 }
 

@@ -15,6 +15,10 @@ template <class C> int launch_ctx_domain(const CtxDomainArgs& a, uint32_t n, rt_
 template <class C> int launch_ctx_table(const CtxTableArgs& a, uint32_t n, rt_stream_t s);
 template <class C> int launch_ctx_lines(const CtxLinesArgs& a, uint32_t n, rt_stream_t s);
 template <class C> int launch_ctx_lines_coop(const CtxLinesCoopArgs& a, uint32_t n, rt_stream_t s);
+template <class C> int launch_iss_decode(const IssDecodeArgs& a, uint32_t n, rt_stream_t s);
+template <class C> int launch_iss_domain(const IssDomainArgs& a, uint32_t n, rt_stream_t s);
+template <class C> int launch_iss_lines(const IssLinesArgs& a, uint32_t n, rt_stream_t s);
+template <class C> int launch_iss_lines_coop(const IssLinesCoopArgs& a, uint32_t n, rt_stream_t s);
 int launch_gen_seed(const GenSeedArgs& a, rt_stream_t s);
 template <class C> int launch_gen_point(const GenPointArgs& a, uint32_t n, rt_stream_t s);
 template <class C> int launch_h2s(const H2sArgs& a, uint32_t n, rt_stream_t s);

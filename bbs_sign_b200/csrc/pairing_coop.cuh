@@ -48,6 +48,8 @@ struct CoopArgs {
     uint8_t* status;
     uint32_t* gscratch;        // per block: COOP_ROLES cells
     uint32_t n;
+    const uint32_t* item_issuer;   // MULTI kernel: item i reads the line table at lines + item_issuer[i] * line_stride
+    uint32_t line_stride;
 };
 
 // ---- per-curve bindings of the generated primitives ---------------------------------------------------------
@@ -267,7 +269,9 @@ template <class C> __device__ __forceinline__ void coop_finish2(uint32_t* r0, ui
     for (int i = 0; i < N; i++) { r0[i] = w0[i]; r1[i] = w1[i]; }
 }
 
-template <class C>
+// MULTI: every lane (item) reads the line constants of its own issuer (issuer sets, kernels.cuh); the loads stay 128-bit
+// but are no longer warp-uniform, everything else is identical.
+template <class C, bool MULTI>
 __global__ void __maxnreg__(Coop<C>::MAXREG) pairing_coop_kernel(const CoopArgs a) {
     constexpr int COOP_GROUPS = Coop<C>::GROUPS;
     constexpr int N = Coop<C>::N;
@@ -284,6 +288,8 @@ __global__ void __maxnreg__(Coop<C>::MAXREG) pairing_coop_kernel(const CoopArgs 
     const bool valid = item < a.n;
     const uint32_t fl = valid ? a.flags[item] : (uint32_t)(FL_DONE | FL_SKIP0 | FL_SKIP1);
     uint4* cells = smem + lane;
+    const uint32_t* lines = a.lines;
+    if constexpr (MULTI) lines += (size_t)((valid && !(fl & FL_DONE)) ? a.item_issuer[item] : 0u) * a.line_stride;
 
     // prologue: f = 1 in slot 0 (cells 0..5), P0 -> cell 16, P1 -> cell 17 (x in c0, y in c1)
     {
@@ -338,7 +344,7 @@ __global__ void __maxnreg__(Coop<C>::MAXREG) pairing_coop_kernel(const CoopArgs 
             coop_operand<C, false>(x, cells + ((cur >> 6) & 255) * CELL, (cur >> 14) & 3, (cur >> 16) & 3);
             const uint32_t yc = (cur >> 18) & 255;
             if ((cur >> 30) & 1) {
-                const uint32_t* g = yc >= 128 ? a.lines + ((size_t)line * 4 + (yc - 128)) * (2 * N)
+                const uint32_t* g = yc >= 128 ? lines + ((size_t)line * 4 + (yc - 128)) * (2 * N)
                                               : Coop<C>::consts() + yc * (2 * N);
                 coop_operand<C, true>(y, g, (cur >> 26) & 3, (cur >> 28) & 3);
             } else {

@@ -40,9 +40,26 @@ template int launch_gen_point<Bn>(const GenPointArgs&, uint32_t, rt_stream_t);
 template <class C> int launch_ctx_lines_coop(const CtxLinesCoopArgs& a, uint32_t n, rt_stream_t s) {
     return rt_launch<CtxLinesCoopArgs, &ctx_lines_coop_item<C>, 32>(a, n, s);
 }
+// issuer sets (kernels.cuh): one thread per issuer, resp. per (issuer, line, pair)
+template <class C> int launch_iss_decode(const IssDecodeArgs& a, uint32_t n, rt_stream_t s) {
+    return rt_launch<IssDecodeArgs, &iss_decode_item<C>, 32>(a, n, s);
+}
+template <class C> int launch_iss_domain(const IssDomainArgs& a, uint32_t n, rt_stream_t s) {
+    return rt_launch<IssDomainArgs, &iss_domain_item<C>, 32>(a, n, s);
+}
+template <class C> int launch_iss_lines(const IssLinesArgs& a, uint32_t n, rt_stream_t s) {
+    return rt_launch<IssLinesArgs, &iss_lines_item<C>, 32>(a, n, s);
+}
+template <class C> int launch_iss_lines_coop(const IssLinesCoopArgs& a, uint32_t n, rt_stream_t s) {
+    return rt_launch<IssLinesCoopArgs, &iss_lines_coop_item<C>, 64>(a, n, s);
+}
 
 #if defined(BBS_TU_BLS) || !defined(BBS_TU_BN)
 template int launch_ctx_lines_coop<Bls>(const CtxLinesCoopArgs&, uint32_t, rt_stream_t);
+template int launch_iss_decode<Bls>(const IssDecodeArgs&, uint32_t, rt_stream_t);
+template int launch_iss_domain<Bls>(const IssDomainArgs&, uint32_t, rt_stream_t);
+template int launch_iss_lines<Bls>(const IssLinesArgs&, uint32_t, rt_stream_t);
+template int launch_iss_lines_coop<Bls>(const IssLinesCoopArgs&, uint32_t, rt_stream_t);
 template int launch_ctx_decode<Bls>(const CtxDecodeArgs&, uint32_t, rt_stream_t);
 template int launch_ctx_domain<Bls>(const CtxDomainArgs&, uint32_t, rt_stream_t);
 template int launch_ctx_table<Bls>(const CtxTableArgs&, uint32_t, rt_stream_t);
@@ -50,6 +67,10 @@ template int launch_ctx_lines<Bls>(const CtxLinesArgs&, uint32_t, rt_stream_t);
 #endif
 #if defined(BBS_TU_BN) || !defined(BBS_TU_BLS)
 template int launch_ctx_lines_coop<Bn>(const CtxLinesCoopArgs&, uint32_t, rt_stream_t);
+template int launch_iss_decode<Bn>(const IssDecodeArgs&, uint32_t, rt_stream_t);
+template int launch_iss_domain<Bn>(const IssDomainArgs&, uint32_t, rt_stream_t);
+template int launch_iss_lines<Bn>(const IssLinesArgs&, uint32_t, rt_stream_t);
+template int launch_iss_lines_coop<Bn>(const IssLinesCoopArgs&, uint32_t, rt_stream_t);
 template int launch_ctx_decode<Bn>(const CtxDecodeArgs&, uint32_t, rt_stream_t);
 template int launch_ctx_domain<Bn>(const CtxDomainArgs&, uint32_t, rt_stream_t);
 template int launch_ctx_table<Bn>(const CtxTableArgs&, uint32_t, rt_stream_t);

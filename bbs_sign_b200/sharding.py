@@ -9,7 +9,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .api import BatchContext, Ciphersuite
+from .api import BatchContext, Ciphersuite, IssuerSet
 
 
 def shard_bounds(n: int, world: int) -> List[Tuple[int, int]]:
@@ -105,60 +105,35 @@ class ShardedVerifier:
 
 
 class MultiIssuerVerifier:
-    """Batches with a public key PER ITEM ("multi-issuer batches").  Everything that is per issuer in
-    the reference call -- `self.pk`, the generators, `calculate_domain` (verify.rs:53-79) -- lives in a BatchContext; this
-    helper keeps one context per distinct key (built on first use, spread round-robin over `devices`), groups the items
-    of a batch by key, runs every group through its context on its own host thread and scatters the statuses back to the
-    callers' order.  Per item the result is exactly `PublicKey::verify` under that item's key."""
+    """Batches with a public key PER ITEM ("multi-issuer batches") on top of `api.IssuerSet`
+    (`bbs_issuer_set_create` / `bbs_verify_batch_multi`): the distinct keys of a batch are registered once (the generator
+    tables are shared, a key costs ~26 KB), items carry an index into the set, one call verifies the whole mixed batch.
+    Per item the result is exactly `PublicKey::verify` under that item's key (verify.rs:18-30).  A new key rebuilds the
+    set (all keys are processed in parallel on the GPU, one thread per key)."""
 
-    def __init__(self, suite: Ciphersuite, header: bytes, n_messages: int, devices: Sequence[int] = (0,),
-                 lib_path: Optional[str] = None):
+    def __init__(self, suite: Ciphersuite, header: bytes, n_messages: int, device: int = 0, lib_path: Optional[str] = None):
         self.suite, self.header, self.n_messages = suite, header, n_messages
-        self.devices, self.lib_path = list(devices), lib_path
-        self.ctxs: dict = {}
+        self.device, self.lib_path = device, lib_path
+        self.index: dict = {}
+        self.keys: list = []
+        self.set: Optional[IssuerSet] = None
 
-    def context(self, pk: bytes) -> BatchContext:
-        pk = bytes(pk)
-        if pk not in self.ctxs:
-            dev = self.devices[len(self.ctxs) % len(self.devices)]
-            self.ctxs[pk] = BatchContext(self.suite, pk, self.header, self.n_messages, device=dev, lib_path=self.lib_path)
-        return self.ctxs[pk]
-
-    def _grouped(self, pks: Sequence[bytes], run) -> np.ndarray:
-        n = len(pks)
-        out = np.full(n, 255, dtype=np.uint8)
-        groups: dict = {}
-        for i, pk in enumerate(pks):
-            groups.setdefault(bytes(pk), []).append(i)
-        ctxs = {pk: self.context(pk) for pk in groups}          # built before the threads start
-        errs: list = []
-
-        def work(pk, idx):
-            try:
-                out[np.asarray(idx)] = run(ctxs[pk], idx)
-            except Exception as e:  # pragma: no cover
-                errs.append(e)
-
-        ts = [threading.Thread(target=work, args=(pk, idx)) for pk, idx in groups.items()]
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
-        if errs:
-            raise errs[0]
-        return out
+    def _ensure(self, pks: Sequence[bytes]):
+        new = [bytes(pk) for pk in dict.fromkeys(bytes(pk) for pk in pks) if bytes(pk) not in self.index]
+        if new or self.set is None:
+            for pk in new:
+                self.index[pk] = len(self.keys)
+                self.keys.append(pk)
+            if self.set is not None:
+                self.set.close()
+            self.set = IssuerSet(self.suite, self.keys, self.header, self.n_messages, device=self.device, lib_path=self.lib_path)
 
     def verify_batch(self, pks: Sequence[bytes], signatures: Sequence[bytes], messages: Sequence[Sequence[bytes]]) -> np.ndarray:
         """status[i] = verify of signatures[i] over messages[i] under pks[i] (compressed G2)"""
-        return self._grouped(pks, lambda ctx, idx: ctx.verify_batch(b"".join(bytes(signatures[i]) for i in idx),
-                                                                   [messages[i] for i in idx]))
-
-    def proof_verify_batch(self, pks: Sequence[bytes], proofs, ph: bytes, disclosed_messages, disclosed_indexes) -> np.ndarray:
-        return self._grouped(pks, lambda ctx, idx: ctx.proof_verify_batch([proofs[i] for i in idx], ph,
-                                                                         [disclosed_messages[i] for i in idx],
-                                                                         [disclosed_indexes[i] for i in idx]))
+        self._ensure(pks)
+        return self.set.verify_batch([self.index[bytes(pk)] for pk in pks], b"".join(bytes(x) for x in signatures), messages)
 
     def close(self):
-        for c in self.ctxs.values():
-            c.close()
-        self.ctxs = {}
+        if self.set is not None:
+            self.set.close()
+            self.set = None

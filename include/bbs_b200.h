@@ -42,6 +42,7 @@ extern "C" {
 #endif
 
 typedef struct bbs_ctx bbs_ctx;
+typedef struct bbs_issuer_set bbs_issuer_set;
 
 /* curve_id: the reference's type parameter E (with its C / H / F companions) */
 #define BBS_CURVE_BLS12_381 1 /* Bls12_381 + Bls12381Const + HashToG1Bls12381  (src/constants.rs:63-89) */
@@ -174,6 +175,31 @@ int bbs_proof_gen_batch(bbs_ctx* ctx, size_t n, const uint8_t* sigs, const uint8
                         const uint8_t* ph, size_t ph_len, uint8_t* proofs_fixed_out, uint8_t* commitments_out,
                         uint8_t* status);
 
+/* ---- multi-issuer batches ---------------------------------------------------------------------------------
+ * In the reference the public key is `&self` of every call (src/verify.rs:18-30), so a stream of signatures may name a
+ * different issuer per item.  An issuer set holds n_issuers keys over ONE generator list / header / api_id: what depends
+ * only on (suite, api_id, L) -- the decoded generators and their fixed-base tables -- is built once and shared; per key
+ * it keeps W, calculate_domain (src/utils/core_utilities.rs:24-63), K = P1 + Q1 * domain and the Miller-loop lines of W:
+ * about 26 KB (BLS12-381) / 17 KB (BN254) per issuer instead of a whole context, so tens of thousands of issuers fit.
+ *   pks           : n_issuers x compressed G2
+ *   issuer_status : n_issuers bytes out: ACCEPT = key usable, ERR_MALFORMED = what ark `PublicKey::deserialize_compressed`
+ *                   refuses (bad flags, not on the twist, not in the subgroup) -- every item naming such an issuer gets
+ *                   ERR_MALFORMED.  (A key whose ate walk meets a line through the origin, probability ~2^-380, is
+ *                   reported the same way; verify such a key through its own bbs_ctx_create context.)
+ * bbs_verify_batch_multi / bbs_core_verify_batch_multi: item i is `pks[item_issuer[i]].verify(..)` /
+ * `.core_verify(..)`; everything else as bbs_verify_batch / bbs_core_verify_batch (item_issuer[i] >= n_issuers gives
+ * ERR_MALFORMED).  bbs_issuer_set_memory_bytes returns the bytes that grow with the number of issuers and, in
+ * *shared_bytes, the shared part. */
+int bbs_issuer_set_create(int curve_id, int device, size_t n_issuers, const uint8_t* pks, const uint8_t* generators,
+                          uint32_t n_generators, const uint8_t* header, size_t header_len, const uint8_t* api_id,
+                          size_t api_id_len, uint8_t* issuer_status, bbs_issuer_set** out);
+void bbs_issuer_set_destroy(bbs_issuer_set* set);
+uint64_t bbs_issuer_set_memory_bytes(bbs_issuer_set* set, uint64_t* shared_bytes);
+int bbs_verify_batch_multi(bbs_issuer_set* set, size_t n, const uint32_t* item_issuer, const uint8_t* sigs,
+                           const uint8_t* msgs, const uint64_t* offsets, uint32_t n_msgs, uint8_t* status);
+int bbs_core_verify_batch_multi(bbs_issuer_set* set, size_t n, const uint32_t* item_issuer, const uint8_t* sigs,
+                                const uint8_t* msg_scalars, uint32_t n_msgs, uint8_t* status);
+
 /* ---- random-linear-combination batch mode (the optional mode of the north star; not in the reference) ----------
  * One verdict for n signatures under the context's issuer key:
  *     e( sum r_i A_i , W ) * e( sum r_i (e_i A_i - B_i) , BP2 ) == 1,   B_i as in src/verify.rs:81-86,
@@ -218,6 +244,8 @@ int bbs_core_proof_verify_batch_dev(bbs_ctx* ctx, size_t n, const uint8_t* d_pro
 
 /* Number of kernels the library has launched on this context since creation (for bench accounting). */
 uint64_t bbs_ctx_launch_count(bbs_ctx* ctx);
+/* Device memory the context holds (tables, key state and the grow-only batch scratch), bytes. */
+uint64_t bbs_ctx_memory_bytes(bbs_ctx* ctx);
 
 /* ---- test hooks (CUDA kernels either way; results are identical) ---------------------------------------
  * bbs_ctx_use_per_thread_pairing: run the pairing check with the one-thread-per-item kernel that a context with a

@@ -36,6 +36,11 @@ use crate::{
 pub struct BbsCtx {
     _p: [u8; 0],
 }
+/// Opaque `bbs_issuer_set` of include/bbs_b200.h.
+#[repr(C)]
+pub struct BbsIssuerSet {
+    _p: [u8; 0],
+}
 
 // Every symbol include/bbs_b200.h declares, in the header's order.
 extern "C" {
@@ -72,8 +77,15 @@ extern "C" {
                            disclosed_idx: *const u32, dis_off: *const u64, random_scalars: *const u8, rand_off: *const u64,
                            commit_off: *const u64, ph: *const u8, ph_len: usize, proofs_fixed_out: *mut u8,
                            commitments_out: *mut u8, status: *mut u8) -> i32;
-    fn bbs_verify_batch_multi(n_ctx: usize, ctxs: *const *mut BbsCtx, n: usize, item_ctx: *const u32, sigs: *const u8,
-                              msgs: *const u8, offsets: *const u64, n_msgs: u32, status: *mut u8) -> i32;
+    fn bbs_issuer_set_create(curve_id: i32, device: i32, n_issuers: usize, pks: *const u8, generators: *const u8,
+                             n_generators: u32, header: *const u8, header_len: usize, api_id: *const u8, api_id_len: usize,
+                             issuer_status: *mut u8, out: *mut *mut BbsIssuerSet) -> i32;
+    fn bbs_issuer_set_destroy(set: *mut BbsIssuerSet);
+    fn bbs_issuer_set_memory_bytes(set: *mut BbsIssuerSet, shared_bytes: *mut u64) -> u64;
+    fn bbs_verify_batch_multi(set: *mut BbsIssuerSet, n: usize, item_issuer: *const u32, sigs: *const u8, msgs: *const u8,
+                              offsets: *const u64, n_msgs: u32, status: *mut u8) -> i32;
+    fn bbs_core_verify_batch_multi(set: *mut BbsIssuerSet, n: usize, item_issuer: *const u32, sigs: *const u8,
+                                   msg_scalars: *const u8, n_msgs: u32, status: *mut u8) -> i32;
     fn bbs_rlc_partial_core(ctx: *mut BbsCtx, n: usize, sigs: *const u8, msg_scalars: *const u8, n_msgs: u32, seed: *const u8,
                             index_base: u64, parts_out: *mut u8, status: *mut u8) -> i32;
     fn bbs_rlc_partial(ctx: *mut BbsCtx, n: usize, sigs: *const u8, msgs: *const u8, offsets: *const u64, n_msgs: u32,
@@ -453,25 +465,70 @@ pub fn proof_gen_batch<E: Pairing, F: Field + FromOkm<48, F>>(ctx: &BatchCtx, si
         .collect())
 }
 
-/// Batches whose items name different issuers: `ctxs[item_ctx[i]]` is the context (issuer key) of item i; all contexts
-/// share the curve, the device and the message count.  Per item the result is `PublicKey::verify` under that item's key
-/// (`&self` is per call in the reference, src/verify.rs:18-30).
-pub fn verify_batch_multi<E: Pairing, F: Field>(ctxs: &[&BatchCtx], item_ctx: &[u32], sigs: &[Signature<E, F>],
-    messages: &[&[&[u8]]]) -> Result<Vec<Result<bool, ItemError<SignatureError>>>, BatchError> {
-    assert!(item_ctx.len() == sigs.len() && messages.len() == sigs.len());
-    let l = uniform_len(messages)?;
-    let raws: Vec<*mut BbsCtx> = ctxs.iter().map(|c| c.raw).collect();
-    let mut sb = Vec::new();
-    for s in sigs {
-        ser(s, &mut sb);
+/// Many issuer keys over one generator list / header (`bbs_issuer_set_create`): the key is `&self` of every call in the
+/// reference (src/verify.rs:18-30), so a batch may name a different issuer per item.  The generator tables are shared;
+/// a key costs ~26 KB on BLS12-381.
+pub struct IssuerSet {
+    raw: *mut BbsIssuerSet,
+    /// per key: `true` = usable, `false` = refused like `PublicKey::deserialize_compressed` would (items naming it come
+    /// back `ItemError::Malformed`)
+    pub usable: Vec<bool>,
+}
+unsafe impl Send for IssuerSet {}
+impl Drop for IssuerSet {
+    fn drop(&mut self) {
+        unsafe { bbs_issuer_set_destroy(self.raw) }
     }
-    let (flat, offs) = pack(messages);
-    let mut st = vec![0u8; sigs.len()];
-    check(unsafe {
-        bbs_verify_batch_multi(raws.len(), raws.as_ptr(), sigs.len(), item_ctx.as_ptr(), sb.as_ptr(), flat.as_ptr(), offs.as_ptr(),
-                               l as u32, st.as_mut_ptr())
-    })?;
-    Ok(st.into_iter().map(signature_status).collect())
+}
+
+impl IssuerSet {
+    pub fn new<E, H, C>(pks: &[PublicKey<E>], header: &[u8], l: usize, device: i32) -> Result<Self, BatchError>
+    where
+        E: Pairing,
+        H: HashToG1<E>,
+        C: for<'a> Constants<'a, E> + CurveId,
+    {
+        let api_id = [C::CIPHERSUITE_ID, b"H2G_HM2S_"].concat();
+        let (mut keys, mut gens) = (Vec::new(), Vec::new());
+        for pk in pks {
+            ser(&pk.pk, &mut keys);
+        }
+        for g in create_generators::<E, H>(l + 1, &api_id) {
+            ser(&g, &mut gens);
+        }
+        let mut st = vec![0u8; pks.len()];
+        let mut raw = std::ptr::null_mut();
+        check(unsafe {
+            bbs_issuer_set_create(C::ID, device, pks.len(), keys.as_ptr(), gens.as_ptr(), (l + 1) as u32, header.as_ptr(),
+                                  header.len(), api_id.as_ptr(), api_id.len(), st.as_mut_ptr(), &mut raw)
+        })?;
+        Ok(IssuerSet { raw, usable: st.into_iter().map(|s| s == ST_ACCEPT).collect() })
+    }
+
+    /// `result[i]` is what `pks[item_issuer[i]].verify(sigs[i], header, messages[i])` returns.
+    pub fn verify_batch<E: Pairing, F: Field>(&self, item_issuer: &[u32], sigs: &[Signature<E, F>], messages: &[&[&[u8]]])
+        -> Result<Vec<Result<bool, ItemError<SignatureError>>>, BatchError> {
+        assert!(item_issuer.len() == sigs.len() && messages.len() == sigs.len());
+        let l = uniform_len(messages)?;
+        let mut sb = Vec::new();
+        for s in sigs {
+            ser(s, &mut sb);
+        }
+        let (flat, offs) = pack(messages);
+        let mut st = vec![0u8; sigs.len()];
+        check(unsafe {
+            bbs_verify_batch_multi(self.raw, sigs.len(), item_issuer.as_ptr(), sb.as_ptr(), flat.as_ptr(), offs.as_ptr(), l as u32,
+                                   st.as_mut_ptr())
+        })?;
+        Ok(st.into_iter().map(signature_status).collect())
+    }
+
+    /// (bytes that grow with the number of issuers, shared bytes)
+    pub fn memory_bytes(&self) -> (u64, u64) {
+        let mut shared = 0u64;
+        let per = unsafe { bbs_issuer_set_memory_bytes(self.raw, &mut shared) };
+        (per, shared)
+    }
 }
 
 /// Optional random-linear-combination mode (not in the reference): ONE verdict for the whole batch, wrong with probability
@@ -509,7 +566,7 @@ fn _unused_bindings() {
         bbs_core_proof_gen_batch as usize, bbs_rlc_partial_core as usize, bbs_rlc_partial as usize, bbs_rlc_combine as usize,
         bbs_rlc_core_verify_batch as usize, bbs_msg_to_scalars_dev as usize, bbs_core_verify_batch_dev as usize,
         bbs_verify_batch_dev as usize, bbs_core_sign_batch_dev as usize, bbs_core_proof_verify_batch_dev as usize,
-        bbs_ctx_launch_count as usize, bbs_ctx_memory_bytes as usize, bbs_ctx_use_per_thread_pairing as usize,
+        bbs_ctx_launch_count as usize, bbs_ctx_memory_bytes as usize, bbs_core_verify_batch_multi as usize, bbs_ctx_use_per_thread_pairing as usize,
         bbs_ctx_set_rlc_windows as usize, bbs_ctx_set_profiling as usize, bbs_ctx_kernel_times as usize, bbs_imad_peak as usize,
         bbs_selftest_field as usize, bbs_selftest_g1_mul as usize, bbs_selftest_pairing as usize,
     );

@@ -699,3 +699,58 @@ def case_subgroup(lib_path, curve_name):
         assert ctx.rlc_verify_batch(enc, msgs, seed) == A.ST_ERR_MALFORMED
         assert ctx.rlc_verify_batch([enc[0], enc[2]], [msgs[0], msgs[2]], seed) == A.ST_ERR_MALFORMED
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+def case_multi_issuer(lib_path, curve_name, n_issuers=5, per_issuer=3, L=2):
+    """bbs_issuer_set_create / bbs_verify_batch_multi: items of one batch name different issuer keys (the key is `&self` of
+    every call in the reference, verify.rs:18-30).  Each status must equal the oracle's verify under the item's claimed key:
+    own-issuer signatures, a signature checked under another issuer's key, a forged e, the identity key, an off-subgroup
+    key (refused at creation, its items come back malformed), an out-of-range issuer index."""
+    suite, ocs = SUITES[curve_name]
+    header = b"multi"
+    keys = [keypair(ocs, 10 + k) for k in range(n_issuers)]
+    pks = [ocs.g2_compress(pk) for _, pk in keys]
+    bad_key = ocs.g2_compress(off_subgroup_g2(ocs))
+    ident = ocs.g2_compress(None)
+    all_pks = pks + [bad_key, ident]
+    gens = O.create_generators_cached(ocs, L + 1, ocs.api_id)
+    iset = A.IssuerSet(suite, all_pks, header, generators=gens_bytes(ocs, gens), lib_path=lib_path)
+    assert iset.status.tolist() == [1] * n_issuers + [A.ST_ERR_MALFORMED, 1]
+    per, shared = iset.memory_bytes()
+    assert 0 < per < 64 * 1024 * len(all_pks) and shared > 0
+    items = []            # (issuer index, signature, messages, expected)
+    for k in range(n_issuers):
+        sk, pk = keys[k]
+        for t in range(per_issuer):
+            m = [rng_bytes(f"mi{k}.{t}.{j}", 32) for j in range(L)]
+            sig = O.sign(ocs, sk, m, header)
+            claimed = k
+            if t == 1 and k % 2 == 0:
+                claimed = (k + 1) % n_issuers                         # verified under another issuer's key
+            if t == 2 and k % 3 == 0:
+                sig = (sig[0], (sig[1] + 1) % ocs.r)                  # forged
+            csk, cpk = keys[claimed]
+            use_pairing = (k == 0 and t < 2)                          # a few items with the pairing oracle, the rest by trapdoor
+            want = int(O.verify(ocs, cpk, sig, header, m, trapdoor_sk=None if use_pairing else csk))
+            items.append((claimed, sig, m, want))
+    sk0, _ = keys[0]
+    m = [rng_bytes(f"mi-x.{j}", 32) for j in range(L)]
+    sig = O.sign(ocs, sk0, m, header)
+    items.append((n_issuers, sig, m, A.ST_ERR_MALFORMED))                   # the off-subgroup key
+    items.append((n_issuers + 1, sig, m, int(O.verify(ocs, None, sig, header, m))))   # identity key: Ok(false)
+    items.append((n_issuers + 2, sig, m, A.ST_ERR_MALFORMED))               # no such issuer
+    random.Random(3).shuffle(items)
+    enc = b"".join(O.signature_to_bytes(ocs, it[1]) for it in items)
+    got = iset.verify_batch([it[0] for it in items], enc, [it[2] for it in items])
+    assert got.tolist() == [it[3] for it in items], (curve_name, got.tolist(), [it[3] for it in items])
+    sc = b"".join(ocs.scalar_le(x) for it in items for x in O.msg_to_scalars(ocs, it[2], ocs.api_id))
+    got2 = iset.core_verify_batch([it[0] for it in items], np.frombuffer(enc, dtype=np.uint8), np.frombuffer(sc, dtype=np.uint8), L)
+    assert got2.tolist() == got.tolist()
+    # per key, the set's domain-dependent state equals a dedicated context's: same verdicts through bbs_ctx_create
+    ctx, _ = make_ctx(lib_path, suite, ocs, keys[1][1], header, L, gens=gens)
+    mine = [it for it in items if it[0] == 1]
+    one = ctx.verify_batch(np.frombuffer(b"".join(O.signature_to_bytes(ocs, it[1]) for it in mine), dtype=np.uint8), [it[2] for it in mine])
+    assert one.tolist() == [it[3] for it in mine]
+    ctx.close()
+    iset.close()

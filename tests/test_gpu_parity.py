@@ -147,8 +147,9 @@ def test_create_generators(lib, curve):
 
 
 def test_multi_issuer_batch(lib):
-    """per-item public keys: three issuers interleaved in one batch, one wrong-issuer item, one forged
-    signature; every status equals the oracle's verify under that item's key"""
+    """per-item public keys through the MultiIssuerVerifier helper (api.IssuerSet underneath): three issuers
+    interleaved in one batch, one wrong-issuer item, one forged signature; every status equals the oracle's verify under
+    that item's key"""
     from bbs_sign_b200.sharding import MultiIssuerVerifier
     from oracle import bbs_oracle as O
     suite, ocs = P.SUITES["BLS12_381"]
@@ -168,8 +169,83 @@ def test_multi_issuer_batch(lib):
             for i in range(n)]
     assert O.verify(ocs, keys[claimed[4]][1], sigs[4], b"mi", msgs[4]) is False        # and once with the pairing oracle
     assert got.tolist() == want == [1, 1, 1, 1, 0, 1, 1, 0, 1]
-    assert len(mv.ctxs) == 3
+    assert len(mv.keys) == 3
     mv.close()
+
+
+def test_multi_issuer_1024_issuers(lib):
+    """1,024 issuers x 4 items in one mixed batch: keys sk_k * BP2 and signatures from the GPU signer under
+    per-issuer contexts would need 1,024 contexts, so items are signed by the ORACLE-free trapdoor construction instead:
+    A = B * (sk_k + e)^-1 needs B, which the single-issuer GPU signer provides (b_out) under a context for that key's
+    domain.  Cheaper and independent: sign on the GPU under 8 real contexts, register those 8 keys 128 times each at
+    different set positions (a key is what it is wherever it sits), interleave, corrupt a known subset, and compare
+    with (a) the construction and (b) the oracle's trapdoor verify on a sample.  Memory per issuer and the throughput
+    relative to the single-issuer path are printed."""
+    import time
+    import numpy as np
+    import bench
+    from bbs_sign_b200 import api as A
+    from oracle import bbs_oracle as O
+    suite, ocs = P.SUITES["BLS12_381"]
+    L, n_keys, copies, per = 10, 8, 128, 4
+    header = b""
+    keys = [P.keypair(ocs, 40 + k) for k in range(n_keys)]
+    pkb = [ocs.g2_compress(pk) for _, pk in keys]
+    n_issuers = n_keys * copies
+    set_pks = [pkb[s % n_keys] for s in range(n_issuers)]
+    rng = np.random.default_rng(8)
+    n = n_issuers * per
+    msgs = rng.integers(0, 256, size=(n, L, 32), dtype=np.uint8)
+    issuer = np.repeat(np.arange(n_issuers, dtype=np.uint32), per)
+    rng.shuffle(issuer)
+    sigs = np.zeros((n, 80), dtype=np.uint8)
+    for k in range(n_keys):
+        ctx = A.BatchContext(suite, pkb[k], header, n_messages=L)
+        sel = np.nonzero(issuer % n_keys == k)[0]
+        s_k, _, st = ctx.sign_batch(ocs.scalar_le(keys[k][0]), [[bytes(msgs[i, j]) for j in range(L)] for i in sel])
+        assert (st == 1).all()
+        sigs[sel] = s_k
+        ctx.close()
+    expect = np.ones(n, dtype=np.uint8)
+    claimed = issuer.copy()
+    for t, i in enumerate(range(7, n, 16)):
+        if t % 2 == 0:
+            claimed[i] = (issuer[i] + 1) % n_issuers          # another issuer's key (a different secret: +1 mod 8)
+        else:
+            sigs[i, 48] ^= 1
+        expect[i] = 0
+    t0 = time.perf_counter()
+    iset = A.IssuerSet(suite, set_pks, header, n_messages=L)
+    t_create = time.perf_counter() - t0
+    assert (iset.status == 1).all()
+    per_b, shared_b = iset.memory_bytes()
+    msg_lists = [[bytes(msgs[i, j]) for j in range(L)] for i in range(n)]
+    got = iset.verify_batch(claimed, sigs.reshape(-1), msg_lists)
+    assert np.array_equal(got, expect), int((got != expect).sum())
+    t0 = time.perf_counter()
+    got = iset.verify_batch(claimed, sigs.reshape(-1), msg_lists)
+    t_multi = time.perf_counter() - t0
+    # oracle (trapdoor) on a sample, valid and corrupted
+    gens = O.create_generators_cached(ocs, L + 1, ocs.api_id)
+    for i in [7, 23, 39, 55, 0, 1, 1000, n - 1]:
+        sk_c, pk_c = keys[int(claimed[i]) % n_keys]
+        sig = (ocs.g1_decompress(bytes(sigs[i, :48])), int.from_bytes(bytes(sigs[i, 48:]), "little"))
+        assert bool(got[i]) == O.verify(ocs, pk_c, sig, header, msg_lists[i], trapdoor_sk=sk_c), i
+    # the same number of items under ONE issuer through the single-issuer path
+    ctx = A.BatchContext(suite, pkb[0], header, n_messages=L)
+    s_1, _, _ = ctx.sign_batch(ocs.scalar_le(keys[0][0]), msg_lists)
+    ctx.verify_batch(s_1.reshape(-1), msg_lists)
+    t0 = time.perf_counter()
+    one = ctx.verify_batch(s_1.reshape(-1), msg_lists)
+    t_single = time.perf_counter() - t0
+    assert (one == 1).all()
+    ctx_bytes = ctx.memory_bytes()
+    ctx.close()
+    iset.close()
+    print(f"\nmulti-issuer: {n_issuers} issuers x {per} items: set creation {t_create * 1e3:.0f} ms, {per_b / n_issuers / 1024:.1f} KiB per issuer "
+          f"(+ {shared_b / 2**20:.0f} MiB shared) vs {ctx_bytes / 2**20:.0f} MiB for one single-issuer context; "
+          f"verify {n} items: {t_multi * 1e3:.1f} ms multi-issuer vs {t_single * 1e3:.1f} ms single-issuer (host-buffer calls, Python packing included)")
+    assert per_b / n_issuers < 64 * 1024
 
 
 @pytest.mark.parametrize("curve", ["BN254", "BLS12_381"])
@@ -193,3 +269,8 @@ def test_per_thread_pairing_kernel(lib, curve):
     the cooperative kernel and the oracle on valid items and every rejection class"""
     P.case_verify(None, curve, 3, n=12, use_pairing_oracle_on=1, per_thread_pairing=True)
     P.case_proof_verify(None, curve, 4, [0, 2], n=8, pairing_on=1, per_thread_pairing=True)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_multi_issuer_set(lib, curve):
+    P.case_multi_issuer(None, curve)

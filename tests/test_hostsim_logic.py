@@ -100,3 +100,8 @@ def test_g1_mul_edges(lib, curve):
 @pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
 def test_subgroup_validation(lib_path, curve):
     P.case_subgroup(lib_path, curve)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_multi_issuer_set(lib_path, curve):
+    P.case_multi_issuer(lib_path, curve)

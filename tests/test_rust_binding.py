@@ -27,7 +27,7 @@ def c_prototypes():
         types = []
         if params and params != "void":
             for p in params.split(","):
-                p = re.sub(r"\[[^\]]*\]", "*", p.strip())                     # array parameter = pointer
+                p = re.sub(r"(\w+)\s*\[[^\]]*\]", r"* \1", p.strip())             # array parameter = pointer
                 p = re.sub(r"\s*\*\s*", "* ", p)
                 toks = p.split()
                 if len(toks) > 1 and not toks[-1].endswith("*"):
