@@ -26,6 +26,8 @@ SYMBOLS = {
     "bbs_create_generators": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]),
     "bbs_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t,
                                  C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "bbs_ctx_create_ex": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t,
+                                    C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "bbs_ctx_destroy": (None, [C.c_void_p]),
     "bbs_ctx_domain": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bbs_ctx_launch_count": (C.c_uint64, [C.c_void_p]),

@@ -29,6 +29,7 @@ from . import _native
 
 ST_REJECT, ST_ACCEPT, ST_ERR_MSG_GEN_LEN, ST_ERR_DISCLOSED_INDEX, ST_ERR_IDX_MSG_LEN, ST_ERR_MALFORMED = range(6)
 ST_ERR_DISCLOSED_LEN, ST_ERR_RANDOM_LEN = 6, 7
+CTX_SMALL_TABLES = 1          # BBS_CTX_SMALL_TABLES (bbs_ctx_create_ex)
 
 
 
@@ -100,7 +101,7 @@ class BatchContext:
 
     def __init__(self, suite: Ciphersuite, pk: bytes, header: bytes = b"", n_messages: Optional[int] = None,
                  generators: Optional[bytes] = None, api_id: Optional[bytes] = None, device: int = 0,
-                 lib_path: Optional[str] = None):
+                 lib_path: Optional[str] = None, small_tables: bool = False):
         self.suite = suite
         self.lib = _native.load(lib_path)
         if generators is None:
@@ -119,8 +120,9 @@ class BatchContext:
         h = C.c_void_p()
         hdr = _buf(header) if header else None
         aid = _buf(self.api_id) if self.api_id else None
-        rc = self.lib.bbs_ctx_create(suite.curve_id, device, _ptr(_buf(self.pk)), _ptr(_buf(generators)),
-                                     self.n_generators, _ptr(hdr), len(header), _ptr(aid), len(self.api_id), C.byref(h))
+        rc = self.lib.bbs_ctx_create_ex(suite.curve_id, device, CTX_SMALL_TABLES if small_tables else 0, _ptr(_buf(self.pk)),
+                                        _ptr(_buf(generators)), self.n_generators, _ptr(hdr), len(header), _ptr(aid),
+                                        len(self.api_id), C.byref(h))
         if rc != 0:
             raise BbsError(f"bbs_ctx_create failed ({rc}): {self.lib.bbs_last_error().decode()}")
         self._h = h

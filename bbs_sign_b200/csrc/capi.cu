@@ -108,7 +108,8 @@ struct Impl {
     static constexpr size_t PROOF = 3 * C::G1_BYTES + 128;
 
     static int create(Ctx* c, const uint8_t* pk, const uint8_t* gens, uint32_t n_gens, const uint8_t* header,
-                      size_t header_len, const uint8_t* api_id, size_t api_id_len) {
+                      size_t header_len, const uint8_t* api_id, size_t api_id_len, uint32_t flags) {
+        const TabGeom G((flags & BBS_CTX_SMALL_TABLES) ? (uint32_t)TAB_BITS_SMALL : (uint32_t)BBS_TAB_BITS_GLV);
         const uint32_t L = n_gens - 1;
         c->L = L;
         c->api_id_len = api_id_len; c->header_len = header_len;
@@ -130,7 +131,7 @@ struct Impl {
         TRY(c->K.reserve(2 * C::Fp::N * 4));
         TRY(c->domain.reserve(32));
         TRY(c->misc.reserve((n_gens + 2) * 4));
-        const size_t tab_entries = (size_t)(L + 1) * TabGeom<C>::WINDOWS * TabGeom<C>::ENTRIES;
+        const size_t tab_entries = (size_t)(L + 1) * G.windows * G.entries;
         TRY(c->tab.reserve(tab_entries * 2 * C::Fp::N * 4));
         const int n_lines = ate_line_count<C>();
         TRY(c->lines.reserve((size_t)n_lines * 2 * 4 * C::Fp::N * 4));
@@ -164,8 +165,9 @@ struct Impl {
         TRY(rt_d2h(&k_inf, d_kinf, 4, s));
         TRY(rt_sync(s));
         // 3. window tables, 4. line tables
-        TRY(c->wbase.reserve((size_t)(L + 1) * TabGeom<C>::WINDOWS * 2 * C::Fp::N * 4));
-        CtxTableArgs ta{(const uint32_t*)c->K.p, (const uint32_t*)c->gens.p, (uint32_t*)c->tab.p, (uint32_t*)c->wbase.p};
+        TRY(c->wbase.reserve((size_t)(L + 1) * G.windows * 2 * C::Fp::N * 4));
+        CtxTableArgs ta{(const uint32_t*)c->K.p, (const uint32_t*)c->gens.p, (uint32_t*)c->tab.p, (uint32_t*)c->wbase.p,
+                        (uint32_t)G.bits};
         TRY((launch_ctx_table<C>(ta, L + 1, s)));
         CtxLinesArgs la{(const uint32_t*)c->W.p, w_inf, (uint32_t*)c->lines.p};
         TRY((launch_ctx_lines<C>(la, 2, s)));
@@ -188,7 +190,7 @@ struct Impl {
         }
 #endif
         CtxView& v = c->view;
-        v.L = L; v.w_inf = w_inf; v.k_inf = k_inf;
+        v.L = L; v.w_inf = w_inf; v.k_inf = k_inf; v.tab_bits = (uint32_t)G.bits;
         v.dst_h2s = (const uint8_t*)c->dst_h2s.p; v.dst_h2s_len = (uint32_t)dsth.size();
         v.dst_map = (const uint8_t*)c->dst_map.p; v.dst_map_len = (uint32_t)dstm.size();
         v.gens = (const uint32_t*)c->gens.p; v.W = (const uint32_t*)c->W.p; v.K = (const uint32_t*)c->K.p;
@@ -789,11 +791,12 @@ int bbs_create_generators(int curve, int device, const uint8_t* api_id, size_t a
     return rc;
 }
 
-int bbs_ctx_create(int curve, int device, const uint8_t* pk, const uint8_t* generators, uint32_t n_generators,
-                   const uint8_t* header, size_t header_len, const uint8_t* api_id, size_t api_id_len, bbs_ctx** out) {
+int bbs_ctx_create_ex(int curve, int device, uint32_t flags, const uint8_t* pk, const uint8_t* generators, uint32_t n_generators,
+                      const uint8_t* header, size_t header_len, const uint8_t* api_id, size_t api_id_len, bbs_ctx** out) {
     if (!out) return arg_error("out is null");
     *out = nullptr;
     if (curve != BBS_CURVE_BLS12_381 && curve != BBS_CURVE_BN254) return arg_error("unknown curve id");
+    if (flags & ~(uint32_t)BBS_CTX_SMALL_TABLES) return arg_error("unknown context flag");
     if (!pk || !generators || n_generators < 1) return arg_error("pk / generators missing");
     if (n_generators - 1 > BBS_MAX_MESSAGES) return arg_error("too many generators");
     if ((header_len && !header) || (api_id_len && !api_id)) return arg_error("null header / api_id");
@@ -804,12 +807,16 @@ int bbs_ctx_create(int curve, int device, const uint8_t* pk, const uint8_t* gene
     int rc = rt_stream_create(&c->stream);
     if (!rc) {
         rc = curve == BBS_CURVE_BLS12_381
-                 ? Impl<Bls>::create(c, pk, generators, n_generators, header, header_len, api_id, api_id_len)
-                 : Impl<Bn>::create(c, pk, generators, n_generators, header, header_len, api_id, api_id_len);
+                 ? Impl<Bls>::create(c, pk, generators, n_generators, header, header_len, api_id, api_id_len, flags)
+                 : Impl<Bn>::create(c, pk, generators, n_generators, header, header_len, api_id, api_id_len, flags);
     }
     if (rc) { c->release_all(); rt_stream_destroy(c->stream); delete c; return rc; }
     *out = reinterpret_cast<bbs_ctx*>(c);
     return BBS_OK;
+}
+int bbs_ctx_create(int curve, int device, const uint8_t* pk, const uint8_t* generators, uint32_t n_generators,
+                   const uint8_t* header, size_t header_len, const uint8_t* api_id, size_t api_id_len, bbs_ctx** out) {
+    return bbs_ctx_create_ex(curve, device, 0, pk, generators, n_generators, header, header_len, api_id, api_id_len, out);
 }
 
 void bbs_ctx_destroy(bbs_ctx* p) {

@@ -31,6 +31,9 @@ enum : uint8_t {
 //   table (phi of an entry is (beta x, y): one extra multiplication), so 16-bit windows need only 8 windows: 16 mixed
 //   additions per generator from a 50 MB (BLS12-381) / 34 MB (BN254) table per generator, 96- / 64-byte gathers from HBM.
 //   The host simulation (tests only) builds its tables on CPU cores and uses 8-bit windows.
+//   A context may instead be built with SMALL tables (bbs_ctx_create_ex, BBS_CTX_SMALL_TABLES): 8-bit windows, 16 windows,
+//   32 additions per generator from a 390 KB (BLS12-381) table per generator that stays resident in L2 -- 128 x less memory
+//   and table-building work, for roughly twice the fixed-base additions.
 #ifndef BBS_TAB_BITS_GLV
 #ifdef BBS_HOSTSIM
 #define BBS_TAB_BITS_GLV 8
@@ -38,16 +41,18 @@ enum : uint8_t {
 #define BBS_TAB_BITS_GLV 16
 #endif
 #endif
-template <class C> struct TabGeom {
-    static constexpr int BITS = BBS_TAB_BITS_GLV;
-    static constexpr int WINDOWS = (128 + BITS - 1) / BITS;
-    static constexpr int ENTRIES = (1 << BITS) - 1;
+constexpr int TAB_BITS_SMALL = 8;
+// geometry of a context's tables for a window width chosen at creation
+struct TabGeom {
+    int bits, windows;
+    uint32_t entries;
+    BBS_HD explicit TabGeom(uint32_t b) : bits((int)b), windows((128 + (int)b - 1) / (int)b), entries((1u << b) - 1u) {}
 };
-template <class C> BBS_HD uint32_t tab_digit(const uint32_t* s, int nlimbs, int w) {      // s: canonical limbs
-    const int bit = w * TabGeom<C>::BITS, word = bit >> 5, off = bit & 31;
+BBS_HD uint32_t tab_digit(const TabGeom& G, const uint32_t* s, int nlimbs, int w) {      // s: canonical limbs
+    const int bit = w * G.bits, word = bit >> 5, off = bit & 31;
     uint64_t v = s[word];
     if (word + 1 < nlimbs) v |= (uint64_t)s[word + 1] << 32;
-    return (uint32_t)(v >> off) & (uint32_t)TabGeom<C>::ENTRIES;
+    return (uint32_t)(v >> off) & G.entries;
 }
 constexpr int MAX_L = 256;
 // per-issuer flags of an issuer set (below): identity public key, identity K, unusable key
@@ -58,6 +63,7 @@ struct CtxView {
     uint32_t L;               // message generators H_1..H_L
     uint32_t w_inf;           // public key is the identity
     uint32_t k_inf;           // K = P1 + Q1*domain is the identity
+    uint32_t tab_bits;        // window width of `tab` (16, or 8 for small tables)
     uint32_t dst_h2s_len, dst_map_len;
     const uint8_t* dst_h2s;   // api_id || "H2S_"
     const uint8_t* dst_map;   // api_id || "MAP_MSG_TO_SCALAR_AS_HASH_"
@@ -106,13 +112,14 @@ template <class C> BBS_HD void ctx_domain_item(const CtxDomainArgs& a, uint32_t)
     *a.k_inf = g1_to_affine_vt<C>(a.K, acc) ? 0u : 1u;
 }
 
-struct CtxTableArgs { const uint32_t* K; const uint32_t* gens; uint32_t* tab; uint32_t* wbase; };
+struct CtxTableArgs { const uint32_t* K; const uint32_t* gens; uint32_t* tab; uint32_t* wbase; uint32_t tab_bits; };
 // entry (g, w, d) = (d * 2^(BITS w)) * base_g in affine form, in two steps:
 //   ctx_wbase_item: the window bases 2^(BITS w) * base_g, affine (one thread per (g, w); a K at infinity gives zeros);
 //   ctx_table_item: d * window base by a BITS-bit double-and-add, then to affine.
 template <class C> BBS_HD void ctx_wbase_item(const CtxTableArgs& a, uint32_t i) {
-    constexpr uint32_t TAB_WINDOWS = TabGeom<C>::WINDOWS;
-    constexpr int TAB_BITS = TabGeom<C>::BITS;
+    const TabGeom G(a.tab_bits);
+    const uint32_t TAB_WINDOWS = (uint32_t)G.windows;
+    const int TAB_BITS = G.bits;
     const uint32_t w = i % TAB_WINDOWS, g = i / TAB_WINDOWS;
     const uint32_t* base = g == 0 ? a.K : a.gens + g * G1A;
     BBS_A16 uint32_t acc[G1J];
@@ -123,8 +130,9 @@ template <class C> BBS_HD void ctx_wbase_item(const CtxTableArgs& a, uint32_t i)
 }
 // Jacobian d * window base for table entry i; false when the base is the identity
 template <class C> BBS_HD bool ctx_table_head(uint32_t* acc, const CtxTableArgs& a, uint32_t i) {
-    constexpr uint32_t TAB_ENTRIES = TabGeom<C>::ENTRIES;
-    constexpr int TAB_BITS = TabGeom<C>::BITS;
+    const TabGeom G(a.tab_bits);
+    const uint32_t TAB_ENTRIES = G.entries;
+    const int TAB_BITS = G.bits;
     const uint32_t d = i % TAB_ENTRIES + 1;
     const uint32_t* wb = a.wbase + (size_t)(i / TAB_ENTRIES) * G1A;      // (g, w) = i / ENTRIES
     if (bn_is_zero<2 * C::Fp::N>(wb)) { g1_set_inf<C>(acc); return false; }
@@ -238,22 +246,22 @@ template <class C> BBS_HD void h2s_item(const H2sArgs& a, uint32_t t) {
 
 // ---- fixed-base MSM over the window tables -------------------------------------------------------------
 // acc += s * base_g, s canonical limbs (8)
-template <class C> BBS_HDN void tab_accumulate(uint32_t* acc, const uint32_t* tab, uint32_t g, const uint32_t* s) {
-    using G = TabGeom<C>;
-    const uint32_t* tg = tab + (size_t)g * G::WINDOWS * G::ENTRIES * G1A;
+template <class C> BBS_HDN void tab_accumulate(uint32_t* acc, const CtxView& cx, uint32_t g, const uint32_t* s) {
+    const TabGeom G(cx.tab_bits);
+    const uint32_t* tg = cx.tab + (size_t)g * G.windows * G.entries * G1A;
     BBS_A16 uint32_t k1[5], k2[5];
     glv_split<C>(k1, k2, s);
-    for (int w = 0; w < G::WINDOWS; w++) {
-        uint32_t d1 = tab_digit<C>(k1, 5, w), d2 = tab_digit<C>(k2, 5, w);
+    for (int w = 0; w < G.windows; w++) {
+        uint32_t d1 = tab_digit(G, k1, 5, w), d2 = tab_digit(G, k2, 5, w);
         if (d1) {
             BBS_A16 uint32_t e[G1A];
-            const uint32_t* src = tg + ((size_t)w * G::ENTRIES + (d1 - 1)) * G1A;
+            const uint32_t* src = tg + ((size_t)w * G.entries + (d1 - 1)) * G1A;
             bn_copy<2 * C::Fp::N>(e, src);                               // 96- / 64-byte gather as 128-bit loads
             g1_add_mixed<C>(acc, acc, e);
         }
         if (d2) {
             BBS_A16 uint32_t e[G1A], t[FPN];
-            const uint32_t* src = tg + ((size_t)w * G::ENTRIES + (d2 - 1)) * G1A;
+            const uint32_t* src = tg + ((size_t)w * G.entries + (d2 - 1)) * G1A;
             bn_copy<2 * C::Fp::N>(e, src);
             fe_mul<typename C::Fp>(t, e, C::GLV_BETA());            // phi(x, y) = (beta x, y)
             bn_copy<C::Fp::N>(e, t);
@@ -302,7 +310,7 @@ template <class C> BBS_HD bool verify_g1_head(const VerifyG1Args& a, uint32_t i,
     for (uint32_t j = 0; j < a.n_msgs && ok; j++) {
         BBS_A16 uint32_t m[8];
         ok = fr_from_le32<C>(m, sc + j * 32);
-        if (ok) tab_accumulate<C>(B, cx.tab, j + 1, m);
+        if (ok) tab_accumulate<C>(B, cx, j + 1, m);
     }
     if (!ok) { a.status[i] = ST_ERR_MALFORMED; a.flags[i] = FL_DONE; return false; }
     // e(A, W + e BP2) e(B, -BP2) == 1  <=>  e(A, W) e(eA - B, BP2) == 1   (SURVEY 8a note (i))
@@ -474,7 +482,7 @@ template <class C> BBS_HD bool sign_head(const SignArgs& a, uint32_t i, uint32_t
         ok = fr_from_le32<C>(m, sc + j * 32);
         if (!ok) break;
         for (int k = 7; k >= 0; k--) x.s.update_words(&m[k], 1);
-        tab_accumulate<C>(B, cx.tab, j + 1, m);                                      // sign.rs:120-126
+        tab_accumulate<C>(B, cx, j + 1, m);                                      // sign.rs:120-126
     }
     if (!ok) { a.status[i] = ST_ERR_MALFORMED; return false; }
     for (int k = 7; k >= 0; k--) x.s.update_words(&cx.domain[k], 1);
@@ -616,12 +624,12 @@ template <class C> BBS_HD void proof_g1_item(const ProofG1Args& a, uint32_t i) {
     BBS_A16 uint32_t cm[8];
     fe_to_mont<Fr>(cm, c);
     g1_set_inf<C>(T2);
-    if (!cx.k_inf) tab_accumulate<C>(T2, cx.tab, 0, c);
+    if (!cx.k_inf) tab_accumulate<C>(T2, cx, 0, c);
     for (uint64_t k = 0; k < R; k++) {
         BBS_A16 uint32_t m[8];
         if (!fr_from_le32<C>(m, a.dis_scalars + (db + k) * 32)) PROOF_FAIL(ST_ERR_MALFORMED)
         fe_mul<Fr>(m, m, cm);                                   // c * m_k, canonical
-        tab_accumulate<C>(T2, cx.tab, a.dis_idx[db + k] + 1, m);
+        tab_accumulate<C>(T2, cx, a.dis_idx[db + k] + 1, m);
     }
     {
         uint64_t k = 0;
@@ -629,7 +637,7 @@ template <class C> BBS_HD void proof_g1_item(const ProofG1Args& a, uint32_t i) {
             if ((mask[j >> 5] >> (j & 31)) & 1) continue;
             BBS_A16 uint32_t m[8];
             if (!fr_from_le32<C>(m, a.commitments + (cb + k) * 32)) PROOF_FAIL(ST_ERR_MALFORMED)
-            tab_accumulate<C>(T2, cx.tab, j + 1, m);
+            tab_accumulate<C>(T2, cx, j + 1, m);
             k++;
         }
     }
@@ -735,7 +743,7 @@ template <class C> BBS_HD void proof_gen_item(const ProofGenArgs& a, uint32_t i)
     for (uint32_t j = 0; j < (uint32_t)L; j++) {
         BBS_A16 uint32_t m[8];
         if (!fr_from_le32<C>(m, sc + j * 32)) GEN_FAIL(ST_ERR_MALFORMED)
-        tab_accumulate<C>(B, cx.tab, j + 1, m);
+        tab_accumulate<C>(B, cx, j + 1, m);
     }
     // D = B r1 ; Abar = A (r0 r1)   (:254-255)
     BBS_A16 uint32_t r0m[8], r01[8], Baff[G1A], Dj[G1J], Abj[G1J];
@@ -775,7 +783,7 @@ template <class C> BBS_HD void proof_gen_item(const ProofGenArgs& a, uint32_t i)
             if ((mask[j >> 5] >> (j & 31)) & 1) continue;
             BBS_A16 uint32_t m[8];
             if (!fr_from_le32<C>(m, a.rand + (rb + 5 + k) * 32)) GEN_FAIL(ST_ERR_MALFORMED)
-            tab_accumulate<C>(T2, cx.tab, j + 1, m);
+            tab_accumulate<C>(T2, cx, j + 1, m);
             k++;
         }
     }

@@ -271,7 +271,7 @@ template <class C> __global__ void __launch_bounds__(RLC_TPB, 1) rlc_msm_finish_
         }
     } else if (job == 3) {
         for (uint32_t j = lane; j <= a.n_msgs; j += 32)
-            if (!(j == 0 && cx.k_inf)) tab_accumulate<C>(acc, cx.tab, j, sums[j]);
+            if (!(j == 0 && cx.k_inf)) tab_accumulate<C>(acc, cx, j, sums[j]);
         g1_copy<C>(sf[lane], acc);                           // warp 3 only
         __syncwarp();
         for (int st = 16; st >= 1; st >>= 1) {

@@ -11,7 +11,8 @@ template <class C> int launch_ctx_domain(const CtxDomainArgs& a, uint32_t n, rt_
     return rt_launch<CtxDomainArgs, &ctx_domain_item<C>, 32>(a, n, s);
 }
 template <class C> int launch_ctx_table(const CtxTableArgs& a, uint32_t n_generators, rt_stream_t s) {
-    const uint32_t n_bases = n_generators * TabGeom<C>::WINDOWS, n = n_bases * TabGeom<C>::ENTRIES;
+    const TabGeom G(a.tab_bits);
+    const uint32_t n_bases = n_generators * (uint32_t)G.windows, n = n_bases * G.entries;
     int rc = rt_launch<CtxTableArgs, &ctx_wbase_item<C>, 32>(a, n_bases, s);
     if (rc) return rc;
 #ifdef BBS_HOSTSIM

@@ -1,5 +1,6 @@
 // Translation unit for the `sign` kernels (see launchers.cuh).  Built once per curve: -DBBS_TU_BLS / -DBBS_TU_BN;
 // with neither macro both curves are instantiated (host-simulation build).
+#define BBS_NO_DEDICATED_SQR      // see field.cuh FeSqr: this unit's kernels are faster with one multiplication body
 #include "launchers.cuh"
 
 // occupancy knobs (threads per block, min resident blocks per SM -> register cap); -D overridable

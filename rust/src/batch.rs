@@ -53,6 +53,8 @@ extern "C" {
     fn bbs_create_generators(curve_id: i32, device: i32, api_id: *const u8, api_id_len: usize, count: u32, out: *mut u8) -> i32;
     fn bbs_ctx_create(curve_id: i32, device: i32, pk: *const u8, generators: *const u8, n_generators: u32, header: *const u8,
                       header_len: usize, api_id: *const u8, api_id_len: usize, out: *mut *mut BbsCtx) -> i32;
+    fn bbs_ctx_create_ex(curve_id: i32, device: i32, flags: u32, pk: *const u8, generators: *const u8, n_generators: u32,
+                         header: *const u8, header_len: usize, api_id: *const u8, api_id_len: usize, out: *mut *mut BbsCtx) -> i32;
     fn bbs_ctx_destroy(ctx: *mut BbsCtx);
     fn bbs_ctx_domain(ctx: *mut BbsCtx, out_le32: *mut u8) -> i32;
     fn bbs_msg_to_scalars(ctx: *mut BbsCtx, count: usize, msgs: *const u8, offsets: *const u64, out: *mut u8) -> i32;
@@ -561,7 +563,7 @@ pub fn assert_cuda_build() {
 #[allow(dead_code)]
 fn _unused_bindings() {
     let _ = (
-        bbs_g1_bytes as usize, bbs_g2_bytes as usize, bbs_create_generators as usize, bbs_msg_to_scalars as usize,
+        bbs_g1_bytes as usize, bbs_g2_bytes as usize, bbs_ctx_create_ex as usize, bbs_create_generators as usize, bbs_msg_to_scalars as usize,
         bbs_core_verify_batch as usize, bbs_core_sign_batch as usize, bbs_core_proof_verify_batch as usize,
         bbs_core_proof_gen_batch as usize, bbs_rlc_partial_core as usize, bbs_rlc_partial as usize, bbs_rlc_combine as usize,
         bbs_rlc_core_verify_batch as usize, bbs_msg_to_scalars_dev as usize, bbs_core_verify_batch_dev as usize,

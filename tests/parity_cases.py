@@ -48,12 +48,15 @@ def gens_bytes(ocs, gens):
     return b"".join(ocs.g1_compress(g) for g in gens)
 
 
+SMALL_TABLES = False      # test_small_tables flips this: every context of a case is then built with BBS_CTX_SMALL_TABLES
+
+
 def make_ctx(lib_path, suite, ocs, pk, header, L, api_id=None, gens=None):
     api_id = ocs.api_id if api_id is None else api_id
     if gens is None:
         gens = O.create_generators_cached(ocs, L + 1, api_id)
     return A.BatchContext(suite, ocs.g2_compress(pk), header, generators=gens_bytes(ocs, gens), api_id=api_id,
-                          lib_path=lib_path), gens
+                          lib_path=lib_path, small_tables=SMALL_TABLES), gens
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -274,3 +274,13 @@ def test_per_thread_pairing_kernel(lib, curve):
 @pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
 def test_multi_issuer_set(lib, curve):
     P.case_multi_issuer(None, curve)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_small_tables(lib, curve, monkeypatch):
+    """contexts built with BBS_CTX_SMALL_TABLES (8-bit windows, L2-resident tables) give byte-identical signatures, B points,
+    proofs and verdicts"""
+    monkeypatch.setattr(P, "SMALL_TABLES", True)
+    P.case_verify(None, curve, 3, n=6, use_pairing_oracle_on=1)
+    P.case_proof_gen(None, curve, 3, [0, 2], n=3)
+    P.case_proof_verify(None, curve, 4, [0, 2], n=8, pairing_on=0)

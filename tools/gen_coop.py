@@ -401,7 +401,7 @@ def arr(mapping):
         for prefix, expr in mapping:
             if v.startswith(prefix) and v[len(prefix):].isdigit():
                 return expr % int(v[len(prefix):])
-        if v in ("m", "cy", "x0", "x1", "ext"):
+        if v in ("m", "cy", "cz", "x0", "x1", "ext"):
             return v
         raise KeyError(v)
     return f
