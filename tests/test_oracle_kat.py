@@ -111,3 +111,89 @@ def test_bn254_roundtrip_readme_example():  # README.md:64-92 (BASELINE config 1
     # encodings round-trip
     assert BN.g1_decompress(BN.g1_compress(sig[0])) == sig[0]
     assert BN.g2_decompress(BN.g2_compress(pk)) == pk
+
+
+def test_subgroup_tests_are_sound():
+    """The device decides subgroup membership with endomorphism identities (g1.cuh g1_in_subgroup, g2.cuh g2_in_subgroup)
+    instead of the definition [r]P == O the oracle uses.  Their sufficiency rests on number facts checked here:
+      G1 (BLS12-381): phi^2 + phi + 1 = 0 and [x^2]P == -phi^2(P)  =>  (x^4 - x^2 + 1) P = r P = O;
+      G2: psi^2 - tr psi + p = 0 and psi(Q) == [k]Q  =>  ord(Q) | gcd(k^2 - tr k + p, #E'(Fp2)), which must be r
+          for k = x (BLS12-381) and k = 6 t^2 (BN254);
+    and the identities themselves are evaluated with the oracle's arithmetic on subgroup and non-subgroup points."""
+    import math
+    import random
+    from oracle.bbs_oracle import ec_add, ec_mul, ec_neg
+    rnd = random.Random(5)
+    # ---- BLS12-381
+    cs = BLS
+    p, r, F1, F2 = cs.p, cs.r, cs.F1, cs.F2
+    x = -0xD201000000010000
+    assert r == x ** 4 - x ** 2 + 1
+    beta = 0x1a0111ea397fe699ec02408663d4de85aa0d857d89759ad4897d29650fb85f9b409427eb4f49fffd8bfd00000000aaac
+    assert pow(beta, 3, p) == 1 and beta != 1
+    h1 = (x - 1) ** 2 // 3
+
+    def on_curve_pt():
+        while True:
+            xx = rnd.randrange(p)
+            rhs = (xx ** 3 + 4) % p
+            yy = pow(rhs, (p + 1) // 4, p)
+            if yy * yy % p == rhs:
+                return (xx, yy)
+
+    def g1_test(P):
+        Q = ec_mul(F1, ec_mul(F1, P, abs(x)), abs(x))
+        return Q is not None and Q[0] == (-(beta * P[0] + P[0])) % p and Q[1] == (-P[1]) % p      # (beta^2 x, -y)
+
+    for _ in range(3):
+        raw = on_curve_pt()
+        assert g1_test(ec_mul(F1, raw, h1)) and cs.g1_in_subgroup(ec_mul(F1, raw, h1))
+        assert g1_test(raw) == cs.g1_in_subgroup(raw) == False
+    assert not g1_test((0, 2))                                                   # order 3
+    tr = x + 1
+    n2 = p * p + 1 - (tr * tr - 2 * p)                                            # #E(Fp2); the sextic twist has p^2 + 1 - t' points
+    h2 = 0x5d543a95414e7f1091d50792876a202cd91de4547085abaa68a205b2e5a7ddfa628f1cb4d9e82ef21537e293a6691ae1616ec6e786f0c70cf1c38e31c7238e5
+    assert math.gcd(x * x - tr * x + p, h2 * r) == r
+    xi = (1, 1)
+
+    def f2pow(F, a, e):
+        out = (1, 0)
+        while e:
+            if e & 1:
+                out = F.mul(out, a)
+            a = F.mul(a, a)
+            e >>= 1
+        return out
+
+    conj = lambda a, q: (a[0], (-a[1]) % q)
+    gx, gy = f2pow(F2, xi, (p - 1) // 3), f2pow(F2, xi, (p - 1) // 2)
+    psi_m = lambda Q: (F2.mul(conj(Q[0], p), F2.inv(gx)), F2.mul(conj(Q[1], p), F2.inv(gy)))
+    g2_test_bls = lambda Q: ec_mul(F2, Q, abs(x)) == ec_neg(F2, psi_m(Q))
+    assert g2_test_bls(cs.BP2) and g2_test_bls(ec_mul(F2, cs.BP2, 0x1234567890abcdef))
+
+    def twist_pt(suite):
+        F = suite.F2
+        while True:
+            X = (rnd.randrange(suite.p), rnd.randrange(suite.p))
+            y = F.sqrt(F.add(F.mul(F.mul(X, X), X), suite.b2))
+            if y is not None:
+                return (X, y)
+
+    Q = twist_pt(cs)
+    assert ec_mul(F2, Q, h2 * r) is None and not g2_test_bls(Q) and not cs.g2_in_subgroup(Q)
+    assert g2_test_bls(ec_mul(F2, Q, h2))
+    # ---- BN254
+    bn = BN
+    t = 4965661367192848881
+    pb, rb, G2 = bn.p, bn.r, bn.F2
+    trb = 6 * t * t + 1
+    n2b = rb * (2 * pb - rb)
+    k = 6 * t * t
+    assert math.gcd(k * k - trb * k + pb, n2b) == rb
+    gxb, gyb = f2pow(G2, (9, 1), (pb - 1) // 3), f2pow(G2, (9, 1), (pb - 1) // 2)
+    psi_d = lambda Q: (G2.mul(conj(Q[0], pb), gxb), G2.mul(conj(Q[1], pb), gyb))
+    g2_test_bn = lambda Q: ec_mul(G2, Q, k) == psi_d(Q)
+    assert g2_test_bn(bn.BP2) and g2_test_bn(ec_mul(G2, bn.BP2, 0xfedcba987654321))
+    Q = twist_pt(bn)
+    assert ec_mul(G2, Q, n2b) is None and not g2_test_bn(Q) and not bn.g2_in_subgroup(Q)
+    assert g2_test_bn(ec_mul(G2, Q, 2 * pb - rb))
