@@ -30,23 +30,27 @@ template <class C> BBS_HD void g1_neg(uint32_t* r, const uint32_t* p) {
     bn_copy<C::Fp::N>(r, p); fe_neg<typename C::Fp>(r + FPN, p + FPN); bn_copy<C::Fp::N>(r + 2 * FPN, p + 2 * FPN);
 }
 
+// The three group operations write their result in place and keep as few temporaries as the formulas allow: every
+// temporary is a 48- / 32-byte array in the thread's local memory, and the hot set of those arrays (x 512 resident
+// threads per SM) is what decides the L1 hit rate of the per-thread kernels (profiles/summary_r02.md).  r may alias p
+// (the accumulator pattern acc = acc + q); r never aliases q.
+
 // dbl-2009-l: 2M + 5S
 template <class C> BBS_HDN void g1_dbl(uint32_t* r, const uint32_t* p) {
     using F = typename C::Fp;
     const uint32_t *X = p, *Y = p + FPN, *Z = p + 2 * FPN;
-    BBS_A16 uint32_t A[FPN], B[FPN], Cc[FPN], D[FPN], E[FPN], Fq[FPN], t[FPN], Z3[FPN];
+    BBS_A16 uint32_t A[FPN], B[FPN], Cc[FPN], D[FPN], Fq[FPN];
     fe_sqr<F>(A, X);
     fe_sqr<F>(B, Y);
     fe_sqr<F>(Cc, B);
-    fe_add<F>(t, X, B); fe_sqr<F>(t, t); fe_sub<F>(t, t, A); fe_sub<F>(t, t, Cc); fe_dbl<F>(D, t);
-    fe_dbl<F>(E, A); fe_add<F>(E, E, A);
-    fe_sqr<F>(Fq, E);
-    fe_mul<F>(Z3, Y, Z); fe_dbl<F>(Z3, Z3);
-    fe_dbl<F>(t, D); fe_sub<F>(r, Fq, t);                       // X3 = F - 2D
-    fe_sub<F>(t, D, r); fe_mul<F>(t, E, t);
+    fe_add<F>(D, X, B); fe_sqr<F>(D, D); fe_sub<F>(D, D, A); fe_sub<F>(D, D, Cc); fe_dbl<F>(D, D);   // D = 2((X+B)^2 - A - C)
+    fe_dbl<F>(B, A); fe_add<F>(A, B, A);                        // E = 3A (in A)
+    fe_sqr<F>(Fq, A);
+    fe_mul<F>(B, Y, Z); fe_dbl<F>(r + 2 * FPN, B);              // Z3 = 2 Y Z; identity stays identity (Z3 = 0); X, Y are dead now
+    fe_dbl<F>(B, D); fe_sub<F>(r, Fq, B);                       // X3 = F - 2D
+    fe_sub<F>(D, D, r); fe_mul<F>(D, A, D);
     fe_dbl<F>(Cc, Cc); fe_dbl<F>(Cc, Cc); fe_dbl<F>(Cc, Cc);    // 8C
-    fe_sub<F>(r + FPN, t, Cc);
-    bn_copy<C::Fp::N>(r + 2 * FPN, Z3);                         // identity stays identity (Z3 = 0)
+    fe_sub<F>(r + FPN, D, Cc);
 }
 
 // madd-2007-bl (Jacobian += affine): 7M + 4S, complete via the rare-case branches
@@ -54,26 +58,26 @@ template <class C> BBS_HDN void g1_add_mixed(uint32_t* r, const uint32_t* p, con
     using F = typename C::Fp;
     if (g1_is_inf<C>(p)) { g1_from_affine<C>(r, q); return; }
     const uint32_t *X1 = p, *Y1 = p + FPN, *Z1 = p + 2 * FPN, *X2 = q, *Y2 = q + FPN;
-    BBS_A16 uint32_t Z1Z1[FPN], U2[FPN], S2[FPN], H[FPN], HH[FPN], I[FPN], J[FPN], rr[FPN], V[FPN], t[FPN], X3[FPN], Y3[FPN], Z3[FPN];
+    BBS_A16 uint32_t Z1Z1[FPN], H[FPN], rr[FPN], HH[FPN], V[FPN], J[FPN];
     fe_sqr<F>(Z1Z1, Z1);
-    fe_mul<F>(U2, X2, Z1Z1);
-    fe_mul<F>(S2, Y2, Z1); fe_mul<F>(S2, S2, Z1Z1);
-    fe_sub<F>(H, U2, X1);
-    fe_sub<F>(rr, S2, Y1);
+    fe_mul<F>(H, X2, Z1Z1);                                     // U2
+    fe_mul<F>(rr, Y2, Z1); fe_mul<F>(rr, rr, Z1Z1);             // S2
+    fe_sub<F>(H, H, X1);
+    fe_sub<F>(rr, rr, Y1);
     if (bn_is_zero<C::Fp::N>(H)) {
         if (bn_is_zero<C::Fp::N>(rr)) { g1_dbl<C>(r, p); } else { g1_set_inf<C>(r); }
         return;
     }
     fe_dbl<F>(rr, rr);
     fe_sqr<F>(HH, H);
-    fe_dbl<F>(I, HH); fe_dbl<F>(I, I);
-    fe_mul<F>(J, H, I);
-    fe_mul<F>(V, X1, I);
-    fe_sqr<F>(X3, rr); fe_sub<F>(X3, X3, J); fe_sub<F>(X3, X3, V); fe_sub<F>(X3, X3, V);
-    fe_sub<F>(t, V, X3); fe_mul<F>(Y3, rr, t);
-    fe_mul<F>(t, Y1, J); fe_dbl<F>(t, t); fe_sub<F>(Y3, Y3, t);
-    fe_add<F>(Z3, Z1, H); fe_sqr<F>(Z3, Z3); fe_sub<F>(Z3, Z3, Z1Z1); fe_sub<F>(Z3, Z3, HH);
-    bn_copy<C::Fp::N>(r, X3); bn_copy<C::Fp::N>(r + FPN, Y3); bn_copy<C::Fp::N>(r + 2 * FPN, Z3);
+    fe_dbl<F>(V, HH); fe_dbl<F>(V, V);                          // I = 4 HH
+    fe_mul<F>(J, H, V);
+    fe_mul<F>(V, X1, V);                                        // V = X1 I
+    fe_add<F>(H, Z1, H); fe_sqr<F>(H, H); fe_sub<F>(H, H, Z1Z1); fe_sub<F>(r + 2 * FPN, H, HH);   // Z3; Z1, X1 are dead now
+    fe_sqr<F>(HH, rr); fe_sub<F>(HH, HH, J); fe_sub<F>(HH, HH, V); fe_sub<F>(r, HH, V);           // X3 = r^2 - J - 2V
+    fe_sub<F>(V, V, r); fe_mul<F>(V, rr, V);
+    fe_mul<F>(J, Y1, J); fe_dbl<F>(J, J);
+    fe_sub<F>(r + FPN, V, J);                                   // Y3 = r (V - X3) - 2 Y1 J
 }
 
 // add-2007-bl (Jacobian += Jacobian): 11M + 5S, complete via the rare-case branches
@@ -82,29 +86,29 @@ template <class C> BBS_HDN void g1_add(uint32_t* r, const uint32_t* p, const uin
     if (g1_is_inf<C>(p)) { g1_copy<C>(r, q); return; }
     if (g1_is_inf<C>(q)) { g1_copy<C>(r, p); return; }
     const uint32_t *X1 = p, *Y1 = p + FPN, *Z1 = p + 2 * FPN, *X2 = q, *Y2 = q + FPN, *Z2 = q + 2 * FPN;
-    BBS_A16 uint32_t Z1Z1[FPN], Z2Z2[FPN], U1[FPN], U2[FPN], S1[FPN], S2[FPN], H[FPN], I[FPN], J[FPN], rr[FPN], V[FPN], t[FPN],
-        X3[FPN], Y3[FPN], Z3[FPN];
+    BBS_A16 uint32_t Z1Z1[FPN], Z2Z2[FPN], U1[FPN], S1[FPN], H[FPN], rr[FPN], V[FPN], J[FPN];
     fe_sqr<F>(Z1Z1, Z1);
     fe_sqr<F>(Z2Z2, Z2);
     fe_mul<F>(U1, X1, Z2Z2);
-    fe_mul<F>(U2, X2, Z1Z1);
+    fe_mul<F>(H, X2, Z1Z1);                                     // U2
     fe_mul<F>(S1, Y1, Z2); fe_mul<F>(S1, S1, Z2Z2);
-    fe_mul<F>(S2, Y2, Z1); fe_mul<F>(S2, S2, Z1Z1);
-    fe_sub<F>(H, U2, U1);
-    fe_sub<F>(rr, S2, S1);
+    fe_mul<F>(rr, Y2, Z1); fe_mul<F>(rr, rr, Z1Z1);             // S2
+    fe_sub<F>(H, H, U1);
+    fe_sub<F>(rr, rr, S1);
     if (bn_is_zero<C::Fp::N>(H)) {
         if (bn_is_zero<C::Fp::N>(rr)) { g1_dbl<C>(r, p); } else { g1_set_inf<C>(r); }
         return;
     }
     fe_dbl<F>(rr, rr);
-    fe_dbl<F>(I, H); fe_sqr<F>(I, I);
-    fe_mul<F>(J, H, I);
-    fe_mul<F>(V, U1, I);
-    fe_sqr<F>(X3, rr); fe_sub<F>(X3, X3, J); fe_sub<F>(X3, X3, V); fe_sub<F>(X3, X3, V);
-    fe_sub<F>(t, V, X3); fe_mul<F>(Y3, rr, t);
-    fe_mul<F>(t, S1, J); fe_dbl<F>(t, t); fe_sub<F>(Y3, Y3, t);
-    fe_add<F>(Z3, Z1, Z2); fe_sqr<F>(Z3, Z3); fe_sub<F>(Z3, Z3, Z1Z1); fe_sub<F>(Z3, Z3, Z2Z2); fe_mul<F>(Z3, Z3, H);
-    bn_copy<C::Fp::N>(r, X3); bn_copy<C::Fp::N>(r + FPN, Y3); bn_copy<C::Fp::N>(r + 2 * FPN, Z3);
+    fe_add<F>(V, Z1, Z2); fe_sqr<F>(V, V); fe_sub<F>(V, V, Z1Z1); fe_sub<F>(V, V, Z2Z2);
+    fe_mul<F>(r + 2 * FPN, V, H);                               // Z3 = ((Z1+Z2)^2 - Z1Z1 - Z2Z2) H; p and q are dead now
+    fe_dbl<F>(V, H); fe_sqr<F>(V, V);                           // I = (2H)^2
+    fe_mul<F>(J, H, V);
+    fe_mul<F>(V, U1, V);                                        // V = U1 I
+    fe_sqr<F>(H, rr); fe_sub<F>(H, H, J); fe_sub<F>(H, H, V); fe_sub<F>(r, H, V);                 // X3
+    fe_sub<F>(V, V, r); fe_mul<F>(V, rr, V);
+    fe_mul<F>(J, S1, J); fe_dbl<F>(J, J);
+    fe_sub<F>(r + FPN, V, J);                                   // Y3
 }
 
 // Jacobian -> affine (x, y); returns false for the identity (then r is zeroed)
