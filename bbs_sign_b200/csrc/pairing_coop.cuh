@@ -65,6 +65,7 @@ template <> struct Coop<Bls> {
     static constexpr bool POINT_RATIO = false; // the item's points enter as (x, y)
     static constexpr bool QCANON = false;      // canonicalisation by the step ladder only (at most 4 steps here)
     static constexpr bool WARP_INV = true;     // INV shares one inversion among the 32 lanes (coop_warp_inverse): -4.5 %
+    static constexpr bool WARP_INV_PRO = false;
     static __device__ __forceinline__ void canon_q(uint32_t*) {}
     static __device__ __forceinline__ void add_kp(uint32_t* acc, const uint32_t* k) { coop_acc_add_e12(acc, k); }
     static __device__ __forceinline__ void xi(uint32_t*, uint32_t*) {}
@@ -103,8 +104,10 @@ template <> struct Coop<Bn> {
     static constexpr int PARK = 3;
     static constexpr bool ACC_XI = true;
     static constexpr bool POINT_RATIO = true;  // D-type twist: the line is normalised by 1/y, the points enter as (x/y, 1/y)
-    static constexpr bool WARP_INV = false;    // at this kernel's 80-register cap the shared inversion spills in the hot loop
-                                               // (measured +3.7 %): per-lane Fermat ladders as before
+    // the lanes of a warp share ONE inversion (coop_warp_inverse) in the prologue (x / y, 1 / y: -2.2 %) but not for the INV
+    // instruction: inside the interpreter loop the call makes ptxas re-allocate this kernel's 80 registers (+4.8 %)
+    static constexpr bool WARP_INV = false;
+    static constexpr bool WARP_INV_PRO = true;
     static __device__ __forceinline__ const uint32_t* prog() { return COOP_PROG_BN; }
     static __device__ __forceinline__ const uint32_t* prog_off() { return COOP_PROG_OFF_BN; }
     static __device__ __forceinline__ const uint32_t* consts() { return COOP_CONSTS_BN; }
@@ -353,7 +356,7 @@ __global__ void __maxnreg__(Coop<C>::MAXREG) pairing_coop_kernel(const CoopArgs 
                 BBS_A16 uint32_t x[N], y[N], yi[N];
                 coop_load<N>(x, cells + (16 + role) * CELL);
                 coop_load<N>(y, cells + (16 + role) * CELL + Q * 32);
-                if constexpr (Coop<C>::WARP_INV) coop_warp_inverse<C>(yi, y); else fe_inv<typename C::Fp>(yi, y);
+                if constexpr (Coop<C>::WARP_INV_PRO) coop_warp_inverse<C>(yi, y); else fe_inv<typename C::Fp>(yi, y);
                 fe_mul<typename C::Fp>(x, x, yi);
                 coop_store<N>(cells + (16 + role) * CELL, x);
                 coop_store<N>(cells + (16 + role) * CELL + Q * 32, yi);

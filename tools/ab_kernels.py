@@ -67,6 +67,24 @@ def run(path):
     res["verify_65536_ms[h2s,g1,pairing]"] = ts[2:]
     res["clk_after_verify"] = clocks()
     ctx.close()
+    # BN254 core_verify, L = 31
+    key = np.load(os.path.join(ROOT, "tests", "golden", "bn254_bench_key.npz"))
+    n = 131072
+    ctx = api.BatchContext(api.BN254, bytes(key["pk"]), header=b"", n_messages=31, lib_path=path)
+    lib.bbs_ctx_set_profiling(ctx.handle, 1)
+    sc, sigs, expect, _ = bench.make_bn254_workload(ctx, lib, n, seed=9, L=31)
+    d_s, d_c = torch.from_numpy(sigs).to(dev), torch.from_numpy(sc).to(dev)
+    d_st = torch.zeros(n, dtype=torch.uint8, device=dev)
+    ts = []
+    for _ in range(4):
+        assert lib.bbs_core_verify_batch_dev(ctx.handle, n, bench.ptr(d_s), bench.ptr(d_c), 31, bench.ptr(d_st), sp) == 0
+        torch.cuda.synchronize()
+        kt = (C.c_float * 3)()
+        lib.bbs_ctx_kernel_times(ctx.handle, kt, 3)
+        ts.append([round(x, 2) for x in kt][1:])
+    assert np.array_equal(d_st.cpu().numpy(), expect)
+    res["bn254_131072_ms[g1,pairing]"] = ts[2:]
+    ctx.close()
     return res
 
 
