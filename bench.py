@@ -783,7 +783,7 @@ def run_reference(args):
         # the same workload as our arm; every step times a bounded sample of it (named in cpu_baseline.sample): CPU
         # throughput does not depend on the batch size
         "config": verify_config(N_DEFAULT if args.n is None else args.n, args.L),
-        "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample", "as_reference") if k in last},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -16,6 +16,7 @@
  * Build: make -C oracle/cref   ->  oracle/_ref/libbbs_cref.so
  */
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -137,6 +138,19 @@ static void xmd48(uint8_t out[48], const uint8_t* m1, size_t n1, const uint8_t* 
     memcpy(out, b1, 32); memcpy(out + 32, b2, 16);
 }
 static void hash_to_scalar(fr* r, const uint8_t* msg, size_t n, const uint8_t* dst, size_t dlen) { uint8_t okm[48]; xmd48(okm, msg, n, NULL, 0, dst, dlen); fr_from_okm(r, okm); }
+
+/* expand_message_xmd for any output length <= 8160 (utilities_helper.rs:42-97) */
+static void xmd(uint8_t* out, size_t len, const uint8_t* m1, size_t n1, const uint8_t* m2, size_t n2, const uint8_t* dst, size_t dlen) {
+    uint8_t z[64] = {0}, b0[32], bi[32], t[33]; uint8_t dl = (uint8_t)dlen; uint8_t lib[3] = {(uint8_t)(len >> 8), (uint8_t)len, 0};
+    size_t ell = (len + 31) / 32;
+    sha256 s; sha_init(&s); sha_update(&s, z, 64); sha_update(&s, m1, n1); sha_update(&s, m2, n2); sha_update(&s, lib, 3); sha_update(&s, dst, dlen); sha_update(&s, &dl, 1); sha_final(&s, b0);
+    memset(bi, 0, 32);
+    for (size_t i = 1; i <= ell; i++) {
+        for (int k = 0; k < 32; k++) t[k] = (i == 1) ? b0[k] : (uint8_t)(b0[k] ^ bi[k]);
+        t[32] = (uint8_t)i; sha_init(&s); sha_update(&s, t, 33); sha_update(&s, dst, dlen); sha_update(&s, &dl, 1); sha_final(&s, bi);
+        size_t off = 32 * (i - 1), take = len - off < 32 ? len - off : 32; memcpy(out + off, bi, take);
+    }
+}
 
 /* ---- Fp2 ---- */
 static void f2_add(fp2* r, const fp2* a, const fp2* b) { fp_add(&r->c0, &a->c0, &b->c0); fp_add(&r->c1, &a->c1, &b->c1); }
@@ -380,6 +394,96 @@ static void pairing(fp12* out, const g1* p, const g2* q) {
 }
 
 /* ---- context: the `generators` argument and the issuer key, decoded once (they are typed values in the reference) ---- */
+/* ---- create_generators (interface_utilities.rs:47-73) with HashToG1Bls12381 (:30-44) = zkcrypto bls12_381 hash_to_curve,
+ * RFC 9380 BLS12381G1_XMD:SHA-256_SSWU_RO_: hash_to_field (two elements from 128 bytes), simplified SWU onto the 11-isogenous
+ * curve E': y^2 = x^3 + A'x + B' (Z = 11), the isogeny E' -> E evaluated by Velu's formulas from the x-coordinates of its
+ * rational order-11 kernel (the five denominators share one inversion), cofactor clearing by
+ * h_eff = 0xd201000000010001.  The reference runs this for L + 1 generators inside EVERY verify (verify.rs:35). ---- */
+static fp H2C_A, H2C_B, H2C_Z, H2C_NBA, H2C_BZA, H2C_I11_2, H2C_I11_3;
+static struct { fp xq, yq, gxgy, vq, uq; } VELU[5];
+static u64 EXP_SQRT[6];
+static void fp_from_hex(fp* r, const char* hex) {       /* 96 hex digits, big-endian */
+    uint8_t b[48]; for (int i = 0; i < 48; i++) { unsigned v; sscanf(hex + 2 * i, "%2x", &v); b[i] = (uint8_t)v; } fp_from_be48(r, b);
+}
+static int fp_sqrt(fp* y, const fp* a) { fp c; fp_pow(y, a, EXP_SQRT, 6); fp_sqr(&c, y); return fp_eq(&c, a); }
+static int fp_parity(const fp* a) { u64 c[6]; fp_to_canon(c, a); return (int)(c[0] & 1); }
+static void h2c_init(void) {
+    fp_from_hex(&H2C_A, "00144698a3b8e9433d693a02c96d4982b0ea985383ee66a8d8e8981aefd881ac98936f8da0e0f97f5cf428082d584c1d");
+    fp_from_hex(&H2C_B, "12e2908d11688030018b12e8753eee3b2016c1f0f24f4070a0b9c14fcef35ef55a23215a316ceaa5d1cc48e98e172be0");
+    fp_from_u64(&H2C_Z, 11);
+    fp ai, t; fp_inv(&ai, &H2C_A); fp_mul(&t, &H2C_B, &ai); fp_neg(&H2C_NBA, &t);                 /* -B/A */
+    fp za; fp_mul(&za, &H2C_Z, &H2C_A); fp_inv(&za, &za); fp_mul(&H2C_BZA, &H2C_B, &za);       /* B/(Z A) */
+    fp e11; fp_from_u64(&e11, 11); fp_inv(&e11, &e11); fp_sqr(&H2C_I11_2, &e11); fp_mul(&H2C_I11_3, &H2C_I11_2, &e11);
+    { u64 tmp[6]; memcpy(tmp, P, 48); tmp[0] += 1; u64 c = 0; for (int i = 5; i >= 0; i--) { u64 v = tmp[i]; EXP_SQRT[i] = (v >> 2) | (c << 62); c = v & 3; } }
+    static const char* KER[5] = {
+        "010ef325dd1e98bdf0d97a4c6b7f968ed7f31f2fbff088acb39d5319cfc261ea18773405f325612742f0c5d90634bcf4",
+        "0d7f2d0d03ae035321eed4c1479d13251abf0e9a96479623eb5380b575e319851fb5e5a8b43b9c1a46880f54bf2b2f7c",
+        "105249b4cac630ce5aa18e6c1189a18c82019b4e12e491fbac012c259ca3a67f638560b8bb416af02a4724385ed0fc8e",
+        "140d41735b10ce710727cd9356905701a2b866b803baa468948b7f423ddcc560c9a8f1cd5f8ed4297c37464fb8bfe4a7",
+        "1665a9c648e78314490a94f654d9b1039ab85847223bfaed9aa54f0f07736d122d1ceca1ac0e9123e753fde16e97c3d7"};
+    for (int k = 0; k < 5; k++) {
+        fp xq, rhs, yq, gx, gy, t2; fp_from_hex(&xq, KER[k]);
+        fp_sqr(&rhs, &xq); fp_mul(&rhs, &rhs, &xq); fp_mul(&t2, &H2C_A, &xq); fp_add(&rhs, &rhs, &t2); fp_add(&rhs, &rhs, &H2C_B);
+        fp_sqrt(&yq, &rhs);
+        fp_sqr(&gx, &xq); fp_dbl(&t2, &gx); fp_add(&gx, &gx, &t2); fp_add(&gx, &gx, &H2C_A);            /* 3 xq^2 + A */
+        fp_dbl(&gy, &yq); fp_neg(&gy, &gy);                                                              /* -2 yq */
+        VELU[k].xq = xq; VELU[k].yq = yq; fp_mul(&VELU[k].gxgy, &gx, &gy); fp_dbl(&VELU[k].vq, &gx); fp_sqr(&VELU[k].uq, &gy);
+    }
+}
+static void fp_from_be64_mod(fp* r, const uint8_t b[64]) {      /* OS2IP(64 bytes) mod p, Montgomery form */
+    uint8_t hi[48] = {0}; memcpy(hi + 32, b, 16); fp h, l; fp_from_be48(&h, hi); fp_from_be48(&l, b + 16); fp_mul(&h, &h, &FP_R2); fp_add(r, &h, &l);
+}
+static void sswu(fp* X, fp* Y, const fp* u) {
+    fp u2, tv, tv1, x1, g, t, y;
+    fp_sqr(&u2, u); fp_mul(&tv, &H2C_Z, &u2);                       /* Z u^2 */
+    fp_sqr(&t, &tv); fp_add(&tv1, &t, &tv);                          /* Z^2 u^4 + Z u^2 */
+    if (fp_is_zero(&tv1)) x1 = H2C_BZA;
+    else { fp_inv(&tv1, &tv1); fp_add(&t, &FP_ONE, &tv1); fp_mul(&x1, &H2C_NBA, &t); }
+    fp_sqr(&g, &x1); fp_mul(&g, &g, &x1); fp_mul(&t, &H2C_A, &x1); fp_add(&g, &g, &t); fp_add(&g, &g, &H2C_B);
+    if (fp_sqrt(&y, &g)) { *X = x1; }
+    else {
+        fp_mul(X, &tv, &x1);                                         /* Z u^2 x1 */
+        fp_sqr(&g, X); fp_mul(&g, &g, X); fp_mul(&t, &H2C_A, X); fp_add(&g, &g, &t); fp_add(&g, &g, &H2C_B);
+        fp_sqrt(&y, &g);
+    }
+    if (fp_parity(u) != fp_parity(&y)) fp_neg(&y, &y);
+    *Y = y;
+}
+static void iso11(g1* out, const fp* X, const fp* Y) {
+    fp den[5], pre[5], inv, xo = *X, yo = *Y, t, d, d2, d3, a, b;
+    for (int k = 0; k < 5; k++) { fp_sub(&den[k], X, &VELU[k].xq); if (k == 0) pre[0] = den[0]; else fp_mul(&pre[k], &pre[k - 1], &den[k]); }
+    fp_inv(&inv, &pre[4]);
+    for (int k = 4; k >= 0; k--) {
+        if (k > 0) { fp_mul(&d, &inv, &pre[k - 1]); fp_mul(&inv, &inv, &den[k]); } else d = inv;
+        fp_sqr(&d2, &d); fp_mul(&d3, &d2, &d);
+        fp_mul(&a, &VELU[k].vq, &d); fp_mul(&b, &VELU[k].uq, &d2); fp_add(&xo, &xo, &a); fp_add(&xo, &xo, &b);
+        fp_mul(&a, &VELU[k].uq, Y); fp_dbl(&a, &a); fp_mul(&a, &a, &d3);                       /* 2 uq Y d^3 */
+        fp_sub(&t, Y, &VELU[k].yq); fp_mul(&b, &VELU[k].vq, &t); fp_mul(&b, &b, &d2);            /* vq (Y - yq) d^2 */
+        fp_add(&a, &a, &b); fp_mul(&b, &VELU[k].gxgy, &d2); fp_sub(&a, &a, &b);                  /* - gx gy d^2 */
+        fp_sub(&yo, &yo, &a);
+    }
+    fp_mul(&out->x, &xo, &H2C_I11_2); fp_mul(&out->y, &yo, &H2C_I11_3); out->z = FP_ONE;
+}
+static void hash_to_g1(g1* out, const uint8_t* msg, size_t n, const uint8_t* dst, size_t dlen) {
+    uint8_t ub[128]; xmd(ub, 128, msg, n, NULL, 0, dst, dlen);
+    fp u0, u1, X, Y; g1 q0, q1, r; fp_from_be64_mod(&u0, ub); fp_from_be64_mod(&u1, ub + 64);
+    sswu(&X, &Y, &u0); iso11(&q0, &X, &Y); sswu(&X, &Y, &u1); iso11(&q1, &X, &Y);
+    g1_add(&r, &q0, &q1);
+    fr h; memset(&h, 0, sizeof h); h.l[0] = 0xd201000000010001ULL; g1_mul(out, &r, &h);
+}
+static void create_generators(g1* out, int count, const uint8_t* api_id, size_t api_len) {
+    uint8_t seed_dst[300], gen_dst[300], gen_seed[300], v[56];
+    memcpy(seed_dst, api_id, api_len); memcpy(seed_dst + api_len, "SIG_GENERATOR_SEED_", 19);
+    memcpy(gen_dst, api_id, api_len); memcpy(gen_dst + api_len, "SIG_GENERATOR_DST_", 18);
+    memcpy(gen_seed, api_id, api_len); memcpy(gen_seed + api_len, "MESSAGE_GENERATOR_SEED", 22);
+    xmd(v, 48, gen_seed, api_len + 22, NULL, 0, seed_dst, api_len + 19);
+    for (int i = 1; i <= count; i++) {
+        for (int k = 0; k < 8; k++) v[48 + k] = (uint8_t)((u64)i >> (56 - 8 * k));
+        uint8_t nv[48]; xmd(nv, 48, v, 56, NULL, 0, seed_dst, api_len + 19); memcpy(v, nv, 48);
+        hash_to_g1(&out[i - 1], v, 48, gen_dst, api_len + 18);
+    }
+}
+
 typedef struct { int L; g1* gens; g2 pk; uint8_t api_id[256]; size_t api_len; uint8_t dst_h2s[256], dst_map[256]; size_t dst_h2s_len, dst_map_len; } cref_ctx;
 
 static int inited = 0;
@@ -408,6 +512,7 @@ static void init_consts(void) {
     static const uint8_t bp2c[96] = {0x93,0xe0,0x2b,0x60,0x52,0x71,0x9f,0x60,0x7d,0xac,0xd3,0xa0,0x88,0x27,0x4f,0x65,0x59,0x6b,0xd0,0xd0,0x99,0x20,0xb6,0x1a,0xb5,0xda,0x61,0xbb,0xdc,0x7f,0x50,0x49,0x33,0x4c,0xf1,0x12,0x13,0x94,0x5d,0x57,0xe5,0xac,0x7d,0x05,0x5d,0x04,0x2b,0x7e,
                                      0x02,0x4a,0xa2,0xb2,0xf0,0x8f,0x0a,0x91,0x26,0x08,0x05,0x27,0x2d,0xc5,0x10,0x51,0xc6,0xe4,0x7a,0xd4,0xfa,0x40,0x3b,0x02,0xb4,0x51,0x0b,0x64,0x7a,0xe3,0xd1,0x77,0x0b,0xac,0x03,0x26,0xa8,0x05,0xbb,0xef,0xd4,0x80,0x56,0xc8,0xc1,0x21,0xbd,0xb8};
     g1_decompress(&G1_P1, p1c); g2_decompress(&G2_GEN, bp2c);
+    h2c_init();
     inited = 1;
 }
 
@@ -440,8 +545,29 @@ static void compute_B(g1* B, const cref_ctx* c, const fr* dom, const fr* m) {
 }
 
 /* PublicKey::verify for one item (verify.rs:18-93, generators given): returns 1 / 0, -1 for an undecodable signature */
+static int verify_one(const cref_ctx* c, const uint8_t* sig80, const uint8_t* msgs, const u64* offs, const uint8_t* header, size_t hlen);
 int cref_verify_one(void* p, const uint8_t* sig80, const uint8_t* msgs, const u64* offs, const uint8_t* header, size_t hlen) {
-    cref_ctx* c = (cref_ctx*)p; g1 A; fr e; fr m[256];
+    return verify_one((const cref_ctx*)p, sig80, msgs, offs, header, hlen);
+}
+/* mode (A) of BASELINE.md: exactly PublicKey::verify (verify.rs:18-50) -- create_generators(L + 1) recomputed for the item */
+int cref_verify_one_as_reference(void* p, const uint8_t* sig80, const uint8_t* msgs, const u64* offs, const uint8_t* header, size_t hlen) {
+    cref_ctx local = *(const cref_ctx*)p;
+    g1* gens = (g1*)malloc((size_t)(local.L + 1) * sizeof(g1));
+    create_generators(gens, local.L + 1, local.api_id, local.api_len);
+    local.gens = gens;
+    int r = verify_one(&local, sig80, msgs, offs, header, hlen);
+    free(gens);
+    return r;
+}
+void cref_create_generators(const uint8_t* api_id, size_t api_len, int count, uint8_t* out48) {
+    init_consts();
+    g1* g = (g1*)malloc((size_t)count * sizeof(g1));
+    create_generators(g, count, api_id, api_len);
+    for (int i = 0; i < count; i++) g1_compress(out48 + 48 * i, &g[i]);
+    free(g);
+}
+static int verify_one(const cref_ctx* c, const uint8_t* sig80, const uint8_t* msgs, const u64* offs, const uint8_t* header, size_t hlen) {
+    g1 A; fr e; fr m[256];
     if (g1_decompress(&A, sig80) < 0) return -1;
     fr_from_le32(&e, sig80 + 48);
     for (int j = 0; j < c->L; j++) hash_to_scalar(&m[j], msgs + offs[j], (size_t)(offs[j + 1] - offs[j]), c->dst_map, c->dst_map_len);
@@ -457,6 +583,11 @@ void cref_verify_batch(void* p, size_t n, const uint8_t* sigs, const uint8_t* ms
     cref_ctx* c = (cref_ctx*)p;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
     for (long i = 0; i < (long)n; i++) { int r = cref_verify_one(p, sigs + 80 * i, msgs, offs + (size_t)i * c->L, header, hlen); status[i] = r < 0 ? 5 : (uint8_t)r; }
+}
+void cref_verify_batch_as_reference(void* p, size_t n, const uint8_t* sigs, const uint8_t* msgs, const u64* offs, const uint8_t* header, size_t hlen, uint8_t* status, int threads) {
+    cref_ctx* c = (cref_ctx*)p;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+    for (long i = 0; i < (long)n; i++) { int r = cref_verify_one_as_reference(p, sigs + 80 * i, msgs, offs + (size_t)i * c->L, header, hlen); status[i] = r < 0 ? 5 : (uint8_t)r; }
 }
 /* SecretKey::sign for one item (sign.rs:32-133, generators and pk given): B and A = B * (sk+e)^-1 */
 int cref_sign_one(void* p, const uint8_t sk_le32[32], const uint8_t* msgs, const u64* offs, const uint8_t* header, size_t hlen, uint8_t sig80[80], uint8_t b48[48]) {

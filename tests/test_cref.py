@@ -59,3 +59,28 @@ def test_against_python_oracle(CB, L):
     assert st.tolist() == exp
     # the pairing itself (no trapdoor) on one valid and one forged item
     assert O.verify(cs, pk, items[0][0], b"hd", items[0][1]) == bool(st[0])
+
+
+def test_cref_create_generators_and_as_reference_mode():
+    """mode (A) of BASELINE.md: the C port's create_generators (hash-to-G1: SSWU + 11-isogeny + cofactor clearing) gives the
+    oracle's / the IRTF generators, and verify with generators recomputed per item (PublicKey::verify as written,
+    verify.rs:35) gives the same verdicts as with cached generators."""
+    from oracle import cref_binding
+    cs = O.BLS12_381
+    want = b"".join(cs.g1_compress(g) for g in O.create_generators_cached(cs, 5, cs.api_id))
+    assert cref_binding.create_generators(cs, 5) == want
+    assert want[:48].hex().startswith("a9ec65b70a7fbe40c874c9eb041c2cb0")          # Q1, test_vector.rs:132
+    other = b"some-other-api-id_"
+    assert cref_binding.create_generators(cs, 2, other) == b"".join(cs.g1_compress(g) for g in O.create_generators(cs, 2, other))
+    sk = O.key_gen(cs, b"cref-mode-a-key-material-32bytes", b"", b"BBS-SIG-KEYGEN-SALT-")
+    pk = O.sk_to_pk(cs, sk)
+    L = 3
+    gens = O.create_generators_cached(cs, L + 1, cs.api_id)
+    ctx = cref_binding.CrefContext(cs, pk, gens)
+    msgs = [[bytes([i, j]) * 7 for j in range(L)] for i in range(4)]
+    sigs = [O.sign(cs, sk, m, b"h") for m in msgs]
+    sigs[2] = (sigs[2][0], (sigs[2][1] + 1) % cs.r)
+    blob = b"".join(O.signature_to_bytes(cs, s) for s in sigs)
+    a = ctx.verify_batch(blob, msgs, header=b"h", as_reference=True)
+    b = ctx.verify_batch(blob, msgs, header=b"h")
+    assert a.tolist() == b.tolist() == [1, 1, 0, 1]
