@@ -227,6 +227,9 @@ class BatchContext:
     def use_per_thread_pairing(self, on: bool = True):
         self._check(self.lib.bbs_ctx_use_per_thread_pairing(self._h, 1 if on else 0), "bbs_ctx_use_per_thread_pairing")
 
+    def set_g1_split(self, max_items: int):
+        self._check(self.lib.bbs_ctx_set_g1_split(self._h, max_items), "bbs_ctx_set_g1_split")
+
     def set_rlc_windows(self, windows: int):
         self._check(self.lib.bbs_ctx_set_rlc_windows(self._h, windows), "bbs_ctx_set_rlc_windows")
 

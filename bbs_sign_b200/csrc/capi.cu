@@ -63,13 +63,14 @@ struct Ctx {
     uint32_t rlc_windows = 0;        // bbs_ctx_set_rlc_windows: digits per 128-bit value of the bucket MSM (0 = cost model)
     CtxView view{};
     // grow-only scratch for the batch calls
-    DevBuf s_rand, s_rand_off, s_sk;
+    DevBuf s_rand, s_rand_off, s_sk, s_g1v, s_g1f, s_g1st, s_g1t;
+    size_t split_max = 0;            // batches up to this size take the two-task G1 path (bbs_ctx_set_g1_split)
     DevBuf s_gscr, s_rlc_pt, s_rlc_sc, s_rlc_parts, s_rlc_bad, s_msm_pts, s_msm_kv, s_msm_idx, s_msm_entries, s_msm_buckets;
     DevBuf s_sigs, s_scalars, s_msgs, s_offsets, s_pair, s_flags, s_status, s_out, s_out2;
     DevBuf s_commit, s_commit_off, s_dis_idx, s_dis_scalars, s_dis_off, s_ph, s_dis_msgs, s_dis_msg_off;
     template <class Fn> void each_buffer(Fn f) {
         DevBuf* all[] = {&pk_comp, &gens_comp, &api_id, &header, &dst_h2s, &dst_map, &gens, &W, &K, &domain, &tab, &wbase,
-                         &lines, &lines_coop, &s_rand, &s_rand_off, &s_sk, &s_gscr, &s_rlc_pt, &s_rlc_sc, &s_rlc_parts, &s_rlc_bad, &s_msm_pts, &s_msm_kv, &s_msm_idx, &s_msm_entries, &s_msm_buckets, &misc, &s_sigs, &s_scalars, &s_msgs, &s_offsets, &s_pair, &s_flags, &s_status, &s_out,
+                         &lines, &lines_coop, &s_rand, &s_rand_off, &s_sk, &s_g1v, &s_g1f, &s_g1st, &s_g1t, &s_gscr, &s_rlc_pt, &s_rlc_sc, &s_rlc_parts, &s_rlc_bad, &s_msm_pts, &s_msm_kv, &s_msm_idx, &s_msm_entries, &s_msm_buckets, &misc, &s_sigs, &s_scalars, &s_msgs, &s_offsets, &s_pair, &s_flags, &s_status, &s_out,
                          &s_out2, &s_commit, &s_commit_off, &s_dis_idx, &s_dis_scalars, &s_dis_off, &s_ph, &s_dis_msgs,
                          &s_dis_msg_off};
         for (DevBuf* b : all) f(b);
@@ -196,6 +197,9 @@ struct Impl {
         v.gens = (const uint32_t*)c->gens.p; v.W = (const uint32_t*)c->W.p; v.K = (const uint32_t*)c->K.p;
         v.domain = (const uint32_t*)c->domain.p; v.tab = (const uint32_t*)c->tab.p;
         v.lines = (const uint32_t*)c->lines.p;
+#ifndef BBS_HOSTSIM
+        c->split_max = (size_t)-1;       // the two-task G1 path is faster at every batch size measured
+#endif
         return BBS_OK;
     }
 
@@ -232,6 +236,12 @@ struct Impl {
         TRY(c->s_pair.reserve(n * 6 * C::Fp::N * 4));
         TRY(c->s_flags.reserve(n * 4));
         VerifyG1Args a{c->view, d_sigs, d_scalars, n_msgs, (uint32_t*)c->s_pair.p, (uint32_t*)c->s_flags.p, d_status};
+        if (n <= c->split_max) {
+            TRY(c->s_g1v.reserve(n * 3 * C::Fp::N * 4));
+            TRY(c->s_g1f.reserve(n * 3 * C::Fp::N * 4));
+            TRY(c->s_g1st.reserve(2 * n));
+            a.part_v = (uint32_t*)c->s_g1v.p; a.part_f = (uint32_t*)c->s_g1f.p; a.part_st = (uint8_t*)c->s_g1st.p;
+        }
         if (S) {
             a.item_issuer = (const uint32_t*)S->item_issuer.p;
             a.iss = IssuerSetView{(const uint32_t*)S->K.p, (const uint32_t*)S->flags.p, (const uint32_t*)S->lines.p,
@@ -239,7 +249,7 @@ struct Impl {
         }
         PROF(c, 1, s);
         TRY((launch_verify_g1<C>(a, (uint32_t)n, s)));
-        c->launches += n ? 1 : 0;
+        c->launches += n ? (a.part_v ? 2 : 1) : 0;
         PROF(c, 2, s);
         TRY(pairing_dev(c, n, d_status, s, S));
         PROF(c, 3, s);
@@ -369,9 +379,17 @@ struct Impl {
         TRY(c->s_flags.reserve(n * 4));
         ProofG1Args a{c->view, d_proofs, d_commit, d_commit_off, d_idx, d_dis_scalars, d_dis_off, d_ph,
                       (uint32_t)ph_len, (uint32_t*)c->s_pair.p, (uint32_t*)c->s_flags.p, d_status};
+        if (n <= c->split_max) {
+            TRY(c->s_g1t.reserve(n * 3 * C::Fp::N * 4));
+            TRY(c->s_g1v.reserve(n * 3 * C::Fp::N * 4));
+            TRY(c->s_g1f.reserve(n * 3 * C::Fp::N * 4));
+            TRY(c->s_g1st.reserve(2 * n));
+            a.part_t1 = (uint32_t*)c->s_g1t.p; a.part_v2 = (uint32_t*)c->s_g1v.p; a.part_f = (uint32_t*)c->s_g1f.p;
+            a.part_st = (uint8_t*)c->s_g1st.p;
+        }
         PROF(c, 1, s);
         TRY((launch_proof_g1<C>(a, (uint32_t)n, s)));
-        c->launches += n ? 1 : 0;
+        c->launches += n ? (a.part_t1 ? 2 : 1) : 0;
         PROF(c, 2, s);
         TRY(pairing_dev(c, n, d_status, s));
         PROF(c, 3, s);
@@ -861,6 +879,12 @@ int bbs_ctx_set_rlc_windows(bbs_ctx* p, uint32_t windows) {
     if (!p) return arg_error("null context");
     if (windows != 0 && (windows < 8 || windows > 32)) return arg_error("windows must be 0 (cost model) or 8..32");
     as_ctx(p)->rlc_windows = windows;
+    return BBS_OK;
+}
+
+int bbs_ctx_set_g1_split(bbs_ctx* p, size_t max_items) {
+    if (!p) return arg_error("null context");
+    as_ctx(p)->split_max = max_items;
     return BBS_OK;
 }
 

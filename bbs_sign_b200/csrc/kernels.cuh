@@ -283,7 +283,10 @@ struct VerifyG1Args {
     uint32_t* pair; uint32_t* flags; uint8_t* status;
     const uint32_t* item_issuer;   // multi-issuer batches: issuer of item i in `iss` (nullptr: the context's own key)
     IssuerSetView iss;
+    // split path (verify_g1_split_kernel + verify_g1_combine_kernel): per item the Jacobian e*A and B and a state byte
+    uint32_t* part_v; uint32_t* part_f; uint8_t* part_st;
 };
+enum : uint8_t { VST_PA = 3, VST_VDONE = 4, VST_FBAD = 8 };      // part_st: PT_* of A | status already final | bad scalar
 // the key-dependent inputs of item i: K and the two identity flags
 template <class C> BBS_HD uint32_t verify_issuer(const VerifyG1Args& a, uint32_t i, const uint32_t*& K) {
     if (!a.item_issuer) { K = a.ctx.K; return (a.ctx.w_inf ? ISS_W_INF : 0u) | (a.ctx.k_inf ? ISS_K_INF : 0u); }
@@ -354,6 +357,75 @@ template <class C> BBS_HD void verify_g1_item(const VerifyG1Args& a, uint32_t i)
     if (!verify_g1_head<C>(a, i, Cc, pa)) return;
     if (!g1_is_inf_ool<C>(Cc)) fe_inv<typename C::Fp>(zinv, Cc + 2 * FPN);
     verify_g1_tail<C>(a, i, Cc, zinv, pa);
+}
+
+// ---- the same work as two independent tasks per item (CUDA build, verify_g1_split_kernel) --------------------------------
+// One thread per item is a serial chain of ~5,300 field multiplications; at the headline batch (65,536 items = 443 threads
+// per SM) every item is resident at once and the kernel time is that chain's latency.  Split per item into the
+// variable-base task V (decode + subgroup test of A, e*A: ~3,400 multiplications) and the fixed-base task F
+// (B = K + sum tab: ~1,900), 2n tasks go through the block scheduler -- V blocks first, F blocks fill in behind -- and the
+// critical path per item shrinks to V.  A small third kernel joins them (C = e*A - B, one inversion per block, flags).
+template <class C> BBS_HD void verify_task_v(const VerifyG1Args& a, uint32_t i) {
+    const CtxView& cx = a.ctx;
+    a.part_st[i] = VST_VDONE;
+    if (a.n_msgs != cx.L) { a.status[i] = ST_ERR_MSG_GEN_LEN; a.flags[i] = FL_DONE; return; }          // verify.rs:68-71
+    const uint32_t* Kp;
+    const uint32_t ifl = verify_issuer<C>(a, i, Kp);
+    if (ifl & ISS_BAD) { a.status[i] = ST_ERR_MALFORMED; a.flags[i] = FL_DONE; return; }
+    const uint8_t* sig = a.sigs + (size_t)i * (C::G1_BYTES + 32);
+    BBS_A16 uint32_t A[G1A], e[8];
+    const int pa = g1_decompress<C>(A, sig);
+    if (pa == PT_BAD || !fr_from_le32<C>(e, sig + C::G1_BYTES)) { a.status[i] = ST_ERR_MALFORMED; a.flags[i] = FL_DONE; return; }
+    uint32_t* pv = a.part_v + (size_t)i * G1J;
+    if (pa == PT_OK) {
+        BBS_A16 uint32_t eA[G1J];
+        g1_mul_scalar<C>(eA, A, e);
+        g1_copy<C>(pv, eA);
+    }
+    uint32_t* pr = a.pair + (size_t)i * PAIR_WORDS;
+    bn_copy<2 * C::Fp::N>(pr, A); fe_set_one<typename C::Fp>(pr + 2 * FPN);
+    a.part_st[i] = (uint8_t)pa;
+}
+template <class C> BBS_HD void verify_task_f(const VerifyG1Args& a, uint32_t i, uint8_t* fbad) {
+    const CtxView& cx = a.ctx;
+    *fbad = 0;
+    if (a.n_msgs != cx.L) return;
+    const uint32_t* Kp;
+    const uint32_t ifl = verify_issuer<C>(a, i, Kp);
+    if (ifl & ISS_BAD) return;
+    BBS_A16 uint32_t B[G1J];
+    if (ifl & ISS_K_INF) g1_set_inf<C>(B); else g1_from_affine<C>(B, Kp);
+    const uint8_t* sc = a.scalars + (size_t)i * a.n_msgs * 32;
+    bool ok = true;
+    for (uint32_t j = 0; j < a.n_msgs && ok; j++) {
+        BBS_A16 uint32_t m[8];
+        ok = fr_from_le32<C>(m, sc + j * 32);
+        if (ok) tab_accumulate<C>(B, cx, j + 1, m);
+    }
+    if (!ok) { *fbad = 1; return; }
+    g1_copy<C>(a.part_f + (size_t)i * G1J, B);
+}
+
+// join, part 1: Cc = e*A - B; false when the item's status is already final
+template <class C> BBS_HD bool verify_join_head(const VerifyG1Args& a, uint32_t i, const uint8_t* fbad, uint32_t* Cc, int& pa) {
+    const uint8_t st = a.part_st[i];
+    if (st & VST_VDONE) return false;
+    if (fbad[i]) { a.status[i] = ST_ERR_MALFORMED; a.flags[i] = FL_DONE; return false; }
+    pa = st & VST_PA;
+    BBS_A16 uint32_t B[G1J];
+    g1_copy<C>(B, a.part_f + (size_t)i * G1J);
+    g1_neg<C>(Cc, B);                                  // e(A, W) e(eA - B, BP2) == 1   (SURVEY 8a note (i))
+    if (pa == PT_OK) g1_add<C>(Cc, Cc, a.part_v + (size_t)i * G1J);
+    return true;
+}
+// the join with one inversion per item (host simulation of verify_g1_combine_kernel)
+template <class C> BBS_HD void verify_join_item(const VerifyG1Args& a, uint32_t i, const uint8_t* fbad) {
+    using F = typename C::Fp;
+    BBS_A16 uint32_t Cc[G1J], z[FPN];
+    int pa = PT_BAD;
+    if (!verify_join_head<C>(a, i, fbad, Cc, pa)) return;
+    if (!g1_is_inf_ool<C>(Cc)) fe_inv<F>(z, Cc + 2 * FPN); else fe_set_one<F>(z);
+    verify_g1_tail<C>(a, i, Cc, z, pa);
 }
 
 #if defined(__CUDACC__) && !defined(BBS_HOSTSIM)
@@ -431,6 +503,27 @@ template <class C, int TPB, int MINB> __global__ void __launch_bounds__(TPB, MIN
 #else
     block_batch_inverse<F, TPB, (TPB < 256)>(z, tree);
 #endif
+    if (live) verify_g1_tail<C>(a, i, Cc, z, pa);
+}
+
+// 2 * nb blocks: the first nb run task V for items [0, n), the next nb task F.  `fbad` (one byte per item) is written by F.
+template <class C, int TPB, int MINB> __global__ void __launch_bounds__(TPB, MINB)
+verify_g1_split_kernel(const VerifyG1Args a, uint32_t n, uint32_t nb, uint8_t* fbad) {
+    const bool var = blockIdx.x < nb;
+    const uint32_t i = (blockIdx.x - (var ? 0u : nb)) * TPB + threadIdx.x;
+    if (i >= n) return;
+    if (var) verify_task_v<C>(a, i); else verify_task_f<C>(a, i, fbad + i);
+}
+template <class C, int TPB> __global__ void __launch_bounds__(TPB, 2)
+verify_g1_combine_kernel(const VerifyG1Args a, uint32_t n, const uint8_t* fbad) {
+    using F = typename C::Fp;
+    __shared__ BBS_A16 uint32_t tree[2 * TPB][C::Fp::N];
+    const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+    BBS_A16 uint32_t Cc[G1J], z[FPN];
+    int pa = PT_BAD;
+    const bool live = i < n && verify_join_head<C>(a, i, fbad, Cc, pa);
+    if (live && !g1_is_inf_ool<C>(Cc)) bn_copy<C::Fp::N>(z, Cc + 2 * FPN); else fe_set_one<F>(z);
+    block_batch_inverse<F, TPB, true>(z, tree);
     if (live) verify_g1_tail<C>(a, i, Cc, z, pa);
 }
 #endif
@@ -585,6 +678,8 @@ struct ProofG1Args {
     const uint64_t* dis_off;       // n+1
     const uint8_t* ph; uint32_t ph_len;
     uint32_t* pair; uint32_t* flags; uint8_t* status;
+    // split path (proof_g1_split_kernel + proof_g1_join_kernel): Jacobian T1, D*r3^, fixed-base part of T2; state bytes
+    uint32_t* part_t1; uint32_t* part_v2; uint32_t* part_f; uint8_t* part_st;
 };
 template <class C> BBS_HD void proof_g1_item(const ProofG1Args& a, uint32_t i) {
     using F = typename C::Fp;
@@ -688,6 +783,167 @@ template <class C> BBS_HD void proof_g1_item(const ProofG1Args& a, uint32_t i) {
     if (pB == PT_INF) fl |= FL_SKIP1;
     a.flags[i] = fl;
 #undef PROOF_FAIL
+}
+
+// ---- core_proof_verify, G1 half, as three independent tasks per proof + a join (CUDA build) -----------------------------
+// One thread per proof is a serial chain of ~16,500 field multiplications.  Tasks: V1 = the checks of
+// proof_verify.rs:139-150, decoding + subgroup tests of Abar, Bbar, D and T1 (~8,400); F = the fixed-base part of T2,
+// K*c + sum H_disclosed (c m) + sum H_undisclosed m^ (~5,800); V2 = D * r3^ (~2,500, decodes D again).  The join adds the
+// two parts of T2, normalises T1 and T2 with one inversion per block, hashes the challenge and writes the pairing record.
+// Statuses are those of proof_g1_item: V1 owns every status of the checks and decodings, F only reports a non-canonical
+// message / commitment scalar (the same ERR_MALFORMED), the join owns the challenge comparison.
+struct ProofShape { uint64_t cb, U, db, R, L; uint32_t mask[MAX_L / 32]; };
+enum : uint8_t { PST_DONE = 0x80 };       // part_st[i]: status final | PT_* of Abar, Bbar, D in bits 0-1, 2-3, 4-5
+// the checks of proof_verify.rs:139-150 in the reference's order; 0 = fine, else the status
+template <class C> BBS_HD uint8_t proof_shape(const ProofG1Args& a, uint32_t i, ProofShape& s) {
+    s.cb = a.commit_off[i]; s.U = a.commit_off[i + 1] - s.cb;
+    s.db = a.dis_off[i]; s.R = a.dis_off[i + 1] - s.db;
+    s.L = s.R + s.U;
+    for (int k = 0; k < MAX_L / 32; k++) s.mask[k] = 0;
+    bool dup = false;
+    for (uint64_t k = 0; k < s.R; k++) {
+        uint32_t idx = a.dis_idx[s.db + k];
+        if (idx >= s.L) return ST_ERR_DISCLOSED_INDEX;
+        if (idx < MAX_L) { dup |= (s.mask[idx >> 5] >> (idx & 31)) & 1; s.mask[idx >> 5] |= 1u << (idx & 31); }
+    }
+    if (s.L != a.ctx.L) return ST_ERR_MSG_GEN_LEN;
+    if (dup) return ST_ERR_MALFORMED;     // the reference indexes out of bounds and panics (proof_verify.rs:179)
+    return 0;
+}
+template <class C> BBS_HD void proof_task_v1(const ProofG1Args& a, uint32_t i) {
+    using F = typename C::Fp;
+    constexpr int GB = C::G1_BYTES;
+    const uint8_t* pf = a.proofs + (size_t)i * (3 * GB + 128);
+    a.part_st[i] = PST_DONE;
+    ProofShape sh;
+    const uint8_t err = proof_shape<C>(a, i, sh);
+    if (err) { a.status[i] = err; a.flags[i] = FL_DONE; return; }
+    BBS_A16 uint32_t Ab[G1A], Bb[G1A], D[G1A], ecap[8], r1cap[8], r3cap[8], c[8];
+    int pA = g1_decompress<C>(Ab, pf), pB = g1_decompress<C>(Bb, pf + GB), pD = g1_decompress<C>(D, pf + 2 * GB);
+    bool ok = pA != PT_BAD && pB != PT_BAD && pD != PT_BAD;
+    ok = ok && fr_from_le32<C>(ecap, pf + 3 * GB) && fr_from_le32<C>(r1cap, pf + 3 * GB + 32) &&
+         fr_from_le32<C>(r3cap, pf + 3 * GB + 64) && fr_from_le32<C>(c, pf + 3 * GB + 96);
+    if (!ok) { a.status[i] = ST_ERR_MALFORMED; a.flags[i] = FL_DONE; return; }
+    // T1 = Bbar*c + Abar*e^ + D*r1^   (proof_verify.rs:163-164)
+    {
+        BBS_A16 uint32_t T1[G1J];
+        const uint32_t* pts[3] = {pB == PT_OK ? Bb : nullptr, pA == PT_OK ? Ab : nullptr, pD == PT_OK ? D : nullptr};
+        const uint32_t* ks[3] = {c, ecap, r1cap};
+        g1_msm_scalar<C, 3>(T1, pts, ks);
+        g1_copy<C>(a.part_t1 + (size_t)i * G1J, T1);
+    }
+    // e(Abar, W) e(Bbar, -BP2) = e(Abar, W) e(-Bbar, BP2)      (proof_verify.rs:112-115); the join sets the flags
+    uint32_t* pr = a.pair + (size_t)i * PAIR_WORDS;
+    bn_copy<2 * C::Fp::N>(pr, Ab); fe_set_one<F>(pr + 2 * FPN);
+    bn_copy<C::Fp::N>(pr + 3 * FPN, Bb); fe_neg<F>(pr + 4 * FPN, Bb + FPN); fe_set_one<F>(pr + 5 * FPN);
+    a.part_st[i] = (uint8_t)(pA | (pB << 2) | (pD << 4));
+}
+template <class C> BBS_HD void proof_task_v2(const ProofG1Args& a, uint32_t i) {
+    constexpr int GB = C::G1_BYTES;
+    const uint8_t* pf = a.proofs + (size_t)i * (3 * GB + 128);
+    ProofShape sh;
+    if (proof_shape<C>(a, i, sh)) return;
+    BBS_A16 uint32_t D[G1A], r3cap[8], t[G1J];
+    if (g1_decompress<C>(D, pf + 2 * GB) != PT_OK || !fr_from_le32<C>(r3cap, pf + 3 * GB + 64)) return;   // V1 reports what is wrong
+    g1_mul_scalar<C>(t, D, r3cap);
+    g1_copy<C>(a.part_v2 + (size_t)i * G1J, t);
+}
+template <class C> BBS_HD void proof_task_f(const ProofG1Args& a, uint32_t i, uint8_t* fbad) {
+    using Fr = typename C::Fr;
+    const CtxView& cx = a.ctx;
+    constexpr int GB = C::G1_BYTES;
+    const uint8_t* pf = a.proofs + (size_t)i * (3 * GB + 128);
+    *fbad = 0;
+    ProofShape sh;
+    if (proof_shape<C>(a, i, sh)) return;
+    BBS_A16 uint32_t c[8], cm[8], T2[G1J];
+    if (!fr_from_le32<C>(c, pf + 3 * GB + 96)) return;                                  // V1 reports it
+    // Bv*c = K*c + sum H_disclosed (c m), then sum H_undisclosed m^   (proof_verify.rs:165-182)
+    fe_to_mont<Fr>(cm, c);
+    g1_set_inf<C>(T2);
+    if (!cx.k_inf) tab_accumulate<C>(T2, cx, 0, c);
+    for (uint64_t k = 0; k < sh.R; k++) {
+        BBS_A16 uint32_t m[8];
+        if (!fr_from_le32<C>(m, a.dis_scalars + (sh.db + k) * 32)) { *fbad = 1; return; }
+        fe_mul<Fr>(m, m, cm);                                   // c * m_k, canonical
+        tab_accumulate<C>(T2, cx, a.dis_idx[sh.db + k] + 1, m);
+    }
+    uint64_t k = 0;
+    for (uint32_t j = 0; j < (uint32_t)sh.L; j++) {
+        if ((sh.mask[j >> 5] >> (j & 31)) & 1) continue;
+        BBS_A16 uint32_t m[8];
+        if (!fr_from_le32<C>(m, a.commitments + (sh.cb + k) * 32)) { *fbad = 1; return; }
+        tab_accumulate<C>(T2, cx, j + 1, m);
+        k++;
+    }
+    g1_copy<C>(a.part_f + (size_t)i * G1J, T2);
+}
+// join, part 1: T2 = F part (+ V2 part); false when the item's status is already final
+template <class C> BBS_HD bool proof_join_head(const ProofG1Args& a, uint32_t i, const uint8_t* fbad, uint32_t* T1, uint32_t* T2, uint8_t& st) {
+    st = a.part_st[i];
+    if (st & PST_DONE) return false;
+    if (fbad[i]) { a.status[i] = ST_ERR_MALFORMED; a.flags[i] = FL_DONE; return false; }
+    g1_copy<C>(T1, a.part_t1 + (size_t)i * G1J);
+    g1_copy<C>(T2, a.part_f + (size_t)i * G1J);
+    if (((st >> 4) & 3) == PT_OK) g1_add<C>(T2, T2, a.part_v2 + (size_t)i * G1J);
+    return true;
+}
+// join, part 2: zinv = 1 / (Z(T1) Z(T2)) with identities counted as Z = 1; challenge (proof_gen.rs:272-328), comparison, flags
+template <class C> BBS_HD void proof_join_tail(const ProofG1Args& a, uint32_t i, const uint32_t* T1, const uint32_t* T2, const uint32_t* zinv, uint8_t st) {
+    using F = typename C::Fp;
+    using Fr = typename C::Fr;
+    const CtxView& cx = a.ctx;
+    constexpr int GB = C::G1_BYTES;
+    const uint8_t* pf = a.proofs + (size_t)i * (3 * GB + 128);
+    const uint64_t db = a.dis_off[i], R = a.dis_off[i + 1] - db;
+    Xmd48 x;
+    x.begin();
+    x.s.put_be64(R);
+    for (uint64_t k = 0; k < R; k++) {
+        BBS_A16 uint32_t m[8];
+        x.s.put_be64(a.dis_idx[db + k]);
+        limbs_from_le<8>(m, a.dis_scalars + (db + k) * 32);
+        for (int q = 7; q >= 0; q--) x.s.update_words(&m[q], 1);
+    }
+    x.s.update(pf, 3 * GB);                                     // canonical encodings of Abar, Bbar, D
+    {
+        const bool i1 = g1_is_inf_ool<C>(T1), i2 = g1_is_inf_ool<C>(T2);
+        BBS_A16 uint32_t z1[FPN], z2[FPN], t[FPN], zz[FPN], aff[G1A];
+        uint8_t enc[GB];
+        if (i1) fe_set_one<F>(z1); else bn_copy<C::Fp::N>(z1, T1 + 2 * FPN);
+        if (i2) fe_set_one<F>(z2); else bn_copy<C::Fp::N>(z2, T2 + 2 * FPN);
+        fe_mul<F>(t, zinv, z2);                                 // 1/z1
+        fe_mul<F>(zz, zinv, z1);                                // 1/z2
+        fe_sqr<F>(z1, t); fe_mul<F>(aff, T1, z1); fe_mul<F>(z1, z1, t); fe_mul<F>(aff + FPN, T1 + FPN, z1);
+        g1_compress_affine<C>(enc, aff, i1); x.s.update(enc, GB);
+        fe_sqr<F>(z2, zz); fe_mul<F>(aff, T2, z2); fe_mul<F>(z2, z2, zz); fe_mul<F>(aff + FPN, T2 + FPN, z2);
+        g1_compress_affine<C>(enc, aff, i2); x.s.update(enc, GB);
+    }
+    for (int q = 7; q >= 0; q--) x.s.update_words(&cx.domain[q], 1);
+    x.s.put_be64(a.ph_len);
+    x.s.update(a.ph, a.ph_len);
+    BBS_A16 uint32_t okm[12], c2[8], c[8];
+    x.finish(cx.dst_h2s, cx.dst_h2s_len, okm);
+    okm48_to_scalar<Fr>(c2, okm);
+    limbs_from_le<8>(c, pf + 3 * GB + 96);
+    if (!bn_eq<8>(c2, c)) { a.status[i] = ST_REJECT; a.flags[i] = FL_DONE; return; }      // proof_verify.rs:108-110: no pairing
+    uint32_t fl = 0;
+    if ((st & 3) == PT_INF || cx.w_inf) fl |= FL_SKIP0;
+    if (((st >> 2) & 3) == PT_INF) fl |= FL_SKIP1;
+    a.flags[i] = fl;
+}
+
+// the join with one inversion per proof (host simulation of proof_g1_join_kernel)
+template <class C> BBS_HD void proof_join_item(const ProofG1Args& a, uint32_t i, const uint8_t* fbad) {
+    using F = typename C::Fp;
+    BBS_A16 uint32_t T1[G1J], T2[G1J], z[FPN];
+    uint8_t st = 0;
+    if (!proof_join_head<C>(a, i, fbad, T1, T2, st)) return;
+    fe_set_one<F>(z);
+    if (!g1_is_inf_ool<C>(T1)) bn_copy<C::Fp::N>(z, T1 + 2 * FPN);
+    if (!g1_is_inf_ool<C>(T2)) fe_mul<F>(z, z, T2 + 2 * FPN);
+    fe_inv<F>(z, z);
+    proof_join_tail<C>(a, i, T1, T2, z, st);
 }
 
 // ---- core_proof_gen (proof_gen.rs:116-365: proof_init, proof_challenge_calculate, proof_finalize) ---------------
@@ -857,5 +1113,31 @@ template <class C> BBS_HD void proof_gen_item(const ProofGenArgs& a, uint32_t i)
     a.status[i] = ST_ACCEPT;
 #undef GEN_FAIL
 }
+
+#if defined(__CUDACC__) && !defined(BBS_HOSTSIM)
+// 3 * nb blocks: V1 for items [0, n), then F, then V2 (longest tasks first)
+template <class C, int TPB, int MINB> __global__ void __launch_bounds__(TPB, MINB)
+proof_g1_split_kernel(const ProofG1Args a, uint32_t n, uint32_t nb, uint8_t* fbad) {
+    const uint32_t kind = blockIdx.x / nb;
+    const uint32_t i = (blockIdx.x - kind * nb) * TPB + threadIdx.x;
+    if (i >= n) return;
+    if (kind == 0) proof_task_v1<C>(a, i); else if (kind == 1) proof_task_f<C>(a, i, fbad + i); else proof_task_v2<C>(a, i);
+}
+template <class C, int TPB> __global__ void __launch_bounds__(TPB, 4) proof_g1_join_kernel(const ProofG1Args a, uint32_t n, const uint8_t* fbad) {
+    using F = typename C::Fp;
+    __shared__ BBS_A16 uint32_t tree[2 * TPB][C::Fp::N];
+    const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+    BBS_A16 uint32_t T1[G1J], T2[G1J], z[FPN];
+    uint8_t st = 0;
+    const bool live = i < n && proof_join_head<C>(a, i, fbad, T1, T2, st);
+    fe_set_one<F>(z);
+    if (live) {
+        if (!g1_is_inf_ool<C>(T1)) bn_copy<C::Fp::N>(z, T1 + 2 * FPN);
+        if (!g1_is_inf_ool<C>(T2)) fe_mul<F>(z, z, T2 + 2 * FPN);
+    }
+    block_batch_inverse<F, TPB, true>(z, tree);
+    if (live) proof_join_tail<C>(a, i, T1, T2, z, st);
+}
+#endif
 
 }  // namespace bbs

@@ -261,9 +261,13 @@ uint64_t bbs_ctx_memory_bytes(bbs_ctx* ctx);
  *   degenerate line (a tangent / chord of the public key's ate walk through the origin; impossible for an honest key)
  *   falls back to, instead of the cooperative role-warp kernel.
  * bbs_ctx_set_rlc_windows: digits per 128-bit value of the bucket MSM of the random-linear-combination mode
- *   (8..32; 0 = the cost model's choice). */
+ *   (8..32; 0 = the cost model's choice).
+ * bbs_ctx_set_g1_split: verify / core_verify batches of up to max_items items run their G1 half as two tasks per item
+ *   (variable-base and fixed-base part in parallel, then a join) instead of one thread per item; the default is SIZE_MAX
+ *   (always: it is faster at every batch size measured), 0 selects the one-thread-per-item kernel. */
 int bbs_ctx_use_per_thread_pairing(bbs_ctx* ctx, int on);
 int bbs_ctx_set_rlc_windows(bbs_ctx* ctx, uint32_t windows);
+int bbs_ctx_set_g1_split(bbs_ctx* ctx, size_t max_items);
 
 /* ---- measurement hooks ------------------------------------------------------------------------------
  * With profiling on, every *_dev batch call records CUDA events on its launching stream around each of its

@@ -48,6 +48,7 @@ def gens_bytes(ocs, gens):
     return b"".join(ocs.g1_compress(g) for g in gens)
 
 
+G1_SPLIT = None             # None: the library default; else bbs_ctx_set_g1_split on every context make_ctx builds
 SMALL_TABLES = False      # test_small_tables flips this: every context of a case is then built with BBS_CTX_SMALL_TABLES
 
 
@@ -55,8 +56,11 @@ def make_ctx(lib_path, suite, ocs, pk, header, L, api_id=None, gens=None):
     api_id = ocs.api_id if api_id is None else api_id
     if gens is None:
         gens = O.create_generators_cached(ocs, L + 1, api_id)
-    return A.BatchContext(suite, ocs.g2_compress(pk), header, generators=gens_bytes(ocs, gens), api_id=api_id,
-                          lib_path=lib_path, small_tables=SMALL_TABLES), gens
+    ctx = A.BatchContext(suite, ocs.g2_compress(pk), header, generators=gens_bytes(ocs, gens), api_id=api_id,
+                         lib_path=lib_path, small_tables=SMALL_TABLES)
+    if G1_SPLIT is not None:
+        ctx.set_g1_split(G1_SPLIT)
+    return ctx, gens
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -284,3 +284,20 @@ def test_small_tables(lib, curve, monkeypatch):
     P.case_verify(None, curve, 3, n=6, use_pairing_oracle_on=1)
     P.case_proof_gen(None, curve, 3, [0, 2], n=3)
     P.case_proof_verify(None, curve, 4, [0, 2], n=8, pairing_on=0)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_one_thread_per_item_g1_kernel(lib, curve, monkeypatch):
+    """verify / core_verify through the one-thread-per-item G1 kernel (bbs_ctx_set_g1_split(0)); the default is the two-task
+    split, which every other test exercises"""
+    from bbs_sign_b200 import api as A
+    orig = A.BatchContext.__init__
+
+    def init(self, *a, **k):
+        orig(self, *a, **k)
+        self.set_g1_split(0)
+
+    monkeypatch.setattr(A.BatchContext, "__init__", init)
+    P.case_verify(None, curve, 3, n=12, use_pairing_oracle_on=1)
+    P.case_verify_malformed(None, curve)
+    P.case_subgroup(None, curve)

@@ -115,3 +115,17 @@ def test_small_tables(lib_path, curve, monkeypatch):
     P.case_verify(lib_path, curve, 3, n=6, use_pairing_oracle_on=1)
     P.case_proof_gen(lib_path, curve, 3, [0, 2], n=3)
     P.case_proof_verify(lib_path, curve, 4, [0, 2], n=8, pairing_on=0)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_g1_task_split(lib_path, curve, monkeypatch):
+    """the G1 halves of verify / proof-verify as independent tasks + a join (kernels.cuh verify_task_* / proof_task_*): the
+    CUDA build's default; here the same task functions run in sequence"""
+    monkeypatch.setattr(P, "G1_SPLIT", 1 << 62)
+    P.case_verify(lib_path, curve, 3, n=8, use_pairing_oracle_on=1)
+    P.case_verify_malformed(lib_path, curve)
+    P.case_subgroup(lib_path, curve)
+    P.case_proof_verify(lib_path, curve, 4, [0, 2], n=10, pairing_on=0)
+    P.case_proof_verify(lib_path, curve, 3, [], n=6, pairing_on=0)
+    P.case_proof_verify(lib_path, curve, 3, [0, 1, 2], n=6, pairing_on=0)
+    P.case_proof_errors(lib_path, curve)
