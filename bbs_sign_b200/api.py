@@ -468,15 +468,21 @@ class ProofBytes:
 class PublicKey:
     """`PublicKey<E>` (key_gen.rs:12-15) with the batch entry points the north star adds."""
 
-    def __init__(self, suite: Ciphersuite, pk: bytes):
-        self.suite, self.pk = suite, bytes(pk)
-        self._ctx = {}
+    MAX_CONTEXTS = 4       # contexts kept per key: one is 0.55 GB of HBM at L = 10 (header and L vary per call in the reference)
+
+    def __init__(self, suite: Ciphersuite, pk: bytes, lib_path: Optional[str] = None):
+        self.suite, self.pk, self.lib_path = suite, bytes(pk), lib_path
+        self._ctx = {}         # (header, L, device) -> BatchContext, least recently used first
 
     def context(self, header: bytes, n_messages: int, device: int = 0) -> BatchContext:
         key = (header, n_messages, device)
-        if key not in self._ctx:
-            self._ctx[key] = BatchContext(self.suite, self.pk, header, n_messages, device=device)
-        return self._ctx[key]
+        ctx = self._ctx.pop(key, None)
+        if ctx is None:
+            while len(self._ctx) >= self.MAX_CONTEXTS:
+                self._ctx.pop(next(iter(self._ctx))).close()
+            ctx = BatchContext(self.suite, self.pk, header, n_messages, device=device, lib_path=self.lib_path)
+        self._ctx[key] = ctx
+        return ctx
 
     def verify_batch(self, signatures, header: bytes, messages: Sequence[Sequence[bytes]], device: int = 0) -> np.ndarray:
         """verify.rs:18-50 for a batch sharing `header`; messages[i] is the message list of signature i."""

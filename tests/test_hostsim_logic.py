@@ -1,6 +1,7 @@
 """GPU-less logic tests: the CUDA sources compiled for x86 (tests/hostsim.py) driven through the same C
 ABI and the same parity cases the GPU tests use.  They check the pipeline logic, byte plumbing and
 the oracle agreement of everything except the PTX arithmetic itself (which only a GPU can run)."""
+import numpy as np
 import pytest
 
 import hostsim
@@ -129,3 +130,21 @@ def test_g1_task_split(lib_path, curve, monkeypatch):
     P.case_proof_verify(lib_path, curve, 3, [], n=6, pairing_on=0)
     P.case_proof_verify(lib_path, curve, 3, [0, 1, 2], n=6, pairing_on=0)
     P.case_proof_errors(lib_path, curve)
+
+
+def test_public_key_keeps_a_bounded_number_of_contexts(lib_path):
+    """PublicKey.context: header and L are per call in the reference (verify.rs:18-30), a context per distinct pair is device
+    memory; the least recently used one is destroyed beyond MAX_CONTEXTS"""
+    from bbs_sign_b200 import api as A
+    suite, ocs = P.SUITES["BLS12_381"]
+    sk = P.O.key_gen(ocs, bytes([7] * 32), b"", b"BBS-SIG-KEYGEN-SALT-")
+    pk = A.PublicKey(suite, ocs.g2_compress(P.O.sk_to_pk(ocs, sk)), lib_path=lib_path)
+    first = pk.context(b"h0", 1)
+    ctxs = [pk.context(b"h%d" % i, 1) for i in range(1, A.PublicKey.MAX_CONTEXTS)]
+    assert pk.context(b"h0", 1) is first and first._h                      # a hit refreshes the entry
+    pk.context(b"one more", 1)
+    assert len(pk._ctx) == A.PublicKey.MAX_CONTEXTS
+    assert ctxs[0]._h is None and first._h                                 # h1 was the least recently used
+    msgs = [[b"m"]]
+    sig = P.O.signature_to_bytes(ocs, P.O.sign(ocs, sk, msgs[0], b"h1"))
+    assert pk.verify_batch(np.frombuffer(sig, dtype=np.uint8).reshape(1, -1), b"h1", msgs).tolist() == [1]              # rebuilt on demand
