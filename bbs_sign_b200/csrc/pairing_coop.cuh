@@ -14,6 +14,7 @@
 #ifdef __CUDACC__
 #include "gen_coop.cuh"
 #define COOP_BN_QCANON_M 1354u                 // floor(2^32 / ((p_bn254 >> 232) + 1)), checked by tools/gen_coop.py
+#define COOP_BLS_QCANON_M 165164498u           // floor(2^56 / ((p_bls12_381 >> 352) + 1)), checked by tools/gen_coop.py
 #ifdef BBS_COOP_PROG_HEADER
 #include BBS_COOP_PROG_HEADER              // timing experiments: alternative (not result-correct) programs
 #else
@@ -63,11 +64,31 @@ template <> struct Coop<Bls> {
     static constexpr int PARK = 1;             // Fp12 values a group parks in HBM (GSAVE / GLOAD slots)
     static constexpr bool ACC_XI = false;      // xi = 1 + u: multiplication by xi is routed through the EP signs
     static constexpr bool POINT_RATIO = false; // the item's points enter as (x, y)
-    static constexpr bool QCANON = false;      // canonicalisation by the step ladder only (at most 4 steps here)
+    // w (12 words, < R < 10 p) -> w mod p: q^ = (w[11] * floor(2^56 / (top 29 bits of p + 1))) >> 56 is q or q - 1
+    // (tools/gen_coop.py check_canon_q_bls), q^ p comes from a 10-row table in shared memory (the row index differs per lane),
+    // then ONE conditional subtraction: 42 instructions per component where the step ladder (8p, 4p, 2p, p) took 50-100
+    static constexpr bool QCANON = true;
+    static constexpr int QCANON_MIN = 1;       // canon levels below this keep the ladder (level 0: one step)
+    static constexpr int QTAB_UINT4 = 10 * 3;  // shared-memory table: q p for q < 10
+    static __device__ __forceinline__ const uint32_t* qtab() { return COOP_QP_BLS; }
+    static __device__ __forceinline__ void canon_q(uint32_t* w, const uint4* tab) {
+        const uint32_t q = __umulhi(w[11], COOP_BLS_QCANON_M) >> 24;
+        const uint4 a = tab[q * 3], b = tab[q * 3 + 1], c = tab[q * 3 + 2];
+        asm("sub.cc.u32 %0, %0, %12; subc.cc.u32 %1, %1, %13; subc.cc.u32 %2, %2, %14; subc.cc.u32 %3, %3, %15; subc.cc.u32 %4, %4, %16; "
+            "subc.cc.u32 %5, %5, %17; subc.cc.u32 %6, %6, %18; subc.cc.u32 %7, %7, %19; subc.cc.u32 %8, %8, %20; subc.cc.u32 %9, %9, %21; "
+            "subc.cc.u32 %10, %10, %22; subc.u32 %11, %11, %23;"
+            : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]), "+r"(w[8]), "+r"(w[9]),
+              "+r"(w[10]), "+r"(w[11])
+            : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w));
+        uint32_t d[12];
+        const uint32_t bo = coop_sub_1p_bls(d, w);
+#pragma unroll
+        for (int i = 0; i < 12; i++) w[i] = bo ? w[i] : d[i];
+    }
     static constexpr bool WARP_INV = true;     // INV shares one inversion among the 32 lanes (coop_warp_inverse): -4.5 %
     static constexpr bool WARP_INV_PRO = false;
-    static __device__ __forceinline__ void canon_q(uint32_t*) {}
-    static __device__ __forceinline__ void add_kp(uint32_t* acc, const uint32_t* k) { coop_acc_add_e12(acc, k); }
+    static constexpr int KPW = 12;             // KP[k] = k p R: the table holds k p, added to the high half of the accumulator
+    static __device__ __forceinline__ void add_kp(uint32_t* acc, const uint32_t* k) { coop_acc_add_hi12(acc, k); }
     static __device__ __forceinline__ void xi(uint32_t*, uint32_t*) {}
     static __device__ __forceinline__ const uint32_t* prog() { return COOP_PROG_BLS; }
     static __device__ __forceinline__ const uint32_t* prog_off() { return COOP_PROG_OFF_BLS; }
@@ -123,6 +144,7 @@ template <> struct Coop<Bn> {
     static __device__ __forceinline__ void subn(uint32_t* d, const uint32_t* s) { coop_subn8(d, s); }
     static __device__ __forceinline__ void add_p(uint32_t* d) { coop_add_p_bn(d); }
     static __device__ __forceinline__ void redc(uint32_t* r, uint32_t* t) { coop_redc_wide_bn(r, t); }
+    static constexpr int KPW = 17;             // KP[k] = multiples of p^2, full accumulator width
     static __device__ __forceinline__ void add_kp(uint32_t* acc, const uint32_t* k) { coop_acc_add_f8(acc, k); }
     template <int K> static __device__ __forceinline__ uint32_t sub_kp(uint32_t* d, const uint32_t* r) {
         if (K == 64) return coop_sub_64p_bn9(d, r);
@@ -137,7 +159,10 @@ template <> struct Coop<Bn> {
     // p + 1)) / 2^32) is q or q - 1 (q = floor(w / p) < 128; bound in tools/gen_coop.py check_canon_q), so one multiply-
     // subtract by q^ p and ONE conditional subtraction replace the 5..7 conditional subtractions of the step ladder
     static constexpr bool QCANON = true;
-    static __device__ __forceinline__ void canon_q(uint32_t* w) {
+    static constexpr int QCANON_MIN = 2;
+    static constexpr int QTAB_UINT4 = 0;       // no table: q^ p is computed (q < 128)
+    static __device__ __forceinline__ const uint32_t* qtab() { return nullptr; }
+    static __device__ __forceinline__ void canon_q(uint32_t* w, const uint4*) {
         const uint32_t* p = BN_FP_P();
         const uint32_t v = (w[8] << 24) | (w[7] >> 8);
         const uint32_t q = __umulhi(v, COOP_BN_QCANON_M);
@@ -256,7 +281,7 @@ template <class C> __device__ __noinline__ void coop_warp_inverse(uint32_t* o, c
 // both output components: (accR, accI) -> canonical Fp2.  The two reductions are independent; they are written
 // step by step side by side (one basic block per step) so that their dependency chains overlap.
 template <class C> __device__ __forceinline__ void coop_finish2(uint32_t* r0, uint32_t* r1, uint32_t* R, uint32_t* I,
-                                                                uint32_t ins, const uint4* zp) {
+                                                                uint32_t ins, const uint4* zp, const uint4* qtab) {
     constexpr int N = Coop<C>::N;
     constexpr int Q = N / 4;
     if ((ins >> 10) & 1) {                       // triple
@@ -279,10 +304,11 @@ template <class C> __device__ __forceinline__ void coop_finish2(uint32_t* r0, ui
     }
     const uint32_t kp = ((ins >> 22) & 3) | (((ins >> 31) & 1) << 2);
     if (kp) {
-        uint32_t k[2 * N + 1];
-        const uint32_t* kt = Coop<C>::kp() + kp * (2 * N + 1);
+        constexpr int KPW = Coop<C>::KPW;
+        uint32_t k[KPW];
+        const uint32_t* kt = Coop<C>::kp() + kp * KPW;
 #pragma unroll
-        for (int i = 0; i <= 2 * N; i++) k[i] = kt[i];
+        for (int i = 0; i < KPW; i++) k[i] = kt[i];
         Coop<C>::add_kp(R, k);
         Coop<C>::add_kp(I, k);
     }
@@ -295,15 +321,15 @@ template <class C> __device__ __forceinline__ void coop_finish2(uint32_t* r0, ui
 #define COOP_CANON_STEP(K)                                                                     \
     b0 = Coop<C>::template sub_kp<K>(d0, w0); b1 = Coop<C>::template sub_kp<K>(d1, w1);         \
     _Pragma("unroll") for (int i = 0; i < RW; i++) { w0[i] = b0 ? w0[i] : d0[i]; w1[i] = b1 ? w1[i] : d1[i]; }
-    if (Coop<C>::QCANON && canon >= 2) {
-        Coop<C>::canon_q(w0);
-        Coop<C>::canon_q(w1);
+    if (Coop<C>::QCANON && canon >= Coop<C>::QCANON_MIN) {
+        Coop<C>::canon_q(w0, qtab);
+        Coop<C>::canon_q(w1, qtab);
     } else {
         if constexpr (!Coop<C>::QCANON) {
             if (canon >= 3) { COOP_CANON_STEP(8) }
             if (canon >= 2) { COOP_CANON_STEP(4) }
         }
-        if (canon >= 1) { COOP_CANON_STEP(2) }
+        if (!(Coop<C>::QCANON && Coop<C>::QCANON_MIN <= 1) && canon >= 1) { COOP_CANON_STEP(2) }
         COOP_CANON_STEP(1)
     }
 #undef COOP_CANON_STEP
@@ -326,6 +352,13 @@ __global__ void __maxnreg__(Coop<C>::MAXREG) pairing_coop_kernel(const CoopArgs 
     const uint32_t gblock = blockIdx.x * COOP_GROUPS + group;      // 32-item group index
     const uint32_t item = gblock * COOP_ITEMS + lane;
 #define COOP_BAR() asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(COOP_ROLES * 32) : "memory")
+    const uint4* qtab = smem_all + (size_t)COOP_GROUPS * (COOP_CELLS * CELL + COOP_ROLES * 32 / 4);
+    if constexpr (Coop<C>::QTAB_UINT4 > 0) {
+        // q p table of canon_q: written by the first threads of every group with the same values (a group whose items are
+        // all beyond n leaves below, so no group may depend on another one's writes); ordered by the group barrier below
+        if ((int)(threadIdx.x % (COOP_ROLES * 32)) < Coop<C>::QTAB_UINT4)
+            ((uint4*)qtab)[threadIdx.x % (COOP_ROLES * 32)] = ((const uint4*)Coop<C>::qtab())[threadIdx.x % (COOP_ROLES * 32)];
+    }
     if (gblock * COOP_ITEMS >= a.n) return;          // a whole group without items (its named barrier is its own)
     const bool valid = item < a.n;
     const uint32_t fl = valid ? a.flags[item] : (uint32_t)(FL_DONE | FL_SKIP0 | FL_SKIP1);
@@ -409,7 +442,7 @@ __global__ void __maxnreg__(Coop<C>::MAXREG) pairing_coop_kernel(const CoopArgs 
             uint4* dp = cells + ((cur >> 2) & 255) * CELL;
             const uint32_t sk = (cur >> 27) & 3;
             const bool zero = ((sk & 1) && (fl & ((sk & 2) ? FL_SKIP1 : FL_SKIP0))), fp_only = (cur >> 29) & 1;
-            coop_finish2<C>(r0, r1, R, I, cur, zp);
+            coop_finish2<C>(r0, r1, R, I, cur, zp, qtab);
             if ((sk & 1) || fp_only) {
 #pragma unroll
                 for (int i = 0; i < N; i++) { r0[i] = zero ? 0u : r0[i]; r1[i] = (zero || fp_only) ? 0u : r1[i]; }
@@ -474,7 +507,8 @@ template <class C> constexpr size_t coop_gscratch_bytes(size_t n) {
     return ((n + per_block - 1) / per_block) * COOP_GROUPS * Coop<C>::PARK * COOP_ROLES * (2 * (Coop<C>::N / 4) * 32) * sizeof(uint4);
 }
 template <class C> constexpr size_t coop_smem_bytes() {
-    return Coop<C>::GROUPS * ((size_t)COOP_CELLS * (2 * (Coop<C>::N / 4) * 32) * sizeof(uint4) + COOP_ROLES * 32 * sizeof(uint32_t));
+    return Coop<C>::GROUPS * ((size_t)COOP_CELLS * (2 * (Coop<C>::N / 4) * 32) * sizeof(uint4) + COOP_ROLES * 32 * sizeof(uint32_t)) +
+           Coop<C>::QTAB_UINT4 * sizeof(uint4);
 }
 
 }  // namespace bbs

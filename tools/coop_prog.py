@@ -31,8 +31,11 @@ C_END, C_REP, C_ENDREP, C_NEXTLINE, C_BAR, C_GSAVE, C_GLOAD, C_CHECK, C_INV = ra
 F_C0, F_C1, F_SUM, F_DIFF = range(4)
 FORM_BOUND = {F_C0: 1, F_C1: 1, F_SUM: 2, F_DIFF: 2}     # in units of p (cells are canonical)
 LINE_BASE = 128        # global-constant ids >= LINE_BASE address the line table relative to the line counter
-KP_MULT = (0, 8, 24, 40)         # KP[k] = KP_MULT[k] * p^2, added before REDC so the accumulator is >= 0   (BLS12-381)
-CANON_STEPS = (1, 2, 3, 4)       # canon level l: output < 2^(l+1) p, conditional subtractions of 2^l p ... p
+KP_HI = (0, 1, 2, 3, 4, 5, 6, 7)  # BLS12-381: KP[k] = KP_HI[k] * p * R, added before REDC so the accumulator is >= 0.  A multiple
+                                 # of R touches only the HIGH half of the accumulator (13-word addition of k p instead of 25 words)
+QP_ROWS = 10                     # BLS12-381: a reduction result is < R < 10 p; the kernel subtracts q^ p from a table (canon_q)
+CANON_STEPS = (1, 2, 3, 4)       # canon level l: output < 2^(l+1) p; level 0: one conditional subtraction of p, above: canon_q
+                                 # (BLS12-381: quotient estimate + table of q p; the step ladder 2^l p ... p remains as fallback)
 # BN254: xi = 9 + u is applied to the ACCUMULATORS (instruction XI: (R, I) <- (9R - I, 9I + R)), so sums reach a few
 # hundred p^2; the reduction there returns N+1 limbs (< 128 p) and canonicalises in up to 7 steps
 KP_MULT_WIDE = (0, 8, 16, 32, 64, 128, 256, 512)
@@ -100,7 +103,8 @@ class Curve:
 
     @property
     def kp_mult(self):
-        return KP_MULT_WIDE if self.wide else KP_MULT
+        """KP table in units of p^2"""
+        return KP_MULT_WIDE if self.wide else tuple(Fraction(k * self.R, self.p) for k in KP_HI)
 
     @property
     def canon_steps(self):
@@ -632,7 +636,8 @@ class Emulator:
         self.lines = [[(self.mont(c[0]), self.mont(c[1])) for c in ln] for ln in lines]
         self.cells = {}
         self.gscratch = {}
-        self.kp = [m * p * p for m in curve.kp_mult]
+        self.kp = [int(m * p * p) for m in curve.kp_mult]
+        assert all(k == m * p * p for k, m in zip(self.kp, curve.kp_mult))
         self.max_out = 0
         self.n_intervals = 0
 

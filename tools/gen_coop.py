@@ -380,6 +380,22 @@ def check_canon_q(p, trials=200000):
         assert q in (w // p, w // p - 1), (w, q)
 
 
+def check_canon_q_bls(p, trials=200000):
+    """pairing_coop.cuh Coop<Bls>::canon_q: for every 12-word w the estimate q^ = (w[11] * M) >> 56,
+    M = floor(2^56 / ((p >> 352) + 1)), is q or q - 1 with q = floor(w / p) < 10"""
+    M = (1 << 56) // ((p >> 352) + 1)
+    assert M == 165164498 and M < 1 << 32
+    R = 1 << 384
+    assert 9 * p < R < 10 * p
+    rnd = random.Random(78)
+    cases = [k * p + d for k in range(11) for d in (-1, 0, 1, 1 << 352, -(1 << 352), (1 << 352) - 1) if 0 <= k * p + d < R]
+    cases += [R - 1, 0] + [rnd.randrange(R) for _ in range(trials)]
+    cases += [(v << 352) + d for v in (rnd.randrange(1 << 32) for _ in range(20000)) for d in (0, (1 << 352) - 1)]
+    for w in cases:
+        q = ((w >> 352) * M) >> 56
+        assert q in (w // p, w // p - 1) and q < 10, (w, q)
+
+
 def check_redc(n, p, trials=300):
     R = 1 << (32 * n)
     rnd = random.Random(200 + n)
@@ -548,6 +564,7 @@ def main():
         check_redc(n, p)
     check_redc_wide(8, P_BN, 127 * (1 << 256) // P_BN)
     check_canon_q(P_BN)
+    check_canon_q_bls(P_BLS)
     txt = emit_all()
     with open(OUT, "w") as f:
         f.write(txt)
