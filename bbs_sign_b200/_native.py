@@ -39,6 +39,8 @@ SYMBOLS = {
     "bbs_verify_batch_multi": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                          C.c_void_p]),
     "bbs_core_verify_batch_multi": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "bbs_core_proof_verify_batch_multi": (C.c_int, [C.c_void_p, C.c_size_t] + [C.c_void_p] * 8 + [C.c_size_t, C.c_void_p]),
+    "bbs_proof_verify_batch_multi": (C.c_int, [C.c_void_p, C.c_size_t] + [C.c_void_p] * 9 + [C.c_size_t, C.c_void_p]),
     "bbs_ctx_use_per_thread_pairing": (C.c_int, [C.c_void_p, C.c_int]),
     "bbs_ctx_set_rlc_windows": (C.c_int, [C.c_void_p, C.c_uint32]),
     "bbs_ctx_set_g1_split": (C.c_int, [C.c_void_p, C.c_size_t]),

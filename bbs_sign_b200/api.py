@@ -444,6 +444,54 @@ class IssuerSet:
             raise BbsError(f"bbs_core_verify_batch_multi failed ({rc}): {self.lib.bbs_last_error().decode()}")
         return st
 
+    def proof_verify_batch(self, item_issuer: Sequence[int], proofs, ph: bytes, disclosed_messages: Sequence[Sequence[bytes]],
+                           disclosed_indexes: Sequence[Sequence[int]]) -> np.ndarray:
+        """status[i] = `pks[item_issuer[i]].proof_verify(proofs[i], header, ph, disclosed_messages[i], disclosed_indexes[i])`
+        (proof_verify.rs:19-34)"""
+        n = len(proofs)
+        if len(item_issuer) != n:
+            raise BbsError("one issuer index per proof required")
+        st = np.full(n, 255, dtype=np.uint8)
+        bad = [len(disclosed_messages[i]) != len(disclosed_indexes[i]) for i in range(n)]
+        keep = [i for i in range(n) if not bad[i]]
+        if keep:
+            fixed, commit, commit_off, idx, dis_off = BatchContext._pack_proofs(self, [proofs[i] for i in keep],
+                                                                                [disclosed_indexes[i] for i in keep])
+            flat, moffs = _pack_ragged([m for i in keep for m in disclosed_messages[i]])
+            iss = np.ascontiguousarray(np.asarray([item_issuer[i] for i in keep], dtype=np.uint32))
+            phb = _buf(ph) if ph else None
+            out = np.full(len(keep), 255, dtype=np.uint8)
+            rc = self.lib.bbs_proof_verify_batch_multi(self._h, len(keep), _ptr(iss), _ptr(fixed), _ptr(commit), _ptr(commit_off),
+                                                       _ptr(idx), _ptr(flat), _ptr(moffs), _ptr(dis_off), _ptr(phb), len(ph), _ptr(out))
+            if rc != 0:
+                raise BbsError(f"bbs_proof_verify_batch_multi failed ({rc}): {self.lib.bbs_last_error().decode()}")
+            st[keep] = out
+        for i in range(n):
+            if bad[i]:
+                st[i] = BatchContext._length_error_status(self, proofs[i], disclosed_indexes[i])
+        return st
+
+    def core_proof_verify_batch(self, item_issuer: Sequence[int], proofs, ph: bytes, disclosed_scalars: Sequence[Sequence[bytes]],
+                                disclosed_indexes: Sequence[Sequence[int]]) -> np.ndarray:
+        """as proof_verify_batch with the disclosed messages already mapped to scalars (32-byte little-endian)"""
+        n = len(proofs)
+        if len(item_issuer) != n or any(len(disclosed_scalars[i]) != len(disclosed_indexes[i]) for i in range(n)):
+            raise BbsError("one issuer index per proof and one scalar per disclosed index required")
+        if not n:
+            return np.zeros(0, dtype=np.uint8)
+        fixed, commit, commit_off, idx, dis_off = BatchContext._pack_proofs(self, proofs, disclosed_indexes)
+        sc = np.frombuffer(b"".join(s for d in disclosed_scalars for s in d), dtype=np.uint8)
+        if sc.size == 0:
+            sc = np.zeros(1, np.uint8)
+        iss = np.ascontiguousarray(np.asarray(item_issuer, dtype=np.uint32))
+        phb = _buf(ph) if ph else None
+        st = np.full(n, 255, dtype=np.uint8)
+        rc = self.lib.bbs_core_proof_verify_batch_multi(self._h, n, _ptr(iss), _ptr(fixed), _ptr(commit), _ptr(commit_off), _ptr(idx),
+                                                        _ptr(sc), _ptr(dis_off), _ptr(phb), len(ph), _ptr(st))
+        if rc != 0:
+            raise BbsError(f"bbs_core_proof_verify_batch_multi failed ({rc}): {self.lib.bbs_last_error().decode()}")
+        return st
+
 
 @dataclass
 class ProofBytes:

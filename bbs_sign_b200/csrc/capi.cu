@@ -245,7 +245,7 @@ struct Impl {
         if (S) {
             a.item_issuer = (const uint32_t*)S->item_issuer.p;
             a.iss = IssuerSetView{(const uint32_t*)S->K.p, (const uint32_t*)S->flags.p, (const uint32_t*)S->lines.p,
-                                  S->line_stride, (uint32_t)S->n_issuers};
+                                  S->line_stride, (uint32_t)S->n_issuers, (const uint32_t*)S->domains.p};
         }
         PROF(c, 1, s);
         TRY((launch_verify_g1<C>(a, (uint32_t)n, s)));
@@ -374,12 +374,17 @@ struct Impl {
     static int core_proof_verify_dev(Ctx* c, size_t n, const uint8_t* d_proofs, const uint8_t* d_commit,
                                      const uint64_t* d_commit_off, const uint32_t* d_idx, const uint8_t* d_dis_scalars,
                                      const uint64_t* d_dis_off, const uint8_t* d_ph, size_t ph_len, uint8_t* d_status,
-                                     rt_stream_t s) {
+                                     rt_stream_t s, const IssuerSet* S = nullptr) {
         TRY(c->s_pair.reserve(n * 6 * C::Fp::N * 4));
         TRY(c->s_flags.reserve(n * 4));
         ProofG1Args a{c->view, d_proofs, d_commit, d_commit_off, d_idx, d_dis_scalars, d_dis_off, d_ph,
                       (uint32_t)ph_len, (uint32_t*)c->s_pair.p, (uint32_t*)c->s_flags.p, d_status};
-        if (n <= c->split_max) {
+        if (S) {                           // issuer sets go through the task split (kernels.cuh proof_task_*) at every size
+            a.item_issuer = (const uint32_t*)S->item_issuer.p;
+            a.iss = IssuerSetView{(const uint32_t*)S->K.p, (const uint32_t*)S->flags.p, (const uint32_t*)S->lines.p,
+                                  S->line_stride, (uint32_t)S->n_issuers, (const uint32_t*)S->domains.p};
+        }
+        if (S || n <= c->split_max) {
             TRY(c->s_g1t.reserve(n * 3 * C::Fp::N * 4));
             TRY(c->s_g1v.reserve(n * 3 * C::Fp::N * 4));
             TRY(c->s_g1f.reserve(n * 3 * C::Fp::N * 4));
@@ -391,7 +396,7 @@ struct Impl {
         TRY((launch_proof_g1<C>(a, (uint32_t)n, s)));
         c->launches += n ? (a.part_t1 ? 2 : 1) : 0;
         PROF(c, 2, s);
-        TRY(pairing_dev(c, n, d_status, s));
+        TRY(pairing_dev(c, n, d_status, s, S));
         PROF(c, 3, s);
         return BBS_OK;
     }
@@ -715,8 +720,9 @@ struct Impl {
     }
     static int proof_common(Ctx* c, size_t n, const uint8_t* proofs, const uint8_t* commit, const uint64_t* commit_off,
                             const uint32_t* idx, const uint64_t* dis_off, const uint8_t* ph, size_t ph_len,
-                            uint8_t* status) {
+                            uint8_t* status, IssuerSet* S = nullptr, const uint32_t* item_issuer = nullptr) {
         rt_stream_t s = c->stream;
+        if (S) TRY(stage(S->item_issuer, item_issuer, n * 4, s));
         TRY(stage(c->s_sigs, proofs, n * PROOF, s));
         TRY(stage(c->s_commit, commit, commit_off[n] * 32, s));
         TRY(stage(c->s_commit_off, commit_off, (n + 1) * 8, s));
@@ -727,18 +733,20 @@ struct Impl {
         TRY(core_proof_verify_dev(c, n, (const uint8_t*)c->s_sigs.p, (const uint8_t*)c->s_commit.p,
                                   (const uint64_t*)c->s_commit_off.p, (const uint32_t*)c->s_dis_idx.p,
                                   (const uint8_t*)c->s_dis_scalars.p, (const uint64_t*)c->s_dis_off.p,
-                                  (const uint8_t*)c->s_ph.p, ph_len, (uint8_t*)c->s_status.p, s));
+                                  (const uint8_t*)c->s_ph.p, ph_len, (uint8_t*)c->s_status.p, s, S));
         return finish_status(c, n, status);
     }
     static int core_proof_verify(Ctx* c, size_t n, const uint8_t* proofs, const uint8_t* commit, const uint64_t* commit_off,
                                  const uint32_t* idx, const uint8_t* dis_scalars, const uint64_t* dis_off,
-                                 const uint8_t* ph, size_t ph_len, uint8_t* status) {
+                                 const uint8_t* ph, size_t ph_len, uint8_t* status, IssuerSet* S = nullptr,
+                                 const uint32_t* item_issuer = nullptr) {
         TRY(stage(c->s_dis_scalars, dis_scalars, dis_off[n] * 32, c->stream));
-        return proof_common(c, n, proofs, commit, commit_off, idx, dis_off, ph, ph_len, status);
+        return proof_common(c, n, proofs, commit, commit_off, idx, dis_off, ph, ph_len, status, S, item_issuer);
     }
     static int proof_verify(Ctx* c, size_t n, const uint8_t* proofs, const uint8_t* commit, const uint64_t* commit_off,
                             const uint32_t* idx, const uint8_t* dis_msgs, const uint64_t* dis_msg_off,
-                            const uint64_t* dis_off, const uint8_t* ph, size_t ph_len, uint8_t* status) {
+                            const uint64_t* dis_off, const uint8_t* ph, size_t ph_len, uint8_t* status,
+                            IssuerSet* S = nullptr, const uint32_t* item_issuer = nullptr) {
         rt_stream_t s = c->stream;
         const size_t count = dis_off[n];
         TRY(stage(c->s_dis_msgs, dis_msgs, dis_msg_off[count], s));
@@ -746,7 +754,7 @@ struct Impl {
         TRY(c->s_dis_scalars.reserve(count * 32));
         TRY(h2s_dev(c, count, (const uint8_t*)c->s_dis_msgs.p, (const uint64_t*)c->s_dis_msg_off.p,
                     (uint8_t*)c->s_dis_scalars.p, s));
-        return proof_common(c, n, proofs, commit, commit_off, idx, dis_off, ph, ph_len, status);
+        return proof_common(c, n, proofs, commit, commit_off, idx, dis_off, ph, ph_len, status, S, item_issuer);
     }
 };
 
@@ -1060,6 +1068,29 @@ int bbs_core_verify_batch_multi(bbs_issuer_set* p, size_t n, const uint32_t* ite
     if (!item_issuer || !sigs || !status || (n_msgs && !scalars)) return arg_error("null");
     CHECK_COUNTS(n, n_msgs);
     DISPATCH_SET(S, verify_multi(S, n, item_issuer, sigs, scalars, nullptr, nullptr, n_msgs, status));
+}
+
+int bbs_core_proof_verify_batch_multi(bbs_issuer_set* p, size_t n, const uint32_t* item_issuer, const uint8_t* proofs,
+                                      const uint8_t* commit, const uint64_t* commit_off, const uint32_t* idx,
+                                      const uint8_t* dis_scalars, const uint64_t* dis_off, const uint8_t* ph, size_t ph_len,
+                                      uint8_t* status) {
+    IssuerSet* S = reinterpret_cast<IssuerSet*>(p);
+    if (!n) return BBS_OK;
+    if (!item_issuer || !proofs || !commit_off || !dis_off || !status) return arg_error("null");
+    CHECK_COUNTS(n, 1);
+    if (commit_off[n] > 0xffffffffull || dis_off[n] > 0xffffffffull) return arg_error("batch too large: flat counts must fit in 32 bits");
+    DISPATCH_SET(S, core_proof_verify(S->base, n, proofs, commit, commit_off, idx, dis_scalars, dis_off, ph, ph_len, status, S, item_issuer));
+}
+int bbs_proof_verify_batch_multi(bbs_issuer_set* p, size_t n, const uint32_t* item_issuer, const uint8_t* proofs,
+                                 const uint8_t* commit, const uint64_t* commit_off, const uint32_t* idx, const uint8_t* dis_msgs,
+                                 const uint64_t* dis_msg_off, const uint64_t* dis_off, const uint8_t* ph, size_t ph_len,
+                                 uint8_t* status) {
+    IssuerSet* S = reinterpret_cast<IssuerSet*>(p);
+    if (!n) return BBS_OK;
+    if (!item_issuer || !proofs || !commit_off || !dis_off || !dis_msg_off || !status) return arg_error("null");
+    CHECK_COUNTS(n, 1);
+    if (commit_off[n] > 0xffffffffull || dis_off[n] > 0xffffffffull) return arg_error("batch too large: flat counts must fit in 32 bits");
+    DISPATCH_SET(S, proof_verify(S->base, n, proofs, commit, commit_off, idx, dis_msgs, dis_msg_off, dis_off, ph, ph_len, status, S, item_issuer));
 }
 
 // ---- random-linear-combination batch mode ----------------------------------------------------------------

@@ -205,6 +205,7 @@ struct IssuerSetView {
                                 // (A, Bc) layout in the host simulation)
     uint32_t line_stride;
     uint32_t n_issuers;
+    const uint32_t* domains;    // n_issuers x 8 words: calculate_domain of issuer i (proof verification hashes it into the challenge)
 };
 
 struct IssDecodeArgs { const uint8_t* pks; uint32_t* W; uint32_t* flags; };
@@ -680,6 +681,8 @@ struct ProofG1Args {
     uint32_t* pair; uint32_t* flags; uint8_t* status;
     // split path (proof_g1_split_kernel + proof_g1_join_kernel): Jacobian T1, D*r3^, fixed-base part of T2; state bytes
     uint32_t* part_t1; uint32_t* part_v2; uint32_t* part_f; uint8_t* part_st;
+    // issuer sets (split path only): proof i is checked under issuer item_issuer[i]; K_i * c is variable-base then
+    const uint32_t* item_issuer; IssuerSetView iss;
 };
 template <class C> BBS_HD void proof_g1_item(const ProofG1Args& a, uint32_t i) {
     using F = typename C::Fp;
@@ -810,6 +813,15 @@ template <class C> BBS_HD uint8_t proof_shape(const ProofG1Args& a, uint32_t i, 
     if (dup) return ST_ERR_MALFORMED;     // the reference indexes out of bounds and panics (proof_verify.rs:179)
     return 0;
 }
+// the key-dependent inputs of proof i: K, domain and the identity flags (issuer sets: per item)
+template <class C> BBS_HD uint32_t proof_issuer(const ProofG1Args& a, uint32_t i, const uint32_t*& K, const uint32_t*& domain) {
+    K = a.ctx.K; domain = a.ctx.domain;
+    if (!a.item_issuer) return (a.ctx.w_inf ? ISS_W_INF : 0u) | (a.ctx.k_inf ? ISS_K_INF : 0u);
+    const uint32_t s = a.item_issuer[i];
+    if (s >= a.iss.n_issuers) return ISS_BAD;
+    K = a.iss.K + (size_t)s * G1A; domain = a.iss.domains + (size_t)s * 8;
+    return a.iss.flags[s];
+}
 template <class C> BBS_HD void proof_task_v1(const ProofG1Args& a, uint32_t i) {
     using F = typename C::Fp;
     constexpr int GB = C::G1_BYTES;
@@ -818,6 +830,10 @@ template <class C> BBS_HD void proof_task_v1(const ProofG1Args& a, uint32_t i) {
     ProofShape sh;
     const uint8_t err = proof_shape<C>(a, i, sh);
     if (err) { a.status[i] = err; a.flags[i] = FL_DONE; return; }
+    {
+        const uint32_t *Kp, *dom;
+        if (proof_issuer<C>(a, i, Kp, dom) & ISS_BAD) { a.status[i] = ST_ERR_MALFORMED; a.flags[i] = FL_DONE; return; }   // undecodable issuer key
+    }
     BBS_A16 uint32_t Ab[G1A], Bb[G1A], D[G1A], ecap[8], r1cap[8], r3cap[8], c[8];
     int pA = g1_decompress<C>(Ab, pf), pB = g1_decompress<C>(Bb, pf + GB), pD = g1_decompress<C>(D, pf + 2 * GB);
     bool ok = pA != PT_BAD && pB != PT_BAD && pD != PT_BAD;
@@ -844,6 +860,20 @@ template <class C> BBS_HD void proof_task_v2(const ProofG1Args& a, uint32_t i) {
     ProofShape sh;
     if (proof_shape<C>(a, i, sh)) return;
     BBS_A16 uint32_t D[G1A], r3cap[8], t[G1J];
+    if (a.item_issuer) {
+        // issuer sets: K_i has no window table, so K_i * c joins D * r3^ in one two-point multiplication
+        const uint32_t *Kp, *dom;
+        const uint32_t ifl = proof_issuer<C>(a, i, Kp, dom);
+        BBS_A16 uint32_t c[8], Ka[G1A];
+        const int pD = g1_decompress<C>(D, pf + 2 * GB);
+        if ((ifl & ISS_BAD) || pD == PT_BAD || !fr_from_le32<C>(r3cap, pf + 3 * GB + 64) || !fr_from_le32<C>(c, pf + 3 * GB + 96)) return;
+        bn_copy<2 * C::Fp::N>(Ka, Kp);
+        const uint32_t* pts[2] = {pD == PT_OK ? D : nullptr, (ifl & ISS_K_INF) ? nullptr : Ka};
+        const uint32_t* ks[2] = {r3cap, c};
+        g1_msm_scalar<C, 2>(t, pts, ks);
+        g1_copy<C>(a.part_v2 + (size_t)i * G1J, t);
+        return;
+    }
     if (g1_decompress<C>(D, pf + 2 * GB) != PT_OK || !fr_from_le32<C>(r3cap, pf + 3 * GB + 64)) return;   // V1 reports what is wrong
     g1_mul_scalar<C>(t, D, r3cap);
     g1_copy<C>(a.part_v2 + (size_t)i * G1J, t);
@@ -861,7 +891,7 @@ template <class C> BBS_HD void proof_task_f(const ProofG1Args& a, uint32_t i, ui
     // Bv*c = K*c + sum H_disclosed (c m), then sum H_undisclosed m^   (proof_verify.rs:165-182)
     fe_to_mont<Fr>(cm, c);
     g1_set_inf<C>(T2);
-    if (!cx.k_inf) tab_accumulate<C>(T2, cx, 0, c);
+    if (!a.item_issuer && !cx.k_inf) tab_accumulate<C>(T2, cx, 0, c);       // issuer sets: K_i * c is part of task V2
     for (uint64_t k = 0; k < sh.R; k++) {
         BBS_A16 uint32_t m[8];
         if (!fr_from_le32<C>(m, a.dis_scalars + (sh.db + k) * 32)) { *fbad = 1; return; }
@@ -885,7 +915,7 @@ template <class C> BBS_HD bool proof_join_head(const ProofG1Args& a, uint32_t i,
     if (fbad[i]) { a.status[i] = ST_ERR_MALFORMED; a.flags[i] = FL_DONE; return false; }
     g1_copy<C>(T1, a.part_t1 + (size_t)i * G1J);
     g1_copy<C>(T2, a.part_f + (size_t)i * G1J);
-    if (((st >> 4) & 3) == PT_OK) g1_add<C>(T2, T2, a.part_v2 + (size_t)i * G1J);
+    if (((st >> 4) & 3) == PT_OK || a.item_issuer) g1_add<C>(T2, T2, a.part_v2 + (size_t)i * G1J);
     return true;
 }
 // join, part 2: zinv = 1 / (Z(T1) Z(T2)) with identities counted as Z = 1; challenge (proof_gen.rs:272-328), comparison, flags
@@ -896,6 +926,8 @@ template <class C> BBS_HD void proof_join_tail(const ProofG1Args& a, uint32_t i,
     constexpr int GB = C::G1_BYTES;
     const uint8_t* pf = a.proofs + (size_t)i * (3 * GB + 128);
     const uint64_t db = a.dis_off[i], R = a.dis_off[i + 1] - db;
+    const uint32_t *Kp, *domain;
+    const uint32_t ifl = proof_issuer<C>(a, i, Kp, domain);
     Xmd48 x;
     x.begin();
     x.s.put_be64(R);
@@ -919,7 +951,7 @@ template <class C> BBS_HD void proof_join_tail(const ProofG1Args& a, uint32_t i,
         fe_sqr<F>(z2, zz); fe_mul<F>(aff, T2, z2); fe_mul<F>(z2, z2, zz); fe_mul<F>(aff + FPN, T2 + FPN, z2);
         g1_compress_affine<C>(enc, aff, i2); x.s.update(enc, GB);
     }
-    for (int q = 7; q >= 0; q--) x.s.update_words(&cx.domain[q], 1);
+    for (int q = 7; q >= 0; q--) x.s.update_words(&domain[q], 1);
     x.s.put_be64(a.ph_len);
     x.s.update(a.ph, a.ph_len);
     BBS_A16 uint32_t okm[12], c2[8], c[8];
@@ -928,7 +960,7 @@ template <class C> BBS_HD void proof_join_tail(const ProofG1Args& a, uint32_t i,
     limbs_from_le<8>(c, pf + 3 * GB + 96);
     if (!bn_eq<8>(c2, c)) { a.status[i] = ST_REJECT; a.flags[i] = FL_DONE; return; }      // proof_verify.rs:108-110: no pairing
     uint32_t fl = 0;
-    if ((st & 3) == PT_INF || cx.w_inf) fl |= FL_SKIP0;
+    if ((st & 3) == PT_INF || (ifl & ISS_W_INF)) fl |= FL_SKIP0;
     if (((st >> 2) & 3) == PT_INF) fl |= FL_SKIP1;
     a.flags[i] = fl;
 }

@@ -406,8 +406,8 @@ def bench_verify(env, args):
             "clocks": clocks,
             "kernels_ms": {"msg_to_scalars": float(kmean[0]), "verify_g1": float(kmean[1]), "pairing": float(kmean[2])},
             "roofline": roof,
-            "roofline_g1": imad_roofline(env, "verify_g1_kernel<Bls> (decompress + subgroup test of A, fixed-base MSM over the GLV tables, e*A, to affine)",
-                                         n, PRODUCTS_G1, float(kmean[1]), traffic_key="verify_g1_kernel<Bls>"),
+            "roofline_g1": imad_roofline(env, "verify_g1_split_kernel<Bls> + verify_g1_combine_kernel<Bls> (decompress + subgroup test of A and e*A | fixed-base MSM over the GLV tables, as two tasks per item; join: e*A - B to affine)",
+                                         n, PRODUCTS_G1, float(kmean[1]), traffic_key="verify_g1_split_kernel<Bls>"),
         }
     ctx.close()
     return out
@@ -475,8 +475,8 @@ def bench_proof(env, n, steps, warmup, seed=77):
                     "h2d_bytes_per_step": sum(int(w[k].nbytes) for k in keys), "d2h_bytes_per_step": int(n)},
             "gpu_launches": int(launches),
             "kernels_ms": {"msg_to_scalars": kt[0], "proof_g1": kt[1], "pairing": kt[2]},
-            "roofline": dict(imad_roofline(env, "whole step: h2s_item + proof_g1_item<Bls> + pairing_coop_kernel<Bls>", n, PRODUCTS_PROOF,
-                                           step_ms, traffic_key="proof_g1_item<Bls>"),
+            "roofline": dict(imad_roofline(env, "whole step: h2s_item + proof_g1_split_kernel<Bls> + proof_g1_join_kernel<Bls> + pairing_coop_kernel<Bls>", n, PRODUCTS_PROOF,
+                                           step_ms, traffic_key="proof_g1_split_kernel<Bls>"),
                              g1_kernel_frac=n * (PRODUCTS_PROOF - PRODUCTS_PAIRING) / (kt[1] * 1e-3) / env.peak_products() if kt[1] > 0 else None,
                              pairing_kernel_frac=n * PRODUCTS_PAIRING / (kt[2] * 1e-3) / env.peak_products() if kt[2] > 0 else None)}
 
@@ -560,7 +560,7 @@ def bench_bn254(env, n, steps, warmup, seed=5):
                     "h2d_bytes_per_step": int(sigs.nbytes + sc.nbytes), "d2h_bytes_per_step": int(n)},
             "gpu_launches": int(launches),
             "kernels_ms": {"verify_g1": kt[1], "pairing": kt[2]},
-            "roofline": dict(imad_roofline(env, "whole step: verify_g1_kernel<Bn> + pairing_coop_kernel<Bn>", n, PRODUCTS_BN254, step_ms,
+            "roofline": dict(imad_roofline(env, "whole step: verify_g1_split_kernel<Bn> + verify_g1_combine_kernel<Bn> + pairing_coop_kernel<Bn>", n, PRODUCTS_BN254, step_ms,
                                            traffic_key="pairing_coop_kernel<Bn>"),
                              pairing_kernel_frac=n * 2530000 / (kt[2] * 1e-3) / env.peak_products() if kt[2] > 0 else None)}
 

@@ -208,6 +208,18 @@ int bbs_verify_batch_multi(bbs_issuer_set* set, size_t n, const uint32_t* item_i
                            const uint8_t* msgs, const uint64_t* offsets, uint32_t n_msgs, uint8_t* status);
 int bbs_core_verify_batch_multi(bbs_issuer_set* set, size_t n, const uint32_t* item_issuer, const uint8_t* sigs,
                                 const uint8_t* msg_scalars, uint32_t n_msgs, uint8_t* status);
+/* bbs_proof_verify_batch_multi / bbs_core_proof_verify_batch_multi: proof i is `pks[item_issuer[i]].proof_verify(..)`
+ * (src/proof_verify.rs:19-34) / core_proof_verify under that key; everything else as bbs_proof_verify_batch /
+ * bbs_core_proof_verify_batch.  The issuer enters through its domain (challenge, src/proof_gen.rs:272-328),
+ * K_i = P1 + Q1 * domain_i (the K_i * c term of proof_verify_init, :165, a variable-base product here) and the lines of W_i. */
+int bbs_core_proof_verify_batch_multi(bbs_issuer_set* set, size_t n, const uint32_t* item_issuer, const uint8_t* proofs_fixed,
+                                      const uint8_t* commitments, const uint64_t* commit_off, const uint32_t* disclosed_idx,
+                                      const uint8_t* disclosed_scalars, const uint64_t* dis_off, const uint8_t* ph,
+                                      size_t ph_len, uint8_t* status);
+int bbs_proof_verify_batch_multi(bbs_issuer_set* set, size_t n, const uint32_t* item_issuer, const uint8_t* proofs_fixed,
+                                 const uint8_t* commitments, const uint64_t* commit_off, const uint32_t* disclosed_idx,
+                                 const uint8_t* dis_msgs, const uint64_t* dis_msg_off, const uint64_t* dis_off,
+                                 const uint8_t* ph, size_t ph_len, uint8_t* status);
 
 /* ---- random-linear-combination batch mode (the optional mode of the north star; not in the reference) ----------
  * One verdict for n signatures under the context's issuer key:

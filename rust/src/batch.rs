@@ -88,6 +88,13 @@ extern "C" {
                               offsets: *const u64, n_msgs: u32, status: *mut u8) -> i32;
     fn bbs_core_verify_batch_multi(set: *mut BbsIssuerSet, n: usize, item_issuer: *const u32, sigs: *const u8,
                                    msg_scalars: *const u8, n_msgs: u32, status: *mut u8) -> i32;
+    fn bbs_core_proof_verify_batch_multi(set: *mut BbsIssuerSet, n: usize, item_issuer: *const u32, proofs_fixed: *const u8,
+                                         commitments: *const u8, commit_off: *const u64, disclosed_idx: *const u32,
+                                         disclosed_scalars: *const u8, dis_off: *const u64, ph: *const u8, ph_len: usize,
+                                         status: *mut u8) -> i32;
+    fn bbs_proof_verify_batch_multi(set: *mut BbsIssuerSet, n: usize, item_issuer: *const u32, proofs_fixed: *const u8,
+                                    commitments: *const u8, commit_off: *const u64, disclosed_idx: *const u32, dis_msgs: *const u8,
+                                    dis_msg_off: *const u64, dis_off: *const u64, ph: *const u8, ph_len: usize, status: *mut u8) -> i32;
     fn bbs_rlc_partial_core(ctx: *mut BbsCtx, n: usize, sigs: *const u8, msg_scalars: *const u8, n_msgs: u32, seed: *const u8,
                             index_base: u64, parts_out: *mut u8, status: *mut u8) -> i32;
     fn bbs_rlc_partial(ctx: *mut BbsCtx, n: usize, sigs: *const u8, msgs: *const u8, offsets: *const u64, n_msgs: u32,
@@ -368,6 +375,18 @@ fn join_proof<E: Pairing, F: Field>(fixed: &[u8], commits: &[u8]) -> Proof<E, F>
 pub fn proof_verify_batch<E: Pairing, F: Field>(ctx: &BatchCtx, proofs: &[Proof<E, F>], ph: &[u8],
     disclosed_messages: &[&[&[u8]]], disclosed_indexes: &[&[usize]])
     -> Result<Vec<Result<bool, ItemError<ProofGenError>>>, BatchError> {
+    proof_verify_on(ProofTarget::Ctx(ctx.raw), proofs, ph, disclosed_messages, disclosed_indexes)
+}
+
+/// Where a proof batch is verified: under the one key of a context, or under a key per proof of an issuer set.
+enum ProofTarget<'a> {
+    Ctx(*mut BbsCtx),
+    Set(*mut BbsIssuerSet, &'a [u32]),
+}
+
+fn proof_verify_on<E: Pairing, F: Field>(target: ProofTarget, proofs: &[Proof<E, F>], ph: &[u8],
+    disclosed_messages: &[&[&[u8]]], disclosed_indexes: &[&[usize]])
+    -> Result<Vec<Result<bool, ItemError<ProofGenError>>>, BatchError> {
     let n = proofs.len();
     assert!(disclosed_messages.len() == n && disclosed_indexes.len() == n, "one message / index list per proof");
     // InvalidIndicesAndMessagesLength (src/proof_verify.rs:144-146) is a property of the two host-side lists; the index
@@ -405,9 +424,19 @@ pub fn proof_verify_batch<E: Pairing, F: Field>(ctx: &BatchCtx, proofs: &[Proof<
     }
     let mut st = vec![0u8; keep.len()];
     if !keep.is_empty() {
-        check(unsafe {
-            bbs_proof_verify_batch(ctx.raw, keep.len(), fixed.as_ptr(), commits.as_ptr(), coff.as_ptr(), idx.as_ptr(), flat.as_ptr(),
-                                   moffs.as_ptr(), doff.as_ptr(), ph.as_ptr(), ph.len(), st.as_mut_ptr())
+        check(match target {
+            ProofTarget::Ctx(raw) => unsafe {
+                bbs_proof_verify_batch(raw, keep.len(), fixed.as_ptr(), commits.as_ptr(), coff.as_ptr(), idx.as_ptr(), flat.as_ptr(),
+                                       moffs.as_ptr(), doff.as_ptr(), ph.as_ptr(), ph.len(), st.as_mut_ptr())
+            },
+            ProofTarget::Set(raw, item_issuer) => {
+                let iss: Vec<u32> = keep.iter().map(|&i| item_issuer[i]).collect();
+                unsafe {
+                    bbs_proof_verify_batch_multi(raw, keep.len(), iss.as_ptr(), fixed.as_ptr(), commits.as_ptr(), coff.as_ptr(),
+                                                 idx.as_ptr(), flat.as_ptr(), moffs.as_ptr(), doff.as_ptr(), ph.as_ptr(), ph.len(),
+                                                 st.as_mut_ptr())
+                }
+            }
         })?;
     }
     let mut out: Vec<Result<bool, ItemError<ProofGenError>>> =
@@ -526,6 +555,15 @@ impl IssuerSet {
         Ok(st.into_iter().map(signature_status).collect())
     }
 
+    /// `result[i]` is what `pks[item_issuer[i]].proof_verify(proofs[i], header, ph, disclosed_messages[i],
+    /// disclosed_indexes[i])` returns (src/proof_verify.rs:19-34).
+    pub fn proof_verify_batch<E: Pairing, F: Field>(&self, item_issuer: &[u32], proofs: &[Proof<E, F>], ph: &[u8],
+        disclosed_messages: &[&[&[u8]]], disclosed_indexes: &[&[usize]])
+        -> Result<Vec<Result<bool, ItemError<ProofGenError>>>, BatchError> {
+        assert!(item_issuer.len() == proofs.len());
+        proof_verify_on(ProofTarget::Set(self.raw, item_issuer), proofs, ph, disclosed_messages, disclosed_indexes)
+    }
+
     /// (bytes that grow with the number of issuers, shared bytes)
     pub fn memory_bytes(&self) -> (u64, u64) {
         let mut shared = 0u64;
@@ -569,7 +607,7 @@ fn _unused_bindings() {
         bbs_core_proof_gen_batch as usize, bbs_rlc_partial_core as usize, bbs_rlc_partial as usize, bbs_rlc_combine as usize,
         bbs_rlc_core_verify_batch as usize, bbs_msg_to_scalars_dev as usize, bbs_core_verify_batch_dev as usize,
         bbs_verify_batch_dev as usize, bbs_core_sign_batch_dev as usize, bbs_core_proof_verify_batch_dev as usize,
-        bbs_ctx_launch_count as usize, bbs_ctx_memory_bytes as usize, bbs_core_verify_batch_multi as usize, bbs_ctx_use_per_thread_pairing as usize,
+        bbs_ctx_launch_count as usize, bbs_ctx_memory_bytes as usize, bbs_core_verify_batch_multi as usize, bbs_core_proof_verify_batch_multi as usize, bbs_ctx_use_per_thread_pairing as usize,
         bbs_ctx_set_rlc_windows as usize, bbs_ctx_set_g1_split as usize, bbs_ctx_set_profiling as usize, bbs_ctx_kernel_times as usize, bbs_imad_peak as usize,
         bbs_selftest_field as usize, bbs_selftest_g1_mul as usize, bbs_selftest_pairing as usize,
     );

@@ -761,3 +761,69 @@ def case_multi_issuer(lib_path, curve_name, n_issuers=5, per_issuer=3, L=2):
     assert one.tolist() == [it[3] for it in mine]
     ctx.close()
     iset.close()
+
+
+def case_multi_issuer_proofs(lib_path, curve_name, n_issuers=3, L=3, disclosed=(0, 2), pairing_on=1):
+    """bbs_proof_verify_batch_multi: proof i is checked under pks[item_issuer[i]] (the key is `&self` of proof_verify too,
+    proof_verify.rs:19-34).  Every status equals the oracle's proof_verify under the claimed key: own-issuer proofs, a proof
+    checked under another issuer's key (its challenge no longer matches: the domain differs), forged fields, ragged
+    disclosure, the identity key, an off-subgroup key, an out-of-range issuer index; the scalar-level entry point agrees."""
+    suite, ocs = SUITES[curve_name]
+    header, ph = b"multi-proof", b"ph"
+    keys = [keypair(ocs, 20 + k) for k in range(n_issuers)]
+    all_pks = [ocs.g2_compress(pk) for _, pk in keys] + [ocs.g2_compress(off_subgroup_g2(ocs)), ocs.g2_compress(None)]
+    gens = O.create_generators_cached(ocs, L + 1, ocs.api_id)
+    iset = A.IssuerSet(suite, all_pks, header, generators=gens_bytes(ocs, gens), lib_path=lib_path)
+    assert iset.status.tolist() == [1] * n_issuers + [A.ST_ERR_MALFORMED, 1]
+    items = []                              # (claimed issuer, proof, disclosed messages, disclosed indexes, expected)
+    kinds = ["ok", "other-issuer", "challenge+1", "ok-none-disclosed", "wrong-msg", "Abar=identity", "ok-all-disclosed"]
+    n_pair = 0
+    for k in range(n_issuers):
+        sk, pk = keys[k]
+        for t, kind in enumerate(kinds):
+            dis = sorted(set(disclosed))
+            if kind == "ok-none-disclosed":
+                dis = []
+            elif kind == "ok-all-disclosed":
+                dis = list(range(L))
+            (pr, msgs), = make_proofs(ocs, sk, pk, header, ph, L, dis, 1, seed=f"mp{k}.{t}.")
+            p = O.Proof(pr.a_bar, pr.b_bar, pr.d, pr.e_cap, pr.r1_cap, pr.r3_cap, list(pr.commitments), pr.challenge)
+            dm = [msgs[j] for j in dis]
+            claimed = k
+            if kind == "other-issuer":
+                claimed = (k + 1) % n_issuers
+            elif kind == "challenge+1":
+                p.challenge = (p.challenge + 1) % ocs.r
+            elif kind == "wrong-msg":
+                dm[0] = dm[0] + b"!"
+            elif kind == "Abar=identity":
+                p.a_bar = None
+            csk, cpk = keys[claimed]
+            td = csk
+            if kind == "ok" and n_pair < pairing_on:
+                td, n_pair = None, n_pair + 1                          # a few through the oracle's pairing, the rest by trapdoor
+            want = int(O.proof_verify(ocs, cpk, p, header, ph, dm, dis, trapdoor_sk=td))
+            items.append((claimed, p, dm, dis, want))
+    (pr, msgs), = make_proofs(ocs, keys[0][0], keys[0][1], header, ph, L, sorted(set(disclosed)), 1, seed="mpx")
+    dis = sorted(set(disclosed))
+    dm = [msgs[j] for j in dis]
+    items.append((n_issuers, pr, dm, dis, A.ST_ERR_MALFORMED))                                  # the off-subgroup key
+    items.append((n_issuers + 1, pr, dm, dis, int(O.proof_verify(ocs, None, pr, header, ph, dm, dis))))   # identity key
+    items.append((n_issuers + 2, pr, dm, dis, A.ST_ERR_MALFORMED))                              # no such issuer
+    items.append((0, pr, dm, [0, L], A.ST_ERR_DISCLOSED_INDEX))                                 # the checks come first
+    random.Random(5).shuffle(items)
+    proofs = [A.ProofBytes.from_canonical(suite, O.proof_to_bytes(ocs, it[1])) for it in items]
+    got = iset.proof_verify_batch([it[0] for it in items], proofs, ph, [it[2] for it in items], [it[3] for it in items])
+    exp = [it[4] for it in items]
+    assert got.tolist() == exp, (curve_name, got.tolist(), exp)
+    assert exp.count(1) >= 3 * n_issuers - 1
+    dsc = [[ocs.scalar_le(x) for x in O.msg_to_scalars(ocs, it[2], ocs.api_id)] for it in items]
+    got2 = iset.core_proof_verify_batch([it[0] for it in items], proofs, ph, dsc, [it[3] for it in items])
+    assert got2.tolist() == exp
+    # the same proofs of issuer 1 through a dedicated context give the same verdicts
+    ctx, _ = make_ctx(lib_path, suite, ocs, keys[1][1], header, L, gens=gens)
+    mine = [k for k, it in enumerate(items) if it[0] == 1]
+    one = ctx.proof_verify_batch([proofs[k] for k in mine], ph, [items[k][2] for k in mine], [items[k][3] for k in mine])
+    assert one.tolist() == [exp[k] for k in mine]
+    ctx.close()
+    iset.close()

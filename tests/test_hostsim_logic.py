@@ -109,6 +109,11 @@ def test_multi_issuer_set(lib_path, curve):
 
 
 @pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_multi_issuer_proofs(lib_path, curve):
+    P.case_multi_issuer_proofs(lib_path, curve, n_issuers=2, pairing_on=0)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
 def test_small_tables(lib_path, curve, monkeypatch):
     """contexts built with BBS_CTX_SMALL_TABLES (8-bit windows, L2-resident tables) give byte-identical signatures, B points,
     proofs and verdicts"""

@@ -16,8 +16,8 @@ full() {  # name, kernel regex, bench arguments...
   ncu -i $OUT/prof_${name}_$TAG.ncu-rep --page raw --csv > $OUT/raw_${name}_$TAG.csv 2>/dev/null
 }
 full coop 'pairing_coop_kernel' --extras ''
-full verify_g1 'verify_g1_kernel' --extras ''
-full proof_g1 "proof_g1_item" --workload proof --n 65536
+full verify_g1 'verify_g1_split_kernel' --extras ''
+full proof_g1 "proof_g1_split_kernel" --workload proof --n 65536
 full sign 'sign_kernel' --workload sign --n 524288
 full rlc_prep 'rlc_prep_kernel' --workload rlc --n 524288
 ls -la $OUT | tail -20
