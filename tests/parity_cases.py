@@ -810,7 +810,7 @@ def case_multi_issuer_proofs(lib_path, curve_name, n_issuers=3, L=3, disclosed=(
     items.append((n_issuers, pr, dm, dis, A.ST_ERR_MALFORMED))                                  # the off-subgroup key
     items.append((n_issuers + 1, pr, dm, dis, int(O.proof_verify(ocs, None, pr, header, ph, dm, dis))))   # identity key
     items.append((n_issuers + 2, pr, dm, dis, A.ST_ERR_MALFORMED))                              # no such issuer
-    items.append((0, pr, dm, [0, L], A.ST_ERR_DISCLOSED_INDEX))                                 # the checks come first
+    items.append((0, pr, dm[:2], [0, L], A.ST_ERR_DISCLOSED_INDEX))                             # the checks come first
     random.Random(5).shuffle(items)
     proofs = [A.ProofBytes.from_canonical(suite, O.proof_to_bytes(ocs, it[1])) for it in items]
     got = iset.proof_verify_batch([it[0] for it in items], proofs, ph, [it[2] for it in items], [it[3] for it in items])

@@ -277,6 +277,13 @@ def test_multi_issuer_set(lib, curve):
 
 
 @pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_multi_issuer_proofs(lib, curve):
+    """bbs_proof_verify_batch_multi: a proof batch naming a different issuer per item, against the oracle per item"""
+    P.case_multi_issuer_proofs(None, curve, n_issuers=3, pairing_on=1)
+    P.case_multi_issuer_proofs(None, curve, n_issuers=2, L=5, disclosed=(1, 3, 4), pairing_on=0)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
 def test_small_tables(lib, curve, monkeypatch):
     """contexts built with BBS_CTX_SMALL_TABLES (8-bit windows, L2-resident tables) give byte-identical signatures, B points,
     proofs and verdicts"""
