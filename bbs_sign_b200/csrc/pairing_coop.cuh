@@ -87,6 +87,7 @@ template <> struct Coop<Bls> {
     }
     static constexpr bool WARP_INV = true;     // INV shares one inversion among the 32 lanes (coop_warp_inverse): -4.5 %
     static constexpr bool WARP_INV_PRO = false;
+    static constexpr bool REP_SMEM = false;
     static constexpr int KPW = 12;             // KP[k] = k p R: the table holds k p, added to the high half of the accumulator
     static __device__ __forceinline__ void add_kp(uint32_t* acc, const uint32_t* k) { coop_acc_add_hi12(acc, k); }
     static __device__ __forceinline__ void xi(uint32_t*, uint32_t*) {}
@@ -129,6 +130,7 @@ template <> struct Coop<Bn> {
     // instruction: inside the interpreter loop the call makes ptxas re-allocate this kernel's 80 registers (+4.8 %)
     static constexpr bool WARP_INV = false;
     static constexpr bool WARP_INV_PRO = true;
+    static constexpr bool REP_SMEM = true;
     static __device__ __forceinline__ const uint32_t* prog() { return COOP_PROG_BN; }
     static __device__ __forceinline__ const uint32_t* prog_off() { return COOP_PROG_OFF_BN; }
     static __device__ __forceinline__ const uint32_t* consts() { return COOP_CONSTS_BN; }
@@ -347,12 +349,12 @@ __global__ void __maxnreg__(Coop<C>::MAXREG) pairing_coop_kernel(const CoopArgs 
     constexpr int CELL = 2 * Q * 32;           // uint4 per cell
     extern __shared__ uint4 smem_all[];
     const int lane = threadIdx.x & 31, role = (threadIdx.x >> 5) % COOP_ROLES, group = threadIdx.x / (COOP_ROLES * 32);
-    uint4* smem = smem_all + (size_t)group * (COOP_CELLS * CELL + COOP_ROLES * 32 / 4);
+    uint4* smem = smem_all + (size_t)group * (COOP_CELLS * CELL + COOP_ROLES * 32 / 4 + COOP_ROLES);
     uint32_t* votes = (uint32_t*)(smem + COOP_CELLS * CELL);      // [role][lane]
     const uint32_t gblock = blockIdx.x * COOP_GROUPS + group;      // 32-item group index
     const uint32_t item = gblock * COOP_ITEMS + lane;
 #define COOP_BAR() asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(COOP_ROLES * 32) : "memory")
-    const uint4* qtab = smem_all + (size_t)COOP_GROUPS * (COOP_CELLS * CELL + COOP_ROLES * 32 / 4);
+    const uint4* qtab = smem_all + (size_t)COOP_GROUPS * (COOP_CELLS * CELL + COOP_ROLES * 32 / 4 + COOP_ROLES);
     if constexpr (Coop<C>::QTAB_UINT4 > 0) {
         // q p table of canon_q: written by the first threads of every group with the same values (a group whose items are
         // all beyond n leaves below, so no group may depend on another one's writes); ordered by the group barrier below
@@ -400,7 +402,11 @@ __global__ void __maxnreg__(Coop<C>::MAXREG) pairing_coop_kernel(const CoopArgs 
 
     const uint32_t* prog = Coop<C>::prog() + Coop<C>::prog_off()[role];
     uint32_t pc = 0, line = 0;
-    uint32_t rep_pc[2], rep_cnt[2];
+    // REP / ENDREP state (two nesting levels): in registers, or in shared memory (Coop<C>::REP_SMEM) -- it is touched ~1,000
+    // times per item against ~23,000 EP / FIN.  Measured: BN254 (80-register cap) -1.0 % in shared memory; BLS12-381 +3.7 %
+    // although its 8-byte spill in the EP path disappears (ptxas schedules the loop differently), so it keeps registers.
+    volatile uint32_t* rep = votes + COOP_ROLES * 32 + role * 4;       // [pc0, cnt0, pc1, cnt1] of this role-warp
+    uint32_t rep_pc[2] = {0, 0}, rep_cnt[2] = {0, 0};
     int rep_sp = 0;
     uint32_t R[2 * N + 1], I[2 * N + 1];
 #pragma unroll
@@ -456,9 +462,20 @@ __global__ void __maxnreg__(Coop<C>::MAXREG) pairing_coop_kernel(const CoopArgs 
             // ---- CTL -----------------------------------------------------------------------------------------
             const uint32_t sub = (cur >> 2) & 15, arg = cur >> 6;
             if (sub == 0) break;                                           // END
-            if (sub == 1) { rep_pc[rep_sp] = pc; rep_cnt[rep_sp] = arg; rep_sp++; }           // REP
+            if (sub == 1) {                                                // REP
+                if constexpr (Coop<C>::REP_SMEM) { if (lane == 0) { rep[2 * rep_sp] = pc; rep[2 * rep_sp + 1] = arg; } __syncwarp(); }
+                else { rep_pc[rep_sp] = pc; rep_cnt[rep_sp] = arg; }
+                rep_sp++;
+            }
             else if (sub == 2) {                                           // ENDREP
-                if (--rep_cnt[rep_sp - 1] > 0) { pc = rep_pc[rep_sp - 1]; ins = __ldg(prog + pc); } else rep_sp--;
+                if constexpr (Coop<C>::REP_SMEM) {
+                    const uint32_t left = rep[2 * rep_sp - 1] - 1;
+                    __syncwarp();
+                    if (left > 0) { if (lane == 0) rep[2 * rep_sp - 1] = left; pc = rep[2 * rep_sp - 2]; ins = __ldg(prog + pc); } else rep_sp--;
+                    __syncwarp();
+                } else {
+                    if (--rep_cnt[rep_sp - 1] > 0) { pc = rep_pc[rep_sp - 1]; ins = __ldg(prog + pc); } else rep_sp--;
+                }
             }
             else if (sub == 3) line++;                                     // NEXTLINE
             else if (sub == 4) COOP_BAR();                            // BAR
@@ -507,7 +524,8 @@ template <class C> constexpr size_t coop_gscratch_bytes(size_t n) {
     return ((n + per_block - 1) / per_block) * COOP_GROUPS * Coop<C>::PARK * COOP_ROLES * (2 * (Coop<C>::N / 4) * 32) * sizeof(uint4);
 }
 template <class C> constexpr size_t coop_smem_bytes() {
-    return Coop<C>::GROUPS * ((size_t)COOP_CELLS * (2 * (Coop<C>::N / 4) * 32) * sizeof(uint4) + COOP_ROLES * 32 * sizeof(uint32_t)) +
+    return Coop<C>::GROUPS * ((size_t)COOP_CELLS * (2 * (Coop<C>::N / 4) * 32) * sizeof(uint4) + COOP_ROLES * 32 * sizeof(uint32_t) +
+                              COOP_ROLES * 4 * sizeof(uint32_t)) +
            Coop<C>::QTAB_UINT4 * sizeof(uint4);
 }
 
