@@ -428,7 +428,7 @@ def emit_all():
          "#pragma once", "#include <stdint.h>", "#ifdef __CUDACC__", ""]
     for n in (8, 12):
         for odd in (False, True):
-            prog, top = wmul_prog(n, odd)
+            prog, top = wmul_prog(n, odd, int(os.environ.get('COOP_ROWS_PER_STMT_%d' % n, 3)))
             nm = "o" if odd else "e"
             s.append(f"// {'odd' if odd else 'even'}-aligned half of the {n}x{n}-limb product, fresh ({top} words)")
             s.append(f"__device__ __forceinline__ void coop_wmul_{nm}{n}(uint32_t* w, const uint32_t* a, const uint32_t* b) {{")
