@@ -44,6 +44,7 @@ SYMBOLS = {
     "bbs_ctx_use_per_thread_pairing": (C.c_int, [C.c_void_p, C.c_int]),
     "bbs_ctx_set_rlc_windows": (C.c_int, [C.c_void_p, C.c_uint32]),
     "bbs_ctx_set_g1_split": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "bbs_ctx_set_pairing_split": (C.c_int, [C.c_void_p, C.c_size_t]),
     "bbs_msg_to_scalars": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bbs_core_verify_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "bbs_verify_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),

@@ -230,6 +230,10 @@ class BatchContext:
     def set_g1_split(self, max_items: int):
         self._check(self.lib.bbs_ctx_set_g1_split(self._h, max_items), "bbs_ctx_set_g1_split")
 
+    def set_pairing_split(self, max_items: int):
+        """test hook: batches of up to `max_items` (<= 32) items run the pairing kernel with two warps per role; 0 = never"""
+        self._check(self.lib.bbs_ctx_set_pairing_split(self._h, max_items), "bbs_ctx_set_pairing_split")
+
     def set_rlc_windows(self, windows: int):
         self._check(self.lib.bbs_ctx_set_rlc_windows(self._h, windows), "bbs_ctx_set_rlc_windows")
 

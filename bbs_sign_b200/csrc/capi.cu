@@ -65,6 +65,7 @@ struct Ctx {
     // grow-only scratch for the batch calls
     DevBuf s_rand, s_rand_off, s_sk, s_g1v, s_g1f, s_g1st, s_g1t;
     size_t split_max = 0;            // batches up to this size take the two-task G1 path (bbs_ctx_set_g1_split)
+    uint32_t pair_split_max = 32;    // batches up to this size (<= 32) run the pairing with two warps per role (bbs_ctx_set_pairing_split)
     DevBuf s_gscr, s_rlc_pt, s_rlc_sc, s_rlc_parts, s_rlc_bad, s_msm_pts, s_msm_kv, s_msm_idx, s_msm_entries, s_msm_buckets;
     DevBuf s_sigs, s_scalars, s_msgs, s_offsets, s_pair, s_flags, s_status, s_out, s_out2;
     DevBuf s_commit, s_commit_off, s_dis_idx, s_dis_scalars, s_dis_off, s_ph, s_dis_msgs, s_dis_msg_off;
@@ -218,7 +219,7 @@ struct Impl {
             TRY(c->s_gscr.reserve(coop_gscratch_size<C>(n)));
             CoopArgs ca{(const uint32_t*)(S ? S->lines.p : c->lines_coop.p), (const uint32_t*)c->s_pair.p,
                         (const uint32_t*)c->s_flags.p, d_status, (uint32_t*)c->s_gscr.p, (uint32_t)n, d_issuer,
-                        S ? S->line_stride : 0u};
+                        S ? S->line_stride : 0u, c->pair_split_max};
             TRY((launch_pairing_coop<C>(ca, s)));
             c->launches += n ? 1 : 0;
             return BBS_OK;
@@ -893,6 +894,12 @@ int bbs_ctx_set_rlc_windows(bbs_ctx* p, uint32_t windows) {
 int bbs_ctx_set_g1_split(bbs_ctx* p, size_t max_items) {
     if (!p) return arg_error("null context");
     as_ctx(p)->split_max = max_items;
+    return BBS_OK;
+}
+
+int bbs_ctx_set_pairing_split(bbs_ctx* p, size_t max_items) {
+    if (!p) return arg_error("null context");
+    as_ctx(p)->pair_split_max = (uint32_t)std::min<size_t>(max_items, 32);
     return BBS_OK;
 }
 

@@ -51,6 +51,7 @@ struct CoopArgs {
     uint32_t n;
     const uint32_t* item_issuer;   // MULTI kernel: item i reads the line table at lines + item_issuer[i] * line_stride
     uint32_t line_stride;
+    uint32_t split2_max;           // batches of up to this many items (<= 32) run the SPLIT = 2 kernel (two warps per role)
 };
 
 // ---- per-curve bindings of the generated primitives ---------------------------------------------------------
@@ -339,28 +340,92 @@ template <class C> __device__ __forceinline__ void coop_finish2(uint32_t* r0, ui
     for (int i = 0; i < N; i++) { r0[i] = w0[i]; r1[i] = w1[i]; }
 }
 
+// ONE output component (the SPLIT = 2 kernel: each warp of a role pair reduces one accumulator): M -> canonical Fp
+template <class C> __device__ __forceinline__ void coop_finish1(uint32_t* r, uint32_t* M, uint32_t ins, const uint4* zp, const uint4* qtab) {
+    constexpr int N = Coop<C>::N;
+    if ((ins >> 10) & 1) {                       // triple
+        uint32_t t[2 * N + 1];
+#pragma unroll
+        for (int i = 2 * N; i > 0; i--) t[i] = __funnelshift_l(M[i - 1], M[i], 1);
+        t[0] = M[0] << 1;
+        Coop<C>::add_e(M, t);
+        M[2 * N] += t[2 * N];
+    }
+    const uint32_t zs = (ins >> 11) & 3;
+    if (zs) {
+        uint32_t z[N];
+        coop_load<N>(z, zp);
+        if ((ins >> 13) & 1) coop_shl<N>(z, 1);
+        if (zs == 1) Coop<C>::add_hi(M, z); else Coop<C>::sub_hi(M, z);
+    }
+    const uint32_t kp = ((ins >> 22) & 3) | (((ins >> 31) & 1) << 2);
+    if (kp) {
+        constexpr int KPW = Coop<C>::KPW;
+        uint32_t k[KPW];
+        const uint32_t* kt = Coop<C>::kp() + kp * KPW;
+#pragma unroll
+        for (int i = 0; i < KPW; i++) k[i] = kt[i];
+        Coop<C>::add_kp(M, k);
+    }
+    constexpr int RW = Coop<C>::RW;
+    uint32_t w[RW];
+    Coop<C>::redc(w, M);
+    const uint32_t canon = ((ins >> 24) & 3) | (((ins >> 30) & 1) << 2);
+    uint32_t d[RW], b;
+#define COOP_CANON_STEP(K)                                                                     \
+    b = Coop<C>::template sub_kp<K>(d, w);                                                     \
+    _Pragma("unroll") for (int i = 0; i < RW; i++) w[i] = b ? w[i] : d[i];
+    if (Coop<C>::QCANON && canon >= Coop<C>::QCANON_MIN) {
+        Coop<C>::canon_q(w, qtab);
+    } else {
+        if constexpr (!Coop<C>::QCANON) {
+            if (canon >= 3) { COOP_CANON_STEP(8) }
+            if (canon >= 2) { COOP_CANON_STEP(4) }
+        }
+        if (!(Coop<C>::QCANON && Coop<C>::QCANON_MIN <= 1) && canon >= 1) { COOP_CANON_STEP(2) }
+        COOP_CANON_STEP(1)
+    }
+#undef COOP_CANON_STEP
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = w[i];
+}
+
 // MULTI: every lane (item) reads the line constants of its own issuer (issuer sets, kernels.cuh); the loads stay 128-bit
 // but are no longer warp-uniform, everything else is identical.
-template <class C, bool MULTI>
+// SPLIT = 2 (small batches: one block of up to 32 items, TWELVE warps): a role is a PAIR of warps.  With a handful of
+// items a role-warp has one or a few active lanes and the kernel is pure dependent-issue latency, so the work of a role is
+// cut in two: every EP of the stream carries a half tag (bit 31, tools/coop_prog.py) and is executed by that half only;
+// at a FIN the halves exchange one accumulator each through shared memory (half 0 ends up with the whole real sum, half
+// 1 with the whole imaginary sum; half 1 routes the EP signs crosswise, so "its" sum is always the first array), reduce ONE
+// component each and meet at a pair barrier before either reads the cell.  Same program, same results, about half the
+// latency.
+template <class C, bool MULTI, int SPLIT>
 __global__ void __maxnreg__(Coop<C>::MAXREG) pairing_coop_kernel(const CoopArgs a) {
-    constexpr int COOP_GROUPS = Coop<C>::GROUPS;
+    constexpr int COOP_GROUPS = SPLIT == 2 ? 1 : Coop<C>::GROUPS;
+    constexpr int GW = COOP_ROLES * SPLIT;     // warps per group
     constexpr int N = Coop<C>::N;
     constexpr int Q = N / 4;
     constexpr int CELL = 2 * Q * 32;           // uint4 per cell
     extern __shared__ uint4 smem_all[];
-    const int lane = threadIdx.x & 31, role = (threadIdx.x >> 5) % COOP_ROLES, group = threadIdx.x / (COOP_ROLES * 32);
-    uint4* smem = smem_all + (size_t)group * (COOP_CELLS * CELL + COOP_ROLES * 32 / 4 + COOP_ROLES);
+    const int lane = threadIdx.x & 31, wig = (threadIdx.x >> 5) % GW, role = wig % COOP_ROLES;
+    const int half = SPLIT == 2 ? wig / COOP_ROLES : 0;
+    const int group = threadIdx.x / (GW * 32);
+    uint4* smem = smem_all + (size_t)group * (COOP_CELLS * CELL + COOP_ROLES * 32 / 4 + GW);
     uint32_t* votes = (uint32_t*)(smem + COOP_CELLS * CELL);      // [role][lane]
     const uint32_t gblock = blockIdx.x * COOP_GROUPS + group;      // 32-item group index
     const uint32_t item = gblock * COOP_ITEMS + lane;
-#define COOP_BAR() asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(COOP_ROLES * 32) : "memory")
-    const uint4* qtab = smem_all + (size_t)COOP_GROUPS * (COOP_CELLS * CELL + COOP_ROLES * 32 / 4 + COOP_ROLES);
+#define COOP_BAR() asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(GW * 32) : "memory")
+#define COOP_PAIR_BAR() do { if constexpr (SPLIT == 2) asm volatile("bar.sync %0, 64;" ::"r"(8 + role) : "memory"); } while (0)
+    const uint4* qtab = smem_all + (size_t)COOP_GROUPS * (COOP_CELLS * CELL + COOP_ROLES * 32 / 4 + GW);
     if constexpr (Coop<C>::QTAB_UINT4 > 0) {
         // q p table of canon_q: written by the first threads of every group with the same values (a group whose items are
         // all beyond n leaves below, so no group may depend on another one's writes); ordered by the group barrier below
-        if ((int)(threadIdx.x % (COOP_ROLES * 32)) < Coop<C>::QTAB_UINT4)
-            ((uint4*)qtab)[threadIdx.x % (COOP_ROLES * 32)] = ((const uint4*)Coop<C>::qtab())[threadIdx.x % (COOP_ROLES * 32)];
+        if ((int)(threadIdx.x % (GW * 32)) < Coop<C>::QTAB_UINT4)
+            ((uint4*)qtab)[threadIdx.x % (GW * 32)] = ((const uint4*)Coop<C>::qtab())[threadIdx.x % (GW * 32)];
     }
+    // SPLIT = 2: exchange buffer of the role pairs, [role][half][word][lane]
+    uint32_t* xbuf = (uint32_t*)(qtab + Coop<C>::QTAB_UINT4);
+    (void)xbuf;
     if (gblock * COOP_ITEMS >= a.n) return;          // a whole group without items (its named barrier is its own)
     const bool valid = item < a.n;
     const uint32_t fl = valid ? a.flags[item] : (uint32_t)(FL_DONE | FL_SKIP0 | FL_SKIP1);
@@ -368,26 +433,28 @@ __global__ void __maxnreg__(Coop<C>::MAXREG) pairing_coop_kernel(const CoopArgs 
     const uint32_t* lines = a.lines;
     if constexpr (MULTI) lines += (size_t)((valid && !(fl & FL_DONE)) ? a.item_issuer[item] : 0u) * a.line_stride;
 
-    // prologue: f = 1 in slot 0 (cells 0..5), P0 -> cell 16, P1 -> cell 17 (x in c0, y in c1)
+    // prologue: f = 1 in slot 0 (cells 0..5), P0 -> cell 16, P1 -> cell 17 (x in c0, y in c1); by the first half of a pair
     {
         uint32_t v[N];
+        if (half == 0) {
 #pragma unroll
-        for (int i = 0; i < N; i++) v[i] = (role == 0) ? C::Fp::ONE()[i] : 0u;
-        coop_store<N>(cells + role * CELL, v);
+            for (int i = 0; i < N; i++) v[i] = (role == 0) ? C::Fp::ONE()[i] : 0u;
+            coop_store<N>(cells + role * CELL, v);
 #pragma unroll
-        for (int i = 0; i < N; i++) v[i] = 0u;
-        coop_store<N>(cells + role * CELL + Q * 32, v);
-        if (role < 4) {
-            // role r loads coordinate (r & 1) of point (r >> 1)
-            const uint32_t* src = a.pair + (size_t)(valid ? item : 0) * (6 * N) + (role >> 1) * 3 * N + (role & 1) * N;
+            for (int i = 0; i < N; i++) v[i] = 0u;
+            coop_store<N>(cells + role * CELL + Q * 32, v);
+            if (role < 4) {
+                // role r loads coordinate (r & 1) of point (r >> 1)
+                const uint32_t* src = a.pair + (size_t)(valid ? item : 0) * (6 * N) + (role >> 1) * 3 * N + (role & 1) * N;
 #pragma unroll
-            for (int i = 0; i < N; i++) v[i] = valid ? src[i] : 0u;
-            coop_store<N>(cells + (16 + (role >> 1)) * CELL + (role & 1) * Q * 32, v);
+                for (int i = 0; i < N; i++) v[i] = valid ? src[i] : 0u;
+                coop_store<N>(cells + (16 + (role >> 1)) * CELL + (role & 1) * Q * 32, v);
+            }
         }
         if constexpr (Coop<C>::POINT_RATIO) {
             // (x, y) -> (x / y, 1 / y), one point per role-warp (y != 0 on a curve of odd order; skipped pairs hold zeros)
             COOP_BAR();
-            if (role < 2) {
+            if (role < 2 && half == 0) {
                 BBS_A16 uint32_t x[N], y[N], yi[N];
                 coop_load<N>(x, cells + (16 + role) * CELL);
                 coop_load<N>(y, cells + (16 + role) * CELL + Q * 32);
@@ -405,9 +472,10 @@ __global__ void __maxnreg__(Coop<C>::MAXREG) pairing_coop_kernel(const CoopArgs 
     // REP / ENDREP state (two nesting levels): in registers, or in shared memory (Coop<C>::REP_SMEM) -- it is touched ~1,000
     // times per item against ~23,000 EP / FIN.  Measured: BN254 (80-register cap) -1.0 % in shared memory; BLS12-381 +3.7 %
     // although its 8-byte spill in the EP path disappears (ptxas schedules the loop differently), so it keeps registers.
-    volatile uint32_t* rep = votes + COOP_ROLES * 32 + role * 4;       // [pc0, cnt0, pc1, cnt1] of this role-warp
+    volatile uint32_t* rep = votes + COOP_ROLES * 32 + wig * 4;        // [pc0, cnt0, pc1, cnt1] of this warp
     uint32_t rep_pc[2] = {0, 0}, rep_cnt[2] = {0, 0};
     int rep_sp = 0;
+    // R, I: real / imaginary accumulator (SPLIT = 2, half 1: the other way round -- R is always the one this warp reduces)
     uint32_t R[2 * N + 1], I[2 * N + 1];
 #pragma unroll
     for (int i = 0; i <= 2 * N; i++) { R[i] = 0; I[i] = 0; }
@@ -421,6 +489,7 @@ __global__ void __maxnreg__(Coop<C>::MAXREG) pairing_coop_kernel(const CoopArgs 
         const uint32_t kind = cur & 3;
         if (kind == 0) {
             // ---- EP ------------------------------------------------------------------------------------------
+            if constexpr (SPLIT == 2) { if (((cur >> 31) & 1) != (uint32_t)half) continue; }       // the other half's product
             uint32_t x[N], y[N], w[2 * N], v[2 * N];
             coop_operand<C, false>(x, cells + ((cur >> 6) & 255) * CELL, (cur >> 14) & 3, (cur >> 16) & 3);
             const uint32_t yc = (cur >> 18) & 255;
@@ -431,7 +500,8 @@ __global__ void __maxnreg__(Coop<C>::MAXREG) pairing_coop_kernel(const CoopArgs 
             } else {
                 coop_operand<C, false>(y, cells + yc * CELL, (cur >> 26) & 3, (cur >> 28) & 3);
             }
-            const uint32_t sR = (cur >> 2) & 3, sI = (cur >> 4) & 3;
+            uint32_t sR = (cur >> 2) & 3, sI = (cur >> 4) & 3;
+            if constexpr (SPLIT == 2) { if (half) { const uint32_t t = sR; sR = sI; sI = t; } }
             // the two half products are independent carry chains: issued back to back they interleave on the IMAD pipe
             Coop<C>::wmul_e(w, x, y);
             Coop<C>::wmul_o(v, x, y);
@@ -440,23 +510,46 @@ __global__ void __maxnreg__(Coop<C>::MAXREG) pairing_coop_kernel(const CoopArgs 
             if (sI == 1) Coop<C>::add_e(I, w); else if (sI == 2) Coop<C>::sub_e(I, w);
         } else if (kind == 3) {
             // ---- XI: accumulators *= xi (curves whose xi is not a sign choice) ----------------------------------
-            if constexpr (Coop<C>::ACC_XI) Coop<C>::xi(R, I);
+            // (linear, so each half of a SPLIT = 2 pair applies it to its partial sums; half 1 holds them crosswise)
+            if constexpr (Coop<C>::ACC_XI) { if (SPLIT == 2 && half) Coop<C>::xi(I, R); else Coop<C>::xi(R, I); }
         } else if (kind == 1) {
             // ---- FIN -----------------------------------------------------------------------------------------
-            uint32_t r0[N], r1[N];
             const uint4* zp = cells + ((cur >> 14) & 255) * CELL;
             uint4* dp = cells + ((cur >> 2) & 255) * CELL;
             const uint32_t sk = (cur >> 27) & 3;
             const bool zero = ((sk & 1) && (fl & ((sk & 2) ? FL_SKIP1 : FL_SKIP0))), fp_only = (cur >> 29) & 1;
-            coop_finish2<C>(r0, r1, R, I, cur, zp, qtab);
-            if ((sk & 1) || fp_only) {
+            if constexpr (SPLIT == 2) {
+                // hand the accumulator this warp does not reduce to its partner, take the partner's share of the own one
+                uint32_t* xo = xbuf + ((role * 2 + half) * (2 * N + 1)) * 32 + lane;
 #pragma unroll
-                for (int i = 0; i < N; i++) { r0[i] = zero ? 0u : r0[i]; r1[i] = (zero || fp_only) ? 0u : r1[i]; }
+                for (int i = 0; i <= 2 * N; i++) xo[i * 32] = I[i];
+                COOP_PAIR_BAR();
+                const uint32_t* xi_ = xbuf + ((role * 2 + (half ^ 1)) * (2 * N + 1)) * 32 + lane;
+                uint32_t t[2 * N + 1];
+#pragma unroll
+                for (int i = 0; i <= 2 * N; i++) t[i] = xi_[i * 32];
+                Coop<C>::add_e(R, t);
+                R[2 * N] += t[2 * N];
+                uint32_t r[N];
+                coop_finish1<C>(r, R, cur, zp + half * Q * 32, qtab);
+                if ((sk & 1) || fp_only) {
+#pragma unroll
+                    for (int i = 0; i < N; i++) r[i] = (zero || (fp_only && half)) ? 0u : r[i];
+                }
+                coop_store<N>(dp + half * Q * 32, r);
+            } else {
+                uint32_t r0[N], r1[N];
+                coop_finish2<C>(r0, r1, R, I, cur, zp, qtab);
+                if ((sk & 1) || fp_only) {
+#pragma unroll
+                    for (int i = 0; i < N; i++) { r0[i] = zero ? 0u : r0[i]; r1[i] = (zero || fp_only) ? 0u : r1[i]; }
+                }
+                coop_store<N>(dp, r0);
+                coop_store<N>(dp + Q * 32, r1);
             }
-            coop_store<N>(dp, r0);
-            coop_store<N>(dp + Q * 32, r1);
 #pragma unroll
             for (int i = 0; i <= 2 * N; i++) { R[i] = 0; I[i] = 0; }
+            COOP_PAIR_BAR();                 // both components of the cell are visible to both halves; the exchange buffer is free
             if ((cur >> 26) & 1) COOP_BAR();
         } else {
             // ---- CTL -----------------------------------------------------------------------------------------
@@ -480,34 +573,42 @@ __global__ void __maxnreg__(Coop<C>::MAXREG) pairing_coop_kernel(const CoopArgs 
             else if (sub == 3) line++;                                     // NEXTLINE
             else if (sub == 4) COOP_BAR();                            // BAR
             else if (sub == 5 || sub == 6) {                               // GSAVE / GLOAD (own cell <-> global)
-                uint4* g = (uint4*)a.gscratch + (((size_t)gblock * Coop<C>::PARK + (arg >> 8)) * COOP_ROLES + role) * CELL + lane;
-                uint4* c = cells + (arg & 255) * CELL;
+                if (half == 0) {
+                    uint4* g = (uint4*)a.gscratch + (((size_t)gblock * Coop<C>::PARK + (arg >> 8)) * COOP_ROLES + role) * CELL + lane;
+                    uint4* c = cells + (arg & 255) * CELL;
 #pragma unroll
-                for (int q = 0; q < 2 * Q; q++) { if (sub == 5) g[q * 32] = c[q * 32]; else c[q * 32] = g[q * 32]; }
+                    for (int q = 0; q < 2 * Q; q++) { if (sub == 5) g[q * 32] = c[q * 32]; else c[q * 32] = g[q * 32]; }
+                }
+                COOP_PAIR_BAR();
             }
             else if (sub == 8) {                                           // INV: cell.c0 = cell.c0^-1 (one inversion per warp)
-                BBS_A16 uint32_t v[N], o[N];
-                coop_load<N>(v, cells + arg * CELL);
-                if constexpr (Coop<C>::WARP_INV) coop_warp_inverse<C>(o, v); else fe_inv<typename C::Fp>(o, v);
-                coop_store<N>(cells + arg * CELL, o);
+                if (half == 0) {
+                    BBS_A16 uint32_t v[N], o[N];
+                    coop_load<N>(v, cells + arg * CELL);
+                    if constexpr (Coop<C>::WARP_INV) coop_warp_inverse<C>(o, v); else fe_inv<typename C::Fp>(o, v);
+                    coop_store<N>(cells + arg * CELL, o);
+                }
                 // INV only ever follows a FIN (tools/coop_prog.py fp_inverse): the accumulators are zero here.  Saying so
                 // makes them dead across the call, so that nothing of the hot loop's state has to be spilled around it.
                 if constexpr (Coop<C>::WARP_INV) {
 #pragma unroll
                     for (int i = 0; i <= 2 * N; i++) { R[i] = 0; I[i] = 0; }
                 }
+                COOP_PAIR_BAR();
             }
             else if (sub == 7) {                                           // CHECK: result == 1 ?
-                uint32_t v[N], o = 0;
-                coop_load<N>(v, cells + arg * CELL);
+                if (half == 0) {
+                    uint32_t v[N], o = 0;
+                    coop_load<N>(v, cells + arg * CELL);
 #pragma unroll
-                for (int i = 0; i < N; i++) o |= v[i] ^ ((role == 0) ? C::Fp::ONE()[i] : 0u);
-                coop_load<N>(v, cells + arg * CELL + Q * 32);
+                    for (int i = 0; i < N; i++) o |= v[i] ^ ((role == 0) ? C::Fp::ONE()[i] : 0u);
+                    coop_load<N>(v, cells + arg * CELL + Q * 32);
 #pragma unroll
-                for (int i = 0; i < N; i++) o |= v[i];
-                votes[role * 32 + lane] = o;
+                    for (int i = 0; i < N; i++) o |= v[i];
+                    votes[role * 32 + lane] = o;
+                }
                 COOP_BAR();
-                if (role == 0) {
+                if (role == 0 && half == 0) {
                     uint32_t all = 0;
 #pragma unroll
                     for (int k = 0; k < COOP_ROLES; k++) all |= votes[k * 32 + lane];
@@ -523,10 +624,12 @@ template <class C> constexpr size_t coop_gscratch_bytes(size_t n) {
     const size_t per_block = (size_t)COOP_ITEMS * COOP_GROUPS;
     return ((n + per_block - 1) / per_block) * COOP_GROUPS * Coop<C>::PARK * COOP_ROLES * (2 * (Coop<C>::N / 4) * 32) * sizeof(uint4);
 }
-template <class C> constexpr size_t coop_smem_bytes() {
-    return Coop<C>::GROUPS * ((size_t)COOP_CELLS * (2 * (Coop<C>::N / 4) * 32) * sizeof(uint4) + COOP_ROLES * 32 * sizeof(uint32_t) +
-                              COOP_ROLES * 4 * sizeof(uint32_t)) +
-           Coop<C>::QTAB_UINT4 * sizeof(uint4);
+template <class C, int SPLIT = 1> constexpr size_t coop_smem_bytes() {
+    constexpr size_t groups = SPLIT == 2 ? 1 : Coop<C>::GROUPS, gw = COOP_ROLES * SPLIT;
+    return groups * ((size_t)COOP_CELLS * (2 * (Coop<C>::N / 4) * 32) * sizeof(uint4) + COOP_ROLES * 32 * sizeof(uint32_t) +
+                     gw * 4 * sizeof(uint32_t)) +
+           Coop<C>::QTAB_UINT4 * sizeof(uint4) +
+           (SPLIT == 2 ? (size_t)COOP_ROLES * 2 * (2 * Coop<C>::N + 1) * 32 * sizeof(uint32_t) : 0);
 }
 
 }  // namespace bbs

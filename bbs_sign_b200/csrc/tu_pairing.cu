@@ -18,18 +18,21 @@ template <class C> int launch_pairing(const PairingArgs& a, uint32_t n, rt_strea
 
 #ifndef BBS_HOSTSIM
 template <class C> size_t coop_gscratch_size(size_t n) { return coop_gscratch_bytes<C>(n); }
-template <class C, bool MULTI> static int launch_pairing_coop_t(const CoopArgs& a, rt_stream_t s) {
-    constexpr size_t smem = coop_smem_bytes<C>();
-    RT_CHECK(cudaFuncSetAttribute(pairing_coop_kernel<C, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RT_CHECK(cudaFuncSetAttribute(pairing_coop_kernel<C, MULTI>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    const uint32_t per_block = COOP_ITEMS * Coop<C>::GROUPS;
-    pairing_coop_kernel<C, MULTI><<<(a.n + per_block - 1) / per_block, COOP_ROLES * 32 * Coop<C>::GROUPS, smem, s>>>(a);
+template <class C, bool MULTI, int SPLIT> static int launch_pairing_coop_t(const CoopArgs& a, rt_stream_t s) {
+    constexpr size_t smem = coop_smem_bytes<C, SPLIT>();
+    RT_CHECK(cudaFuncSetAttribute(pairing_coop_kernel<C, MULTI, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RT_CHECK(cudaFuncSetAttribute(pairing_coop_kernel<C, MULTI, SPLIT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    const uint32_t groups = SPLIT == 2 ? 1 : Coop<C>::GROUPS, per_block = COOP_ITEMS * groups;
+    pairing_coop_kernel<C, MULTI, SPLIT><<<(a.n + per_block - 1) / per_block, COOP_ROLES * 32 * SPLIT * groups, smem, s>>>(a);
     RT_CHECK(cudaGetLastError());
     return 0;
 }
 template <class C> int launch_pairing_coop(const CoopArgs& a, rt_stream_t s) {
     if (a.n == 0) return 0;
-    return a.item_issuer ? launch_pairing_coop_t<C, true>(a, s) : launch_pairing_coop_t<C, false>(a, s);
+    // a batch that fits one group is latency-bound: two warps per role (pairing_coop.cuh, SPLIT = 2)
+    if (a.n <= COOP_ITEMS && a.n <= a.split2_max)
+        return a.item_issuer ? launch_pairing_coop_t<C, true, 2>(a, s) : launch_pairing_coop_t<C, false, 2>(a, s);
+    return a.item_issuer ? launch_pairing_coop_t<C, true, 1>(a, s) : launch_pairing_coop_t<C, false, 1>(a, s);
 }
 #endif
 

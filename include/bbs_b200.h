@@ -276,10 +276,13 @@ uint64_t bbs_ctx_memory_bytes(bbs_ctx* ctx);
  *   (8..32; 0 = the cost model's choice).
  * bbs_ctx_set_g1_split: verify / core_verify batches of up to max_items items run their G1 half as two tasks per item
  *   (variable-base and fixed-base part in parallel, then a join) instead of one thread per item; the default is SIZE_MAX
- *   (always: it is faster at every batch size measured), 0 selects the one-thread-per-item kernel. */
+ *   (always: it is faster at every batch size measured), 0 selects the one-thread-per-item kernel.
+ * bbs_ctx_set_pairing_split: batches of up to max_items (<= 32, the default) items run the cooperative pairing kernel with
+ *   TWO warps per role (a batch that fits one 32-item group is latency-bound: about half the time); 0 = always one. */
 int bbs_ctx_use_per_thread_pairing(bbs_ctx* ctx, int on);
 int bbs_ctx_set_rlc_windows(bbs_ctx* ctx, uint32_t windows);
 int bbs_ctx_set_g1_split(bbs_ctx* ctx, size_t max_items);
+int bbs_ctx_set_pairing_split(bbs_ctx* ctx, size_t max_items);
 
 /* ---- measurement hooks ------------------------------------------------------------------------------
  * With profiling on, every *_dev batch call records CUDA events on its launching stream around each of its

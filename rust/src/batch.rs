@@ -121,6 +121,7 @@ extern "C" {
     fn bbs_ctx_use_per_thread_pairing(ctx: *mut BbsCtx, on: i32) -> i32;
     fn bbs_ctx_set_rlc_windows(ctx: *mut BbsCtx, windows: u32) -> i32;
     fn bbs_ctx_set_g1_split(ctx: *mut BbsCtx, max_items: usize) -> i32;
+    fn bbs_ctx_set_pairing_split(ctx: *mut BbsCtx, max_items: usize) -> i32;
     fn bbs_ctx_set_profiling(ctx: *mut BbsCtx, on: i32) -> i32;
     fn bbs_ctx_kernel_times(ctx: *mut BbsCtx, ms: *mut f32, n: i32) -> i32;
     fn bbs_imad_peak(device: i32, iters: i32, mode: i32, gprod_per_s: *mut f64, ms: *mut f32) -> i32;
@@ -608,7 +609,7 @@ fn _unused_bindings() {
         bbs_rlc_core_verify_batch as usize, bbs_msg_to_scalars_dev as usize, bbs_core_verify_batch_dev as usize,
         bbs_verify_batch_dev as usize, bbs_core_sign_batch_dev as usize, bbs_core_proof_verify_batch_dev as usize,
         bbs_ctx_launch_count as usize, bbs_ctx_memory_bytes as usize, bbs_core_verify_batch_multi as usize, bbs_core_proof_verify_batch_multi as usize, bbs_ctx_use_per_thread_pairing as usize,
-        bbs_ctx_set_rlc_windows as usize, bbs_ctx_set_g1_split as usize, bbs_ctx_set_profiling as usize, bbs_ctx_kernel_times as usize, bbs_imad_peak as usize,
+        bbs_ctx_set_rlc_windows as usize, bbs_ctx_set_g1_split as usize, bbs_ctx_set_pairing_split as usize, bbs_ctx_set_profiling as usize, bbs_ctx_kernel_times as usize, bbs_imad_peak as usize,
         bbs_selftest_field as usize, bbs_selftest_g1_mul as usize, bbs_selftest_pairing as usize,
     );
 }

@@ -49,6 +49,7 @@ def gens_bytes(ocs, gens):
 
 
 G1_SPLIT = None             # None: the library default; else bbs_ctx_set_g1_split on every context make_ctx builds
+PAIRING_SPLIT = None        # None: the library default (batches of <= 32 items: two warps per role); else bbs_ctx_set_pairing_split
 SMALL_TABLES = False      # test_small_tables flips this: every context of a case is then built with BBS_CTX_SMALL_TABLES
 
 
@@ -60,6 +61,8 @@ def make_ctx(lib_path, suite, ocs, pk, header, L, api_id=None, gens=None):
                          lib_path=lib_path, small_tables=SMALL_TABLES)
     if G1_SPLIT is not None:
         ctx.set_g1_split(G1_SPLIT)
+    if PAIRING_SPLIT is not None:
+        ctx.set_pairing_split(PAIRING_SPLIT)
     return ctx, gens
 
 

@@ -308,3 +308,21 @@ def test_one_thread_per_item_g1_kernel(lib, curve, monkeypatch):
     P.case_verify(None, curve, 3, n=12, use_pairing_oracle_on=1)
     P.case_verify_malformed(None, curve)
     P.case_subgroup(None, curve)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_one_warp_per_role_pairing_kernel_on_small_batches(lib, curve, monkeypatch):
+    """batches of up to 32 items run the cooperative pairing kernel with two warps per role (every small case of this file);
+    here the same cases go through the one-warp-per-role kernel the large batches use (bbs_ctx_set_pairing_split(0))"""
+    monkeypatch.setattr(P, "PAIRING_SPLIT", 0)
+    P.case_verify(None, curve, 3, n=12, use_pairing_oracle_on=2)
+    P.case_verify(None, curve, 1, n=33, use_pairing_oracle_on=0)
+    P.case_proof_verify(None, curve, 4, [0, 2], n=8, pairing_on=1)
+    P.case_rlc(None, curve)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_two_warps_per_role_pairing_kernel_sizes(lib, curve):
+    """the SPLIT = 2 pairing kernel at its boundaries: 1, 31 and 32 items (33 is the first size of the other kernel)"""
+    for n in (1, 31, 32, 33):
+        P.case_verify(None, curve, 2, n=n, use_pairing_oracle_on=1 if n == 1 else 0)

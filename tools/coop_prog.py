@@ -30,6 +30,7 @@ K_EP, K_FIN, K_CTL, K_XI = 0, 1, 2, 3
 C_END, C_REP, C_ENDREP, C_NEXTLINE, C_BAR, C_GSAVE, C_GLOAD, C_CHECK, C_INV = range(9)
 F_C0, F_C1, F_SUM, F_DIFF = range(4)
 FORM_BOUND = {F_C0: 1, F_C1: 1, F_SUM: 2, F_DIFF: 2}     # in units of p (cells are canonical)
+EP_HALF = 1 << 31      # EP only: executed by the second warp of a role pair in the SPLIT = 2 kernel (ignored otherwise)
 LINE_BASE = 128        # global-constant ids >= LINE_BASE address the line table relative to the line counter
 KP_HI = (0, 1, 2, 3, 4, 5, 6, 7)  # BLS12-381: KP[k] = KP_HI[k] * p * R, added before REDC so the accumulator is >= 0.  A multiple
                                  # of R touches only the HIGH half of the accumulator (13-word addition of k p instead of 25 words)
@@ -213,7 +214,23 @@ class Builder:
 
     def finish(self):
         self.ctl_all(C_END)
-        return [list(s) for s in self.streams]
+        return [self._tag_halves(s) for s in self.streams]
+
+    @staticmethod
+    def _tag_halves(stream):
+        """EP_HALF bit for the kernel's two-warps-per-role variant (small batches, pairing_coop.cuh SPLIT = 2): the EPs
+        between two FINs alternate between the halves of the pair; each half accumulates its share, the FIN adds the
+        shares (exact: integer accumulators).  The one-warp kernel and the emulator ignore the bit."""
+        out, k = [], 0
+        for w in stream:
+            kind = w & 3
+            if kind == K_EP:
+                w |= (k & 1) << 31
+                k += 1
+            elif kind == K_FIN:
+                k = 0
+            out.append(w)
+        return out
 
 
 # ---- Fp2-level decompositions into EPs (Karatsuba, 3 EPs per Fp2 product) --------------------------------
