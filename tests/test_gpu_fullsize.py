@@ -152,3 +152,52 @@ def test_config5_bls_sign_and_rlc_524288(lib):
         assert out["value"] > 0 and out["checked"]
     finally:
         env.close()
+
+
+def test_chunked_host_signing_equals_one_shot(lib):
+    """bbs_sign_batch / bbs_core_sign_batch with >= 524,288 items go through the chunked, overlapped host-buffer path
+    (capi.cu sign_chunked): signatures, B points and statuses must equal those of one-shot calls on the two halves,
+    with a ragged tail, ragged message lengths and a few non-canonical scalars in the scalar-level call"""
+    import bench
+    from bbs_sign_b200 import api as A
+    L = 2
+    n = 2 * 262144 + 777
+    ctx = A.BatchContext(A.BLS12_381, bench.IRTF_PK, header=b"chunk", n_messages=L)
+    rng = np.random.default_rng(5)
+    lens = rng.integers(0, 9, size=n * L)
+    offs = np.zeros(n * L + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum(lens, dtype=np.uint64)
+    msgs = rng.integers(0, 256, size=int(offs[-1]) + 1, dtype=np.uint8)
+    sk = np.frombuffer(bench.IRTF_SK.to_bytes(32, "little"), dtype=np.uint8).copy()
+
+    def run(i0, i1):
+        cnt = i1 - i0
+        o = (offs[i0 * L: i1 * L + 1] - offs[i0 * L]).astype(np.uint64)
+        m = msgs[int(offs[i0 * L]): int(offs[i1 * L]) + 1].copy()
+        sig = np.zeros(cnt * bench.SIG_BYTES, dtype=np.uint8)
+        b = np.zeros(cnt * 48, dtype=np.uint8)
+        st = np.full(cnt, 255, dtype=np.uint8)
+        assert lib.bbs_sign_batch(ctx.handle, bench.ptr(sk), cnt, bench.ptr(m), bench.ptr(o), L, bench.ptr(sig), bench.ptr(b), bench.ptr(st)) == 0
+        return sig, b, st
+
+    sig, b, st = run(0, n)                      # chunked
+    h = n // 2 - 5
+    s0, b0, t0 = run(0, h)                      # one shot (below the threshold)
+    s1, b1, t1 = run(h, n)
+    assert np.array_equal(sig, np.concatenate([s0, s1])) and np.array_equal(b, np.concatenate([b0, b1]))
+    assert np.array_equal(st, np.concatenate([t0, t1])) and st.min() == 1
+    # scalar-level entry point, some scalars >= r
+    sc = rng.integers(0, 256, size=(n * L, 32), dtype=np.uint8)
+    sc[:, 31] &= 0x3f
+    bad = rng.choice(n, size=50, replace=False)
+    sc[bad * L + 1, :] = 0xff
+    sc = sc.reshape(-1)
+    sig2 = np.zeros(n * bench.SIG_BYTES, dtype=np.uint8)
+    st2 = np.full(n, 255, dtype=np.uint8)
+    assert lib.bbs_core_sign_batch(ctx.handle, bench.ptr(sk), n, bench.ptr(sc), L, bench.ptr(sig2), None, bench.ptr(st2)) == 0
+    sig3 = np.zeros(h * bench.SIG_BYTES, dtype=np.uint8)
+    st3 = np.full(h, 255, dtype=np.uint8)
+    assert lib.bbs_core_sign_batch(ctx.handle, bench.ptr(sk), h, bench.ptr(sc), L, bench.ptr(sig3), None, bench.ptr(st3)) == 0
+    assert np.array_equal(sig2[: h * bench.SIG_BYTES], sig3) and np.array_equal(st2[:h], st3)
+    assert sorted(np.nonzero(st2 != 1)[0].tolist()) == sorted(bad.tolist()) and set(st2[bad].tolist()) == {A.ST_ERR_MALFORMED}
+    ctx.close()
