@@ -830,3 +830,88 @@ def case_multi_issuer_proofs(lib_path, curve_name, n_issuers=3, L=3, disclosed=(
     assert one.tolist() == [exp[k] for k in mine]
     ctx.close()
     iset.close()
+
+
+def case_split_differential(lib_path, curve_name, n=48, seed=1):
+    """The G1 halves exist twice in the library: one thread per item (verify_g1_item / proof_g1_item) and as independent
+    tasks plus a join (verify_task_* / proof_task_*), where the statuses of an item are owned by different tasks.  Random
+    byte damage anywhere in the inputs (point encodings: flags, not on the curve, off the subgroup, identity; scalars:
+    non-canonical; commitments; disclosed scalars; disclosed indexes out of range or repeated) must give the SAME status
+    vector through both, and the undamaged items the oracle's verdict."""
+    suite, ocs = SUITES[curve_name]
+    rnd = random.Random(seed)
+    sk, pk = keypair(ocs, 3)
+    L, header, ph = 3, b"diff", b"p"
+    gens = O.create_generators_cached(ocs, L + 1, ocs.api_id)
+
+    def ctx_with(split):
+        c = A.BatchContext(suite, ocs.g2_compress(pk), header, generators=gens_bytes(ocs, gens), lib_path=lib_path)
+        c.set_g1_split(split)
+        return c
+
+    def damage(b: bytes, how: int) -> bytes:
+        b = bytearray(b)
+        if how == 1:                                  # one random bit anywhere
+            i = rnd.randrange(len(b)); b[i] ^= 1 << rnd.randrange(8)
+        elif how == 2:                                # a whole field set to 0xff (non-canonical scalar / x >= p)
+            f = rnd.randrange(len(b) // 16); b[16 * f: 16 * f + 16] = b"\xff" * 16
+        elif how == 3:                                # flag bits of the first byte
+            b[0] ^= rnd.choice([0x80, 0x40, 0x20])
+        elif how == 4:                                # a run of zero bytes
+            i = rnd.randrange(len(b) - 8); b[i: i + 8] = bytes(8)
+        return bytes(b)
+
+    # ---- signatures ----
+    msgs = [[rng_bytes(f"d{seed}.{i}.{j}", 16) for j in range(L)] for i in range(n)]
+    sigs = [O.signature_to_bytes(ocs, O.sign(ocs, sk, m, header)) for m in msgs]
+    scal = [b"".join(ocs.scalar_le(x) for x in O.msg_to_scalars(ocs, m, ocs.api_id)) for m in msgs]
+    clean = []
+    for i in range(n):
+        how = rnd.randrange(6)                        # 0 and 5: untouched
+        if how in (1, 2, 3, 4):
+            if rnd.random() < 0.6:
+                sigs[i] = damage(sigs[i], how)
+            else:
+                scal[i] = damage(scal[i], how)
+        else:
+            clean.append(i)
+    sg = np.frombuffer(b"".join(sigs), dtype=np.uint8)
+    sc = np.frombuffer(b"".join(scal), dtype=np.uint8)
+    res = []
+    for split in (0, 1 << 62):
+        c = ctx_with(split)
+        res.append(c.core_verify_batch(sg, sc, L).tolist())
+        c.close()
+    assert res[0] == res[1], (curve_name, "verify", res)
+    assert all(res[0][i] == 1 for i in clean) and len(set(res[0])) >= 2
+    # ---- proofs ----
+    base = make_proofs(ocs, sk, pk, header, ph, L, [0, 2], n, seed=f"dp{seed}.")
+    proofs, dsc, didx, clean = [], [], [], []
+    for i, (pr, m) in enumerate(base):
+        pb = A.ProofBytes.from_canonical(suite, O.proof_to_bytes(ocs, pr))
+        fixed, commit = pb.fixed, pb.commitments
+        d = [ocs.scalar_le(x) for x in O.msg_to_scalars(ocs, [m[0], m[2]], ocs.api_id)]
+        idx = [0, 2]
+        how = rnd.randrange(8)
+        if how in (1, 2, 3, 4):
+            r = rnd.random()
+            if r < 0.5:
+                fixed = damage(fixed, how)
+            elif r < 0.75:
+                commit = damage(commit, how)
+            else:
+                d[rnd.randrange(2)] = damage(d[0], how)
+        elif how == 5:
+            idx = [0, L + rnd.randrange(3)]            # out of range
+        elif how == 6:
+            idx = [2, 2]                              # repeated
+        else:
+            clean.append(i)
+        proofs.append(A.ProofBytes(fixed, commit)); dsc.append(d); didx.append(idx)
+    res = []
+    for split in (0, 1 << 62):
+        c = ctx_with(split)
+        res.append(c.core_proof_verify_batch(proofs, ph, dsc, didx).tolist())
+        c.close()
+    assert res[0] == res[1], (curve_name, "proof", res)
+    assert all(res[0][i] == 1 for i in clean) and len(set(res[0])) >= 3

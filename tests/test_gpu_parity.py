@@ -326,3 +326,9 @@ def test_two_warps_per_role_pairing_kernel_sizes(lib, curve):
     """the SPLIT = 2 pairing kernel at its boundaries: 1, 31 and 32 items (33 is the first size of the other kernel)"""
     for n in (1, 31, 32, 33):
         P.case_verify(None, curve, 2, n=n, use_pairing_oracle_on=1 if n == 1 else 0)
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_split_paths_agree_with_one_thread_paths_on_damaged_inputs(lib, curve):
+    for seed in (1, 2, 3):
+        P.case_split_differential(None, curve, n=64, seed=seed)

@@ -153,3 +153,8 @@ def test_public_key_keeps_a_bounded_number_of_contexts(lib_path):
     msgs = [[b"m"]]
     sig = P.O.signature_to_bytes(ocs, P.O.sign(ocs, sk, msgs[0], b"h1"))
     assert pk.verify_batch(np.frombuffer(sig, dtype=np.uint8).reshape(1, -1), b"h1", msgs).tolist() == [1]              # rebuilt on demand
+
+
+@pytest.mark.parametrize("curve", ["BLS12_381", "BN254"])
+def test_split_paths_agree_with_one_thread_paths_on_damaged_inputs(lib_path, curve):
+    P.case_split_differential(lib_path, curve, n=24, seed=2)
