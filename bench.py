@@ -8,13 +8,14 @@ key, 1/16 of them corrupted; weak scaling (65,536 per GPU).  Signatures are prod
 construction (valid -> 1, corrupted -> 0).
 
 `extra` (same line): the rest of the metric, STRONG-scaled (the total is fixed, every GPU takes total / N):
+  proof_l10  the metric's proof-verify leg at the headline's L: 524,288 proofs, L = 10, 5 disclosed (proof-verifies/s)
   proof  BASELINE configs[3]: 262,144 selective-disclosure proofs, L = 32, 16 disclosed   (proof-verifies/s)
   bn254  BASELINE configs[2]: 1,048,576 BN254 core_verify over 31 pre-hashed scalars       (verifies/s)
   sign   BASELINE configs[4], first leg: 4,194,304 signatures                              (signatures/s)
   rlc    BASELINE configs[4], second leg: ONE random-linear-combination verdict over 4,194,304 signatures
 
   python bench.py --gpus N --steps K --warmup W           our arm (torchrun for N > 1, one rank per GPU)
-  python bench.py --workload proof|bn254|sign|rlc ...     one workload as the line itself (ad-hoc runs, profiling)
+  python bench.py --workload proof|proof_l10|bn254|sign|rlc ...     one workload as the line itself (ad-hoc runs, profiling)
   python bench.py --impl reference ...                    CPU arm: the oracle port of the reference's path
 
 Prints ONE JSON line (rank 0)."""
@@ -49,7 +50,8 @@ PRODUCTS_PROOF = 27423 * 300 + 8521 * 234                   # 1.022e7  BLS12-381
 PRODUCTS_BN254 = 26874 * 136 + 5846 * 108                   # 4.29e6   BN254 core_verify, L = 31
 PRODUCTS_SIGN = 3616 * 300 + 3285 * 234                     # 1.85e6   BLS12-381 sign, L = 10
 PRODUCTS_RLC = 74000                                        # 7.4e4    per signature of an RLC batch (+ 70 SHA-256 blocks)
-TOTALS = {"proof": 262144, "bn254": 1 << 20, "sign": 1 << 22, "rlc": 1 << 22}     # BASELINE configs[3], [2], [4], [4]
+TOTALS = {"proof": 262144, "proof_l10": 524288, "bn254": 1 << 20, "sign": 1 << 22, "rlc": 1 << 22}   # BASELINE configs[3], metric's
+                                                                                   # proof leg at L = 10, configs[2], [4], [4]
 SIG_BYTES = 80
 MSG_BYTES = 32
 PROOF_FIXED = 3 * 48 + 128
@@ -413,12 +415,12 @@ def bench_verify(env, args):
     return out
 
 
-def bench_proof(env, n, steps, warmup, seed=77):
+def bench_proof(env, n, steps, warmup, seed=77, L=32, R=16):
     """BASELINE configs[3] shape: BLS12-381 batch proof_verify, L = 32 with 16 disclosed messages, n DISTINCT proofs per GPU
     (make_proof_workload).  A step = msg_to_scalars of the disclosed messages + core_proof_verify (G1 half with the
-    challenge hash, then the cooperative pairing kernel)."""
+    challenge hash, then the cooperative pairing kernel).  With L = 10, R = 5 it is the proof-verify leg of BASELINE.json's
+    headline metric ("verifies/sec & proof-verifies/sec, L=10")."""
     torch, lib, api = env.torch, env.lib, env.api
-    L, R = 32, 16
     ctx = api.BatchContext(api.BLS12_381, IRTF_PK, header=b"", n_messages=L, device=env.local)
     w = make_proof_workload(ctx, lib, n, seed + env.rank, L, R)
     expect = w["expect"]
@@ -464,21 +466,31 @@ def bench_proof(env, n, steps, warmup, seed=77):
     if env.rank != 0:
         return None
     step_ms = t / steps * 1e3
-    return {"metric": "bls12_381_bbs_proof_verifies_per_sec_L32_R16", "value": value, "unit": "proof-verifies/s",
+    config3 = (L, R) == (32, 16)
+    # the counting model of SURVEY Appendix D covers configs[3]; other shapes report the pairing kernel against its own count
+    products, g1_products = (PRODUCTS_PROOF, PRODUCTS_PROOF - PRODUCTS_PAIRING) if config3 else (None, None)
+    return {"metric": f"bls12_381_bbs_proof_verifies_per_sec_L{L}_R{R}", "value": value, "unit": "proof-verifies/s",
             "n_gpus": env.world, "n_total": env.world * n, "n_per_gpu": n, "steps": steps, "warmup": warmup, "ms_per_step": step_ms,
             "checked": True,
-            "config": {"workload": f"BLS12-381 batch proof_verify: {env.world * n} distinct proofs ({n} per GPU), L=32, 16 disclosed "
+            "config": {"workload": f"BLS12-381 batch proof_verify: {env.world * n} distinct proofs ({n} per GPU), L={L}, {R} disclosed "
                                    "32-B messages, one issuer key, made by bbs_sign_batch + bbs_proof_gen_batch, 1/16 corrupted over 7 "
-                                   "rejection classes (BASELINE configs[3])",
+                                   "rejection classes (" + ("BASELINE configs[3]" if config3 else "the proof-verify leg of BASELINE.json's "
+                                   "metric at the headline's L") + ")",
                        "l2": "256 MB flush write between timed iterations", "sharding": "by proof index, no collective"},
             "e2e": {"value": env.world * n * steps / te, "unit": "proof-verifies/s",
                     "h2d_bytes_per_step": sum(int(w[k].nbytes) for k in keys), "d2h_bytes_per_step": int(n)},
             "gpu_launches": int(launches),
             "kernels_ms": {"msg_to_scalars": kt[0], "proof_g1": kt[1], "pairing": kt[2]},
-            "roofline": dict(imad_roofline(env, "whole step: h2s_item + proof_g1_split_kernel<Bls> + proof_g1_join_kernel<Bls> + pairing_coop_kernel<Bls>", n, PRODUCTS_PROOF,
-                                           step_ms, traffic_key="proof_g1_split_kernel<Bls>"),
-                             g1_kernel_frac=n * (PRODUCTS_PROOF - PRODUCTS_PAIRING) / (kt[1] * 1e-3) / env.peak_products() if kt[1] > 0 else None,
+            "roofline": dict(imad_roofline(env, "whole step: h2s_item + proof_g1_split_kernel<Bls> + proof_g1_join_kernel<Bls> + pairing_coop_kernel<Bls>", n, products,
+                                           step_ms, traffic_key="proof_g1_split_kernel<Bls>") if config3 else
+                             imad_roofline(env, "pairing_coop_kernel<Bls> (the dominant kernel of the step)", n, PRODUCTS_PAIRING, kt[2],
+                                           traffic_key="pairing_coop_kernel<Bls>"),
+                             g1_kernel_frac=n * g1_products / (kt[1] * 1e-3) / env.peak_products() if config3 and kt[1] > 0 else None,
                              pairing_kernel_frac=n * PRODUCTS_PAIRING / (kt[2] * 1e-3) / env.peak_products() if kt[2] > 0 else None)}
+
+
+def bench_proof_l10(env, n, steps, warmup, seed=91):
+    return bench_proof(env, n, steps, warmup, seed=seed, L=10, R=5)
 
 
 def make_bn254_workload(ctx, lib, n, seed, L=31):
@@ -712,7 +724,7 @@ def bench_rlc(env, n, steps, warmup, L=10, seed=99):
                                       n, PRODUCTS_RLC, t / steps * 1e3, traffic_key="msm_bucket_kernel<Bls>")}
 
 
-EXTRAS = {"proof": bench_proof, "bn254": bench_bn254, "sign": bench_sign, "rlc": bench_rlc}
+EXTRAS = {"proof": bench_proof, "proof_l10": bench_proof_l10, "bn254": bench_bn254, "sign": bench_sign, "rlc": bench_rlc}
 
 
 def run_ours(args):
@@ -799,9 +811,9 @@ def main():
     ap.add_argument("--L", type=int, default=L_DEFAULT)
     ap.add_argument("--cpu-sample", type=int, default=0, help="signatures per CPU-baseline step (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="verify", choices=["verify", "proof", "rlc", "bn254", "sign"],
+    ap.add_argument("--workload", default="verify", choices=["verify", "proof", "proof_l10", "rlc", "bn254", "sign"],
                     help="verify = BASELINE configs[1] (the headline) with the other configs under `extra`")
-    ap.add_argument("--extras", default="proof,bn254,sign,rlc", help="comma list of extra workloads of the default run ('' = none)")
+    ap.add_argument("--extras", default="proof_l10,proof,bn254,sign,rlc", help="comma list of extra workloads of the default run ('' = none)")
     ap.add_argument("--extra-steps", type=int, default=3, help="timed steps per extra workload (at most --steps)")
     ap.add_argument("--extra-n", type=int, default=None, help="items per GPU for every extra workload (default: BASELINE total / N)")
     args = ap.parse_args()
