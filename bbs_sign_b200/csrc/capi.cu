@@ -234,11 +234,12 @@ struct Impl {
         return BBS_OK;
     }
 
-    static int core_verify_dev(Ctx* c, size_t n, const uint8_t* d_sigs, const uint8_t* d_scalars, uint32_t n_msgs,
-                               uint8_t* d_status, rt_stream_t s, const IssuerSet* S = nullptr) {
-        TRY(c->s_pair.reserve(n * 6 * C::Fp::N * 4));
-        TRY(c->s_flags.reserve(n * 4));
-        VerifyG1Args a{c->view, d_sigs, d_scalars, n_msgs, (uint32_t*)c->s_pair.p, (uint32_t*)c->s_flags.p, d_status};
+    // G1 half of core_verify for items [first, first + n) of a batch whose pair records / flags / statuses are indexed by the
+    // batch (scratch of the task split is per launch: reserve it for the largest launch BEFORE a chunked sequence starts)
+    static int verify_g1_dev(Ctx* c, size_t n, size_t first, const uint8_t* d_sigs, const uint8_t* d_scalars, uint32_t n_msgs,
+                             uint8_t* d_status, rt_stream_t s, const IssuerSet* S = nullptr) {
+        VerifyG1Args a{c->view, d_sigs + first * SIG, d_scalars + first * n_msgs * 32, n_msgs,
+                       (uint32_t*)c->s_pair.p + first * 6 * C::Fp::N, (uint32_t*)c->s_flags.p + first, d_status + first};
         if (n <= c->split_max) {
             TRY(c->s_g1v.reserve(n * 3 * C::Fp::N * 4));
             TRY(c->s_g1f.reserve(n * 3 * C::Fp::N * 4));
@@ -246,18 +247,89 @@ struct Impl {
             a.part_v = (uint32_t*)c->s_g1v.p; a.part_f = (uint32_t*)c->s_g1f.p; a.part_st = (uint8_t*)c->s_g1st.p;
         }
         if (S) {
-            a.item_issuer = (const uint32_t*)S->item_issuer.p;
+            a.item_issuer = (const uint32_t*)S->item_issuer.p + first;
             a.iss = IssuerSetView{(const uint32_t*)S->K.p, (const uint32_t*)S->flags.p, (const uint32_t*)S->lines.p,
                                   S->line_stride, (uint32_t)S->n_issuers, (const uint32_t*)S->domains.p};
         }
-        PROF(c, 1, s);
         TRY((launch_verify_g1<C>(a, (uint32_t)n, s)));
         c->launches += n ? (a.part_v ? 2 : 1) : 0;
+        return BBS_OK;
+    }
+    static int core_verify_dev(Ctx* c, size_t n, const uint8_t* d_sigs, const uint8_t* d_scalars, uint32_t n_msgs,
+                               uint8_t* d_status, rt_stream_t s, const IssuerSet* S = nullptr) {
+        TRY(c->s_pair.reserve(n * 6 * C::Fp::N * 4));
+        TRY(c->s_flags.reserve(n * 4));
+        PROF(c, 1, s);
+        TRY(verify_g1_dev(c, n, 0, d_sigs, d_scalars, n_msgs, d_status, s, S));
         PROF(c, 2, s);
         TRY(pairing_dev(c, n, d_status, s, S));
         PROF(c, 3, s);
         return BBS_OK;
     }
+#ifndef BBS_HOSTSIM
+    // Host buffers of a LARGE verify batch (>= 2 * VERIFY_CHUNK items) in up to 8 chunks of doubling size: all uploads are
+    // queued on the copy stream with one event per chunk; the compute stream hashes (byte messages) and runs the G1 half of
+    // chunk k while chunk k + 1 is in flight; ONE pairing launch over the whole batch follows (it is 3/4 of the work and
+    // loses nothing to chunking that way).  Statuses are those of the one-shot path: the items are independent.
+    static constexpr size_t VERIFY_CHUNK = 131072;
+    static int verify_chunked(Ctx* c, size_t n, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off, const uint8_t* scalars,
+                              uint32_t n_msgs, uint8_t* status) {
+        rt_stream_t s = c->stream;
+        const size_t count = n * n_msgs;
+        size_t bounds[9];
+        int n_chunks = 0;
+        size_t largest = 0;
+        bounds[0] = 0;
+        for (size_t at = 0, cur = VERIFY_CHUNK; at < n; cur *= 2) {
+            size_t take = std::min(n - at, cur);
+            if (n - at - take < VERIFY_CHUNK || n_chunks == 7) take = n - at;
+            largest = std::max(largest, take);
+            at += take;
+            bounds[++n_chunks] = at;
+        }
+        TRY(c->s_sigs.reserve(n * SIG));
+        TRY(c->s_scalars.reserve(count * 32));
+        if (msgs) {
+            TRY(c->s_msgs.reserve(off[count]));
+            TRY(c->s_offsets.reserve((count + 1) * 8));
+        }
+        TRY(c->s_status.reserve(n));
+        TRY(c->s_pair.reserve(n * 6 * C::Fp::N * 4));
+        TRY(c->s_flags.reserve(n * 4));
+        if (largest <= c->split_max) {                   // no reallocation between the chunk launches
+            TRY(c->s_g1v.reserve(largest * 3 * C::Fp::N * 4));
+            TRY(c->s_g1f.reserve(largest * 3 * C::Fp::N * 4));
+            TRY(c->s_g1st.reserve(2 * largest));
+        }
+        if (!c->copy_stream) RT_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        if (!c->copy_done[0]) for (auto& e : c->copy_done) RT_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        RT_CHECK(cudaEventRecord(c->copy_done[7], s));
+        RT_CHECK(cudaStreamWaitEvent(c->copy_stream, c->copy_done[7], 0));
+        for (int k = 0; k < n_chunks; k++) {
+            const size_t i0 = bounds[k], i1 = bounds[k + 1], m0 = i0 * n_msgs, m1 = i1 * n_msgs;
+            TRY(rt_h2d((uint8_t*)c->s_sigs.p + i0 * SIG, sigs + i0 * SIG, (i1 - i0) * SIG, c->copy_stream));
+            if (msgs) {
+                TRY(rt_h2d((uint8_t*)c->s_msgs.p + off[m0], msgs + off[m0], off[m1] - off[m0], c->copy_stream));
+                TRY(rt_h2d((uint64_t*)c->s_offsets.p + m0, off + m0, (m1 - m0 + 1) * 8, c->copy_stream));
+            } else {
+                TRY(rt_h2d((uint8_t*)c->s_scalars.p + m0 * 32, scalars + m0 * 32, (m1 - m0) * 32, c->copy_stream));
+            }
+            RT_CHECK(cudaEventRecord(c->copy_done[k], c->copy_stream));
+        }
+        int rc = BBS_OK;
+        for (int k = 0; k < n_chunks && !rc; k++) {
+            const size_t i0 = bounds[k], i1 = bounds[k + 1], m0 = i0 * n_msgs, m1 = i1 * n_msgs;
+            RT_CHECK(cudaStreamWaitEvent(s, c->copy_done[k], 0));
+            if (msgs) rc = h2s_dev(c, m1 - m0, (const uint8_t*)c->s_msgs.p, (const uint64_t*)c->s_offsets.p + m0,
+                                   (uint8_t*)c->s_scalars.p + m0 * 32, s);
+            if (!rc) rc = verify_g1_dev(c, i1 - i0, i0, (const uint8_t*)c->s_sigs.p, (const uint8_t*)c->s_scalars.p, n_msgs,
+                                        (uint8_t*)c->s_status.p, s);
+        }
+        if (!rc) rc = pairing_dev(c, n, (uint8_t*)c->s_status.p, s);
+        if (rc) { cudaStreamSynchronize(c->copy_stream); rt_sync(s); return rc; }
+        return finish_status(c, n, status);
+    }
+#endif
 
     // ---- issuer sets ------------------------------------------------------------------------------------
     // per-issuer state for n keys on top of an existing base context: decode + subgroup test, domain and K, the ate walk
@@ -669,6 +741,9 @@ struct Impl {
         return rt_sync(s);
     }
     static int core_verify(Ctx* c, size_t n, const uint8_t* sigs, const uint8_t* scalars, uint32_t n_msgs, uint8_t* status) {
+#ifndef BBS_HOSTSIM
+        if (n >= 2 * VERIFY_CHUNK) return verify_chunked(c, n, sigs, nullptr, nullptr, scalars, n_msgs, status);
+#endif
         rt_stream_t s = c->stream;
         TRY(stage(c->s_sigs, sigs, n * SIG, s));
         TRY(stage(c->s_scalars, scalars, n * n_msgs * 32, s));
@@ -679,6 +754,9 @@ struct Impl {
     }
     static int verify(Ctx* c, size_t n, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off, uint32_t n_msgs,
                       uint8_t* status) {
+#ifndef BBS_HOSTSIM
+        if (n >= 2 * VERIFY_CHUNK) return verify_chunked(c, n, sigs, msgs, off, nullptr, n_msgs, status);
+#endif
         rt_stream_t s = c->stream;
         const size_t count = n * n_msgs;
         TRY(stage(c->s_sigs, sigs, n * SIG, s));

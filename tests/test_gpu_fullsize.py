@@ -201,3 +201,34 @@ def test_chunked_host_signing_equals_one_shot(lib):
     assert np.array_equal(sig2[: h * bench.SIG_BYTES], sig3) and np.array_equal(st2[:h], st3)
     assert sorted(np.nonzero(st2 != 1)[0].tolist()) == sorted(bad.tolist()) and set(st2[bad].tolist()) == {A.ST_ERR_MALFORMED}
     ctx.close()
+
+
+def test_chunked_host_verify_equals_device_path(lib):
+    """bbs_verify_batch / bbs_core_verify_batch with >= 262,144 items upload in chunks under the G1 half (capi.cu
+    verify_chunked) and run ONE pairing launch: the status vector must equal the construction and the device-buffer entry
+    point's (never chunked), with a ragged number of items"""
+    import ctypes as C
+    import torch
+    import bench
+    from bbs_sign_b200 import api as A
+    L = 3
+    n = 262144 + 131072 + 555
+    ctx = A.BatchContext(A.BLS12_381, bench.IRTF_PK, header=b"", n_messages=L)
+    msgs, offs, sigs, expect = bench.make_workload(ctx, lib, n, L, seed=17)
+    st = np.full(n, 255, dtype=np.uint8)
+    assert lib.bbs_verify_batch(ctx.handle, n, bench.ptr(sigs), bench.ptr(msgs), bench.ptr(offs), L, bench.ptr(st)) == 0
+    assert np.array_equal(st, expect) and 0 < int((expect == 0).sum()) < n
+    dev = torch.device("cuda", 0)
+    d = [torch.from_numpy(a).to(dev) for a in (sigs, msgs, offs.view(np.int64))]
+    d_st = torch.zeros(n, dtype=torch.uint8, device=dev)
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert lib.bbs_verify_batch_dev(ctx.handle, n, bench.ptr(d[0]), bench.ptr(d[1]), bench.ptr(d[2]), L, bench.ptr(d_st), sp) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(d_st.cpu().numpy(), st)
+    # scalar-level entry point on the same batch
+    sc = np.zeros(n * L * 32, dtype=np.uint8)
+    assert lib.bbs_msg_to_scalars(ctx.handle, n * L, bench.ptr(msgs), bench.ptr(offs), bench.ptr(sc)) == 0
+    st2 = np.full(n, 255, dtype=np.uint8)
+    assert lib.bbs_core_verify_batch(ctx.handle, n, bench.ptr(sigs), bench.ptr(sc), L, bench.ptr(st2)) == 0
+    assert np.array_equal(st2, expect)
+    ctx.close()
