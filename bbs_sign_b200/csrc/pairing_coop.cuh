@@ -147,8 +147,13 @@ template <> struct Coop<Bn> {
     static __device__ __forceinline__ void subn(uint32_t* d, const uint32_t* s) { coop_subn8(d, s); }
     static __device__ __forceinline__ void add_p(uint32_t* d) { coop_add_p_bn(d); }
     static __device__ __forceinline__ void redc(uint32_t* r, uint32_t* t) { coop_redc_wide_bn(r, t); }
-    static constexpr int KPW = 17;             // KP[k] = multiples of p^2, full accumulator width
-    static __device__ __forceinline__ void add_kp(uint32_t* acc, const uint32_t* k) { coop_acc_add_f8(acc, k); }
+    static constexpr int KPW = 9;              // KP[k] = k p R (k <= 97: nine words of k p), added to acc[8..16]
+    static __device__ __forceinline__ void add_kp(uint32_t* acc, const uint32_t* k) {
+        asm("add.cc.u32 %0, %0, %9; addc.cc.u32 %1, %1, %10; addc.cc.u32 %2, %2, %11; addc.cc.u32 %3, %3, %12; addc.cc.u32 %4, %4, %13; "
+            "addc.cc.u32 %5, %5, %14; addc.cc.u32 %6, %6, %15; addc.cc.u32 %7, %7, %16; addc.u32 %8, %8, %17;"
+            : "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11]), "+r"(acc[12]), "+r"(acc[13]), "+r"(acc[14]), "+r"(acc[15]), "+r"(acc[16])
+            : "r"(k[0]), "r"(k[1]), "r"(k[2]), "r"(k[3]), "r"(k[4]), "r"(k[5]), "r"(k[6]), "r"(k[7]), "r"(k[8]));
+    }
     template <int K> static __device__ __forceinline__ uint32_t sub_kp(uint32_t* d, const uint32_t* r) {
         if (K == 64) return coop_sub_64p_bn9(d, r);
         if (K == 32) return coop_sub_32p_bn9(d, r);

@@ -39,7 +39,7 @@ CANON_STEPS = (1, 2, 3, 4)       # canon level l: output < 2^(l+1) p; level 0: o
                                  # (BLS12-381: quotient estimate + table of q p; the step ladder 2^l p ... p remains as fallback)
 # BN254: xi = 9 + u is applied to the ACCUMULATORS (instruction XI: (R, I) <- (9R - I, 9I + R)), so sums reach a few
 # hundred p^2; the reduction there returns N+1 limbs (< 128 p) and canonicalises in up to 7 steps
-KP_MULT_WIDE = (0, 8, 16, 32, 64, 128, 256, 512)
+KP_HI_WIDE = (0, 2, 4, 7, 13, 25, 49, 97)       # BN254 (R / p = 5.29): KP[k] = KP_HI_WIDE[k] * p * R >= (0, 8, ..., 512) p^2
 CANON_STEPS_WIDE = (1, 2, 3, 4, 5, 6, 7)
 
 
@@ -105,7 +105,7 @@ class Curve:
     @property
     def kp_mult(self):
         """KP table in units of p^2"""
-        return KP_MULT_WIDE if self.wide else tuple(Fraction(k * self.R, self.p) for k in KP_HI)
+        return tuple(Fraction(k * self.R, self.p) for k in (KP_HI_WIDE if self.wide else KP_HI))
 
     @property
     def canon_steps(self):
